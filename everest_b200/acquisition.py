@@ -1,0 +1,213 @@
+"""Acquisition functions with the constructor / forward contract BoFire relies on.
+
+Reference call sites (arguments mirrored here):
+  * qNoisyExpectedHypervolumeImprovement(model, ref_point, X_baseline, prune_baseline, objective,
+    cache_root, X_pending, constraints, eta, alpha)          strategies/predictives/qnehvi.py:39-52, mobo.py:72-90
+  * qExpectedHypervolumeImprovement(model, ref_point, partitioning, objective, X_pending)   qehvi.py:67-76
+  * get_acquisition_function("qLogEI", model, objective, X_observed, ..., mc_samples)       sobo.py:64-89
+forward(X[b, q, d]) -> [b] is the L1 boundary of SURVEY.md 8b (called from calc_acquisition
+botorch.py:223, optimize_acqf's raw-sample screen and optimize_acqf_discrete botorch.py:461).
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import sampling
+from .model import DeviceGPState, _dev_ptr, _stream
+from .objectives import MultiObjective, ObjectiveSpec, OutputConstraint, ScalarObjective, c_array
+
+
+class _DeviceAcquisition:
+    """Shared forward plumbing: X -> device, base samples of the q new points, bo_acqf_forward."""
+
+    def __init__(self, model: DeviceGPState, mc_samples: int, seed: Optional[int]):
+        if not model.factorized:
+            model.factorize()
+        self.model = model
+        self.S = int(mc_samples)
+        # BoTorch draws the sampler seed from torch's global RNG (seeded by BotorchStrategy, botorch.py:86)
+        self.seed = int(torch.randint(0, 1000000, (1,)).item()) if seed is None else int(seed)
+        self._zq = {}
+        self.nb = 0
+        self.last_info = None
+
+    def base_samples_q(self, q: int) -> torch.Tensor:
+        """[S, q, M] base samples of the new points: the last q points of a fresh (n_b + q)-point Sobol
+        draw with the sampler's seed ([UPSTREAM] NormalMCSampler._update_base_samples)."""
+        if q not in self._zq:
+            z = sampling.base_samples(self.nb + q, self.model.M, self.S, self.seed)
+            self._zq[q] = z[:, self.nb:, :].contiguous().to(self.model.device)
+        return self._zq[q]
+
+    def set_base_samples_q(self, q: int, zq):
+        zq = torch.as_tensor(zq, dtype=torch.double)
+        if tuple(zq.shape) != (self.S, q, self.model.M):
+            raise ValueError(f"zq must be [{self.S}, {q}, {self.model.M}]")
+        self._zq[q] = zq.to(self.model.device).contiguous()
+
+    def forward(self, X) -> torch.Tensor:
+        X = torch.as_tensor(X, dtype=torch.double)
+        if X.dim() == 2:
+            X = X.unsqueeze(0)
+        if X.dim() != 3 or X.shape[-1] != self.model.d:
+            raise ValueError(f"X must be [b, q, {self.model.d}]")
+        on_cpu = X.device.type == "cpu"
+        Xd = X.to(self.model.device).contiguous()
+        b, q, _ = Xd.shape
+        out = torch.empty(b, dtype=torch.double, device=self.model.device)
+        info = torch.zeros(b, dtype=torch.int32, device=self.model.device)
+        zq = self.base_samples_q(q)
+        with torch.cuda.device(self.model.device):
+            L.check(self.model.lib.bo_acqf_forward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
+                                                   _dev_ptr(info), _stream()))
+        self.last_info = info
+        return out.cpu() if on_cpu else out
+
+    __call__ = forward
+
+    def forward_host(self, X: np.ndarray) -> np.ndarray:
+        """Same call with HOST buffers through bo_acqf_forward_host (pinned staging + H2D + D2H inside)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim == 2:
+            X = X[None]
+        b, q, d = X.shape
+        if d != self.model.d:
+            raise ValueError(f"X must be [b, q, {self.model.d}]")
+        out = np.empty(b, dtype=np.float64)
+        zq = self.base_samples_q(q)
+        with torch.cuda.device(self.model.device):
+            L.check(self.model.lib.bo_acqf_forward_host(self.model.handle, X.ctypes.data_as(C.c_void_p), b, q,
+                                                        _dev_ptr(zq), out.ctypes.data_as(C.c_void_p), _stream()))
+        return out
+
+
+class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
+    def __init__(self, model: DeviceGPState, ref_point: Sequence[float], X_baseline, objective: MultiObjective,
+                 constraints: Optional[List[OutputConstraint]] = None, eta=None, prune_baseline: bool = False,
+                 alpha: float = 0.0, cache_root: bool = True, X_pending=None, mc_samples: int = 512,
+                 seed: Optional[int] = None, prune_samples: int = 2048, base_samples_baseline=None):
+        super().__init__(model, mc_samples, seed)
+        if alpha != 0.0:
+            raise NotImplementedError("approximate partitioning (alpha > 0) is not part of the accelerated path")
+        if not cache_root:
+            raise NotImplementedError("cache_root=False (joint re-sampling of the baseline) is not accelerated")
+        self.ref_point = [float(v) for v in ref_point]
+        self.objective = objective
+        if len(self.ref_point) != len(objective.ops):
+            raise ValueError("ref_point and objective must have the same number of outcomes")
+        self.constraints = list(constraints) if constraints else []
+        if eta is not None and self.constraints:
+            etas = [float(eta)] * len(self.constraints) if np.ndim(eta) == 0 else [float(e) for e in eta]
+            self.constraints = [OutputConstraint(c.idx, c.sign, c.tp, e) for c, e in zip(self.constraints, etas)]
+        self._obj_c, self._n_obj = c_array(list(objective.ops), L.ObjectiveOp)
+        self._con_c, self._n_con = c_array(self.constraints, L.ConstraintOp)
+        self._ref_c = (C.c_double * len(self.ref_point))(*self.ref_point)
+
+        Xb = torch.as_tensor(X_baseline, dtype=torch.double)
+        if Xb.dim() != 2:
+            raise ValueError("X_baseline must be [n, d]")
+        self.prune_idx = None
+        if prune_baseline and Xb.shape[0] > 0:
+            self.prune_idx = self._prune(Xb, prune_samples)
+            Xb = Xb[self.prune_idx.cpu()]
+        if X_pending is not None:
+            Xb = torch.cat([Xb, torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d)], dim=0)
+        self.X_baseline = Xb
+        self.nb = Xb.shape[0]
+        zb = base_samples_baseline
+        if zb is None:
+            zb = sampling.base_samples(self.nb, model.M, self.S, self.seed)
+        zb = torch.as_tensor(zb, dtype=torch.double).to(model.device).contiguous()
+        if tuple(zb.shape) != (self.S, self.nb, model.M):
+            raise ValueError(f"base_samples_baseline must be [{self.S}, {self.nb}, {model.M}]")
+        self._zb = zb
+        Xbd = Xb.to(model.device).contiguous()
+        info = (C.c_int32 * model.M)()
+        maxc = C.c_int32(0)
+        with torch.cuda.device(model.device):
+            L.check(model.lib.bo_nehvi_prepare(model.handle, _dev_ptr(Xbd), self.nb, _dev_ptr(zb), self.S, self._obj_c,
+                                               self._n_obj, self._con_c, self._n_con, self._ref_c, info, C.byref(maxc),
+                                               _stream()))
+        self.max_cells = int(maxc.value)
+
+    def _prune(self, Xb, prune_samples, seed_offset=7919):
+        """[UPSTREAM] prune_inferior_points_multi_objective: keep points with non-zero probability of being
+        non-dominated and better than the reference point under `prune_samples` joint posterior samples."""
+        model = self.model
+        n = Xb.shape[0]
+        z = sampling.base_samples(n, model.M, prune_samples, self.seed + seed_offset).to(model.device).contiguous()
+        self._z_prune = z
+        counts = torch.zeros(n, dtype=torch.int32, device=model.device)
+        info = (C.c_int32 * model.M)()
+        Xd = Xb.to(model.device).contiguous()
+        with torch.cuda.device(model.device):
+            L.check(model.lib.bo_prune_counts(model.handle, _dev_ptr(Xd), n, _dev_ptr(z), prune_samples, self._obj_c,
+                                              self._n_obj, self._con_c, self._n_con, self._ref_c, _dev_ptr(counts), info,
+                                              _stream()))
+        self.prune_counts = counts
+        return torch.nonzero(counts > 0).view(-1)
+
+    # introspection used by the parity tests
+    def cell_bounds(self):
+        """(lower, upper) as [S, C, m] CPU tensors and the per-sample cell counts."""
+        m = len(self.ref_point)
+        st = self.model
+        nc = st.debug_get("ncells", dtype=torch.int32).cpu()
+        cap_guess = 64 * max(64, 8 * (self.nb + 1) * m) * m * self.S
+        lo = st.debug_get("cell_lo", capacity=cap_guess)
+        up = st.debug_get("cell_up", capacity=cap_guess)
+        cap = lo.numel() // (m * self.S)
+        lo = lo.view(cap, m, self.S).permute(2, 0, 1).cpu()
+        up = up.view(cap, m, self.S).permute(2, 0, 1).cpu()
+        return lo, up, nc
+
+
+class qExpectedHypervolumeImprovement(_DeviceAcquisition):
+    """Fixed partitioning of the observed front (qehvi.py:37-77). `partitioning_Y` are the objective values
+    (maximisation frame, already multiplied by the ref-point mask) BoFire hands to NondominatedPartitioning."""
+
+    def __init__(self, model: DeviceGPState, ref_point, partitioning_Y, objective: MultiObjective, mc_samples: int = 512,
+                 seed: Optional[int] = None, X_pending=None):
+        super().__init__(model, mc_samples, seed)
+        if X_pending is not None:
+            raise NotImplementedError("X_pending with qEHVI is not accelerated; use qNEHVI")
+        self.ref_point = [float(v) for v in ref_point]
+        self.objective = objective
+        Y = torch.as_tensor(partitioning_Y, dtype=torch.double).reshape(-1, len(self.ref_point)).to(model.device).contiguous()
+        self._obj_c, self._n_obj = c_array(list(objective.ops), L.ObjectiveOp)
+        self._ref_c = (C.c_double * len(self.ref_point))(*self.ref_point)
+        maxc = C.c_int32(0)
+        with torch.cuda.device(model.device):
+            L.check(model.lib.bo_ehvi_prepare(model.handle, _dev_ptr(Y), Y.shape[0], self.S, self._obj_c, self._n_obj,
+                                              self._ref_c, C.byref(maxc), _stream()))
+        self.max_cells = int(maxc.value)
+
+
+class qLogExpectedImprovement(_DeviceAcquisition):
+    def __init__(self, model: DeviceGPState, best_f: float, objective: ScalarObjective, mc_samples: int = 512,
+                 seed: Optional[int] = None, constraints=None, X_pending=None):
+        super().__init__(model, mc_samples, seed)
+        if constraints:
+            raise NotImplementedError("output constraints with qLogEI are not accelerated yet")
+        if X_pending is not None:
+            raise NotImplementedError("X_pending with qLogEI is not accelerated yet")
+        self.best_f = float(best_f)
+        self.objective = objective
+        self._obj_c, self._n_obj = c_array(list(objective.ops), L.ObjectiveOp)
+        with torch.cuda.device(model.device):
+            L.check(model.lib.bo_logei_prepare(model.handle, self.S, objective.combine_code, self._obj_c, self._n_obj,
+                                               self.best_f, _stream()))
+
+
+def get_acquisition_function(acquisition_function_name: str, model: DeviceGPState, objective, X_observed,
+                             X_pending=None, constraints=None, mc_samples: int = 512, seed=None, **kwargs):
+    """Mirror of botorch.acquisition.factory.get_acquisition_function for the accelerated names."""
+    if acquisition_function_name == "qLogEI":
+        mean, _ = model.posterior(X_observed)
+        best_f = float(objective(mean.cpu()).max())
+        return qLogExpectedImprovement(model, best_f, objective, mc_samples=mc_samples, seed=seed,
+                                       constraints=constraints, X_pending=X_pending)
+    raise NotImplementedError(f"Unknown / non-accelerated acquisition function {acquisition_function_name}")

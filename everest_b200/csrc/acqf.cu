@@ -1,0 +1,785 @@
+// K3 (small batched Cholesky / triangular solve), K4/K5 (MC reparameterisation + objective and
+// constraint transforms), K6 (qNEHVI / qEHVI inclusion-exclusion), K7 (non-dominated front + box
+// decomposition), K8 (qLogEI).
+//
+// Reference call sites: qNoisyExpectedHypervolumeImprovement built at
+// strategies/predictives/qnehvi.py:39-52 and mobo.py:72-90, qExpectedHypervolumeImprovement at
+// qehvi.py:67-76, qLogEI via get_acquisition_function at sobo.py:64-89; the arithmetic is BoTorch's
+// (sample_cached_cholesky, _compute_qehvi, FastNondominatedPartitioning, log_fatplus/fatmax), restated
+// in oracle/bo_oracle.py.  Objective / constraint formulas: utils/torch_tools.py:258-337,384-450.
+#include "common.cuh"
+#include "acqf.cuh"
+
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------------
+// z[S, n, M] -> zT[(e*M + m)*S + s]   and   zM[m][s][ldn] (row-major per output, zero padded)
+__global__ void transpose_base_samples_kernel(const double* __restrict__ z, int S, int n, int M, double* __restrict__ zT,
+                                              double* __restrict__ zM, int ldn) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)S * n * M;
+  if (idx >= total) return;
+  int m = (int)(idx % M);
+  long long r = idx / M;
+  int e = (int)(r % n);
+  int s = (int)(r / n);
+  double v = z[idx];
+  if (zT) zT[((size_t)e * M + m) * S + s] = v;
+  if (zM) zM[((size_t)m * S + s) * ldn + e] = v;
+}
+
+int launch_transpose_base_samples(const double* z, int S, int n, int M, double* zT, double* zM, int ldn, cudaStream_t st,
+                                  LaunchCounter* lc) {
+  long long total = (long long)S * n * M;
+  if (total <= 0) return BO_OK;
+  transpose_base_samples_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, S, n, M, zT, zM, ldn);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+__global__ void scale_matrix_kernel(double* __restrict__ A, int ld, int rows, int cols, double s) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (r < rows && c < cols) A[(size_t)r * ld + c] *= s;
+}
+int launch_scale_matrix(double* A, int ld, int rows, int cols, double s, cudaStream_t st, LaunchCounter* lc) {
+  if (rows <= 0 || cols <= 0) return BO_OK;
+  dim3 grid((cols + 255) / 256, rows);
+  scale_matrix_kernel<<<grid, 256, 0, st>>>(A, ld, rows, cols, s);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+__global__ void add_diag_kernel(double* __restrict__ A, int ld, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[(size_t)i * ld + i] += v;
+}
+int launch_add_diag(double* A, int ld, int n, double v, cudaStream_t st, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, ld, n, v);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// dst[r*ldd + c] = scale * src[r*lds + c]
+__global__ void copy_scale_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows,
+                                  int cols, double scale) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (r < rows && c < cols) dst[(size_t)r * ldd + c] = scale * src[(size_t)r * lds + c];
+}
+int launch_copy_scale(const double* src, int lds, double* dst, int ldd, int rows, int cols, double scale, cudaStream_t st,
+                      LaunchCounter* lc) {
+  if (rows <= 0 || cols <= 0) return BO_OK;
+  dim3 grid((cols + 255) / 256, rows);
+  copy_scale_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols, scale);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// out[i*ldo + m] = (mean_const + raw[i]) * y_std + y_mean
+__global__ void finish_mean_kernel(const double* __restrict__ raw, int n, double mean_const, double y_std, double y_mean,
+                                   double* __restrict__ out, int ldo, int m) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[(size_t)i * ldo + m] = (mean_const + raw[i]) * y_std + y_mean;
+}
+int launch_finish_mean(const double* raw, int n, double mean_const, double y_std, double y_mean, double* out, int ldo,
+                       int m, cudaStream_t st, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  finish_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(raw, n, mean_const, y_std, y_mean, out, ldo, m);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// var[i*ldo + m] = (k(x_i,x_i) - g[i] (+ noise)) * y_std^2
+__global__ void finish_var_kernel(ModelD md, PrepD prep, const double* __restrict__ g, int n, int add_noise,
+                                  double* __restrict__ out, int ldo, int m) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double kii = model_eval_pair(md, prep, i, prep, i, true);
+  double v = kii - g[i];
+  if (add_noise) v += md.noise;
+  out[(size_t)i * ldo + m] = v * md.y_std * md.y_std;
+}
+int launch_finish_var(const ModelD& md, PrepD prep, const double* g, int n, int add_noise, double* out, int ldo, int m,
+                      cudaStream_t st, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  finish_var_kernel<<<(n + 127) / 128, 128, 0, st>>>(md, prep, g, n, add_noise, out, ldo, m);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cond_root: one warp per (q-batch, output).  Sqq, Sqb -> bl = Sqb L_b^-T (forward substitution with
+// warp-shuffle dot products), br = psd_safe_chol(Sqq - bl bl^T) with the 1e-8..1e-3 jitter ladder,
+// un-standardised mean.  root[(batch*M + m)][q][nb + q] = [bl | br].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cond_root_kernel(CondRootArgs a) {
+  extern __shared__ double csm[];
+  const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int batch = blockIdx.x * 4 + warp_in_cta;
+  if (batch >= a.b) return;
+  const int q = a.q, nb = a.nb, nr = nb + q;
+  const ModelD& md = a.md;
+  double* Sqb = csm + (size_t)warp_in_cta * (q * nr + 2 * q * q);  // [q][nb] -> becomes bl in place
+  double* Sc = Sqb + q * nb;                                        // [q][q]
+  double* Lq = Sc + q * q;                                          // [q][q]
+  const double s2 = md.y_std * md.y_std;
+  const int row0 = batch * q;
+
+  for (int j = 0; j < q; ++j)
+    for (int e = lane; e < nb; e += 32) {
+      double kqb = model_eval_pair(md, a.prep_q, row0 + j, a.prep_b, e, false);
+      Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
+    }
+  for (int p = lane; p < q * q; p += 32) {
+    int i = p / q, j = p % q;
+    if (j >= i) {
+      double kqq = model_eval_pair(md, a.prep_q, row0 + i, a.prep_q, row0 + j, i == j);
+      double v = (kqq - a.Gqq[((size_t)batch * q + i) * q + j]) * s2;
+      Sc[i * q + j] = v;
+      Sc[j * q + i] = v;
+    }
+  }
+  __syncwarp();
+  // forward substitution: bl[j][e] = (Sqb[j][e] - sum_{l<e} bl[j][l] Lb[e][l]) / Lb[e][e]
+  for (int e = 0; e < nb; ++e) {
+    const double* Lrow = a.Lb + (size_t)e * a.ldlb;
+    const double diag = Lrow[e];
+    for (int j = 0; j < q; ++j) {
+      double s = 0.0;
+      for (int l = lane; l < e; l += 32) s = fma(Sqb[j * nb + l], Lrow[l], s);
+      s = warp_sum(s);
+      if (lane == 0) Sqb[j * nb + e] = (Sqb[j * nb + e] - s) / diag;
+    }
+    __syncwarp();
+  }
+  // Sc -= bl bl^T
+  for (int p = 0; p < q * q; ++p) {
+    int i = p / q, j = p % q;
+    if (j < i) continue;
+    double s = 0.0;
+    for (int e = lane; e < nb; e += 32) s = fma(Sqb[i * nb + e], Sqb[j * nb + e], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      Sc[i * q + j] -= s;
+      if (i != j) Sc[j * q + i] -= s;
+    }
+  }
+  __syncwarp();
+  // psd_safe_cholesky on q x q (lane 0), jitter ladder 1e-8 * 10^i, i = 0..5, added incrementally
+  int fail = 0;
+  double jitter_total = 0.0;
+  if (lane == 0) {
+    double prev = 0.0;
+    for (int attempt = 0; attempt <= 6; ++attempt) {
+      if (attempt > 0) {
+        const double ladder[6] = {1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0};
+        double nw = 1e-8 * ladder[attempt - 1];
+        for (int i = 0; i < q; ++i) Sc[i * q + i] += (nw - prev);
+        jitter_total += (nw - prev);
+        prev = nw;
+      }
+      fail = 0;
+      for (int j = 0; j < q && !fail; ++j) {
+        double d = Sc[j * q + j];
+        for (int l = 0; l < j; ++l) d -= Lq[j * q + l] * Lq[j * q + l];
+        if (!(d > 0.0)) { fail = 1; break; }
+        d = sqrt(d);
+        Lq[j * q + j] = d;
+        for (int i = j + 1; i < q; ++i) {
+          double s = Sc[i * q + j];
+          for (int l = 0; l < j; ++l) s -= Lq[i * q + l] * Lq[j * q + l];
+          Lq[i * q + j] = s / d;
+        }
+        for (int i = 0; i < j; ++i) Lq[i * q + j] = 0.0;
+      }
+      if (!fail) break;
+    }
+    if (fail) {
+      const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+      for (int p = 0; p < q * q; ++p) Lq[p] = nanv;
+    }
+    if (a.info) a.info[(size_t)batch * a.M + a.m] = fail;
+    if (a.jitter) a.jitter[(size_t)batch * a.M + a.m] = jitter_total;
+  }
+  __syncwarp();
+  double* root = a.root + ((size_t)batch * a.M + a.m) * q * nr;
+  for (int idx = lane; idx < q * nr; idx += 32) {
+    int j = idx / nr, c = idx % nr;
+    root[idx] = (c < nb) ? Sqb[j * nb + c] : Lq[j * q + (c - nb)];
+  }
+  for (int j = lane; j < q; j += 32)
+    a.mu[((size_t)(row0 + j)) * a.M + a.m] = (md.mean_const + a.mu_raw[row0 + j]) * md.y_std + md.y_mean;
+}
+
+int launch_cond_root(const CondRootArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  size_t smem = (size_t)4 * (a.q * (a.nb + a.q) + 2 * a.q * a.q) * sizeof(double);
+  if (smem > 200 * 1024) { bo_set_error("cond_root: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  cond_root_kernel<<<(a.b + 3) / 4, 128, smem, st>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// objective transform of a sample matrix F[m][s][ldf] + mean -> obj[(s*n + e)*n_obj + o], feasibility
+// ------------------------------------------------------------------------------------------------
+__global__ void baseline_objective_kernel(const double* __restrict__ F, int ldf, int S, int n, int M,
+                                          const double* __restrict__ mean /*[n, M]*/, ObjD od,
+                                          double* __restrict__ obj, unsigned char* __restrict__ feas,
+                                          double* __restrict__ samples /* optional [S, n, M] */) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)S * n) return;
+  int e = (int)(idx % n), s = (int)(idx / n);
+  double y[BO_MAX_OBJECTIVES * 2];
+  for (int m = 0; m < M; ++m) {
+    y[m] = mean[(size_t)e * M + m] + F[((size_t)m * S + s) * ldf + e];
+    if (samples) samples[((size_t)s * n + e) * M + m] = y[m];
+  }
+  for (int o = 0; o < od.n_obj; ++o) obj[((size_t)s * n + e) * od.n_obj + o] = objective_apply(od.op[o], y);
+  unsigned char ok = 1;
+  for (int c = 0; c < od.n_cons; ++c) {
+    double cv = od.con[c].sign * (y[od.con[c].out_idx] - od.con[c].tp);
+    if (!(cv <= 0.0)) ok = 0;
+  }
+  feas[(size_t)s * n + e] = ok;
+}
+int launch_baseline_objective(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od,
+                              double* obj, unsigned char* feas, double* samples, cudaStream_t st, LaunchCounter* lc) {
+  long long total = (long long)S * n;
+  if (total <= 0) return BO_OK;
+  baseline_objective_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, ldf, S, n, M, mean, od, obj, feas, samples);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: per-sample non-dominated front.  One CTA per sample.  front[s][e] = 1 iff point e is feasible,
+// strictly better than ref in every objective, not dominated, and (dedup) the first of its duplicates.
+// With count_only (pruning, BoTorch deduplicate=False) duplicates are all kept and counts[e] += 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+front_kernel(const double* __restrict__ obj, const unsigned char* __restrict__ feas, int n, int Mo,
+             const double* __restrict__ ref, int dedup, unsigned char* __restrict__ front, int* __restrict__ counts,
+             int infeasible_to_ref) {
+  const int s = blockIdx.x;
+  const double* Y = obj + (size_t)s * n * Mo;
+  const unsigned char* fz = feas + (size_t)s * n;
+  double r[BO_MAX_OBJECTIVES];
+  for (int o = 0; o < Mo; ++o) r[o] = ref[o];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    double y[BO_MAX_OBJECTIVES];
+    bool valid = fz[e] != 0;
+    for (int o = 0; o < Mo; ++o) {
+      y[o] = Y[(size_t)e * Mo + o];
+      if (!(y[o] > r[o])) valid = false;
+    }
+    bool keep = valid;
+    if (valid) {
+      for (int k = 0; k < n && keep; ++k) {
+        if (k == e) continue;
+        bool kvalid = fz[k] != 0;
+        if (!kvalid && !infeasible_to_ref) continue;
+        // pruning semantics: infeasible points sit AT the ref point -> they can never dominate a valid point
+        if (!kvalid) continue;
+        bool ge = true, gt = false, eq = true;
+        for (int o = 0; o < Mo; ++o) {
+          double v = Y[(size_t)k * Mo + o];
+          ge = ge && (v >= y[o]);
+          gt = gt || (v > y[o]);
+          eq = eq && (v == y[o]);
+        }
+        if (ge && gt) keep = false;
+        if (dedup && eq && k < e) keep = false;
+      }
+    }
+    if (front) front[(size_t)s * n + e] = keep ? 1 : 0;
+    if (counts && keep) atomicAdd(&counts[e], 1);
+  }
+}
+int launch_front(const double* obj, const unsigned char* feas, int S, int n, int Mo, const double* ref_dev, int dedup,
+                 unsigned char* front, int* counts, cudaStream_t st, LaunchCounter* lc) {
+  if (S <= 0 || n <= 0) return BO_OK;
+  front_kernel<<<S, 256, 0, st>>>(obj, feas, n, Mo, ref_dev, dedup, front, counts, 1);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// 2-objective box decomposition of the non-dominated space.  Front sorted by objective 0 ascending
+// (rank by counting, ties by row); cell c: lower = (y0[c-1] | ref0, y1[c] | ref1), upper = (y0[c] | inf, inf).
+// Cells are stored sample-minor for coalesced reads: lo/up[(c*Mo + o)*S + s].
+__global__ void __launch_bounds__(256)
+partition2d_kernel(const double* __restrict__ obj, const unsigned char* __restrict__ front, int n, int S, int cap,
+                   const double* __restrict__ ref, double* __restrict__ lo, double* __restrict__ up,
+                   int* __restrict__ ncells, int* __restrict__ front_idx /* [S, cap] sorted row indices */) {
+  const int s = blockIdx.x;
+  const double* Y = obj + (size_t)s * n * 2;
+  const unsigned char* fr = front + (size_t)s * n;
+  __shared__ int count;
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  int local = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    if (!fr[e]) continue;
+    ++local;
+    double y0 = Y[e * 2], y1 = Y[e * 2 + 1];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      if (!fr[k]) continue;
+      double v = Y[k * 2];
+      if (v < y0 || (v == y0 && k < e)) ++rank;
+    }
+    if (rank + 1 < cap) {
+      lo[((size_t)(rank + 1) * 2 + 0) * S + s] = y0;
+      up[((size_t)(rank + 1) * 2 + 1) * S + s] = inf;
+    }
+    if (rank < cap) {
+      lo[((size_t)rank * 2 + 1) * S + s] = y1;
+      up[((size_t)rank * 2 + 0) * S + s] = y0;
+      if (front_idx) front_idx[(size_t)s * cap + rank] = e;
+    }
+  }
+  if (local) atomicAdd(&count, local);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int p = count;
+    ncells[s] = p + 1;
+    lo[((size_t)0 * 2 + 0) * S + s] = ref[0];
+    up[((size_t)0 * 2 + 1) * S + s] = inf;
+    if (p < cap) {
+      lo[((size_t)p * 2 + 1) * S + s] = ref[1];
+      up[((size_t)p * 2 + 0) * S + s] = inf;
+    }
+  }
+}
+int launch_partition2d(const double* obj, const unsigned char* front, int n, int S, int cap, const double* ref_dev,
+                       double* lo, double* up, int* ncells, int* front_idx, cudaStream_t st, LaunchCounter* lc) {
+  partition2d_kernel<<<S, 256, 0, st>>>(obj, front, n, S, cap, ref_dev, lo, up, ncells, front_idx);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// Block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix and the
+// block total through *total.  Keeps thread order, so compactions built on it are stable.
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* wsum /* [9] shared */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 8; ++i) { int t = wsum[i]; wsum[i] = run; run += t; }
+    wsum[8] = run;
+  }
+  __syncthreads();
+  *total = wsum[8];
+  return wsum[w] + inc - v;
+}
+
+// General (m >= 2) box decomposition of the non-dominated space via local upper bounds
+// (Lacour et al. 2017, Alg. 3 + Eq. 2), one CTA per MC sample.  Front points are inserted in row
+// order; kept bounds stay in order and new bounds are appended in (dominated-u, k) order, exactly
+// like the list operations of the CPU restatement, so the cell list is bit-identical.
+// Work buffers per sample: two ping-pong copies of U[cap][m] and Z[cap][m][m] (minimisation frame).
+__global__ void __launch_bounds__(256)
+partition_nd_kernel(const double* __restrict__ obj, const unsigned char* __restrict__ front, int n, int S, int Mo,
+                    int cap, const double* __restrict__ ref, double* __restrict__ work, double* __restrict__ lo,
+                    double* __restrict__ up, int* __restrict__ ncells, int* __restrict__ overflow) {
+  const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int mm = Mo * Mo;
+  double* base = work + (size_t)s * 2 * cap * (Mo + mm);
+  double* Ub[2] = {base, base + (size_t)cap * (Mo + mm)};
+  double* Zb[2] = {Ub[0] + (size_t)cap * Mo, Ub[1] + (size_t)cap * Mo};
+  __shared__ int wsum[9];
+  __shared__ int sh_count, sh_over;
+  const double ninf = __longlong_as_double(0xfff0000000000000LL);
+  const double pinf = __longlong_as_double(0x7ff0000000000000LL);
+  int cur = 0;
+  if (tid == 0) {
+    for (int j = 0; j < Mo; ++j) {
+      Ub[0][j] = -ref[j];
+      for (int i = 0; i < Mo; ++i) Zb[0][i * Mo + j] = (i == j) ? -ref[j] : ninf;
+    }
+    sh_count = 1;
+    sh_over = 0;
+  }
+  __syncthreads();
+  for (int e = 0; e < n; ++e) {
+    if (!front[(size_t)s * n + e]) continue;
+    double z[BO_MAX_OBJECTIVES];
+    for (int j = 0; j < Mo; ++j) z[j] = -obj[((size_t)s * n + e) * Mo + j];
+    const int count = sh_count;
+    const double* U = Ub[cur];
+    const double* Z = Zb[cur];
+    double* U2 = Ub[cur ^ 1];
+    double* Z2 = Zb[cur ^ 1];
+    // pass A: how many bounds survive
+    int kept_total = 0;
+    for (int b0 = 0; b0 < count; b0 += nt) {
+      int u = b0 + tid;
+      int keep = 0;
+      if (u < count) {
+        bool dom = true;
+        for (int j = 0; j < Mo; ++j) dom = dom && (U[(size_t)u * Mo + j] > z[j]);
+        keep = dom ? 0 : 1;
+      }
+      int tot;
+      block_excl_scan(keep, &tot, wsum);
+      kept_total += tot;
+    }
+    // pass B: stable compaction of survivors, then the children of every dominated bound
+    int kept_run = 0, new_run = 0;
+    for (int b0 = 0; b0 < count; b0 += nt) {
+      int u = b0 + tid;
+      int keep = 0, newc = 0;
+      unsigned newmask = 0;
+      if (u < count) {
+        bool dom = true;
+        for (int j = 0; j < Mo; ++j) dom = dom && (U[(size_t)u * Mo + j] > z[j]);
+        keep = dom ? 0 : 1;
+        if (dom) {
+          for (int k = 0; k < Mo; ++k) {
+            double lower = ninf;
+            for (int i = 0; i < Mo; ++i)
+              if (i != k) lower = fmax(lower, Z[(size_t)u * mm + i * Mo + k]);
+            if (z[k] >= lower) { newmask |= (1u << k); ++newc; }
+          }
+        }
+      }
+      int tk, tn;
+      int koff = block_excl_scan(keep, &tk, wsum);
+      int noff = block_excl_scan(newc, &tn, wsum);
+      if (keep) {
+        int dst = kept_run + koff;
+        if (dst < cap) {
+          for (int j = 0; j < Mo; ++j) U2[(size_t)dst * Mo + j] = U[(size_t)u * Mo + j];
+          for (int j = 0; j < mm; ++j) Z2[(size_t)dst * mm + j] = Z[(size_t)u * mm + j];
+        }
+      }
+      if (newc) {
+        int dst = kept_total + new_run + noff;
+        for (int k = 0; k < Mo; ++k) {
+          if (!(newmask & (1u << k))) continue;
+          if (dst < cap) {
+            for (int j = 0; j < Mo; ++j) U2[(size_t)dst * Mo + j] = (j == k) ? z[k] : U[(size_t)u * Mo + j];
+            for (int i = 0; i < Mo; ++i)
+              for (int j = 0; j < Mo; ++j)
+                Z2[(size_t)dst * mm + i * Mo + j] = (i == k) ? z[j] : Z[(size_t)u * mm + i * Mo + j];
+          }
+          ++dst;
+        }
+      }
+      kept_run += tk;
+      new_run += tn;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int nc = kept_total + new_run;
+      if (nc > cap) { sh_over = 1; nc = cap; }
+      sh_count = nc;
+    }
+    __syncthreads();
+    cur ^= 1;
+    if (sh_over) break;
+  }
+  if (sh_over) {
+    if (tid == 0) { atomicExch(overflow, 1); ncells[s] = 0; }
+    return;
+  }
+  // cell bounds (Eq. 2), dropping empty cells, written sample-minor in the maximisation frame
+  const int count = sh_count;
+  const double* U = Ub[cur];
+  const double* Z = Zb[cur];
+  int run = 0;
+  for (int b0 = 0; b0 < count; b0 += nt) {
+    int u = b0 + tid;
+    int ok = 0;
+    double lmin[BO_MAX_OBJECTIVES], umin[BO_MAX_OBJECTIVES];
+    if (u < count) {
+      ok = 1;
+      for (int j = 0; j < Mo; ++j) {
+        umin[j] = U[(size_t)u * Mo + j];
+        double l = ninf;
+        for (int k = 0; k < j; ++k) l = fmax(l, Z[(size_t)u * mm + k * Mo + j]);
+        lmin[j] = l;
+        if (umin[j] <= lmin[j]) ok = 0;
+      }
+    }
+    int tot;
+    int off = block_excl_scan(ok, &tot, wsum);
+    if (ok) {
+      int c = run + off;
+      for (int j = 0; j < Mo; ++j) {
+        lo[((size_t)c * Mo + j) * S + s] = -umin[j];
+        up[((size_t)c * Mo + j) * S + s] = (lmin[j] == ninf) ? pinf : -lmin[j];
+      }
+    }
+    run += tot;
+  }
+  if (tid == 0) ncells[s] = run;
+}
+int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
+                        const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
+                        cudaStream_t st, LaunchCounter* lc) {
+  partition_nd_kernel<<<S, 256, 0, st>>>(obj, front, n, S, Mo, cap, ref_dev, work, lo, up, ncells, overflow);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4/K5/K6: one CTA per q-batch, threads over MC samples.
+// f = mu + bl z_b + br z_q  ->  objective / feasibility  ->  inclusion-exclusion HVI over the sample's
+// own cells, restricted to the points that overlap the cell (subsets containing a zero-length point
+// contribute exactly 0, so skipping them leaves the sum unchanged).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256)
+mc_hvi_kernel(McArgs a) {
+  extern __shared__ double msm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  double* root = msm;                   // [M][q][nr]
+  double* mu = root + M * q * nr;       // [q][M]
+  double* objs = mu + q * M;            // [q*Mo][nt]
+  double* fw = objs + (size_t)q * Mo * nt;  // [q][nt] feasibility weights
+  double* red = fw + (size_t)q * nt;    // [32]
+  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+
+  double total = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) {
+        const double* rr = root + ((size_t)m * q + j) * nr;
+        double sb = 0.0, sq = 0.0;
+        for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+        for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+        y[m] = (mu[j * M + m] + sb) + sq;
+      }
+      for (int o = 0; o < Mo; ++o) objs[((size_t)j * Mo + o) * nt + tid] = objective_apply(a.od.op[o], y);
+      double w = 1.0;
+      for (int c = 0; c < a.od.n_cons; ++c) {
+        double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+        w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));  // sigmoid(-c / eta)
+      }
+      fw[(size_t)j * nt + tid] = w;
+    }
+    const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+    const int sc = a.cells_shared ? 0 : s;
+    const int Sc = a.cells_shared ? 1 : S;
+    double acc = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double lo[BO_MAX_OBJECTIVES], up[BO_MAX_OBJECTIVES];
+      for (int o = 0; o < Mo; ++o) {
+        lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+        up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
+      }
+      unsigned active = 0;
+      for (int j = 0; j < q; ++j) {
+        bool pos = true;
+        for (int o = 0; o < Mo; ++o) {
+          double len = fmin(objs[((size_t)j * Mo + o) * nt + tid], up[o]) - lo[o];
+          pos = pos && (len > 0.0);
+        }
+        if (pos) active |= (1u << j);
+      }
+      if (!active) continue;
+      double cell = 0.0;
+      // subsets of the active set, grouped by size like the reference (sizes 1..q, alternating sign)
+      for (int size = 1; size <= q; ++size) {
+        double asum = 0.0;
+        bool any = false;
+        for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+          if (__popc(sub) != size) continue;
+          any = true;
+          double vol = 1.0, wprod = 1.0;
+          for (int o = 0; o < Mo; ++o) {
+            double mn = up[o];
+            for (unsigned rest = sub; rest; rest &= rest - 1) {
+              int j = __ffs(rest) - 1;
+              mn = fmin(mn, objs[((size_t)j * Mo + o) * nt + tid]);
+            }
+            vol *= fmax(mn - lo[o], 0.0);
+          }
+          if (a.od.n_cons) {
+            for (unsigned rest = sub; rest; rest &= rest - 1) wprod *= fw[(size_t)(__ffs(rest) - 1) * nt + tid];
+            vol *= wprod;
+          }
+          asum += vol;
+        }
+        if (any) cell += (size & 1) ? asum : -asum;
+      }
+      acc += cell;
+    }
+    total += acc;
+  }
+  double t = block_sum(total, red);
+  if (tid == 0) {
+    a.out[batch] = t / (double)S;
+    if (a.info_out) {
+      int v = 0;
+      for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
+      a.info_out[batch] = v;
+    }
+  }
+}
+
+int launch_mc_hvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  const int nt = 256;
+  size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + (size_t)a.q * a.od.n_obj * nt + (size_t)a.q * nt + 32) *
+                sizeof(double);
+  if (smem > 220 * 1024) { bo_set_error("mc_hvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_hvi_kernel<<<a.b, nt, smem, st>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: qLogEI = logmeanexp_S( fatmax_q( log_fatplus(obj - best_f, tau_relu), tau_max ) )
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double softplus_d(double x) {  // torch softplus(beta=1, threshold=32)
+  return (x > 32.0) ? x : log1p(exp(x));
+}
+__device__ __forceinline__ double log_softplus_d(double x) {
+  return (x > -35.0) ? log(softplus_d(x)) : x;  // tau = 1: x / tau + log(tau)
+}
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+  double mx = fmax(a, b), mn = fmin(a, b);
+  if (isinf(mx) && mx < 0) return mx;
+  return mx + log1p(exp(mn - mx));
+}
+__device__ __forceinline__ double log_fatplus_d(double x, double tau) {
+  double z = x / tau;
+  return log(tau) + logaddexp_d(log_softplus_d(z), log(1e-1) - log1p(z * z));
+}
+
+__global__ void __launch_bounds__(256)
+mc_logei_kernel(McArgs a) {
+  extern __shared__ double msm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
+  double* root = msm;
+  double* mu = root + M * q * nr;
+  double* vals = mu + q * M;  // [S]
+  double* red = vals + S;     // [32]
+  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+  const double tau_relu = 1e-6, tau_max = 1e-2;
+  double lmax = -INFINITY;
+  for (int s = tid; s < S; s += nt) {
+    double li[BO_MAX_Q];
+    double mx = -INFINITY;
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) {
+        const double* rr = root + ((size_t)m * q + j) * nr;
+        double sb = 0.0, sq = 0.0;
+        for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+        for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+        y[m] = (mu[j * M + m] + sb) + sq;
+      }
+      double o;
+      if (a.od.combine == BO_COMBINE_SINGLE) {
+        o = objective_apply(a.od.op[0], y);
+      } else if (a.od.combine == BO_COMBINE_ADDITIVE) {
+        o = 0.0;
+        for (int k = 0; k < a.od.n_obj; ++k) o = o + objective_apply(a.od.op[k], y) * a.od.op[k].w;
+      } else {
+        o = 1.0;
+        for (int k = 0; k < a.od.n_obj; ++k) o = o * pow(objective_apply(a.od.op[k], y), a.od.op[k].w);
+      }
+      li[j] = log_fatplus_d(o - a.best_f, tau_relu);
+      mx = fmax(mx, li[j]);
+    }
+    // fatmax over q: mx + tau * log(sum_j pareto((mx - li_j) / tau)), pareto(x) = (2 / (2 + 2x + x^2)) for alpha = 2
+    double ps = 0.0;
+    for (int j = 0; j < q; ++j) {
+      double x = (mx - li[j]) / tau_max;
+      ps += 2.0 / (2.0 + 2.0 * x + x * x);
+    }
+    double v = mx + tau_max * log(ps);
+    vals[s] = v;
+    lmax = fmax(lmax, v);
+  }
+  // block max
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = lmax;
+  __syncthreads();
+  double bm = -INFINITY;
+  for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, red[w]);
+  double se = 0.0;
+  for (int s = tid; s < S; s += nt) se += exp(vals[s] - bm);
+  double t = block_sum(se, red);
+  if (tid == 0) {
+    a.out[batch] = bm + log(t) - log((double)S);
+    if (a.info_out) {
+      int v = 0;
+      for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
+      a.info_out[batch] = v;
+    }
+  }
+}
+
+int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  const int nt = 256;
+  size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + a.S + 32) * sizeof(double);
+  if (smem > 220 * 1024) { bo_set_error("mc_logei: shared memory budget exceeded"); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_logei_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_logei_kernel<<<a.b, nt, smem, st>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}

@@ -1,0 +1,59 @@
+// Argument blocks and launchers of acqf.cu.
+#pragma once
+#include "common.cuh"
+
+struct CondRootArgs {
+  ModelD md;
+  PrepD prep_q, prep_b;
+  int b, q, nb, M, m;
+  const double* Gqq;     // [b, q, q]
+  const double* W;       // [b*q, ldw]
+  int ldw;
+  const double* mu_raw;  // [b*q]
+  const double* Lb;      // [nb, ldlb] cached baseline root of output m
+  int ldlb;
+  double* root;          // [b, M, q, nb+q]
+  double* mu;            // [b*q, M]
+  int* info;             // [b, M] or NULL
+  double* jitter;        // [b, M] or NULL
+};
+
+struct McArgs {
+  int b, q, nb, M, S;
+  ObjD od;
+  const double* root;
+  const double* mu;
+  const double* zbT;      // [(e*M+m)*S + s]
+  const double* zqT;      // [(k*M+m)*S + s]
+  const double* cell_lo;  // [(c*Mo+o)*S + s]  (or [(c*Mo+o)] when cells_shared)
+  const double* cell_up;
+  const int* ncells;      // [S] (or [1])
+  int cells_shared;
+  double best_f;
+  double* out;            // [b]
+  const int* info_in;     // [b, M] flags from cond_root
+  int* info_out;          // [b] or NULL
+};
+
+int launch_transpose_base_samples(const double* z, int S, int n, int M, double* zT, double* zM, int ldn, cudaStream_t st,
+                                  LaunchCounter* lc);
+int launch_scale_matrix(double* A, int ld, int rows, int cols, double s, cudaStream_t st, LaunchCounter* lc);
+int launch_copy_scale(const double* src, int lds, double* dst, int ldd, int rows, int cols, double scale, cudaStream_t st,
+                      LaunchCounter* lc);
+int launch_add_diag(double* A, int ld, int n, double v, cudaStream_t st, LaunchCounter* lc);
+int launch_finish_mean(const double* raw, int n, double mean_const, double y_std, double y_mean, double* out, int ldo,
+                       int m, cudaStream_t st, LaunchCounter* lc);
+int launch_finish_var(const ModelD& md, PrepD prep, const double* g, int n, int add_noise, double* out, int ldo, int m,
+                      cudaStream_t st, LaunchCounter* lc);
+int launch_cond_root(const CondRootArgs& a, cudaStream_t st, LaunchCounter* lc);
+int launch_baseline_objective(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od,
+                              double* obj, unsigned char* feas, double* samples, cudaStream_t st, LaunchCounter* lc);
+int launch_front(const double* obj, const unsigned char* feas, int S, int n, int Mo, const double* ref_dev, int dedup,
+                 unsigned char* front, int* counts, cudaStream_t st, LaunchCounter* lc);
+int launch_partition2d(const double* obj, const unsigned char* front, int n, int S, int cap, const double* ref_dev,
+                       double* lo, double* up, int* ncells, int* front_idx, cudaStream_t st, LaunchCounter* lc);
+int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
+                        const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
+                        cudaStream_t st, LaunchCounter* lc);
+int launch_mc_hvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc);

@@ -1,0 +1,765 @@
+// C-ABI entry points (include/everest_b200.h) and host-side orchestration of the kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "acqf.cuh"
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void bo_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int round_up(int v, int m) { return ((v + m - 1) / m) * m; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need, bool zero = false) {
+    if (need == 0) need = 16;
+    if (bytes < need) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      bytes = 0;
+      cudaError_t e = cudaMalloc(&p, need);
+      if (e != cudaSuccess) {
+        bo_set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        return BO_ERR_CUDA;
+      }
+      bytes = need;
+      zero = true;
+    }
+    if (zero) {
+      cudaError_t e = cudaMemset(p, 0, bytes);
+      if (e != cudaSuccess) { bo_set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return BO_ERR_CUDA; }
+    }
+    return BO_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+#define RC(expr) do { int _rc = (expr); if (_rc != BO_OK) return _rc; } while (0)
+
+struct PrepBuf {
+  DevBuf Xs[BO_MAX_LEAVES], n2[BO_MAX_LEAVES], codes[BO_MAX_LEAVES], bits[BO_MAX_LEAVES], pc[BO_MAX_LEAVES];
+  int ensure(const ModelD& md, int n, PrepD* out) {
+    memset(out, 0, sizeof(PrepD));
+    out->n = n;
+    size_t nn = (size_t)std::max(n, 1);
+    for (int l = 0; l < md.n_leaves; ++l) {
+      const LeafD& L = md.leaf[l];
+      if (L.kind <= BO_LEAF_MATERN52) {
+        RC(Xs[l].ensure(nn * L.dpad * sizeof(double)));
+        RC(n2[l].ensure(nn * sizeof(double)));
+        out->Xs[l] = Xs[l].as<double>();
+        out->n2[l] = n2[l].as<double>();
+      } else if (L.kind == BO_LEAF_HAMMING) {
+        RC(codes[l].ensure(nn * L.nd * sizeof(int)));
+        out->codes[l] = codes[l].as<int>();
+      } else {
+        RC(bits[l].ensure(nn * L.dpad * sizeof(u64)));
+        RC(pc[l].ensure(nn * sizeof(int)));
+        out->bits[l] = bits[l].as<u64>();
+        out->pc[l] = pc[l].as<int>();
+      }
+    }
+    return BO_OK;
+  }
+  void release() {
+    for (int l = 0; l < BO_MAX_LEAVES; ++l) { Xs[l].release(); n2[l].release(); codes[l].release(); bits[l].release(); pc[l].release(); }
+  }
+};
+
+struct OutputH {
+  ModelD md;
+  std::vector<void*> owned;  // small parameter arrays
+  PrepBuf train_prep;
+  PrepD train_prepd;
+  DevBuf L, Linv, LinvT, alpha_row, dinv, resid, tvec;
+  double jitter = 0.0;
+  // acquisition state
+  PrepBuf base_prep;
+  PrepD base_prepd;
+  DevBuf Ext, Lb, Sbb;
+  // per-forward query prep
+  PrepBuf q_prep;
+  PrepD q_prepd;
+};
+
+struct TimingRec { std::string name; cudaEvent_t a, b; };
+
+struct bo_state {
+  int N = 0, d = 0, M = 0, ldk = 0, Nr = 0;
+  bool factorized = false;
+  DevBuf X_train;
+  std::vector<OutputH> out;
+  LaunchCounter lc{0};
+  // workspaces
+  DevBuf wsKx, wsV, wsGqq, wsW, wsMuRaw, wsRoot, wsMu, wsZqT, wsTmp, wsInfo, wsCov, wsMean, wsF, wsZM, wsObj, wsFeas,
+      wsFront, wsCounts, wsJit, wsPart;
+  // acquisition
+  int acqf_kind = 0;  // 0 none, 1 nehvi, 2 ehvi, 3 logei
+  int nb = 0, S = 0, ldlb = 0, cap = 0;
+  ObjD od;
+  double best_f = 0.0;
+  DevBuf zbT, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b;
+  int cells_shared = 0;
+  // host staging for the HOST-buffer entry point
+  void* pin_in = nullptr; size_t pin_in_bytes = 0;
+  void* pin_out = nullptr; size_t pin_out_bytes = 0;
+  DevBuf stage_in, stage_out;
+  // timing
+  bool timing = false;
+  std::vector<TimingRec> recs;
+};
+
+static int upload(void** dst, const void* src, size_t bytes, std::vector<void*>& owned) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+  if (e != cudaSuccess) { bo_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return BO_ERR_CUDA; }
+  if (bytes) {
+    e = cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { bo_set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); return BO_ERR_CUDA; }
+  }
+  owned.push_back(p);
+  *dst = p;
+  return BO_OK;
+}
+
+extern "C" int bo_version(void) { return 100; }
+extern "C" const char* bo_last_error(void) { return g_err; }
+
+extern "C" void bo_state_destroy(bo_state* st) {
+  if (!st) return;
+  for (auto& o : st->out) {
+    for (void* p : o.owned) cudaFree(p);
+    o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
+    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Ext, &o.Lb, &o.Sbb};
+    for (DevBuf* b : bs) b->release();
+  }
+  DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
+                  &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
+                  &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
+                  &st->cell_up, &st->ncells, &st->front_idx, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
+                  &st->stage_in, &st->stage_out};
+  for (DevBuf* b : bs) b->release();
+  if (st->pin_in) cudaFreeHost(st->pin_in);
+  if (st->pin_out) cudaFreeHost(st->pin_out);
+  for (auto& r : st->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  delete st;
+}
+
+extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state) {
+  if (!cfg || !out_state) { bo_set_error("null argument"); return BO_ERR_INVALID; }
+  if (cfg->N < 1 || cfg->d < 1 || cfg->M < 1 || cfg->M > 2 * BO_MAX_OBJECTIVES) {
+    bo_set_error("bad sizes N=%d d=%d M=%d (M <= %d)", cfg->N, cfg->d, cfg->M, 2 * BO_MAX_OBJECTIVES);
+    return BO_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    bo_set_error("no CUDA device: everest_b200 has no CPU fallback");
+    return BO_ERR_CUDA;
+  }
+  bo_state* st = new bo_state();
+  st->N = cfg->N; st->d = cfg->d; st->M = cfg->M;
+  st->ldk = round_up(cfg->N, 16);
+  st->Nr = round_up(cfg->N, 128);
+  const int N = cfg->N, d = cfg->d;
+  int rc = st->X_train.ensure((size_t)N * d * sizeof(double));
+  if (rc) { bo_state_destroy(st); return rc; }
+  cudaMemcpy(st->X_train.p, cfg->X_train, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice);
+  st->out.resize(cfg->M);
+  for (int m = 0; m < cfg->M; ++m) {
+    const bo_output_model& om = cfg->outputs[m];
+    OutputH& o = st->out[m];
+    memset(&o.md, 0, sizeof(ModelD));
+    if (om.n_leaves < 1 || om.n_leaves > BO_MAX_LEAVES || om.n_terms < 1 || om.n_terms > BO_MAX_TERMS) {
+      bo_set_error("output %d: n_leaves=%d n_terms=%d out of range", m, om.n_leaves, om.n_terms);
+      bo_state_destroy(st); return BO_ERR_INVALID;
+    }
+    if (!(om.y_std > 0.0) || !(om.noise >= 0.0)) { bo_set_error("output %d: y_std must be > 0 and noise >= 0", m); bo_state_destroy(st); return BO_ERR_INVALID; }
+    o.md.n_leaves = om.n_leaves; o.md.n_terms = om.n_terms;
+    o.md.mean_const = om.mean_const; o.md.noise = om.noise; o.md.y_mean = om.y_mean; o.md.y_std = om.y_std;
+    for (int t = 0; t < om.n_terms; ++t) {
+      const bo_kernel_term& kt = om.terms[t];
+      if (kt.n_factors < 1 || kt.n_factors > BO_MAX_FACTORS) { bo_set_error("term %d: bad n_factors", t); bo_state_destroy(st); return BO_ERR_INVALID; }
+      o.md.coef[t] = kt.coef; o.md.nfac[t] = kt.n_factors;
+      for (int f = 0; f < kt.n_factors; ++f) {
+        if (kt.factors[f] < 0 || kt.factors[f] >= om.n_leaves) { bo_set_error("term %d: bad leaf index", t); bo_state_destroy(st); return BO_ERR_INVALID; }
+        o.md.fac[t][f] = kt.factors[f];
+      }
+    }
+    for (int l = 0; l < om.n_leaves; ++l) {
+      const bo_kernel_leaf& kl = om.leaves[l];
+      LeafD& L = o.md.leaf[l];
+      L.kind = kl.kind; L.nd = kl.n_dims;
+      if (kl.n_dims < 1) { bo_set_error("leaf %d: n_dims < 1", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+      for (int k = 0; k < kl.n_dims; ++k) {
+        int width = (kl.kind == BO_LEAF_HAMMING) ? kl.cardinality[k] : 1;
+        if (kl.dims[k] < 0 || kl.dims[k] + width > d) { bo_set_error("leaf %d: column out of range", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+      }
+      std::vector<int> col(kl.dims, kl.dims + kl.n_dims);
+      void* p;
+      rc = upload(&p, col.data(), col.size() * sizeof(int), o.owned); if (rc) { bo_state_destroy(st); return rc; }
+      L.col = (const int*)p;
+      if (kl.kind <= BO_LEAF_MATERN52) {
+        if (kl.kind < 0 || (kl.n_ls != 1 && kl.n_ls != kl.n_dims) || !kl.lengthscale) { bo_set_error("leaf %d: bad lengthscale spec", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+        L.dpad = round_up(kl.n_dims, 4);
+        std::vector<double> off(kl.n_dims), scl(kl.n_dims), ls(kl.n_dims), cen(kl.n_dims);
+        for (int k = 0; k < kl.n_dims; ++k) {
+          off[k] = om.in_offset ? om.in_offset[kl.dims[k]] : 0.0;
+          scl[k] = om.in_scale ? om.in_scale[kl.dims[k]] : 1.0;
+          ls[k] = kl.lengthscale[kl.n_ls == 1 ? 0 : k];
+          if (!(ls[k] > 0.0) || scl[k] == 0.0) { bo_set_error("leaf %d: non-positive lengthscale / zero scale", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+          double acc = 0.0;
+          for (int i = 0; i < N; ++i) acc += (cfg->X_train[(size_t)i * d + kl.dims[k]] - off[k]) / scl[k];
+          cen[k] = acc / (double)N;
+        }
+        rc = upload(&p, off.data(), off.size() * 8, o.owned); if (rc) { bo_state_destroy(st); return rc; } L.in_off = (const double*)p;
+        rc = upload(&p, scl.data(), scl.size() * 8, o.owned); if (rc) { bo_state_destroy(st); return rc; } L.in_scl = (const double*)p;
+        rc = upload(&p, cen.data(), cen.size() * 8, o.owned); if (rc) { bo_state_destroy(st); return rc; } L.center = (const double*)p;
+        rc = upload(&p, ls.data(), ls.size() * 8, o.owned); if (rc) { bo_state_destroy(st); return rc; } L.ls = (const double*)p;
+      } else if (kl.kind == BO_LEAF_HAMMING) {
+        if (kl.n_dims > BO_MAX_GROUPS || !kl.cardinality || !kl.lengthscale || (kl.n_ls != 1 && kl.n_ls < kl.n_dims)) {
+          bo_set_error("leaf %d: bad Hamming spec (<= %d groups)", l, BO_MAX_GROUPS); bo_state_destroy(st); return BO_ERR_INVALID;
+        }
+        L.dpad = kl.n_dims;
+        std::vector<int> card(kl.cardinality, kl.cardinality + kl.n_dims);
+        std::vector<double> wls(kl.n_dims);
+        for (int k = 0; k < kl.n_dims; ++k) wls[k] = 1.0 / kl.lengthscale[kl.n_ls == 1 ? 0 : k];
+        rc = upload(&p, card.data(), card.size() * sizeof(int), o.owned); if (rc) { bo_state_destroy(st); return rc; } L.card = (const int*)p;
+        rc = upload(&p, wls.data(), wls.size() * 8, o.owned); if (rc) { bo_state_destroy(st); return rc; } L.wls = (const double*)p;
+      } else if (kl.kind == BO_LEAF_TANIMOTO) {
+        L.dpad = (kl.n_dims + 63) / 64;
+        for (int i = 0; i < N; ++i)
+          for (int k = 0; k < kl.n_dims; ++k) {
+            double v = cfg->X_train[(size_t)i * d + kl.dims[k]];
+            if (v != 0.0 && v != 1.0) {
+              bo_set_error("leaf %d: Tanimoto columns must hold 0/1 fingerprints (count features are not supported)", l);
+              bo_state_destroy(st); return BO_ERR_INVALID;
+            }
+          }
+      } else { bo_set_error("leaf %d: unknown kind %d", l, kl.kind); bo_state_destroy(st); return BO_ERR_INVALID; }
+    }
+    // prepared training side
+    rc = o.train_prep.ensure(o.md, N, &o.train_prepd); if (rc) { bo_state_destroy(st); return rc; }
+    rc = launch_prep_points(o.md, st->X_train.as<double>(), N, d, o.train_prepd, 0, &st->lc); if (rc) { bo_state_destroy(st); return rc; }
+    for (int l = 0; l < om.n_leaves; ++l) {
+      LeafD& L = o.md.leaf[l];
+      L.Xs = o.train_prepd.Xs[l]; L.n2 = o.train_prepd.n2[l]; L.codes = o.train_prepd.codes[l];
+      L.bits = o.train_prepd.bits[l]; L.pc = o.train_prepd.pc[l];
+    }
+    // residual r = (y - y_mean) / y_std - mean_const, zero padded row of length ldk
+    std::vector<double> r(st->ldk, 0.0);
+    for (int i = 0; i < N; ++i) r[i] = (om.y[i] - om.y_mean) / om.y_std - om.mean_const;
+    rc = o.resid.ensure((size_t)st->ldk * 8); if (rc) { bo_state_destroy(st); return rc; }
+    cudaMemcpy(o.resid.p, r.data(), (size_t)st->ldk * 8, cudaMemcpyHostToDevice);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { bo_set_error("create: %s", cudaGetErrorString(e)); bo_state_destroy(st); return BO_ERR_CUDA; }
+  *out_state = st;
+  return BO_OK;
+}
+
+// psd-safe blocked Cholesky of `src` (n x n, ld) into `dst`: jitter ladder 1e-8 .. 1e-3 on the whole diagonal.
+static int psd_safe_chol(bo_state* st, const double* src, double* dst, int ld, int n, DevBuf& dinv, int* info_out,
+                         double* jitter_out, cudaStream_t s) {
+  RC(dinv.ensure((size_t)((n + 63) / 64) * 64 * 64 * 8));
+  RC(st->wsInfo.ensure(64));
+  int* info_dev = st->wsInfo.as<int>();
+  double applied = 0.0;
+  for (int attempt = 0; attempt <= 6; ++attempt) {
+    CUDA_CHECK_RET(cudaMemcpyAsync(dst, src, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
+    if (attempt > 0) {
+      applied = 1e-8 * pow(10.0, attempt - 1);
+      RC(launch_add_diag(dst, ld, n, applied, s, &st->lc));
+    }
+    CUDA_CHECK_RET(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+    RC(chol_blocked(dst, ld, n, dinv.as<double>(), info_dev, s, &st->lc));
+    int info = 0;
+    CUDA_CHECK_RET(cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));
+    *info_out = info;
+    if (info == 0) { if (jitter_out) *jitter_out = applied; return BO_OK; }
+  }
+  if (jitter_out) *jitter_out = applied;
+  return BO_OK;  // caller inspects info
+}
+
+extern "C" int bo_state_factorize(bo_state* st, int32_t* info, double* jitter, void* stream) {
+  if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = st->N, ldk = st->ldk, Nr = st->Nr;
+  bool ok = true;
+  for (int m = 0; m < st->M; ++m) {
+    OutputH& o = st->out[m];
+    RC(st->wsCov.ensure((size_t)Nr * ldk * 8, true));
+    double* G = st->wsCov.as<double>();
+    RC(launch_crosscov(o.md, o.train_prepd, o.train_prepd, true, N, G, ldk, true, s, &st->lc));
+    RC(launch_add_diag(G, ldk, N, o.md.noise, s, &st->lc));
+    RC(o.L.ensure((size_t)Nr * ldk * 8, true));
+    int inf = 0; double jit = 0.0;
+    RC(psd_safe_chol(st, G, o.L.as<double>(), ldk, N, o.dinv, &inf, &jit, s));
+    if (info) info[m] = inf;
+    if (jitter) jitter[m] = jit;
+    o.jitter = jit;
+    if (inf != 0) { ok = false; continue; }
+    RC(o.Linv.ensure((size_t)Nr * ldk * 8, true));
+    RC(o.LinvT.ensure((size_t)Nr * ldk * 8, true));
+    RC(st->wsTmp.ensure((size_t)64 * ldk * 8, true));
+    RC(tri_inverse_blocked(o.L.as<double>(), ldk, N, o.dinv.as<double>(), o.Linv.as<double>(), o.LinvT.as<double>(), ldk,
+                           st->wsTmp.as<double>(), s, &st->lc));
+    // alpha = L^-T (L^-1 r)
+    RC(o.tvec.ensure((size_t)ldk * 8, true));
+    RC(o.alpha_row.ensure((size_t)ldk * 8, true));
+    RC(launch_gemm_nt(N, 1, N, 1.0, o.Linv.as<double>(), ldk, o.resid.as<double>(), ldk, 0.0, o.tvec.as<double>(), 1, false, s, &st->lc));
+    RC(launch_gemm_nt(N, 1, N, 1.0, o.LinvT.as<double>(), ldk, o.tvec.as<double>(), ldk, 0.0, o.alpha_row.as<double>(), 1, false, s, &st->lc));
+  }
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  st->factorized = ok;
+  if (!ok) { bo_set_error("training Gram matrix not positive definite after jitter 1e-3"); return BO_ERR_NOT_PSD; }
+  return BO_OK;
+}
+
+// mean [n, M] (ldo = M), optional cov_m written by callback-free path below
+static int posterior_blocks(bo_state* st, int m, const double* X_dev, int n, PrepBuf& pb, PrepD* pd, double* Kx,
+                            double* V, double* mu_raw, cudaStream_t s) {
+  OutputH& o = st->out[m];
+  RC(pb.ensure(o.md, n, pd));
+  RC(launch_prep_points(o.md, X_dev, n, st->d, *pd, s, &st->lc));
+  RC(launch_crosscov(o.md, *pd, o.train_prepd, true, st->N, Kx, st->ldk, false, s, &st->lc));
+  if (V) RC(launch_gemm_nt(n, st->N, st->N, 1.0, Kx, st->ldk, o.Linv.as<double>(), st->ldk, 0.0, V, st->ldk, false, s, &st->lc));
+  if (mu_raw) RC(launch_gemm_nt(n, 1, st->N, 1.0, Kx, st->ldk, o.alpha_row.as<double>(), st->ldk, 0.0, mu_raw, 1, false, s, &st->lc));
+  return BO_OK;
+}
+
+extern "C" int bo_posterior_joint(bo_state* st, const double* X_dev, int32_t n, double* mean_dev, double* cov_dev,
+                                  void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ldk = st->ldk, ldn = round_up(n, 16);
+  RC(st->wsKx.ensure((size_t)n * ldk * 8));
+  RC(st->wsV.ensure((size_t)n * ldk * 8, true));
+  RC(st->wsMuRaw.ensure((size_t)n * 8));
+  RC(st->wsCov.ensure((size_t)n * ldn * 8));
+  for (int m = 0; m < st->M; ++m) {
+    OutputH& o = st->out[m];
+    RC(posterior_blocks(st, m, X_dev, n, o.q_prep, &o.q_prepd, st->wsKx.as<double>(), st->wsV.as<double>(), st->wsMuRaw.as<double>(), s));
+    RC(launch_finish_mean(st->wsMuRaw.as<double>(), n, o.md.mean_const, o.md.y_std, o.md.y_mean, mean_dev, st->M, m, s, &st->lc));
+    if (cov_dev) {
+      RC(launch_crosscov(o.md, o.q_prepd, o.q_prepd, false, n, st->wsCov.as<double>(), ldn, true, s, &st->lc));
+      RC(launch_gemm_nt(n, n, st->N, -1.0, st->wsV.as<double>(), ldk, st->wsV.as<double>(), ldk, 1.0, st->wsCov.as<double>(), ldn, false, s, &st->lc));
+      RC(launch_copy_scale(st->wsCov.as<double>(), ldn, cov_dev + (size_t)m * n * n, n, n, n, o.md.y_std * o.md.y_std, s, &st->lc));
+    }
+  }
+  return BO_OK;
+}
+
+extern "C" int bo_posterior_marginal(bo_state* st, const double* X_dev, int32_t n, int32_t observation_noise,
+                                     double* mean_dev, double* var_dev, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ldk = st->ldk;
+  RC(st->wsKx.ensure((size_t)n * ldk * 8));
+  RC(st->wsMuRaw.ensure((size_t)n * 8));
+  RC(st->wsGqq.ensure((size_t)n * 8));
+  for (int m = 0; m < st->M; ++m) {
+    OutputH& o = st->out[m];
+    RC(posterior_blocks(st, m, X_dev, n, o.q_prep, &o.q_prepd, st->wsKx.as<double>(), nullptr, nullptr, s));
+    PostGemmArgs a;
+    a.Kx = st->wsKx.as<double>(); a.rows = n; a.ldk = ldk; a.Linv = o.Linv.as<double>(); a.Ext = o.alpha_row.as<double>();
+    a.N = st->N; a.Nr = st->Nr; a.n_ext = 1; a.q = 1; a.Gqq = st->wsGqq.as<double>(); a.W = nullptr; a.ldw = 0;
+    a.mu_raw = st->wsMuRaw.as<double>();
+    RC(launch_posterior_gemm(a, s, &st->lc));
+    RC(launch_finish_mean(st->wsMuRaw.as<double>(), n, o.md.mean_const, o.md.y_std, o.md.y_mean, mean_dev, st->M, m, s, &st->lc));
+    RC(launch_finish_var(o.md, o.q_prepd, st->wsGqq.as<double>(), n, observation_noise, var_dev, st->M, m, s, &st->lc));
+  }
+  return BO_OK;
+}
+
+static int fill_objd(ObjD* od, const bo_objective_op* obj, int n_obj, const bo_constraint_op* cons, int n_cons, int combine,
+                     int M) {
+  if (n_obj < 1 || n_obj > BO_MAX_OBJECTIVES || n_cons < 0 || n_cons > BO_MAX_CONSTRAINTS) {
+    bo_set_error("n_obj=%d / n_cons=%d out of range", n_obj, n_cons);
+    return BO_ERR_INVALID;
+  }
+  memset(od, 0, sizeof(ObjD));
+  od->n_obj = n_obj; od->n_cons = n_cons; od->combine = combine;
+  for (int i = 0; i < n_obj; ++i) {
+    if (obj[i].out_idx < 0 || obj[i].out_idx >= M || obj[i].kind < 0 || obj[i].kind > BO_OBJ_TARGET) { bo_set_error("objective %d invalid", i); return BO_ERR_INVALID; }
+    od->op[i] = obj[i];
+  }
+  for (int i = 0; i < n_cons; ++i) {
+    if (cons[i].out_idx < 0 || cons[i].out_idx >= M || !(cons[i].eta > 0.0)) { bo_set_error("constraint %d invalid", i); return BO_ERR_INVALID; }
+    od->con[i] = cons[i];
+  }
+  return BO_OK;
+}
+
+// Joint posterior at X (n points): mean_dev [n, M]; per output the lower Cholesky root of the
+// un-standardised covariance into roots[m] ([n, ldn]); V rows optionally kept in Vkeep[m] ([n, ldk]).
+static int joint_root(bo_state* st, int m, const double* X_dev, int n, int ldn, PrepBuf& pb, PrepD* pd, double* mean_dev,
+                      DevBuf& rootbuf, DevBuf& covcopy, double* Vdst, int* info, double* jit, cudaStream_t s) {
+  OutputH& o = st->out[m];
+  const int ldk = st->ldk;
+  RC(st->wsKx.ensure((size_t)n * ldk * 8));
+  RC(st->wsMuRaw.ensure((size_t)n * 8));
+  RC(posterior_blocks(st, m, X_dev, n, pb, pd, st->wsKx.as<double>(), Vdst, st->wsMuRaw.as<double>(), s));
+  RC(launch_finish_mean(st->wsMuRaw.as<double>(), n, o.md.mean_const, o.md.y_std, o.md.y_mean, mean_dev, st->M, m, s, &st->lc));
+  RC(covcopy.ensure((size_t)n * ldn * 8, true));
+  RC(rootbuf.ensure((size_t)n * ldn * 8, true));
+  double* C = covcopy.as<double>();
+  RC(launch_crosscov(o.md, *pd, *pd, false, n, C, ldn, true, s, &st->lc));
+  RC(launch_gemm_nt(n, n, st->N, -1.0, Vdst, ldk, Vdst, ldk, 1.0, C, ldn, false, s, &st->lc));
+  RC(launch_scale_matrix(C, ldn, n, n, o.md.y_std * o.md.y_std, s, &st->lc));
+  DevBuf dinv_local;
+  int rc = psd_safe_chol(st, C, rootbuf.as<double>(), ldn, n, dinv_local, info, jit, s);
+  dinv_local.release();
+  return rc;
+}
+
+extern "C" int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S,
+                               const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                               const double* ref_point, int32_t* counts_dev, int32_t* info, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ObjD od;
+  RC(fill_objd(&od, obj, n_obj, cons, n_cons, 0, st->M));
+  const int M = st->M, ldn = round_up(n, 16), ldk = st->ldk;
+  RC(st->wsMean.ensure((size_t)n * M * 8));
+  RC(st->wsZM.ensure((size_t)M * S * ldn * 8, true));
+  RC(st->wsF.ensure((size_t)M * S * ldn * 8));
+  RC(st->wsV.ensure((size_t)n * ldk * 8, true));
+  RC(launch_transpose_base_samples(z_dev, S, n, M, nullptr, st->wsZM.as<double>(), ldn, s, &st->lc));
+  DevBuf root, cov;
+  PrepBuf pb; PrepD pd;
+  int rcode = BO_OK;
+  for (int m = 0; m < M && rcode == BO_OK; ++m) {
+    int inf = 0; double jit = 0;
+    rcode = joint_root(st, m, X_dev, n, ldn, pb, &pd, st->wsMean.as<double>(), root, cov, st->wsV.as<double>(), &inf, &jit, s);
+    if (info) info[m] = inf;
+    if (rcode == BO_OK && inf != 0) { bo_set_error("posterior covariance at the baseline not p.d. (output %d)", m); rcode = BO_ERR_NOT_PSD; }
+    if (rcode == BO_OK)
+      rcode = launch_gemm_nt(S, n, n, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldn, ldn, root.as<double>(), ldn, 0.0,
+                             st->wsF.as<double>() + (size_t)m * S * ldn, ldn, false, s, &st->lc);
+  }
+  if (rcode == BO_OK) rcode = st->wsObj.ensure((size_t)S * n * n_obj * 8);
+  if (rcode == BO_OK) rcode = st->wsFeas.ensure((size_t)S * n);
+  if (rcode == BO_OK) rcode = st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8);
+  if (rcode == BO_OK) {
+    cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s);
+    rcode = launch_baseline_objective(st->wsF.as<double>(), ldn, S, n, M, st->wsMean.as<double>(), od, st->wsObj.as<double>(),
+                                      st->wsFeas.as<unsigned char>(), nullptr, s, &st->lc);
+  }
+  if (rcode == BO_OK) {
+    cudaMemsetAsync(counts_dev, 0, (size_t)n * sizeof(int), s);
+    rcode = launch_front(st->wsObj.as<double>(), st->wsFeas.as<unsigned char>(), S, n, n_obj, st->ref_dev.as<double>(), 0,
+                         nullptr, counts_dev, s, &st->lc);
+  }
+  cudaStreamSynchronize(s);
+  root.release(); cov.release(); pb.release();
+  return rcode;
+}
+
+static int build_cells(bo_state* st, const double* obj, const unsigned char* feas, int n, int S, int Mo, int* max_cells,
+                       cudaStream_t s) {
+  RC(st->wsFront.ensure((size_t)S * std::max(n, 1)));
+  RC(launch_front(obj, feas, S, n, Mo, st->ref_dev.as<double>(), 1, st->wsFront.as<unsigned char>(), nullptr, s, &st->lc));
+  RC(st->ncells.ensure((size_t)S * sizeof(int)));
+  if (Mo == 2) {
+    st->cap = n + 1;
+    RC(st->cell_lo.ensure((size_t)st->cap * Mo * S * 8));
+    RC(st->cell_up.ensure((size_t)st->cap * Mo * S * 8));
+    RC(st->front_idx.ensure((size_t)S * st->cap * sizeof(int)));
+    CUDA_CHECK_RET(cudaMemsetAsync(st->front_idx.p, 0xff, (size_t)S * st->cap * sizeof(int), s));
+    RC(launch_partition2d(obj, st->wsFront.as<unsigned char>(), n, S, st->cap, st->ref_dev.as<double>(),
+                          st->cell_lo.as<double>(), st->cell_up.as<double>(), st->ncells.as<int>(), st->front_idx.as<int>(), s, &st->lc));
+  } else {
+    // capacity: start generous, double on overflow
+    int cap = std::max(64, 8 * (n + 1) * Mo);
+    for (;;) {
+      st->cap = cap;
+      RC(st->cell_lo.ensure((size_t)cap * Mo * S * 8));
+      RC(st->cell_up.ensure((size_t)cap * Mo * S * 8));
+      RC(st->wsPart.ensure((size_t)S * 2 * cap * (Mo + Mo * Mo) * 8));
+      RC(st->wsInfo.ensure(64));
+      CUDA_CHECK_RET(cudaMemsetAsync(st->wsInfo.p, 0, sizeof(int), s));
+      RC(launch_partition_nd(obj, st->wsFront.as<unsigned char>(), n, S, Mo, cap, st->ref_dev.as<double>(), st->wsPart.as<double>(),
+                             st->cell_lo.as<double>(), st->cell_up.as<double>(), st->ncells.as<int>(), st->wsInfo.as<int>(), s, &st->lc));
+      int overflow = 0;
+      CUDA_CHECK_RET(cudaMemcpyAsync(&overflow, st->wsInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK_RET(cudaStreamSynchronize(s));
+      if (!overflow) break;
+      cap *= 2;
+      if ((size_t)cap * (Mo + Mo * Mo) * S * 16 > ((size_t)48 << 30)) { bo_set_error("box decomposition exceeds the workspace budget"); return BO_ERR_INVALID; }
+    }
+  }
+  std::vector<int> nc(S);
+  CUDA_CHECK_RET(cudaMemcpyAsync(nc.data(), st->ncells.p, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  int mx = 0;
+  for (int v : nc) mx = std::max(mx, v);
+  if (max_cells) *max_cells = mx;
+  return BO_OK;
+}
+
+extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b, const double* zb_dev, int32_t S,
+                                const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                                const double* ref_point, int32_t* info, int32_t* max_cells, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  if (n_obj < 2) { bo_set_error("qNEHVI needs at least two objectives"); return BO_ERR_INVALID; }
+  if (S < 1 || n_b < 0) { bo_set_error("bad S / n_b"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  st->acqf_kind = 0;
+  RC(fill_objd(&st->od, obj, n_obj, cons, n_cons, 0, st->M));
+  const int M = st->M, ldk = st->ldk, nb = n_b, ldlb = round_up(std::max(nb, 1), 16);
+  st->nb = nb; st->S = S; st->ldlb = ldlb; st->cells_shared = 0;
+  RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
+  RC(st->mean_b.ensure((size_t)std::max(nb, 1) * M * 8));
+  RC(st->zbT.ensure((size_t)std::max(nb, 1) * M * S * 8));
+  RC(st->wsZM.ensure((size_t)M * S * ldlb * 8, true));
+  RC(st->wsF.ensure((size_t)M * S * ldlb * 8));
+  if (nb > 0) RC(launch_transpose_base_samples(zb_dev, S, nb, M, st->zbT.as<double>(), st->wsZM.as<double>(), ldlb, s, &st->lc));
+  for (int m = 0; m < M; ++m) {
+    OutputH& o = st->out[m];
+    RC(o.Ext.ensure((size_t)(nb + 1) * ldk * 8, true));
+    if (nb > 0) {
+      int inf = 0; double jit = 0;
+      RC(joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, o.Ext.as<double>(), &inf, &jit, s));
+      if (info) info[m] = inf;
+      if (inf != 0) { bo_set_error("baseline posterior covariance not p.d. (output %d)", m); return BO_ERR_NOT_PSD; }
+      RC(launch_gemm_nt(S, nb, nb, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldlb, ldlb, o.Lb.as<double>(), ldlb, 0.0,
+                        st->wsF.as<double>() + (size_t)m * S * ldlb, ldlb, false, s, &st->lc));
+    } else {
+      RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
+      RC(o.Lb.ensure(16));
+      if (info) info[m] = 0;
+    }
+    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.as<double>() + (size_t)nb * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  RC(st->obj_b.ensure((size_t)S * std::max(nb, 1) * n_obj * 8));
+  RC(st->samples_b.ensure((size_t)S * std::max(nb, 1) * M * 8));
+  RC(st->wsFeas.ensure((size_t)S * std::max(nb, 1)));
+  RC(launch_baseline_objective(st->wsF.as<double>(), ldlb, S, nb, M, st->mean_b.as<double>(), st->od, st->obj_b.as<double>(),
+                               st->wsFeas.as<unsigned char>(), st->samples_b.as<double>(), s, &st->lc));
+  RC(build_cells(st, st->obj_b.as<double>(), st->wsFeas.as<unsigned char>(), nb, S, n_obj, max_cells, s));
+  st->acqf_kind = 1;
+  return BO_OK;
+}
+
+extern "C" int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, int32_t S, const bo_objective_op* obj,
+                               int32_t n_obj, const double* ref_point, int32_t* max_cells, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  st->acqf_kind = 0;
+  RC(fill_objd(&st->od, obj, n_obj, nullptr, 0, 0, st->M));
+  st->nb = 0; st->S = S; st->ldlb = 16; st->cells_shared = 1;
+  RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
+  RC(st->wsFeas.ensure((size_t)std::max(n, 1)));
+  CUDA_CHECK_RET(cudaMemsetAsync(st->wsFeas.p, 1, (size_t)std::max(n, 1), s));
+  RC(st->zbT.ensure(16));
+  for (int m = 0; m < st->M; ++m) {
+    OutputH& o = st->out[m];
+    RC(o.Ext.ensure((size_t)st->ldk * 8, true));
+    RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
+    RC(o.Lb.ensure(16));
+    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.p, o.alpha_row.p, (size_t)st->ldk * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  RC(build_cells(st, Yobj_dev, st->wsFeas.as<unsigned char>(), n, 1, n_obj, max_cells, s));
+  st->acqf_kind = 2;
+  return BO_OK;
+}
+
+extern "C" int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
+                                double best_f, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  st->acqf_kind = 0;
+  if (combine == BO_COMBINE_SINGLE && n_obj != 1) { bo_set_error("single objective needs n_obj == 1"); return BO_ERR_INVALID; }
+  RC(fill_objd(&st->od, obj, n_obj, nullptr, 0, combine, st->M));
+  st->nb = 0; st->S = S; st->ldlb = 16; st->cells_shared = 0; st->best_f = best_f;
+  RC(st->zbT.ensure(16));
+  for (int m = 0; m < st->M; ++m) {
+    OutputH& o = st->out[m];
+    RC(o.Ext.ensure((size_t)st->ldk * 8, true));
+    RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
+    RC(o.Lb.ensure(16));
+    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.p, o.alpha_row.p, (size_t)st->ldk * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  st->acqf_kind = 3;
+  return BO_OK;
+}
+
+static void rec_begin(bo_state* st, const char* name, cudaStream_t s) {
+  if (!st->timing) return;
+  TimingRec r;
+  r.name = name;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  st->recs.push_back(r);
+}
+static void rec_end(bo_state* st, cudaStream_t s) {
+  if (!st->timing) return;
+  cudaEventRecord(st->recs.back().b, s);
+}
+
+extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                               double* out_dev, int32_t* info_dev, void* stream) {
+  if (!st || !st->factorized || st->acqf_kind == 0) { bo_set_error("forward before prepare"); return BO_ERR_STATE; }
+  if (b < 1 || q < 1 || q > BO_MAX_Q) { bo_set_error("bad b=%d / q=%d (q <= %d)", b, q, BO_MAX_Q); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st->timing) {
+    for (auto& r : st->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    st->recs.clear();
+  }
+  const int M = st->M, ldk = st->ldk, nb = st->nb, S = st->S, nr = nb + q;
+  const int ldw = std::max(nb, 1);
+  // chunk the q-batches so that the K(X*,X) workspace stays below ~4 GiB
+  long long max_rows = std::max<long long>(((long long)4 << 30) / ((long long)ldk * 8), (long long)q);
+  int bchunk = (int)std::min<long long>(b, std::max<long long>(1, max_rows / q));
+  RC(st->wsZqT.ensure((size_t)q * M * S * 8));
+  RC(launch_transpose_base_samples(zq_dev, S, q, M, st->wsZqT.as<double>(), nullptr, 0, s, &st->lc));
+  RC(st->wsKx.ensure((size_t)bchunk * q * ldk * 8));
+  RC(st->wsGqq.ensure((size_t)bchunk * q * q * 8));
+  RC(st->wsW.ensure((size_t)bchunk * q * ldw * 8));
+  RC(st->wsMuRaw.ensure((size_t)bchunk * q * 8));
+  RC(st->wsRoot.ensure((size_t)bchunk * M * q * nr * 8));
+  RC(st->wsMu.ensure((size_t)bchunk * q * M * 8));
+  RC(st->wsJit.ensure((size_t)bchunk * M * sizeof(int)));
+  for (int b0 = 0; b0 < b; b0 += bchunk) {
+    const int bc = std::min(bchunk, b - b0), rows = bc * q;
+    const double* Xc = X_dev + (size_t)b0 * q * st->d;
+    for (int m = 0; m < M; ++m) {
+      OutputH& o = st->out[m];
+      RC(o.q_prep.ensure(o.md, rows, &o.q_prepd));
+      rec_begin(st, "prep", s);
+      RC(launch_prep_points(o.md, Xc, rows, st->d, o.q_prepd, s, &st->lc));
+      rec_end(st, s);
+      rec_begin(st, "crosscov", s);
+      RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, st->wsKx.as<double>(), ldk, false, s, &st->lc));
+      rec_end(st, s);
+      PostGemmArgs a;
+      a.Kx = st->wsKx.as<double>(); a.rows = rows; a.ldk = ldk; a.Linv = o.Linv.as<double>(); a.Ext = o.Ext.as<double>();
+      a.N = st->N; a.Nr = st->Nr; a.n_ext = nb + 1; a.q = q; a.Gqq = st->wsGqq.as<double>(); a.W = st->wsW.as<double>();
+      a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>();
+      rec_begin(st, "posterior_gemm", s);
+      RC(launch_posterior_gemm(a, s, &st->lc));
+      rec_end(st, s);
+      CondRootArgs c;
+      c.md = o.md; c.prep_q = o.q_prepd; c.prep_b = o.base_prepd; c.b = bc; c.q = q; c.nb = nb; c.M = M; c.m = m;
+      c.Gqq = st->wsGqq.as<double>(); c.W = st->wsW.as<double>(); c.ldw = ldw; c.mu_raw = st->wsMuRaw.as<double>();
+      c.Lb = o.Lb.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
+      c.info = st->wsJit.as<int>(); c.jitter = nullptr;
+      rec_begin(st, "cond_root", s);
+      RC(launch_cond_root(c, s, &st->lc));
+      rec_end(st, s);
+    }
+    McArgs ma;
+    ma.b = bc; ma.q = q; ma.nb = nb; ma.M = M; ma.S = S; ma.od = st->od; ma.root = st->wsRoot.as<double>();
+    ma.mu = st->wsMu.as<double>(); ma.zbT = st->zbT.as<double>(); ma.zqT = st->wsZqT.as<double>();
+    ma.cell_lo = st->cell_lo.as<double>(); ma.cell_up = st->cell_up.as<double>(); ma.ncells = st->ncells.as<int>();
+    ma.cells_shared = st->cells_shared; ma.best_f = st->best_f; ma.out = out_dev + b0;
+    ma.info_in = st->wsJit.as<int>(); ma.info_out = info_dev ? info_dev + b0 : nullptr;
+    rec_begin(st, "mc_acqf", s);
+    if (st->acqf_kind == 3) RC(launch_mc_logei(ma, s, &st->lc));
+    else RC(launch_mc_hvi(ma, s, &st->lc));
+    rec_end(st, s);
+  }
+  return BO_OK;
+}
+
+extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
+                                    double* out_host, void* stream) {
+  if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t in_bytes = (size_t)b * q * st->d * 8, out_bytes = (size_t)b * 8;
+  if (st->pin_in_bytes < in_bytes) {
+    if (st->pin_in) cudaFreeHost(st->pin_in);
+    CUDA_CHECK_RET(cudaHostAlloc(&st->pin_in, in_bytes, cudaHostAllocDefault));
+    st->pin_in_bytes = in_bytes;
+  }
+  if (st->pin_out_bytes < out_bytes) {
+    if (st->pin_out) cudaFreeHost(st->pin_out);
+    CUDA_CHECK_RET(cudaHostAlloc(&st->pin_out, out_bytes, cudaHostAllocDefault));
+    st->pin_out_bytes = out_bytes;
+  }
+  RC(st->stage_in.ensure(in_bytes));
+  RC(st->stage_out.ensure(out_bytes));
+  memcpy(st->pin_in, X_host, in_bytes);
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->stage_in.p, st->pin_in, in_bytes, cudaMemcpyHostToDevice, s));
+  RC(bo_acqf_forward(st, st->stage_in.as<double>(), b, q, zq_dev, st->stage_out.as<double>(), nullptr, s));
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  memcpy(out_host, st->pin_out, out_bytes);
+  return BO_OK;
+}
+
+extern "C" int64_t bo_launch_count(const bo_state* st) { return st ? st->lc.n : 0; }
+
+extern "C" int bo_set_timing(bo_state* st, int32_t enabled) {
+  if (!st) return BO_ERR_INVALID;
+  st->timing = enabled != 0;
+  return BO_OK;
+}
+
+extern "C" int bo_last_timing(const bo_state* st, const char* name, double* ms) {
+  if (!st || !ms) return BO_ERR_INVALID;
+  double total = 0.0;
+  int cnt = 0;
+  for (auto& r : st->recs) {
+    if (r.name != name) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { bo_set_error("event sync failed"); return BO_ERR_CUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    total += t;
+    ++cnt;
+  }
+  *ms = total;
+  return cnt;
+}
+
+extern "C" int bo_debug_get(bo_state* st, const char* name, int32_t m, double* out_dev, int64_t capacity,
+                            int64_t* n_written, void* stream) {
+  if (!st || !name) return BO_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::string nm(name);
+  const double* src = nullptr;
+  int64_t n = 0;
+  auto chk_m = [&]() { return m >= 0 && m < st->M; };
+  if (nm == "L" && chk_m()) { src = st->out[m].L.as<double>(); n = (int64_t)st->N * st->ldk; }
+  else if (nm == "Linv" && chk_m()) { src = st->out[m].Linv.as<double>(); n = (int64_t)st->N * st->ldk; }
+  else if (nm == "alpha" && chk_m()) { src = st->out[m].alpha_row.as<double>(); n = st->N; }
+  else if (nm == "baseline_L" && chk_m()) { src = st->out[m].Lb.as<double>(); n = (int64_t)st->nb * st->ldlb; }
+  else if (nm == "Kx") { src = st->wsKx.as<double>(); n = std::min<int64_t>(capacity, (int64_t)st->wsKx.bytes / 8); }
+  else if (nm == "root") { src = st->wsRoot.as<double>(); n = std::min<int64_t>(capacity, (int64_t)st->wsRoot.bytes / 8); }
+  else if (nm == "mu") { src = st->wsMu.as<double>(); n = std::min<int64_t>(capacity, (int64_t)st->wsMu.bytes / 8); }
+  else if (nm == "cell_lo") { src = st->cell_lo.as<double>(); n = (int64_t)st->cap * st->od.n_obj * (st->cells_shared ? 1 : st->S); }
+  else if (nm == "cell_up") { src = st->cell_up.as<double>(); n = (int64_t)st->cap * st->od.n_obj * (st->cells_shared ? 1 : st->S); }
+  else if (nm == "samples_b") { src = st->samples_b.as<double>(); n = (int64_t)st->S * st->nb * st->M; }
+  else if (nm == "obj_b") { src = st->obj_b.as<double>(); n = (int64_t)st->S * st->nb * st->od.n_obj; }
+  else if (nm == "ncells" || nm == "front_idx") {
+    // integer buffers are returned through the same byte pipe (caller views them as int32)
+    const void* isrc = (nm == "ncells") ? st->ncells.p : st->front_idx.p;
+    int64_t bytes = (nm == "ncells") ? (int64_t)(st->cells_shared ? 1 : st->S) * 4 : (int64_t)st->S * st->cap * 4;
+    if (bytes > capacity * 8) { bo_set_error("debug_get: capacity too small"); return BO_ERR_INVALID; }
+    CUDA_CHECK_RET(cudaMemcpyAsync(out_dev, isrc, bytes, cudaMemcpyDeviceToDevice, s));
+    if (n_written) *n_written = bytes / 4;
+    return BO_OK;
+  } else { bo_set_error("debug_get: unknown buffer '%s'", name); return BO_ERR_INVALID; }
+  if (n > capacity) { bo_set_error("debug_get: capacity %lld < %lld", (long long)capacity, (long long)n); return BO_ERR_INVALID; }
+  CUDA_CHECK_RET(cudaMemcpyAsync(out_dev, src, n * 8, cudaMemcpyDeviceToDevice, s));
+  if (n_written) *n_written = n;
+  return BO_OK;
+}

@@ -1,0 +1,305 @@
+// K3 (GEMM part): FP64 tensor-pipe (DMMA m8n8k4) "NT" GEMMs.
+//
+//   gemm_nt_kernel        C[m,n] = alpha * sum_k A[m,k] B[n,k] + beta * C        (set-up work:
+//                         blocked Cholesky updates, inverse root, baseline / pruning posteriors)
+//   posterior_gemm_kernel the hot loop of AcquisitionFunction.forward: V = K(X*,X) L^-T against
+//                         the cached LOWER-TRIANGULAR inverse root, fused with the reductions the
+//                         posterior needs from V, so V itself never reaches HBM:
+//                           Gqq[batch] = V_q V_q^T   (q x q block of K*X (K+s2 I)^-1 KX*)
+//                           W          = V_q V_b^T   (cross block against the cached baseline rows)
+//                           mu_raw     = K*X alpha
+//
+// This is what gpytorch's DefaultPredictionStrategy.exact_predictive_covar / exact_predictive_mean
+// compute on CPU with MKL (reached from model.posterior, reference botorch.py:180,223):
+// test_train_covar @ L^-T, then (.) @ (.)^T.  SURVEY.md 2.3 K3 / 8a rows a8.
+//
+// Both operands are K-contiguous ("NT"), so one 16-byte shared-memory load feeds TWO DMMAs
+// (k = 2t and 2t+1 of an 8-wide k group; A and B use the same k permutation).  Tiles are staged
+// with a 3-deep cp.async (LDGSTS) pipeline; row stride 24 doubles (192 B) makes every quarter-warp
+// 128-bit fragment load hit 8 distinct 16-byte bank groups.
+#include "common.cuh"
+
+#define GK 16       // k per pipeline stage
+#define GLDS 24     // smem row stride in doubles
+
+template <int ROWS, int NTHREADS>
+__device__ __forceinline__ void load_tile_async(double* s, const double* __restrict__ g, int ld, int row0,
+                                                int rows_valid, int k0, int tid) {
+#pragma unroll
+  for (int c = tid; c < ROWS * 8; c += NTHREADS) {
+    int r = c >> 3, ch = c & 7;
+    bool p = (row0 + r) < rows_valid;
+    const double* src = g + (size_t)(p ? (row0 + r) : 0) * ld + k0 + ch * 2;
+    cp_async16(s + r * GLDS + ch * 2, src, p);
+  }
+}
+
+template <int TM, int TN>
+__device__ __forceinline__ void mma_stage(const double* As, const double* Bs, int wm0, int wn0, int g, int t,
+                                          double (&acc)[TM][TN][2]) {
+#pragma unroll
+  for (int kg = 0; kg < 2; ++kg) {
+    double2 af[TM], bf[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+      af[i] = *reinterpret_cast<const double2*>(As + (wm0 + i * 8 + g) * GLDS + kg * 8 + 2 * t);
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+      bf[j] = *reinterpret_cast<const double2*>(Bs + (wn0 + j * 8 + g) * GLDS + kg * 8 + 2 * t);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        mma_884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+        mma_884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic NT GEMM: 64 x 64 tile, 4 warps (2 x 2), warp tile 32 x 32
+// ------------------------------------------------------------------------------------------------
+#define G1_BM 64
+#define G1_BN 64
+#define G1_ST 3
+
+__global__ void __launch_bounds__(128)
+gemm_nt_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
+               const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc, int lower_only) {
+  extern __shared__ __align__(16) double gsm[];
+  const int m0 = blockIdx.y * G1_BM, n0 = blockIdx.x * G1_BN;
+  if (lower_only && n0 > m0 + G1_BM - 1) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 32;
+  double* As = gsm;
+  double* Bs = gsm + G1_ST * G1_BM * GLDS;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (k + GK - 1) / GK;
+  for (int s = 0; s < G1_ST - 1; ++s) {
+    if (s < nk) {
+      load_tile_async<G1_BM, 128>(As + s * G1_BM * GLDS, A, lda, m0, m, s * GK, tid);
+      load_tile_async<G1_BN, 128>(Bs + s * G1_BN * GLDS, B, ldb, n0, n, s * GK, tid);
+    }
+    cp_async_commit();
+  }
+  for (int ks = 0; ks < nk; ++ks) {
+    cp_async_wait<G1_ST - 2>();
+    __syncthreads();
+    int nx = ks + G1_ST - 1;
+    if (nx < nk) {
+      int st = nx % G1_ST;
+      load_tile_async<G1_BM, 128>(As + st * G1_BM * GLDS, A, lda, m0, m, nx * GK, tid);
+      load_tile_async<G1_BN, 128>(Bs + st * G1_BN * GLDS, B, ldb, n0, n, nx * GK, tid);
+    }
+    cp_async_commit();
+    int st = ks % G1_ST;
+    mma_stage<4, 4>(As + st * G1_BM * GLDS, Bs + st * G1_BN * GLDS, wm0, wn0, g, t, acc);
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = m0 + wm0 + i * 8 + g;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int c = n0 + wn0 + j * 8 + 2 * t + e;
+        if (c >= n) continue;
+        if (lower_only && c > r) continue;
+        double v = alpha * acc[i][j][e];
+        if (beta != 0.0) v += beta * C[(size_t)r * ldc + c];
+        C[(size_t)r * ldc + c] = v;
+      }
+  }
+}
+
+int launch_gemm_nt(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+                   double* C, int ldc, bool lower_only, cudaStream_t s, LaunchCounter* lc) {
+  if (m <= 0 || n <= 0) return BO_OK;
+  if ((lda % 2) || (ldb % 2) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) {
+    bo_set_error("gemm_nt: operands must be 16-byte aligned with even leading dimensions");
+    return BO_ERR_INVALID;
+  }
+  // k is rounded up to a multiple of 16 inside the kernel: callers guarantee zero padding up to ld.
+  if (((k + GK - 1) / GK) * GK > lda || ((k + GK - 1) / GK) * GK > ldb) {
+    bo_set_error("gemm_nt: k=%d padded to 16 exceeds lda=%d / ldb=%d", k, lda, ldb);
+    return BO_ERR_INVALID;
+  }
+  static bool attr_set = false;
+  size_t smem = (size_t)G1_ST * (G1_BM + G1_BN) * GLDS * sizeof(double);
+  if (!attr_set) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((n + G1_BN - 1) / G1_BN, (m + G1_BM - 1) / G1_BM);
+  gemm_nt_kernel<<<grid, 128, smem, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// posterior GEMM: 128-row CTA owns whole q-batches and walks every 128-column block of L^-1
+// (triangular: k only up to the block's last row) plus the dense extra rows [V_b ; alpha].
+// 8 warps (2 x 4), warp tile 64 x 32 -> 32 DMMA accumulator pairs per thread.
+// ------------------------------------------------------------------------------------------------
+#define PG_BM 128
+#define PG_BN 128
+#define PG_ST 3
+#define PG_THREADS 256
+#define PG_VLD (PG_BN + 1)
+#define PG_MAXITEMS 5  // ceil(max_q items / 256): q=16 -> 8 batches * 136 pairs = 1088
+
+size_t posterior_gemm_smem_bytes() {
+  size_t pipe = (size_t)PG_ST * (PG_BM + PG_BN) * GLDS * sizeof(double);
+  size_t stage = (size_t)PG_BM * PG_VLD * sizeof(double);
+  return pipe > stage ? pipe : stage;
+}
+
+__global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmArgs a) {
+  extern __shared__ __align__(16) double psm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+  const int q = a.q;
+  const int nbat_cta = PG_BM / q;           // whole q-batches per CTA
+  const int rows_cta = nbat_cta * q;
+  const int row0 = blockIdx.x * rows_cta;
+  const int rows_valid = min(a.rows, row0 + rows_cta);  // rows >= rows_valid are zero-filled
+  const int npairs = q * (q + 1) / 2;
+  const int nitems = nbat_cta * npairs;
+
+  double* As = psm;
+  double* Bs = psm + PG_ST * PG_BM * GLDS;
+  double* Vs = psm;  // reused after the pipeline drains
+
+  double gacc[PG_MAXITEMS];
+#pragma unroll
+  for (int i = 0; i < PG_MAXITEMS; ++i) gacc[i] = 0.0;
+
+  const int n_tri_blocks = a.Nr / PG_BN;
+  const int n_ext_blocks = (a.n_ext + PG_BN - 1) / PG_BN;
+  const int kfull = a.ldk;  // multiple of 16, zero padded
+
+  for (int jb = 0; jb < n_tri_blocks + n_ext_blocks; ++jb) {
+    const bool tri = jb < n_tri_blocks;
+    const int n0 = tri ? jb * PG_BN : (jb - n_tri_blocks) * PG_BN;  // first row of the B operand block
+    const double* Bg = tri ? a.Linv : a.Ext;
+    // L^-1 rows n0..n0+127 are zero beyond column n0+127
+    const int kmax = tri ? min(kfull, n0 + PG_BN) : kfull;
+    const int nk = (kmax + GK - 1) / GK;
+    const int brow_valid = tri ? a.Nr : a.n_ext;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int s = 0; s < PG_ST - 1; ++s) {
+      if (s < nk) {
+        load_tile_async<PG_BM, PG_THREADS>(As + s * PG_BM * GLDS, a.Kx, a.ldk, row0, rows_valid, s * GK, tid);
+        load_tile_async<PG_BN, PG_THREADS>(Bs + s * PG_BN * GLDS, Bg, a.ldk, n0, brow_valid, s * GK, tid);
+      }
+      cp_async_commit();
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+      cp_async_wait<PG_ST - 2>();
+      __syncthreads();
+      int nx = ks + PG_ST - 1;
+      if (nx < nk) {
+        int st = nx % PG_ST;
+        load_tile_async<PG_BM, PG_THREADS>(As + st * PG_BM * GLDS, a.Kx, a.ldk, row0, rows_valid, nx * GK, tid);
+        load_tile_async<PG_BN, PG_THREADS>(Bs + st * PG_BN * GLDS, Bg, a.ldk, n0, brow_valid, nx * GK, tid);
+      }
+      cp_async_commit();
+      int st = ks % PG_ST;
+      mma_stage<8, 4>(As + st * PG_BM * GLDS, Bs + st * PG_BN * GLDS, wm0, wn0, g, t, acc);
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // pipeline drained: stage buffers are free
+
+    // stage the V tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int r = wm0 + i * 8 + g, c = wn0 + j * 8 + 2 * t;
+        Vs[r * PG_VLD + c] = acc[i][j][0];
+        Vs[r * PG_VLD + c + 1] = acc[i][j][1];
+      }
+    __syncthreads();
+
+    if (tri) {
+      // Gqq[batch][i][j] += sum_c V[i][c] V[j][c]   (padding columns of L^-1 are zero)
+#pragma unroll
+      for (int it = 0; it < PG_MAXITEMS; ++it) {
+        int item = tid + it * PG_THREADS;
+        if (item < nitems) {
+          int bat = item / npairs, p = item % npairs;
+          int i = 0, rem = p;  // p -> (i <= j) in row-major upper-triangular order
+          while (rem >= q - i) { rem -= q - i; ++i; }
+          int j = i + rem;
+          const double* vi = Vs + (bat * q + i) * PG_VLD;
+          const double* vj = Vs + (bat * q + j) * PG_VLD;
+          double s = 0.0;
+#pragma unroll 8
+          for (int c = 0; c < PG_BN; ++c) s = fma(vi[c], vj[c], s);
+          gacc[it] += s;
+        }
+      }
+    } else {
+      const int e0 = n0;
+      for (int idx = tid; idx < rows_cta * PG_BN; idx += PG_THREADS) {
+        int r = idx / PG_BN, c = idx % PG_BN;
+        int e = e0 + c;
+        if (row0 + r < rows_valid && e < a.n_ext) {
+          double v = Vs[r * PG_VLD + c];
+          if (e < a.n_ext - 1) a.W[(size_t)(row0 + r) * a.ldw + e] = v;
+          else a.mu_raw[row0 + r] = v;
+        }
+      }
+    }
+    __syncthreads();  // Vs is about to be overwritten by the next block's prologue loads
+  }
+
+#pragma unroll
+  for (int it = 0; it < PG_MAXITEMS; ++it) {
+    int item = tid + it * PG_THREADS;
+    if (item < nitems) {
+      int bat = item / npairs, p = item % npairs;
+      int gb = blockIdx.x * nbat_cta + bat;
+      if (gb * q < a.rows) {
+        int i = 0, rem = p;
+        while (rem >= q - i) { rem -= q - i; ++i; }
+        int j = i + rem;
+        a.Gqq[((size_t)gb * q + i) * q + j] = gacc[it];
+        a.Gqq[((size_t)gb * q + j) * q + i] = gacc[it];
+      }
+    }
+  }
+}
+
+int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  if (a.rows <= 0) return BO_OK;
+  if (a.q < 1 || a.q > BO_MAX_Q || a.rows % a.q != 0) { bo_set_error("posterior_gemm: bad q"); return BO_ERR_INVALID; }
+  if (a.ldk % GK != 0 || a.Nr % PG_BN != 0) { bo_set_error("posterior_gemm: padding violated"); return BO_ERR_INVALID; }
+  static bool attr_set = false;
+  size_t smem = posterior_gemm_smem_bytes();
+  if (!attr_set) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int nbat_cta = PG_BM / a.q;
+  int nbat = a.rows / a.q;
+  int grid = (nbat + nbat_cta - 1) / nbat_cta;
+  posterior_gemm_kernel<<<grid, PG_THREADS, smem, s>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}

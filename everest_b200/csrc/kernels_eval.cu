@@ -1,0 +1,280 @@
+// K1 + K2: input transforms / packing and the fused cross-covariance kernel.
+//
+// Replaces (reference, CPU float64 via BoTorch/GPyTorch):
+//   * Normalize / OneHotToNumeric input transforms built in bofire/surrogates/utils.py:103-164 and
+//     surrogates/mixed_single_task_gp.py:82-88  -> prep_points_kernel
+//   * kernel evaluation K(X*, X) for RBF / Matern / Hamming / Tanimoto and Scale/Add/Mul trees
+//     (bofire/kernels/mapper.py:31-253, kernels/categorical.py:43-70,
+//     fingerprint_kernels/base_fingerprint_kernel.py:36-53)     -> crosscov_kernel
+//
+// crosscov_kernel: 64 x 64 output tile per CTA, 8 warps, each warp a 16 x 32 sub-tile made of
+// 2 x 4 DMMA m8n8k4 accumulators for the a.b contraction of continuous leaves (FP64 tensor pipe);
+// Tanimoto uses AND + POPC over bit-packed words, Hamming compares integer codes.  Distances,
+// lengthscales (pre-divided coordinates), outputscales (term coefficients) and the kernel function
+// are applied in the same pass; HBM traffic is one 8-byte store per element.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// prep: one warp per point
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_points_kernel(ModelD md, const double* __restrict__ X, int n, int d, PrepD prep) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double* x = X + (size_t)warp * d;
+  for (int l = 0; l < md.n_leaves; ++l) {
+    const LeafD& L = md.leaf[l];
+    if (L.kind <= BO_LEAF_MATERN52) {
+      double* o = prep.Xs[l] + (size_t)warp * L.dpad;
+      double acc = 0.0;
+      for (int k = lane; k < L.dpad; k += 32) {
+        double u = 0.0;
+        if (k < L.nd) {
+          double t = (x[L.col[k]] - L.in_off[k]) / L.in_scl[k];
+          u = (t - L.center[k]) / L.ls[k];
+        }
+        o[k] = u;
+        acc = fma(u, u, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) prep.n2[l][warp] = acc;
+    } else if (L.kind == BO_LEAF_HAMMING) {
+      for (int f = lane; f < L.nd; f += 32) {
+        int s = L.col[f], c = L.card[f];
+        int best = 0;
+        double bv = x[s];
+        for (int j = 1; j < c; ++j) {
+          double v = x[s + j];
+          if (v > bv) { bv = v; best = j; }
+        }
+        prep.codes[l][(size_t)warp * L.nd + f] = best;
+      }
+    } else {  // Tanimoto: pack 64 columns per word with two ballots
+      int total = 0;
+      for (int w = 0; w < L.dpad; ++w) {
+        int k0 = w * 64 + lane, k1 = k0 + 32;
+        bool b0 = (k0 < L.nd) && (x[L.col[k0]] != 0.0);
+        bool b1 = (k1 < L.nd) && (x[L.col[k1]] != 0.0);
+        unsigned lo = __ballot_sync(0xffffffffu, b0);
+        unsigned hi = __ballot_sync(0xffffffffu, b1);
+        u64 word = ((u64)hi << 32) | (u64)lo;
+        total += __popcll(word);
+        if (lane == 0) prep.bits[l][(size_t)warp * L.dpad + w] = word;
+      }
+      if (lane == 0) prep.pc[l][warp] = total;
+    }
+  }
+}
+
+int launch_prep_points(const ModelD& md, const double* X, int n, int d, PrepD prep, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  int threads = 256;
+  int blocks = (n * 32 + threads - 1) / threads;
+  prep_points_kernel<<<blocks, threads, 0, s>>>(md, X, n, d, prep);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// crosscov
+// ------------------------------------------------------------------------------------------------
+#define CC_TILE 64
+#define CC_KC 32
+#define CC_LDS 36  // CC_KC + 4 -> (stride mod 16) == 4: conflict-free 64-bit fragment loads
+
+struct ColSides { LeafSide s[BO_MAX_LEAVES]; };
+
+__global__ void __launch_bounds__(256, 2)
+crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __restrict__ out, int ld, int same_set) {
+  __shared__ __align__(16) double smem[2 * CC_TILE * CC_LDS];
+  double* As = smem;
+  double* Bs = smem + CC_TILE * CC_LDS;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp & 3, wc = warp >> 2;  // 4 row groups of 16, 2 col groups of 32
+  const int row0 = blockIdx.y * CC_TILE, col0 = blockIdx.x * CC_TILE;
+  const int n_rows = rows.n;
+
+  double total[16], prod[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) total[e] = 0.0;
+
+  for (int term = 0; term < md.n_terms; ++term) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) prod[e] = md.coef[term];
+    for (int f = 0; f < md.nfac[term]; ++f) {
+      const int l = md.fac[term][f];
+      const LeafD& L = md.leaf[l];
+      double lv[16];
+      if (L.kind <= BO_LEAF_MATERN52) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double* Ag = rows.Xs[l];
+        const double* Bg = cols.s[l].Xs;
+        for (int k0 = 0; k0 < L.dpad; k0 += CC_KC) {
+          const int kc = min(CC_KC, L.dpad - k0);
+          __syncthreads();
+          for (int idx = tid; idx < CC_TILE * CC_KC; idx += 256) {
+            int r = idx / CC_KC, k = idx % CC_KC;
+            double va = 0.0, vb = 0.0;
+            if (k < kc) {
+              if (row0 + r < n_rows) va = Ag[(size_t)(row0 + r) * L.dpad + k0 + k];
+              if (col0 + r < n_cols) vb = Bg[(size_t)(col0 + r) * L.dpad + k0 + k];
+            }
+            As[r * CC_LDS + k] = va;
+            Bs[r * CC_LDS + k] = vb;
+          }
+          __syncthreads();
+          for (int kk = 0; kk < kc; kk += 4) {
+            double a[2], b[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = As[(wr * 16 + i * 8 + g) * CC_LDS + kk + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(wc * 32 + j * 8 + g) * CC_LDS + kk + t];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
+        }
+        const double* n2a = rows.n2[l];
+        const double* n2b = cols.s[l].n2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          int r = row0 + wr * 16 + i * 8 + g;
+          double na = (r < n_rows) ? n2a[r] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int c = col0 + wc * 32 + j * 8 + 2 * t + e;
+              double nb = (c < n_cols) ? n2b[c] : 0.0;
+              double stat = fmax(na + nb - 2.0 * acc[i][j][e], 0.0);
+              if (same_set && r == c) stat = 0.0;
+              lv[(i * 4 + j) * 2 + e] = leaf_value_from_stat(L.kind, stat);
+            }
+        }
+      } else if (L.kind == BO_LEAF_HAMMING) {
+        int* Ac = reinterpret_cast<int*>(smem);
+        int* Bc = Ac + CC_TILE * BO_MAX_GROUPS;
+        __syncthreads();
+        for (int idx = tid; idx < CC_TILE * L.nd; idx += 256) {
+          int r = idx / L.nd, f = idx % L.nd;
+          Ac[r * BO_MAX_GROUPS + f] = (row0 + r < n_rows) ? rows.codes[l][(size_t)(row0 + r) * L.nd + f] : 0;
+          Bc[r * BO_MAX_GROUPS + f] = (col0 + r < n_cols) ? cols.s[l].codes[(size_t)(col0 + r) * L.nd + f] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
+              double acc = 0.0;
+              for (int f = 0; f < L.nd; ++f)
+                acc += (Ac[rl * BO_MAX_GROUPS + f] != Bc[cl * BO_MAX_GROUPS + f]) ? L.wls[f] : 0.0;
+              lv[(i * 4 + j) * 2 + e] = exp(-(acc / (double)L.nd));
+            }
+      } else {  // Tanimoto
+        const int WC = 16;  // words per chunk; row stride WC + 1 words keeps AND/POPC loads conflict-light
+        u64* Ab = reinterpret_cast<u64*>(smem);
+        u64* Bb = Ab + CC_TILE * (WC + 1);
+        int dot[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dot[e] = 0;
+        for (int w0 = 0; w0 < L.dpad; w0 += WC) {
+          const int wn = min(WC, L.dpad - w0);
+          __syncthreads();
+          for (int idx = tid; idx < CC_TILE * WC; idx += 256) {
+            int r = idx / WC, w = idx % WC;
+            u64 va = 0, vb = 0;
+            if (w < wn) {
+              if (row0 + r < n_rows) va = rows.bits[l][(size_t)(row0 + r) * L.dpad + w0 + w];
+              if (col0 + r < n_cols) vb = cols.s[l].bits[(size_t)(col0 + r) * L.dpad + w0 + w];
+            }
+            Ab[r * (WC + 1) + w] = va;
+            Bb[r * (WC + 1) + w] = vb;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
+                int s = 0;
+                for (int w = 0; w < wn; ++w) s += __popcll(Ab[rl * (WC + 1) + w] & Bb[cl * (WC + 1) + w]);
+                dot[(i * 4 + j) * 2 + e] += s;
+              }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          int r = row0 + wr * 16 + i * 8 + g;
+          int pa = (r < n_rows) ? rows.pc[l][r] : 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int c = col0 + wc * 32 + j * 8 + 2 * t + e;
+              int pb = (c < n_cols) ? cols.s[l].pc[c] : 0;
+              lv[(i * 4 + j) * 2 + e] = tanimoto_value(dot[(i * 4 + j) * 2 + e], pa, pb);
+            }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) prod[e] *= lv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) total[e] += prod[e];
+  }
+
+  // store (two adjacent doubles per thread -> 16-byte stores); zero the padding columns [n_cols, ld)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int r = row0 + wr * 16 + i * 8 + g;
+    if (r >= n_rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = col0 + wc * 32 + j * 8 + 2 * t;
+      double v0 = (c < n_cols) ? total[(i * 4 + j) * 2] : 0.0;
+      double v1 = (c + 1 < n_cols) ? total[(i * 4 + j) * 2 + 1] : 0.0;
+      if (c + 1 < ld) {
+        *reinterpret_cast<double2*>(out + (size_t)r * ld + c) = make_double2(v0, v1);
+      } else if (c < ld) {
+        out[(size_t)r * ld + c] = v0;
+      }
+    }
+  }
+}
+
+int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_are_train, int n_cols, double* out,
+                    int ld, bool same_set, cudaStream_t s, LaunchCounter* lc) {
+  if (rows.n <= 0 || n_cols <= 0) return BO_OK;
+  if (ld % 2 != 0) { bo_set_error("crosscov: ld must be even"); return BO_ERR_INVALID; }
+  ColSides cs;
+  for (int l = 0; l < BO_MAX_LEAVES; ++l) {
+    if (l < md.n_leaves) {
+      if (cols_are_train) {
+        const LeafD& L = md.leaf[l];
+        cs.s[l].Xs = L.Xs; cs.s[l].n2 = L.n2; cs.s[l].codes = L.codes; cs.s[l].bits = L.bits; cs.s[l].pc = L.pc;
+      } else {
+        cs.s[l].Xs = colsOrTrain.Xs[l]; cs.s[l].n2 = colsOrTrain.n2[l]; cs.s[l].codes = colsOrTrain.codes[l];
+        cs.s[l].bits = colsOrTrain.bits[l]; cs.s[l].pc = colsOrTrain.pc[l];
+      }
+    } else {
+      cs.s[l] = LeafSide{nullptr, nullptr, nullptr, nullptr, nullptr};
+    }
+  }
+  dim3 grid((ld + CC_TILE - 1) / CC_TILE, (rows.n + CC_TILE - 1) / CC_TILE);
+  crosscov_kernel2<<<grid, 256, 0, s>>>(md, rows, cs, n_cols, out, ld, same_set ? 1 : 0);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}

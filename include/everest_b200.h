@@ -1,0 +1,179 @@
+/*
+ * everest_b200 -- C ABI of the B200-native acquisition-evaluation path.
+ *
+ * The reference (BoFire, /root/reference) is pure Python over BoTorch and has NO native
+ * interface for this path; each entry point below therefore cites the Python call it
+ * replaces.  Plain pointers and sizes only; row-major float64 everywhere; no torch types.
+ *
+ * Pointer convention: `*_dev` arguments are CUDA device pointers (the host side hands in
+ * `tensor.data_ptr()`), everything else is host memory.  `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  All functions return BO_OK (0) or a negative error
+ * code and never throw; `bo_last_error()` returns a message for the calling thread.
+ * Numerical failure is reported LAPACK-style through `info` outputs (0 = fine, k > 0 =
+ * first non-positive pivot k), mirroring BoTorch's NotPSDError-driven fallbacks
+ * ("Failure detection").
+ */
+#ifndef EVEREST_B200_H
+#define EVEREST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BO_OK 0
+#define BO_ERR_INVALID -1   /* bad argument / unsupported configuration (Python: ValueError) */
+#define BO_ERR_CUDA -2      /* CUDA runtime failure */
+#define BO_ERR_NOT_PSD -3   /* matrix not positive definite after jitter escalation (NotPSDError) */
+#define BO_ERR_STATE -4     /* call order violated (e.g. forward before prepare) */
+
+#define BO_MAX_LEAVES 8
+#define BO_MAX_TERMS 8
+#define BO_MAX_FACTORS 4
+#define BO_MAX_Q 16
+#define BO_MAX_OBJECTIVES 8
+#define BO_MAX_CONSTRAINTS 8
+
+/* Leaf kernels: bofire/kernels/mapper.py:31-69 (RBF, Matern), :206-253 + kernels/categorical.py:43-70
+ * (Hamming on one-hot groups), :191-203 + fingerprint_kernels/base_fingerprint_kernel.py:36-53 (Tanimoto). */
+enum bo_leaf_kind {
+  BO_LEAF_RBF = 0,
+  BO_LEAF_MATERN12 = 1,
+  BO_LEAF_MATERN32 = 2,
+  BO_LEAF_MATERN52 = 3,
+  BO_LEAF_HAMMING = 4,
+  BO_LEAF_TANIMOTO = 5
+};
+
+typedef struct {
+  int32_t kind;           /* bo_leaf_kind */
+  int32_t n_dims;         /* RBF/Matern: active columns; Hamming: one-hot groups; Tanimoto: bit columns */
+  const int32_t* dims;    /* [n_dims] column index (Hamming: START column of each group) */
+  const int32_t* cardinality; /* Hamming only: [n_dims] group sizes */
+  const double* lengthscale;  /* [n_ls]; NULL for Tanimoto */
+  int32_t n_ls;           /* 1 = isotropic, n_dims = ARD (Hamming: first n_dims entries are used) */
+} bo_kernel_leaf;
+
+/* A Scale/Additive/Multiplicative tree (kernels/mapper.py:126-188, surrogates/mixed_tanimoto_gp.py:101-215)
+ * flattened by the host into  K = sum_t coef_t * prod_{l in factors_t} leaf_l. */
+typedef struct {
+  double coef;
+  int32_t n_factors;
+  int32_t factors[BO_MAX_FACTORS];
+} bo_kernel_term;
+
+/* One single-output exact GP (SingleTaskGPSurrogate._fit, surrogates/single_task_gp.py:39-71):
+ * Normalize input transform on selected columns, Standardize outcome transform, constant mean,
+ * homoskedastic noise.  M of these form the ModelListGP (botorch_surrogates.py:124-128). */
+typedef struct {
+  int32_t n_leaves;
+  const bo_kernel_leaf* leaves;
+  int32_t n_terms;
+  const bo_kernel_term* terms;
+  const double* in_offset; /* [d] x' = (x - in_offset) / in_scale ; 0 / 1 on untransformed columns */
+  const double* in_scale;  /* [d] */
+  double mean_const;       /* constant mean in standardised outcome space */
+  double noise;            /* noise variance in standardised outcome space */
+  double y_mean, y_std;    /* Standardize(m=1) */
+  const double* y;         /* [N] raw training targets */
+} bo_output_model;
+
+typedef struct {
+  int32_t N, d, M;
+  const double* X_train;   /* [N, d] host, BoFire-transformed input space (one-hot / 0-1 fingerprint columns as doubles) */
+  const bo_output_model* outputs; /* [M] */
+} bo_state_config;
+
+/* Objective callables as an op table (utils/torch_tools.py:384-450). p0..p2 by kind:
+ *   MAX/MIN: lower_bound, upper_bound        CLOSE_TO_TARGET: target_value, exponent
+ *   MIN_SIGMOID/MAX_SIGMOID: steepness, tp   TARGET: target_value, tolerance, steepness */
+enum bo_objective_kind {
+  BO_OBJ_MAX = 0, BO_OBJ_MIN = 1, BO_OBJ_CLOSE_TO_TARGET = 2,
+  BO_OBJ_MIN_SIGMOID = 3, BO_OBJ_MAX_SIGMOID = 4, BO_OBJ_TARGET = 5
+};
+typedef struct { int32_t kind; int32_t out_idx; double p0, p1, p2; double w; } bo_objective_op;
+
+/* Output constraints (constrained_objective2botorch, utils/torch_tools.py:258-337):
+ * c(y) = sign * (y[out_idx] - tp), feasible iff c <= 0, smoothed weight sigmoid(-c / eta). */
+typedef struct { int32_t out_idx; double sign; double tp; double eta; } bo_constraint_op;
+
+enum bo_combine { BO_COMBINE_SINGLE = 0, BO_COMBINE_ADDITIVE = 1, BO_COMBINE_MULTIPLICATIVE = 2 };
+
+typedef struct bo_state bo_state;
+
+int bo_version(void);
+const char* bo_last_error(void);
+
+/* Replaces the model construction the acquisition path consumes: BotorchSurrogates.compatibilize ->
+ * ModelListGP (botorch_surrogates.py:79-128) + the GPyTorch prediction-strategy caches.  Copies
+ * everything; the config may be freed after the call. */
+int bo_state_create(const bo_state_config* cfg, bo_state** out);
+void bo_state_destroy(bo_state* st);
+
+/* Training Gram K + sigma^2 I, psd-safe Cholesky (jitter 1e-8 .. 1e-3), mean cache alpha and the
+ * inverse root L^-1 -- what gpytorch's DefaultPredictionStrategy caches on the first
+ * model.posterior() call (reached from botorch.py:180,223).  info[M]: 0 or first bad pivot;
+ * jitter[M]: diagonal jitter that was needed. */
+int bo_state_factorize(bo_state* st, int32_t* info, double* jitter, void* stream);
+
+/* model.posterior(X, observation_noise) marginals: BotorchStrategy._predict (botorch.py:174-194).
+ * X_dev [n, d]; mean_dev, var_dev [n, M] in the original outcome space. */
+int bo_posterior_marginal(bo_state* st, const double* X_dev, int32_t n, int32_t observation_noise,
+                          double* mean_dev, double* var_dev, void* stream);
+
+/* Joint posterior of one point set (used by tests and by acquisition set-up): mean_dev [n, M],
+ * cov_dev [M, n, n]. */
+int bo_posterior_joint(bo_state* st, const double* X_dev, int32_t n, double* mean_dev, double* cov_dev,
+                       void* stream);
+
+/* prune_inferior_points_multi_objective as called by qNoisyExpectedHypervolumeImprovement(
+ * prune_baseline=True) (qnehvi.py:39-51): joint posterior samples at X [n, d] with base samples
+ * z_dev [S, n, M]; counts_dev[n] receives, per point, the number of samples in which it is
+ * non-dominated and strictly better than ref_point (host keeps counts > 0). */
+int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S,
+                    const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                    const double* ref_point, int32_t* counts_dev, int32_t* info, void* stream);
+
+/* qNoisyExpectedHypervolumeImprovement.__init__ after pruning (NoisyExpectedHypervolumeMixin.
+ * _set_cell_bounds): posterior at X_baseline, cached root baseline_L, S baseline samples from
+ * zb_dev [S, n_b, M], objective transform, per-sample non-dominated front + box decomposition.
+ * Also serves MoboStrategy (mobo.py:72-90).  info[M]; returns max cells per sample in *max_cells. */
+int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b, const double* zb_dev, int32_t S,
+                     const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                     const double* ref_point, int32_t* info, int32_t* max_cells, void* stream);
+
+/* qExpectedHypervolumeImprovement with a fixed partitioning of the observed front (qehvi.py:37-77):
+ * Yobj_dev [n, n_obj] objective values (maximisation frame) of the observations. */
+int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, int32_t S,
+                    const bo_objective_op* obj, int32_t n_obj, const double* ref_point, int32_t* max_cells,
+                    void* stream);
+
+/* qLogExpectedImprovement as built by SoboStrategy._get_acqfs (sobo.py:51-90). */
+int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
+                     double best_f, void* stream);
+
+/* AcquisitionFunction.forward(X[b, q, d]) -> [b]  (called from calc_acquisition botorch.py:223,
+ * optimize_acqf's raw-sample screen, optimize_acqf_discrete botorch.py:461).  zq_dev [S, q, M] are the
+ * base samples of the q new points.  info_dev[b] (may be NULL): 0, or 1 if the conditional
+ * q x q root needed more jitter than 1e-3 (BoTorch would fall back to joint sampling). */
+int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                    double* out_dev, int32_t* info_dev, void* stream);
+
+/* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values. */
+int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
+                         double* out_host, void* stream);
+
+/* Introspection for tests: copies internal device buffers to the given device pointers. */
+int bo_debug_get(bo_state* st, const char* name, int32_t m, double* out_dev, int64_t capacity, int64_t* n_written,
+                 void* stream);
+/* Kernels launched by this library since the handle was created (bench.py's gpu_launches). */
+int64_t bo_launch_count(const bo_state* st);
+/* Average device time (ms) of the named kernel family in the last forward (CUDA events on the launch stream). */
+int bo_last_timing(const bo_state* st, const char* name, double* ms);
+int bo_set_timing(bo_state* st, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,292 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200 box:
+    python -m pytest tests -m gpu -x -q
+Tolerances: posterior 1e-9 relative (north_star); acquisition values 1e-8 relative (different summation
+order over cells / MC samples); front / box indexing bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from everest_b200 import configs as Cf
+from everest_b200 import kernels as K
+from everest_b200.objectives import (MaximizeObjective, MinimizeObjective, MultiObjective, OutputConstraint,
+                                     ScalarObjective)
+from oracle import bo_oracle as O
+from tests import problems as P
+
+pytestmark = pytest.mark.gpu
+DT = torch.float64
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = a.detach().cpu().to(DT), b.detach().cpu().to(DT)
+    return float(((a - b).abs() / (b.abs() + floor)).max())
+
+
+def small_problem(kind, **kw):
+    if kind == "zdt1":
+        return Cf.zdt1_qnehvi(N=96, S=32, raw=24, d=6, q=3, **kw)
+    if kind == "dtlz2":
+        return Cf.dtlz2_qnehvi(N=70, S=16, raw=12, d=5, m_obj=3, q=2, **kw)
+    if kind == "himmelblau":
+        return Cf.himmelblau_qlogei(N=150, S=64, raw=40)
+    if kind == "mixed":
+        return Cf.mixed_tanimoto_qlogei(N=130, n_bits=200, S=32, n_choices=50)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["zdt1", "dtlz2", "himmelblau", "mixed"])
+def test_factorization_and_posterior(kind):
+    p = small_problem(kind)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    N, ldk = st.N, ((st.N + 15) // 16) * 16
+    for m in range(st.M):
+        f = gp._fact[m]
+        Ld = st.debug_get("L", m).view(N, ldk)[:, :N].cpu()
+        assert torch.allclose(Ld, f["L"], rtol=1e-9, atol=1e-11), kind
+        Li = st.debug_get("Linv", m).view(N, ldk)[:, :N].cpu()
+        scale = float(f["Linv"].abs().max())
+        assert float((Li - f["Linv"]).abs().max()) <= 1e-9 * scale
+        al = st.debug_get("alpha", m).cpu()
+        assert float((al - f["alpha"]).abs().max()) <= 1e-8 * float(f["alpha"].abs().max())
+    Xq = Cf.candidates(p, 9).reshape(-1, p["d"])
+    mean_o, cov_o = gp.posterior(Xq)
+    mean_d, cov_d = st.posterior_joint(Xq)
+    assert rel_err(mean_d, mean_o, floor=1e-6) < 1e-9
+    vmax = float(cov_o.diagonal(dim1=-1, dim2=-2).abs().max())
+    assert float((cov_d.cpu() - cov_o).abs().max()) < 1e-9 * vmax
+    mean_m, var_m = st.posterior(Xq, observation_noise=True)
+    mo, co = gp.posterior(Xq, observation_noise=True)
+    assert rel_err(mean_m, mo, floor=1e-6) < 1e-9
+    assert float((var_m.cpu().T - co.diagonal(dim1=-1, dim2=-2)).abs().max()) < 1e-9 * vmax
+
+
+@pytest.mark.parametrize("nu", [0.5, 1.5, 2.5])
+def test_matern_and_scale_kernels(nu):
+    p = Cf.himmelblau_qlogei(N=90, S=16, raw=8)
+    p["outputs"][0]["kernel"] = K.ScaleKernel(K.MaternKernel([0, 1], [0.3, 0.5], nu=nu), outputscale=1.7)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    Xq = Cf.candidates(p, 8).reshape(-1, 2)
+    mo, co = gp.posterior(Xq)
+    md, cd = st.posterior_joint(Xq)
+    assert rel_err(md, mo, floor=1e-6) < 1e-9
+    assert float((cd.cpu() - co).abs().max()) < 1e-9 * float(co.abs().max())
+
+
+@pytest.mark.parametrize("m_obj,n", [(2, 40), (3, 25), (4, 18)])
+def test_box_decomposition_bit_exact(m_obj, n):
+    """Identical objective values in -> identical cell lists out (no arithmetic, only comparisons)."""
+    from everest_b200 import acquisition as A
+
+    p = Cf.dtlz2_qnehvi(N=40, S=8, raw=4, d=m_obj + 2, m_obj=m_obj, q=1)
+    st = Cf.build_state(p)
+    g = torch.Generator().manual_seed(11 + m_obj)
+    Yobj = torch.rand(n, m_obj, dtype=DT, generator=g)
+    Yobj[3] = Yobj[1]  # duplicate point
+    ref = [0.1] * m_obj
+    acq = A.qExpectedHypervolumeImprovement(st, ref, Yobj, p["objective"], mc_samples=8, seed=1)
+    lo = st.debug_get("cell_lo")
+    up = st.debug_get("cell_up")
+    nc = int(st.debug_get("ncells", dtype=torch.int32)[0])
+    cap = lo.numel() // m_obj
+    lo = lo.view(cap, m_obj)[:nc].cpu()
+    up = up.view(cap, m_obj)[:nc].cpu()
+    Pf, _ = O.pareto_front_above_ref(Yobj, torch.tensor(ref, dtype=DT))
+    if m_obj == 2:
+        lo_o, up_o, _ = O.partition_2d(Pf, torch.tensor(ref, dtype=DT))
+    else:
+        lo_o, up_o = O.partition_nd(Pf, torch.tensor(ref, dtype=DT))
+    assert nc == lo_o.shape[0] == acq.max_cells
+    assert torch.equal(lo, lo_o) and torch.equal(up, up_o)
+
+
+@pytest.mark.parametrize("kind", ["zdt1", "dtlz2"])
+def test_qnehvi_prune_cells_and_forward(kind):
+    p = small_problem(kind)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=256)
+    acq_d = Cf.build_acqf(p, st, prune_samples=256)
+    # pruning keeps exactly the same baseline points
+    assert acq_d.prune_idx.cpu().tolist() == acq_o.prune_idx.tolist()
+    assert acq_d.nb == acq_o.nb
+    # cached baseline root and samples
+    ldlb = ((max(acq_o.nb, 1) + 15) // 16) * 16
+    for m in range(st.M):
+        Lb = st.debug_get("baseline_L", m).view(acq_o.nb, ldlb)[:, : acq_o.nb].cpu()
+        assert float((Lb - acq_o.baseline_L[m]).abs().max()) < 1e-8 * float(acq_o.baseline_L[m].abs().max())
+    fb = st.debug_get("samples_b").view(acq_o.S, acq_o.nb, st.M).cpu()
+    assert float((fb - acq_o.samples_b).abs().max()) < 1e-8 * float(acq_o.samples_b.abs().max())
+    # per-sample cells: same count, same front membership, bounds to rounding
+    lo, up, nc = acq_d.cell_bounds()
+    assert nc.tolist() == acq_o.n_cells.tolist()
+    for s in range(acq_o.S):
+        c = int(nc[s])
+        assert torch.allclose(lo[s, :c], acq_o.cell_lower[s, :c], rtol=1e-9, atol=1e-10)
+        fin = torch.isfinite(acq_o.cell_upper[s, :c])
+        assert torch.equal(torch.isfinite(up[s, :c]), fin)
+        assert torch.allclose(up[s, :c][fin], acq_o.cell_upper[s, :c][fin], rtol=1e-9, atol=1e-10)
+    if kind == "zdt1":
+        fi = st.debug_get("front_idx", dtype=torch.int32).view(acq_o.S, acq_o.nb + 1).cpu()
+        for s in range(acq_o.S):
+            k = len(acq_o.fronts[s])
+            assert fi[s, :k].tolist() == acq_o.fronts[s].tolist()  # bit-exact front indexing
+    # forward
+    X = Cf.candidates(p)
+    v_o, parts = acq_o.forward(X, return_parts=True)
+    v_d = acq_d(X.to(st.device))
+    q, nr = p["q"], acq_o.nb + p["q"]
+    root = st.debug_get("root").view(-1)[: X.shape[0] * st.M * q * nr].view(X.shape[0], st.M, q, nr).cpu()
+    bl_o = parts["bl"].permute(1, 0, 2, 3)
+    br_o = parts["br"].permute(1, 0, 2, 3)
+    sc = float(br_o.abs().max())
+    assert float((root[..., : acq_o.nb] - bl_o).abs().max()) < 1e-7 * max(sc, float(bl_o.abs().max()))
+    assert float((root[..., acq_o.nb:] - br_o).abs().max()) < 1e-7 * sc
+    assert int(acq_d.last_info.sum()) == 0 and float(parts["jitter"].abs().sum()) == 0.0
+    scale = float(v_o.abs().max())
+    assert scale > 0
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * scale
+    # batch independence / determinism: evaluating a slice gives bit-identical values
+    v_half = acq_d(X[: X.shape[0] // 2].to(st.device))
+    assert torch.equal(v_half.cpu(), v_d.cpu()[: X.shape[0] // 2])
+    # host-buffer entry point agrees bit for bit with the device-pointer one
+    v_host = acq_d.forward_host(X.numpy())
+    assert np.array_equal(v_host, v_d.cpu().numpy())
+
+
+def test_qnehvi_with_output_constraint_and_pending():
+    from everest_b200 import acquisition as A
+
+    p = Cf.zdt1_qnehvi(N=60, S=24, raw=16, d=5, q=2)
+    # third output used only as a constraint
+    y3 = p["X"][:, 2] + 0.1 * p["X"][:, 3]
+    p["outputs"].append(dict(kernel=K.RBFKernel(list(range(5)), [0.7] * 5), y=y3, noise=1e-3, mean_const=0.1))
+    cons = [OutputConstraint(2, 1.0, 0.6, 0.25)]
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    Xp = Cf.candidates(p, 2)[0]
+    ops = [P.op_to_oracle(o) for o in p["objective"].ops]
+    acq_o = O.QNEHVIOracle(gp, p["ref_point"], p["X"], ops, constraints=[(2, 1.0, 0.6, 0.25)], mc_samples=p["S"],
+                           seed=p["sampler_seed"], prune_baseline=True, prune_samples=128,
+                           prune_seed=p["sampler_seed"] + 7919, X_pending=Xp)
+    acq_d = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], p["X"], p["objective"], constraints=cons,
+                                                   prune_baseline=True, X_pending=Xp, mc_samples=p["S"],
+                                                   seed=p["sampler_seed"], prune_samples=128)
+    assert acq_d.prune_idx.cpu().tolist() == acq_o.prune_idx.tolist()
+    X = Cf.candidates(p)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
+
+
+@pytest.mark.parametrize("kind", ["himmelblau", "mixed"])
+def test_qlogei_forward(kind):
+    p = small_problem(kind)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp)
+    acq_d = Cf.build_acqf(p, st)
+    assert abs(acq_d.best_f - acq_o.best_f) < 1e-9 * max(1.0, abs(acq_o.best_f))
+    X = Cf.candidates(p)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-7 * float(v_o.abs().max())
+
+
+def test_qlogei_q_batch_additive_objective():
+    from everest_b200 import acquisition as A
+
+    p = Cf.zdt1_qnehvi(N=50, S=32, raw=10, d=4, q=3)
+    obj = ScalarObjective([MaximizeObjective(0, w=0.4), MinimizeObjective(1, w=0.6)], "additive")
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    spec = ("additive", [(P.op_to_oracle(o), o.w) for o in obj.ops])
+    acq_o = O.QLogEIOracle(gp, spec, p["X"], mc_samples=32, seed=5)
+    acq_d = A.get_acquisition_function("qLogEI", st, obj, p["X"], mc_samples=32, seed=5)
+    X = Cf.candidates(p)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-7 * float(v_o.abs().max())
+
+
+def test_qehvi_forward():
+    from everest_b200 import acquisition as A
+
+    p = small_problem("zdt1")
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    Yobj = -torch.as_tensor(p["Y"], dtype=DT)
+    acq_o = O.QEHVIOracle(gp, p["ref_point"], Yobj, [P.op_to_oracle(o) for o in p["objective"].ops], mc_samples=32, seed=9)
+    acq_d = A.qExpectedHypervolumeImprovement(st, p["ref_point"], Yobj, p["objective"], mc_samples=32, seed=9)
+    X = Cf.candidates(p, 12)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * max(float(v_o.abs().max()), 1e-12)
+
+
+def test_jitter_on_duplicate_candidates_matches_oracle():
+    """Two identical points in a q-batch make the conditional q x q block singular: both paths must walk
+    the same psd_safe_cholesky jitter ladder."""
+    p = small_problem("zdt1")
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=128)
+    acq_d = Cf.build_acqf(p, st, prune_samples=128)
+    X = Cf.candidates(p, 4).clone()
+    X[1, 1] = X[1, 0]
+    v_o, parts = acq_o.forward(X, return_parts=True)
+    v_d = acq_d(X.to(st.device))
+    assert float(parts["jitter"][:, 1].max()) > 0
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-6 * float(v_o.abs().max())
+
+
+def test_full_size_properties_headline_config():
+    """Config 3 at BASELINE size (N=2000, d=30, q=4, S=512): size-independent properties."""
+    p = Cf.zdt1_qnehvi(raw=1024)
+    st = Cf.build_state(p)
+    N, ldk = st.N, ((st.N + 15) // 16) * 16
+    # Cholesky round trip and inverse-root identity on the device factor
+    for m in range(st.M):
+        Ld = st.debug_get("L", m).view(N, ldk)[:, :N]
+        Li = st.debug_get("Linv", m).view(N, ldk)[:, :N]
+        eye = torch.eye(N, dtype=DT, device=Ld.device)
+        assert float((Li @ Ld - eye).abs().max()) < 1e-8
+        assert float(torch.triu(Ld, 1).abs().max()) == 0.0 and float(torch.triu(Li, 1).abs().max()) == 0.0
+    # interpolation: posterior mean at the training points reproduces y to noise level, variance ~ noise
+    Xt = torch.as_tensor(p["X"][:256])
+    mean, var = st.posterior(Xt)
+    Y = torch.as_tensor(p["Y"][:256])
+    assert float((mean.cpu() - Y).abs().max()) < 5e-2
+    assert float(var.min()) > 0 and float(var.max()) < 1e-2
+    acq = Cf.build_acqf(p, st)
+    X = Cf.candidates(p)
+    v = acq(X.to(st.device))
+    assert bool(torch.isfinite(v).all()) and float(v.min()) >= 0.0 and float(v.max()) > 0.0
+    assert int(acq.last_info.sum()) == 0
+    # batch independence at full size, bit-exact
+    v2 = acq(X[300:700].to(st.device))
+    assert torch.equal(v2, v[300:700])
+    # a q-batch whose points are all dominated by the baseline front in every MC sample scores exactly 0
+    Xbad = torch.ones(1, p["q"], p["d"], dtype=DT)
+    assert float(acq(Xbad.to(st.device))[0]) < 1e-3
+
+
+def test_errors_are_loud():
+    from everest_b200 import DeviceGPState, SingleTaskGPSpec, acquisition as A
+
+    X = np.random.default_rng(0).random((10, 3))
+    with pytest.raises(ValueError):
+        DeviceGPState(X, [SingleTaskGPSpec(kernel=K.RBFKernel([0, 1, 5], [0.5]), y=np.zeros(10))])
+    with pytest.raises(ValueError):
+        DeviceGPState(X, [SingleTaskGPSpec(kernel=K.TanimotoKernel([0, 1, 2]), y=np.zeros(10))])  # not 0/1 bits
+    st = DeviceGPState(X, [SingleTaskGPSpec(kernel=K.RBFKernel([0, 1, 2], [0.5]), y=X[:, 0])] * 2).factorize()
+    with pytest.raises(NotImplementedError):
+        A.qNoisyExpectedHypervolumeImprovement(st, [0, 0], X, MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]),
+                                               alpha=0.1)
+    acq = A.qNoisyExpectedHypervolumeImprovement(st, [0, 0], X, MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]),
+                                                 mc_samples=16, seed=0)
+    with pytest.raises(ValueError):
+        acq(torch.zeros(2, 1, 4, dtype=DT))

@@ -1,0 +1,184 @@
+"""CPU tests of the host-side mirror: kernel flattening, objective specs against the reference golden
+vectors, restart selection, base samples, config builders, C-ABI export list, sharding (gloo, world 2)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import everest_b200 as E
+from everest_b200 import _lib, configs as Cf, distributed as D, kernels as K, objectives as Ob, optim, sampling
+from oracle import bo_oracle as O
+from tests import problems as P
+
+DT = torch.float64
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_golden.json")))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "everest_b200.h")).read()
+    declared = set(re.findall(r"\b(bo_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().bo_version() >= 100
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "everest_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.EverestError):
+        E.DeviceGPState(np.zeros((4, 2)), [E.SingleTaskGPSpec(kernel=K.RBFKernel([0, 1], [1.0]), y=np.zeros(4))])
+
+
+def test_flatten_matches_tree_evaluation():
+    kc = lambda: K.MaternKernel([0, 1], [0.5, 0.7], nu=2.5)  # noqa: E731
+    kh = lambda: K.HammingDistanceKernel({2: 3, 5: 2}, [1.0, 2.0])  # noqa: E731
+    km = lambda: K.TanimotoKernel(list(range(7, 19)))  # noqa: E731
+    tree = K.AdditiveKernel([
+        K.ScaleKernel(K.AdditiveKernel([kc(), K.ScaleKernel(kh(), 0.3)]), 1.5),
+        K.ScaleKernel(K.MultiplicativeKernel([kc(), kh(), K.ScaleKernel(km(), 0.8)]), 0.7)])
+    flat = K.flatten(tree)
+    assert len(flat.leaves) == 5 and len(flat.terms) == 3
+    g = torch.Generator().manual_seed(0)
+    n, d = 12, 19
+    X = torch.rand(n, d, dtype=DT, generator=g)
+    X[:, 2:5] = torch.eye(3, dtype=DT)[torch.randint(0, 3, (n,), generator=g)]
+    X[:, 5:7] = torch.eye(2, dtype=DT)[torch.randint(0, 2, (n,), generator=g)]
+    X[:, 7:] = (torch.rand(n, 12, generator=g) < 0.3).to(DT)
+    c = X.mean(0)
+    full = O.eval_kernel(P.kernel_to_oracle(tree), X, X, c)
+    acc = torch.zeros(n, n, dtype=DT)
+    for coef, facs in flat.terms:
+        t = torch.full((n, n), coef, dtype=DT)
+        for f in facs:
+            t = t * O.eval_kernel(P.kernel_to_oracle(flat.leaves[f]), X, X, c)
+        acc = acc + t
+    assert torch.allclose(acc, full, rtol=1e-13, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        K.flatten(object())
+
+
+def test_objective_specs_match_reference_golden():
+    Y = torch.tensor(G["objective_callables"]["Y"], dtype=DT)
+    for c in G["objective_callables"]["cases"]:
+        kind, idx, *params = c["op"]
+        spec = Ob.ObjectiveSpec(kind, idx, *params)
+        assert torch.equal(spec(Y), torch.tensor(c["out"], dtype=DT)), c["op"]
+    g = G["multiobjective"]
+    mo = Ob.MultiObjective([Ob.ObjectiveSpec(o[0], o[1], *o[2:]) for o in g["ops"]])
+    assert torch.equal(mo(Y), torch.tensor(g["out"], dtype=DT))
+    add = Ob.ScalarObjective([Ob.ObjectiveSpec(o[0], o[1], *o[2:], w=w) for o, w in zip(g["ops"], g["additive"]["weights"])],
+                             "additive")
+    assert torch.equal(add(Y), torch.tensor(g["additive"]["out"], dtype=DT))
+    mg = g["multiplicative"]
+    mul = Ob.ScalarObjective([Ob.ObjectiveSpec(o[0], o[1], *o[2:], w=w) for o, w in zip(mg["ops"], mg["weights"])],
+                             "multiplicative")
+    assert torch.equal(mul(Y), torch.tensor(mg["out"], dtype=DT))
+    cons = Ob.constraints_from_sigmoid_objectives([Ob.MaximizeSigmoidObjective(1, 4.0, 1.5), Ob.MinimizeSigmoidObjective(2, 0.5, 2.5)])
+    assert [c.eta for c in cons] == G["constraints"]["etas"]
+    for c, ref in zip(cons, G["constraints"]["values"]):
+        assert torch.equal(c(Y), torch.tensor(ref, dtype=DT))
+    with pytest.raises(NotImplementedError):
+        Ob.ObjectiveSpec("desirability", 0).to_c()
+
+
+def test_benchmark_functions_match_reference_golden():
+    from everest_b200 import benchmarks as B
+
+    g = G["dtlz2_6d_4obj"]
+    assert np.allclose(B.dtlz2(np.array(g["X"]), 4), np.array(g["Y"]), rtol=1e-14, atol=1e-15)
+    g = G["himmelblau"]
+    assert np.allclose(B.himmelblau(np.array(g["X"])), np.array(g["Y"]), rtol=1e-13, atol=1e-12)
+    g = G["detergent"]
+    assert np.allclose(B.detergent(np.array(g["X"])), np.array(g["Y"]), rtol=1e-13, atol=1e-13)
+    assert np.array_equal(B.DETERGENT_COEF, np.array(g["coef"]))
+
+
+def test_base_samples_agree_with_oracle_convention():
+    z = sampling.base_samples(5, 3, 16, seed=7)
+    assert torch.equal(z, O.base_samples_points_by_outputs(5, 3, 16, 7))
+    assert sampling.base_samples(0, 2, 8, 1).shape == (8, 0, 2)
+
+
+def test_initialize_q_batch_semantics():
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(64, 2, 3, dtype=DT, generator=g)
+    Y = torch.rand(64, dtype=DT, generator=g)
+    Xs, idcs = optim.initialize_q_batch(X, Y, n=8, generator=g)
+    assert Xs.shape == (8, 2, 3) and len(set(idcs.tolist())) == 8
+    assert int(torch.argmax(Y)) in idcs.tolist()  # the arg-max is always kept
+    Xall, idall = optim.initialize_q_batch(X, Y, n=64)
+    assert torch.equal(Xall, X)
+    with pytest.raises(RuntimeError):
+        optim.initialize_q_batch(X, Y, n=65)
+    Xc, _ = optim.initialize_q_batch(X, torch.ones(64, dtype=DT), n=4, generator=g)  # zero std -> random pick
+    assert Xc.shape == (4, 2, 3)
+    S = optim.draw_sobol_samples(torch.tensor([[0.0, -1.0], [2.0, 1.0]]), 16, 3, seed=1)
+    assert S.shape == (16, 3, 2) and float(S[..., 0].min()) >= 0 and float(S[..., 1].min()) >= -1 and float(S[..., 0].max()) <= 2
+    assert torch.equal(optim.apply_fixed_features(S, {1: 0.25})[..., 1], torch.full((16, 3), 0.25, dtype=DT))
+
+
+def test_config_builders_and_oracle_conversion():
+    for p in (Cf.zdt1_qnehvi(scale=0.01), Cf.dtlz2_qnehvi(scale=0.02), Cf.himmelblau_qlogei(scale=0.05),
+              Cf.detergent_qnehvi(), Cf.mixed_tanimoto_qlogei(scale=0.004, n_bits=128)):
+        gp = P.oracle_gp(p)
+        mean, cov = gp.posterior(torch.as_tensor(p["X"][:3], dtype=DT))
+        assert torch.isfinite(mean).all() and torch.isfinite(cov).all()
+        assert Cf.candidates(p, 5).shape[-1] == p["d"]
+    full = Cf.zdt1_qnehvi()
+    assert full["X"].shape == (2000, 30) and full["q"] == 4 and full["S"] == 512 and full["raw_samples"] == 16384
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 16, 16385):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from everest_b200 import distributed as D
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+g = torch.Generator().manual_seed(3)
+X = torch.rand(37, 2, 3, dtype=torch.double, generator=g)
+acq = lambda x: (x.sum(dim=(1, 2)) * 1.5 - x[:, 0, 0] ** 2)
+full = acq(X)
+got = D.sharded_forward(acq, X)
+assert torch.equal(got, full), "sharded_forward mismatch"
+v, i = D.sharded_argmax(acq, X)
+assert i == int(torch.argmax(full)) and v == float(full.max())
+dist.barrier()
+dist.destroy_process_group()
+print("rank", sys.argv[3], "ok")
+"""
+
+
+def test_sharded_forward_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
