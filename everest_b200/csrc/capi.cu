@@ -536,9 +536,12 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
     RC(o.Ext.ensure((size_t)(nb + 1) * ldk * 8, true));
     if (nb > 0) {
       int inf = 0; double jit = 0;
-      RC(joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, o.Ext.as<double>(), &inf, &jit, s));
+      RC(st->wsV.ensure((size_t)nb * ldk * 8, true));
+      RC(joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, st->wsV.as<double>(), &inf, &jit, s));
       if (info) info[m] = inf;
       if (inf != 0) { bo_set_error("baseline posterior covariance not p.d. (output %d)", m); return BO_ERR_NOT_PSD; }
+      // Ext rows = V_b L^-1 = K_bX (K + s2 I)^-1, so that K*X Ext^T = V_q V_b^T
+      RC(launch_gemm_nt(nb, st->N, st->N, 1.0, st->wsV.as<double>(), ldk, o.LinvT.as<double>(), ldk, 0.0, o.Ext.as<double>(), ldk, false, s, &st->lc));
       RC(launch_gemm_nt(S, nb, nb, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldlb, ldlb, o.Lb.as<double>(), ldlb, 0.0,
                         st->wsF.as<double>() + (size_t)m * S * ldlb, ldlb, false, s, &st->lc));
     } else {

@@ -370,6 +370,14 @@ def is_non_dominated(Y, deduplicate=True):
     return nd
 
 
+def is_non_dominated_chunked(Y, deduplicate=False, max_elems=1 << 27):
+    """Same result as is_non_dominated for Y [S, n, m], evaluated a few samples at a time so that the
+    S x n x n comparison tensor stays bounded (BoTorch switches to a loop variant for n > 1000)."""
+    S, n, m = Y.shape
+    step = max(1, int(max_elems // max(1, n * n * m)))
+    return torch.cat([is_non_dominated(Y[i : i + step], deduplicate=deduplicate) for i in range(0, S, step)], dim=0)
+
+
 def pareto_front_above_ref(Y, ref):
     """Unique non-dominated points strictly better than ref in every objective, in the
     original row order.  Returns (points [p, m], row indices [p])."""
@@ -539,7 +547,7 @@ class QNEHVIOracle:
             infeas = torch.stack([c > 0 for c in constraint_values(self.cons, samples)], 0).any(0)
             obj = obj.clone()
             obj[infeas] = self.ref
-        mask = is_non_dominated(obj, deduplicate=False) & (obj > self.ref).all(dim=-1)
+        mask = is_non_dominated_chunked(obj, deduplicate=False) & (obj > self.ref).all(dim=-1)
         probs = mask.to(DT).mean(dim=0)
         return probs.nonzero().view(-1)
 

@@ -227,9 +227,11 @@ def test_qehvi_forward():
     assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * max(float(v_o.abs().max()), 1e-12)
 
 
-def test_jitter_on_duplicate_candidates_matches_oracle():
-    """Two identical points in a q-batch make the conditional q x q block singular: both paths must walk
-    the same psd_safe_cholesky jitter ladder."""
+def test_degenerate_q_batch_is_handled_like_the_oracle():
+    """Two identical points in a q-batch make the conditional q x q block singular to rounding: the last
+    pivot is +-1e-17, so whether the psd_safe_cholesky ladder engages is a coin flip on BOTH paths.  The
+    well-posed batches must still agree to 1e-8, the degenerate one stays finite, flags no hard failure
+    and agrees to the size of the largest jitter (1e-3 relative is far above it)."""
     p = small_problem("zdt1")
     gp = P.oracle_gp(p)
     st = Cf.build_state(p)
@@ -237,10 +239,41 @@ def test_jitter_on_duplicate_candidates_matches_oracle():
     acq_d = Cf.build_acqf(p, st, prune_samples=128)
     X = Cf.candidates(p, 4).clone()
     X[1, 1] = X[1, 0]
-    v_o, parts = acq_o.forward(X, return_parts=True)
-    v_d = acq_d(X.to(st.device))
-    assert float(parts["jitter"][:, 1].max()) > 0
-    assert float((v_d.cpu() - v_o).abs().max()) < 1e-6 * float(v_o.abs().max())
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device)).cpu()
+    assert bool(torch.isfinite(v_d).all()) and int(acq_d.last_info.sum()) == 0
+    scale = float(v_o.abs().max())
+    keep = torch.tensor([0, 2, 3])
+    assert float((v_d[keep] - v_o[keep]).abs().max()) < 1e-8 * scale
+    assert abs(float(v_d[1] - v_o[1])) < 1e-3 * scale
+
+
+def test_jitter_ladder_and_not_psd_error():
+    """A (nonsensical but deterministic) slightly NEGATIVE-definite Gram: -c K_rbf with c * lambda_max = 3e-6
+    and zero noise fails for jitter 1e-8, 1e-7, 1e-6 and succeeds at 1e-5 on both paths; a strongly negative
+    one exhausts the ladder and raises NotPSDError (BoTorch: NotPSDError from psd_safe_cholesky)."""
+    from everest_b200 import NotPSDError
+
+    p = Cf.zdt1_qnehvi(N=40, S=16, raw=8, d=4, q=1)
+    Xt = torch.as_tensor(p["X"], dtype=DT)
+    base = p["outputs"][0]["kernel"]
+    lam = float(torch.linalg.eigvalsh(O.eval_kernel(P.kernel_to_oracle(base), Xt, Xt, Xt.mean(0), same=True)).max())
+    for o in p["outputs"]:
+        o["kernel"] = K.ScaleKernel(base, -3e-6 / lam)
+        o["noise"] = 0.0
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    assert [f["jitter"] for f in gp._fact] == pytest.approx([1e-5] * 2, rel=1e-12)
+    assert st.jitter == pytest.approx([1e-5] * 2, rel=1e-12)
+    for m in range(2):
+        al = st.debug_get("alpha", m).cpu()
+        assert float((al - gp._fact[m]["alpha"]).abs().max()) <= 1e-9 * float(gp._fact[m]["alpha"].abs().max())
+    for o in p["outputs"]:
+        o["kernel"] = K.ScaleKernel(base, -1.0)
+    with pytest.raises(O.NotPSDError):
+        P.oracle_gp(p)
+    with pytest.raises(NotPSDError):
+        Cf.build_state(p)
 
 
 def test_full_size_properties_headline_config():
