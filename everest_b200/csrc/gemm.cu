@@ -17,6 +17,8 @@
 // (k = 2t and 2t+1 of an 8-wide k group; A and B use the same k permutation).  Tiles are staged
 // with a 3-deep cp.async (LDGSTS) pipeline; row stride 24 doubles (192 B) makes every quarter-warp
 // 128-bit fragment load hit 8 distinct 16-byte bank groups.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define GK 16       // k per pipeline stage
@@ -285,8 +287,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
   }
 }
 
+int launch_posterior_gemm_tma(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc);
+
 int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
   if (a.rows <= 0) return BO_OK;
+  {
+    // v2 (TMA + mbarrier ring + tensor-pipe Gram) whenever a q-batch cannot straddle an 8-row MMA group
+    static int force_v1 = -1;
+    if (force_v1 < 0) { const char* e = getenv("EVEREST_GEMM_V1"); force_v1 = (e && e[0] == '1') ? 1 : 0; }
+    const bool q_ok = (a.q == 1 || a.q == 2 || a.q == 4 || a.q == 8);
+    if (q_ok && !force_v1 && a.ldk % GK == 0 && a.Nr % PG_BN == 0 && ((uintptr_t)a.Kx % 16) == 0)
+      return launch_posterior_gemm_tma(a, s, lc);
+  }
   if (a.q < 1 || a.q > BO_MAX_Q || a.rows % a.q != 0) { bo_set_error("posterior_gemm: bad q"); return BO_ERR_INVALID; }
   if (a.ldk % GK != 0 || a.Nr % PG_BN != 0) { bo_set_error("posterior_gemm: padding violated"); return BO_ERR_INVALID; }
   static bool attr_set = false;
@@ -299,6 +311,246 @@ int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* 
   int nbat = a.rows / a.q;
   int grid = (nbat + nbat_cta - 1) / nbat_cta;
   posterior_gemm_kernel<<<grid, PG_THREADS, smem, s>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// posterior GEMM v2 (q in {1, 2, 4, 8}): TMA-staged tiles + mbarrier ring, no CTA-wide barrier in the
+// main loop, Gram epilogue on the tensor pipe.
+//
+//  * A (K(X*,X) rows) and B (L^-1 / extra rows) tiles of 128 x 16 doubles arrive by
+//    cp.async.bulk.tensor.2d with SWIZZLE_128B into a 6-deep ring (32 KB per stage); one elected lane
+//    of warp 0 is the producer, every warp waits on full[stage] and arrives on empty[stage].
+//  * Fragment row g of an 8-row MMA tile maps to tile row rho(g) = (g >> 1) | ((g & 1) << 2), which
+//    makes each quarter-warp 128-bit load touch 8 distinct 16-byte chunks of the swizzled layout.
+//  * V never leaves registers: per 8-row group the 8 x 8 Gram block is accumulated with
+//    DMMA(a = acc, b = acc) (A[g][k=t] and B[k=t][n=g] are the same register for V V^T), so warps run
+//    from one column block straight into the next without draining the pipeline.
+// ------------------------------------------------------------------------------------------------
+#include <cuda.h>
+
+#define P2_ST 6
+#define P2_TILE_BYTES (128 * 16 * 8)
+#define P2_STAGE_BYTES (2 * P2_TILE_BYTES)
+#define P2_DIST (P2_ST - 2)  // prefetch distance in stages
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapL,
+                          const __grid_constant__ CUtensorMap mapE, PostGemmArgs a) {
+  extern __shared__ unsigned char p2raw[];
+  const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(p2raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;           // SWIZZLE_128B wants 1024-byte aligned tiles
+  unsigned char* sm = p2raw + (base - raw_addr);
+  const uint32_t bar_full = base + P2_ST * P2_STAGE_BYTES;      // 6 x 8 bytes
+  const uint32_t bar_empty = bar_full + P2_ST * 8;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+  const int rho_g = (g >> 1) | ((g & 1) << 2);
+  const int q = a.q;
+  const int row0 = blockIdx.x * PG_BM;
+
+  if (tid == 0) {
+    for (int s = 0; s < P2_ST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int n_tri = a.Nr / PG_BN;
+  const int n_ext_blocks = (a.n_ext + PG_BN - 1) / PG_BN;
+  const int n_blocks = n_tri + n_ext_blocks;
+  const int kfull = a.ldk;
+  auto nk_of = [&](int jb) {
+    int kmax = (jb < n_tri) ? min(kfull, (jb + 1) * PG_BN) : kfull;
+    return (kmax + GK - 1) / GK;
+  };
+
+  // producer state (only meaningful in warp 0 / lane 0)
+  int p_it = 0, p_jb = 0, p_ks = 0, p_nk = nk_of(0);
+  auto produce = [&]() {
+    if (p_jb >= n_blocks) return;
+    const int slot = p_it % P2_ST, fill = p_it / P2_ST;
+    if (fill > 0) mbar_wait(bar_empty + 8 * slot, (fill - 1) & 1);
+    const uint32_t dstA = base + slot * P2_STAGE_BYTES, dstB = dstA + P2_TILE_BYTES;
+    mbar_expect_tx(bar_full + 8 * slot, P2_STAGE_BYTES);
+    tma_load_2d(dstA, &mapA, p_ks * GK, row0, bar_full + 8 * slot);
+    if (p_jb < n_tri) tma_load_2d(dstB, &mapL, p_ks * GK, p_jb * PG_BN, bar_full + 8 * slot);
+    else tma_load_2d(dstB, &mapE, p_ks * GK, (p_jb - n_tri) * PG_BN, bar_full + 8 * slot);
+    ++p_it;
+    if (++p_ks == p_nk) { p_ks = 0; ++p_jb; if (p_jb < n_blocks) p_nk = nk_of(p_jb); }
+  };
+  if (warp == 0) {
+    if (lane == 0)
+      for (int s = 0; s < P2_DIST; ++s) produce();
+    __syncwarp();
+  }
+
+  // swizzled fragment offsets: element (row r, k) sits at r*128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1)*8
+  const int offk0 = ((0 + t) ^ rho_g) << 4, offk1 = ((4 + t) ^ rho_g) << 4;
+  const int arow = (wm0 + rho_g) * 128, brow = (wn0 + rho_g) * 128;
+
+  double gram[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gram[i][0] = gram[i][1] = 0.0;
+
+  int it = 0;
+  for (int jb = 0; jb < n_blocks; ++jb) {
+    const bool tri = jb < n_tri;
+    const int nk = nk_of(jb);
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int ks = 0; ks < nk; ++ks, ++it) {
+      if (warp == 0) {
+        if (lane == 0) produce();
+        __syncwarp();
+      }
+      const int slot = it % P2_ST;
+      mbar_wait(bar_full + 8 * slot, (it / P2_ST) & 1);
+      const unsigned char* As = sm + slot * P2_STAGE_BYTES;
+      const unsigned char* Bs = As + P2_TILE_BYTES;
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg) {
+        const int off = kg ? offk1 : offk0;
+        double2 af[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[i] = *reinterpret_cast<const double2*>(As + arow + i * 1024 + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(Bs + brow + j * 1024 + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+    }
+
+    if (tri) {
+      // Gram of each 8-row group over this warp's 32 columns, on the tensor pipe
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mma_884(gram[i][0], gram[i][1], acc[i][j][0], acc[i][j][0]);
+          mma_884(gram[i][0], gram[i][1], acc[i][j][1], acc[i][j][1]);
+        }
+    } else {
+      const int e0 = (jb - n_tri) * PG_BN;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + wm0 + i * 8 + rho_g;
+        if (r >= a.rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c2 = 2 * t + e;
+            const int col = e0 + wn0 + j * 8 + ((c2 >> 1) | ((c2 & 1) << 2));
+            if (col < a.n_ext - 1) a.W[(size_t)r * a.ldw + col] = acc[i][j][e];
+            else if (col == a.n_ext - 1) a.mu_raw[r] = acc[i][j][e];
+          }
+      }
+    }
+  }
+
+  // reduce the 4 column-warps' partial Grams and emit Gqq (q divides 8: a q-batch never straddles an 8-row group)
+  __syncthreads();  // every warp is past its last tile read: the ring can be reused
+  double* Gs = reinterpret_cast<double*>(sm);  // [4][128][8]
+  const int wcol = warp >> 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c2 = 2 * t + e;
+      Gs[(wcol * 128 + wm0 + i * 8 + rho_g) * 8 + ((c2 >> 1) | ((c2 & 1) << 2))] = gram[i][e];
+    }
+  __syncthreads();
+  for (int idx = tid; idx < PG_BM * q; idx += PG_THREADS) {
+    const int r = idx / q, a2 = idx % q;       // row in tile, partner index within its q-batch
+    if (row0 + r >= a.rows) continue;
+    const int a1 = r % q;
+    const int r2 = r - a1 + a2;
+    const int slot8 = r2 & 7;
+    double s = Gs[(0 * 128 + r) * 8 + slot8];
+    s += Gs[(1 * 128 + r) * 8 + slot8];
+    s += Gs[(2 * 128 + r) * 8 + slot8];
+    s += Gs[(3 * 128 + r) * 8 + slot8];
+    a.Gqq[((size_t)(row0 + r) / q * q + a1) * q + a2] = s;
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tile_map(CUtensorMap* map, const double* ptr, int rows, int ld) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      bo_set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+      return BO_ERR_CUDA;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bo_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return BO_ERR_CUDA; }
+  return BO_OK;
+}
+
+int launch_posterior_gemm_tma(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  CUtensorMap mA, mL, mE;
+  int rc;
+  if ((rc = make_tile_map(&mA, a.Kx, a.rows, a.ldk)) != BO_OK) return rc;
+  if ((rc = make_tile_map(&mL, a.Linv, a.Nr, a.ldk)) != BO_OK) return rc;
+  if ((rc = make_tile_map(&mE, a.Ext, a.n_ext, a.ldk)) != BO_OK) return rc;
+  static bool attr_set = false;
+  const size_t smem = (size_t)P2_ST * P2_STAGE_BYTES + 2 * P2_ST * 8 + 1024;
+  if (!attr_set) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = (a.rows + PG_BM - 1) / PG_BM;
+  posterior_gemm_tma_kernel<<<grid, PG_THREADS, smem, s>>>(mA, mL, mE, a);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -157,6 +157,28 @@ def test_qnehvi_prune_cells_and_forward(kind):
     assert np.array_equal(v_host, v_d.cpu().numpy())
 
 
+@pytest.mark.parametrize("q,N", [(1, 77), (2, 130), (4, 200), (8, 96), (3, 50), (5, 141), (16, 64)])
+def test_qnehvi_forward_all_q_paths(q, N):
+    """q in {1,2,4,8} runs the TMA/mbarrier GEMM with the tensor-pipe Gram epilogue, every other q the generic
+    cp.async kernel; N exercises the zero padding up to the 16 / 128 multiples."""
+    p = Cf.zdt1_qnehvi(N=N, S=16, raw=37, d=5, q=q)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=64)
+    acq_d = Cf.build_acqf(p, st, prune_samples=64)
+    assert acq_d.prune_idx.cpu().tolist() == acq_o.prune_idx.tolist()
+    X = Cf.candidates(p)
+    v_o, parts = acq_o.forward(X, return_parts=True)
+    v_d = acq_d(X.to(st.device))
+    nr = acq_o.nb + q
+    root = st.debug_get("root").view(-1)[: X.shape[0] * st.M * q * nr].view(X.shape[0], st.M, q, nr).cpu()
+    br_o = parts["br"].permute(1, 0, 2, 3)
+    assert float((root[..., acq_o.nb:] - br_o).abs().max()) < 1e-7 * float(br_o.abs().max())
+    mu = st.debug_get("mu").view(-1)[: X.shape[0] * q * st.M].view(X.shape[0], q, st.M).cpu()
+    assert rel_err(mu, parts["mu"], floor=1e-6) < 1e-9
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
+
+
 def test_qnehvi_with_output_constraint_and_pending():
     from everest_b200 import acquisition as A
 
