@@ -318,11 +318,13 @@ def run_b200(args):
         avg = {k: (sum(t for t, _ in v) / len(v), v[0][1]) for k, v in per.items()}
         total_ms = sum(t for t, _ in avg.values())
         kernel_share = {k: round(t / total_ms, 4) for k, (t, _) in avg.items()}
-        g_ms, g_cnt = avg["posterior_gemm"]
+        g_ms, g_cnt = avg["posterior_gemm"]  # ms per step summed over its launches, launches per step
         N, nb, M = st.N, acq.nb, st.M
         rows = b * q
-        flops_per_launch = rows * (float(N) * N + 2.0 * N * (nb + 1))  # triangular solve-equivalent + extra rows
-        achieved = flops_per_launch / ((g_ms / g_cnt) * 1e-3) / 1e12
+        # triangular solve-equivalent N^2 flops per point and output + the 1 + n_b dense extra rows
+        flops_per_step = M * rows * (float(N) * N + 2.0 * N * (nb + 1))
+        flops_per_launch = flops_per_step / g_cnt
+        achieved = flops_per_step / (g_ms * 1e-3) / 1e12
         peak = measure_fp64_peak(device)
         roofline = {"bound": "tensor", "kernel": "posterior_gemm_kernel (FP64 DMMA m8n8k4)", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

@@ -85,12 +85,13 @@ struct OutputH {
   std::vector<void*> owned;  // small parameter arrays
   PrepBuf train_prep;
   PrepD train_prepd;
-  DevBuf L, Linv, LinvT, alpha_row, dinv, resid, tvec;
+  DevBuf L, Linv, LinvT, LinvExt, alpha_row, dinv, resid, tvec;
+  int Rpad = 0;  // rows of LinvExt
   double jitter = 0.0;
   // acquisition state
   PrepBuf base_prep;
   PrepD base_prepd;
-  DevBuf Ext, Lb, Sbb;
+  DevBuf Lb, Sbb;
   // per-forward query prep
   PrepBuf q_prep;
   PrepD q_prepd;
@@ -144,7 +145,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (auto& o : st->out) {
     for (void* p : o.owned) cudaFree(p);
     o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
-    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Ext, &o.Lb, &o.Sbb};
+    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb};
     for (DevBuf* b : bs) b->release();
   }
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
@@ -296,6 +297,16 @@ static int psd_safe_chol(bo_state* st, const double* src, double* dst, int ld, i
   return BO_OK;  // caller inspects info
 }
 
+// LinvExt = [L^-1 (N rows) ; alpha ; n_b baseline rows (filled by the caller) ; zero padding to 128 rows]
+static int build_linv_ext(bo_state* st, OutputH& o, int nb, cudaStream_t s) {
+  const int N = st->N, ldk = st->ldk;
+  o.Rpad = round_up(N + 1 + nb, 128);
+  RC(o.LinvExt.ensure((size_t)o.Rpad * ldk * 8, true));
+  CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.p, o.Linv.p, (size_t)N * ldk * 8, cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.as<double>() + (size_t)N * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
+  return BO_OK;
+}
+
 extern "C" int bo_state_factorize(bo_state* st, int32_t* info, double* jitter, void* stream) {
   if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -324,6 +335,7 @@ extern "C" int bo_state_factorize(bo_state* st, int32_t* info, double* jitter, v
     RC(o.alpha_row.ensure((size_t)ldk * 8, true));
     RC(launch_gemm_nt(N, 1, N, 1.0, o.Linv.as<double>(), ldk, o.resid.as<double>(), ldk, 0.0, o.tvec.as<double>(), 1, false, s, &st->lc));
     RC(launch_gemm_nt(N, 1, N, 1.0, o.LinvT.as<double>(), ldk, o.tvec.as<double>(), ldk, 0.0, o.alpha_row.as<double>(), 1, false, s, &st->lc));
+    RC(build_linv_ext(st, o, 0, s));
   }
   CUDA_CHECK_RET(cudaStreamSynchronize(s));
   st->factorized = ok;
@@ -377,8 +389,8 @@ extern "C" int bo_posterior_marginal(bo_state* st, const double* X_dev, int32_t 
     OutputH& o = st->out[m];
     RC(posterior_blocks(st, m, X_dev, n, o.q_prep, &o.q_prepd, st->wsKx.as<double>(), nullptr, nullptr, s));
     PostGemmArgs a;
-    a.Kx = st->wsKx.as<double>(); a.rows = n; a.ldk = ldk; a.Linv = o.Linv.as<double>(); a.Ext = o.alpha_row.as<double>();
-    a.N = st->N; a.Nr = st->Nr; a.n_ext = 1; a.q = 1; a.Gqq = st->wsGqq.as<double>(); a.W = nullptr; a.ldw = 0;
+    a.Kx = st->wsKx.as<double>(); a.rows = n; a.ldk = ldk; a.B = o.LinvExt.as<double>();
+    a.N = st->N; a.Rpad = o.Rpad; a.n_ext = 1; a.q = 1; a.Gqq = st->wsGqq.as<double>(); a.W = nullptr; a.ldw = 0;
     a.mu_raw = st->wsMuRaw.as<double>();
     RC(launch_posterior_gemm(a, s, &st->lc));
     RC(launch_finish_mean(st->wsMuRaw.as<double>(), n, o.md.mean_const, o.md.y_std, o.md.y_mean, mean_dev, st->M, m, s, &st->lc));
@@ -533,23 +545,24 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
   if (nb > 0) RC(launch_transpose_base_samples(zb_dev, S, nb, M, st->zbT.as<double>(), st->wsZM.as<double>(), ldlb, s, &st->lc));
   for (int m = 0; m < M; ++m) {
     OutputH& o = st->out[m];
-    RC(o.Ext.ensure((size_t)(nb + 1) * ldk * 8, true));
     if (nb > 0) {
       int inf = 0; double jit = 0;
       RC(st->wsV.ensure((size_t)nb * ldk * 8, true));
       RC(joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, st->wsV.as<double>(), &inf, &jit, s));
       if (info) info[m] = inf;
       if (inf != 0) { bo_set_error("baseline posterior covariance not p.d. (output %d)", m); return BO_ERR_NOT_PSD; }
-      // Ext rows = V_b L^-1 = K_bX (K + s2 I)^-1, so that K*X Ext^T = V_q V_b^T
-      RC(launch_gemm_nt(nb, st->N, st->N, 1.0, st->wsV.as<double>(), ldk, o.LinvT.as<double>(), ldk, 0.0, o.Ext.as<double>(), ldk, false, s, &st->lc));
+      // extra rows = V_b L^-1 = K_bX (K + s2 I)^-1, so that K*X (.)^T = V_q V_b^T
+      RC(build_linv_ext(st, o, nb, s));
+      RC(launch_gemm_nt(nb, st->N, st->N, 1.0, st->wsV.as<double>(), ldk, o.LinvT.as<double>(), ldk, 0.0,
+                        o.LinvExt.as<double>() + (size_t)(st->N + 1) * ldk, ldk, false, s, &st->lc));
       RC(launch_gemm_nt(S, nb, nb, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldlb, ldlb, o.Lb.as<double>(), ldlb, 0.0,
                         st->wsF.as<double>() + (size_t)m * S * ldlb, ldlb, false, s, &st->lc));
     } else {
       RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
       RC(o.Lb.ensure(16));
+      RC(build_linv_ext(st, o, 0, s));
       if (info) info[m] = 0;
     }
-    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.as<double>() + (size_t)nb * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
   }
   RC(st->obj_b.ensure((size_t)S * std::max(nb, 1) * n_obj * 8));
   RC(st->samples_b.ensure((size_t)S * std::max(nb, 1) * M * 8));
@@ -575,10 +588,9 @@ extern "C" int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, 
   RC(st->zbT.ensure(16));
   for (int m = 0; m < st->M; ++m) {
     OutputH& o = st->out[m];
-    RC(o.Ext.ensure((size_t)st->ldk * 8, true));
     RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
     RC(o.Lb.ensure(16));
-    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.p, o.alpha_row.p, (size_t)st->ldk * 8, cudaMemcpyDeviceToDevice, s));
+    RC(build_linv_ext(st, o, 0, s));
   }
   RC(build_cells(st, Yobj_dev, st->wsFeas.as<unsigned char>(), n, 1, n_obj, max_cells, s));
   st->acqf_kind = 2;
@@ -596,10 +608,9 @@ extern "C" int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const 
   RC(st->zbT.ensure(16));
   for (int m = 0; m < st->M; ++m) {
     OutputH& o = st->out[m];
-    RC(o.Ext.ensure((size_t)st->ldk * 8, true));
     RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
     RC(o.Lb.ensure(16));
-    CUDA_CHECK_RET(cudaMemcpyAsync(o.Ext.p, o.alpha_row.p, (size_t)st->ldk * 8, cudaMemcpyDeviceToDevice, s));
+    RC(build_linv_ext(st, o, 0, s));
   }
   st->acqf_kind = 3;
   return BO_OK;
@@ -629,40 +640,46 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
   }
   const int M = st->M, ldk = st->ldk, nb = st->nb, S = st->S, nr = nb + q;
   const int ldw = std::max(nb, 1);
-  // chunk the q-batches so that the K(X*,X) workspace stays below ~4 GiB
-  long long max_rows = std::max<long long>(((long long)4 << 30) / ((long long)ldk * 8), (long long)q);
+  // chunk the q-batches so that the K(X*,X) workspace (all outputs) stays below ~4 GiB
+  long long max_rows = std::max<long long>(((long long)4 << 30) / ((long long)ldk * 8 * M), (long long)q);
   int bchunk = (int)std::min<long long>(b, std::max<long long>(1, max_rows / q));
   RC(st->wsZqT.ensure((size_t)q * M * S * 8));
   RC(launch_transpose_base_samples(zq_dev, S, q, M, st->wsZqT.as<double>(), nullptr, 0, s, &st->lc));
-  RC(st->wsKx.ensure((size_t)bchunk * q * ldk * 8));
-  RC(st->wsGqq.ensure((size_t)bchunk * q * q * 8));
-  RC(st->wsW.ensure((size_t)bchunk * q * ldw * 8));
-  RC(st->wsMuRaw.ensure((size_t)bchunk * q * 8));
+  const size_t rows_max = (size_t)bchunk * q;
+  RC(st->wsKx.ensure(rows_max * ldk * 8 * M));
+  RC(st->wsGqq.ensure(rows_max * q * 8 * M));
+  RC(st->wsW.ensure(rows_max * ldw * 8 * M));
+  RC(st->wsMuRaw.ensure(rows_max * 8 * M));
   RC(st->wsRoot.ensure((size_t)bchunk * M * q * nr * 8));
-  RC(st->wsMu.ensure((size_t)bchunk * q * M * 8));
+  RC(st->wsMu.ensure(rows_max * M * 8));
   RC(st->wsJit.ensure((size_t)bchunk * M * sizeof(int)));
+  std::vector<PostGemmArgs> pg(M);
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
     const double* Xc = X_dev + (size_t)b0 * q * st->d;
     for (int m = 0; m < M; ++m) {
       OutputH& o = st->out[m];
+      double* Kx = st->wsKx.as<double>() + (size_t)m * rows_max * ldk;
       RC(o.q_prep.ensure(o.md, rows, &o.q_prepd));
       rec_begin(st, "prep", s);
       RC(launch_prep_points(o.md, Xc, rows, st->d, o.q_prepd, s, &st->lc));
       rec_end(st, s);
       rec_begin(st, "crosscov", s);
-      RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, st->wsKx.as<double>(), ldk, false, s, &st->lc));
+      RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, s, &st->lc));
       rec_end(st, s);
-      PostGemmArgs a;
-      a.Kx = st->wsKx.as<double>(); a.rows = rows; a.ldk = ldk; a.Linv = o.Linv.as<double>(); a.Ext = o.Ext.as<double>();
-      a.N = st->N; a.Nr = st->Nr; a.n_ext = nb + 1; a.q = q; a.Gqq = st->wsGqq.as<double>(); a.W = st->wsW.as<double>();
-      a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>();
-      rec_begin(st, "posterior_gemm", s);
-      RC(launch_posterior_gemm(a, s, &st->lc));
-      rec_end(st, s);
+      PostGemmArgs& a = pg[m];
+      a.Kx = Kx; a.rows = rows; a.ldk = ldk; a.B = o.LinvExt.as<double>(); a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad;
+      a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
+      a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
+    }
+    rec_begin(st, "posterior_gemm", s);
+    RC(launch_posterior_gemm_multi(pg.data(), M, s, &st->lc));
+    rec_end(st, s);
+    for (int m = 0; m < M; ++m) {
+      OutputH& o = st->out[m];
       CondRootArgs c;
       c.md = o.md; c.prep_q = o.q_prepd; c.prep_b = o.base_prepd; c.b = bc; c.q = q; c.nb = nb; c.M = M; c.m = m;
-      c.Gqq = st->wsGqq.as<double>(); c.W = st->wsW.as<double>(); c.ldw = ldw; c.mu_raw = st->wsMuRaw.as<double>();
+      c.Gqq = pg[m].Gqq; c.W = pg[m].W; c.ldw = ldw; c.mu_raw = pg[m].mu_raw;
       c.Lb = o.Lb.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
       c.info = st->wsJit.as<int>(); c.jitter = nullptr;
       rec_begin(st, "cond_root", s);

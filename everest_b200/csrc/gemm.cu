@@ -18,6 +18,7 @@
 // with a 3-deep cp.async (LDGSTS) pipeline; row stride 24 doubles (192 B) makes every quarter-warp
 // 128-bit fragment load hit 8 distinct 16-byte bank groups.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -147,9 +148,12 @@ int launch_gemm_nt(int m, int n, int k, double alpha, const double* A, int lda, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// posterior GEMM: 128-row CTA owns whole q-batches and walks every 128-column block of L^-1
-// (triangular: k only up to the block's last row) plus the dense extra rows [V_b ; alpha].
-// 8 warps (2 x 4), warp tile 64 x 32 -> 32 DMMA accumulator pairs per thread.
+// posterior GEMM.  B operand = "LinvExt" [Rpad, ldk]: rows [0, N) the lower-triangular inverse root,
+// row N the mean cache alpha, rows N+1 .. N+n_ext-1 the baseline rows K_bX (K + s2 I)^-1, zero padded
+// to a multiple of 128 rows.  A 128-row CTA owns whole q-batches and walks every 128-column block:
+// purely triangular blocks need k only up to their last row; blocks containing extra rows are dense.
+// Columns n < N feed the Gram reduction Gqq = V_q V_q^T; columns n >= N are outputs
+// (e = n - N: e == 0 -> mu_raw, e >= 1 -> W[:, e-1] = V_q V_b^T).
 // ------------------------------------------------------------------------------------------------
 #define PG_BM 128
 #define PG_BN 128
@@ -164,6 +168,7 @@ size_t posterior_gemm_smem_bytes() {
   return pipe > stage ? pipe : stage;
 }
 
+// v1 (any q <= 16): cp.async pipeline, V tile staged through shared memory for the Gram reduction.
 __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmArgs a) {
   extern __shared__ __align__(16) double psm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -184,18 +189,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
 #pragma unroll
   for (int i = 0; i < PG_MAXITEMS; ++i) gacc[i] = 0.0;
 
-  const int n_tri_blocks = a.Nr / PG_BN;
-  const int n_ext_blocks = (a.n_ext + PG_BN - 1) / PG_BN;
+  const int n_blocks = a.Rpad / PG_BN;
   const int kfull = a.ldk;  // multiple of 16, zero padded
 
-  for (int jb = 0; jb < n_tri_blocks + n_ext_blocks; ++jb) {
-    const bool tri = jb < n_tri_blocks;
-    const int n0 = tri ? jb * PG_BN : (jb - n_tri_blocks) * PG_BN;  // first row of the B operand block
-    const double* Bg = tri ? a.Linv : a.Ext;
-    // L^-1 rows n0..n0+127 are zero beyond column n0+127
-    const int kmax = tri ? min(kfull, n0 + PG_BN) : kfull;
+  for (int jb = 0; jb < n_blocks; ++jb) {
+    const int n0 = jb * PG_BN;
+    const bool dense = (n0 + PG_BN > a.N);
+    const int kmax = dense ? kfull : (n0 + PG_BN);
     const int nk = (kmax + GK - 1) / GK;
-    const int brow_valid = tri ? a.Nr : a.n_ext;
+    const int first_ext = max(0, min(PG_BN, a.N - n0));  // columns >= first_ext of this block are extra rows
 
     double acc[8][4][2];
 #pragma unroll
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
     for (int s = 0; s < PG_ST - 1; ++s) {
       if (s < nk) {
         load_tile_async<PG_BM, PG_THREADS>(As + s * PG_BM * GLDS, a.Kx, a.ldk, row0, rows_valid, s * GK, tid);
-        load_tile_async<PG_BN, PG_THREADS>(Bs + s * PG_BN * GLDS, Bg, a.ldk, n0, brow_valid, s * GK, tid);
+        load_tile_async<PG_BN, PG_THREADS>(Bs + s * PG_BN * GLDS, a.B, a.ldk, n0, a.Rpad, s * GK, tid);
       }
       cp_async_commit();
     }
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
       if (nx < nk) {
         int st = nx % PG_ST;
         load_tile_async<PG_BM, PG_THREADS>(As + st * PG_BM * GLDS, a.Kx, a.ldk, row0, rows_valid, nx * GK, tid);
-        load_tile_async<PG_BN, PG_THREADS>(Bs + st * PG_BN * GLDS, Bg, a.ldk, n0, brow_valid, nx * GK, tid);
+        load_tile_async<PG_BN, PG_THREADS>(Bs + st * PG_BN * GLDS, a.B, a.ldk, n0, a.Rpad, nx * GK, tid);
       }
       cp_async_commit();
       int st = ks % PG_ST;
@@ -226,7 +228,6 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
     cp_async_wait<0>();
     __syncthreads();  // pipeline drained: stage buffers are free
 
-    // stage the V tile
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -237,8 +238,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
       }
     __syncthreads();
 
-    if (tri) {
-      // Gqq[batch][i][j] += sum_c V[i][c] V[j][c]   (padding columns of L^-1 are zero)
+    if (first_ext > 0) {
 #pragma unroll
       for (int it = 0; it < PG_MAXITEMS; ++it) {
         int item = tid + it * PG_THREADS;
@@ -251,19 +251,20 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
           const double* vj = Vs + (bat * q + j) * PG_VLD;
           double s = 0.0;
 #pragma unroll 8
-          for (int c = 0; c < PG_BN; ++c) s = fma(vi[c], vj[c], s);
+          for (int c = 0; c < first_ext; ++c) s = fma(vi[c], vj[c], s);
           gacc[it] += s;
         }
       }
-    } else {
-      const int e0 = n0;
-      for (int idx = tid; idx < rows_cta * PG_BN; idx += PG_THREADS) {
-        int r = idx / PG_BN, c = idx % PG_BN;
-        int e = e0 + c;
+    }
+    if (first_ext < PG_BN) {
+      const int next = PG_BN - first_ext;
+      for (int idx = tid; idx < rows_cta * next; idx += PG_THREADS) {
+        int r = idx / next, c = first_ext + idx % next;
+        int e = n0 + c - a.N;
         if (row0 + r < rows_valid && e < a.n_ext) {
           double v = Vs[r * PG_VLD + c];
-          if (e < a.n_ext - 1) a.W[(size_t)(row0 + r) * a.ldw + e] = v;
-          else a.mu_raw[row0 + r] = v;
+          if (e == 0) a.mu_raw[row0 + r] = v;
+          else a.W[(size_t)(row0 + r) * a.ldw + (e - 1)] = v;
         }
       }
     }
@@ -287,40 +288,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) posterior_gemm_kernel(PostGemmA
   }
 }
 
-int launch_posterior_gemm_tma(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc);
-
-int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  if (a.rows <= 0) return BO_OK;
-  {
-    // v2 (TMA + mbarrier ring + tensor-pipe Gram) whenever a q-batch cannot straddle an 8-row MMA group
-    static int force_v1 = -1;
-    if (force_v1 < 0) { const char* e = getenv("EVEREST_GEMM_V1"); force_v1 = (e && e[0] == '1') ? 1 : 0; }
-    const bool q_ok = (a.q == 1 || a.q == 2 || a.q == 4 || a.q == 8);
-    if (q_ok && !force_v1 && a.ldk % GK == 0 && a.Nr % PG_BN == 0 && ((uintptr_t)a.Kx % 16) == 0)
-      return launch_posterior_gemm_tma(a, s, lc);
-  }
-  if (a.q < 1 || a.q > BO_MAX_Q || a.rows % a.q != 0) { bo_set_error("posterior_gemm: bad q"); return BO_ERR_INVALID; }
-  if (a.ldk % GK != 0 || a.Nr % PG_BN != 0) { bo_set_error("posterior_gemm: padding violated"); return BO_ERR_INVALID; }
-  static bool attr_set = false;
-  size_t smem = posterior_gemm_smem_bytes();
-  if (!attr_set) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  int nbat_cta = PG_BM / a.q;
-  int nbat = a.rows / a.q;
-  int grid = (nbat + nbat_cta - 1) / nbat_cta;
-  posterior_gemm_kernel<<<grid, PG_THREADS, smem, s>>>(a);
-  if (lc) lc->n++;
-  CUDA_CHECK_RET(cudaGetLastError());
-  return BO_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
-// posterior GEMM v2 (q in {1, 2, 4, 8}): TMA-staged tiles + mbarrier ring, no CTA-wide barrier in the
-// main loop, Gram epilogue on the tensor pipe.
+// v2 (q in {1, 2, 4, 8}; all outputs of the model list in ONE launch, blockIdx.y = output):
+// TMA-staged tiles + mbarrier ring, no CTA-wide barrier in the main loop, Gram on the tensor pipe.
 //
-//  * A (K(X*,X) rows) and B (L^-1 / extra rows) tiles of 128 x 16 doubles arrive by
+//  * A (K(X*,X) rows) and B (LinvExt rows) tiles of 128 x 16 doubles arrive by
 //    cp.async.bulk.tensor.2d with SWIZZLE_128B into a 6-deep ring (32 KB per stage); one elected lane
 //    of warp 0 is the producer, every warp waits on full[stage] and arrives on empty[stage].
 //  * Fragment row g of an 8-row MMA tile maps to tile row rho(g) = (g >> 1) | ((g & 1) << 2), which
@@ -335,6 +307,14 @@ int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* 
 #define P2_TILE_BYTES (128 * 16 * 8)
 #define P2_STAGE_BYTES (2 * P2_TILE_BYTES)
 #define P2_DIST (P2_ST - 2)  // prefetch distance in stages
+#define P2_MAXOUT 8
+
+struct alignas(128) P2Item {
+  CUtensorMap mapA;
+  CUtensorMap mapB;
+  PostGemmArgs a;
+};
+struct P2Batch { P2Item item[P2_MAXOUT]; };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
@@ -357,10 +337,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
-posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapL,
-                          const __grid_constant__ CUtensorMap mapE, PostGemmArgs a) {
+__global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid_constant__ P2Batch batch) {
   extern __shared__ unsigned char p2raw[];
+  const P2Item& item = batch.item[blockIdx.y];
+  const PostGemmArgs& a = item.a;
   const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(p2raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;           // SWIZZLE_128B wants 1024-byte aligned tiles
   unsigned char* sm = p2raw + (base - raw_addr);
@@ -370,7 +350,7 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
   const int rho_g = (g >> 1) | ((g & 1) << 2);
-  const int q = a.q;
+  const int q = a.q, N = a.N, rows = a.rows;
   const int row0 = blockIdx.x * PG_BM;
 
   if (tid == 0) {
@@ -379,12 +359,10 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   }
   __syncthreads();
 
-  const int n_tri = a.Nr / PG_BN;
-  const int n_ext_blocks = (a.n_ext + PG_BN - 1) / PG_BN;
-  const int n_blocks = n_tri + n_ext_blocks;
+  const int n_blocks = a.Rpad / PG_BN;
   const int kfull = a.ldk;
   auto nk_of = [&](int jb) {
-    int kmax = (jb < n_tri) ? min(kfull, (jb + 1) * PG_BN) : kfull;
+    int kmax = ((jb + 1) * PG_BN > N) ? kfull : (jb + 1) * PG_BN;
     return (kmax + GK - 1) / GK;
   };
 
@@ -396,9 +374,8 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (fill > 0) mbar_wait(bar_empty + 8 * slot, (fill - 1) & 1);
     const uint32_t dstA = base + slot * P2_STAGE_BYTES, dstB = dstA + P2_TILE_BYTES;
     mbar_expect_tx(bar_full + 8 * slot, P2_STAGE_BYTES);
-    tma_load_2d(dstA, &mapA, p_ks * GK, row0, bar_full + 8 * slot);
-    if (p_jb < n_tri) tma_load_2d(dstB, &mapL, p_ks * GK, p_jb * PG_BN, bar_full + 8 * slot);
-    else tma_load_2d(dstB, &mapE, p_ks * GK, (p_jb - n_tri) * PG_BN, bar_full + 8 * slot);
+    tma_load_2d(dstA, &item.mapA, p_ks * GK, row0, bar_full + 8 * slot);
+    tma_load_2d(dstB, &item.mapB, p_ks * GK, p_jb * PG_BN, bar_full + 8 * slot);
     ++p_it;
     if (++p_ks == p_nk) { p_ks = 0; ++p_jb; if (p_jb < n_blocks) p_nk = nk_of(p_jb); }
   };
@@ -418,7 +395,7 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 
   int it = 0;
   for (int jb = 0; jb < n_blocks; ++jb) {
-    const bool tri = jb < n_tri;
+    const int n0 = jb * PG_BN;
     const int nk = nk_of(jb);
     double acc[8][4][2];
 #pragma unroll
@@ -456,7 +433,27 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
       if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
     }
 
-    if (tri) {
+    if (n0 + PG_BN > N) {
+      // block holds extra rows: emit them and clear them out of the Gram operand
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c2 = 2 * t + e;
+          const int ext = n0 + wn0 + j * 8 + ((c2 >> 1) | ((c2 & 1) << 2)) - N;  // extra-row index, < 0 for L^-1 columns
+          if (ext < 0) continue;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = row0 + wm0 + i * 8 + rho_g;
+            if (r < rows && ext < a.n_ext) {
+              if (ext == 0) a.mu_raw[r] = acc[i][j][e];
+              else a.W[(size_t)r * a.ldw + (ext - 1)] = acc[i][j][e];
+            }
+            acc[i][j][e] = 0.0;
+          }
+        }
+    }
+    if (n0 < N) {
       // Gram of each 8-row group over this warp's 32 columns, on the tensor pipe
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -465,22 +462,6 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
           mma_884(gram[i][0], gram[i][1], acc[i][j][0], acc[i][j][0]);
           mma_884(gram[i][0], gram[i][1], acc[i][j][1], acc[i][j][1]);
         }
-    } else {
-      const int e0 = (jb - n_tri) * PG_BN;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + wm0 + i * 8 + rho_g;
-        if (r >= a.rows) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c2 = 2 * t + e;
-            const int col = e0 + wn0 + j * 8 + ((c2 >> 1) | ((c2 & 1) << 2));
-            if (col < a.n_ext - 1) a.W[(size_t)r * a.ldw + col] = acc[i][j][e];
-            else if (col == a.n_ext - 1) a.mu_raw[r] = acc[i][j][e];
-          }
-      }
     }
   }
 
@@ -498,7 +479,7 @@ posterior_gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
   __syncthreads();
   for (int idx = tid; idx < PG_BM * q; idx += PG_THREADS) {
     const int r = idx / q, a2 = idx % q;       // row in tile, partner index within its q-batch
-    if (row0 + r >= a.rows) continue;
+    if (row0 + r >= rows) continue;
     const int a1 = r % q;
     const int r2 = r - a1 + a2;
     const int slot8 = r2 & 7;
@@ -537,21 +518,64 @@ static int make_tile_map(CUtensorMap* map, const double* ptr, int rows, int ld) 
   return BO_OK;
 }
 
-int launch_posterior_gemm_tma(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  CUtensorMap mA, mL, mE;
-  int rc;
-  if ((rc = make_tile_map(&mA, a.Kx, a.rows, a.ldk)) != BO_OK) return rc;
-  if ((rc = make_tile_map(&mL, a.Linv, a.Nr, a.ldk)) != BO_OK) return rc;
-  if ((rc = make_tile_map(&mE, a.Ext, a.n_ext, a.ldk)) != BO_OK) return rc;
-  static bool attr_set = false;
-  const size_t smem = (size_t)P2_ST * P2_STAGE_BYTES + 2 * P2_ST * 8 + 1024;
-  if (!attr_set) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+static bool use_v2(const PostGemmArgs& a) {
+  static int force_v1 = -1;
+  if (force_v1 < 0) { const char* e = getenv("EVEREST_GEMM_V1"); force_v1 = (e && e[0] == '1') ? 1 : 0; }
+  const bool q_ok = (a.q == 1 || a.q == 2 || a.q == 4 || a.q == 8);
+  return q_ok && !force_v1 && ((uintptr_t)a.Kx % 16) == 0 && ((uintptr_t)a.B % 16) == 0;
+}
+
+// All outputs of one forward in as few launches as possible (v2: up to 8 outputs per launch).
+int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, cudaStream_t s, LaunchCounter* lc) {
+  if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
+  for (int m = 0; m < n_out; ++m) {
+    const PostGemmArgs& a = args[m];
+    if (a.q < 1 || a.q > BO_MAX_Q || a.rows % a.q != 0) { bo_set_error("posterior_gemm: bad q"); return BO_ERR_INVALID; }
+    if (a.ldk % GK != 0 || a.Rpad % PG_BN != 0 || a.N + a.n_ext > a.Rpad) { bo_set_error("posterior_gemm: padding violated"); return BO_ERR_INVALID; }
   }
-  const int grid = (a.rows + PG_BM - 1) / PG_BM;
-  posterior_gemm_tma_kernel<<<grid, PG_THREADS, smem, s>>>(mA, mL, mE, a);
-  if (lc) lc->n++;
-  CUDA_CHECK_RET(cudaGetLastError());
+  if (use_v2(args[0])) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)P2_ST * P2_STAGE_BYTES + 2 * P2_ST * 8 + 1024;
+    if (!attr_set) {
+      CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    for (int m0 = 0; m0 < n_out; m0 += P2_MAXOUT) {
+      const int cnt = (n_out - m0 < P2_MAXOUT) ? (n_out - m0) : P2_MAXOUT;
+      P2Batch batch;
+      memset(&batch, 0, sizeof(batch));
+      for (int i = 0; i < cnt; ++i) {
+        const PostGemmArgs& a = args[m0 + i];
+        int rc;
+        if ((rc = make_tile_map(&batch.item[i].mapA, a.Kx, a.rows, a.ldk)) != BO_OK) return rc;
+        if ((rc = make_tile_map(&batch.item[i].mapB, a.B, a.Rpad, a.ldk)) != BO_OK) return rc;
+        batch.item[i].a = a;
+      }
+      dim3 grid((args[m0].rows + PG_BM - 1) / PG_BM, cnt);
+      posterior_gemm_tma_kernel<<<grid, PG_THREADS, smem, s>>>(batch);
+      if (lc) lc->n++;
+      CUDA_CHECK_RET(cudaGetLastError());
+    }
+    return BO_OK;
+  }
+  static bool attr_set1 = false;
+  const size_t smem1 = posterior_gemm_smem_bytes();
+  if (!attr_set1) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    attr_set1 = true;
+  }
+  for (int m = 0; m < n_out; ++m) {
+    const PostGemmArgs& a = args[m];
+    int nbat_cta = PG_BM / a.q;
+    int nbat = a.rows / a.q;
+    int grid = (nbat + nbat_cta - 1) / nbat_cta;
+    posterior_gemm_kernel<<<grid, PG_THREADS, smem1, s>>>(a);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+  }
   return BO_OK;
+}
+
+int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
+  return launch_posterior_gemm_multi(&a, 1, s, lc);
 }
