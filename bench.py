@@ -311,7 +311,7 @@ def run_b200(args):
         for _ in range(reps):
             acq(X)
             torch.cuda.synchronize(device)
-            for name in ("prep", "crosscov", "posterior_gemm", "cond_root", "mc_acqf"):
+            for name in ("prep", "crosscov", "posterior_gemm", "cond_root", "sample_gemm", "mc_acqf"):
                 t, cnt = st.last_timing(name)
                 per.setdefault(name, []).append((t, cnt))
         st.set_timing(False)

@@ -216,6 +216,12 @@ cond_root_kernel(CondRootArgs a) {
     int j = idx / nr, c = idx % nr;
     root[idx] = (c < nb) ? Sqb[j * nb + c] : Lq[j * q + (c - nb)];
   }
+  if (a.BL) {
+    for (int idx = lane; idx < q * a.ldbl; idx += 32) {
+      int j = idx / a.ldbl, c = idx % a.ldbl;
+      a.BL[(size_t)(row0 + j) * a.ldbl + c] = (c < nb) ? Sqb[j * nb + c] : 0.0;
+    }
+  }
   for (int j = lane; j < q; j += 32)
     a.mu[((size_t)(row0 + j)) * a.M + a.m] = (md.mean_const + a.mu_raw[row0 + j]) * md.y_std + md.y_mean;
 }
@@ -591,7 +597,8 @@ mc_hvi_kernel(McArgs a) {
       for (int m = 0; m < M; ++m) {
         const double* rr = root + ((size_t)m * q + j) * nr;
         double sb = 0.0, sq = 0.0;
-        for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+        if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
+        else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
         for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
         y[m] = (mu[j * M + m] + sb) + sq;
       }
@@ -663,8 +670,173 @@ mc_hvi_kernel(McArgs a) {
   }
 }
 
-int launch_mc_hvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
+// Tiled variant for small cell lists (2-objective fronts): a CTA owns 64 MC samples x 64 q-batches, keeps
+// the samples' cells and new-point base samples in shared memory (read once per CTA instead of once
+// per q-batch) and takes the baseline part bl z_b from the sample GEMM.  Thread = (sample, batch lane);
+// per-batch sums over the CTA's 64 samples go to partial[sample_group][batch], reduced by a second
+// tiny kernel in a fixed order (deterministic).
+#define MT_S 64
+#define MT_B 64
+template <int QMAX, int MO>
+__global__ void __launch_bounds__(256)
+mc_hvi_tiled_kernel(McArgs a, int maxc) {
+  extern __shared__ double tsm[];
+  const int tid = threadIdx.x, sl = tid & 63, bl = tid >> 6;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
+  const int s0 = blockIdx.x * MT_S, b0 = blockIdx.y * MT_B;
+  double* clo = tsm;                              // [maxc*MO][64]
+  double* cup = clo + (size_t)maxc * MO * MT_S;   // [maxc*MO][64]
+  double* zq = cup + (size_t)maxc * MO * MT_S;    // [q*M][64]
+  double* half = zq + (size_t)q * M * MT_S;       // [8] warp sums
+  int* ncs = reinterpret_cast<int*>(half + 8);    // [64]
+  for (int i = tid; i < MT_S; i += 256) ncs[i] = (s0 + i < S) ? a.ncells[s0 + i] : 0;
+  for (int idx = tid; idx < maxc * MO * MT_S; idx += 256) {
+    int ss = idx & 63, co = idx >> 6;
+    bool ok = s0 + ss < S;
+    clo[idx] = ok ? a.cell_lo[(size_t)co * S + s0 + ss] : 0.0;
+    cup[idx] = ok ? a.cell_up[(size_t)co * S + s0 + ss] : 0.0;
+  }
+  for (int idx = tid; idx < q * M * MT_S; idx += 256) {
+    int ss = idx & 63, km = idx >> 6;
+    zq[idx] = (s0 + ss < S) ? a.zqT[(size_t)km * S + s0 + ss] : 0.0;
+  }
+  __syncthreads();
+  const int s = s0 + sl;
+  const bool s_ok = s < S;
+  const int nc = ncs[sl];
+  const bool has_cons = a.od.n_cons > 0;
+  for (int bat = bl; bat < MT_B; bat += 4) {
+    const int batch = b0 + bat;
+    if (batch >= a.b) break;  // uniform for the two warps of a batch lane
+    double acc = 0.0;
+    if (s_ok) {
+      double obj[QMAX][MO], fwt[QMAX];
+#pragma unroll
+      for (int j = 0; j < QMAX; ++j) {
+        fwt[j] = 1.0;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) obj[j][o] = -INFINITY;  // unused slots never overlap a cell
+        if (j < q) {
+          double y[2 * BO_MAX_OBJECTIVES];
+          for (int m = 0; m < M; ++m) {
+            const double* rr = a.root + (((size_t)batch * M + m) * q + j) * nr + nb;
+            double sb = (nb > 0) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0;
+            double sq = 0.0;
+            for (int k = 0; k < q; ++k) sq = fma(rr[k], zq[(k * M + m) * MT_S + sl], sq);
+            y[m] = (a.mu[((size_t)batch * q + j) * M + m] + sb) + sq;
+          }
+#pragma unroll
+          for (int o = 0; o < MO; ++o) obj[j][o] = objective_apply(a.od.op[o], y);
+          if (has_cons) {
+            double w = 1.0;
+            for (int c = 0; c < a.od.n_cons; ++c) {
+              double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+              w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+            }
+            fwt[j] = w;
+          }
+        }
+      }
+      for (int c = 0; c < nc; ++c) {
+        double lo[MO], len[QMAX][MO];
+        unsigned active = 0;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) lo[o] = clo[(c * MO + o) * MT_S + sl];
+#pragma unroll
+        for (int j = 0; j < QMAX; ++j) {
+          bool pos = true;
+#pragma unroll
+          for (int o = 0; o < MO; ++o) {
+            len[j][o] = fmin(obj[j][o], cup[(c * MO + o) * MT_S + sl]) - lo[o];
+            pos = pos && (len[j][o] > 0.0);
+          }
+          if (pos) active |= (1u << j);
+        }
+        if (!active) continue;
+        double cell = 0.0;
+        for (int size = 1; size <= q; ++size) {
+          double asum = 0.0;
+          bool any = false;
+          for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+            if (__popc(sub) != size) continue;
+            any = true;
+            double vol = 1.0;
+#pragma unroll
+            for (int o = 0; o < MO; ++o) {
+              double mn = INFINITY;
+#pragma unroll
+              for (int j = 0; j < QMAX; ++j)
+                if ((sub >> j) & 1u) mn = fmin(mn, len[j][o]);
+              vol *= fmax(mn, 0.0);
+            }
+            if (has_cons) {
+#pragma unroll
+              for (int j = 0; j < QMAX; ++j)
+                if ((sub >> j) & 1u) vol *= fwt[j];
+            }
+            asum += vol;
+          }
+          if (any) cell += (size & 1) ? asum : -asum;
+        }
+        acc += cell;
+      }
+    }
+    // sum over this CTA's 64 samples: two warps share one batch lane
+    double wsum = warp_sum(acc);
+    if ((tid & 31) == 0) half[tid >> 5] = wsum;
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;\n" ::"r"(1 + bl));
+    if (sl == 0) a.partial[(size_t)blockIdx.x * a.b + batch] = half[bl * 2] + half[bl * 2 + 1];
+    asm volatile("bar.sync %0, 64;\n" ::"r"(1 + bl));
+  }
+}
+
+typedef void (*McTiledFn)(McArgs, int);
+template <int MO>
+static McTiledFn pick_tiled_q(int q) {
+  if (q <= 2) return mc_hvi_tiled_kernel<2, MO>;
+  if (q <= 4) return mc_hvi_tiled_kernel<4, MO>;
+  if (q <= 8) return mc_hvi_tiled_kernel<8, MO>;
+  return nullptr;
+}
+static McTiledFn pick_tiled(int q, int Mo) {
+  if (Mo == 2) return pick_tiled_q<2>(q);
+  if (Mo == 3) return pick_tiled_q<3>(q);
+  if (Mo == 4) return pick_tiled_q<4>(q);
+  return nullptr;
+}
+
+__global__ void mc_reduce_partials_kernel(const double* __restrict__ partial, int groups, int b, int S,
+                                          double* __restrict__ out, const int* __restrict__ info_in, int M,
+                                          int* __restrict__ info_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  double t = 0.0;
+  for (int g = 0; g < groups; ++g) t += partial[(size_t)g * b + i];
+  out[i] = t / (double)S;
+  if (info_out) {
+    int v = 0;
+    for (int m = 0; m < M; ++m) v |= info_in[(size_t)i * M + m];
+    info_out[i] = v;
+  }
+}
+
+int launch_mc_hvi(const McArgs& a, int max_cells, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
+  const int Mo = a.od.n_obj;
+  // tiled path: needs per-sample cells, the sample GEMM output (or no baseline) and a cell list that fits
+  size_t tiled = ((size_t)2 * max_cells * Mo * MT_S + (size_t)a.q * a.M * MT_S + 8) * sizeof(double) + MT_S * sizeof(int);
+  McTiledFn fn = pick_tiled(a.q, Mo);
+  if (fn && !a.cells_shared && a.partial && (a.nb == 0 || a.Fp) && tiled <= 100 * 1024) {
+    if (tiled > 48 * 1024) CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled));
+    dim3 grid((a.S + MT_S - 1) / MT_S, (a.b + MT_B - 1) / MT_B);
+    fn<<<grid, 256, tiled, st>>>(a, max_cells);
+    if (lc) lc->n++;
+    mc_reduce_partials_kernel<<<(a.b + 255) / 256, 256, 0, st>>>(a.partial, grid.x, a.b, a.S, a.out, a.info_in, a.M, a.info_out);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return BO_OK;
+  }
   const int nt = 256;
   size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + (size_t)a.q * a.od.n_obj * nt + (size_t)a.q * nt + 32) *
                 sizeof(double);

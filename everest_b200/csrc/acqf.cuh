@@ -13,6 +13,8 @@ struct CondRootArgs {
   const double* Lb;      // [nb, ldlb] cached baseline root of output m
   int ldlb;
   double* root;          // [b, M, q, nb+q]
+  double* BL;            // [b*q, ldbl] copy of bl for output m, zero padded (operand of the sample GEMM) or NULL
+  int ldbl;
   double* mu;            // [b*q, M]
   int* info;             // [b, M] or NULL
   double* jitter;        // [b, M] or NULL
@@ -25,6 +27,9 @@ struct McArgs {
   const double* mu;
   const double* zbT;      // [(e*M+m)*S + s]
   const double* zqT;      // [(k*M+m)*S + s]
+  const double* Fp;       // [M][b*q][S] baseline part bl z_b of every sample (DMMA GEMM) or NULL
+  size_t fp_stride;       // elements between outputs in Fp
+  double* partial;        // [ceil(S/64)][b] per-sample-group sums (tiled kernel)
   const double* cell_lo;  // [(c*Mo+o)*S + s]  (or [(c*Mo+o)] when cells_shared)
   const double* cell_up;
   const int* ncells;      // [S] (or [1])
@@ -55,5 +60,5 @@ int launch_partition2d(const double* obj, const unsigned char* front, int n, int
 int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc);
-int launch_mc_hvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_hvi(const McArgs& a, int max_cells, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc);

@@ -113,7 +113,8 @@ struct bo_state {
   int nb = 0, S = 0, ldlb = 0, cap = 0;
   ObjD od;
   double best_f = 0.0;
-  DevBuf zbT, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b;
+  DevBuf zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
+  int max_cells = 0;
   int cells_shared = 0;
   // host staging for the HOST-buffer entry point
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
@@ -151,7 +152,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
-                  &st->cell_up, &st->ncells, &st->front_idx, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
+                  &st->cell_up, &st->ncells, &st->front_idx, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
                   &st->stage_in, &st->stage_out};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
@@ -540,9 +541,9 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
   CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
   RC(st->mean_b.ensure((size_t)std::max(nb, 1) * M * 8));
   RC(st->zbT.ensure((size_t)std::max(nb, 1) * M * S * 8));
-  RC(st->wsZM.ensure((size_t)M * S * ldlb * 8, true));
+  RC(st->zbM.ensure((size_t)M * S * ldlb * 8, true));
   RC(st->wsF.ensure((size_t)M * S * ldlb * 8));
-  if (nb > 0) RC(launch_transpose_base_samples(zb_dev, S, nb, M, st->zbT.as<double>(), st->wsZM.as<double>(), ldlb, s, &st->lc));
+  if (nb > 0) RC(launch_transpose_base_samples(zb_dev, S, nb, M, st->zbT.as<double>(), st->zbM.as<double>(), ldlb, s, &st->lc));
   for (int m = 0; m < M; ++m) {
     OutputH& o = st->out[m];
     if (nb > 0) {
@@ -555,7 +556,7 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
       RC(build_linv_ext(st, o, nb, s));
       RC(launch_gemm_nt(nb, st->N, st->N, 1.0, st->wsV.as<double>(), ldk, o.LinvT.as<double>(), ldk, 0.0,
                         o.LinvExt.as<double>() + (size_t)(st->N + 1) * ldk, ldk, false, s, &st->lc));
-      RC(launch_gemm_nt(S, nb, nb, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldlb, ldlb, o.Lb.as<double>(), ldlb, 0.0,
+      RC(launch_gemm_nt(S, nb, nb, 1.0, st->zbM.as<double>() + (size_t)m * S * ldlb, ldlb, o.Lb.as<double>(), ldlb, 0.0,
                         st->wsF.as<double>() + (size_t)m * S * ldlb, ldlb, false, s, &st->lc));
     } else {
       RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
@@ -569,7 +570,8 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
   RC(st->wsFeas.ensure((size_t)S * std::max(nb, 1)));
   RC(launch_baseline_objective(st->wsF.as<double>(), ldlb, S, nb, M, st->mean_b.as<double>(), st->od, st->obj_b.as<double>(),
                                st->wsFeas.as<unsigned char>(), st->samples_b.as<double>(), s, &st->lc));
-  RC(build_cells(st, st->obj_b.as<double>(), st->wsFeas.as<unsigned char>(), nb, S, n_obj, max_cells, s));
+  RC(build_cells(st, st->obj_b.as<double>(), st->wsFeas.as<unsigned char>(), nb, S, n_obj, &st->max_cells, s));
+  if (max_cells) *max_cells = st->max_cells;
   st->acqf_kind = 1;
   return BO_OK;
 }
@@ -592,7 +594,8 @@ extern "C" int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, 
     RC(o.Lb.ensure(16));
     RC(build_linv_ext(st, o, 0, s));
   }
-  RC(build_cells(st, Yobj_dev, st->wsFeas.as<unsigned char>(), n, 1, n_obj, max_cells, s));
+  RC(build_cells(st, Yobj_dev, st->wsFeas.as<unsigned char>(), n, 1, n_obj, &st->max_cells, s));
+  if (max_cells) *max_cells = st->max_cells;
   st->acqf_kind = 2;
   return BO_OK;
 }
@@ -653,6 +656,13 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
   RC(st->wsRoot.ensure((size_t)bchunk * M * q * nr * 8));
   RC(st->wsMu.ensure(rows_max * M * 8));
   RC(st->wsJit.ensure((size_t)bchunk * M * sizeof(int)));
+  const bool sample_gemm = (nb > 0 && st->acqf_kind == 1);
+  const int ldbl = st->ldlb;
+  if (sample_gemm) {
+    RC(st->wsBL.ensure(rows_max * ldbl * 8 * M));
+    RC(st->wsFp.ensure(rows_max * (size_t)S * 8 * M));
+  }
+  RC(st->wsPartial.ensure((size_t)((S + 63) / 64) * bchunk * 8));
   std::vector<PostGemmArgs> pg(M);
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
@@ -682,9 +692,17 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
       c.Gqq = pg[m].Gqq; c.W = pg[m].W; c.ldw = ldw; c.mu_raw = pg[m].mu_raw;
       c.Lb = o.Lb.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
       c.info = st->wsJit.as<int>(); c.jitter = nullptr;
+      c.BL = sample_gemm ? st->wsBL.as<double>() + (size_t)m * rows_max * ldbl : nullptr; c.ldbl = ldbl;
       rec_begin(st, "cond_root", s);
       RC(launch_cond_root(c, s, &st->lc));
       rec_end(st, s);
+      if (sample_gemm) {
+        // baseline part of every MC sample, F'[row, s] = sum_e bl[row, e] z_b[s, e], on the tensor pipe
+        rec_begin(st, "sample_gemm", s);
+        RC(launch_gemm_nt(rows, S, nb, 1.0, c.BL, ldbl, st->zbM.as<double>() + (size_t)m * S * ldbl, ldbl, 0.0,
+                          st->wsFp.as<double>() + (size_t)m * rows_max * S, S, false, s, &st->lc));
+        rec_end(st, s);
+      }
     }
     McArgs ma;
     ma.b = bc; ma.q = q; ma.nb = nb; ma.M = M; ma.S = S; ma.od = st->od; ma.root = st->wsRoot.as<double>();
@@ -692,9 +710,11 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
     ma.cell_lo = st->cell_lo.as<double>(); ma.cell_up = st->cell_up.as<double>(); ma.ncells = st->ncells.as<int>();
     ma.cells_shared = st->cells_shared; ma.best_f = st->best_f; ma.out = out_dev + b0;
     ma.info_in = st->wsJit.as<int>(); ma.info_out = info_dev ? info_dev + b0 : nullptr;
+    ma.Fp = sample_gemm ? st->wsFp.as<double>() : nullptr; ma.fp_stride = rows_max * (size_t)S;
+    ma.partial = st->wsPartial.as<double>();
     rec_begin(st, "mc_acqf", s);
     if (st->acqf_kind == 3) RC(launch_mc_logei(ma, s, &st->lc));
-    else RC(launch_mc_hvi(ma, s, &st->lc));
+    else RC(launch_mc_hvi(ma, st->max_cells, s, &st->lc));
     rec_end(st, s);
   }
   return BO_OK;
