@@ -76,7 +76,7 @@ def workload_config(p, n_gpus, extra=None):
 # ----------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the BoTorch op sequence, all host threads)
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_setup(p, baseline_idx=None):
+def cpu_reference_setup(p, baseline_idx=None, cell_bounds=None):
     from tests import problems as P
     from oracle import bo_oracle as O
 
@@ -88,7 +88,7 @@ def cpu_reference_setup(p, baseline_idx=None):
         else:  # reuse the pruned baseline found by the device path (same points; saves CPU set-up time)
             acq = O.QNEHVIOracle(gp, p["ref_point"], torch.as_tensor(p["X"])[baseline_idx],
                                  [P.op_to_oracle(o) for o in p["objective"].ops], mc_samples=p["S"],
-                                 seed=p["sampler_seed"], prune_baseline=False)
+                                 seed=p["sampler_seed"], prune_baseline=False, cell_bounds=cell_bounds)
     else:
         acq = P.oracle_acqf(p, gp)
     return acq
@@ -339,8 +339,20 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             idx = acq.prune_idx.cpu() if getattr(acq, "prune_idx", None) is not None else None
-            acq_cpu = cpu_reference_setup(p, baseline_idx=idx)
-            n = args.cpu_sample or (256 if p["acqf"] == "qnehvi" else 1024)
+            cells = None
+            if p["acqf"] == "qnehvi" and len(p["ref_point"]) > 2:
+                # the oracle's pure-Python Lacour decomposition of 512 fronts takes minutes: time its forward pass
+                # on the device's cell list (padded with empty cells), which the parity tests pin at small sizes
+                lo, up, nc = acq.cell_bounds()
+                C = int(nc.max())
+                ref = torch.tensor(p["ref_point"], dtype=torch.double)
+                lo, up = lo[:, :C].clone(), up[:, :C].clone()
+                pad = torch.arange(C).unsqueeze(0) >= nc.unsqueeze(1)
+                lo[pad] = ref
+                up[pad] = ref
+                cells = (lo, up)
+            acq_cpu = cpu_reference_setup(p, baseline_idx=idx, cell_bounds=cells)
+            n = args.cpu_sample or ((256 if cells is None else 16) if p["acqf"] == "qnehvi" else 1024)
             Xc = X_host[:n]
             cpu_time_forward(acq_cpu, Xc[:8], 8)
             v8, dt8 = cpu_time_forward(acq_cpu, Xc, 8)

@@ -515,7 +515,7 @@ class QNEHVIOracle:
 
     def __init__(self, gp: GPOracle, ref_point, X_baseline, objective_ops, constraints=None,
                  mc_samples=512, seed=1234, prune_baseline=True, prune_samples=2048,
-                 prune_seed=4321, X_pending=None, base_samples_baseline=None):
+                 prune_seed=4321, X_pending=None, base_samples_baseline=None, cell_bounds=None):
         self.gp = gp
         self.ref = torch.as_tensor(ref_point, dtype=DT)
         self.ops = objective_ops
@@ -533,6 +533,9 @@ class QNEHVIOracle:
         self.Xb = Xb
         self.nb = Xb.shape[0]
         self.zb = base_samples_baseline
+        # cell_bounds=(lower, upper) [S, C, m] skips the (slow, pure-Python) box decomposition: used only by
+        # bench.py to TIME the forward pass of the many-objective config, never by the parity tests
+        self._injected_cells = cell_bounds
         self._set_cell_bounds()
 
     # -- [UPSTREAM] prune_inferior_points_multi_objective
@@ -571,6 +574,11 @@ class QNEHVIOracle:
             obj = torch.zeros(S, 0, self.Mo, dtype=DT)
             feas = None
         self.obj_b = obj
+        if self._injected_cells is not None:
+            self.cell_lower, self.cell_upper = self._injected_cells
+            self.n_cells = torch.full((S,), self.cell_lower.shape[1])
+            self.fronts = None
+            return
         lows, ups, fronts = [], [], []
         for s in range(S):
             Ys = obj[s] if feas is None else obj[s][feas[s]]

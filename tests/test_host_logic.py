@@ -182,3 +182,47 @@ def test_sharded_forward_world_size_2_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_bofire_data_model_adapter():
+    """map_kernel / objectives_from_outputs against the reference's own data models (importable here; the
+    GPU box has no /root/reference, so skip there)."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not available")
+    sys.path.insert(0, ref)
+    try:
+        import bofire.data_models.kernels.api as dk
+        from bofire.data_models.domain.api import Outputs
+        from bofire.data_models.features.api import ContinuousOutput
+        from bofire.data_models.objectives.api import MaximizeObjective, MaximizeSigmoidObjective, MinimizeObjective
+    except Exception as exc:  # pragma: no cover
+        pytest.skip(f"bofire data models not importable: {exc}")
+    finally:
+        sys.path.remove(ref)
+    from everest_b200 import bofire_adapter as BA
+
+    layout = {"x1": [0], "x2": [1], "c1": [2, 3, 4], "c2": [5, 6]}
+    mapper = lambda feats: [i for f in feats for i in layout[f]]  # noqa: E731
+    dm = dk.AdditiveKernel(kernels=[
+        dk.ScaleKernel(base_kernel=dk.MaternKernel(ard=True, nu=2.5, features=["x1", "x2"])),
+        dk.ScaleKernel(base_kernel=dk.MultiplicativeKernel(kernels=[
+            dk.RBFKernel(ard=False, features=["x1", "x2"]), dk.HammingDistanceKernel(ard=True, features=["c1", "c2"])]))])
+    hyper = {"kernels.0": {"outputscale": 1.5}, "kernels.0.base_kernel": {"lengthscale": [0.3, 0.4]},
+             "kernels.1": {"outputscale": 0.5}, "kernels.1.base_kernel.kernels.0": {"lengthscale": [0.9]},
+             "kernels.1.base_kernel.kernels.1": {"lengthscale": [1.0, 2.0, 0, 0, 0]}}
+    spec = BA.map_kernel(dm, active_dims=list(range(7)), features_to_idx_mapper=mapper, hyper=hyper)
+    flat = K.flatten(spec)
+    assert [type(l).__name__ for l in flat.leaves] == ["MaternKernel", "RBFKernel", "HammingDistanceKernel"]
+    assert flat.terms == [(1.5, [0]), (0.5, [1, 2])]
+    assert flat.leaves[2].categorical_features == {2: 3, 5: 2}  # same one-hot layout as mapper.py:223-245 (offset by active dims)
+    with pytest.raises(RuntimeError):
+        BA.map_kernel(dk.HammingDistanceKernel(features=["x1"]), list(range(7)), mapper)
+    with pytest.raises(NotImplementedError):
+        BA.map_kernel(dk.LinearKernel(), list(range(7)), mapper)
+    outs = Outputs(features=[ContinuousOutput(key="a", objective=MaximizeObjective(w=1.0, bounds=(0, 2))),
+                             ContinuousOutput(key="b", objective=MaximizeSigmoidObjective(w=1.0, steepness=4.0, tp=1.5)),
+                             ContinuousOutput(key="c", objective=MinimizeObjective(w=1.0))])
+    mo, cons = BA.objectives_from_outputs(outs)
+    assert [(o.kind, o.idx, o.p0, o.p1) for o in mo.ops] == [("max", 0, 0.0, 2.0), ("min", 2, 0.0, 1.0)]
+    assert [(c.idx, c.sign, c.tp, c.eta) for c in cons] == [(1, -1.0, 1.5, 0.25)]
