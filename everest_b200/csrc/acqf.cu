@@ -125,12 +125,24 @@ cond_root_kernel(CondRootArgs a) {
   extern __shared__ double csm[];
   const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int batch = blockIdx.x * 4 + warp_in_cta;
-  if (batch >= a.b) return;
   const int q = a.q, nb = a.nb, nr = nb + q;
   const ModelD& md = a.md;
-  double* Sqb = csm + (size_t)warp_in_cta * (q * nr + 2 * q * q);  // [q][nb] -> becomes bl in place
-  double* Sc = Sqb + q * nb;                                        // [q][q]
-  double* Lq = Sc + q * q;                                          // [q][q]
+  // per-warp scratch, then (optionally) the CTA-shared copy of L_b^-1
+  double* Sqb = csm + (size_t)warp_in_cta * (2 * q * nb + 2 * q * q);  // [q][nb]
+  double* Sc = Sqb + q * nb;                                            // [q][q]
+  double* Lq = Sc + q * q;                                              // [q][q]
+  double* BLs = Lq + q * q;                                             // [q][nb] bl
+  const double* Li = a.LbInv;
+  int ldli = a.ldlb;
+  if (a.linv_in_smem) {
+    double* Ls = csm + (size_t)4 * (2 * q * nb + 2 * q * q);
+    ldli = nb | 1;  // odd stride: lanes (rows e) hit distinct banks
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x)
+      Ls[(idx / nb) * ldli + (idx % nb)] = a.LbInv[(size_t)(idx / nb) * a.ldlb + (idx % nb)];
+    Li = Ls;
+  }
+  __syncthreads();
+  if (batch >= a.b) return;
   const double s2 = md.y_std * md.y_std;
   const int row0 = batch * q;
 
@@ -149,24 +161,22 @@ cond_root_kernel(CondRootArgs a) {
     }
   }
   __syncwarp();
-  // forward substitution: bl[j][e] = (Sqb[j][e] - sum_{l<e} bl[j][l] Lb[e][l]) / Lb[e][e]
-  for (int e = 0; e < nb; ++e) {
-    const double* Lrow = a.Lb + (size_t)e * a.ldlb;
-    const double diag = Lrow[e];
+  // bl = Sqb L_b^-T with the cached inverse root: bl[j][e] = sum_{l<=e} Sqb[j][l] LbInv[e][l]  (lanes over e)
+  for (int e = lane; e < nb; e += 32) {
+    const double* lrow = Li + (size_t)e * ldli;
     for (int j = 0; j < q; ++j) {
       double s = 0.0;
-      for (int l = lane; l < e; l += 32) s = fma(Sqb[j * nb + l], Lrow[l], s);
-      s = warp_sum(s);
-      if (lane == 0) Sqb[j * nb + e] = (Sqb[j * nb + e] - s) / diag;
+      for (int l = 0; l <= e; ++l) s = fma(Sqb[j * nb + l], lrow[l], s);
+      BLs[j * nb + e] = s;
     }
-    __syncwarp();
   }
+  __syncwarp();
   // Sc -= bl bl^T
   for (int p = 0; p < q * q; ++p) {
     int i = p / q, j = p % q;
     if (j < i) continue;
     double s = 0.0;
-    for (int e = lane; e < nb; e += 32) s = fma(Sqb[i * nb + e], Sqb[j * nb + e], s);
+    for (int e = lane; e < nb; e += 32) s = fma(BLs[i * nb + e], BLs[j * nb + e], s);
     s = warp_sum(s);
     if (lane == 0) {
       Sc[i * q + j] -= s;
@@ -214,21 +224,26 @@ cond_root_kernel(CondRootArgs a) {
   double* root = a.root + ((size_t)batch * a.M + a.m) * q * nr;
   for (int idx = lane; idx < q * nr; idx += 32) {
     int j = idx / nr, c = idx % nr;
-    root[idx] = (c < nb) ? Sqb[j * nb + c] : Lq[j * q + (c - nb)];
+    root[idx] = (c < nb) ? BLs[j * nb + c] : Lq[j * q + (c - nb)];
   }
   if (a.BL) {
     for (int idx = lane; idx < q * a.ldbl; idx += 32) {
       int j = idx / a.ldbl, c = idx % a.ldbl;
-      a.BL[(size_t)(row0 + j) * a.ldbl + c] = (c < nb) ? Sqb[j * nb + c] : 0.0;
+      a.BL[(size_t)(row0 + j) * a.ldbl + c] = (c < nb) ? BLs[j * nb + c] : 0.0;
     }
   }
   for (int j = lane; j < q; j += 32)
     a.mu[((size_t)(row0 + j)) * a.M + a.m] = (md.mean_const + a.mu_raw[row0 + j]) * md.y_std + md.y_mean;
 }
 
-int launch_cond_root(const CondRootArgs& a, cudaStream_t st, LaunchCounter* lc) {
-  if (a.b <= 0) return BO_OK;
-  size_t smem = (size_t)4 * (a.q * (a.nb + a.q) + 2 * a.q * a.q) * sizeof(double);
+int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc) {
+  if (a0.b <= 0) return BO_OK;
+  CondRootArgs a = a0;
+  size_t per_warp = (size_t)(2 * a.q * a.nb + 2 * a.q * a.q) * sizeof(double);
+  size_t smem = 4 * per_warp;
+  size_t linv = (size_t)a.nb * (a.nb | 1) * sizeof(double);
+  a.linv_in_smem = (a.nb > 0 && smem + linv <= 96 * 1024) ? 1 : 0;
+  if (a.linv_in_smem) smem += linv;
   if (smem > 200 * 1024) { bo_set_error("cond_root: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {

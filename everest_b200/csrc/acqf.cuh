@@ -11,7 +11,9 @@ struct CondRootArgs {
   int ldw;
   const double* mu_raw;  // [b*q]
   const double* Lb;      // [nb, ldlb] cached baseline root of output m
+  const double* LbInv;   // [nb, ldlb] its inverse (lower triangular): bl = Sqb LbInv^T
   int ldlb;
+  int linv_in_smem;      // set by the launcher
   double* root;          // [b, M, q, nb+q]
   double* BL;            // [b*q, ldbl] copy of bl for output m, zero padded (operand of the sample GEMM) or NULL
   int ldbl;

@@ -91,7 +91,7 @@ struct OutputH {
   // acquisition state
   PrepBuf base_prep;
   PrepD base_prepd;
-  DevBuf Lb, Sbb;
+  DevBuf Lb, Sbb, LbInv, LbInvT;
   // per-forward query prep
   PrepBuf q_prep;
   PrepD q_prepd;
@@ -146,7 +146,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (auto& o : st->out) {
     for (void* p : o.owned) cudaFree(p);
     o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
-    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb};
+    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
     for (DevBuf* b : bs) b->release();
   }
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
@@ -422,7 +422,8 @@ static int fill_objd(ObjD* od, const bo_objective_op* obj, int n_obj, const bo_c
 // Joint posterior at X (n points): mean_dev [n, M]; per output the lower Cholesky root of the
 // un-standardised covariance into roots[m] ([n, ldn]); V rows optionally kept in Vkeep[m] ([n, ldk]).
 static int joint_root(bo_state* st, int m, const double* X_dev, int n, int ldn, PrepBuf& pb, PrepD* pd, double* mean_dev,
-                      DevBuf& rootbuf, DevBuf& covcopy, double* Vdst, int* info, double* jit, cudaStream_t s) {
+                      DevBuf& rootbuf, DevBuf& covcopy, double* Vdst, int* info, double* jit, cudaStream_t s,
+                      DevBuf* dinv_keep = nullptr) {
   OutputH& o = st->out[m];
   const int ldk = st->ldk;
   RC(st->wsKx.ensure((size_t)n * ldk * 8));
@@ -436,7 +437,8 @@ static int joint_root(bo_state* st, int m, const double* X_dev, int n, int ldn, 
   RC(launch_gemm_nt(n, n, st->N, -1.0, Vdst, ldk, Vdst, ldk, 1.0, C, ldn, false, s, &st->lc));
   RC(launch_scale_matrix(C, ldn, n, n, o.md.y_std * o.md.y_std, s, &st->lc));
   DevBuf dinv_local;
-  int rc = psd_safe_chol(st, C, rootbuf.as<double>(), ldn, n, dinv_local, info, jit, s);
+  DevBuf& dinv = dinv_keep ? *dinv_keep : dinv_local;
+  int rc = psd_safe_chol(st, C, rootbuf.as<double>(), ldn, n, dinv, info, jit, s);
   dinv_local.release();
   return rc;
 }
@@ -549,9 +551,19 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
     if (nb > 0) {
       int inf = 0; double jit = 0;
       RC(st->wsV.ensure((size_t)nb * ldk * 8, true));
-      RC(joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, st->wsV.as<double>(), &inf, &jit, s));
+      DevBuf dinv_b;
+      int rcj = joint_root(st, m, Xb_dev, nb, ldlb, o.base_prep, &o.base_prepd, st->mean_b.as<double>(), o.Lb, o.Sbb, st->wsV.as<double>(), &inf, &jit, s, &dinv_b);
       if (info) info[m] = inf;
-      if (inf != 0) { bo_set_error("baseline posterior covariance not p.d. (output %d)", m); return BO_ERR_NOT_PSD; }
+      if (rcj != BO_OK) { dinv_b.release(); return rcj; }
+      if (inf != 0) { dinv_b.release(); bo_set_error("baseline posterior covariance not p.d. (output %d)", m); return BO_ERR_NOT_PSD; }
+      // inverse of the cached baseline root: the per-q-batch triangular solve becomes a small product
+      int rci = o.LbInv.ensure((size_t)round_up(nb, 64) * ldlb * 8, true);
+      if (rci == BO_OK) rci = o.LbInvT.ensure((size_t)round_up(nb, 64) * ldlb * 8, true);
+      if (rci == BO_OK) rci = st->wsTmp.ensure((size_t)64 * std::max(ldlb, st->ldk) * 8, true);
+      if (rci == BO_OK) rci = tri_inverse_blocked(o.Lb.as<double>(), ldlb, nb, dinv_b.as<double>(), o.LbInv.as<double>(), o.LbInvT.as<double>(), ldlb, st->wsTmp.as<double>(), s, &st->lc);
+      cudaStreamSynchronize(s);
+      dinv_b.release();
+      if (rci != BO_OK) return rci;
       // extra rows = V_b L^-1 = K_bX (K + s2 I)^-1, so that K*X (.)^T = V_q V_b^T
       RC(build_linv_ext(st, o, nb, s));
       RC(launch_gemm_nt(nb, st->N, st->N, 1.0, st->wsV.as<double>(), ldk, o.LinvT.as<double>(), ldk, 0.0,
@@ -690,7 +702,7 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
       CondRootArgs c;
       c.md = o.md; c.prep_q = o.q_prepd; c.prep_b = o.base_prepd; c.b = bc; c.q = q; c.nb = nb; c.M = M; c.m = m;
       c.Gqq = pg[m].Gqq; c.W = pg[m].W; c.ldw = ldw; c.mu_raw = pg[m].mu_raw;
-      c.Lb = o.Lb.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
+      c.Lb = o.Lb.as<double>(); c.LbInv = o.LbInv.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
       c.info = st->wsJit.as<int>(); c.jitter = nullptr;
       c.BL = sample_gemm ? st->wsBL.as<double>() + (size_t)m * rows_max * ldbl : nullptr; c.ldbl = ldbl;
       rec_begin(st, "cond_root", s);

@@ -254,6 +254,103 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path: one term, one continuous leaf with <= 32 (padded) dims -- the SingleTaskGP default
+// (RBF-ARD, or Scale(Matern)).  A CTA keeps its 64 query rows in shared memory and streams a strip of
+// CC3_CT column tiles of training rows through a cp.async double buffer; the kernel function is a
+// template parameter, so the per-element epilogue is branch-free.
+// ------------------------------------------------------------------------------------------------
+#define CC3_CT 8
+
+template <int ROWS>
+__device__ __forceinline__ void cc3_load_tile(double* dst, const double* __restrict__ src, int dpad, int row0, int n_valid,
+                                              int tid) {
+  const int chunks = dpad >> 1;  // 16-byte chunks per row
+  for (int c = tid; c < ROWS * chunks; c += 256) {
+    int r = c / chunks, ch = c - r * chunks;
+    bool p = (row0 + r) < n_valid;
+    cp_async16(dst + r * CC_LDS + ch * 2, src + (size_t)(p ? row0 + r : 0) * dpad + ch * 2, p);
+  }
+}
+
+#define CC3_CLD 66  // C tile row stride (doubles): 16-byte aligned rows, staggered banks
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2)
+crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n2a_g, int n_rows,
+                     const double* __restrict__ Bt, const double* __restrict__ n2b_g, int n_cols, int dpad,
+                     double coef, double* __restrict__ out, int ld, int same_set) {
+  extern __shared__ __align__(16) double cc3sm[];
+  double* As = cc3sm;
+  double* Bs[2] = {cc3sm + CC_TILE * CC_LDS, cc3sm + 2 * CC_TILE * CC_LDS};
+  double* Cs = cc3sm + 3 * CC_TILE * CC_LDS;  // [64][CC3_CLD] raw a.b dot products
+  double* n2a_s = Cs + CC_TILE * CC3_CLD;     // [64]
+  double* n2b_s = n2a_s + CC_TILE;            // [64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp & 3, wc = warp >> 2;
+  const int row0 = blockIdx.y * CC_TILE;
+  const int ct0 = blockIdx.x * CC3_CT;
+  const int n_ct_total = (ld + CC_TILE - 1) / CC_TILE;
+  const int n_ct = min(CC3_CT, n_ct_total - ct0);
+
+  cc3_load_tile<CC_TILE>(As, Aq, dpad, row0, n_rows, tid);
+  cc3_load_tile<CC_TILE>(Bs[0], Bt, dpad, ct0 * CC_TILE, n_cols, tid);
+  cp_async_commit();
+  if (tid < CC_TILE) n2a_s[tid] = (row0 + tid < n_rows) ? n2a_g[row0 + tid] : 0.0;
+  for (int ci = 0; ci < n_ct; ++ci) {
+    const int col0 = (ct0 + ci) * CC_TILE;
+    cp_async_wait<0>();
+    __syncthreads();  // tile ci landed; previous epilogue finished with Cs / n2b_s
+    if (ci + 1 < n_ct) cc3_load_tile<CC_TILE>(Bs[(ci + 1) & 1], Bt, dpad, col0 + CC_TILE, n_cols, tid);
+    cp_async_commit();
+    if (tid < CC_TILE) n2b_s[tid] = (col0 + tid < n_cols) ? n2b_g[col0 + tid] : 0.0;
+    const double* B = Bs[ci & 1];
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kk = 0; kk < dpad; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = As[(wr * 16 + i * 8 + g) * CC_LDS + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = B[(wc * 32 + j * 8 + g) * CC_LDS + kk + t];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(Cs + (wr * 16 + i * 8 + g) * CC3_CLD + wc * 32 + j * 8 + 2 * t) =
+            make_double2(acc[i][j][0], acc[i][j][1]);
+    __syncthreads();
+    // compact, coalesced epilogue: one instance of the kernel function in the instruction stream
+#pragma unroll 1
+    for (int idx = tid; idx < CC_TILE * (CC_TILE / 2); idx += 256) {
+      const int r = idx >> 5, c2 = (idx & 31) * 2;
+      const int gr = row0 + r, gc = col0 + c2;
+      if (gr >= n_rows || gc >= ld) continue;
+      const double2 d = *reinterpret_cast<const double2*>(Cs + r * CC3_CLD + c2);
+      const double na = n2a_s[r];
+      double s0 = fmax(na + n2b_s[c2] - 2.0 * d.x, 0.0);
+      double s1 = fmax(na + n2b_s[c2 + 1] - 2.0 * d.y, 0.0);
+      if (same_set) {
+        if (gr == gc) s0 = 0.0;
+        if (gr == gc + 1) s1 = 0.0;
+      }
+      const double v0 = (gc < n_cols) ? coef * leaf_value_from_stat(KIND, s0) : 0.0;
+      const double v1 = (gc + 1 < n_cols) ? coef * leaf_value_from_stat(KIND, s1) : 0.0;
+      if (gc + 1 < ld) *reinterpret_cast<double2*>(out + (size_t)gr * ld + gc) = make_double2(v0, v1);
+      else out[(size_t)gr * ld + gc] = v0;
+    }
+  }
+}
+
 int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_are_train, int n_cols, double* out,
                     int ld, bool same_set, cudaStream_t s, LaunchCounter* lc) {
   if (rows.n <= 0 || n_cols <= 0) return BO_OK;
@@ -271,6 +368,41 @@ int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_a
     } else {
       cs.s[l] = LeafSide{nullptr, nullptr, nullptr, nullptr, nullptr};
     }
+  }
+  if (md.n_terms == 1 && md.nfac[0] == 1 && md.leaf[md.fac[0][0]].kind <= BO_LEAF_MATERN52 &&
+      md.leaf[md.fac[0][0]].dpad <= CC_KC) {
+    const int l = md.fac[0][0];
+    const LeafD& L = md.leaf[l];
+    const int n_ct = (ld + CC_TILE - 1) / CC_TILE;
+    dim3 gridf((n_ct + CC3_CT - 1) / CC3_CT, (rows.n + CC_TILE - 1) / CC_TILE);
+    const double* Aq = rows.Xs[l];
+    const double* n2a = rows.n2[l];
+    const size_t smf = ((size_t)3 * CC_TILE * CC_LDS + (size_t)CC_TILE * CC3_CLD + 2 * CC_TILE) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_MATERN12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_MATERN32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      attr_set = true;
+    }
+    switch (L.kind) {
+      case BO_LEAF_RBF:
+        crosscov_fast_kernel<BO_LEAF_RBF><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        break;
+      case BO_LEAF_MATERN12:
+        crosscov_fast_kernel<BO_LEAF_MATERN12><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        break;
+      case BO_LEAF_MATERN32:
+        crosscov_fast_kernel<BO_LEAF_MATERN32><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        break;
+      default:
+        crosscov_fast_kernel<BO_LEAF_MATERN52><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        break;
+    }
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return BO_OK;
   }
   dim3 grid((ld + CC_TILE - 1) / CC_TILE, (rows.n + CC_TILE - 1) / CC_TILE);
   crosscov_kernel2<<<grid, 256, 0, s>>>(md, rows, cs, n_cols, out, ld, same_set ? 1 : 0);
