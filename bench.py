@@ -326,8 +326,12 @@ def run_b200(args):
         flops_per_launch = flops_per_step / g_cnt
         achieved = flops_per_step / (g_ms * 1e-3) / 1e12
         peak = measure_fp64_peak(device)
-        roofline = {"bound": "tensor", "kernel": "posterior_gemm_kernel (FP64 DMMA m8n8k4)", "achieved": achieved,
-                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        # DRAM bytes of one launch from the committed ncu --set full capture (profiles/r01_ncu_summary.txt); only valid
+        # for the default headline workload, null otherwise
+        traffic = 1.623e10 if (args.workload == "zdt1" and not args.raw_samples) else None
+        roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full)",
                     "peak_source": "torch.matmul f64 8192^3 (cuBLAS DGEMM) best of 5 measured in this run; "
                                    "MEASURED_PEAKS.json holds no fp64 figure; tools/fp64_peak measured 37.0 TFLOP/s "
                                    "for raw DMMA and DFMA issue on this pool",
@@ -366,6 +370,29 @@ def run_b200(args):
         except Exception as exc:  # the baseline must never take the headline number down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
 
+    # ---- ask() latency: acqf construction + screen + L-BFGS-B refinement of the restarts (rank 0, N=1) ----
+    ask = None
+    if rank == 0 and world == 1 and p.get("bounds") is not None:
+        from everest_b200 import optim
+
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        acq2 = Cf.build_acqf(p, st)
+        torch.cuda.synchronize(device)
+        t1 = time.perf_counter()
+        bnds = torch.as_tensor(p["bounds"])
+        Xic, Yic, _, _ = optim.gen_batch_initial_conditions(acq2, bnds, p["q"], p["num_restarts"], p["raw_samples"], seed=0)
+        torch.cuda.synchronize(device)
+        t2 = time.perf_counter()
+        maxit = 50
+        _, Yref, info = optim.gen_candidates_scipy(Xic, acq2, bnds[0], bnds[1], options={"maxiter": maxit})
+        torch.cuda.synchronize(device)
+        t3 = time.perf_counter()
+        ask = {"acqf_build_s": t1 - t0, "screen_s": t2 - t1, "refine_s": t3 - t2, "refine_maxiter": maxit,
+               "refine_iterations": info["nit"], "refine_acqf_evals": info["n_acqf_evals"],
+               "best_screened": float(Yic.max()), "best_refined": float(torch.maximum(Yref, Yic).max()),
+               "note": "refinement = scipy L-BFGS-B over all restarts with batched finite-difference gradients on the device"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -374,7 +401,7 @@ def run_b200(args):
             "config": workload_config(p, world, {
                 "n_baseline_after_pruning": int(acq.nb), "max_cells_per_sample": int(getattr(acq, "max_cells", 0)),
                 "l2": "per-step working set (K(X*,X) 1.05 GB per output + factors) >> 126 MB L2; no flush needed",
-                "qbatch_x_mc_samples_per_sec": value * p["S"], "setup_s": {"factorize": t_factor, "acqf_prepare": t_prepare}}),
+                "qbatch_x_mc_samples_per_sec": value * p["S"], "setup_s": {"factorize": t_factor, "acqf_prepare": t_prepare}, "ask_latency": ask}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b * q * d * 8), "d2h_bytes_per_step": int(b * 8)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }

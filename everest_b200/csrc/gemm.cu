@@ -348,7 +348,10 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   const uint32_t bar_empty = bar_full + P2_ST * 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
+  // column group of the warp: warps w and w+4 share an SM sub-partition and get groups (0,3) / (1,2), so the
+  // k-stages each may skip inside a diagonal block (L^-1 is lower triangular) are balanced per sub-partition
+  const int wc = (warp < 4) ? (warp >> 1) : (3 - ((warp - 4) >> 1));
+  const int wm0 = (warp & 1) * 64, wn0 = wc * 32;
   const int rho_g = (g >> 1) | ((g & 1) << 2);
   const int q = a.q, N = a.N, rows = a.rows;
   const int row0 = blockIdx.x * PG_BM;
@@ -397,6 +400,9 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   for (int jb = 0; jb < n_blocks; ++jb) {
     const int n0 = jb * PG_BN;
     const int nk = nk_of(jb);
+    // this warp's 32 columns are rows n0+wn0 .. n0+wn0+31 of LinvExt: if they are all L^-1 rows they vanish for
+    // k beyond the last of them
+    const int kneed = (n0 + wn0 + 32 <= N) ? (n0 + wn0 + 32) : kfull;
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -412,6 +418,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
       mbar_wait(bar_full + 8 * slot, (it / P2_ST) & 1);
       const unsigned char* As = sm + slot * P2_STAGE_BYTES;
       const unsigned char* Bs = As + P2_TILE_BYTES;
+      if (ks * GK < kneed) {
 #pragma unroll
       for (int kg = 0; kg < 2; ++kg) {
         const int off = kg ? offk1 : offk0;
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+      }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   // reduce the 4 column-warps' partial Grams and emit Gqq (q divides 8: a q-batch never straddles an 8-row group)
   __syncthreads();  // every warp is past its last tile read: the ring can be reused
   double* Gs = reinterpret_cast<double*>(sm);  // [4][128][8]
-  const int wcol = warp >> 1;
+  const int wcol = wc;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll

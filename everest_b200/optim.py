@@ -4,12 +4,15 @@ botorch.optim.optimize_acqf / optimize_acqf_discrete).
 
 Round-1 scope: the raw-sample screen runs as ONE device call over all raw_samples q-batches (the
 reference scores them in raw_samples / batch_limit sequential CPU calls), then
-`initialize_q_batch` picks the restarts.  The gradient refinement of the restarts ([UPSTREAM]
-gen_candidates_scipy, L-BFGS-B) needs d acqf / d X and is listed as the next step in DESIGN.md; until
-then `optimize_acqf` returns the best screened restart.
+`initialize_q_batch` picks the restarts, then `gen_candidates_scipy` refines them with scipy's L-BFGS-B
+exactly like [UPSTREAM] botorch.generation.gen_candidates_scipy (all restarts as one vector, loss =
+-sum acqf, box bounds, fixed features).  The gradient is a central finite difference evaluated in ONE
+batched device call per iteration (the MC acquisition value is deterministic for fixed base samples);
+the analytic adjoint kernels are the next step.
 """
 from typing import Dict, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import sampling
@@ -74,16 +77,91 @@ def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num
     return X_ic, Y_rnd.cpu()[idcs], X_rnd, Y_rnd
 
 
+def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function, lower_bounds, upper_bounds,
+                         fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None):
+    """[UPSTREAM] botorch.generation.gen_candidates_scipy for box bounds: joint L-BFGS-B over all restarts.
+    Returns (candidates [r, q, d] CPU, acq values [r] CPU).  options: maxiter (default 2000, BoFire's
+    `maxiter`), fd_step (relative to the bound width, default 1e-6)."""
+    from scipy.optimize import minimize
+
+    options = options or {}
+    maxiter = int(options.get("maxiter", 2000))
+    rel_h = float(options.get("fd_step", 1e-6))
+    X0 = torch.as_tensor(initial_conditions, dtype=torch.double).cpu().clone()
+    r, q, d = X0.shape
+    lb = torch.as_tensor(lower_bounds, dtype=torch.double).cpu().expand(d).clone()
+    ub = torch.as_tensor(upper_bounds, dtype=torch.double).cpu().expand(d).clone()
+    free = [j for j in range(d) if not (fixed_features and j in fixed_features) and float(ub[j]) > float(lb[j])]
+    X0 = apply_fixed_features(X0, fixed_features)
+    h = rel_h * (ub - lb)
+    nf = len(free)
+    free_t = torch.tensor(free, dtype=torch.long)
+    device = acquisition_function.model.device
+    state = {"n_eval": 0}
+
+    def unpack(x):
+        X = X0.clone()
+        X[:, :, free_t] = torch.from_numpy(x).view(r, q, nf)
+        return X
+
+    def f_and_grad(x):
+        X = unpack(np.ascontiguousarray(x))
+        # [r, 1 + 2*q*nf, q, d]: the point itself, then +h / -h along every free coordinate of every q-point
+        P = X.unsqueeze(1).repeat(1, 1 + 2 * q * nf, 1, 1)
+        hp = torch.empty(q, nf, dtype=torch.double)
+        hm = torch.empty(q, nf, dtype=torch.double)
+        for a, j in enumerate(free):
+            # stay inside the box: shrink the step on the side that would leave it
+            up_room = (ub[j] - X[:, :, j]).clamp_min(0.0)
+            dn_room = (X[:, :, j] - lb[j]).clamp_min(0.0)
+            sp = torch.minimum(up_room, h[j].expand_as(up_room))
+            sm = torch.minimum(dn_room, h[j].expand_as(dn_room))
+            for p in range(q):
+                k = 1 + 2 * (p * nf + a)
+                P[:, k, p, j] += sp[:, p]
+                P[:, k + 1, p, j] -= sm[:, p]
+            if a == 0:
+                SP = torch.empty(r, q, nf, dtype=torch.double)
+                SM = torch.empty(r, q, nf, dtype=torch.double)
+            SP[:, :, a], SM[:, :, a] = sp, sm
+        with torch.no_grad():
+            vals = acquisition_function(P.view(-1, q, d).to(device)).cpu().view(r, 1 + 2 * q * nf)
+        state["n_eval"] += vals.numel()
+        f0 = vals[:, 0]
+        vp = vals[:, 1::2].reshape(r, q, nf)
+        vm = vals[:, 2::2].reshape(r, q, nf)
+        denom = (SP + SM).clamp_min(1e-300)
+        g = (vp - vm) / denom
+        g[(SP + SM) == 0] = 0.0
+        return -float(f0.sum()), (-g).reshape(-1).numpy().astype(np.float64)
+
+    x0 = X0[:, :, free_t].reshape(-1).numpy().astype(np.float64)
+    bnds = [(float(lb[j]), float(ub[j])) for _ in range(r * q) for j in free]
+    res = minimize(f_and_grad, x0, jac=True, method="L-BFGS-B", bounds=bnds, options={"maxiter": maxiter})
+    Xf = unpack(np.clip(res.x, [b_[0] for b_ in bnds], [b_[1] for b_ in bnds]))
+    with torch.no_grad():
+        vals = acquisition_function(Xf.to(device)).cpu()
+    return Xf, vals, {"nit": int(res.nit), "n_acqf_evals": state["n_eval"] + r, "message": str(res.message)}
+
+
 def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                   fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
-                  return_best_only: bool = True, seed: Optional[int] = None, **unsupported):
+                  return_best_only: bool = True, seed: Optional[int] = None, refine: bool = True, **unsupported):
     """Same signature / return convention as botorch.optim.optimize_acqf as BoFire calls it
     (botorch.py:384-405): (candidates [q, d] on CPU, acq_value scalar tensor)."""
     for key in ("equality_constraints", "inequality_constraints", "nonlinear_inequality_constraints"):
         if unsupported.get(key):
             raise NotImplementedError(f"{key} are not handled by the accelerated optimiser yet")
+    bounds = torch.as_tensor(bounds, dtype=torch.double)
     X_ic, Y_ic, _, _ = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples,
                                                     fixed_features=fixed_features, options=options, seed=seed)
+    if refine:
+        X_ref, Y_ref, _ = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
+                                               options=options)
+        # never return something worse than the screened start (FD gradients on a piecewise-smooth MC estimate)
+        better = Y_ref >= Y_ic
+        X_ic = torch.where(better.view(-1, 1, 1), X_ref, X_ic.cpu())
+        Y_ic = torch.where(better, Y_ref, Y_ic)
     if return_best_only:
         best = int(torch.argmax(Y_ic))
         return X_ic[best].cpu(), Y_ic[best]

@@ -329,6 +329,52 @@ def test_full_size_properties_headline_config():
     assert float(acq(Xbad.to(st.device))[0]) < 1e-3
 
 
+def test_optimize_acqf_screen_refine_and_fd_gradient():
+    """Finite-difference gradient of the device acquisition value vs autograd through the oracle, and the
+    L2 boundary: optimize_acqf returns a [q, d] CPU candidate inside the bounds that is at least as good as the
+    best screened raw sample."""
+    from everest_b200 import optim
+
+    p = Cf.zdt1_qnehvi(N=64, S=32, raw=64, d=4, q=2)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=128)
+    acq_d = Cf.build_acqf(p, st, prune_samples=128)
+    X = Cf.candidates(p)
+    v = acq_d(X.to(st.device)).cpu()
+    i = int(torch.argmax(v))
+    x0 = X[i : i + 1].clone().requires_grad_(True)
+    acq_o.forward(x0).sum().backward()
+    g_ad = x0.grad[0]
+    h = 1e-6
+    g_fd = torch.zeros_like(g_ad)
+    pert = []
+    for a in range(p["q"]):
+        for j in range(p["d"]):
+            for sgn in (1.0, -1.0):
+                xp = X[i].clone()
+                xp[a, j] += sgn * h
+                pert.append(xp)
+    vals = acq_d(torch.stack(pert).to(st.device)).cpu().view(p["q"], p["d"], 2)
+    g_fd = (vals[..., 0] - vals[..., 1]) / (2 * h)
+    assert float((g_fd - g_ad).abs().max()) < 1e-5 * max(float(g_ad.abs().max()), 1e-8) + 1e-9
+    bounds = torch.as_tensor(p["bounds"])
+    cand, val = optim.optimize_acqf(acq_d, bounds, q=p["q"], num_restarts=4, raw_samples=64, options={"maxiter": 30}, seed=3)
+    assert cand.shape == (p["q"], p["d"]) and cand.device.type == "cpu"
+    assert bool((cand >= bounds[0] - 1e-12).all()) and bool((cand <= bounds[1] + 1e-12).all())
+    X_rnd = optim.draw_sobol_samples(bounds, 64, p["q"], seed=3)
+    best_raw = float(acq_d(X_rnd.to(st.device)).max())
+    assert float(val) >= best_raw - 1e-15
+    assert abs(float(acq_d(cand.unsqueeze(0).to(st.device))[0]) - float(val)) < 1e-12
+    # discrete branch (botorch.py:461): arg-max over a choice set
+    choices = X_rnd[:, 0, :]
+    p1 = Cf.zdt1_qnehvi(N=64, S=32, raw=64, d=4, q=1)
+    acq1 = Cf.build_acqf(p1, Cf.build_state(p1), prune_samples=128)
+    c, cv = optim.optimize_acqf_discrete(acq1, q=1, choices=choices)
+    allv = acq1(choices.unsqueeze(1).to(st.device)).cpu()
+    assert float(cv) == float(allv.max()) and torch.equal(c[0], choices[int(torch.argmax(allv))])
+
+
 def test_errors_are_loud():
     from everest_b200 import DeviceGPState, SingleTaskGPSpec, acquisition as A
 

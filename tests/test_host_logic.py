@@ -134,6 +134,28 @@ def test_initialize_q_batch_semantics():
     assert torch.equal(optim.apply_fixed_features(S, {1: 0.25})[..., 1], torch.full((16, 3), 0.25, dtype=DT))
 
 
+def test_gen_candidates_scipy_on_a_known_concave_function():
+    class _M:
+        device = torch.device("cpu")
+
+    class _Fake:
+        model = _M()
+
+        def __call__(self, X):
+            return -((X - 0.3) ** 2).sum(dim=(1, 2))
+
+    g = torch.Generator().manual_seed(1)
+    ic = torch.rand(3, 2, 4, dtype=DT, generator=g)
+    Xf, vals, info = optim.gen_candidates_scipy(ic, _Fake(), torch.zeros(4), torch.ones(4), fixed_features={1: 0.9},
+                                                options={"maxiter": 50})
+    assert torch.allclose(Xf[..., 1], torch.full((3, 2), 0.9, dtype=DT))          # fixed feature untouched
+    assert torch.allclose(Xf[..., [0, 2, 3]], torch.full((3, 2, 3), 0.3, dtype=DT), atol=1e-6)
+    assert torch.allclose(vals, torch.full((3,), -0.72, dtype=DT), atol=1e-9)
+    # optimum outside the box -> lands on the bound (one-sided differences at the boundary)
+    Xb, _, _ = optim.gen_candidates_scipy(ic, _Fake(), torch.full((4,), 0.5), torch.ones(4), options={"maxiter": 50})
+    assert torch.allclose(Xb, torch.full((3, 2, 4), 0.5, dtype=DT), atol=1e-9)
+
+
 def test_config_builders_and_oracle_conversion():
     for p in (Cf.zdt1_qnehvi(scale=0.01), Cf.dtlz2_qnehvi(scale=0.02), Cf.himmelblau_qlogei(scale=0.05),
               Cf.detergent_qnehvi(), Cf.mixed_tanimoto_qlogei(scale=0.004, n_bits=128)):
