@@ -11,6 +11,7 @@
 #include "acqf.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // layout helpers
@@ -162,12 +163,27 @@ cond_root_kernel(CondRootArgs a) {
   }
   __syncwarp();
   // bl = Sqb L_b^-T with the cached inverse root: bl[j][e] = sum_{l<=e} Sqb[j][l] LbInv[e][l]  (lanes over e)
-  for (int e = lane; e < nb; e += 32) {
-    const double* lrow = Li + (size_t)e * ldli;
-    for (int j = 0; j < q; ++j) {
-      double s = 0.0;
-      for (int l = 0; l <= e; ++l) s = fma(Sqb[j * nb + l], lrow[l], s);
-      BLs[j * nb + e] = s;
+  if (a.linv_in_smem) {
+    for (int e = lane; e < nb; e += 32) {
+      const double* lrow = Li + (size_t)e * ldli;
+      for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        for (int l = 0; l <= e; ++l) s = fma(Sqb[j * nb + l], lrow[l], s);
+        BLs[j * nb + e] = s;
+      }
+    }
+  } else {
+    // large baselines: stream the TRANSPOSED inverse (rows l, lanes over consecutive e -> coalesced);
+    // entries with l > e are exact zeros of the triangular factor
+    for (int e0 = 0; e0 < nb; e0 += 32) {
+      const int e = e0 + lane;
+      const int lmax = min(nb, e0 + 32);
+      for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        if (e < nb)
+          for (int l = 0; l < lmax; ++l) s = fma(Sqb[j * nb + l], a.LbInvT[(size_t)l * a.ldlb + e], s);
+        if (e < nb) BLs[j * nb + e] = s;
+      }
     }
   }
   __syncwarp();
@@ -690,6 +706,57 @@ mc_hvi_kernel(McArgs a) {
 // per q-batch) and takes the baseline part bl z_b from the sample GEMM.  Thread = (sample, batch lane);
 // per-batch sums over the CTA's 64 samples go to partial[sample_group][batch], reduced by a second
 // tiny kernel in a fixed order (deterministic).
+// Contribution of one cell to the inclusion-exclusion sum for one MC sample.  A point overlaps the cell iff
+// obj > lower in every objective (cells are non-empty, so upper > lower); the overlap test is compare-only
+// and most cells are rejected after the first objective.  Only overlapping points enter the subset sums.
+template <int QMAX, int MO>
+__device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO], const double (&fwt)[QMAX], int q,
+                                                    bool has_cons, const double* __restrict__ lo_p,
+                                                    const double* __restrict__ up_p, int stride) {
+  unsigned active = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  double lo[MO];
+#pragma unroll
+  for (int o = 0; o < MO; ++o) {
+    if (active) {
+      lo[o] = lo_p[o * stride];
+      unsigned m = 0;
+#pragma unroll
+      for (int j = 0; j < QMAX; ++j) m |= (obj[j][o] > lo[o]) ? (1u << j) : 0u;
+      active &= m;
+    }
+  }
+  if (!active) return 0.0;
+  double up[MO];
+#pragma unroll
+  for (int o = 0; o < MO; ++o) up[o] = up_p[o * stride];
+  double cell = 0.0;
+  for (int size = 1; size <= q; ++size) {
+    double asum = 0.0;
+    bool any = false;
+    for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+      if (__popc(sub) != size) continue;
+      any = true;
+      double vol = 1.0;
+#pragma unroll
+      for (int o = 0; o < MO; ++o) {
+        double mn = up[o];
+#pragma unroll
+        for (int j = 0; j < QMAX; ++j)
+          if ((sub >> j) & 1u) mn = fmin(mn, obj[j][o]);
+        vol *= fmax(mn - lo[o], 0.0);
+      }
+      if (has_cons) {
+#pragma unroll
+        for (int j = 0; j < QMAX; ++j)
+          if ((sub >> j) & 1u) vol *= fwt[j];
+      }
+      asum += vol;
+    }
+    if (any) cell += (size & 1) ? asum : -asum;
+  }
+  return cell;
+}
+
 #define MT_S 64
 #define MT_B 64
 template <int QMAX, int MO>
@@ -752,49 +819,8 @@ mc_hvi_tiled_kernel(McArgs a, int maxc) {
           }
         }
       }
-      for (int c = 0; c < nc; ++c) {
-        double lo[MO], len[QMAX][MO];
-        unsigned active = 0;
-#pragma unroll
-        for (int o = 0; o < MO; ++o) lo[o] = clo[(c * MO + o) * MT_S + sl];
-#pragma unroll
-        for (int j = 0; j < QMAX; ++j) {
-          bool pos = true;
-#pragma unroll
-          for (int o = 0; o < MO; ++o) {
-            len[j][o] = fmin(obj[j][o], cup[(c * MO + o) * MT_S + sl]) - lo[o];
-            pos = pos && (len[j][o] > 0.0);
-          }
-          if (pos) active |= (1u << j);
-        }
-        if (!active) continue;
-        double cell = 0.0;
-        for (int size = 1; size <= q; ++size) {
-          double asum = 0.0;
-          bool any = false;
-          for (unsigned sub = active; sub; sub = (sub - 1) & active) {
-            if (__popc(sub) != size) continue;
-            any = true;
-            double vol = 1.0;
-#pragma unroll
-            for (int o = 0; o < MO; ++o) {
-              double mn = INFINITY;
-#pragma unroll
-              for (int j = 0; j < QMAX; ++j)
-                if ((sub >> j) & 1u) mn = fmin(mn, len[j][o]);
-              vol *= fmax(mn, 0.0);
-            }
-            if (has_cons) {
-#pragma unroll
-              for (int j = 0; j < QMAX; ++j)
-                if ((sub >> j) & 1u) vol *= fwt[j];
-            }
-            asum += vol;
-          }
-          if (any) cell += (size & 1) ? asum : -asum;
-        }
-        acc += cell;
-      }
+      for (int c = 0; c < nc; ++c)
+        acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MT_S + sl, cup + (c * MO) * MT_S + sl, MT_S);
     }
     // sum over this CTA's 64 samples: two warps share one batch lane
     double wsum = warp_sum(acc);
@@ -821,6 +847,119 @@ static McTiledFn pick_tiled(int q, int Mo) {
   return nullptr;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Many-cell variant (>2 objectives: thousands of cells per MC sample).  Pass 1 writes the objective
+// values of every (q-batch, MC sample) sample-minor; pass 2 streams each sample's cell list through
+// shared memory in chunks and scores 8 q-batches per thread against every chunk, so a cell is read from
+// L2 once per 64 q-batches instead of once per q-batch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mc_objectives_kernel(McArgs a, double* __restrict__ objw) {
+  // objw[(batch * (q*Mo + q) + slot) * S + s]: slots [0, q*Mo) objectives (j-major), [q*Mo, q*Mo+q) feasibility weights
+  const int batch = blockIdx.x;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  const int slots = q * Mo + q;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) {
+        const double* rr = a.root + (((size_t)batch * M + m) * q + j) * nr + nb;
+        double sb = (nb > 0) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0;
+        double sq = 0.0;
+        for (int k = 0; k < q; ++k) sq = fma(rr[k], a.zqT[((size_t)k * M + m) * S + s], sq);
+        y[m] = (a.mu[((size_t)batch * q + j) * M + m] + sb) + sq;
+      }
+      for (int o = 0; o < Mo; ++o) objw[((size_t)batch * slots + j * Mo + o) * S + s] = objective_apply(a.od.op[o], y);
+      double w = 1.0;
+      for (int c = 0; c < a.od.n_cons; ++c) {
+        double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+        w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+      }
+      objw[((size_t)batch * slots + q * Mo + j) * S + s] = w;
+    }
+  }
+}
+
+#define MC2_S 32     // samples per CTA (one warp = the 32 samples of one batch group)
+#define MC2_BG 8     // batch groups per CTA (warps)
+#define MC2_BPT 8    // q-batches per thread
+#define MC2_CH 24    // cells per chunk
+template <int QMAX, int MO>
+__global__ void __launch_bounds__(256, 2)
+mc_hvi_chunked_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
+  __shared__ double clo[MC2_CH * MO * MC2_S];
+  __shared__ double cup[MC2_CH * MO * MC2_S];
+  const int tid = threadIdx.x, sl = tid & 31, bg = tid >> 5;
+  const int q = a.q, S = a.S;
+  const int s0 = blockIdx.x * MC2_S, b0 = blockIdx.y * (MC2_BG * MC2_BPT);
+  const int s = s0 + sl;
+  const bool s_ok = s < S;
+  const int slots = q * MO + q;
+  const bool has_cons = a.od.n_cons > 0;
+  double acc[MC2_BPT];
+#pragma unroll
+  for (int t = 0; t < MC2_BPT; ++t) acc[t] = 0.0;
+  // longest cell list among the CTA's samples
+  int nc = s_ok ? a.ncells[s] : 0;
+  int ncmax = nc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ncmax = max(ncmax, __shfl_xor_sync(0xffffffffu, ncmax, o));
+  for (int c0 = 0; c0 < ncmax; c0 += MC2_CH) {
+    __syncthreads();
+    for (int idx = tid; idx < MC2_CH * MO * MC2_S; idx += 256) {
+      const int ss = idx & 31, co = idx >> 5;  // co = c_local * MO + o
+      const int c = c0 + co / MO;
+      const int sg = s0 + ss;
+      const bool ok = (sg < S) && (c < a.ncells[min(sg, S - 1)]);
+      // cells past the end of a sample's list can never overlap anything
+      clo[idx] = ok ? a.cell_lo[((size_t)c * MO + co % MO) * S + sg] : INFINITY;
+      cup[idx] = ok ? a.cell_up[((size_t)c * MO + co % MO) * S + sg] : -INFINITY;
+    }
+    __syncthreads();
+    if (!s_ok) continue;
+    const int cn = min(MC2_CH, ncmax - c0);
+#pragma unroll 1
+    for (int t = 0; t < MC2_BPT; ++t) {
+      const int batch = b0 + bg + t * MC2_BG;
+      if (batch >= a.b) continue;
+      double obj[QMAX][MO], fwt[QMAX];
+      const double* ob = objw + (size_t)batch * slots * S + s;
+#pragma unroll
+      for (int j = 0; j < QMAX; ++j) {
+        fwt[j] = 1.0;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) obj[j][o] = (j < q) ? ob[(size_t)(j * MO + o) * S] : -INFINITY;
+        if (has_cons && j < q) fwt[j] = ob[(size_t)(q * MO + j) * S];
+      }
+      double sum = 0.0;
+      for (int c = 0; c < cn; ++c)
+        sum += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MC2_S + sl, cup + (c * MO) * MC2_S + sl, MC2_S);
+      acc[t] += sum;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MC2_BPT; ++t) {
+    const int batch = b0 + bg + t * MC2_BG;
+    double w = warp_sum(s_ok ? acc[t] : 0.0);
+    if (sl == 0 && batch < a.b) a.partial[(size_t)blockIdx.x * a.b + batch] = w;
+  }
+}
+
+typedef void (*McChunkedFn)(McArgs, const double*, int);
+template <int MO>
+static McChunkedFn pick_chunked_q(int q) {
+  if (q <= 2) return mc_hvi_chunked_kernel<2, MO>;
+  if (q <= 4) return mc_hvi_chunked_kernel<4, MO>;
+  if (q <= 8) return mc_hvi_chunked_kernel<8, MO>;
+  return nullptr;
+}
+static McChunkedFn pick_chunked(int q, int Mo) {
+  if (Mo == 2) return pick_chunked_q<2>(q);
+  if (Mo == 3) return pick_chunked_q<3>(q);
+  if (Mo == 4) return pick_chunked_q<4>(q);
+  return nullptr;
+}
+
 __global__ void mc_reduce_partials_kernel(const double* __restrict__ partial, int groups, int b, int S,
                                           double* __restrict__ out, const int* __restrict__ info_in, int M,
                                           int* __restrict__ info_out) {
@@ -836,13 +975,52 @@ __global__ void mc_reduce_partials_kernel(const double* __restrict__ partial, in
   }
 }
 
-int launch_mc_hvi(const McArgs& a, int max_cells, cudaStream_t st, LaunchCounter* lc) {
+// EVEREST_MC_PATH = tiled | chunked | generic forces one of the three HVI kernels (tests); default: automatic
+static int mc_forced_path() {
+  const char* e = getenv("EVEREST_MC_PATH");
+  if (!e) return 0;
+  if (e[0] == 't') return 1;
+  if (e[0] == 'c') return 2;
+  if (e[0] == 'g') return 3;
+  return 0;
+}
+static bool mc_use_tiled(const McArgs& a, int max_cells, size_t* bytes) {
+  const int Mo = a.od.n_obj;
+  const int forced = mc_forced_path();
+  if (forced == 2 || forced == 3) { if (bytes) *bytes = 0; return false; }
+  size_t tiled = ((size_t)2 * max_cells * Mo * MT_S + (size_t)a.q * a.M * MT_S + 8) * sizeof(double) + MT_S * sizeof(int);
+  if (bytes) *bytes = tiled;
+  return pick_tiled(a.q, Mo) && !a.cells_shared && a.partial && (a.nb == 0 || a.Fp) && tiled <= 100 * 1024;
+}
+static bool mc_use_chunked(const McArgs& a, int max_cells) {
+  if (mc_forced_path() == 3) return false;
+  return !mc_use_tiled(a, max_cells, nullptr) && pick_chunked(a.q, a.od.n_obj) && !a.cells_shared && a.partial &&
+         (a.nb == 0 || a.Fp);
+}
+size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells) {
+  if (!mc_use_chunked(a, max_cells)) return 0;
+  return (size_t)a.b * (a.q * a.od.n_obj + a.q) * a.S * sizeof(double);
+}
+
+int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   const int Mo = a.od.n_obj;
+  if (obj_ws && mc_use_chunked(a, max_cells)) {
+    mc_objectives_kernel<<<a.b, 256, 0, st>>>(a, obj_ws);
+    if (lc) lc->n++;
+    McChunkedFn cf = pick_chunked(a.q, Mo);
+    dim3 grid((a.S + MC2_S - 1) / MC2_S, (a.b + MC2_BG * MC2_BPT - 1) / (MC2_BG * MC2_BPT));
+    cf<<<grid, 256, 0, st>>>(a, obj_ws, max_cells);
+    if (lc) lc->n++;
+    mc_reduce_partials_kernel<<<(a.b + 255) / 256, 256, 0, st>>>(a.partial, grid.x, a.b, a.S, a.out, a.info_in, a.M, a.info_out);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return BO_OK;
+  }
   // tiled path: needs per-sample cells, the sample GEMM output (or no baseline) and a cell list that fits
-  size_t tiled = ((size_t)2 * max_cells * Mo * MT_S + (size_t)a.q * a.M * MT_S + 8) * sizeof(double) + MT_S * sizeof(int);
+  size_t tiled = 0;
   McTiledFn fn = pick_tiled(a.q, Mo);
-  if (fn && !a.cells_shared && a.partial && (a.nb == 0 || a.Fp) && tiled <= 100 * 1024) {
+  if (mc_use_tiled(a, max_cells, &tiled)) {
     if (tiled > 48 * 1024) CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled));
     dim3 grid((a.S + MT_S - 1) / MT_S, (a.b + MT_B - 1) / MT_B);
     fn<<<grid, 256, tiled, st>>>(a, max_cells);

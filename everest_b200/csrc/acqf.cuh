@@ -12,6 +12,7 @@ struct CondRootArgs {
   const double* mu_raw;  // [b*q]
   const double* Lb;      // [nb, ldlb] cached baseline root of output m
   const double* LbInv;   // [nb, ldlb] its inverse (lower triangular): bl = Sqb LbInv^T
+  const double* LbInvT;  // [nb, ldlb] transpose of the inverse (coalesced access when it does not fit in smem)
   int ldlb;
   int linv_in_smem;      // set by the launcher
   double* root;          // [b, M, q, nb+q]
@@ -62,5 +63,6 @@ int launch_partition2d(const double* obj, const unsigned char* front, int n, int
 int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc);
-int launch_mc_hvi(const McArgs& a, int max_cells, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc);
+size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
 int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc);

@@ -113,7 +113,7 @@ struct bo_state {
   int nb = 0, S = 0, ldlb = 0, cap = 0;
   ObjD od;
   double best_f = 0.0;
-  DevBuf zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
+  DevBuf wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
   int cells_shared = 0;
   // host staging for the HOST-buffer entry point
@@ -152,7 +152,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
-                  &st->cell_up, &st->ncells, &st->front_idx, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
+                  &st->cell_up, &st->ncells, &st->front_idx, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
                   &st->stage_in, &st->stage_out};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
@@ -674,7 +674,7 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
     RC(st->wsBL.ensure(rows_max * ldbl * 8 * M));
     RC(st->wsFp.ensure(rows_max * (size_t)S * 8 * M));
   }
-  RC(st->wsPartial.ensure((size_t)((S + 63) / 64) * bchunk * 8));
+  RC(st->wsPartial.ensure((size_t)((S + 31) / 32) * bchunk * 8));
   std::vector<PostGemmArgs> pg(M);
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
@@ -702,7 +702,7 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
       CondRootArgs c;
       c.md = o.md; c.prep_q = o.q_prepd; c.prep_b = o.base_prepd; c.b = bc; c.q = q; c.nb = nb; c.M = M; c.m = m;
       c.Gqq = pg[m].Gqq; c.W = pg[m].W; c.ldw = ldw; c.mu_raw = pg[m].mu_raw;
-      c.Lb = o.Lb.as<double>(); c.LbInv = o.LbInv.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
+      c.Lb = o.Lb.as<double>(); c.LbInv = o.LbInv.as<double>(); c.LbInvT = o.LbInvT.as<double>(); c.ldlb = st->ldlb; c.root = st->wsRoot.as<double>(); c.mu = st->wsMu.as<double>();
       c.info = st->wsJit.as<int>(); c.jitter = nullptr;
       c.BL = sample_gemm ? st->wsBL.as<double>() + (size_t)m * rows_max * ldbl : nullptr; c.ldbl = ldbl;
       rec_begin(st, "cond_root", s);
@@ -726,7 +726,11 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
     ma.partial = st->wsPartial.as<double>();
     rec_begin(st, "mc_acqf", s);
     if (st->acqf_kind == 3) RC(launch_mc_logei(ma, s, &st->lc));
-    else RC(launch_mc_hvi(ma, st->max_cells, s, &st->lc));
+    else {
+      size_t ow = mc_hvi_obj_ws_bytes(ma, st->max_cells);
+      if (ow) RC(st->wsObjW.ensure(ow));
+      RC(launch_mc_hvi(ma, st->max_cells, ow ? st->wsObjW.as<double>() : nullptr, s, &st->lc));
+    }
     rec_end(st, s);
   }
   return BO_OK;

@@ -179,6 +179,23 @@ def test_qnehvi_forward_all_q_paths(q, N):
     assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
 
 
+@pytest.mark.parametrize("path", ["tiled", "chunked", "generic"])
+@pytest.mark.parametrize("kind,q", [("zdt1", 4), ("dtlz2", 2), ("dtlz2", 7)])
+def test_all_three_hvi_kernels_agree_with_oracle(monkeypatch, path, kind, q):
+    """EVEREST_MC_PATH forces the tiled (cells resident in smem), chunked (cells streamed, 8 q-batches per
+    thread) or generic (one CTA per q-batch) inclusion-exclusion kernel."""
+    monkeypatch.setenv("EVEREST_MC_PATH", path)
+    p = Cf.zdt1_qnehvi(N=60, S=40, raw=70, d=5, q=q) if kind == "zdt1" else Cf.dtlz2_qnehvi(N=50, S=40, raw=70, d=5, m_obj=3, q=q)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=64)
+    acq_d = Cf.build_acqf(p, st, prune_samples=64)
+    X = Cf.candidates(p)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
+
+
 def test_qnehvi_with_output_constraint_and_pending():
     from everest_b200 import acquisition as A
 
