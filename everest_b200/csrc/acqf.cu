@@ -760,7 +760,7 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
 #define MT_S 64
 #define MT_B 64
 template <int QMAX, int MO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (QMAX <= 4) ? 3 : 2)
 mc_hvi_tiled_kernel(McArgs a, int maxc) {
   extern __shared__ double tsm[];
   const int tid = threadIdx.x, sl = tid & 63, bl = tid >> 6;
@@ -1022,6 +1022,7 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   McTiledFn fn = pick_tiled(a.q, Mo);
   if (mc_use_tiled(a, max_cells, &tiled)) {
     if (tiled > 48 * 1024) CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     dim3 grid((a.S + MT_S - 1) / MT_S, (a.b + MT_B - 1) / MT_B);
     fn<<<grid, 256, tiled, st>>>(a, max_cells);
     if (lc) lc->n++;

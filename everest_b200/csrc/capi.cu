@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "acqf.cuh"
@@ -753,8 +754,30 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   }
   RC(st->stage_in.ensure(in_bytes));
   RC(st->stage_out.ensure(out_bytes));
-  memcpy(st->pin_in, X_host, in_bytes);
-  CUDA_CHECK_RET(cudaMemcpyAsync(st->stage_in.p, st->pin_in, in_bytes, cudaMemcpyHostToDevice, s));
+  // pageable -> pinned staging in 4 MiB pieces on up to 4 host threads, each piece's H2D DMA issued as soon as it
+  // is staged so that the copy engine overlaps the remaining staging
+  {
+    const size_t piece = (size_t)4 << 20;
+    const size_t n_pieces = (in_bytes + piece - 1) / piece;
+    const int n_thr = (int)std::min<size_t>(4, n_pieces);
+    const char* src = reinterpret_cast<const char*>(X_host);
+    char* dst = reinterpret_cast<char*>(st->pin_in);
+    for (size_t p0 = 0; p0 < n_pieces; p0 += n_thr) {
+      const size_t cnt = std::min<size_t>(n_thr, n_pieces - p0);
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < cnt; ++t) {
+        size_t off = (p0 + t) * piece, len = std::min(piece, in_bytes - off);
+        th.emplace_back([=]() { memcpy(dst + off, src + off, len); });
+      }
+      {
+        size_t off = p0 * piece, len = std::min(piece, in_bytes - off);
+        memcpy(dst + off, src + off, len);
+      }
+      for (auto& t : th) t.join();
+      size_t off = p0 * piece, len = std::min(cnt * piece, in_bytes - off);
+      CUDA_CHECK_RET(cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, dst + off, len, cudaMemcpyHostToDevice, s));
+    }
+  }
   RC(bo_acqf_forward(st, st->stage_in.as<double>(), b, q, zq_dev, st->stage_out.as<double>(), nullptr, s));
   CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK_RET(cudaStreamSynchronize(s));

@@ -196,6 +196,52 @@ def test_all_three_hvi_kernels_agree_with_oracle(monkeypatch, path, kind, q):
     assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
 
 
+@pytest.mark.parametrize("N", [2, 5])
+def test_detergent_config1_five_objectives(N):
+    """BASELINE config 1 (README loop): 5 inputs, 5 Maximize outputs, N = 2..5 observations, q = 1, Normalize
+    input transform, ref point inferred from the data; exercises the 5-objective box decomposition and the
+    generic HVI kernel on a launch-bound problem."""
+    p = Cf.detergent_qnehvi(N=N, S=64, raw=50)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=128)
+    acq_d = Cf.build_acqf(p, st, prune_samples=128)
+    assert acq_d.prune_idx.cpu().tolist() == acq_o.prune_idx.tolist()
+    lo, up, nc = acq_d.cell_bounds()
+    assert nc.tolist() == acq_o.n_cells.tolist()
+    X = Cf.candidates(p)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device))
+    assert float(v_o.abs().max()) > 0
+    assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * float(v_o.abs().max())
+    preds, stds = st.predict(X[:, 0, :])
+    mo, co = gp.posterior(X[:, 0, :], observation_noise=True)
+    assert np.allclose(preds, mo.numpy(), rtol=1e-9, atol=1e-12)
+    assert np.allclose(stds, co.diagonal(dim1=-1, dim2=-2).T.sqrt().numpy(), rtol=1e-7, atol=1e-12)
+
+
+def test_single_q_batch_and_single_sample_edge_cases():
+    """b = 1, S = 1, empty baseline after pruning (ref point better than every observation)."""
+    from everest_b200 import acquisition as A
+
+    p = Cf.zdt1_qnehvi(N=20, S=1, raw=1, d=3, q=2)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=32)
+    acq_d = Cf.build_acqf(p, st, prune_samples=32)
+    X = Cf.candidates(p)
+    assert X.shape[0] == 1
+    assert abs(float(acq_d(X.to(st.device))[0]) - float(acq_o.forward(X)[0])) <= 1e-8 * max(1e-12, abs(float(acq_o.forward(X)[0])))
+    p["ref_point"] = [10.0, 10.0]  # nothing is better than this -> pruning removes every baseline point
+    p["S"] = 8
+    acq_o2 = P.oracle_acqf(p, gp, prune_samples=32)
+    acq_d2 = Cf.build_acqf(p, st, prune_samples=32)
+    assert acq_o2.nb == 0 and acq_d2.nb == 0
+    X2 = Cf.candidates(p, 5)
+    v_o, v_d = acq_o2.forward(X2), acq_d2(X2.to(st.device)).cpu()
+    assert float((v_d - v_o).abs().max()) <= 1e-8 * max(float(v_o.abs().max()), 1e-300)
+
+
 def test_qnehvi_with_output_constraint_and_pending():
     from everest_b200 import acquisition as A
 
