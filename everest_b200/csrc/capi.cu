@@ -40,7 +40,10 @@ struct DevBuf {
       zero = true;
     }
     if (zero) {
-      cudaError_t e = cudaMemset(p, 0, bytes);
+      // set-up paths only (the forward pass never zeroes): order the clear against every stream
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { bo_set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return BO_ERR_CUDA; }
     }
     return BO_OK;
