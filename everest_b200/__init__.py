@@ -3,7 +3,7 @@
 Host-side mirror of the reference's interface for this one path; all arithmetic runs
 in hand-written sm_100a CUDA kernels behind the C ABI in include/everest_b200.h.  No CPU fallback.
 """
-from . import kernels, objectives, sampling  # noqa: F401
+from . import kernels, multiobjective, objectives, sampling  # noqa: F401
 from ._lib import EverestError, NotPSDError  # noqa: F401
 from .acquisition import (  # noqa: F401
     get_acquisition_function,

@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+__device__ __forceinline__ double block_sum(double v, double* red);
+
 // ------------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------------
@@ -583,6 +585,57 @@ int launch_partition_nd(const double* obj, const unsigned char* front, int n, in
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc) {
   partition_nd_kernel<<<S, 256, 0, st>>>(obj, front, n, S, Mo, cap, ref_dev, work, lo, up, ncells, overflow);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// mask[e] = front flag as int32; ideal[o] = max over the front (or ref if the front is empty)
+__global__ void front_to_mask_kernel(const unsigned char* __restrict__ front, int n, int* __restrict__ mask) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mask[i] = front[i] ? 1 : 0;
+}
+int launch_front_to_mask(const unsigned char* front, int n, int* mask, cudaStream_t st, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  front_to_mask_kernel<<<(n + 255) / 256, 256, 0, st>>>(front, n, mask);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// Exact hypervolume from the non-dominated decomposition (single sample, S = 1 layout):
+// hv = prod(ideal - ref) - sum_cells prod_o max(min(up, ideal) - lo, 0).  One CTA, fixed reduction order.
+__global__ void __launch_bounds__(256)
+hypervolume_from_cells_kernel(const double* __restrict__ obj, const unsigned char* __restrict__ front, int n, int Mo,
+                              const double* __restrict__ ref, const double* __restrict__ lo, const double* __restrict__ up,
+                              const int* __restrict__ ncells, double* __restrict__ hv) {
+  __shared__ double ideal[BO_MAX_OBJECTIVES];
+  __shared__ double red[32];
+  if (threadIdx.x < Mo) {
+    double mx = ref[threadIdx.x];
+    for (int e = 0; e < n; ++e)
+      if (front[e]) mx = fmax(mx, obj[(size_t)e * Mo + threadIdx.x]);
+    ideal[threadIdx.x] = mx;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const int nc = ncells[0];
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    double v = 1.0;
+    for (int o = 0; o < Mo; ++o) v *= fmax(fmin(up[c * Mo + o], ideal[o]) - lo[c * Mo + o], 0.0);
+    acc += v;
+  }
+  double t = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    double box = 1.0;
+    for (int o = 0; o < Mo; ++o) box *= (ideal[o] - ref[o]);
+    hv[0] = box - t;
+  }
+}
+int launch_hypervolume_from_cells(const double* obj, const unsigned char* front, int n, int Mo, const double* ref_dev,
+                                  const double* lo, const double* up, const int* ncells, double* hv_dev, cudaStream_t st,
+                                  LaunchCounter* lc) {
+  hypervolume_from_cells_kernel<<<1, 256, 0, st>>>(obj, front, n, Mo, ref_dev, lo, up, ncells, hv_dev);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -66,3 +66,7 @@ int launch_partition_nd(const double* obj, const unsigned char* front, int n, in
 int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc);
 size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
 int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
+int launch_front_to_mask(const unsigned char* front, int n, int* mask, cudaStream_t st, LaunchCounter* lc);
+int launch_hypervolume_from_cells(const double* obj, const unsigned char* front, int n, int Mo, const double* ref_dev,
+                                  const double* lo, const double* up, const int* ncells, double* hv_dev, cudaStream_t st,
+                                  LaunchCounter* lc);

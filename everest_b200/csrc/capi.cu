@@ -788,6 +788,84 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   return BO_OK;
 }
 
+// ---- stand-alone multi-objective utilities (no GP state) ---------------------------------------------
+struct TempBufs {
+  std::vector<void*> ptrs;
+  ~TempBufs() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T> int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16));
+    if (e != cudaSuccess) { bo_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return BO_ERR_CUDA; }
+    ptrs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return BO_OK;
+  }
+};
+
+static int front_of(const double* Y_dev, int n, int m, const double* ref_host, int dedup, TempBufs& tb, unsigned char** front,
+                    unsigned char** feas, double** ref_dev, cudaStream_t s) {
+  RC(tb.alloc(front, (size_t)std::max(n, 1)));
+  RC(tb.alloc(feas, (size_t)std::max(n, 1)));
+  RC(tb.alloc(ref_dev, (size_t)BO_MAX_OBJECTIVES));
+  std::vector<double> ref(BO_MAX_OBJECTIVES, -INFINITY);
+  if (ref_host) for (int o = 0; o < m; ++o) ref[o] = ref_host[o];
+  CUDA_CHECK_RET(cudaMemcpyAsync(*ref_dev, ref.data(), BO_MAX_OBJECTIVES * 8, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK_RET(cudaMemsetAsync(*feas, 1, (size_t)std::max(n, 1), s));
+  RC(launch_front(Y_dev, *feas, 1, n, m, *ref_dev, dedup, *front, nullptr, s, nullptr));
+  return BO_OK;
+}
+
+extern "C" int bo_pareto_mask(const double* Y_dev, int32_t n, int32_t m, int32_t deduplicate, int32_t* mask_dev, void* stream) {
+  if (n < 0 || m < 1 || m > BO_MAX_OBJECTIVES) { bo_set_error("pareto_mask: bad n=%d / m=%d", n, m); return BO_ERR_INVALID; }
+  if (n == 0) return BO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBufs tb;
+  unsigned char *front, *feas;
+  double* ref_dev;
+  RC(front_of(Y_dev, n, m, nullptr, deduplicate ? 1 : 0, tb, &front, &feas, &ref_dev, s));
+  RC(launch_front_to_mask(front, n, mask_dev, s, nullptr));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  return BO_OK;
+}
+
+extern "C" int bo_hypervolume(const double* Y_dev, int32_t n, int32_t m, const double* ref_point, double* hv_out, void* stream) {
+  if (n < 0 || m < 2 || m > BO_MAX_OBJECTIVES || !ref_point || !hv_out) { bo_set_error("hypervolume: bad arguments"); return BO_ERR_INVALID; }
+  *hv_out = 0.0;
+  if (n == 0) return BO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBufs tb;
+  unsigned char *front, *feas;
+  double* ref_dev;
+  RC(front_of(Y_dev, n, m, ref_point, 1, tb, &front, &feas, &ref_dev, s));
+  double *lo, *up, *work, *hv_dev;
+  int *ncells, *overflow;
+  RC(tb.alloc(&ncells, 1));
+  RC(tb.alloc(&overflow, 1));
+  RC(tb.alloc(&hv_dev, 1));
+  int cap = (m == 2) ? n + 1 : std::max(64, 8 * (n + 1) * m);
+  for (;;) {
+    RC(tb.alloc(&lo, (size_t)cap * m));
+    RC(tb.alloc(&up, (size_t)cap * m));
+    if (m == 2) {
+      RC(launch_partition2d(Y_dev, front, n, 1, cap, ref_dev, lo, up, ncells, nullptr, s, nullptr));
+      break;
+    }
+    RC(tb.alloc(&work, (size_t)2 * cap * (m + m * m)));
+    CUDA_CHECK_RET(cudaMemsetAsync(overflow, 0, sizeof(int), s));
+    RC(launch_partition_nd(Y_dev, front, n, 1, m, cap, ref_dev, work, lo, up, ncells, overflow, s, nullptr));
+    int ov = 0;
+    CUDA_CHECK_RET(cudaMemcpyAsync(&ov, overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));
+    if (!ov) break;
+    cap *= 2;
+    if ((size_t)cap * (m + m * m) * 16 > ((size_t)8 << 30)) { bo_set_error("hypervolume: decomposition too large"); return BO_ERR_INVALID; }
+  }
+  RC(launch_hypervolume_from_cells(Y_dev, front, n, m, ref_dev, lo, up, ncells, hv_dev, s, nullptr));
+  CUDA_CHECK_RET(cudaMemcpyAsync(hv_out, hv_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  return BO_OK;
+}
+
 extern "C" int64_t bo_launch_count(const bo_state* st) { return st ? st->lc.n : 0; }
 
 extern "C" int bo_set_timing(bo_state* st, int32_t enabled) {

@@ -14,6 +14,7 @@ from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
+from scipy.optimize import minimize  # imported up front: the first import costs ~0.5 s, keep it out of ask()
 
 from . import sampling
 
@@ -82,8 +83,6 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     """[UPSTREAM] botorch.generation.gen_candidates_scipy for box bounds: joint L-BFGS-B over all restarts.
     Returns (candidates [r, q, d] CPU, acq values [r] CPU).  options: maxiter (default 2000, BoFire's
     `maxiter`), fd_step (relative to the bound width, default 1e-6)."""
-    from scipy.optimize import minimize
-
     options = options or {}
     maxiter = int(options.get("maxiter", 2000))
     rel_h = float(options.get("fd_step", 1e-6))
@@ -104,35 +103,32 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
         X[:, :, free_t] = torch.from_numpy(x).view(r, q, nf)
         return X
 
+    # index tables of the 2*q*nf perturbed copies: copy k = 1 + 2*(p*nf + a) moves point p along free dim a by +h,
+    # copy k + 1 by -h
+    pp, aa = torch.meshgrid(torch.arange(q), torch.arange(nf), indexing="ij")
+    pp, aa = pp.reshape(-1), aa.reshape(-1)
+    kk = 1 + 2 * (pp * nf + aa)
+    jj = free_t[aa]
+    hvec = h[free_t]                       # [nf]
+    lbf, ubf = lb[free_t], ub[free_t]
+
     def f_and_grad(x):
         X = unpack(np.ascontiguousarray(x))
-        # [r, 1 + 2*q*nf, q, d]: the point itself, then +h / -h along every free coordinate of every q-point
-        P = X.unsqueeze(1).repeat(1, 1 + 2 * q * nf, 1, 1)
-        hp = torch.empty(q, nf, dtype=torch.double)
-        hm = torch.empty(q, nf, dtype=torch.double)
-        for a, j in enumerate(free):
-            # stay inside the box: shrink the step on the side that would leave it
-            up_room = (ub[j] - X[:, :, j]).clamp_min(0.0)
-            dn_room = (X[:, :, j] - lb[j]).clamp_min(0.0)
-            sp = torch.minimum(up_room, h[j].expand_as(up_room))
-            sm = torch.minimum(dn_room, h[j].expand_as(dn_room))
-            for p in range(q):
-                k = 1 + 2 * (p * nf + a)
-                P[:, k, p, j] += sp[:, p]
-                P[:, k + 1, p, j] -= sm[:, p]
-            if a == 0:
-                SP = torch.empty(r, q, nf, dtype=torch.double)
-                SM = torch.empty(r, q, nf, dtype=torch.double)
-            SP[:, :, a], SM[:, :, a] = sp, sm
+        Xf = X[:, :, free_t]               # [r, q, nf]
+        # stay inside the box: shrink the step on the side that would leave it (one-sided at the boundary)
+        SP = torch.minimum((ubf - Xf).clamp_min(0.0), hvec.expand_as(Xf))
+        SM = torch.minimum((Xf - lbf).clamp_min(0.0), hvec.expand_as(Xf))
+        P = X.unsqueeze(1).repeat(1, 1 + 2 * q * nf, 1, 1)   # [r, 1 + 2*q*nf, q, d]
+        P[:, kk, pp, jj] += SP.reshape(r, -1)
+        P[:, kk + 1, pp, jj] -= SM.reshape(r, -1)
         with torch.no_grad():
             vals = acquisition_function(P.view(-1, q, d).to(device)).cpu().view(r, 1 + 2 * q * nf)
         state["n_eval"] += vals.numel()
         f0 = vals[:, 0]
         vp = vals[:, 1::2].reshape(r, q, nf)
         vm = vals[:, 2::2].reshape(r, q, nf)
-        denom = (SP + SM).clamp_min(1e-300)
-        g = (vp - vm) / denom
-        g[(SP + SM) == 0] = 0.0
+        width = SP + SM
+        g = torch.where(width > 0, (vp - vm) / width.clamp_min(1e-300), torch.zeros_like(width))
         return -float(f0.sum()), (-g).reshape(-1).numpy().astype(np.float64)
 
     x0 = X0[:, :, free_t].reshape(-1).numpy().astype(np.float64)

@@ -164,6 +164,14 @@ int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
 int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
                          double* out_host, void* stream);
 
+/* Stand-alone multi-objective utilities (maximisation frame), the result metrics of the path:
+ * botorch is_non_dominated as used by get_pareto_front (utils/multiobjective.py:58-84) and Hypervolume.compute as
+ * used by compute_hypervolume (:87-130).  Y_dev [n, m]; mask_dev [n] int32 (1 = non-dominated; with deduplicate
+ * only the first of identical rows is kept).  The hypervolume is exact: box(ref, ideal) minus the volume of the
+ * non-dominated box decomposition clipped to the ideal point. */
+int bo_pareto_mask(const double* Y_dev, int32_t n, int32_t m, int32_t deduplicate, int32_t* mask_dev, void* stream);
+int bo_hypervolume(const double* Y_dev, int32_t n, int32_t m, const double* ref_point, double* hv_out, void* stream);
+
 /* Introspection for tests: copies internal device buffers to the given device pointers. */
 int bo_debug_get(bo_state* st, const char* name, int32_t m, double* out_dev, int64_t capacity, int64_t* n_written,
                  void* stream);

@@ -438,6 +438,39 @@ def test_optimize_acqf_screen_refine_and_fd_gradient():
     assert float(cv) == float(allv.max()) and torch.equal(c[0], choices[int(torch.argmax(allv))])
 
 
+def test_multiobjective_utilities_kat_and_oracle():
+    """get_pareto_front / infer_ref_point / compute_hypervolume against the reference's known-answer tables
+    (tests/bofire/utils/test_multiobjective.py:216-266, via tests/golden/reference_golden.json) and the oracle."""
+    import json
+    import os
+
+    from everest_b200 import multiobjective as MO
+    from everest_b200.objectives import ObjectiveSpec
+
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))
+    for case in G["ref_points"]:
+        Y = np.array(case["Y"])
+        obj = MultiObjective([ObjectiveSpec(o[0], o[1], *o[2:]) for o in case["ops"]])
+        assert MO.get_pareto_front(obj, Y).tolist() == case["expected_pareto_idx"]
+        assert np.array_equal(MO.get_ref_point_mask(obj), np.array(case["mask"]))
+        assert np.array_equal(MO.infer_ref_point(obj, Y, return_masked=True), np.array(case["ref_masked"]))
+        assert np.array_equal(MO.infer_ref_point(obj, Y, return_masked=False), np.array(case["ref_plain"]))
+        hv = MO.compute_hypervolume(obj, Y, (np.array(case["ref_plain"]) - 1.0 * np.array(case["mask"])).tolist())
+        assert hv > 0  # test_compute_hypervolume pins only positivity
+    g = torch.Generator().manual_seed(4)
+    for m in (2, 3, 4, 5):
+        Y = torch.rand(40, m, dtype=DT, generator=g)
+        Y[7] = Y[2]
+        assert torch.equal(MO.is_non_dominated(Y), O.is_non_dominated(Y))
+        assert torch.equal(MO.is_non_dominated(Y, deduplicate=False), O.is_non_dominated(Y, deduplicate=False))
+        obj = MultiObjective([MaximizeObjective(i) for i in range(m)])
+        ref = [0.05] * m
+        hv_d = MO.compute_hypervolume(obj, Y.numpy(), ref)
+        hv_o = O.hypervolume(Y[O.is_non_dominated(Y)], torch.tensor(ref, dtype=DT))
+        assert abs(hv_d - hv_o) < 1e-12
+    assert MO.compute_hypervolume(MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]), np.zeros((3, 2)), [1.0, 1.0]) == 0.0
+
+
 def test_errors_are_loud():
     from everest_b200 import DeviceGPState, SingleTaskGPSpec, acquisition as A
 
