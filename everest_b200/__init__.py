@@ -12,7 +12,7 @@ from .acquisition import (  # noqa: F401
     qNoisyExpectedHypervolumeImprovement,
 )
 from .model import DeviceGPState, SingleTaskGPSpec, normalize_bounds, standardize_stats  # noqa: F401
-from .optim import (gen_batch_initial_conditions, gen_candidates_scipy, initialize_q_batch, optimize_acqf,
-                    optimize_acqf_discrete)  # noqa: F401
+from .optim import (calc_acquisition, gen_batch_initial_conditions, gen_candidates_scipy, initialize_q_batch,
+                    optimize_acqf, optimize_acqf_discrete, optimize_acqf_mixed)  # noqa: F401
 
 __version__ = "0.1.0"

@@ -164,6 +164,36 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
     return X_ic.cpu(), Y_ic
 
 
+def optimize_acqf_mixed(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
+                        fixed_features_list, options: Optional[dict] = None, seed: Optional[int] = None,
+                        refine: bool = True, **unsupported):
+    """[UPSTREAM] botorch.optim.optimize_acqf_mixed as BoFire calls it for categorical combinations
+    (botorch.py:358-378), q == 1: one optimize_acqf per fixed-feature dictionary, best value wins.
+    (For q > 1 BoTorch adds points sequentially with X_pending updates; that needs an acqf rebuild per pick
+    and is not accelerated.)"""
+    if not fixed_features_list:
+        raise ValueError("fixed_features_list must be non-empty.")
+    if q != 1:
+        raise NotImplementedError("optimize_acqf_mixed with q > 1 (sequential X_pending updates) is not accelerated")
+    best_c, best_v = None, None
+    for ff in fixed_features_list:
+        c, v = optimize_acqf(acq_function, bounds, q, num_restarts, raw_samples, fixed_features=ff, options=options,
+                             seed=seed, refine=refine, **unsupported)
+        if best_v is None or float(v) > float(best_v):
+            best_c, best_v = c, v
+    return best_c, best_v
+
+
+def calc_acquisition(acq_function, candidates, combined: bool = False):
+    """BotorchStrategy.calc_acquisition (botorch.py:196-225) on already transformed candidates [n, d]:
+    one value per row, or a single value for the whole set as one q-batch when `combined`."""
+    X = torch.as_tensor(candidates, dtype=torch.double)
+    if not combined:
+        X = X.unsqueeze(-2)
+    with torch.no_grad():
+        return acq_function(X).cpu().numpy()
+
+
 def optimize_acqf_discrete(acq_function, q: int, choices: torch.Tensor, max_batch_size: int = 1 << 20, unique: bool = True):
     """[UPSTREAM] optimize_acqf_discrete as used by the all-categorical branch (botorch.py:425-467):
     sequential greedy selection over a discrete choice set, forward-only."""

@@ -432,6 +432,17 @@ def test_optimize_acqf_screen_refine_and_fd_gradient():
     best_raw = float(acq_d(X_rnd.to(st.device)).max())
     assert float(val) >= best_raw - 1e-15
     assert abs(float(acq_d(cand.unsqueeze(0).to(st.device))[0]) - float(val)) < 1e-12
+    # mixed branch (botorch.py:358-378): best over a list of fixed-feature dictionaries, q = 1
+    p1m = Cf.zdt1_qnehvi(N=64, S=32, raw=64, d=4, q=1)
+    acq1m = Cf.build_acqf(p1m, Cf.build_state(p1m), prune_samples=128)
+    cm, vm = optim.optimize_acqf_mixed(acq1m, bounds, q=1, num_restarts=2, raw_samples=32,
+                                       fixed_features_list=[{0: 0.1}, {0: 0.9}], options={"maxiter": 10}, seed=1)
+    assert cm.shape == (1, 4) and float(cm[0, 0]) in (0.1, 0.9)
+    singles = [optim.optimize_acqf(acq1m, bounds, 1, 2, 32, fixed_features=ff, options={"maxiter": 10}, seed=1)[1] for ff in ({0: 0.1}, {0: 0.9})]
+    assert float(vm) == max(float(s_) for s_ in singles)
+    vals_rows = optim.calc_acquisition(acq1m, X_rnd[:5, 0, :])
+    val_comb = optim.calc_acquisition(acq_d, X_rnd[0], combined=True)
+    assert vals_rows.shape == (5,) and val_comb.shape == (1,)
     # discrete branch (botorch.py:461): arg-max over a choice set
     choices = X_rnd[:, 0, :]
     p1 = Cf.zdt1_qnehvi(N=64, S=32, raw=64, d=4, q=1)
