@@ -66,7 +66,33 @@ class _DeviceAcquisition:
         self.last_info = info
         return out.cpu() if on_cpu else out
 
-    __call__ = forward
+    def __call__(self, X):
+        """forward(X); when X requires grad the result carries the analytic gradient (BoTorch's acqfs are
+        differentiable torch modules: gen_candidates_scipy back-propagates through them)."""
+        if isinstance(X, torch.Tensor) and X.requires_grad and torch.is_grad_enabled():
+            return _AcqfAutograd.apply(X, self)
+        return self.forward(X)
+
+    def forward_backward(self, X):
+        """(values [b], d values[i] / d X[i] as [b, q, d]) through bo_acqf_forward_backward: the analytic adjoint of
+        the whole chain HVI / LogEI -> MC samples -> conditional root -> posterior -> kernel."""
+        X = torch.as_tensor(X, dtype=torch.double)
+        if X.dim() == 2:
+            X = X.unsqueeze(0)
+        if X.dim() != 3 or X.shape[-1] != self.model.d:
+            raise ValueError(f"X must be [b, q, {self.model.d}]")
+        on_cpu = X.device.type == "cpu"
+        Xd = X.detach().to(self.model.device).contiguous()
+        b, q, _ = Xd.shape
+        out = torch.empty(b, dtype=torch.double, device=self.model.device)
+        dX = torch.empty_like(Xd)
+        info = torch.zeros(b, dtype=torch.int32, device=self.model.device)
+        zq = self.base_samples_q(q)
+        with torch.cuda.device(self.model.device):
+            L.check(self.model.lib.bo_acqf_forward_backward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq),
+                                                            _dev_ptr(out), _dev_ptr(dX), _dev_ptr(info), _stream()))
+        self.last_info = info
+        return (out.cpu(), dX.cpu()) if on_cpu else (out, dX)
 
     def forward_host(self, X: np.ndarray) -> np.ndarray:
         """Same call with HOST buffers through bo_acqf_forward_host (pinned staging + H2D + D2H inside)."""
@@ -82,6 +108,24 @@ class _DeviceAcquisition:
             L.check(self.model.lib.bo_acqf_forward_host(self.model.handle, X.ctypes.data_as(C.c_void_p), b, q,
                                                         _dev_ptr(zq), out.ctypes.data_as(C.c_void_p), _stream()))
         return out
+
+
+class _AcqfAutograd(torch.autograd.Function):
+    """torch.autograd bridge: forward = bo_acqf_forward_backward, backward = chain rule with the stored dX."""
+
+    @staticmethod
+    def forward(ctx, X, acqf):
+        squeeze = X.dim() == 2
+        vals, dX = acqf.forward_backward(X)
+        ctx.save_for_backward(dX)
+        ctx.squeeze = squeeze
+        return vals
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dX,) = ctx.saved_tensors
+        g = grad_out.to(dX.device).view(-1, 1, 1) * dX
+        return (g[0] if ctx.squeeze else g), None
 
 
 class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):

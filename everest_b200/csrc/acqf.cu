@@ -9,11 +9,11 @@
 // in oracle/bo_oracle.py.  Objective / constraint formulas: utils/torch_tools.py:258-337,384-450.
 #include "common.cuh"
 #include "acqf.cuh"
+#include "mc_math.cuh"
 
 #include <math.h>
 #include <stdlib.h>
 
-__device__ __forceinline__ double block_sum(double v, double* red);
 
 // ------------------------------------------------------------------------------------------------
 // layout helpers
@@ -647,19 +647,6 @@ int launch_hypervolume_from_cells(const double* obj, const unsigned char* front,
 // own cells, restricted to the points that overlap the cell (subsets containing a zero-length point
 // contribute exactly 0, so skipping them leaves the sum unchanged).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x < 32) {
-    t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
-    t = warp_sum(t);
-  }
-  return t;  // valid in warp 0
-}
-
 __global__ void __launch_bounds__(256)
 mc_hvi_kernel(McArgs a) {
   extern __shared__ double msm[];
@@ -1102,22 +1089,6 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
 // ------------------------------------------------------------------------------------------------
 // K8: qLogEI = logmeanexp_S( fatmax_q( log_fatplus(obj - best_f, tau_relu), tau_max ) )
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double softplus_d(double x) {  // torch softplus(beta=1, threshold=32)
-  return (x > 32.0) ? x : log1p(exp(x));
-}
-__device__ __forceinline__ double log_softplus_d(double x) {
-  return (x > -35.0) ? log(softplus_d(x)) : x;  // tau = 1: x / tau + log(tau)
-}
-__device__ __forceinline__ double logaddexp_d(double a, double b) {
-  double mx = fmax(a, b), mn = fmin(a, b);
-  if (isinf(mx) && mx < 0) return mx;
-  return mx + log1p(exp(mn - mx));
-}
-__device__ __forceinline__ double log_fatplus_d(double x, double tau) {
-  double z = x / tau;
-  return log(tau) + logaddexp_d(log_softplus_d(z), log(1e-1) - log1p(z * z));
-}
-
 __global__ void __launch_bounds__(256)
 mc_logei_kernel(McArgs a) {
   extern __shared__ double msm[];

@@ -70,3 +70,42 @@ int launch_front_to_mask(const unsigned char* front, int n, int* mask, cudaStrea
 int launch_hypervolume_from_cells(const double* obj, const unsigned char* front, int n, int Mo, const double* ref_dev,
                                   const double* lo, const double* up, const int* ncells, double* hv_dev, cudaStream_t st,
                                   LaunchCounter* lc);
+
+// ---- grad.cu: analytic adjoint d acqf / d X (the backward of forward(X[b, q, d])) ----------
+// MC value + d value / d f for every MC sample: dF[m * df_stride + (batch * q + j) * S + s]
+int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_logei_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+// dF -> d root [b, M, q, nb+q] (= [d bl | d br]) and d mu [b*q, M]
+int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, const double* zqT, int S, int nb, int q,
+                       int M, int rows, double* droot, double* dmu, cudaStream_t st, LaunchCounter* lc);
+
+struct CondRootBwdArgs {
+  int b, q, nb, M, m;
+  const double* root;   // [b, M, q, nb+q] forward roots
+  const double* droot;  // [b, M, q, nb+q]
+  const double* dmu;    // [b*q, M]
+  const double* LbInv;  // [nb, ldlb]
+  int ldlb;
+  double y_std;
+  double* EG;           // [b, q, q]   coefficient of U_i in dKx_j  (= -2 s^2 Cbar)
+  double* EW;           // [b*q, ldw]  d value / d W
+  int ldw;
+  double* Emu;          // [b*q]       d value / d mu_raw
+};
+int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounter* lc);
+
+struct KernelGradArgs {
+  ModelD md;
+  PrepD prep_q, prep_b;
+  int rows, q, nb, N, ldk, d;
+  const double* alpha;  // [ldk]
+  const double* Aext;   // [nb, ldk] rows K_bX (K + s2 I)^-1
+  const double* U;      // [rows, ldk] K*X (K + s2 I)^-1
+  const double* EG;     // [b, q, q]
+  const double* EW;     // [rows, ldw]
+  int ldw;
+  const double* Emu;    // [rows]
+  double* dX;           // [rows, d]
+  int accumulate;       // 0: overwrite dX, 1: add (outputs after the first)
+};
+int launch_kernel_grad(const KernelGradArgs& a, cudaStream_t st, LaunchCounter* lc);

@@ -90,6 +90,8 @@ struct OutputH {
   PrepBuf train_prep;
   PrepD train_prepd;
   DevBuf L, Linv, LinvT, LinvExt, alpha_row, dinv, resid, tvec;
+  DevBuf Kinv;  // (K + s2 I)^-1, built lazily by the first backward pass
+  bool kinv_ready = false;
   int Rpad = 0;  // rows of LinvExt
   double jitter = 0.0;
   // acquisition state
@@ -117,6 +119,7 @@ struct bo_state {
   int nb = 0, S = 0, ldlb = 0, cap = 0;
   ObjD od;
   double best_f = 0.0;
+  DevBuf wsDF, wsDRoot, wsDMu, wsEG, wsEW, wsEmu, wsU;  // adjoint workspaces (grad.cu)
   DevBuf wsGramPart, wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
   int cells_shared = 0;
@@ -150,14 +153,14 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (auto& o : st->out) {
     for (void* p : o.owned) cudaFree(p);
     o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
-    DevBuf* bs[] = {&o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
+    DevBuf* bs[] = {&o.Kinv, &o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
     for (DevBuf* b : bs) b->release();
   }
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out};
+                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
@@ -329,6 +332,7 @@ extern "C" int bo_state_factorize(bo_state* st, int32_t* info, double* jitter, v
     if (info) info[m] = inf;
     if (jitter) jitter[m] = jit;
     o.jitter = jit;
+    o.kinv_ready = false;
     if (inf != 0) { ok = false; continue; }
     RC(o.Linv.ensure((size_t)Nr * ldk * 8, true));
     RC(o.LinvT.ensure((size_t)Nr * ldk * 8, true));
@@ -648,8 +652,19 @@ static void rec_end(bo_state* st, cudaStream_t s) {
   cudaEventRecord(st->recs.back().b, s);
 }
 
-extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
-                               double* out_dev, int32_t* info_dev, void* stream) {
+// (K + s2 I)^-1 = L^-T L^-1, needed only by the backward pass (U = K*X (K + s2 I)^-1)
+static int ensure_kinv(bo_state* st, OutputH& o, cudaStream_t s) {
+  if (o.kinv_ready) return BO_OK;
+  RC(o.Kinv.ensure((size_t)st->Nr * st->ldk * 8, true));
+  RC(launch_gemm_nt(st->N, st->N, st->N, 1.0, o.LinvT.as<double>(), st->ldk, o.LinvT.as<double>(), st->ldk, 0.0,
+                    o.Kinv.as<double>(), st->ldk, false, s, &st->lc));
+  o.kinv_ready = true;
+  return BO_OK;
+}
+
+// forward(X[b, q, d]) -> out[b]; when dX_dev is given also d out[i] / d X[i] (each value depends on its own q-batch only)
+static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev, double* out_dev,
+                    double* dX_dev, int32_t* info_dev, void* stream) {
   if (!st || !st->factorized || st->acqf_kind == 0) { bo_set_error("forward before prepare"); return BO_ERR_STATE; }
   if (b < 1 || q < 1 || q > BO_MAX_Q) { bo_set_error("bad b=%d / q=%d (q <= %d)", b, q, BO_MAX_Q); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -732,6 +747,49 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
     ma.info_in = st->wsJit.as<int>(); ma.info_out = info_dev ? info_dev + b0 : nullptr;
     ma.Fp = sample_gemm ? st->wsFp.as<double>() : nullptr; ma.fp_stride = rows_max * (size_t)S;
     ma.partial = st->wsPartial.as<double>();
+    if (dX_dev) {
+      // ---- backward (grad.cu) ----
+      const size_t dfs = rows_max * (size_t)S;
+      RC(st->wsDF.ensure(dfs * 8 * M));
+      RC(st->wsDRoot.ensure((size_t)bchunk * M * q * nr * 8));
+      RC(st->wsDMu.ensure(rows_max * M * 8));
+      RC(st->wsEG.ensure((size_t)bchunk * q * q * 8));
+      RC(st->wsEW.ensure(rows_max * ldw * 8));
+      RC(st->wsEmu.ensure(rows_max * 8));
+      RC(st->wsU.ensure(rows_max * ldk * 8, false));
+      rec_begin(st, "mc_grad", s);
+      if (st->acqf_kind == 3) RC(launch_mc_logei_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      else RC(launch_mc_hvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      rec_end(st, s);
+      rec_begin(st, "grad_reduce", s);
+      RC(launch_grad_reduce(st->wsDF.as<double>(), dfs, st->zbT.as<double>(), st->wsZqT.as<double>(), S, nb, q, M, rows,
+                            st->wsDRoot.as<double>(), st->wsDMu.as<double>(), s, &st->lc));
+      rec_end(st, s);
+      for (int m = 0; m < M; ++m) {
+        OutputH& o = st->out[m];
+        RC(ensure_kinv(st, o, s));
+        CondRootBwdArgs cb;
+        cb.b = bc; cb.q = q; cb.nb = nb; cb.M = M; cb.m = m; cb.root = st->wsRoot.as<double>(); cb.droot = st->wsDRoot.as<double>();
+        cb.dmu = st->wsDMu.as<double>(); cb.LbInv = o.LbInv.as<double>(); cb.ldlb = st->ldlb; cb.y_std = o.md.y_std;
+        cb.EG = st->wsEG.as<double>(); cb.EW = st->wsEW.as<double>(); cb.ldw = ldw; cb.Emu = st->wsEmu.as<double>();
+        rec_begin(st, "cond_root_bwd", s);
+        RC(launch_cond_root_bwd(cb, s, &st->lc));
+        rec_end(st, s);
+        rec_begin(st, "u_gemm", s);
+        RC(launch_gemm_nt(rows, st->N, st->N, 1.0, pg[m].Kx, ldk, o.Kinv.as<double>(), ldk, 0.0, st->wsU.as<double>(), ldk, false, s, &st->lc));
+        rec_end(st, s);
+        KernelGradArgs kg;
+        kg.md = o.md; kg.prep_q = o.q_prepd; kg.prep_b = o.base_prepd; kg.rows = rows; kg.q = q; kg.nb = nb; kg.N = st->N;
+        kg.ldk = ldk; kg.d = st->d; kg.alpha = o.alpha_row.as<double>();
+        kg.Aext = o.LinvExt.as<double>() + (size_t)(st->N + 1) * ldk; kg.U = st->wsU.as<double>();
+        kg.EG = st->wsEG.as<double>(); kg.EW = st->wsEW.as<double>(); kg.ldw = ldw; kg.Emu = st->wsEmu.as<double>();
+        kg.dX = dX_dev + (size_t)b0 * q * st->d; kg.accumulate = m > 0 ? 1 : 0;
+        rec_begin(st, "kernel_grad", s);
+        RC(launch_kernel_grad(kg, s, &st->lc));
+        rec_end(st, s);
+      }
+      continue;
+    }
     rec_begin(st, "mc_acqf", s);
     if (st->acqf_kind == 3) RC(launch_mc_logei(ma, s, &st->lc));
     else {
@@ -742,6 +800,17 @@ extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int
     rec_end(st, s);
   }
   return BO_OK;
+}
+
+extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                               double* out_dev, int32_t* info_dev, void* stream) {
+  return acqf_run(st, X_dev, b, q, zq_dev, out_dev, nullptr, info_dev, stream);
+}
+
+extern "C" int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                                        double* out_dev, double* dX_dev, int32_t* info_dev, void* stream) {
+  if (!dX_dev) { bo_set_error("forward_backward: dX_dev is NULL"); return BO_ERR_INVALID; }
+  return acqf_run(st, X_dev, b, q, zq_dev, out_dev, dX_dev, info_dev, stream);
 }
 
 extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,

@@ -1,0 +1,629 @@
+// Analytic adjoint of the acquisition value with respect to the candidate points: the backward pass of
+// AcquisitionFunction.forward(X[b, q, d]) that BoTorch gets from autograd inside gen_candidates_scipy
+// (reached from BotorchStrategy._optimize_acqf_continuous, strategies/predictives/botorch.py:384-405).
+//
+// Chain (per q-batch, per output m), mirroring the forward kernels in acqf.cu / gemm.cu / kernels_eval.cu:
+//   value  <- MC samples f = mu + bl z_b + br z_q            mc_hvi_grad_kernel / mc_logei_grad_kernel  (d value / d f)
+//   f      <- mu, bl, br                                     grad_reduce_kernel      (sums over the MC samples)
+//   br     <- chol(Sqq - bl bl^T), bl <- Sqb L_b^-T          cond_root_bwd_kernel    (Cholesky adjoint, Murray 2016)
+//   Sqq, Sqb, mu <- K*X (via G = K*X K^-1 K*X^T, W = K*X K^-1 K_Xb, K*X alpha) and the prior blocks K**, K*b
+//   K(x, .) <- x                                             kernel_grad_kernel      (RBF / Matern leaves; Hamming and
+//                                                                                     Tanimoto columns are discrete: zero)
+// Everything is float64; reductions run in a fixed order (deterministic).
+#include "acqf.cuh"
+#include "common.cuh"
+#include "mc_math.cuh"
+
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------------
+// MC value and d value / d f for qNEHVI / qEHVI: one CTA per q-batch, threads over MC samples
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
+  extern __shared__ double gsm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  double* root = gsm;                          // [M][q][nr]
+  double* mu = root + (size_t)M * q * nr;      // [q][M]
+  double* objs = mu + q * M;                   // [q*Mo][nt]
+  double* fw = objs + (size_t)q * Mo * nt;     // [q][nt]
+  double* gob = fw + (size_t)q * nt;           // [q*Mo][nt]  d value / d objective
+  double* gfw = gob + (size_t)q * Mo * nt;     // [q][nt]     d value / d feasibility weight
+  double* ys = gfw + (size_t)q * nt;           // [q*M][nt]   model-output samples
+  double* red = ys + (size_t)q * M * nt;       // [32]
+  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+  const double invS = 1.0 / (double)S;
+  const bool has_cons = a.od.n_cons > 0;
+
+  double total = 0.0;
+  for (int s = tid; s < S; s += nt) {
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) {
+        const double* rr = root + ((size_t)m * q + j) * nr;
+        double sb = 0.0, sq = 0.0;
+        if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
+        else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+        for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+        y[m] = (mu[j * M + m] + sb) + sq;
+        ys[((size_t)j * M + m) * nt + tid] = y[m];
+      }
+      for (int o = 0; o < Mo; ++o) {
+        objs[((size_t)j * Mo + o) * nt + tid] = objective_apply(a.od.op[o], y);
+        gob[((size_t)j * Mo + o) * nt + tid] = 0.0;
+      }
+      double w = 1.0;
+      for (int c = 0; c < a.od.n_cons; ++c) {
+        double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+        w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+      }
+      fw[(size_t)j * nt + tid] = w;
+      gfw[(size_t)j * nt + tid] = 0.0;
+    }
+    const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+    const int sc = a.cells_shared ? 0 : s;
+    const int Sc = a.cells_shared ? 1 : S;
+    double acc = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double lo[BO_MAX_OBJECTIVES], up[BO_MAX_OBJECTIVES];
+      for (int o = 0; o < Mo; ++o) {
+        lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+        up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
+      }
+      unsigned active = 0;
+      for (int j = 0; j < q; ++j) {
+        bool pos = true;
+        for (int o = 0; o < Mo; ++o) {
+          double len = fmin(objs[((size_t)j * Mo + o) * nt + tid], up[o]) - lo[o];
+          pos = pos && (len > 0.0);
+        }
+        if (pos) active |= (1u << j);
+      }
+      if (!active) continue;
+      double cell = 0.0;
+      for (int size = 1; size <= q; ++size) {
+        double asum = 0.0;
+        bool any = false;
+        const double sgn = (size & 1) ? 1.0 : -1.0;
+        for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+          if (__popc(sub) != size) continue;
+          any = true;
+          double vol = 1.0, wprod = 1.0;
+          double len[BO_MAX_OBJECTIVES];
+          int arg[BO_MAX_OBJECTIVES];
+          for (int o = 0; o < Mo; ++o) {
+            double mn = up[o];
+            int aj = -1;
+            for (unsigned rest = sub; rest; rest &= rest - 1) {
+              int j = __ffs(rest) - 1;
+              double v = objs[((size_t)j * Mo + o) * nt + tid];
+              if (v < mn) { mn = v; aj = j; }
+            }
+            len[o] = fmax(mn - lo[o], 0.0);  // > 0: every point of an active subset overlaps the cell
+            arg[o] = aj;
+            vol *= len[o];
+          }
+          if (has_cons)
+            for (unsigned rest = sub; rest; rest &= rest - 1) wprod *= fw[(size_t)(__ffs(rest) - 1) * nt + tid];
+          // adjoint: the side length along o moves with the subset's minimum iff that minimum is below the cell's upper bound
+          for (int o = 0; o < Mo; ++o)
+            if (arg[o] >= 0) {
+              double other = 1.0;
+              for (int o2 = 0; o2 < Mo; ++o2)
+                if (o2 != o) other *= len[o2];
+              gob[((size_t)arg[o] * Mo + o) * nt + tid] += sgn * wprod * other;
+            }
+          if (has_cons) {
+            for (unsigned rest = sub; rest; rest &= rest - 1) {
+              const int j = __ffs(rest) - 1;
+              double others = 1.0;
+              for (unsigned r2 = sub; r2; r2 &= r2 - 1) {
+                const int j2 = __ffs(r2) - 1;
+                if (j2 != j) others *= fw[(size_t)j2 * nt + tid];
+              }
+              gfw[(size_t)j * nt + tid] += sgn * vol * others;
+            }
+            vol *= wprod;
+          }
+          asum += vol;
+        }
+        if (any) cell += (size & 1) ? asum : -asum;
+      }
+      acc += cell;
+    }
+    total += acc;
+    // objectives / feasibility -> model outputs
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) y[m] = ys[((size_t)j * M + m) * nt + tid];
+      double dy[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) dy[m] = 0.0;
+      for (int o = 0; o < Mo; ++o) {
+        const double gv = gob[((size_t)j * Mo + o) * nt + tid];
+        if (gv != 0.0) dy[a.od.op[o].out_idx] += gv * objective_grad(a.od.op[o], y);
+      }
+      if (has_cons) {
+        const double gw = gfw[(size_t)j * nt + tid];
+        if (gw != 0.0) {
+          double sg[BO_MAX_CONSTRAINTS];
+          for (int c = 0; c < a.od.n_cons; ++c) {
+            double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+            sg[c] = 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+          }
+          for (int c = 0; c < a.od.n_cons; ++c) {
+            double rest = 1.0;
+            for (int c2 = 0; c2 < a.od.n_cons; ++c2)
+              if (c2 != c) rest *= sg[c2];
+            // d sigmoid(-cv / eta) / dy = -sign / eta * sg (1 - sg)
+            dy[a.od.con[c].out_idx] += gw * rest * sg[c] * (1.0 - sg[c]) * (-a.od.con[c].sign / a.od.con[c].eta);
+          }
+        }
+      }
+      for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m] * invS;
+    }
+  }
+  double t = block_sum(total, red);
+  if (tid == 0) {
+    a.out[batch] = t / (double)S;
+    if (a.info_out) {
+      int v = 0;
+      for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
+      a.info_out[batch] = v;
+    }
+  }
+}
+
+static int pick_threads(size_t fixed_doubles, size_t per_thread_doubles, size_t* smem_out) {
+  for (int nt = 256; nt >= 32; nt >>= 1) {
+    size_t smem = (fixed_doubles + per_thread_doubles * nt + 32) * sizeof(double);
+    if (smem <= 200 * 1024) { *smem_out = smem; return nt; }
+  }
+  return 0;
+}
+
+int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  const int Mo = a.od.n_obj;
+  size_t smem = 0;
+  const int nt = pick_threads((size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M,
+                              (size_t)2 * a.q * Mo + 2 * a.q + (size_t)a.q * a.M, &smem);
+  if (!nt) { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_hvi_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// qLogEI value and d value / d f:  value = logmeanexp_S( fatmax_q( log_fatplus(obj - best_f) ) )
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mc_logei_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
+  extern __shared__ double gsm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
+  double* root = gsm;
+  double* mu = root + (size_t)M * q * nr;
+  double* vals = mu + q * M;  // [S]
+  double* red = vals + S;     // [32] + broadcast slot
+  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+  const double tau_relu = 1e-6, tau_max = 1e-2;
+  double lmax = -INFINITY;
+  double bm = 0.0, tsum = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int s = tid; s < S; s += nt) {
+      double li[BO_MAX_Q], dli[BO_MAX_Q];
+      double dys[BO_MAX_Q][2 * BO_MAX_OBJECTIVES];
+      double mx = -INFINITY;
+      int jstar = 0;
+      for (int j = 0; j < q; ++j) {
+        double y[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) {
+          const double* rr = root + ((size_t)m * q + j) * nr;
+          double sb = 0.0, sq = 0.0;
+          for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+          for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+          y[m] = (mu[j * M + m] + sb) + sq;
+        }
+        const double o = scalar_objective_apply(a.od, y, M, pass ? dys[j] : nullptr);
+        li[j] = log_fatplus_d(o - a.best_f, tau_relu);
+        if (pass) dli[j] = log_fatplus_grad_d(o - a.best_f, tau_relu);
+        if (li[j] > mx) { mx = li[j]; jstar = j; }
+      }
+      double ps = 0.0;
+      for (int j = 0; j < q; ++j) {
+        double x = (mx - li[j]) / tau_max;
+        ps += 2.0 / (2.0 + 2.0 * x + x * x);
+      }
+      if (!pass) {
+        double v = mx + tau_max * log(ps);
+        vals[s] = v;
+        lmax = fmax(lmax, v);
+      } else {
+        const double wS = exp(vals[s] - bm) / tsum;  // d value / d h_s
+        double via_mx = 1.0;
+        double direct[BO_MAX_Q];
+        for (int j = 0; j < q; ++j) {
+          double x = (mx - li[j]) / tau_max;
+          double P = 2.0 / (2.0 + 2.0 * x + x * x);
+          double dP = -P * P * (1.0 + x);  // pareto'(x)
+          direct[j] = -dP / ps;            // through x_j = (mx - li_j) / tau, mx held fixed
+          via_mx += dP / ps;               // through mx (amax -> arg-max element)
+        }
+        direct[jstar] += via_mx;
+        for (int j = 0; j < q; ++j) {
+          const double gj = wS * direct[j] * dli[j];
+          for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = gj * dys[j][m];
+        }
+      }
+    }
+    if (!pass) {
+      for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+      __syncthreads();
+      if ((tid & 31) == 0) red[tid >> 5] = lmax;
+      __syncthreads();
+      bm = -INFINITY;
+      for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, red[w]);
+      double se = 0.0;
+      for (int s = tid; s < S; s += nt) se += exp(vals[s] - bm);
+      double t = block_sum(se, red);
+      if (tid == 0) {
+        red[32] = t;
+        a.out[batch] = bm + log(t) - log((double)S);
+        if (a.info_out) {
+          int v = 0;
+          for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
+          a.info_out[batch] = v;
+        }
+      }
+      __syncthreads();
+      tsum = red[32];
+    }
+  }
+}
+
+int launch_mc_logei_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  const int nt = 128;
+  size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + a.S + 40) * sizeof(double);
+  if (smem > 220 * 1024) { bo_set_error("mc_logei_grad: shared memory budget exceeded"); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_logei_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_logei_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// d root = [ dF z_b | dF z_q ],  d mu = sum_s dF   (one CTA per (candidate point, output); warps over targets)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const double* __restrict__ dF, size_t df_stride, const double* __restrict__ zbT,
+                   const double* __restrict__ zqT, int S, int nb, int q, int M, double* __restrict__ droot,
+                   double* __restrict__ dmu) {
+  extern __shared__ double rsm[];
+  const int row = blockIdx.x, m = blockIdx.y, batch = row / q, j = row % q, nr = nb + q;
+  const double* src = dF + (size_t)m * df_stride + (size_t)row * S;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) rsm[s] = src[s];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t <= nr; t += nw) {
+    const double* z = (t < nb) ? zbT + ((size_t)t * M + m) * S : (t < nr) ? zqT + ((size_t)(t - nb) * M + m) * S : nullptr;
+    double acc = 0.0;
+    if (z) for (int s = lane; s < S; s += 32) acc = fma(rsm[s], z[s], acc);
+    else for (int s = lane; s < S; s += 32) acc += rsm[s];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (t < nr) droot[(((size_t)batch * M + m) * q + j) * nr + t] = acc;
+      else dmu[(size_t)row * M + m] = acc;
+    }
+  }
+}
+
+int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, const double* zqT, int S, int nb, int q,
+                       int M, int rows, double* droot, double* dmu, cudaStream_t st, LaunchCounter* lc) {
+  if (rows <= 0) return BO_OK;
+  size_t smem = (size_t)S * sizeof(double);
+  if (smem > 200 * 1024) { bo_set_error("grad_reduce: too many MC samples for shared memory (S=%d)", S); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(grad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  dim3 grid(rows, M);
+  grad_reduce_kernel<<<grid, 256, smem, st>>>(dF, df_stride, zbT, zqT, S, nb, q, M, droot, dmu);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjoint of cond_root_kernel: one warp per q-batch (output m).
+//   br = chol(C), C = Sqq - bl bl^T, bl = Sqb L_b^-T, Sqq = s^2 (K** - G), Sqb = s^2 (K*b - W), mu = y_std (c + K*X alpha) + y_mean
+// Cholesky adjoint: Cbar = sym( L^-T Phi(L^T Lbar) L^-1 ), Phi = lower triangle with halved diagonal.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta) {
+  extern __shared__ double bsm[];
+  const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int batch = blockIdx.x * warps_per_cta + wic;
+  if (wic >= warps_per_cta || batch >= a.b) return;
+  const int q = a.q, nb = a.nb, nr = nb + q;
+  double* T = bsm + (size_t)wic * ((size_t)q * nb + 5 * q * q);  // [q][nb] total adjoint of bl
+  double* Lq = T + (size_t)q * nb;                               // [q][q]
+  double* Lbar = Lq + q * q;
+  double* Pm = Lbar + q * q;
+  double* Li = Pm + q * q;
+  double* Cb = Li + q * q;
+  const double* root = a.root + ((size_t)batch * a.M + a.m) * q * nr;
+  const double* droot = a.droot + ((size_t)batch * a.M + a.m) * q * nr;
+  const double s2 = a.y_std * a.y_std;
+  const int row0 = batch * q;
+  for (int p = lane; p < q * q; p += 32) {
+    int i = p / q, j = p % q;
+    Lq[p] = (j <= i) ? root[i * nr + nb + j] : 0.0;
+    Lbar[p] = (j <= i) ? droot[i * nr + nb + j] : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // P = Phi(L^T Lbar)
+    for (int i = 0; i < q; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double s = 0.0;
+        for (int k = i; k < q; ++k) s = fma(Lq[k * q + i], Lbar[k * q + j], s);
+        Pm[i * q + j] = (i == j) ? 0.5 * s : s;
+      }
+    for (int i = 0; i < q; ++i)
+      for (int j = i + 1; j < q; ++j) Pm[i * q + j] = 0.0;
+    // Li = L^-1 (lower)
+    for (int c = 0; c < q; ++c) {
+      for (int i = 0; i < q; ++i) {
+        if (i < c) { Li[i * q + c] = 0.0; continue; }
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) s -= Lq[i * q + k] * Li[k * q + c];
+        Li[i * q + c] = s / Lq[i * q + i];
+      }
+    }
+    // Cb = Li^T P Li, then symmetrise.  tmp = P Li (lower x lower = lower) into Lbar (no longer needed)
+    for (int i = 0; i < q; ++i)
+      for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        for (int k = j; k <= i; ++k) s = fma(Pm[i * q + k], Li[k * q + j], s);
+        Lbar[i * q + j] = s;
+      }
+    for (int i = 0; i < q; ++i)
+      for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        for (int k = i; k < q; ++k) s = fma(Li[k * q + i], Lbar[k * q + j], s);
+        Cb[i * q + j] = s;
+      }
+    for (int i = 0; i < q; ++i)
+      for (int j = 0; j < i; ++j) {
+        double v = 0.5 * (Cb[i * q + j] + Cb[j * q + i]);
+        Cb[i * q + j] = v;
+        Cb[j * q + i] = v;
+      }
+  }
+  __syncwarp();
+  // T = d bl - 2 Cbar bl
+  for (int e = lane; e < nb; e += 32)
+    for (int j = 0; j < q; ++j) {
+      double s = droot[j * nr + e];
+      for (int i = 0; i < q; ++i) s = fma(-2.0 * Cb[j * q + i], root[i * nr + e], s);
+      T[(size_t)j * nb + e] = s;
+    }
+  __syncwarp();
+  // d Sqb[j][l] = sum_{e >= l} T[j][e] LbInv[e][l];  EW = d value / d W = -s^2 d Sqb   (lanes over l: coalesced rows of LbInv)
+  for (int l0 = 0; l0 < nb; l0 += 32) {
+    const int l = l0 + lane;
+    for (int j = 0; j < q; ++j) {
+      double s = 0.0;
+      if (l < nb)
+        for (int e = l0; e < nb; ++e) {
+          const double v = (e >= l) ? a.LbInv[(size_t)e * a.ldlb + l] : 0.0;
+          s = fma(T[(size_t)j * nb + e], v, s);
+        }
+      if (l < nb) a.EW[(size_t)(row0 + j) * a.ldw + l] = -s2 * s;
+    }
+  }
+  for (int p = lane; p < q * q; p += 32) a.EG[(size_t)batch * q * q + p] = -2.0 * s2 * Cb[p];
+  for (int j = lane; j < q; j += 32) a.Emu[row0 + j] = a.y_std * a.dmu[(size_t)(row0 + j) * a.M + a.m];
+}
+
+int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  size_t per_warp = ((size_t)a.q * a.nb + 5 * a.q * a.q) * sizeof(double);
+  int wpc = (4 * per_warp <= 96 * 1024) ? 4 : 1;
+  size_t smem = wpc * per_warp;
+  if (smem > 200 * 1024) { bo_set_error("cond_root_bwd: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  cond_root_bwd_kernel<<<(a.b + wpc - 1) / wpc, 128, smem, st>>>(a, wpc);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// d value / d x for one candidate point per CTA: partners = N training points (weights from mu, W, G),
+// n_b baseline points (K*b) and the other points of the same q-batch (K**).
+// ------------------------------------------------------------------------------------------------
+#define KG_CHUNK 2048
+
+__device__ __forceinline__ double leaf_dk_dstat(int kind, double stat) {
+  switch (kind) {
+    case BO_LEAF_RBF:
+      return -0.5 * exp(-0.5 * stat);
+    case BO_LEAF_MATERN12: {
+      if (!(stat > 1e-30)) return 0.0;
+      double r = sqrt(stat);
+      return -exp(-r) / (2.0 * r);
+    }
+    case BO_LEAF_MATERN32: {
+      if (!(stat > 1e-30)) return 0.0;
+      return -1.5 * exp(-1.7320508075688772 * sqrt(stat));
+    }
+    case BO_LEAF_MATERN52: {
+      if (!(stat > 1e-30)) return 0.0;
+      double r = sqrt(stat);
+      return -(5.0 / 6.0) * (1.0 + 2.23606797749979 * r) * exp(-2.23606797749979 * r);
+    }
+  }
+  return 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+kernel_grad_kernel(const __grid_constant__ KernelGradArgs a, int dpad_max) {
+  extern __shared__ double ksm[];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int q = a.q, nb = a.nb, N = a.N, batch = row / q, jj = row % q;
+  const ModelD& md = a.md;
+  double* w = ksm;               // [KG_CHUNK] d value / d K(x_row, partner)
+  double* g = w + KG_CHUNK;      // [KG_CHUNK] w * dK/dstat for the current leaf
+  double* part = g + KG_CHUNK;   // [2][256]
+  double* xsj = part + 512;      // [dpad_max]
+  double* dxrow = xsj + dpad_max;  // [d]
+  for (int c = tid; c < a.d; c += 256) dxrow[c] = 0.0;
+  const int P = N + nb + q;
+  const double emu = a.Emu[row];
+  const double* ew = a.EW + (size_t)row * a.ldw;
+  const double* eg = a.EG + ((size_t)batch * q + jj) * q;
+  bool any_cont = false;
+  for (int l = 0; l < md.n_leaves; ++l) any_cont = any_cont || (md.leaf[l].kind <= BO_LEAF_MATERN52);
+
+  for (int p0 = 0; any_cont && p0 < P; p0 += KG_CHUNK) {
+    const int cn = min(KG_CHUNK, P - p0);
+    __syncthreads();
+    for (int pl = tid; pl < cn; pl += 256) {
+      const int p = p0 + pl;
+      double wv;
+      if (p < N) {
+        wv = emu * a.alpha[p];
+        for (int e = 0; e < nb; ++e) wv = fma(ew[e], a.Aext[(size_t)e * a.ldk + p], wv);
+        for (int i = 0; i < q; ++i) wv = fma(eg[i], a.U[((size_t)batch * q + i) * a.ldk + p], wv);
+      } else if (p < N + nb) {
+        wv = -ew[p - N];
+      } else {
+        const int i = p - N - nb;
+        wv = (i == jj) ? 0.0 : -eg[i];
+      }
+      w[pl] = wv;
+    }
+    for (int l = 0; l < md.n_leaves; ++l) {
+      const LeafD& L = md.leaf[l];
+      if (L.kind > BO_LEAF_MATERN52) continue;
+      __syncthreads();
+      for (int k = tid; k < L.dpad; k += 256) xsj[k] = a.prep_q.Xs[l][(size_t)row * L.dpad + k];
+      __syncthreads();
+      const double n2j = a.prep_q.n2[l][row];
+      for (int pl = tid; pl < cn; pl += 256) {
+        const int p = p0 + pl;
+        const double wv = w[pl];
+        double gv = 0.0;
+        if (wv != 0.0) {
+          // partner side / index
+          const PrepD* pp;
+          int pi;
+          bool train = false;
+          if (p < N) { train = true; pp = nullptr; pi = p; }
+          else if (p < N + nb) { pp = &a.prep_b; pi = p - N; }
+          else { pp = &a.prep_q; pi = batch * q + (p - N - nb); }
+          // coefficient of this leaf in the sum-of-products tree
+          double cl = 0.0;
+          for (int t = 0; t < md.n_terms; ++t) {
+            bool has = false;
+            for (int f = 0; f < md.nfac[t]; ++f) has = has || (md.fac[t][f] == l);
+            if (!has) continue;
+            double prod = md.coef[t];
+            bool skipped = false;
+            for (int f = 0; f < md.nfac[t]; ++f) {
+              const int lf = md.fac[t][f];
+              if (lf == l && !skipped) { skipped = true; continue; }
+              const LeafSide B = train ? train_side(md.leaf[lf]) : prep_side(*pp, lf);
+              prod *= leaf_eval_pair(md.leaf[lf], prep_side(a.prep_q, lf), row, B, pi, false);
+            }
+            cl += prod;
+          }
+          const double* xb = (train ? L.Xs : pp->Xs[l]) + (size_t)pi * L.dpad;
+          const double n2b = train ? L.n2[pi] : pp->n2[l][pi];
+          double dot = 0.0;
+          for (int k = 0; k < L.nd; ++k) dot = fma(xsj[k], xb[k], dot);
+          const double stat = fmax(n2j + n2b - 2.0 * dot, 0.0);
+          gv = wv * cl * leaf_dk_dstat(L.kind, stat);
+        }
+        g[pl] = gv;
+      }
+      __syncthreads();
+      // d stat / d xs_row[a] = 2 (xs_row[a] - xs_partner[a]):  accumulate sum_p g_p and sum_p g_p xs_p[a]
+      for (int a0 = 0; a0 < L.dpad; a0 += 256) {
+        const int na = min(256, L.dpad - a0);
+        const int nsl = max(1, 256 / na);
+        const int ai = tid % na, sl = tid / na;
+        double accx = 0.0, accg = 0.0;
+        if (sl < nsl) {
+          for (int pl = sl; pl < cn; pl += nsl) {
+            const double gv = g[pl];
+            if (gv == 0.0) continue;
+            const int p = p0 + pl;
+            const double* xb;
+            if (p < N) xb = L.Xs + (size_t)p * L.dpad;
+            else if (p < N + nb) xb = a.prep_b.Xs[l] + (size_t)(p - N) * L.dpad;
+            else xb = a.prep_q.Xs[l] + (size_t)(batch * q + (p - N - nb)) * L.dpad;
+            accx = fma(gv, xb[a0 + ai], accx);
+            accg += gv;
+          }
+        }
+        part[tid] = accx;
+        part[256 + tid] = accg;
+        __syncthreads();
+        if (tid < na) {
+          double sx = 0.0, sg = 0.0;
+          for (int s = 0; s < nsl; ++s) { sx += part[s * na + tid]; sg += part[256 + s * na + tid]; }
+          const int ak = a0 + tid;
+          if (ak < L.nd) dxrow[L.col[ak]] += 2.0 * (xsj[ak] * sg - sx) / (L.in_scl[ak] * L.ls[ak]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.d; c += 256) {
+    double* dst = a.dX + (size_t)row * a.d + c;
+    *dst = (a.accumulate ? *dst : 0.0) + dxrow[c];
+  }
+}
+
+int launch_kernel_grad(const KernelGradArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.rows <= 0) return BO_OK;
+  int dpad_max = 4;
+  for (int l = 0; l < a.md.n_leaves; ++l)
+    if (a.md.leaf[l].kind <= BO_LEAF_MATERN52) dpad_max = std::max(dpad_max, a.md.leaf[l].dpad);
+  size_t smem = ((size_t)2 * KG_CHUNK + 512 + dpad_max + a.d) * sizeof(double);
+  if (smem > 200 * 1024) { bo_set_error("kernel_grad: input dimension too large for shared memory (d=%d)", a.d); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(kernel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  kernel_grad_kernel<<<a.rows, 256, smem, st>>>(a, dpad_max);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}

@@ -1,0 +1,109 @@
+// Small device helpers shared by the MC acquisition kernels (acqf.cu) and their adjoints (grad.cu).
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+
+// [UPSTREAM] botorch.utils.safe_math (restated in oracle/bo_oracle.py: log_softplus, log_fatplus, fatmax)
+__device__ __forceinline__ double softplus_d(double x) {  // torch softplus(beta=1, threshold=32)
+  return (x > 32.0) ? x : log1p(exp(x));
+}
+__device__ __forceinline__ double log_softplus_d(double x) {
+  return (x > -35.0) ? log(softplus_d(x)) : x;  // tau = 1: x / tau + log(tau)
+}
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+  double mx = fmax(a, b), mn = fmin(a, b);
+  if (isinf(mx) && mx < 0) return mx;
+  return mx + log1p(exp(mn - mx));
+}
+__device__ __forceinline__ double log_fatplus_d(double x, double tau) {
+  double z = x / tau;
+  return log(tau) + logaddexp_d(log_softplus_d(z), log(1e-1) - log1p(z * z));
+}
+// d log_fatplus(x, tau) / dx
+__device__ __forceinline__ double log_fatplus_grad_d(double x, double tau) {
+  const double z = x / tau;
+  const double A = log_softplus_d(z), B = log(1e-1) - log1p(z * z);
+  const double lae = logaddexp_d(A, B);
+  double dA;
+  if (z > -35.0) {
+    const double sp = softplus_d(z);
+    const double sg = (z > 32.0) ? 1.0 : 1.0 / (1.0 + exp(-z));
+    dA = sg / sp;
+  } else {
+    dA = 1.0;
+  }
+  const double dB = -2.0 * z / (1.0 + z * z);
+  return (exp(A - lae) * dA + exp(B - lae) * dB) / tau;
+}
+
+// d objective / d y[op.out_idx]  (utils/torch_tools.py:384-450; forward: objective_apply in common.cuh)
+__device__ __forceinline__ double objective_grad(const bo_objective_op& op, const double* y) {
+  const double v = y[op.out_idx];
+  switch (op.kind) {
+    case BO_OBJ_MAX:
+      return 1.0 / (op.p1 - op.p0);
+    case BO_OBJ_MIN:
+      return -1.0 / (op.p1 - op.p0);
+    case BO_OBJ_CLOSE_TO_TARGET: {
+      const double t = v - op.p0;
+      if (t == 0.0) return 0.0;
+      return -op.p1 * pow(fabs(t), op.p1 - 1.0) * (t > 0.0 ? 1.0 : -1.0);
+    }
+    case BO_OBJ_MIN_SIGMOID: {
+      const double sg = 1.0 / (1.0 + exp(-1.0 * op.p0 * (v - op.p1)));
+      return -op.p0 * sg * (1.0 - sg);
+    }
+    case BO_OBJ_MAX_SIGMOID: {
+      const double sg = 1.0 / (1.0 + exp(-1.0 * op.p0 * (v - op.p1)));
+      return op.p0 * sg * (1.0 - sg);
+    }
+    case BO_OBJ_TARGET: {
+      const double s1 = 1.0 / (1.0 + exp(-1.0 * op.p2 * (v - (op.p0 - op.p1))));
+      const double s2 = 1.0 / (1.0 + exp(-1.0 * op.p2 * (v - (op.p0 + op.p1))));
+      return op.p2 * s1 * (1.0 - s1) * (1.0 - s2) - s1 * op.p2 * s2 * (1.0 - s2);
+    }
+  }
+  return 0.0;
+}
+
+// Scalarised objective of qLogEI (single / additive / multiplicative, utils/torch_tools.py:662-697) and, when
+// `dy` is given, its gradient with respect to the M model outputs.
+__device__ __forceinline__ double scalar_objective_apply(const ObjD& od, const double* y, int M, double* dy) {
+  if (dy) for (int m = 0; m < M; ++m) dy[m] = 0.0;
+  if (od.combine == BO_COMBINE_SINGLE) {
+    if (dy) dy[od.op[0].out_idx] = objective_grad(od.op[0], y);
+    return objective_apply(od.op[0], y);
+  }
+  if (od.combine == BO_COMBINE_ADDITIVE) {
+    double o = 0.0;
+    for (int k = 0; k < od.n_obj; ++k) {
+      o = o + objective_apply(od.op[k], y) * od.op[k].w;
+      if (dy) dy[od.op[k].out_idx] += objective_grad(od.op[k], y) * od.op[k].w;
+    }
+    return o;
+  }
+  double o = 1.0;
+  for (int k = 0; k < od.n_obj; ++k) o = o * pow(objective_apply(od.op[k], y), od.op[k].w);
+  if (dy) {
+    for (int k = 0; k < od.n_obj; ++k) {
+      double rest = 1.0;
+      for (int k2 = 0; k2 < od.n_obj; ++k2)
+        if (k2 != k) rest *= pow(objective_apply(od.op[k2], y), od.op[k2].w);
+      const double f = objective_apply(od.op[k], y);
+      dy[od.op[k].out_idx] += rest * od.op[k].w * pow(f, od.op[k].w - 1.0) * objective_grad(od.op[k], y);
+    }
+  }
+  return o;
+}

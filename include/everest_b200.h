@@ -160,6 +160,14 @@ int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objectiv
 int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
                     double* out_dev, int32_t* info_dev, void* stream);
 
+/* forward + analytic gradient: what BoTorch obtains from autograd inside gen_candidates_scipy when
+ * BotorchStrategy._optimize_acqf_continuous refines the restarts (botorch.py:384-405; "differentiable w.r.t. X",
+ * SURVEY.md 8b L1).  dX_dev [b, q, d] receives d out[i] / d X[i] (each value depends on its own q-batch only, so this
+ * is also the gradient of sum(out) that gen_candidates_scipy minimises).  Columns read only by Hamming / Tanimoto
+ * leaves (one-hot / fingerprint columns, fixed during the optimisation) get a zero gradient. */
+int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                             double* out_dev, double* dX_dev, int32_t* info_dev, void* stream);
+
 /* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values. */
 int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
                          double* out_host, void* stream);
