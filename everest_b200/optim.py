@@ -6,9 +6,10 @@ Round-1 scope: the raw-sample screen runs as ONE device call over all raw_sample
 reference scores them in raw_samples / batch_limit sequential CPU calls), then
 `initialize_q_batch` picks the restarts, then `gen_candidates_scipy` refines them with scipy's L-BFGS-B
 exactly like [UPSTREAM] botorch.generation.gen_candidates_scipy (all restarts as one vector, loss =
--sum acqf, box bounds, fixed features).  The gradient is a central finite difference evaluated in ONE
-batched device call per iteration (the MC acquisition value is deterministic for fixed base samples);
-the analytic adjoint kernels are the next step.
+-sum acqf, box bounds, fixed features).  The gradient comes from the analytic adjoint kernels
+(bo_acqf_forward_backward, csrc/grad.cu) -- what BoTorch obtains from autograd; options["gradient"] = "fd"
+switches to central finite differences evaluated in ONE batched device call per iteration (kept as a
+cross-check: the MC acquisition value is deterministic for fixed base samples).
 """
 from typing import Dict, Optional, Tuple
 
@@ -82,9 +83,10 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
                          fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None):
     """[UPSTREAM] botorch.generation.gen_candidates_scipy for box bounds: joint L-BFGS-B over all restarts.
     Returns (candidates [r, q, d] CPU, acq values [r] CPU).  options: maxiter (default 2000, BoFire's
-    `maxiter`), fd_step (relative to the bound width, default 1e-6)."""
+    `maxiter`), gradient ("analytic" | "fd"), fd_step (relative to the bound width, default 1e-6)."""
     options = options or {}
     maxiter = int(options.get("maxiter", 2000))
+    use_fd = options.get("gradient", "analytic") == "fd"
     rel_h = float(options.get("fd_step", 1e-6))
     X0 = torch.as_tensor(initial_conditions, dtype=torch.double).cpu().clone()
     r, q, d = X0.shape
@@ -112,7 +114,17 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     hvec = h[free_t]                       # [nf]
     lbf, ubf = lb[free_t], ub[free_t]
 
-    def f_and_grad(x):
+    def f_and_grad_analytic(x):
+        X = unpack(np.ascontiguousarray(x))
+        vals, dX = acquisition_function.forward_backward(X.to(device))
+        state["n_eval"] += r
+        g = dX.cpu()[:, :, free_t]
+        f = float(vals.sum())
+        if not np.isfinite(f):             # a q-batch whose conditional root failed: steer L-BFGS-B away
+            return 1e300, np.zeros(r * q * nf)
+        return -f, (-g).reshape(-1).numpy().astype(np.float64)
+
+    def f_and_grad_fd(x):
         X = unpack(np.ascontiguousarray(x))
         Xf = X[:, :, free_t]               # [r, q, nf]
         # stay inside the box: shrink the step on the side that would leave it (one-sided at the boundary)
@@ -133,7 +145,7 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
 
     x0 = X0[:, :, free_t].reshape(-1).numpy().astype(np.float64)
     bnds = [(float(lb[j]), float(ub[j])) for _ in range(r * q) for j in free]
-    res = minimize(f_and_grad, x0, jac=True, method="L-BFGS-B", bounds=bnds, options={"maxiter": maxiter})
+    res = minimize(f_and_grad_fd if use_fd else f_and_grad_analytic, x0, jac=True, method="L-BFGS-B", bounds=bnds, options={"maxiter": maxiter})
     Xf = unpack(np.clip(res.x, [b_[0] for b_ in bnds], [b_[1] for b_ in bnds]))
     with torch.no_grad():
         vals = acquisition_function(Xf.to(device)).cpu()
@@ -154,7 +166,7 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
     if refine:
         X_ref, Y_ref, _ = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
                                                options=options)
-        # never return something worse than the screened start (FD gradients on a piecewise-smooth MC estimate)
+        # never return something worse than the screened start (piecewise-smooth MC estimate)
         better = Y_ref >= Y_ic
         X_ic = torch.where(better.view(-1, 1, 1), X_ref, X_ic.cpu())
         Y_ic = torch.where(better, Y_ref, Y_ic)

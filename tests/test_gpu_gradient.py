@@ -106,16 +106,15 @@ def test_qlogei_gradient(kind):
     v_o, g_o = oracle_value_and_grad(acq_o, X)
     v_d, g_d = acq_d.forward_backward(X.to(st.device))
     assert float((v_d.cpu() - v_o).abs().max()) < 1e-7 * float(v_o.abs().max())
-    gs = float(g_o.abs().max())
-    if kind == "mixed" and gs == 0.0:
-        # purely discrete inputs (one-hot + fingerprint columns): nothing to differentiate
-        assert float(g_d.abs().max()) == 0.0
-        return
-    assert float((g_d.cpu() - g_o).abs().max()) < GRAD_TOL * gs
     if kind == "mixed":
-        # columns read only by the Hamming / Tanimoto leaves carry no gradient on the device path (they are fixed
-        # features of the optimisation); continuous columns agree with autograd
-        assert bool(torch.isfinite(g_d).all())
+        # one-hot and 0/1 fingerprint columns are discrete on the device path (bit-packed, fixed features of the
+        # optimisation, botorch.py:358-378): zero gradient there; the oracle's float64 Tanimoto is smooth in them, so
+        # only the continuous columns (0, 1) are compared with autograd
+        assert float(g_d[..., 2:].abs().max()) == 0.0
+        g_o, g_d = g_o[..., :2], g_d[..., :2]
+    gs = float(g_o.abs().max())
+    assert gs > 0
+    assert float((g_d.cpu() - g_o).abs().max()) < GRAD_TOL * gs
 
 
 @pytest.mark.parametrize("combine", ["additive", "multiplicative"])
