@@ -64,15 +64,149 @@ def apply_fixed_features(X: torch.Tensor, fixed_features: Optional[Dict[int, flo
     return X
 
 
+def dense_linear_constraints(constraints, q: int, d: int) -> Tuple[np.ndarray, np.ndarray]:
+    """BoTorch-form linear constraints -> dense rows over the flattened q*d variables of ONE q-batch.
+
+    Each constraint is (indices, coefficients, rhs) as produced by get_linear_constraints / get_interpoint_constraints
+    (utils/torch_tools.py:45-144): 1-d `indices` [k] = an intra-point constraint sum_i coef_i x[idx_i] (>=|==) rhs that
+    holds for every one of the q points; 2-d `indices` [k, 2] = (point, feature) pairs of an inter-point constraint
+    ([UPSTREAM] botorch.optim.parameter_constraints.make_scipy_linear_constraints)."""
+    rows, rhs = [], []
+    for idx, coef, r in constraints or []:
+        idx = torch.as_tensor(idx).long()
+        coef = torch.as_tensor(coef, dtype=torch.double)
+        if idx.dim() == 1:
+            if idx.numel() and (int(idx.max()) >= d or int(idx.min()) < 0):
+                raise RuntimeError(f"Index out of bounds for {d}-dim parameter tensor")
+            for j in range(q):
+                row = np.zeros(q * d)
+                for i, c in zip(idx.tolist(), coef.tolist()):
+                    row[j * d + i] += c
+                rows.append(row)
+                rhs.append(float(r))
+        elif idx.dim() == 2:
+            if int(idx[:, 0].max()) >= q or int(idx[:, 1].max()) >= d:
+                raise RuntimeError(f"Index out of bounds for ({q}, {d})-dim parameter tensor")
+            row = np.zeros(q * d)
+            for (j, i), c in zip(idx.tolist(), coef.tolist()):
+                row[j * d + i] += c
+            rows.append(row)
+            rhs.append(float(r))
+        else:
+            raise ValueError("`indices` must be 1- or 2-dimensional")
+    if not rows:
+        return np.zeros((0, q * d)), np.zeros(0)
+    return np.stack(rows), np.asarray(rhs)
+
+
+def _has_interpoint(constraints) -> bool:
+    return any(torch.as_tensor(c[0]).dim() == 2 for c in (constraints or []))
+
+
+def sample_polytope(A: np.ndarray, b: np.ndarray, C: np.ndarray, c: np.ndarray, lb: np.ndarray, ub: np.ndarray, n: int,
+                    seed: Optional[int] = None, n_burnin: int = 10000, n_thinning: int = 32, n_chains: int = 64) -> np.ndarray:
+    """Uniform samples from {x : A x <= b, C x = c, lb <= x <= ub} by hit-and-run ([UPSTREAM]
+    botorch.utils.sampling.HitAndRunPolytopeSampler as reached through sample_q_batches_from_polytope; BoFire's own
+    RandomStrategy uses the same sampler, strategies/random.py:180-353).  The chains are vectorised: `n_chains` chains
+    each burn in for n_burnin / n_chains * 8 steps (at least 64) and are thinned by n_thinning."""
+    from scipy.optimize import linprog
+
+    k = lb.shape[0]
+    rng = np.random.default_rng(seed)
+    Ab = np.concatenate([A.reshape(-1, k), np.eye(k), -np.eye(k)], axis=0)
+    bb = np.concatenate([b.reshape(-1), ub, -lb])
+    # equality constraints: x = x0 + Nz with N a basis of the null space of C
+    if C.size:
+        Cm = C.reshape(-1, k)
+        x0 = np.linalg.lstsq(Cm, c, rcond=None)[0]
+        _, sv, Vt = np.linalg.svd(Cm)
+        rank = int((sv > 1e-10 * max(1.0, sv.max())).sum())
+        Nb = Vt[rank:].T
+        if Nb.shape[1] == 0:
+            raise ValueError("equality constraints leave no degree of freedom")
+    else:
+        x0 = np.zeros(k)
+        Nb = np.eye(k)
+    Az = Ab @ Nb
+    bz = bb - Ab @ x0
+    kz = Nb.shape[1]
+    # Chebyshev centre: max r  s.t.  Az z + r |Az_i| <= bz
+    norms = np.linalg.norm(Az, axis=1)
+    keep = norms > 1e-14
+    if np.any(bz[~keep] < -1e-9):
+        raise ValueError("the polytope is empty")
+    Az, bz, norms = Az[keep], bz[keep], norms[keep]
+    res = linprog(np.concatenate([np.zeros(kz), [-1.0]]), A_ub=np.concatenate([Az, norms[:, None]], axis=1), b_ub=bz,
+                  bounds=[(None, None)] * kz + [(0, None)], method="highs")
+    if res.status != 0 or res.x[-1] <= 0:
+        raise ValueError("no interior point: the polytope is empty or has no volume")
+    z = np.tile(res.x[:kz], (n_chains, 1))
+    per_chain = -(-n // n_chains)
+    burn = max(64, (n_burnin * 8) // n_chains)
+    out = np.empty((per_chain, n_chains, kz))
+    total = burn + per_chain * n_thinning
+    for it in range(total):
+        dirs = rng.standard_normal((n_chains, kz))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        slack = bz[None, :] - z @ Az.T          # >= 0 inside
+        rate = dirs @ Az.T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = slack / rate
+        t_hi = np.where(rate > 1e-14, t, np.inf).min(axis=1)
+        t_lo = np.where(rate < -1e-14, t, -np.inf).max(axis=1)
+        step = t_lo + (t_hi - t_lo) * rng.random(n_chains)
+        z = z + step[:, None] * dirs
+        if it >= burn and (it - burn + 1) % n_thinning == 0:
+            out[(it - burn + 1) // n_thinning - 1] = z
+    zs = out.reshape(-1, kz)[rng.permutation(per_chain * n_chains)[:n]]
+    return x0[None, :] + zs @ Nb.T
+
+
+def sample_q_batches_from_polytope(n: int, q: int, bounds: torch.Tensor, inequality_constraints=None,
+                                   equality_constraints=None, seed: Optional[int] = None, n_burnin: int = 10000,
+                                   n_thinning: int = 32, fixed_features: Optional[Dict[int, float]] = None) -> torch.Tensor:
+    """[UPSTREAM] botorch.optim.initializers.sample_q_batches_from_polytope: [n, q, d] raw samples inside the bounds
+    and the linear constraints (inequalities in BoTorch's  sum coef x >= rhs  form).  Fixed features are pinned by
+    collapsing their bounds."""
+    bounds = torch.as_tensor(bounds, dtype=torch.double)
+    d = bounds.shape[-1]
+    lb, ub = bounds[0].numpy().copy(), bounds[1].numpy().copy()
+    for j, v in (fixed_features or {}).items():
+        lb[j] = ub[j] = float(v)
+    inter = _has_interpoint(inequality_constraints) or _has_interpoint(equality_constraints)
+    qq = q if inter else 1          # intra-point constraints + box = product of q identical d-polytopes
+    Ai, bi = dense_linear_constraints(inequality_constraints, qq, d)
+    Ce, ce = dense_linear_constraints(equality_constraints, qq, d)
+    lbq, ubq = np.tile(lb, qq), np.tile(ub, qq)
+    # pinned coordinates (fixed features / degenerate bounds) become equalities so that the polytope keeps a volume
+    pinned = np.nonzero(ubq <= lbq)[0]
+    if pinned.size:
+        E = np.zeros((pinned.size, qq * d))
+        E[np.arange(pinned.size), pinned] = 1.0
+        Ce = np.concatenate([Ce, E], axis=0)
+        ce = np.concatenate([ce, lbq[pinned]])
+        lbq = lbq.copy(); ubq = ubq.copy()
+        lbq[pinned] -= 1.0
+        ubq[pinned] += 1.0
+    x = sample_polytope(-Ai, -bi, Ce, ce, lbq, ubq, n * (q // qq), seed=seed, n_burnin=n_burnin, n_thinning=n_thinning)
+    X = torch.from_numpy(x).view(n, q, d)
+    return apply_fixed_features(X, fixed_features)
+
+
 def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                                  fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
-                                 seed: Optional[int] = None):
-    """[UPSTREAM] gen_batch_initial_conditions without linear constraints: Sobol raw samples, one screened
-    forward over ALL of them on the device, then initialize_q_batch."""
+                                 seed: Optional[int] = None, inequality_constraints=None, equality_constraints=None):
+    """[UPSTREAM] gen_batch_initial_conditions: Sobol raw samples (hit-and-run polytope samples when linear
+    constraints are given), one screened forward over ALL of them on the device, then initialize_q_batch."""
     options = options or {}
     if seed is None:
         seed = int(torch.randint(0, 1000000, (1,)).item())
-    X_rnd = apply_fixed_features(draw_sobol_samples(bounds, raw_samples, q, seed=seed), fixed_features)
+    if inequality_constraints or equality_constraints:
+        X_rnd = sample_q_batches_from_polytope(raw_samples, q, bounds, inequality_constraints, equality_constraints,
+                                               seed=seed, n_burnin=options.get("n_burnin", 10000),
+                                               n_thinning=options.get("thinning", 32), fixed_features=fixed_features)
+    else:
+        X_rnd = apply_fixed_features(draw_sobol_samples(bounds, raw_samples, q, seed=seed), fixed_features)
     with torch.no_grad():
         Y_rnd = acq_function(X_rnd.to(acq_function.model.device))
     X_ic, idcs = initialize_q_batch(X_rnd, Y_rnd, n=num_restarts, eta=options.get("eta", 2.0))
@@ -80,8 +214,10 @@ def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num
 
 
 def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function, lower_bounds, upper_bounds,
-                         fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None):
-    """[UPSTREAM] botorch.generation.gen_candidates_scipy for box bounds: joint L-BFGS-B over all restarts.
+                         fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
+                         inequality_constraints=None, equality_constraints=None):
+    """[UPSTREAM] botorch.generation.gen_candidates_scipy: joint L-BFGS-B over all restarts for box bounds, SLSQP
+    with the linear constraints replicated per restart when (in)equality constraints are given.
     Returns (candidates [r, q, d] CPU, acq values [r] CPU).  options: maxiter (default 2000, BoFire's
     `maxiter`), gradient ("analytic" | "fd"), fd_step (relative to the bound width, default 1e-6)."""
     options = options or {}
@@ -145,7 +281,24 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
 
     x0 = X0[:, :, free_t].reshape(-1).numpy().astype(np.float64)
     bnds = [(float(lb[j]), float(ub[j])) for _ in range(r * q) for j in free]
-    res = minimize(f_and_grad_fd if use_fd else f_and_grad_analytic, x0, jac=True, method="L-BFGS-B", bounds=bnds, options={"maxiter": maxiter})
+    fun = f_and_grad_fd if use_fd else f_and_grad_analytic
+    if inequality_constraints or equality_constraints:
+        cons = []
+        free_cols = np.asarray([j * d + a for j in range(q) for a in free])
+        x_fixed = X0[0].reshape(-1).numpy()     # fixed columns hold the same value in every restart
+        fixed_cols = np.setdiff1d(np.arange(q * d), free_cols)
+        for cset, ctype in ((inequality_constraints, "ineq"), (equality_constraints, "eq")):
+            A1, r1 = dense_linear_constraints(cset, q, d)
+            if not A1.shape[0]:
+                continue
+            r1 = r1 - A1[:, fixed_cols] @ x_fixed[fixed_cols]
+            A1 = A1[:, free_cols]
+            Abig = np.kron(np.eye(r), A1)       # the same rows for every restart
+            rbig = np.tile(r1, r)
+            cons.append({"type": ctype, "fun": (lambda x, A=Abig, rr=rbig: A @ x - rr), "jac": (lambda x, A=Abig: A)})
+        res = minimize(fun, x0, jac=True, method="SLSQP", bounds=bnds, constraints=cons, options={"maxiter": maxiter})
+    else:
+        res = minimize(fun, x0, jac=True, method="L-BFGS-B", bounds=bnds, options={"maxiter": maxiter})
     Xf = unpack(np.clip(res.x, [b_[0] for b_ in bnds], [b_[1] for b_ in bnds]))
     with torch.no_grad():
         vals = acquisition_function(Xf.to(device)).cpu()
@@ -157,15 +310,29 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
                   return_best_only: bool = True, seed: Optional[int] = None, refine: bool = True, **unsupported):
     """Same signature / return convention as botorch.optim.optimize_acqf as BoFire calls it
     (botorch.py:384-405): (candidates [q, d] on CPU, acq_value scalar tensor)."""
-    for key in ("equality_constraints", "inequality_constraints", "nonlinear_inequality_constraints"):
-        if unsupported.get(key):
-            raise NotImplementedError(f"{key} are not handled by the accelerated optimiser yet")
+    if unsupported.get("nonlinear_inequality_constraints"):
+        raise NotImplementedError("nonlinear_inequality_constraints (NChooseK / Product) are not handled by the "
+                                  "accelerated optimiser")
+    ineq = unsupported.get("inequality_constraints") or None
+    eq = unsupported.get("equality_constraints") or None
     bounds = torch.as_tensor(bounds, dtype=torch.double)
     X_ic, Y_ic, _, _ = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples,
-                                                    fixed_features=fixed_features, options=options, seed=seed)
+                                                    fixed_features=fixed_features, options=options, seed=seed,
+                                                    inequality_constraints=ineq, equality_constraints=eq)
     if refine:
         X_ref, Y_ref, _ = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
-                                               options=options)
+                                               options=options, inequality_constraints=ineq, equality_constraints=eq)
+        if ineq or eq:
+            # SLSQP may stop slightly outside the polytope: keep a refined restart only if it is feasible
+            Ai, bi = dense_linear_constraints(ineq, q, bounds.shape[-1])
+            Ae, be = dense_linear_constraints(eq, q, bounds.shape[-1])
+            flat = X_ref.reshape(X_ref.shape[0], -1).numpy()
+            ok = np.ones(flat.shape[0], dtype=bool)
+            if Ai.shape[0]:
+                ok &= (flat @ Ai.T - bi >= -1e-8).all(axis=1)
+            if Ae.shape[0]:
+                ok &= (np.abs(flat @ Ae.T - be) <= 1e-8).all(axis=1)
+            Y_ref = torch.where(torch.from_numpy(ok), Y_ref, torch.full_like(Y_ref, -float("inf")))
         # never return something worse than the screened start (piecewise-smooth MC estimate)
         better = Y_ref >= Y_ic
         X_ic = torch.where(better.view(-1, 1, 1), X_ref, X_ic.cpu())

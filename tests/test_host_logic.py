@@ -144,16 +144,62 @@ def test_gen_candidates_scipy_on_a_known_concave_function():
         def __call__(self, X):
             return -((X - 0.3) ** 2).sum(dim=(1, 2))
 
+        def forward_backward(self, X):
+            return self(X), -2.0 * (X - 0.3)
+
     g = torch.Generator().manual_seed(1)
     ic = torch.rand(3, 2, 4, dtype=DT, generator=g)
-    Xf, vals, info = optim.gen_candidates_scipy(ic, _Fake(), torch.zeros(4), torch.ones(4), fixed_features={1: 0.9},
-                                                options={"maxiter": 50})
-    assert torch.allclose(Xf[..., 1], torch.full((3, 2), 0.9, dtype=DT))          # fixed feature untouched
-    assert torch.allclose(Xf[..., [0, 2, 3]], torch.full((3, 2, 3), 0.3, dtype=DT), atol=1e-6)
-    assert torch.allclose(vals, torch.full((3,), -0.72, dtype=DT), atol=1e-9)
-    # optimum outside the box -> lands on the bound (one-sided differences at the boundary)
-    Xb, _, _ = optim.gen_candidates_scipy(ic, _Fake(), torch.full((4,), 0.5), torch.ones(4), options={"maxiter": 50})
-    assert torch.allclose(Xb, torch.full((3, 2, 4), 0.5, dtype=DT), atol=1e-9)
+    for mode in ("analytic", "fd"):
+        Xf, vals, info = optim.gen_candidates_scipy(ic, _Fake(), torch.zeros(4), torch.ones(4), fixed_features={1: 0.9},
+                                                    options={"maxiter": 50, "gradient": mode})
+        assert torch.allclose(Xf[..., 1], torch.full((3, 2), 0.9, dtype=DT))          # fixed feature untouched
+        assert torch.allclose(Xf[..., [0, 2, 3]], torch.full((3, 2, 3), 0.3, dtype=DT), atol=1e-6)
+        assert torch.allclose(vals, torch.full((3,), -0.72, dtype=DT), atol=1e-9)
+        # optimum outside the box -> lands on the bound (one-sided differences at the boundary)
+        Xb, _, _ = optim.gen_candidates_scipy(ic, _Fake(), torch.full((4,), 0.5), torch.ones(4),
+                                              options={"maxiter": 50, "gradient": mode})
+        assert torch.allclose(Xb, torch.full((3, 2, 4), 0.5, dtype=DT), atol=1e-9)
+    # linear constraints (BoTorch form sum coef x >= rhs, utils/torch_tools.py:45-100) -> SLSQP: maximise -|x - 0.3|^2
+    # subject to x0 + x1 >= 1.0 and x2 == x3: optimum x0 = x1 = 0.5, x2 = x3 = 0.3
+    ineq = [(torch.tensor([0, 1]), torch.tensor([1.0, 1.0]), 1.0)]
+    eq = [(torch.tensor([2, 3]), torch.tensor([1.0, -1.0]), 0.0)]
+    Xc, vc, _ = optim.gen_candidates_scipy(ic, _Fake(), torch.zeros(4), torch.ones(4), options={"maxiter": 200},
+                                           inequality_constraints=ineq, equality_constraints=eq)
+    assert torch.allclose(Xc[..., :2], torch.full((3, 2, 2), 0.5, dtype=DT), atol=1e-5)
+    assert torch.allclose(Xc[..., 2:], torch.full((3, 2, 2), 0.3, dtype=DT), atol=1e-5)
+    # whole optimize_acqf with constraints: polytope raw samples, feasible result
+    cand, val = optim.optimize_acqf(_Fake(), torch.tensor([[0.0] * 4, [1.0] * 4]), q=2, num_restarts=3, raw_samples=32,
+                                    options={"maxiter": 100}, seed=0, inequality_constraints=ineq, equality_constraints=eq)
+    assert cand.shape == (2, 4) and float((cand[:, 0] + cand[:, 1]).min()) >= 1.0 - 1e-8
+    assert float((cand[:, 2] - cand[:, 3]).abs().max()) <= 1e-8 and abs(float(val) + 2 * 0.08) < 1e-6
+
+
+def test_polytope_sampler_and_dense_constraints():
+    """sample_q_batches_from_polytope ([UPSTREAM] hit-and-run, reached from botorch.py:384-405 whenever the domain holds
+    Linear(In)EqualityConstraints): feasibility, fixed features, inter-point equalities, roughly uniform marginals."""
+    b = torch.tensor([[0.0] * 5, [1.0] * 5])
+    ineq = [(torch.tensor([0, 1, 2]), torch.tensor([-1.0, -1.0, -1.0]), -1.0), (torch.tensor([3, 4]), torch.tensor([1.0, 1.0]), 0.5)]
+    eq = [(torch.tensor([0, 4]), torch.tensor([1.0, -1.0]), 0.0)]
+    X = optim.sample_q_batches_from_polytope(512, 2, b, ineq, eq, seed=0)
+    assert X.shape == (512, 2, 5) and float(X.min()) >= 0 and float(X.max()) <= 1
+    assert float(X[..., :3].sum(-1).max()) <= 1 + 1e-12 and float((X[..., 3] + X[..., 4]).min()) >= 0.5 - 1e-12
+    assert float((X[..., 0] - X[..., 4]).abs().max()) < 1e-12
+    assert torch.equal(X, optim.sample_q_batches_from_polytope(512, 2, b, ineq, eq, seed=0))  # seeded
+    Xf = optim.sample_q_batches_from_polytope(8, 3, b, ineq, None, seed=0, fixed_features={1: 0.25})
+    assert torch.equal(Xf[..., 1], torch.full((8, 3), 0.25, dtype=DT))
+    ip = [(torch.tensor([[0, 2], [1, 2]]), torch.tensor([1.0, -1.0]), 0.0)]     # x[0, 2] == x[1, 2]
+    Xi = optim.sample_q_batches_from_polytope(16, 2, b, ineq, ip, seed=1)
+    assert float((Xi[:, 0, 2] - Xi[:, 1, 2]).abs().max()) < 1e-12
+    # simplex x0 + x1 + x2 <= 1 in the unit cube: uniform marginal mean of each coordinate is 1/4
+    Xs = optim.sample_q_batches_from_polytope(4096, 1, torch.tensor([[0.0] * 3, [1.0] * 3]),
+                                              [(torch.tensor([0, 1, 2]), torch.tensor([-1.0] * 3), -1.0)], None, seed=3)
+    assert float((Xs.mean(dim=(0, 1)) - 0.25).abs().max()) < 0.02
+    A, r = optim.dense_linear_constraints(ineq, 2, 5)
+    assert A.shape == (4, 10) and r.tolist() == [-1.0, -1.0, 0.5, 0.5] and A[1, 5:8].tolist() == [-1.0] * 3
+    with pytest.raises(RuntimeError):
+        optim.dense_linear_constraints([(torch.tensor([7]), torch.tensor([1.0]), 0.0)], 1, 5)
+    with pytest.raises(ValueError):   # empty polytope
+        optim.sample_q_batches_from_polytope(4, 1, b, [(torch.tensor([0]), torch.tensor([1.0]), 2.0)], None, seed=0)
 
 
 def test_config_builders_and_oracle_conversion():
