@@ -65,16 +65,25 @@ def himmelblau_qlogei(scale=1.0, N=None, S=None, raw=None, seed=0):
 
 def detergent_qnehvi(N=5, S=512, raw=1024, seed=0):
     """Config 1: Detergent README loop -- 5 inputs, 5 Maximize outputs, N=2..5 points, q=1, RBF-ARD."""
-    rng = np.random.default_rng(seed)
+    import torch
+
+    from .optim import sample_q_batches_from_polytope
+
     lo, hi = B.DETERGENT_BOUNDS
-    X = lo + rng.random((N, 5)) * (hi - lo)
+    # the two LinearInequalityConstraints of benchmarks/detergent.py:66-77 (0.2 <= sum x <= 0.4) in BoTorch's
+    # sum coef x >= rhs form, as get_linear_constraints (utils/torch_tools.py:45-100) hands them to optimize_acqf
+    ineq = [(torch.arange(5), torch.ones(5, dtype=torch.double), 0.2),
+            (torch.arange(5), -torch.ones(5, dtype=torch.double), -0.4)]
+    # initial experiments like RandomStrategy: uniform in the constrained polytope (strategies/random.py:180-353)
+    X = sample_q_batches_from_polytope(N, 1, torch.as_tensor(np.stack([lo, hi])), ineq, None, seed=seed, n_burnin=256,
+                                       n_thinning=4)[:, 0, :].numpy()
     Y = B.detergent(X)
     outputs = [dict(kernel=K.RBFKernel(list(range(5)), [0.5] * 5), y=Y[:, m], noise=1e-4, mean_const=0.0) for m in range(5)]
     obj = MultiObjective([MaximizeObjective(i) for i in range(5)])
     ref = Y.min(axis=0).tolist()  # infer_ref_point: worst observed objective value per output
     return dict(name="detergent_qnehvi", d=5, X=X, Y=Y, outputs=outputs, bounds=np.stack([lo, hi]), in_offset=lo,
                 in_scale=hi - lo, acqf="qnehvi", objective=obj, ref_point=ref, q=1, S=S, raw_samples=raw,
-                num_restarts=8, cand_seed=0, sampler_seed=1234)
+                num_restarts=8, cand_seed=0, sampler_seed=1234, inequality_constraints=ineq)
 
 
 def mixed_tanimoto_qlogei(scale=1.0, N=None, n_bits=2048, S=None, n_choices=None, seed=0):

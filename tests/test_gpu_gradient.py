@@ -150,7 +150,11 @@ def test_matern_scale_additive_kernel_gradient(nu):
     st = Cf.build_state(p)
     acq_o = P.oracle_acqf(p, gp, prune_samples=64)
     acq_d = Cf.build_acqf(p, st, prune_samples=64)
-    check(acq_d, acq_o, Cf.candidates(p), st)
+    # nu = 0.5 is not smooth at r = 0: for baseline points that ARE training points the quadratic-expansion distance is
+    # rounding noise (1e-16), its square root 1e-8, and the baseline posterior covariance (7e-6 here) inherits that
+    # noise on BOTH paths (gpytorch's formula has the same property) -> samples agree to ~1e-6 only
+    tol = dict(val_tol=1e-5, grad_tol=1e-4) if nu == 0.5 else {}
+    check(acq_d, acq_o, Cf.candidates(p), st, **tol)
 
 
 def test_gradient_matches_central_differences_and_autograd_bridge():
