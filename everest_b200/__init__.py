@@ -8,8 +8,16 @@ from ._lib import EverestError, NotPSDError  # noqa: F401
 from .acquisition import (  # noqa: F401
     get_acquisition_function,
     qExpectedHypervolumeImprovement,
+    qExpectedImprovement,
+    qLogExpectedHypervolumeImprovement,
     qLogExpectedImprovement,
+    qLogNoisyExpectedHypervolumeImprovement,
+    qLogNoisyExpectedImprovement,
     qNoisyExpectedHypervolumeImprovement,
+    qNoisyExpectedImprovement,
+    qProbabilityOfImprovement,
+    qSimpleRegret,
+    qUpperConfidenceBound,
 )
 from .model import DeviceGPState, SingleTaskGPSpec, normalize_bounds, standardize_stats  # noqa: F401
 from .optim import (calc_acquisition, gen_batch_initial_conditions, gen_candidates_scipy, initialize_q_batch,

@@ -17,6 +17,7 @@ BO_MAX_CONSTRAINTS = 8
 LEAF_RBF, LEAF_MATERN12, LEAF_MATERN32, LEAF_MATERN52, LEAF_HAMMING, LEAF_TANIMOTO = range(6)
 OBJ_MAX, OBJ_MIN, OBJ_CLOSE_TO_TARGET, OBJ_MIN_SIGMOID, OBJ_MAX_SIGMOID, OBJ_TARGET = range(6)
 COMBINE_SINGLE, COMBINE_ADDITIVE, COMBINE_MULTIPLICATIVE = range(3)
+ACQF_QLOGEI, ACQF_QEI, ACQF_QSR, ACQF_QUCB, ACQF_QPI = range(5)
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int32)
@@ -71,6 +72,12 @@ SYMBOLS = {
                                   c_double_p, c_int_p, C.c_void_p]),
     "bo_logei_prepare": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(ObjectiveOp), C.c_int32, C.c_double,
                                    C.c_void_p]),
+    "bo_scalar_prepare": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.POINTER(ObjectiveOp), C.c_int32,
+                                    C.POINTER(ConstraintOp), C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
+                                    c_int_p, C.c_void_p]),
+    "bo_prune_counts_scalar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.POINTER(ObjectiveOp), C.c_int32, C.c_void_p, c_int_p, C.c_void_p]),
+    "bo_acqf_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "bo_acqf_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "bo_acqf_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -34,6 +34,19 @@ class _DeviceAcquisition:
         self.nb = 0
         self.last_info = None
 
+    def _claim(self):
+        """The handle holds ONE prepared acquisition function: remember which object prepared it last."""
+        self.model._active_acqf = self
+
+    def _check_active(self):
+        if getattr(self.model, "_active_acqf", None) is not self:
+            raise L.EverestError("another acquisition function has been prepared on this DeviceGPState since this one "
+                                 "was built; rebuild it (one prepared acquisition function per state)")
+
+    def set_option(self, name: str, value: float):
+        self._check_active()
+        L.check(self.model.lib.bo_acqf_set_option(self.model.handle, name.encode(), float(value)))
+
     def base_samples_q(self, q: int) -> torch.Tensor:
         """[S, q, M] base samples of the new points: the last q points of a fresh (n_b + q)-point Sobol
         draw with the sampler's seed ([UPSTREAM] NormalMCSampler._update_base_samples)."""
@@ -54,6 +67,7 @@ class _DeviceAcquisition:
             X = X.unsqueeze(0)
         if X.dim() != 3 or X.shape[-1] != self.model.d:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
+        self._check_active()
         on_cpu = X.device.type == "cpu"
         Xd = X.to(self.model.device).contiguous()
         b, q, _ = Xd.shape
@@ -81,6 +95,7 @@ class _DeviceAcquisition:
             X = X.unsqueeze(0)
         if X.dim() != 3 or X.shape[-1] != self.model.d:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
+        self._check_active()
         on_cpu = X.device.type == "cpu"
         Xd = X.detach().to(self.model.device).contiguous()
         b, q, _ = Xd.shape
@@ -102,6 +117,7 @@ class _DeviceAcquisition:
         b, q, d = X.shape
         if d != self.model.d:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
+        self._check_active()
         out = np.empty(b, dtype=np.float64)
         zq = self.base_samples_q(q)
         with torch.cuda.device(self.model.device):
@@ -176,6 +192,7 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
                                                self._n_obj, self._con_c, self._n_con, self._ref_c, info, C.byref(maxc),
                                                _stream()))
         self.max_cells = int(maxc.value)
+        self._claim()
 
     def _prune(self, Xb, prune_samples, seed_offset=7919):
         """[UPSTREAM] prune_inferior_points_multi_objective: keep points with non-zero probability of being
@@ -228,30 +245,195 @@ class qExpectedHypervolumeImprovement(_DeviceAcquisition):
             L.check(model.lib.bo_ehvi_prepare(model.handle, _dev_ptr(Y), Y.shape[0], self.S, self._obj_c, self._n_obj,
                                               self._ref_c, C.byref(maxc), _stream()))
         self.max_cells = int(maxc.value)
+        self._claim()
 
 
-class qLogExpectedImprovement(_DeviceAcquisition):
-    def __init__(self, model: DeviceGPState, best_f: float, objective: ScalarObjective, mc_samples: int = 512,
-                 seed: Optional[int] = None, constraints=None, X_pending=None):
+class qLogNoisyExpectedHypervolumeImprovement(qNoisyExpectedHypervolumeImprovement):
+    """MoboStrategy's default (mobo.py:72-90, data_models/strategies/predictives/mobo.py): same construction as qNEHVI,
+    log-space smoothed value ([UPSTREAM] _compute_log_qehvi; tau_relu = 1e-6, tau_max = 1e-2, fat = True)."""
+
+    def __init__(self, *args, tau_relu: float = 1e-6, tau_max: float = 1e-2, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.set_option("log_hvi", 1)
+        self.set_option("tau_relu", tau_relu)
+        self.set_option("tau_max", tau_max)
+
+
+class qLogExpectedHypervolumeImprovement(qExpectedHypervolumeImprovement):
+    def __init__(self, *args, tau_relu: float = 1e-6, tau_max: float = 1e-2, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.set_option("log_hvi", 1)
+        self.set_option("tau_relu", tau_relu)
+        self.set_option("tau_max", tau_max)
+
+
+class _ScalarAcquisition(_DeviceAcquisition):
+    """Single-objective MC acquisition functions of SoboStrategy (sobo.py:51-90): qLogEI, qEI, qSR, qUCB, qPI with a
+    fixed incumbent and -- when `X_baseline` is given -- the noisy variants qLogNEI (SoboStrategy's default) / qNEI, whose
+    incumbent is the best baseline objective of each MC sample under the cached-root joint posterior."""
+
+    _VARIANT = L.ACQF_QLOGEI
+    _NOISY = False
+
+    def __init__(self, model: DeviceGPState, objective: ScalarObjective, best_f: Optional[float] = None, X_baseline=None,
+                 mc_samples: int = 512, seed: Optional[int] = None, constraints: Optional[List[OutputConstraint]] = None,
+                 eta=None, X_pending=None, prune_baseline: bool = True, prune_samples: int = 2048, param: float = 0.0,
+                 cache_root: bool = True):
         super().__init__(model, mc_samples, seed)
-        if constraints:
-            raise NotImplementedError("output constraints with qLogEI are not accelerated yet")
-        if X_pending is not None:
-            raise NotImplementedError("X_pending with qLogEI is not accelerated yet")
-        self.best_f = float(best_f)
+        if not cache_root:
+            raise NotImplementedError("cache_root=False (joint re-sampling of the baseline) is not accelerated")
         self.objective = objective
+        self.constraints = list(constraints) if constraints else []
+        if eta is not None and self.constraints:
+            etas = [float(eta)] * len(self.constraints) if np.ndim(eta) == 0 else [float(e) for e in eta]
+            self.constraints = [OutputConstraint(c.idx, c.sign, c.tp, e) for c, e in zip(self.constraints, etas)]
         self._obj_c, self._n_obj = c_array(list(objective.ops), L.ObjectiveOp)
+        self._con_c, self._n_con = c_array(self.constraints, L.ConstraintOp)
+        self.param = float(param)
+        Xbd, zb = None, None
+        self.prune_idx = None
+        if self._NOISY:
+            if X_baseline is None:
+                raise ValueError("the noisy variants need X_baseline (X_observed)")
+            Xb = torch.as_tensor(X_baseline, dtype=torch.double)
+            if prune_baseline and Xb.shape[0] > 0:
+                self.prune_idx = self._prune(Xb, prune_samples)
+                Xb = Xb[self.prune_idx.cpu()]
+            if X_pending is not None:
+                Xb = torch.cat([Xb, torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d)], dim=0)
+            if Xb.shape[0] == 0:
+                raise ValueError("the noisy variants need at least one baseline point")
+            self.X_baseline = Xb
+            self.nb = Xb.shape[0]
+            zb = sampling.base_samples(self.nb, model.M, self.S, self.seed).to(model.device).contiguous()
+            self._zb = zb
+            Xbd = Xb.to(model.device).contiguous()
+            self.best_f = float("nan")
+        else:
+            if X_pending is not None:
+                raise NotImplementedError("X_pending needs the noisy variants (qNEI / qLogNEI) on the accelerated path")
+            if best_f is None:
+                raise ValueError("best_f is required")
+            self.best_f = float(best_f)
+        info = (C.c_int32 * model.M)()
         with torch.cuda.device(model.device):
-            L.check(model.lib.bo_logei_prepare(model.handle, self.S, objective.combine_code, self._obj_c, self._n_obj,
-                                               self.best_f, _stream()))
+            L.check(model.lib.bo_scalar_prepare(model.handle, self._VARIANT, self.param, self.S, objective.combine_code,
+                                                self._obj_c, self._n_obj, self._con_c, self._n_con,
+                                                0.0 if self._NOISY else self.best_f,
+                                                _dev_ptr(Xbd) if Xbd is not None else None, self.nb,
+                                                _dev_ptr(zb) if zb is not None else None, info, _stream()))
+        self._claim()
+
+    def _prune(self, Xb, prune_samples, seed_offset=7919):
+        """[UPSTREAM] prune_inferior_points: keep the points that are the best one in at least one joint sample."""
+        model = self.model
+        n = Xb.shape[0]
+        z = sampling.base_samples(n, model.M, prune_samples, self.seed + seed_offset).to(model.device).contiguous()
+        counts = torch.zeros(n, dtype=torch.int32, device=model.device)
+        info = (C.c_int32 * model.M)()
+        Xd = Xb.to(model.device).contiguous()
+        with torch.cuda.device(model.device):
+            L.check(model.lib.bo_prune_counts_scalar(model.handle, _dev_ptr(Xd), n, _dev_ptr(z), prune_samples,
+                                                     self.objective.combine_code, self._obj_c, self._n_obj,
+                                                     _dev_ptr(counts), info, _stream()))
+        self.prune_counts = counts
+        return torch.nonzero(counts > 0).view(-1)
+
+
+class qLogExpectedImprovement(_ScalarAcquisition):
+    def __init__(self, model: DeviceGPState, best_f: float, objective: ScalarObjective, mc_samples: int = 512,
+                 seed: Optional[int] = None, constraints=None, eta=None, X_pending=None):
+        super().__init__(model, objective, best_f=best_f, mc_samples=mc_samples, seed=seed, constraints=constraints,
+                         eta=eta, X_pending=X_pending)
+
+
+class qExpectedImprovement(_ScalarAcquisition):
+    _VARIANT = L.ACQF_QEI
+
+    def __init__(self, model, best_f, objective, mc_samples=512, seed=None, constraints=None, eta=None, X_pending=None):
+        super().__init__(model, objective, best_f=best_f, mc_samples=mc_samples, seed=seed, constraints=constraints,
+                         eta=eta, X_pending=X_pending)
+
+
+class qSimpleRegret(_ScalarAcquisition):
+    _VARIANT = L.ACQF_QSR
+
+    def __init__(self, model, objective, mc_samples=512, seed=None, X_pending=None):
+        super().__init__(model, objective, best_f=0.0, mc_samples=mc_samples, seed=seed, X_pending=X_pending)
+
+
+class qUpperConfidenceBound(_ScalarAcquisition):
+    _VARIANT = L.ACQF_QUCB
+
+    def __init__(self, model, beta, objective, mc_samples=512, seed=None, X_pending=None):
+        super().__init__(model, objective, best_f=0.0, mc_samples=mc_samples, seed=seed, X_pending=X_pending, param=beta)
+
+
+class qProbabilityOfImprovement(_ScalarAcquisition):
+    _VARIANT = L.ACQF_QPI
+
+    def __init__(self, model, best_f, objective, tau=1e-3, mc_samples=512, seed=None, constraints=None, eta=None,
+                 X_pending=None):
+        super().__init__(model, objective, best_f=best_f, mc_samples=mc_samples, seed=seed, constraints=constraints,
+                         eta=eta, X_pending=X_pending, param=tau)
+
+
+class qNoisyExpectedImprovement(_ScalarAcquisition):
+    _VARIANT = L.ACQF_QEI
+    _NOISY = True
+
+    def __init__(self, model, X_baseline, objective, mc_samples=512, seed=None, constraints=None, eta=None, X_pending=None,
+                 prune_baseline=True, prune_samples=2048, cache_root=True):
+        super().__init__(model, objective, X_baseline=X_baseline, mc_samples=mc_samples, seed=seed, constraints=constraints,
+                         eta=eta, X_pending=X_pending, prune_baseline=prune_baseline, prune_samples=prune_samples,
+                         cache_root=cache_root)
+
+
+class qLogNoisyExpectedImprovement(qNoisyExpectedImprovement):
+    _VARIANT = L.ACQF_QLOGEI
 
 
 def get_acquisition_function(acquisition_function_name: str, model: DeviceGPState, objective, X_observed,
-                             X_pending=None, constraints=None, mc_samples: int = 512, seed=None, **kwargs):
-    """Mirror of botorch.acquisition.factory.get_acquisition_function for the accelerated names."""
-    if acquisition_function_name == "qLogEI":
+                             X_pending=None, constraints=None, eta=None, mc_samples: int = 512, seed=None,
+                             ref_point=None, Y=None, alpha: float = 0.0, prune_baseline: bool = True, beta: float = 0.2,
+                             tau: float = 1e-3, cache_root: bool = True, **kwargs):
+    """Mirror of botorch.acquisition.factory.get_acquisition_function as BoFire calls it (sobo.py:64-89,
+    mobo.py:72-90): every name the Sobo / Mobo data models can select."""
+    name = acquisition_function_name
+    if name in ("qEI", "qLogEI", "qPI"):
         mean, _ = model.posterior(X_observed)
         best_f = float(objective(mean.cpu()).max())
-        return qLogExpectedImprovement(model, best_f, objective, mc_samples=mc_samples, seed=seed,
-                                       constraints=constraints, X_pending=X_pending)
+        if name == "qLogEI":
+            return qLogExpectedImprovement(model, best_f, objective, mc_samples=mc_samples, seed=seed,
+                                           constraints=constraints, eta=eta, X_pending=X_pending)
+        if name == "qEI":
+            return qExpectedImprovement(model, best_f, objective, mc_samples=mc_samples, seed=seed, constraints=constraints,
+                                        eta=eta, X_pending=X_pending)
+        return qProbabilityOfImprovement(model, best_f, objective, tau=tau, mc_samples=mc_samples, seed=seed,
+                                         constraints=constraints, eta=eta, X_pending=X_pending)
+    if name == "qSR":
+        return qSimpleRegret(model, objective, mc_samples=mc_samples, seed=seed, X_pending=X_pending)
+    if name == "qUCB":
+        return qUpperConfidenceBound(model, beta, objective, mc_samples=mc_samples, seed=seed, X_pending=X_pending)
+    if name in ("qNEI", "qLogNEI"):
+        cls = qNoisyExpectedImprovement if name == "qNEI" else qLogNoisyExpectedImprovement
+        return cls(model, X_observed, objective, mc_samples=mc_samples, seed=seed, constraints=constraints, eta=eta,
+                   X_pending=X_pending, prune_baseline=prune_baseline, cache_root=cache_root, **kwargs)
+    if name in ("qNEHVI", "qLogNEHVI"):
+        if ref_point is None:
+            raise ValueError("`ref_point` must be specified")
+        cls = qNoisyExpectedHypervolumeImprovement if name == "qNEHVI" else qLogNoisyExpectedHypervolumeImprovement
+        return cls(model, ref_point, X_observed, objective, constraints=constraints, eta=eta, prune_baseline=prune_baseline,
+                   alpha=alpha, cache_root=cache_root, X_pending=X_pending, mc_samples=mc_samples, seed=seed, **kwargs)
+    if name in ("qEHVI", "qLogEHVI"):
+        if ref_point is None or Y is None:
+            raise ValueError("`ref_point` and `Y` must be specified")
+        if alpha != 0.0:
+            raise NotImplementedError("approximate partitioning (alpha > 0) is not part of the accelerated path")
+        if constraints:
+            raise NotImplementedError("output constraints with qEHVI / qLogEHVI are not accelerated; use qNEHVI / qLogNEHVI")
+        # [UPSTREAM] the partitioning is built from the objective values of the observations
+        Yobj = objective(torch.as_tensor(Y, dtype=torch.double))
+        cls = qExpectedHypervolumeImprovement if name == "qEHVI" else qLogExpectedHypervolumeImprovement
+        return cls(model, ref_point, Yobj, objective, mc_samples=mc_samples, seed=seed, X_pending=X_pending)
     raise NotImplementedError(f"Unknown / non-accelerated acquisition function {acquisition_function_name}")

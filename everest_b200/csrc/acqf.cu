@@ -1086,90 +1086,3 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   return BO_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K8: qLogEI = logmeanexp_S( fatmax_q( log_fatplus(obj - best_f, tau_relu), tau_max ) )
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-mc_logei_kernel(McArgs a) {
-  extern __shared__ double msm[];
-  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
-  double* root = msm;
-  double* mu = root + M * q * nr;
-  double* vals = mu + q * M;  // [S]
-  double* red = vals + S;     // [32]
-  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
-  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
-  __syncthreads();
-  const double tau_relu = 1e-6, tau_max = 1e-2;
-  double lmax = -INFINITY;
-  for (int s = tid; s < S; s += nt) {
-    double li[BO_MAX_Q];
-    double mx = -INFINITY;
-    for (int j = 0; j < q; ++j) {
-      double y[2 * BO_MAX_OBJECTIVES];
-      for (int m = 0; m < M; ++m) {
-        const double* rr = root + ((size_t)m * q + j) * nr;
-        double sb = 0.0, sq = 0.0;
-        for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
-        for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
-        y[m] = (mu[j * M + m] + sb) + sq;
-      }
-      double o;
-      if (a.od.combine == BO_COMBINE_SINGLE) {
-        o = objective_apply(a.od.op[0], y);
-      } else if (a.od.combine == BO_COMBINE_ADDITIVE) {
-        o = 0.0;
-        for (int k = 0; k < a.od.n_obj; ++k) o = o + objective_apply(a.od.op[k], y) * a.od.op[k].w;
-      } else {
-        o = 1.0;
-        for (int k = 0; k < a.od.n_obj; ++k) o = o * pow(objective_apply(a.od.op[k], y), a.od.op[k].w);
-      }
-      li[j] = log_fatplus_d(o - a.best_f, tau_relu);
-      mx = fmax(mx, li[j]);
-    }
-    // fatmax over q: mx + tau * log(sum_j pareto((mx - li_j) / tau)), pareto(x) = (2 / (2 + 2x + x^2)) for alpha = 2
-    double ps = 0.0;
-    for (int j = 0; j < q; ++j) {
-      double x = (mx - li[j]) / tau_max;
-      ps += 2.0 / (2.0 + 2.0 * x + x * x);
-    }
-    double v = mx + tau_max * log(ps);
-    vals[s] = v;
-    lmax = fmax(lmax, v);
-  }
-  // block max
-  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = lmax;
-  __syncthreads();
-  double bm = -INFINITY;
-  for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, red[w]);
-  double se = 0.0;
-  for (int s = tid; s < S; s += nt) se += exp(vals[s] - bm);
-  double t = block_sum(se, red);
-  if (tid == 0) {
-    a.out[batch] = bm + log(t) - log((double)S);
-    if (a.info_out) {
-      int v = 0;
-      for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
-      a.info_out[batch] = v;
-    }
-  }
-}
-
-int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
-  if (a.b <= 0) return BO_OK;
-  const int nt = 256;
-  size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + a.S + 32) * sizeof(double);
-  if (smem > 220 * 1024) { bo_set_error("mc_logei: shared memory budget exceeded"); return BO_ERR_INVALID; }
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_logei_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  mc_logei_kernel<<<a.b, nt, smem, st>>>(a);
-  if (lc) lc->n++;
-  CUDA_CHECK_RET(cudaGetLastError());
-  return BO_OK;
-}

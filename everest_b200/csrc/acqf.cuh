@@ -38,6 +38,10 @@ struct McArgs {
   const int* ncells;      // [S] (or [1])
   int cells_shared;
   double best_f;
+  int variant;            // scalar family: bo_scalar_acqf; HVI family: 0 = plain, 1 = log-space (qLogEHVI / qLogNEHVI)
+  double vparam;          // qUCB: beta, qPI: tau
+  const double* best_f_s; // [S] per-MC-sample incumbent of the noisy variants (qNEI / qLogNEI) or NULL
+  double tau_relu, tau_max;  // smoothing temperatures of the log-space variants
   double* out;            // [b]
   const int* info_in;     // [b, M] flags from cond_root
   int* info_out;          // [b] or NULL
@@ -65,7 +69,11 @@ int launch_partition_nd(const double* obj, const unsigned char* front, int n, in
                         cudaStream_t st, LaunchCounter* lc);
 int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc);
 size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
-int launch_mc_logei(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_scalar(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
+// scalarised objective of baseline samples F[m][s][ldf] + mean: per-sample best value and / or arg-max counts per point
+int launch_baseline_best(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od, double* best_f_s,
+                         int* counts, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
 int launch_front_to_mask(const unsigned char* front, int n, int* mask, cudaStream_t st, LaunchCounter* lc);
 int launch_hypervolume_from_cells(const double* obj, const unsigned char* front, int n, int Mo, const double* ref_dev,
                                   const double* lo, const double* up, const int* ncells, double* hv_dev, cudaStream_t st,
@@ -74,7 +82,8 @@ int launch_hypervolume_from_cells(const double* obj, const unsigned char* front,
 // ---- grad.cu: analytic adjoint d acqf / d X (the backward of forward(X[b, q, d])) ----------
 // MC value + d value / d f for every MC sample: dF[m * df_stride + (batch * q + j) * S + s]
 int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
-int launch_mc_logei_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 // dF -> d root [b, M, q, nb+q] (= [d bl | d br]) and d mu [b*q, M]
 int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, const double* zqT, int S, int nb, int q,
                        int M, int rows, double* droot, double* dmu, cudaStream_t st, LaunchCounter* lc);

@@ -119,6 +119,12 @@ struct bo_state {
   int nb = 0, S = 0, ldlb = 0, cap = 0;
   ObjD od;
   double best_f = 0.0;
+  int scalar_variant = 0;      // bo_scalar_acqf
+  double vparam = 0.0;         // qUCB beta / qPI tau
+  bool noisy_scalar = false;   // qNEI / qLogNEI: per-sample incumbent in best_f_s
+  DevBuf best_f_s;
+  int log_hvi = 0;
+  double tau_relu = 1e-6, tau_max = 1e-2;
   DevBuf wsDF, wsDRoot, wsDMu, wsEG, wsEW, wsEmu, wsU;  // adjoint workspaces (grad.cu)
   DevBuf wsGramPart, wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
@@ -160,7 +166,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU};
+                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
@@ -536,19 +542,13 @@ static int build_cells(bo_state* st, const double* obj, const unsigned char* fea
   return BO_OK;
 }
 
-extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b, const double* zb_dev, int32_t S,
-                                const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
-                                const double* ref_point, int32_t* info, int32_t* max_cells, void* stream) {
-  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
-  if (n_obj < 2) { bo_set_error("qNEHVI needs at least two objectives"); return BO_ERR_INVALID; }
-  if (S < 1 || n_b < 0) { bo_set_error("bad S / n_b"); return BO_ERR_INVALID; }
-  cudaStream_t s = (cudaStream_t)stream;
-  st->acqf_kind = 0;
-  RC(fill_objd(&st->od, obj, n_obj, cons, n_cons, 0, st->M));
-  const int M = st->M, ldk = st->ldk, nb = n_b, ldlb = round_up(std::max(nb, 1), 16);
-  st->nb = nb; st->S = S; st->ldlb = ldlb; st->cells_shared = 0;
-  RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
-  CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
+// Cached-root state of a baseline point set (shared by qNEHVI / qLogNEHVI and qNEI / qLogNEI): posterior root L_b and
+// its inverse per output, the extra rows K_bX (K + s2 I)^-1 of LinvExt, the transposed base samples and the baseline
+// samples F = z_b L_b^T (wsF, [M][S][ldlb]) with their mean (mean_b).
+static int prepare_baseline(bo_state* st, const double* Xb_dev, int nb, const double* zb_dev, int S, int32_t* info,
+                            cudaStream_t s) {
+  const int M = st->M, ldk = st->ldk, ldlb = round_up(std::max(nb, 1), 16);
+  st->nb = nb; st->S = S; st->ldlb = ldlb;
   RC(st->mean_b.ensure((size_t)std::max(nb, 1) * M * 8));
   RC(st->zbT.ensure((size_t)std::max(nb, 1) * M * S * 8));
   RC(st->zbM.ensure((size_t)M * S * ldlb * 8, true));
@@ -585,6 +585,24 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
       if (info) info[m] = 0;
     }
   }
+  return BO_OK;
+}
+
+extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b, const double* zb_dev, int32_t S,
+                                const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                                const double* ref_point, int32_t* info, int32_t* max_cells, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  if (n_obj < 2) { bo_set_error("qNEHVI needs at least two objectives"); return BO_ERR_INVALID; }
+  if (S < 1 || n_b < 0) { bo_set_error("bad S / n_b"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  st->acqf_kind = 0; st->log_hvi = 0; st->noisy_scalar = false;
+  RC(fill_objd(&st->od, obj, n_obj, cons, n_cons, 0, st->M));
+  const int M = st->M, nb = n_b;
+  st->cells_shared = 0;
+  RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
+  RC(prepare_baseline(st, Xb_dev, nb, zb_dev, S, info, s));
+  const int ldlb = st->ldlb;
   RC(st->obj_b.ensure((size_t)S * std::max(nb, 1) * n_obj * 8));
   RC(st->samples_b.ensure((size_t)S * std::max(nb, 1) * M * 8));
   RC(st->wsFeas.ensure((size_t)S * std::max(nb, 1)));
@@ -600,7 +618,7 @@ extern "C" int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, 
                                int32_t n_obj, const double* ref_point, int32_t* max_cells, void* stream) {
   if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
   cudaStream_t s = (cudaStream_t)stream;
-  st->acqf_kind = 0;
+  st->acqf_kind = 0; st->log_hvi = 0; st->noisy_scalar = false;
   RC(fill_objd(&st->od, obj, n_obj, nullptr, 0, 0, st->M));
   st->nb = 0; st->S = S; st->ldlb = 16; st->cells_shared = 1;
   RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
@@ -620,22 +638,96 @@ extern "C" int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, 
   return BO_OK;
 }
 
-extern "C" int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
-                                double best_f, void* stream) {
+extern "C" int bo_scalar_prepare(bo_state* st, int32_t variant, double param, int32_t S, int32_t combine,
+                                 const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                                 double best_f, const double* Xb_dev, int32_t n_b, const double* zb_dev, int32_t* info,
+                                 void* stream) {
   if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
   cudaStream_t s = (cudaStream_t)stream;
-  st->acqf_kind = 0;
+  st->acqf_kind = 0; st->log_hvi = 0; st->noisy_scalar = false;
+  if (variant < BO_ACQF_QLOGEI || variant > BO_ACQF_QPI) { bo_set_error("unknown scalar acquisition variant %d", variant); return BO_ERR_INVALID; }
   if (combine == BO_COMBINE_SINGLE && n_obj != 1) { bo_set_error("single objective needs n_obj == 1"); return BO_ERR_INVALID; }
-  RC(fill_objd(&st->od, obj, n_obj, nullptr, 0, combine, st->M));
-  st->nb = 0; st->S = S; st->ldlb = 16; st->cells_shared = 0; st->best_f = best_f;
-  RC(st->zbT.ensure(16));
-  for (int m = 0; m < st->M; ++m) {
-    OutputH& o = st->out[m];
-    RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
-    RC(o.Lb.ensure(16));
-    RC(build_linv_ext(st, o, 0, s));
+  if (S < 1 || n_b < 0) { bo_set_error("bad S / n_b"); return BO_ERR_INVALID; }
+  if (n_b > 0 && variant != BO_ACQF_QEI && variant != BO_ACQF_QLOGEI) { bo_set_error("a baseline (noisy variant) exists for qNEI / qLogNEI only"); return BO_ERR_INVALID; }
+  if (n_cons > 0 && (variant == BO_ACQF_QSR || variant == BO_ACQF_QUCB)) { bo_set_error("output constraints need a non-negative utility (not qSR / qUCB)"); return BO_ERR_INVALID; }
+  if (variant == BO_ACQF_QPI && !(param > 0.0)) { bo_set_error("qPI needs tau > 0"); return BO_ERR_INVALID; }
+  if (variant == BO_ACQF_QUCB && !(param >= 0.0)) { bo_set_error("qUCB needs beta >= 0"); return BO_ERR_INVALID; }
+  RC(fill_objd(&st->od, obj, n_obj, cons, n_cons, combine, st->M));
+  st->cells_shared = 0; st->best_f = best_f; st->scalar_variant = variant; st->vparam = param;
+  if (n_b > 0) {
+    RC(prepare_baseline(st, Xb_dev, n_b, zb_dev, S, info, s));
+    RC(st->best_f_s.ensure((size_t)S * 8));
+    RC(launch_baseline_best(st->wsF.as<double>(), st->ldlb, S, n_b, st->M, st->mean_b.as<double>(), st->od,
+                            st->best_f_s.as<double>(), nullptr, s, &st->lc));
+    st->noisy_scalar = true;
+  } else {
+    st->nb = 0; st->S = S; st->ldlb = 16;
+    RC(st->zbT.ensure(16));
+    for (int m = 0; m < st->M; ++m) {
+      OutputH& o = st->out[m];
+      RC(o.base_prep.ensure(o.md, 0, &o.base_prepd));
+      RC(o.Lb.ensure(16));
+      RC(build_linv_ext(st, o, 0, s));
+      if (info) info[m] = 0;
+    }
   }
   st->acqf_kind = 3;
+  return BO_OK;
+}
+
+extern "C" int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
+                                double best_f, void* stream) {
+  return bo_scalar_prepare(st, BO_ACQF_QLOGEI, 0.0, S, combine, obj, n_obj, nullptr, 0, best_f, nullptr, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S,
+                                      int32_t combine, const bo_objective_op* obj, int32_t n_obj, int32_t* counts_dev,
+                                      int32_t* info, void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  if (n < 1 || S < 1) { bo_set_error("bad n / S"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ObjD od;
+  RC(fill_objd(&od, obj, n_obj, nullptr, 0, combine, st->M));
+  const int M = st->M, ldn = round_up(n, 16), ldk = st->ldk;
+  RC(st->wsMean.ensure((size_t)n * M * 8));
+  RC(st->wsZM.ensure((size_t)M * S * ldn * 8, true));
+  RC(st->wsF.ensure((size_t)M * S * ldn * 8));
+  RC(st->wsV.ensure((size_t)n * ldk * 8, true));
+  RC(launch_transpose_base_samples(z_dev, S, n, M, nullptr, st->wsZM.as<double>(), ldn, s, &st->lc));
+  DevBuf root, cov;
+  PrepBuf pb; PrepD pd;
+  int rcode = BO_OK;
+  for (int m = 0; m < M && rcode == BO_OK; ++m) {
+    int inf = 0; double jit = 0;
+    rcode = joint_root(st, m, X_dev, n, ldn, pb, &pd, st->wsMean.as<double>(), root, cov, st->wsV.as<double>(), &inf, &jit, s);
+    if (info) info[m] = inf;
+    if (rcode == BO_OK && inf != 0) { bo_set_error("posterior covariance at the baseline not p.d. (output %d)", m); rcode = BO_ERR_NOT_PSD; }
+    if (rcode == BO_OK)
+      rcode = launch_gemm_nt(S, n, n, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldn, ldn, root.as<double>(), ldn, 0.0,
+                             st->wsF.as<double>() + (size_t)m * S * ldn, ldn, false, s, &st->lc);
+  }
+  if (rcode == BO_OK) {
+    cudaMemsetAsync(counts_dev, 0, (size_t)n * sizeof(int), s);
+    rcode = launch_baseline_best(st->wsF.as<double>(), ldn, S, n, M, st->wsMean.as<double>(), od, nullptr, counts_dev, s, &st->lc);
+  }
+  cudaStreamSynchronize(s);
+  root.release(); cov.release(); pb.release();
+  return rcode;
+}
+
+extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) {
+  if (!st || !name) { bo_set_error("null argument"); return BO_ERR_INVALID; }
+  std::string nm(name);
+  if (nm == "log_hvi") {
+    if (st->acqf_kind != 1 && st->acqf_kind != 2) { bo_set_error("log_hvi applies to a prepared qNEHVI / qEHVI"); return BO_ERR_STATE; }
+    st->log_hvi = value != 0.0;
+  } else if (nm == "tau_relu") {
+    if (!(value > 0.0)) { bo_set_error("tau_relu must be > 0"); return BO_ERR_INVALID; }
+    st->tau_relu = value;
+  } else if (nm == "tau_max") {
+    if (!(value > 0.0)) { bo_set_error("tau_max must be > 0"); return BO_ERR_INVALID; }
+    st->tau_max = value;
+  } else { bo_set_error("unknown option '%s'", name); return BO_ERR_INVALID; }
   return BO_OK;
 }
 
@@ -744,6 +836,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     ma.mu = st->wsMu.as<double>(); ma.zbT = st->zbT.as<double>(); ma.zqT = st->wsZqT.as<double>();
     ma.cell_lo = st->cell_lo.as<double>(); ma.cell_up = st->cell_up.as<double>(); ma.ncells = st->ncells.as<int>();
     ma.cells_shared = st->cells_shared; ma.best_f = st->best_f; ma.out = out_dev + b0;
+    ma.variant = st->acqf_kind == 3 ? st->scalar_variant : st->log_hvi; ma.vparam = st->vparam;
+    ma.best_f_s = st->noisy_scalar ? st->best_f_s.as<double>() : nullptr; ma.tau_relu = st->tau_relu; ma.tau_max = st->tau_max;
     ma.info_in = st->wsJit.as<int>(); ma.info_out = info_dev ? info_dev + b0 : nullptr;
     ma.Fp = sample_gemm ? st->wsFp.as<double>() : nullptr; ma.fp_stride = rows_max * (size_t)S;
     ma.partial = st->wsPartial.as<double>();
@@ -758,7 +852,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       RC(st->wsEmu.ensure(rows_max * 8));
       RC(st->wsU.ensure(rows_max * ldk * 8, false));
       rec_begin(st, "mc_grad", s);
-      if (st->acqf_kind == 3) RC(launch_mc_logei_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      if (st->acqf_kind == 3) RC(launch_mc_scalar_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      else if (st->log_hvi) RC(launch_mc_loghvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
       else RC(launch_mc_hvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
       rec_end(st, s);
       rec_begin(st, "grad_reduce", s);
@@ -791,7 +886,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       continue;
     }
     rec_begin(st, "mc_acqf", s);
-    if (st->acqf_kind == 3) RC(launch_mc_logei(ma, s, &st->lc));
+    if (st->acqf_kind == 3) RC(launch_mc_scalar(ma, s, &st->lc));
+    else if (st->log_hvi) RC(launch_mc_loghvi(ma, s, &st->lc));
     else {
       size_t ow = mc_hvi_obj_ws_bytes(ma, st->max_cells);
       if (ow) RC(st->wsObjW.ensure(ow));

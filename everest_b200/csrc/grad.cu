@@ -203,112 +203,6 @@ int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------------
-// qLogEI value and d value / d f:  value = logmeanexp_S( fatmax_q( log_fatplus(obj - best_f) ) )
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-mc_logei_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
-  extern __shared__ double gsm[];
-  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
-  double* root = gsm;
-  double* mu = root + (size_t)M * q * nr;
-  double* vals = mu + q * M;  // [S]
-  double* red = vals + S;     // [32] + broadcast slot
-  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
-  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
-  __syncthreads();
-  const double tau_relu = 1e-6, tau_max = 1e-2;
-  double lmax = -INFINITY;
-  double bm = 0.0, tsum = 0.0;
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int s = tid; s < S; s += nt) {
-      double li[BO_MAX_Q], dli[BO_MAX_Q];
-      double dys[BO_MAX_Q][2 * BO_MAX_OBJECTIVES];
-      double mx = -INFINITY;
-      int jstar = 0;
-      for (int j = 0; j < q; ++j) {
-        double y[2 * BO_MAX_OBJECTIVES];
-        for (int m = 0; m < M; ++m) {
-          const double* rr = root + ((size_t)m * q + j) * nr;
-          double sb = 0.0, sq = 0.0;
-          for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
-          for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
-          y[m] = (mu[j * M + m] + sb) + sq;
-        }
-        const double o = scalar_objective_apply(a.od, y, M, pass ? dys[j] : nullptr);
-        li[j] = log_fatplus_d(o - a.best_f, tau_relu);
-        if (pass) dli[j] = log_fatplus_grad_d(o - a.best_f, tau_relu);
-        if (li[j] > mx) { mx = li[j]; jstar = j; }
-      }
-      double ps = 0.0;
-      for (int j = 0; j < q; ++j) {
-        double x = (mx - li[j]) / tau_max;
-        ps += 2.0 / (2.0 + 2.0 * x + x * x);
-      }
-      if (!pass) {
-        double v = mx + tau_max * log(ps);
-        vals[s] = v;
-        lmax = fmax(lmax, v);
-      } else {
-        const double wS = exp(vals[s] - bm) / tsum;  // d value / d h_s
-        double via_mx = 1.0;
-        double direct[BO_MAX_Q];
-        for (int j = 0; j < q; ++j) {
-          double x = (mx - li[j]) / tau_max;
-          double P = 2.0 / (2.0 + 2.0 * x + x * x);
-          double dP = -P * P * (1.0 + x);  // pareto'(x)
-          direct[j] = -dP / ps;            // through x_j = (mx - li_j) / tau, mx held fixed
-          via_mx += dP / ps;               // through mx (amax -> arg-max element)
-        }
-        direct[jstar] += via_mx;
-        for (int j = 0; j < q; ++j) {
-          const double gj = wS * direct[j] * dli[j];
-          for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = gj * dys[j][m];
-        }
-      }
-    }
-    if (!pass) {
-      for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-      __syncthreads();
-      if ((tid & 31) == 0) red[tid >> 5] = lmax;
-      __syncthreads();
-      bm = -INFINITY;
-      for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, red[w]);
-      double se = 0.0;
-      for (int s = tid; s < S; s += nt) se += exp(vals[s] - bm);
-      double t = block_sum(se, red);
-      if (tid == 0) {
-        red[32] = t;
-        a.out[batch] = bm + log(t) - log((double)S);
-        if (a.info_out) {
-          int v = 0;
-          for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
-          a.info_out[batch] = v;
-        }
-      }
-      __syncthreads();
-      tsum = red[32];
-    }
-  }
-}
-
-int launch_mc_logei_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
-  if (a.b <= 0) return BO_OK;
-  const int nt = 128;
-  size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + a.S + 40) * sizeof(double);
-  if (smem > 220 * 1024) { bo_set_error("mc_logei_grad: shared memory budget exceeded"); return BO_ERR_INVALID; }
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_logei_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  mc_logei_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
-  if (lc) lc->n++;
-  CUDA_CHECK_RET(cudaGetLastError());
-  return BO_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // d root = [ dF z_b | dF z_q ],  d mu = sum_s dF   (one CTA per (candidate point, output); warps over targets)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -1,0 +1,331 @@
+// Log-space hypervolume improvement: qLogEHVI / qLogNEHVI (MoboStrategy's default acquisition function,
+// strategies/predictives/mobo.py:72-90 -> get_acquisition_function("qLogNEHVI", ...)).
+// [UPSTREAM] botorch.acquisition.multi_objective.logei._compute_log_qehvi, restated in oracle/bo_oracle.py
+// (log_hvi_inclusion_exclusion).  Per MC sample s and cell c, for every non-empty subset J of the q points:
+//   v_o   = fatmin_{j in J} obj_jo                 (tau_max)
+//   w_o   = fatmin(v_o, upper_co)                  (exact v_o for an unbounded cell side)
+//   la_J  = sum_o log_fatplus(w_o - lower_co, tau_relu)  [+ sum_{j in J} log feasibility_j]
+//   cell  = log( sum_{|J| odd} e^la_J - sum_{|J| even} e^la_J ),   sample = logsumexp_c cell,   value = logmeanexp_s sample
+// Unlike the plain HVI nothing can be skipped: the fat tails make every (cell, subset) pair contribute.
+// One CTA per q-batch, threads over MC samples.  The gradient kernel uses running-max rescaling over the cells (the
+// softmax weights of the cells are only known at the end) and writes d value / d f per MC sample.
+#include "acqf.cuh"
+#include "common.cuh"
+#include "mc_math.cuh"
+
+#define LH_MAXO BO_MAX_OBJECTIVES
+
+// side length of the overlap of subset `sub` with the cell along objective o; optionally d len / d obj_j for the members
+__device__ __forceinline__ double subset_axis(unsigned sub, const double* __restrict__ objs_o /* [q] stride nt */, int nt,
+                                              double lo, double up, double tau_max, double* dlen /* [q] or null */) {
+  // fatmin over the members
+  double mn = INFINITY;
+  int kstar = -1;
+  for (unsigned rest = sub; rest; rest &= rest - 1) {
+    const int j = __ffs(rest) - 1;
+    const double x = objs_o[(size_t)j * nt];
+    if (x < mn) { mn = x; kstar = j; }
+  }
+  double v, ps = 1.0, dps = -1.0;  // the minimum itself: P(0) = 1, P'(0) = -1
+  if ((sub & (sub - 1)) == 0) {
+    v = mn;
+  } else {
+    ps = 0.0; dps = 0.0;
+    for (unsigned rest = sub; rest; rest &= rest - 1) {
+      const int j = __ffs(rest) - 1;
+      const double y = (objs_o[(size_t)j * nt] - mn) / tau_max;
+      const double P = pareto2_d(y);
+      ps += P;
+      dps += -P * P * (1.0 + y);
+    }
+    v = mn - tau_max * log(ps);
+  }
+  // smooth minimum with the cell's upper bound
+  double w, dw_dv;
+  if (isinf(up)) {
+    w = v; dw_dv = 1.0;
+  } else if (v <= up) {
+    const double y = (up - v) / tau_max, P = pareto2_d(y);
+    w = v - tau_max * log(1.0 + P);
+    dw_dv = 1.0 + (-P * P * (1.0 + y)) / (1.0 + P);
+  } else {
+    const double y = (v - up) / tau_max, P = pareto2_d(y);
+    w = up - tau_max * log(1.0 + P);
+    dw_dv = P * P * (1.0 + y) / (1.0 + P);
+  }
+  if (dlen) {
+    for (unsigned rest = sub; rest; rest &= rest - 1) {
+      const int j = __ffs(rest) - 1;
+      double dv;
+      if ((sub & (sub - 1)) == 0) dv = 1.0;
+      else {
+        const double y = (objs_o[(size_t)j * nt] - mn) / tau_max;
+        const double P = pareto2_d(y);
+        dv = P * P * (1.0 + y) / ps;               // -P'(y_j) / sum P
+        if (j == kstar) dv += 1.0 + dps / ps;       // through the minimum
+      }
+      dlen[j] = dw_dv * dv;
+    }
+  }
+  return w - lo;
+}
+
+struct LhSmem { double *root, *mu, *objs, *lfw, *gob, *glf, *ys, *vals, *red; };
+
+__device__ __forceinline__ LhSmem lh_smem(double* base, int M, int q, int nr, int Mo, int nt, int S, bool grad) {
+  LhSmem sm;
+  sm.root = base;
+  sm.mu = sm.root + (size_t)M * q * nr;
+  sm.objs = sm.mu + q * M;
+  sm.lfw = sm.objs + (size_t)q * Mo * nt;
+  double* p = sm.lfw + (size_t)q * nt;
+  if (grad) {
+    sm.gob = p; p += (size_t)q * Mo * nt;
+    sm.glf = p; p += (size_t)q * nt;
+    sm.ys = p; p += (size_t)q * M * nt;
+  } else {
+    sm.gob = sm.glf = sm.ys = nullptr;
+  }
+  sm.vals = p;
+  sm.red = sm.vals + S;
+  return sm;
+}
+
+__device__ __forceinline__ void lh_load_sample(const McArgs& a, const LhSmem& sm, int batch, int s, int tid, int nt) {
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  for (int j = 0; j < q; ++j) {
+    double y[2 * BO_MAX_OBJECTIVES];
+    for (int m = 0; m < M; ++m) {
+      const double* rr = sm.root + ((size_t)m * q + j) * nr;
+      double sb = 0.0, sq = 0.0;
+      if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
+      else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+      for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+      y[m] = (sm.mu[j * M + m] + sb) + sq;
+      if (sm.ys) sm.ys[((size_t)j * M + m) * nt + tid] = y[m];
+    }
+    for (int o = 0; o < Mo; ++o) {
+      sm.objs[((size_t)j * Mo + o) * nt + tid] = objective_apply(a.od.op[o], y);
+      if (sm.gob) sm.gob[((size_t)j * Mo + o) * nt + tid] = 0.0;
+    }
+    sm.lfw[(size_t)j * nt + tid] = a.od.n_cons ? log_feas_fat(a.od, y, 0.0, nullptr) : 0.0;
+    if (sm.glf) sm.glf[(size_t)j * nt + tid] = 0.0;
+  }
+}
+
+// log area of the overlap of subset `sub` with the cell
+__device__ __forceinline__ double subset_logarea(const McArgs& a, const LhSmem& sm, unsigned sub, const double* lo,
+                                                 const double* up, int tid, int nt) {
+  const int Mo = a.od.n_obj;
+  double la = 0.0;
+  for (int o = 0; o < Mo; ++o) {
+    const double len = subset_axis(sub, sm.objs + (size_t)o * nt + tid, Mo * nt, lo[o], up[o], a.tau_max, nullptr);
+    la += log_fatplus_d(len, a.tau_relu);
+  }
+  if (a.od.n_cons)
+    for (unsigned rest = sub; rest; rest &= rest - 1) la += sm.lfw[(size_t)(__ffs(rest) - 1) * nt + tid];
+  return la;
+}
+
+__device__ __forceinline__ void lh_finish(const McArgs& a, const LhSmem& sm, double lmax, double* bm_out, double* tsum_out) {
+  const int tid = threadIdx.x, nt = blockDim.x, batch = blockIdx.x, S = a.S;
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  __syncthreads();
+  if ((tid & 31) == 0) sm.red[tid >> 5] = lmax;
+  __syncthreads();
+  double bm = -INFINITY;
+  for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, sm.red[w]);
+  double se = 0.0;
+  for (int s = tid; s < S; s += nt) se += exp(sm.vals[s] - bm);
+  double t = block_sum(se, sm.red);
+  if (tid == 0) sm.red[32] = t;
+  __syncthreads();
+  const double tsum = sm.red[32];
+  if (tid == 0) {
+    a.out[batch] = bm + log(tsum) - log((double)S);
+    if (a.info_out) {
+      int v = 0;
+      for (int m = 0; m < a.M; ++m) v |= a.info_in[(size_t)batch * a.M + m];
+      a.info_out[batch] = v;
+    }
+  }
+  if (bm_out) *bm_out = bm;
+  if (tsum_out) *tsum_out = tsum;
+}
+
+__global__ void __launch_bounds__(256)
+mc_loghvi_kernel(McArgs a) {
+  extern __shared__ double lsm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nr = a.nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  LhSmem sm = lh_smem(lsm, M, q, nr, Mo, nt, S, false);
+  for (int i = tid; i < M * q * nr; i += nt) sm.root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) sm.mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+  const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  double lmax = -INFINITY;
+  for (int s = tid; s < S; s += nt) {
+    lh_load_sample(a, sm, batch, s, tid, nt);
+    const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+    const int sc = a.cells_shared ? 0 : s;
+    const int Sc = a.cells_shared ? 1 : S;
+    double R = -INFINITY, ssum = 0.0;  // running logsumexp over the cells
+    for (int c = 0; c < nc; ++c) {
+      double lo[LH_MAXO], up[LH_MAXO];
+      for (int o = 0; o < Mo; ++o) {
+        lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+        up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
+      }
+      double odd = -INFINITY, even = -INFINITY;
+      for (unsigned sub = 1; sub <= full; ++sub) {
+        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt);
+        if (__popc(sub) & 1) odd = logaddexp_d(odd, la);
+        else even = logaddexp_d(even, la);
+      }
+      const double cellv = (isinf(even) && even < 0) ? odd : odd + log1mexp_d(even - odd);
+      if (cellv > R) { ssum = ssum * exp(R - cellv) + 1.0; R = cellv; }
+      else if (!(isinf(cellv) && cellv < 0)) ssum += exp(cellv - R);
+    }
+    const double sv = (nc > 0) ? R + log(ssum) : -INFINITY;
+    sm.vals[s] = sv;
+    lmax = fmax(lmax, sv);
+  }
+  lh_finish(a, sm, lmax, nullptr, nullptr);
+}
+
+static int lh_pick_threads(const McArgs& a, bool grad, size_t* smem_out) {
+  const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M + a.S + 40;
+  const size_t per = (size_t)a.q * a.od.n_obj + a.q + (grad ? (size_t)a.q * a.od.n_obj + a.q + (size_t)a.q * a.M : 0);
+  for (int nt = 256; nt >= 32; nt >>= 1) {
+    size_t smem = (fixed + per * nt) * sizeof(double);
+    if (smem <= 200 * 1024) { *smem_out = smem; return nt; }
+  }
+  return 0;
+}
+
+int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  size_t smem = 0;
+  const int nt = lh_pick_threads(a, false, &smem);
+  if (!nt) { bo_set_error("mc_loghvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_loghvi_kernel<<<a.b, nt, smem, st>>>(a);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+__global__ void __launch_bounds__(256)
+mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
+  extern __shared__ double lsm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int q = a.q, nr = a.nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  LhSmem sm = lh_smem(lsm, M, q, nr, Mo, nt, S, true);
+  for (int i = tid; i < M * q * nr; i += nt) sm.root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) sm.mu[i] = a.mu[(size_t)batch * q * M + i];
+  __syncthreads();
+  const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  const bool has_cons = a.od.n_cons > 0;
+  double lmax = -INFINITY;
+  for (int s = tid; s < S; s += nt) {
+    lh_load_sample(a, sm, batch, s, tid, nt);
+    const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+    const int sc = a.cells_shared ? 0 : s;
+    const int Sc = a.cells_shared ? 1 : S;
+    double R = -INFINITY, ssum = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      double lo[LH_MAXO], up[LH_MAXO];
+      for (int o = 0; o < Mo; ++o) {
+        lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+        up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
+      }
+      double odd = -INFINITY, even = -INFINITY;
+      for (unsigned sub = 1; sub <= full; ++sub) {
+        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt);
+        if (__popc(sub) & 1) odd = logaddexp_d(odd, la);
+        else even = logaddexp_d(even, la);
+      }
+      const bool no_even = isinf(even) && even < 0;
+      const double cellv = no_even ? odd : odd + log1mexp_d(even - odd);
+      if (isinf(cellv) && cellv < 0) continue;
+      // running-max rescaling of everything accumulated so far
+      double wc;
+      if (cellv > R) {
+        const double sc_old = exp(R - cellv);  // 0 when R = -inf
+        for (int i = 0; i < q * Mo; ++i) sm.gob[(size_t)i * nt + tid] *= sc_old;
+        if (has_cons) for (int j = 0; j < q; ++j) sm.glf[(size_t)j * nt + tid] *= sc_old;
+        ssum = ssum * sc_old + 1.0;
+        R = cellv;
+        wc = 1.0;
+      } else {
+        wc = exp(cellv - R);
+        ssum += wc;
+      }
+      const double r = no_even ? 0.0 : exp(even - odd);
+      const double a_odd = 1.0 / (1.0 - r), a_even = -r / (1.0 - r);
+      for (unsigned sub = 1; sub <= full; ++sub) {
+        // recompute the subset: side lengths and their derivatives
+        double la = 0.0;
+        double dlen[LH_MAXO][BO_MAX_Q];
+        double dlf[LH_MAXO];
+        for (int o = 0; o < Mo; ++o) {
+          const double len = subset_axis(sub, sm.objs + (size_t)o * nt + tid, Mo * nt, lo[o], up[o], a.tau_max, dlen[o]);
+          la += log_fatplus_d(len, a.tau_relu);
+          dlf[o] = log_fatplus_grad_d(len, a.tau_relu);
+        }
+        if (has_cons)
+          for (unsigned rest = sub; rest; rest &= rest - 1) la += sm.lfw[(size_t)(__ffs(rest) - 1) * nt + tid];
+        const bool is_odd = __popc(sub) & 1;
+        const double kappa = wc * (is_odd ? a_odd * exp(la - odd) : a_even * exp(la - even));
+        if (kappa == 0.0) continue;
+        for (unsigned rest = sub; rest; rest &= rest - 1) {
+          const int j = __ffs(rest) - 1;
+          for (int o = 0; o < Mo; ++o) sm.gob[((size_t)j * Mo + o) * nt + tid] += kappa * dlf[o] * dlen[o][j];
+          if (has_cons) sm.glf[(size_t)j * nt + tid] += kappa;
+        }
+      }
+    }
+    const double sv = (ssum > 0.0) ? R + log(ssum) : -INFINITY;
+    sm.vals[s] = sv;
+    lmax = fmax(lmax, sv);
+    // un-normalised d sample value / d f (scaled by the sample's softmax weight after the block reduction)
+    const double inv = (ssum > 0.0) ? 1.0 / ssum : 0.0;
+    for (int j = 0; j < q; ++j) {
+      double y[2 * BO_MAX_OBJECTIVES], dy[2 * BO_MAX_OBJECTIVES];
+      for (int m = 0; m < M; ++m) { y[m] = sm.ys[((size_t)j * M + m) * nt + tid]; dy[m] = 0.0; }
+      for (int o = 0; o < Mo; ++o) {
+        const double gv = sm.gob[((size_t)j * Mo + o) * nt + tid] * inv;
+        if (gv != 0.0) dy[a.od.op[o].out_idx] += gv * objective_grad(a.od.op[o], y);
+      }
+      if (has_cons) log_feas_fat(a.od, y, sm.glf[(size_t)j * nt + tid] * inv, dy);
+      for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m];
+    }
+  }
+  double bm, tsum;
+  lh_finish(a, sm, lmax, &bm, &tsum);
+  for (int s = tid; s < S; s += nt) {
+    const double wS = exp(sm.vals[s] - bm) / tsum;
+    for (int j = 0; j < q; ++j)
+      for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] *= wS;
+  }
+}
+
+int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
+  if (a.b <= 0) return BO_OK;
+  size_t smem = 0;
+  const int nt = lh_pick_threads(a, true, &smem);
+  if (!nt) { bo_set_error("mc_loghvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  mc_loghvi_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}

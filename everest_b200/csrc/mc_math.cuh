@@ -48,6 +48,55 @@ __device__ __forceinline__ double log_fatplus_grad_d(double x, double tau) {
   return (exp(A - lae) * dA + exp(B - lae) * dB) / tau;
 }
 
+// pareto(x) = 2 / (2 + 2x + x^2): the alpha = 2 kernel of fatmax / fatmin; derivative -P^2 (1 + x)
+__device__ __forceinline__ double pareto2_d(double x) { return 2.0 / (2.0 + 2.0 * x + x * x); }
+__device__ __forceinline__ double log1mexp_d(double x) {  // log(1 - exp(x)), x < 0
+  return (x > -0.6931471805599453) ? log(-expm1(x)) : log1p(-exp(x));
+}
+// fatmoid: twice differentiable step with an O(1/x^2) tail (log-space feasibility weights, fat = True)
+__device__ __forceinline__ double fatmoid_d(double x) {
+  const double m = 0.5773502691896258;
+  if (x < 0.0) { const double t = x - m; return (2.0 / 3.0) / (1.0 + t * t); }
+  const double t = x + m;
+  return 1.0 - (2.0 / 3.0) / (1.0 + t * t);
+}
+__device__ __forceinline__ double fatmoid_grad_d(double x) {
+  const double m = 0.5773502691896258;
+  const double t = (x < 0.0) ? x - m : x + m;
+  const double den = 1.0 + t * t;
+  const double g = (2.0 / 3.0) * 2.0 * t / (den * den);
+  return (x < 0.0) ? -g : g;
+}
+// log feasibility weight sum_c log fatmoid(-c(y) / eta) and (optionally) its gradient w.r.t. the outputs (added into dy)
+__device__ __forceinline__ double log_feas_fat(const ObjD& od, const double* y, double scale, double* dy) {
+  double lf = 0.0;
+  for (int c = 0; c < od.n_cons; ++c) {
+    const double x = -od.con[c].sign * (y[od.con[c].out_idx] - od.con[c].tp) / od.con[c].eta;
+    const double f = fatmoid_d(x);
+    lf += log(f);
+    if (dy) dy[od.con[c].out_idx] += scale * (fatmoid_grad_d(x) / f) * (-od.con[c].sign / od.con[c].eta);
+  }
+  return lf;
+}
+// feasibility weight prod_c sigmoid(-c(y) / eta) (fat = False) and (optionally) scale * d weight / d y added into dy
+__device__ __forceinline__ double feas_sigmoid(const ObjD& od, const double* y, double scale, double* dy) {
+  double sg[BO_MAX_CONSTRAINTS];
+  double w = 1.0;
+  for (int c = 0; c < od.n_cons; ++c) {
+    const double cv = od.con[c].sign * (y[od.con[c].out_idx] - od.con[c].tp);
+    sg[c] = 1.0 / (1.0 + exp(cv / od.con[c].eta));
+    w *= sg[c];
+  }
+  if (dy)
+    for (int c = 0; c < od.n_cons; ++c) {
+      double rest = 1.0;
+      for (int c2 = 0; c2 < od.n_cons; ++c2)
+        if (c2 != c) rest *= sg[c2];
+      dy[od.con[c].out_idx] += scale * rest * sg[c] * (1.0 - sg[c]) * (-od.con[c].sign / od.con[c].eta);
+    }
+  return w;
+}
+
 // d objective / d y[op.out_idx]  (utils/torch_tools.py:384-450; forward: objective_apply in common.cuh)
 __device__ __forceinline__ double objective_grad(const bo_objective_op& op, const double* y) {
   const double v = y[op.out_idx];

@@ -153,6 +153,29 @@ int bo_ehvi_prepare(bo_state* st, const double* Yobj_dev, int32_t n, int32_t S,
 int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
                      double best_f, void* stream);
 
+/* The single-objective MC acquisition functions SoboStrategy can select (data_models/acquisition_functions/
+ * acquisition_function.py:21-60, built through get_acquisition_function at sobo.py:64-89). */
+enum bo_scalar_acqf { BO_ACQF_QLOGEI = 0, BO_ACQF_QEI = 1, BO_ACQF_QSR = 2, BO_ACQF_QUCB = 3, BO_ACQF_QPI = 4 };
+
+/* General form of bo_logei_prepare: `variant` from bo_scalar_acqf, `param` = beta (qUCB) / tau (qPI); output
+ * constraints multiply the utility by prod sigmoid(-c/eta) (qEI, qPI) or add sum log fatmoid(-c/eta) (qLogEI).
+ * With n_b > 0 the NOISY variants are built (qNEI for BO_ACQF_QEI, qLogNEI for BO_ACQF_QLOGEI -- SoboStrategy's default,
+ * data_models/strategies/predictives/sobo.py:15-17): posterior root at the baseline Xb_dev [n_b, d] is cached, S
+ * baseline samples are drawn from zb_dev [S, n_b, M] and the incumbent becomes the best baseline objective of each MC
+ * sample; best_f is then ignored. */
+int bo_scalar_prepare(bo_state* st, int32_t variant, double param, int32_t S, int32_t combine, const bo_objective_op* obj,
+                      int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons, double best_f, const double* Xb_dev,
+                      int32_t n_b, const double* zb_dev, int32_t* info, void* stream);
+
+/* prune_inferior_points for the noisy single-objective variants: counts_dev[n] = number of joint posterior samples
+ * (base samples z_dev [S, n, M]) in which point i has the best scalarised objective. */
+int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S, int32_t combine,
+                           const bo_objective_op* obj, int32_t n_obj, int32_t* counts_dev, int32_t* info, void* stream);
+
+/* Named options of the prepared acquisition function: "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of
+ * qEHVI / qNEHVI -- MoboStrategy's default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2). */
+int bo_acqf_set_option(bo_state* st, const char* name, double value);
+
 /* AcquisitionFunction.forward(X[b, q, d]) -> [b]  (called from calc_acquisition botorch.py:223,
  * optimize_acqf's raw-sample screen, optimize_acqf_discrete botorch.py:461).  zq_dev [S, q, M] are the
  * base samples of the q new points.  info_dev[b] (may be NULL): 0, or 1 if the conditional

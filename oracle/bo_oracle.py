@@ -812,6 +812,191 @@ class QLogEIOracle:
 
 
 # ----------------------------------------------------------------------------------------
+# Log-space hypervolume improvement: qLogEHVI / qLogNEHVI ([UPSTREAM] botorch.acquisition.multi_objective.logei,
+# botorch.utils.safe_math; call site mobo.py:72-90 -- qLogNEHVI is MoboStrategy's default,
+# data_models/strategies/predictives/mobo.py).  PARITY UNPINNED: restated from the published algorithm
+# (Ament et al. 2023, "Unexpected Improvements to Expected Improvement", section 4 / appendix).
+# ----------------------------------------------------------------------------------------
+def log1mexp(x):
+    """log(1 - exp(x)) for x < 0."""
+    return torch.where(-math.log(2.0) < x, (-torch.expm1(x)).log(), torch.log1p(-torch.exp(x)))
+
+
+def logdiffexp(log_a, log_b):
+    """log(b - a) from log a and log b (b > a > 0)."""
+    is_inf = log_b.isinf() & log_a.isinf()
+    return log_b + log1mexp(log_a - log_b.masked_fill(is_inf, 0.0))
+
+
+def fatmin(x, dim, tau=1.0, alpha=FATMAX_ALPHA):
+    return -fatmax(-x, dim=dim, tau=tau, alpha=alpha)
+
+
+def fatminimum(a, b, tau):
+    """Smooth element-wise minimum; an infinite `b` (unbounded cell) returns `a` exactly."""
+    a, b = torch.broadcast_tensors(a, b)
+    inf = torch.isinf(b)
+    bf = torch.where(inf, a.detach(), b)
+    sm = fatmin(torch.stack([a, bf], dim=-1), dim=-1, tau=tau)
+    return torch.where(inf, a, sm)
+
+
+def fatmoid(x, tau=1.0):
+    """Twice differentiable step approximation with an O(1/x^2) tail."""
+    x = x / tau
+    m = 1.0 / math.sqrt(3.0)
+    cauchy = lambda t: 1.0 / (1.0 + t.square())  # noqa: E731
+    return torch.where(x < 0, (2.0 / 3.0) * cauchy(x - m), 1.0 - (2.0 / 3.0) * cauchy(x + m))
+
+
+def log_smoothed_feasibility(cons, Y):
+    """[UPSTREAM] compute_smoothed_feasibility_indicator(log=True, fat=True): sum_c log fatmoid(-c / eta)."""
+    w = torch.zeros(Y.shape[:-1], dtype=DT)
+    for (idx, sign, tp, eta), c in zip(cons, constraint_values(cons, Y)):
+        w = w + fatmoid(-c / eta).log()
+    return w
+
+
+def log_hvi_inclusion_exclusion(obj, lower, upper, n_cells, log_feas=None, tau_relu=TAU_RELU, tau_max=TAU_MAX):
+    """[UPSTREAM] qLogExpectedHypervolumeImprovement._compute_log_qehvi.
+    obj [S, b, q, m]; lower / upper [S|1, C, m]; n_cells [S|1] = valid cells per MC sample (the padding cells that make
+    the per-sample lists rectangular are ignored); log_feas [S, b, q] or None -> [b]."""
+    S, b, q, m = obj.shape
+    Sc, C = lower.shape[0], lower.shape[1]
+    lo = lower.view(Sc, 1, C, 1, m)
+    up = upper.view(Sc, 1, C, 1, m)
+    neg_inf = torch.full((S, b, C), -math.inf, dtype=DT)
+    acc = [neg_inf, neg_inf]  # even, odd
+    for i in range(1, q + 1):
+        comb = torch.tensor(list(itertools.combinations(range(q), i)), dtype=torch.long)
+        sub = obj[:, :, comb.view(-1), :].view(S, b, comb.shape[0], i, m)
+        vert = fatmin(sub, dim=-2, tau=tau_max)                    # [S, b, nC, m]
+        vert = fatminimum(vert.unsqueeze(-3), up, tau=tau_max)     # [S, b, C, nC, m]
+        ll = log_fatplus(vert - lo, tau=tau_relu).sum(dim=-1)      # [S, b, C, nC]
+        if log_feas is not None:
+            ll = ll + log_feas[:, :, comb.view(-1)].view(S, b, comb.shape[0], i).sum(dim=-1).unsqueeze(-2)
+        acc[i % 2] = torch.logaddexp(acc[i % 2], torch.logsumexp(ll, dim=-1))
+    cellv = logdiffexp(log_a=acc[0], log_b=acc[1])                 # [S, b, C]
+    valid = torch.arange(C).view(1, 1, C) < torch.as_tensor(n_cells).view(Sc, 1, 1)
+    cellv = torch.where(valid.expand(S, b, C), cellv, neg_inf)
+    return logmeanexp(torch.logsumexp(cellv, dim=-1), dim=0)
+
+
+class QLogNEHVIOracle(QNEHVIOracle):
+    """qLogNoisyExpectedHypervolumeImprovement: same construction as qNEHVI (pruning, cached root, per-sample
+    cells), log-space smoothed value."""
+
+    def forward(self, X, zq=None, return_parts=False):
+        X = torch.as_tensor(X, dtype=DT)
+        f, parts = self.sample_q(X, zq)
+        obj = multi_objective(self.ops, f)
+        lf = log_smoothed_feasibility(self.cons, f) if self.cons else None
+        val = log_hvi_inclusion_exclusion(obj, self.cell_lower, self.cell_upper, self.n_cells, lf)
+        if return_parts:
+            parts.update(samples=f, obj=obj)
+            return val, parts
+        return val
+
+
+class QLogEHVIOracle(QEHVIOracle):
+    def forward(self, X, zq=None):
+        X = torch.as_tensor(X, dtype=DT)
+        b, q, d = X.shape
+        gp = self.gp
+        if zq is None:
+            zq = base_samples_points_by_outputs(q, gp.M, self.S, self.seed)
+        fs = []
+        for i in range(b):
+            mean, cov = gp.posterior(X[i])
+            L = psd_safe_cholesky(cov)
+            fs.append(mean.unsqueeze(0) + torch.einsum("mij,sjm->sim", L, zq))
+        obj = multi_objective(self.ops, torch.stack(fs, dim=1))
+        return log_hvi_inclusion_exclusion(obj, self.cell_lower, self.cell_upper, [self.cell_lower.shape[1]])
+
+
+# ----------------------------------------------------------------------------------------
+# Single-objective MC acquisition functions of SoboStrategy (sobo.py:51-90 via get_acquisition_function):
+# qEI, qLogEI, qSR, qUCB, qPI (fixed best_f) and qNEI, qLogNEI (best value of the cached baseline samples, per MC
+# sample).  [UPSTREAM] botorch.acquisition.monte_carlo / logei -- PARITY UNPINNED.
+# ----------------------------------------------------------------------------------------
+class QScalarOracle(QNEHVIOracle):
+    def __init__(self, gp, kind, objective_spec, X_observed, mc_samples=512, seed=1234, beta=0.2, tau=1e-3,
+                 prune_baseline=True, prune_samples=2048, prune_seed=4321, X_pending=None, constraints=None,
+                 best_f=None):
+        self.gp, self.kind, self.spec, self.S, self.seed = gp, kind, objective_spec, mc_samples, seed
+        self.beta, self.tau, self.cons = beta, tau, constraints
+        self.noisy = kind in ("qNEI", "qLogNEI")
+        Xo = torch.as_tensor(X_observed, dtype=DT)
+        self.zb = None
+        if self.noisy:
+            self.prune_idx = None
+            if prune_baseline:
+                self.prune_idx = self.prune_so(Xo, prune_samples, prune_seed)
+                Xo = Xo[self.prune_idx]
+            if X_pending is not None:
+                Xo = torch.cat([Xo, torch.as_tensor(X_pending, dtype=DT)], dim=0)
+            self.Xb, self.nb = Xo, Xo.shape[0]
+            M = gp.M
+            self.zb = base_samples_points_by_outputs(self.nb, M, self.S, seed)
+            mean, cov = gp.posterior(self.Xb)
+            self.baseline_L = psd_safe_cholesky(cov)
+            fb = mean.unsqueeze(0) + torch.einsum("mij,sjm->sim", self.baseline_L, self.zb)
+            self.samples_b = fb
+            self.best_f_s = scalar_objective(self.spec, fb).max(dim=-1).values  # [S]
+        else:
+            self.Xb, self.nb = torch.zeros(0, gp.d, dtype=DT), 0
+            self.baseline_L = torch.zeros(gp.M, 0, 0, dtype=DT)
+            self.zb = torch.zeros(self.S, 0, gp.M, dtype=DT)
+            if best_f is None:
+                mean, _ = gp.posterior(Xo)
+                best_f = float(scalar_objective(objective_spec, mean).max())
+            self.best_f = best_f
+
+    def prune_so(self, X, num_samples, seed):
+        """[UPSTREAM] prune_inferior_points: keep the points that are the best one in at least one joint sample."""
+        mean, cov = self.gp.posterior(X)
+        n, M = mean.shape
+        z = base_samples_points_by_outputs(n, M, num_samples, seed)
+        L = psd_safe_cholesky(cov)
+        samples = mean.unsqueeze(0) + torch.einsum("mij,sjm->sim", L, z)
+        obj = scalar_objective(self.spec, samples)
+        best = obj.argmax(dim=-1)
+        return torch.unique(best)
+
+    def base_samples_q(self, q):
+        z = base_samples_points_by_outputs(self.nb + q, self.gp.M, self.S, self.seed)
+        return z[:, self.nb:, :].contiguous()
+
+    def forward(self, X, zq=None):
+        X = torch.as_tensor(X, dtype=DT)
+        f, _ = self.sample_q(X, zq)
+        obj = scalar_objective(self.spec, f)  # [S, b, q]
+        bf = self.best_f_s.view(-1, 1, 1) if self.noisy else self.best_f
+        k = self.kind
+        if k in ("qLogEI", "qLogNEI"):
+            li = log_fatplus(obj - bf, tau=TAU_RELU)
+            if self.cons:
+                li = li + log_smoothed_feasibility(self.cons, f)
+            return logmeanexp(fatmax(li, dim=-1, tau=TAU_MAX), dim=0)
+        if k in ("qEI", "qNEI"):
+            u = (obj - bf).clamp_min(0.0)
+        elif k == "qSR":
+            u = obj
+        elif k == "qPI":
+            u = torch.sigmoid((obj - bf) / self.tau)
+        elif k == "qUCB":
+            mean = obj.mean(dim=0)
+            u = mean + math.sqrt(self.beta * math.pi / 2.0) * (obj - mean).abs()
+        else:
+            raise ValueError(k)
+        if self.cons:
+            if k in ("qSR", "qUCB"):
+                raise ValueError("constraints need a non-negative utility")
+            u = u * smoothed_feasibility(self.cons, f)
+        return u.max(dim=-1).values.mean(dim=0)
+
+
+# ----------------------------------------------------------------------------------------
 # Test functions used as input generators for the BASELINE configs
 # ----------------------------------------------------------------------------------------
 def zdt1(X):
