@@ -116,7 +116,7 @@ def run_reference(args):
     t_setup = time.perf_counter()
     acq = cpu_reference_setup(p)
     t_setup = time.perf_counter() - t_setup
-    n = args.cpu_sample or (256 if p["acqf"] == "qnehvi" else 1024)
+    n = args.cpu_sample or (1024 if p["acqf"] == "qnehvi" else 2048)  # ~1.5 s of CPU work per step
     X = Cf.candidates(p, max(n, 8))[:n]
     for _ in range(max(args.warmup, 1)):
         cpu_time_forward(acq, X[: max(8, n // 4)], 8)
@@ -356,7 +356,7 @@ def run_b200(args):
                 up[pad] = ref
                 cells = (lo, up)
             acq_cpu = cpu_reference_setup(p, baseline_idx=idx, cell_bounds=cells)
-            n = args.cpu_sample or ((256 if cells is None else 16) if p["acqf"] == "qnehvi" else 1024)
+            n = args.cpu_sample or ((2048 if cells is None else 16) if p["acqf"] == "qnehvi" else 4096)  # ~10 s of CPU work
             Xc = X_host[:n]
             cpu_time_forward(acq_cpu, Xc[:8], 8)
             v8, dt8 = cpu_time_forward(acq_cpu, Xc, 8)
