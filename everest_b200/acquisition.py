@@ -33,6 +33,22 @@ class _DeviceAcquisition:
         self._zq = {}
         self.nb = 0
         self.last_info = None
+        self.X_pending = None
+
+    # [UPSTREAM] botorch's @concatenate_pending_points: acquisition functions without a cached baseline score the joint
+    # batch cat(X, X_pending); the NEHVI family overrides set_X_pending and folds the points into its baseline instead
+    _PENDING_CONCAT = True
+
+    def set_X_pending(self, X_pending=None):
+        if X_pending is None:
+            self.X_pending = None
+        else:
+            self.X_pending = torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, self.model.d).to(self.model.device)
+
+    def _with_pending(self, Xd):
+        if self._PENDING_CONCAT and self.X_pending is not None and self.X_pending.shape[0] > 0:
+            return torch.cat([Xd, self.X_pending.unsqueeze(0).expand(Xd.shape[0], -1, -1)], dim=1).contiguous()
+        return Xd
 
     def _claim(self):
         """The handle holds ONE prepared acquisition function: remember which object prepared it last."""
@@ -69,7 +85,7 @@ class _DeviceAcquisition:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
         self._check_active()
         on_cpu = X.device.type == "cpu"
-        Xd = X.to(self.model.device).contiguous()
+        Xd = self._with_pending(X.to(self.model.device).contiguous())
         b, q, _ = Xd.shape
         out = torch.empty(b, dtype=torch.double, device=self.model.device)
         info = torch.zeros(b, dtype=torch.int32, device=self.model.device)
@@ -97,7 +113,8 @@ class _DeviceAcquisition:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
         self._check_active()
         on_cpu = X.device.type == "cpu"
-        Xd = X.detach().to(self.model.device).contiguous()
+        q_in = X.shape[1]
+        Xd = self._with_pending(X.detach().to(self.model.device).contiguous())
         b, q, _ = Xd.shape
         out = torch.empty(b, dtype=torch.double, device=self.model.device)
         dX = torch.empty_like(Xd)
@@ -107,6 +124,8 @@ class _DeviceAcquisition:
             L.check(self.model.lib.bo_acqf_forward_backward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq),
                                                             _dev_ptr(out), _dev_ptr(dX), _dev_ptr(info), _stream()))
         self.last_info = info
+        if q != q_in:
+            dX = dX[:, :q_in].contiguous()   # the pending points are constants
         return (out.cpu(), dX.cpu()) if on_cpu else (out, dX)
 
     def forward_host(self, X: np.ndarray) -> np.ndarray:
@@ -118,6 +137,10 @@ class _DeviceAcquisition:
         if d != self.model.d:
             raise ValueError(f"X must be [b, q, {self.model.d}]")
         self._check_active()
+        if self._PENDING_CONCAT and self.X_pending is not None and self.X_pending.shape[0] > 0:
+            P = np.broadcast_to(self.X_pending.cpu().numpy()[None], (b, self.X_pending.shape[0], d))
+            X = np.ascontiguousarray(np.concatenate([X, P], axis=1))
+            q = X.shape[1]
         out = np.empty(b, dtype=np.float64)
         zq = self.base_samples_q(q)
         with torch.cuda.device(self.model.device):
@@ -173,10 +196,21 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
         if prune_baseline and Xb.shape[0] > 0:
             self.prune_idx = self._prune(Xb, prune_samples)
             Xb = Xb[self.prune_idx.cpu()]
+        self._Xb_pruned = Xb
+        self.X_pending = None if X_pending is None else torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d)
+        self._prepare(self.X_pending, base_samples_baseline)
+
+    _PENDING_CONCAT = False
+
+    def _prepare(self, X_pending=None, base_samples_baseline=None):
+        """NoisyExpectedHypervolumeMixin._set_cell_bounds: baseline = pruned observations + pending points."""
+        model = self.model
+        Xb = self._Xb_pruned
         if X_pending is not None:
-            Xb = torch.cat([Xb, torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d)], dim=0)
+            Xb = torch.cat([Xb, torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d).cpu()], dim=0)
         self.X_baseline = Xb
         self.nb = Xb.shape[0]
+        self._zq = {}
         zb = base_samples_baseline
         if zb is None:
             zb = sampling.base_samples(self.nb, model.M, self.S, self.seed)
@@ -193,6 +227,16 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
                                                _stream()))
         self.max_cells = int(maxc.value)
         self._claim()
+        self._after_prepare()
+
+    def _after_prepare(self):
+        pass
+
+    def set_X_pending(self, X_pending=None):
+        """[UPSTREAM] qNEHVI.set_X_pending with cache_pending=True: the pending points join the baseline and the
+        per-sample box decompositions are rebuilt (no new pruning)."""
+        self.X_pending = None if X_pending is None else torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, self.model.d)
+        self._prepare(self.X_pending)
 
     def _prune(self, Xb, prune_samples, seed_offset=7919):
         """[UPSTREAM] prune_inferior_points_multi_objective: keep points with non-zero probability of being
@@ -233,8 +277,7 @@ class qExpectedHypervolumeImprovement(_DeviceAcquisition):
     def __init__(self, model: DeviceGPState, ref_point, partitioning_Y, objective: MultiObjective, mc_samples: int = 512,
                  seed: Optional[int] = None, X_pending=None):
         super().__init__(model, mc_samples, seed)
-        if X_pending is not None:
-            raise NotImplementedError("X_pending with qEHVI is not accelerated; use qNEHVI")
+        self.set_X_pending(X_pending)
         self.ref_point = [float(v) for v in ref_point]
         self.objective = objective
         Y = torch.as_tensor(partitioning_Y, dtype=torch.double).reshape(-1, len(self.ref_point)).to(model.device).contiguous()
@@ -253,10 +296,13 @@ class qLogNoisyExpectedHypervolumeImprovement(qNoisyExpectedHypervolumeImproveme
     log-space smoothed value ([UPSTREAM] _compute_log_qehvi; tau_relu = 1e-6, tau_max = 1e-2, fat = True)."""
 
     def __init__(self, *args, tau_relu: float = 1e-6, tau_max: float = 1e-2, **kwargs):
+        self._taus = (float(tau_relu), float(tau_max))
         super().__init__(*args, **kwargs)
+
+    def _after_prepare(self):
         self.set_option("log_hvi", 1)
-        self.set_option("tau_relu", tau_relu)
-        self.set_option("tau_max", tau_max)
+        self.set_option("tau_relu", self._taus[0])
+        self.set_option("tau_max", self._taus[1])
 
 
 class qLogExpectedHypervolumeImprovement(qExpectedHypervolumeImprovement):
@@ -299,8 +345,6 @@ class _ScalarAcquisition(_DeviceAcquisition):
             if prune_baseline and Xb.shape[0] > 0:
                 self.prune_idx = self._prune(Xb, prune_samples)
                 Xb = Xb[self.prune_idx.cpu()]
-            if X_pending is not None:
-                Xb = torch.cat([Xb, torch.as_tensor(X_pending, dtype=torch.double).reshape(-1, model.d)], dim=0)
             if Xb.shape[0] == 0:
                 raise ValueError("the noisy variants need at least one baseline point")
             self.X_baseline = Xb
@@ -310,11 +354,10 @@ class _ScalarAcquisition(_DeviceAcquisition):
             Xbd = Xb.to(model.device).contiguous()
             self.best_f = float("nan")
         else:
-            if X_pending is not None:
-                raise NotImplementedError("X_pending needs the noisy variants (qNEI / qLogNEI) on the accelerated path")
             if best_f is None:
                 raise ValueError("best_f is required")
             self.best_f = float(best_f)
+        self.set_X_pending(X_pending)    # scored jointly with X ([UPSTREAM] @concatenate_pending_points)
         info = (C.c_int32 * model.M)()
         with torch.cuda.device(model.device):
             L.check(model.lib.bo_scalar_prepare(model.handle, self._VARIANT, self.param, self.S, objective.combine_code,

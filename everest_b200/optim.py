@@ -343,24 +343,43 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
     return X_ic.cpu(), Y_ic
 
 
+def _pending_base(acq_function):
+    Xp = getattr(acq_function, "X_pending", None)
+    return None if Xp is None else torch.as_tensor(Xp, dtype=torch.double).cpu().reshape(-1, acq_function.model.d)
+
+
 def optimize_acqf_mixed(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                         fixed_features_list, options: Optional[dict] = None, seed: Optional[int] = None,
                         refine: bool = True, **unsupported):
     """[UPSTREAM] botorch.optim.optimize_acqf_mixed as BoFire calls it for categorical combinations
-    (botorch.py:358-378), q == 1: one optimize_acqf per fixed-feature dictionary, best value wins.
-    (For q > 1 BoTorch adds points sequentially with X_pending updates; that needs an acqf rebuild per pick
-    and is not accelerated.)"""
+    (botorch.py:358-378): for each of the q points in turn, one optimize_acqf(q=1) per fixed-feature dictionary, the
+    best value wins, and the chosen point becomes pending (set_X_pending) for the next one.  Returns
+    (candidates [q, d], joint acquisition value of the final batch)."""
     if not fixed_features_list:
         raise ValueError("fixed_features_list must be non-empty.")
-    if q != 1:
-        raise NotImplementedError("optimize_acqf_mixed with q > 1 (sequential X_pending updates) is not accelerated")
-    best_c, best_v = None, None
-    for ff in fixed_features_list:
-        c, v = optimize_acqf(acq_function, bounds, q, num_restarts, raw_samples, fixed_features=ff, options=options,
-                             seed=seed, refine=refine, **unsupported)
-        if best_v is None or float(v) > float(best_v):
-            best_c, best_v = c, v
-    return best_c, best_v
+    base_pending = _pending_base(acq_function)
+    chosen = []
+    best_v = None
+    try:
+        for _ in range(q):
+            best_c, best_v = None, None
+            for ff in fixed_features_list:
+                c, v = optimize_acqf(acq_function, bounds, 1, num_restarts, raw_samples, fixed_features=ff, options=options,
+                                     seed=seed, refine=refine, **unsupported)
+                if best_v is None or float(v) > float(best_v):
+                    best_c, best_v = c, v
+            chosen.append(best_c.reshape(1, -1))
+            if q > 1:
+                pend = torch.cat(([base_pending] if base_pending is not None else []) + chosen, dim=0)
+                acq_function.set_X_pending(pend)
+    finally:
+        if q > 1:
+            acq_function.set_X_pending(base_pending)
+    cands = torch.cat(chosen, dim=0)
+    if q > 1:
+        with torch.no_grad():
+            best_v = acq_function(cands.unsqueeze(0).to(acq_function.model.device)).cpu()[0]
+    return cands, best_v
 
 
 def calc_acquisition(acq_function, candidates, combined: bool = False):
@@ -374,12 +393,33 @@ def calc_acquisition(acq_function, candidates, combined: bool = False):
 
 
 def optimize_acqf_discrete(acq_function, q: int, choices: torch.Tensor, max_batch_size: int = 1 << 20, unique: bool = True):
-    """[UPSTREAM] optimize_acqf_discrete as used by the all-categorical branch (botorch.py:425-467):
-    sequential greedy selection over a discrete choice set, forward-only."""
-    if q != 1:
-        raise NotImplementedError("sequential greedy q > 1 needs X_pending updates (set-up cost per pick); q == 1 is accelerated")
+    """[UPSTREAM] optimize_acqf_discrete as used by the all-categorical branch (botorch.py:425-467): sequential greedy
+    selection over a discrete choice set, forward-only; after each pick the point becomes pending and (unique=True)
+    leaves the choice set.  Returns (candidates [q, d], values [q] of the sequential picks; a scalar for q == 1)."""
     choices = torch.as_tensor(choices, dtype=torch.double)
-    with torch.no_grad():
-        vals = acq_function(choices.unsqueeze(-2).to(acq_function.model.device)).cpu()
-    best = int(torch.argmax(vals))
-    return choices[best].unsqueeze(0), vals[best]
+    if choices.dim() != 2 or choices.shape[0] == 0:
+        raise ValueError("`choices` must be a non-empty [n, d] tensor.")
+    if unique and q > choices.shape[0]:
+        raise ValueError(f"Requested {q} unique candidates from a choice set of {choices.shape[0]}.")
+    base_pending = _pending_base(acq_function)
+    picked, vals = [], []
+    remaining = choices
+    try:
+        for _ in range(q):
+            with torch.no_grad():
+                v = torch.cat([acq_function(remaining[i:i + max_batch_size].unsqueeze(-2).to(acq_function.model.device)).cpu()
+                               for i in range(0, remaining.shape[0], max_batch_size)])
+            best = int(torch.argmax(v))
+            picked.append(remaining[best].unsqueeze(0))
+            vals.append(v[best])
+            if q > 1:
+                pend = torch.cat(([base_pending] if base_pending is not None else []) + picked, dim=0)
+                acq_function.set_X_pending(pend)
+                if unique:
+                    remaining = torch.cat([remaining[:best], remaining[best + 1:]], dim=0)
+    finally:
+        if q > 1:
+            acq_function.set_X_pending(base_pending)
+    if q == 1:
+        return picked[0], vals[0]
+    return torch.cat(picked, dim=0), torch.stack(vals)

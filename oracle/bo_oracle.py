@@ -925,6 +925,8 @@ class QScalarOracle(QNEHVIOracle):
                  best_f=None):
         self.gp, self.kind, self.spec, self.S, self.seed = gp, kind, objective_spec, mc_samples, seed
         self.beta, self.tau, self.cons = beta, tau, constraints
+        # [UPSTREAM] @concatenate_pending_points: pending points are scored jointly with X (also for qNEI / qLogNEI)
+        self.X_pending = None if X_pending is None else torch.as_tensor(X_pending, dtype=DT).reshape(-1, gp.d)
         self.noisy = kind in ("qNEI", "qLogNEI")
         Xo = torch.as_tensor(X_observed, dtype=DT)
         self.zb = None
@@ -933,8 +935,6 @@ class QScalarOracle(QNEHVIOracle):
             if prune_baseline:
                 self.prune_idx = self.prune_so(Xo, prune_samples, prune_seed)
                 Xo = Xo[self.prune_idx]
-            if X_pending is not None:
-                Xo = torch.cat([Xo, torch.as_tensor(X_pending, dtype=DT)], dim=0)
             self.Xb, self.nb = Xo, Xo.shape[0]
             M = gp.M
             self.zb = base_samples_points_by_outputs(self.nb, M, self.S, seed)
@@ -969,6 +969,8 @@ class QScalarOracle(QNEHVIOracle):
 
     def forward(self, X, zq=None):
         X = torch.as_tensor(X, dtype=DT)
+        if self.X_pending is not None:
+            X = torch.cat([X, self.X_pending.unsqueeze(0).expand(X.shape[0], -1, -1)], dim=1)
         f, _ = self.sample_q(X, zq)
         obj = scalar_objective(self.spec, f)  # [S, b, q]
         bf = self.best_f_s.view(-1, 1, 1) if self.noisy else self.best_f

@@ -294,3 +294,25 @@ def test_bofire_data_model_adapter():
     mo, cons = BA.objectives_from_outputs(outs)
     assert [(o.kind, o.idx, o.p0, o.p1) for o in mo.ops] == [("max", 0, 0.0, 2.0), ("min", 2, 0.0, 1.0)]
     assert [(c.idx, c.sign, c.tp, c.eta) for c in cons] == [(1, -1.0, 1.5, 0.25)]
+
+
+def test_strategy_host_logic_input_space_and_duplicates():
+    """Host pieces of the strategy mirror (everest_b200/strategy.py <-> botorch.py:226-296, 408-467, 696-724)."""
+    from everest_b200.strategy import InputSpace, drop_duplicate_rows
+
+    # 2 continuous + one-hot(3) + one-hot(2)
+    sp = InputSpace(bounds=np.array([[0.0] * 7, [1.0] * 7]), categorical_groups={2: 3, 5: 2}, fixed_features={1: 0.5},
+                    allowed_categories={2: [0, 2]})
+    assert sp.d == 7 and not sp.is_fully_combinatorial()
+    combos = sp.categorical_combinations()
+    assert len(combos) == 2 * 2
+    for ff in combos:
+        assert ff[1] == 0.5 and sum(ff[c] for c in (2, 3, 4)) == 1.0 and sum(ff[c] for c in (5, 6)) == 1.0 and ff[3] == 0.0
+    spc = InputSpace(bounds=np.array([[0.0] * 4, [1.0, 1.0, 1.0, 3.0]]), categorical_groups={0: 3}, discrete_values={3: [1.0, 2.0, 3.0]})
+    assert spc.is_fully_combinatorial() and len(spc.categorical_combinations()) == 9
+    X = np.array([[0.1, 0.2], [0.3, 0.4], [0.1, 0.2], [0.5, 0.6], [0.3, 0.4]])
+    Y = np.arange(5.0)[:, None]
+    Xd, Yd = drop_duplicate_rows(X, Y)           # keep="first", original order
+    assert Xd.tolist() == [[0.1, 0.2], [0.3, 0.4], [0.5, 0.6]] and Yd[:, 0].tolist() == [0.0, 1.0, 3.0]
+    with pytest.raises(ValueError):
+        InputSpace(bounds=np.zeros(3))
