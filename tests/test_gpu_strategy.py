@@ -119,8 +119,11 @@ def test_x_pending_is_scored_jointly_like_the_oracle(name):
     p = Cf.zdt1_qnehvi(N=60, S=32, raw=6, d=4, q=2)
     gp = P.oracle_gp(p)
     st = Cf.build_state(p)
-    Xp = Cf.candidates(p, 3)[2, :1]                       # one pending point
-    X = Cf.candidates(p, 2)
+    # candidates and the pending point around the incumbent so that the improvement is not identically zero
+    g_ = torch.Generator().manual_seed(0)
+    best = torch.as_tensor(p["X"][int(torch.as_tensor(p["Y"])[:, 1].argmin())], dtype=DT)
+    pts = (best.view(1, 1, -1) + 0.15 * torch.randn(3, 2, p["d"], dtype=DT, generator=g_)).clamp(0.0, 1.0)
+    X, Xp = pts[:2].contiguous(), pts[2, :1].contiguous()
     if name == "qEHVI":
         Yobj = -torch.as_tensor(p["Y"], dtype=DT)
         ops = [P.op_to_oracle(o) for o in p["objective"].ops]
