@@ -328,10 +328,11 @@ def run_b200(args):
         peak = measure_fp64_peak(device)
         # DRAM bytes of one launch from the committed ncu --set full capture (profiles/r01_ncu_summary.txt); only valid
         # for the default headline workload, null otherwise
-        traffic = 1.623e10 if (args.workload == "zdt1" and not args.raw_samples) else None
+        traffic = 2.349e9 if (args.workload == "zdt1" and not args.raw_samples) else None  # profiles/r01_s2_ncu_gemm_dram_groups8.csv
         roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full)",
+                    "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu, profiles/r01_s2_ncu_gemm_dram_groups8.csv; "
+                                    "16.2 GB before the L2-sharing column groups, algorithmic 2.2 GB)",
                     "peak_source": "torch.matmul f64 8192^3 (cuBLAS DGEMM) best of 5 measured in this run; "
                                    "MEASURED_PEAKS.json holds no fp64 figure; tools/fp64_peak measured 37.0 TFLOP/s "
                                    "for raw DMMA and DFMA issue on this pool",

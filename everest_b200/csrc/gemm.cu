@@ -323,6 +323,7 @@ struct alignas(128) P2Item {
 struct P2Batch {
   P2Item item[P2_MAXOUT];
   int n_groups;
+  int interleave;  // 1: blockIdx.x = row_block * n_groups + group (CTAs sharing a K(X*,X) panel run together -> L2 hits)
   int gbeg[P2_MAXGROUPS + 1];
   double* gqq_part[P2_MAXOUT];
   long long gqq_stride;
@@ -366,7 +367,9 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   const int wm0 = (warp & 1) * 64, wn0 = wc * 32;
   const int rho_g = (g >> 1) | ((g & 1) << 2);
   const int q = a.q, N = a.N, rows = a.rows;
-  const int row0 = blockIdx.x * PG_BM;
+  const int grp = batch.interleave ? (int)(blockIdx.x % batch.n_groups) : (int)blockIdx.z;
+  const int row_block = batch.interleave ? (int)(blockIdx.x / batch.n_groups) : (int)blockIdx.x;
+  const int row0 = row_block * PG_BM;
 
   if (tid == 0) {
     for (int s = 0; s < P2_ST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 8); }
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
   }
   __syncthreads();
 
-  const int jb_begin = batch.gbeg[blockIdx.z], n_blocks = batch.gbeg[blockIdx.z + 1];  // this CTA's column blocks
+  const int jb_begin = batch.gbeg[grp], n_blocks = batch.gbeg[grp + 1];  // this CTA's column blocks
   const int kfull = a.ldk;
   auto nk_of = [&](int jb) {
     int kmax = ((jb + 1) * PG_BN > N) ? kfull : (jb + 1) * PG_BN;
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(256, 1) posterior_gemm_tma_kernel(const __grid
     s += Gs[(1 * 128 + r) * 8 + slot8];
     s += Gs[(2 * 128 + r) * 8 + slot8];
     s += Gs[(3 * 128 + r) * 8 + slot8];
-    double* dst = (batch.n_groups > 1) ? (batch.gqq_part[blockIdx.y] + (size_t)blockIdx.z * batch.gqq_stride) : a.Gqq;
+    double* dst = (batch.n_groups > 1) ? (batch.gqq_part[blockIdx.y] + (size_t)grp * batch.gqq_stride) : a.Gqq;
     dst[((size_t)(row0 + r) / q * q + a1) * q + a2] = s;
   }
 }
@@ -557,8 +560,6 @@ static bool use_v2(const PostGemmArgs& a) {
 
 // All outputs of one forward in as few launches as possible (v2: up to 8 outputs per launch).
 size_t posterior_gemm_partial_ws_doubles(int rows, int q, int n_out) {
-  const int row_blocks = (rows + PG_BM - 1) / PG_BM;
-  if (row_blocks * n_out >= 4 * 148) return 0;
   return (size_t)n_out * P2_MAXGROUPS * rows * q;
 }
 
@@ -581,7 +582,7 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const int row_blocks = (args[0].rows + PG_BM - 1) / PG_BM;
     const int n_blocks_total = args[0].Rpad / PG_BN;
-    int groups = 1;
+    int groups = 1, interleave = 0;
     {
       // fewer than ~4 waves of CTAs: pick the group count that wastes the least of the last wave,
       // cost(G) = ceil(ctas * G / n_sm) / G  (in units of one full-length CTA)
@@ -593,6 +594,18 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
           double cost = (double)((ctas * G + n_sm - 1) / n_sm) / (double)G;
           if (cost < best * 0.98) { best = cost; groups = G; }
         }
+      } else if (part_ws) {
+        // many q-batches: a CTA re-reads its 128-row K(X*,X) panel once per column block.  Splitting the column blocks
+        // over G CTAs that are scheduled next to each other keeps the panels of all resident CTAs (n_sm / G panels) in L2,
+        // so that the re-reads stop going to HBM.  Target: resident panels <= ~40 MB (L2 also holds the 34 MB factor).
+        static int forced = -2;
+        if (forced == -2) { const char* e = getenv("EVEREST_GEMM_GROUPS"); forced = e ? atoi(e) : -1; }
+        const double panel_mb = (double)PG_BM * args[0].ldk * 8.0 / (1 << 20);
+        int G = (int)((n_sm * panel_mb + 39.0) / 40.0);
+        if (forced >= 1) G = forced;
+        if (G > n_blocks_total) G = n_blocks_total;
+        if (G > P2_MAXGROUPS) G = P2_MAXGROUPS;
+        if (G > 1) { groups = G; interleave = 1; }
       }
     }
     for (int m0 = 0; m0 < n_out; m0 += P2_MAXOUT) {
@@ -600,6 +613,7 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
       P2Batch batch;
       memset(&batch, 0, sizeof(batch));
       batch.n_groups = groups;
+      batch.interleave = interleave;
       {
         // contiguous groups of similar work; work of block jb = its number of k stages
         const PostGemmArgs& a0 = args[m0];
@@ -627,6 +641,7 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
         batch.item[i].a = a;
       }
       dim3 grid((args[m0].rows + PG_BM - 1) / PG_BM, cnt, groups);
+      if (interleave) grid = dim3(((args[m0].rows + PG_BM - 1) / PG_BM) * groups, cnt, 1);
       posterior_gemm_tma_kernel<<<grid, PG_THREADS, smem, s>>>(batch);
       if (lc) lc->n++;
       if (groups > 1) {
