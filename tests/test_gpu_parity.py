@@ -435,9 +435,12 @@ def test_optimize_acqf_screen_refine_and_fd_gradient():
     # mixed branch (botorch.py:358-378): best over a list of fixed-feature dictionaries, q = 1
     p1m = Cf.zdt1_qnehvi(N=64, S=32, raw=64, d=4, q=1)
     acq1m = Cf.build_acqf(p1m, Cf.build_state(p1m), prune_samples=128)
+    # initialize_q_batch draws the restarts from torch's GLOBAL generator (like BoTorch): same state for both runs
+    torch.manual_seed(11)
     cm, vm = optim.optimize_acqf_mixed(acq1m, bounds, q=1, num_restarts=2, raw_samples=32,
                                        fixed_features_list=[{0: 0.1}, {0: 0.9}], options={"maxiter": 10}, seed=1)
     assert cm.shape == (1, 4) and float(cm[0, 0]) in (0.1, 0.9)
+    torch.manual_seed(11)
     singles = [optim.optimize_acqf(acq1m, bounds, 1, 2, 32, fixed_features=ff, options={"maxiter": 10}, seed=1)[1] for ff in ({0: 0.1}, {0: 0.9})]
     assert float(vm) == max(float(s_) for s_ in singles)
     vals_rows = optim.calc_acquisition(acq1m, X_rnd[:5, 0, :])
