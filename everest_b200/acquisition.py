@@ -67,8 +67,8 @@ class _DeviceAcquisition:
         """[S, q, M] base samples of the new points: the last q points of a fresh (n_b + q)-point Sobol
         draw with the sampler's seed ([UPSTREAM] NormalMCSampler._update_base_samples)."""
         if q not in self._zq:
-            z = sampling.base_samples(self.nb + q, self.model.M, self.S, self.seed)
-            self._zq[q] = z[:, self.nb:, :].contiguous().to(self.model.device)
+            z = sampling.base_samples_device(self.nb + q, self.model.M, self.S, self.seed, self.model.device)
+            self._zq[q] = z[:, self.nb:, :].contiguous()
         return self._zq[q]
 
     def set_base_samples_q(self, q: int, zq):
@@ -213,7 +213,7 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
         self._zq = {}
         zb = base_samples_baseline
         if zb is None:
-            zb = sampling.base_samples(self.nb, model.M, self.S, self.seed)
+            zb = sampling.base_samples_device(self.nb, model.M, self.S, self.seed, model.device)
         zb = torch.as_tensor(zb, dtype=torch.double).to(model.device).contiguous()
         if tuple(zb.shape) != (self.S, self.nb, model.M):
             raise ValueError(f"base_samples_baseline must be [{self.S}, {self.nb}, {model.M}]")
@@ -243,7 +243,7 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
         non-dominated and better than the reference point under `prune_samples` joint posterior samples."""
         model = self.model
         n = Xb.shape[0]
-        z = sampling.base_samples(n, model.M, prune_samples, self.seed + seed_offset).to(model.device).contiguous()
+        z = sampling.base_samples_device(n, model.M, prune_samples, self.seed + seed_offset, model.device)
         self._z_prune = z
         counts = torch.zeros(n, dtype=torch.int32, device=model.device)
         info = (C.c_int32 * model.M)()
@@ -349,7 +349,7 @@ class _ScalarAcquisition(_DeviceAcquisition):
                 raise ValueError("the noisy variants need at least one baseline point")
             self.X_baseline = Xb
             self.nb = Xb.shape[0]
-            zb = sampling.base_samples(self.nb, model.M, self.S, self.seed).to(model.device).contiguous()
+            zb = sampling.base_samples_device(self.nb, model.M, self.S, self.seed, model.device)
             self._zb = zb
             Xbd = Xb.to(model.device).contiguous()
             self.best_f = float("nan")
@@ -371,7 +371,7 @@ class _ScalarAcquisition(_DeviceAcquisition):
         """[UPSTREAM] prune_inferior_points: keep the points that are the best one in at least one joint sample."""
         model = self.model
         n = Xb.shape[0]
-        z = sampling.base_samples(n, model.M, prune_samples, self.seed + seed_offset).to(model.device).contiguous()
+        z = sampling.base_samples_device(n, model.M, prune_samples, self.seed + seed_offset, model.device)
         counts = torch.zeros(n, dtype=torch.int32, device=model.device)
         info = (C.c_int32 * model.M)()
         Xd = Xb.to(model.device).contiguous()

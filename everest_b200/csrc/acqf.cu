@@ -1015,6 +1015,14 @@ __global__ void mc_reduce_partials_kernel(const double* __restrict__ partial, in
   }
 }
 
+int launch_mc_reduce_partials(const double* partial, int groups, int b, int S, double* out, const int* info_in, int M,
+                              int* info_out, cudaStream_t st, LaunchCounter* lc) {
+  mc_reduce_partials_kernel<<<(b + 255) / 256, 256, 0, st>>>(partial, groups, b, S, out, info_in, M, info_out);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 // EVEREST_MC_PATH = tiled | chunked | generic forces one of the three HVI kernels (tests); default: automatic
 static int mc_forced_path() {
   const char* e = getenv("EVEREST_MC_PATH");

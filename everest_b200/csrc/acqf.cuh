@@ -81,6 +81,8 @@ int launch_hypervolume_from_cells(const double* obj, const unsigned char* front,
 
 // ---- grad.cu: analytic adjoint d acqf / d X (the backward of forward(X[b, q, d])) ----------
 // MC value + d value / d f for every MC sample: dF[m * df_stride + (batch * q + j) * S + s]
+int launch_mc_reduce_partials(const double* partial, int groups, int b, int S, double* out, const int* info_in, int M,
+                              int* info_out, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
@@ -114,6 +116,7 @@ struct KernelGradArgs {
   const double* EW;     // [rows, ldw]
   int ldw;
   const double* Emu;    // [rows]
+  const double* Kx;     // [rows, ldk] forward K(X*, X) (fast path of single-leaf RBF models: dK/dstat = -K/2)
   double* dX;           // [rows, d]
   int accumulate;       // 0: overwrite dX, 1: add (outputs after the first)
 };

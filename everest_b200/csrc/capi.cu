@@ -805,13 +805,19 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
-    {
+    const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
+    if (small_rows) {
+      RC(st->wsV.ensure(posterior_small_ws_doubles(rows, st->out[0].Rpad, M) * 8));
+      rec_begin(st, "posterior_gemm", s);
+      RC(launch_posterior_small(pg.data(), M, st->wsV.as<double>(), s, &st->lc));
+      rec_end(st, s);
+    } else {
       size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
       if (pw) RC(st->wsGramPart.ensure(pw * 8));
+      rec_begin(st, "posterior_gemm", s);
+      RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+      rec_end(st, s);
     }
-    rec_begin(st, "posterior_gemm", s);
-    RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
-    rec_end(st, s);
     for (int m = 0; m < M; ++m) {
       OutputH& o = st->out[m];
       CondRootArgs c;
@@ -871,14 +877,19 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         RC(launch_cond_root_bwd(cb, s, &st->lc));
         rec_end(st, s);
         rec_begin(st, "u_gemm", s);
-        RC(launch_gemm_nt(rows, st->N, st->N, 1.0, pg[m].Kx, ldk, o.Kinv.as<double>(), ldk, 0.0, st->wsU.as<double>(), ldk, false, s, &st->lc));
+        if (small_rows) {
+          SkinnyItem it{pg[m].Kx, o.Kinv.as<double>(), st->wsU.as<double>()};
+          RC(launch_skinny_gemm_nt(&it, 1, rows, st->N, st->N, ldk, ldk, ldk, 0, s, &st->lc));
+        } else {
+          RC(launch_gemm_nt(rows, st->N, st->N, 1.0, pg[m].Kx, ldk, o.Kinv.as<double>(), ldk, 0.0, st->wsU.as<double>(), ldk, false, s, &st->lc));
+        }
         rec_end(st, s);
         KernelGradArgs kg;
         kg.md = o.md; kg.prep_q = o.q_prepd; kg.prep_b = o.base_prepd; kg.rows = rows; kg.q = q; kg.nb = nb; kg.N = st->N;
         kg.ldk = ldk; kg.d = st->d; kg.alpha = o.alpha_row.as<double>();
         kg.Aext = o.LinvExt.as<double>() + (size_t)(st->N + 1) * ldk; kg.U = st->wsU.as<double>();
         kg.EG = st->wsEG.as<double>(); kg.EW = st->wsEW.as<double>(); kg.ldw = ldw; kg.Emu = st->wsEmu.as<double>();
-        kg.dX = dX_dev + (size_t)b0 * q * st->d; kg.accumulate = m > 0 ? 1 : 0;
+        kg.dX = dX_dev + (size_t)b0 * q * st->d; kg.accumulate = m > 0 ? 1 : 0; kg.Kx = pg[m].Kx;
         rec_begin(st, "kernel_grad", s);
         RC(launch_kernel_grad(kg, s, &st->lc));
         rec_end(st, s);

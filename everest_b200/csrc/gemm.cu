@@ -676,3 +676,151 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
 int launch_posterior_gemm(const PostGemmArgs& a, cudaStream_t s, LaunchCounter* lc) {
   return launch_posterior_gemm_multi(&a, 1, nullptr, s, lc);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Skinny path for the refinement iterations (rows = restarts * q <= 64): the 128-row tensor-pipe tiles above would be
+// 50-75 % padding and leave most SMs idle.  C[r][n] = sum_k A[r][k] B[n][k] with all rows of A in one CTA and 32 columns
+// per CTA (68 CTAs per output at N = 2000), FP64 FMA from shared-memory tiles; rows n < tri_rows of B are lower
+// triangular (L^-1), so their k loop stops at the end of the column tile.
+// ------------------------------------------------------------------------------------------------
+#define SK_BN 32
+#define SK_BK 32
+#define SK_MAXOUT 8
+struct SkinnyBatch {
+  SkinnyItem item[SK_MAXOUT];
+  int rows, n, k, lda, ldb, ldc, tri_rows;
+};
+
+// leading dimension BK + 4 (= 4 mod 16 doubles): the 32 fragment loads of a warp fall into 2 conflict-free wavefronts
+template <int RB, int BK>
+__global__ void __launch_bounds__(128)
+skinny_gemm_kernel(SkinnyBatch p) {
+  // DMMA m8n8k4: warp w owns columns [n0 + 8w, n0 + 8w + 8) for all RB rows (RB / 8 accumulator pairs); both operands are
+  // K-contiguous, staged by cp.async into a 2-stage ring.
+  __shared__ __align__(16) double As[2][RB][(BK + 4)];
+  __shared__ __align__(16) double Bs[2][SK_BN][(BK + 4)];
+  const SkinnyItem it = p.item[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * SK_BN;
+  int kmax = p.k;
+  if (n0 + SK_BN <= p.tri_rows) kmax = min(p.k, n0 + SK_BN);  // purely triangular tile
+  constexpr int MT = RB / 8;
+  double c0[MT], c1[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) { c0[i] = 0.0; c1[i] = 0.0; }
+  const int n_chunks = (kmax + BK - 1) / BK;
+  auto stage = [&](int chunk, int buf) {
+    const int k0 = chunk * BK;
+    for (int idx = tid; idx < RB * (BK / 2); idx += 128) {
+      const int r = idx / (BK / 2), kk = (idx % (BK / 2)) * 2;
+      cp_async16(&As[buf][r][kk], it.A + (size_t)r * p.lda + k0 + kk, r < p.rows && k0 + kk < kmax);
+    }
+    for (int idx = tid; idx < SK_BN * (BK / 2); idx += 128) {
+      const int c = idx / (BK / 2), kk = (idx % (BK / 2)) * 2;
+      cp_async16(&Bs[buf][c][kk], it.B + (size_t)(n0 + c) * p.ldb + k0 + kk, n0 + c < p.n && k0 + kk < kmax);
+    }
+    cp_async_commit();
+  };
+  stage(0, 0);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < n_chunks) { stage(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      const double bf = Bs[buf][warp * 8 + g][kk + t];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) mma_884(c0[i], c1[i], As[buf][i * 8 + g][kk + t], bf);
+    }
+    __syncthreads();
+  }
+  const int col = n0 + warp * 8 + 2 * t;
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int r = i * 8 + g;
+    if (r < p.rows) {
+      if (col < p.n) it.C[(size_t)r * p.ldc + col] = c0[i];
+      if (col + 1 < p.n) it.C[(size_t)r * p.ldc + col + 1] = c1[i];
+    }
+  }
+}
+
+int launch_skinny_gemm_nt(const SkinnyItem* items, int n_items, int rows, int n, int k, int lda, int ldb, int ldc,
+                          int tri_rows, cudaStream_t s, LaunchCounter* lc) {
+  if (rows <= 0 || n <= 0 || n_items <= 0) return BO_OK;
+  if (rows > 64) { bo_set_error("skinny_gemm: rows=%d > 64", rows); return BO_ERR_INVALID; }
+  for (int i0 = 0; i0 < n_items; i0 += SK_MAXOUT) {
+    SkinnyBatch p;
+    const int cnt = (n_items - i0 < SK_MAXOUT) ? n_items - i0 : SK_MAXOUT;
+    for (int i = 0; i < cnt; ++i) p.item[i] = items[i0 + i];
+    p.rows = rows; p.n = n; p.k = k; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.tri_rows = tri_rows;
+    dim3 grid((n + SK_BN - 1) / SK_BN, cnt);
+    if (rows <= 32) skinny_gemm_kernel<32, 32><<<grid, 128, 0, s>>>(p);
+    else skinny_gemm_kernel<64, 16><<<grid, 128, 0, s>>>(p);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+  }
+  return BO_OK;
+}
+
+// Gram / mean / cross terms from the materialised V = K*X LinvExt^T (ld = ldv): one CTA per (q-batch, output).
+struct SmallGramBatch {
+  const double* V[SK_MAXOUT];
+  double* Gqq[SK_MAXOUT];
+  double* W[SK_MAXOUT];
+  double* mu_raw[SK_MAXOUT];
+  int q, N, n_ext, ldv, ldw;
+};
+
+__global__ void __launch_bounds__(256)
+small_gram_kernel(SmallGramBatch p) {
+  const int batch = blockIdx.x, m = blockIdx.y;
+  const int q = p.q, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const double* V = p.V[m] + (size_t)batch * q * p.ldv;
+  for (int pr = warp; pr < q * q; pr += nw) {
+    const int i = pr / q, j = pr % q;
+    if (j < i) continue;
+    double s = 0.0;
+    for (int n = lane; n < p.N; n += 32) s = fma(V[(size_t)i * p.ldv + n], V[(size_t)j * p.ldv + n], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      p.Gqq[m][((size_t)batch * q + i) * q + j] = s;
+      p.Gqq[m][((size_t)batch * q + j) * q + i] = s;
+    }
+  }
+  for (int idx = threadIdx.x; idx < q * p.n_ext; idx += blockDim.x) {
+    const int i = idx / p.n_ext, e = idx % p.n_ext;
+    const double v = V[(size_t)i * p.ldv + p.N + e];
+    if (e == 0) p.mu_raw[m][(size_t)batch * q + i] = v;
+    else if (p.W[m]) p.W[m][((size_t)batch * q + i) * p.ldw + (e - 1)] = v;
+  }
+}
+
+size_t posterior_small_ws_doubles(int rows, int Rpad, int n_out) { return (size_t)n_out * rows * Rpad; }
+
+// Same outputs as launch_posterior_gemm_multi for rows <= 64; vws holds V for every output ([n_out][rows][Rpad]).
+int launch_posterior_small(const PostGemmArgs* args, int n_out, double* vws, cudaStream_t s, LaunchCounter* lc) {
+  if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
+  const PostGemmArgs& a0 = args[0];
+  std::vector<SkinnyItem> items(n_out);
+  for (int m = 0; m < n_out; ++m) {
+    items[m].A = args[m].Kx; items[m].B = args[m].B; items[m].C = vws + (size_t)m * a0.rows * a0.Rpad;
+    if (args[m].Rpad != a0.Rpad || args[m].rows != a0.rows) { bo_set_error("posterior_small: outputs must share the shapes"); return BO_ERR_INVALID; }
+  }
+  int rc = launch_skinny_gemm_nt(items.data(), n_out, a0.rows, a0.N + a0.n_ext, a0.N, a0.ldk, a0.ldk, a0.Rpad, a0.N, s, lc);
+  if (rc != BO_OK) return rc;
+  for (int m0 = 0; m0 < n_out; m0 += SK_MAXOUT) {
+    SmallGramBatch g;
+    const int cnt = (n_out - m0 < SK_MAXOUT) ? n_out - m0 : SK_MAXOUT;
+    for (int i = 0; i < cnt; ++i) {
+      g.V[i] = items[m0 + i].C; g.Gqq[i] = args[m0 + i].Gqq; g.W[i] = args[m0 + i].W; g.mu_raw[i] = args[m0 + i].mu_raw;
+    }
+    g.q = a0.q; g.N = a0.N; g.n_ext = a0.n_ext; g.ldv = a0.Rpad; g.ldw = a0.ldw;
+    dim3 grid(a0.rows / a0.q, cnt);
+    small_gram_kernel<<<grid, 256, 0, s>>>(g);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+  }
+  return BO_OK;
+}

@@ -39,7 +39,10 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
   const bool has_cons = a.od.n_cons > 0;
 
   double total = 0.0;
-  for (int s = tid; s < S; s += nt) {
+  // the MC samples are split over gridDim.y CTAs (few q-batches: more CTAs than q-batches); partial sums per split
+  const int per_split = (S + gridDim.y - 1) / gridDim.y;
+  const int s_begin = blockIdx.y * per_split, s_end = min(S, s_begin + per_split);
+  for (int s = s_begin + tid; s < s_end; s += nt) {
     for (int j = 0; j < q; ++j) {
       double y[2 * BO_MAX_OBJECTIVES];
       for (int m = 0; m < M; ++m) {
@@ -166,14 +169,7 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
     }
   }
   double t = block_sum(total, red);
-  if (tid == 0) {
-    a.out[batch] = t / (double)S;
-    if (a.info_out) {
-      int v = 0;
-      for (int m = 0; m < M; ++m) v |= a.info_in[(size_t)batch * M + m];
-      a.info_out[batch] = v;
-    }
-  }
+  if (tid == 0) a.partial[(size_t)blockIdx.y * a.b + batch] = t;   // summed in a fixed order by mc_reduce_partials_kernel
 }
 
 static int pick_threads(size_t fixed_doubles, size_t per_thread_doubles, size_t* smem_out) {
@@ -188,18 +184,31 @@ int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream
   if (a.b <= 0) return BO_OK;
   const int Mo = a.od.n_obj;
   size_t smem = 0;
-  const int nt = pick_threads((size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M,
-                              (size_t)2 * a.q * Mo + 2 * a.q + (size_t)a.q * a.M, &smem);
-  if (!nt) { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M;
+  const size_t per = (size_t)2 * a.q * Mo + 2 * a.q + (size_t)a.q * a.M;
+  const int nt_max = pick_threads(fixed, per, &smem);
+  if (!nt_max) { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  if (!a.partial) { bo_set_error("mc_hvi_grad: partial-sum workspace missing"); return BO_ERR_STATE; }
+  // about two waves of CTAs: split the MC samples when there are few q-batches (partial has room for ceil(S / 32) splits)
+  int nsplit = (296 + a.b - 1) / a.b;
+  nsplit = std::max(1, std::min(nsplit, (a.S + 31) / 32));
+  int nt = nt_max;
+  {
+    const int per_split = (a.S + nsplit - 1) / nsplit;
+    const int want = ((per_split + 31) / 32) * 32;
+    if (want < nt) nt = want;
+    smem = (fixed + per * nt + 32) * sizeof(double);
+  }
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  mc_hvi_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
+  dim3 grid(a.b, nsplit);
+  mc_hvi_grad_kernel<<<grid, nt, smem, st>>>(a, dF, df_stride);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
-  return BO_OK;
+  return launch_mc_reduce_partials(a.partial, nsplit, a.b, a.S, a.out, a.info_in, a.M, a.info_out, st, lc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -401,6 +410,8 @@ kernel_grad_kernel(const __grid_constant__ KernelGradArgs a, int dpad_max) {
   const double* eg = a.EG + ((size_t)batch * q + jj) * q;
   bool any_cont = false;
   for (int l = 0; l < md.n_leaves; ++l) any_cont = any_cont || (md.leaf[l].kind <= BO_LEAF_MATERN52);
+  // single RBF leaf (SingleTaskGP default): dK/dstat = -K/2 with K already in the forward K(X*, X) buffer
+  const bool fast_rbf = a.Kx && md.n_terms == 1 && md.nfac[0] == 1 && md.leaf[md.fac[0][0]].kind == BO_LEAF_RBF;
 
   for (int p0 = 0; any_cont && p0 < P; p0 += KG_CHUNK) {
     const int cn = min(KG_CHUNK, P - p0);
@@ -431,7 +442,9 @@ kernel_grad_kernel(const __grid_constant__ KernelGradArgs a, int dpad_max) {
         const int p = p0 + pl;
         const double wv = w[pl];
         double gv = 0.0;
-        if (wv != 0.0) {
+        if (wv != 0.0 && fast_rbf && p < N) {
+          gv = wv * (-0.5) * a.Kx[(size_t)row * a.ldk + p];
+        } else if (wv != 0.0) {
           // partner side / index
           const PrepD* pp;
           int pi;
@@ -472,14 +485,24 @@ kernel_grad_kernel(const __grid_constant__ KernelGradArgs a, int dpad_max) {
         const int ai = tid % na, sl = tid / na;
         double accx = 0.0, accg = 0.0;
         if (sl < nsl) {
-          for (int pl = sl; pl < cn; pl += nsl) {
+          // three partner segments with a fixed base pointer each; g = 0 entries simply add nothing, so the loops carry
+          // no branch and the (L2-resident) row loads of 8 iterations are in flight together
+          const int n_tr = max(0, min(cn, N - p0));                 // training partners in this chunk
+          {
+            const double* xb = L.Xs + (size_t)p0 * L.dpad + a0 + ai;
+#pragma unroll 8
+            for (int pl = sl; pl < n_tr; pl += nsl) {
+              const double gv = g[pl];
+              accx = fma(gv, xb[(size_t)pl * L.dpad], accx);
+              accg += gv;
+            }
+          }
+          for (int pl = n_tr + ((sl - n_tr % nsl + nsl) % nsl); pl < cn; pl += nsl) {   // baseline / same-batch partners
             const double gv = g[pl];
             if (gv == 0.0) continue;
             const int p = p0 + pl;
-            const double* xb;
-            if (p < N) xb = L.Xs + (size_t)p * L.dpad;
-            else if (p < N + nb) xb = a.prep_b.Xs[l] + (size_t)(p - N) * L.dpad;
-            else xb = a.prep_q.Xs[l] + (size_t)(batch * q + (p - N - nb)) * L.dpad;
+            const double* xb = (p < N + nb) ? a.prep_b.Xs[l] + (size_t)(p - N) * L.dpad
+                                            : a.prep_q.Xs[l] + (size_t)(batch * q + (p - N - nb)) * L.dpad;
             accx = fma(gv, xb[a0 + ai], accx);
             accg += gv;
           }

@@ -1,8 +1,16 @@
-"""Base samples for the MC acquisition functions (host side, torch SobolEngine -- the same generator
-BoTorch's SobolQMCNormalSampler uses on CPU in the reference; [UPSTREAM] botorch.sampling.qmc)."""
+"""Base samples for the MC acquisition functions ([UPSTREAM] botorch.sampling.qmc / SobolQMCNormalSampler: torch
+SobolEngine(scramble=True, seed).draw(S) -> v = 0.5 + (1 - 1e-10)(u - 0.5) -> sqrt(2) erfinv(2v - 1)).
+
+`base_samples` is the host version (what the reference does on CPU); `base_samples_device` runs the scramble, the
+Gray-code draw and the inverse CDF in sm_100a kernels (csrc/sobol.cu) and reproduces torch's integer pipeline bit for
+bit -- only the random bits (shift vector, scramble matrices) still come from torch's CPU generator so that a seed means
+exactly what it means in BoTorch."""
+import ctypes as C
 import math
 
 import torch
+
+MAXBIT = 30
 
 
 def draw_sobol_normal_samples(d: int, n: int, seed: int) -> torch.Tensor:
@@ -18,3 +26,40 @@ def base_samples(n_points: int, n_outputs: int, n_samples: int, seed: int) -> to
         return torch.zeros(n_samples, 0, n_outputs, dtype=torch.double)
     z = draw_sobol_normal_samples(n_points * n_outputs, n_samples, seed)
     return z.view(n_samples, n_outputs, n_points).transpose(1, 2).contiguous()
+
+
+def sobol_scramble_inputs(dim: int, seed: int):
+    """The host part of SobolEngine.__init__ / _scramble: unscrambled direction numbers, the random shift and the random
+    unit-lower-triangular matrices packed one 30-bit row per integer (bit 29 - k of row p = L[p][k])."""
+    if dim < 1 or dim > torch.quasirandom.SobolEngine.MAXDIM:
+        raise ValueError(f"Supported range of dimensionality for SobolEngine is [1, {torch.quasirandom.SobolEngine.MAXDIM}]")
+    ss = torch.zeros(dim, MAXBIT, dtype=torch.long)
+    torch._sobol_engine_initialize_state_(ss, dim)
+    g = torch.Generator()
+    g.manual_seed(int(seed))
+    shift_ints = torch.randint(2, (dim, MAXBIT), generator=g)
+    pw = torch.pow(2, torch.arange(0, MAXBIT))
+    shift = torch.mv(shift_ints, pw)
+    ltm = torch.randint(2, (dim, MAXBIT, MAXBIT), generator=g).tril(-1) + torch.eye(MAXBIT, dtype=torch.long)
+    rows = (ltm * pw.flip(0)).sum(dim=-1)          # k-th column weighs 2^(29 - k)
+    return ss, shift, rows
+
+
+def base_samples_device(n_points: int, n_outputs: int, n_samples: int, seed: int, device) -> torch.Tensor:
+    """Same contract as `base_samples`, generated on `device` (a CUDA device)."""
+    from . import _lib as L
+
+    device = torch.device(device)
+    if n_points == 0:
+        return torch.zeros(n_samples, 0, n_outputs, dtype=torch.double, device=device)
+    dim = n_points * n_outputs
+    ss, shift, rows = sobol_scramble_inputs(dim, seed)
+    lib = L.load()
+    ss_d, shift_d, rows_d = ss.to(device), shift.to(device), rows.to(device)
+    out = torch.empty(n_samples, n_points, n_outputs, dtype=torch.double, device=device)
+    with torch.cuda.device(device):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(lib.bo_sobol_scramble(C.c_void_p(ss_d.data_ptr()), C.c_void_p(rows_d.data_ptr()), dim, stream))
+        L.check(lib.bo_sobol_normal(C.c_void_p(ss_d.data_ptr()), C.c_void_p(shift_d.data_ptr()), n_points, n_outputs,
+                                    n_samples, C.c_void_p(out.data_ptr()), stream))
+    return out

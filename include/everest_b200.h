@@ -203,6 +203,15 @@ int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t 
 int bo_pareto_mask(const double* Y_dev, int32_t n, int32_t m, int32_t deduplicate, int32_t* mask_dev, void* stream);
 int bo_hypervolume(const double* Y_dev, int32_t n, int32_t m, const double* ref_point, double* hv_out, void* stream);
 
+/* Base samples on the device ([UPSTREAM] SobolQMCNormalSampler = torch SobolEngine(scramble=True, seed) + inverse normal
+ * CDF, reached from every _get_acqfs and from prune_inferior_points).  bo_sobol_scramble applies the per-dimension
+ * unit-lower-triangular GF(2) matrices (ltm_rows_dev [dim, 30]: bit 29-k of row p = L[p][k]) to the direction numbers
+ * sobolstate_dev [dim, 30] in place; bo_sobol_normal writes z[S, n_points, M] for Sobol dimension m * n_points + i.
+ * Both reproduce torch's integer pipeline bit for bit (the random bits come from torch's CPU generator). */
+int bo_sobol_scramble(int64_t* sobolstate_dev, const int64_t* ltm_rows_dev, int32_t dim, void* stream);
+int bo_sobol_normal(const int64_t* sobolstate_dev, const int64_t* shift_dev, int32_t n_points, int32_t M, int32_t S,
+                    double* out_dev, void* stream);
+
 /* Introspection for tests: copies internal device buffers to the given device pointers. */
 int bo_debug_get(bo_state* st, const char* name, int32_t m, double* out_dev, int64_t capacity, int64_t* n_written,
                  void* stream);
