@@ -377,10 +377,17 @@ def run_b200(args):
         from everest_b200 import optim
 
         torch.cuda.synchronize(device)
+        torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))  # the CPU baseline above may have raised it
         t0 = time.perf_counter()
         acq2 = Cf.build_acqf(p, st)
         torch.cuda.synchronize(device)
         t1 = time.perf_counter()
+        if os.environ.get("EVEREST_BENCH_PROFILE"):
+            import cProfile, pstats
+            pr = cProfile.Profile(); pr.enable()
+            acq2 = Cf.build_acqf(p, st); torch.cuda.synchronize(device)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(16)
         bnds = torch.as_tensor(p["bounds"])
         Xic, Yic, _, _ = optim.gen_batch_initial_conditions(acq2, bnds, p["q"], p["num_restarts"], p["raw_samples"], seed=0)
         torch.cuda.synchronize(device)

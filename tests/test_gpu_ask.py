@@ -90,6 +90,9 @@ def test_device_base_samples_match_the_host_engine():
         zh = sampling.base_samples(n_points, M, S, seed)
         zd = sampling.base_samples_device(n_points, M, S, seed, "cuda:0").cpu()
         assert zd.shape == zh.shape == (S, n_points, M)
-        assert float((zd - zh).abs().max()) < 1e-13
+        diff = (zd - zh).abs()
         assert bool(torch.isfinite(zd).all())
+        # the uniform points are identical; CUDA's and torch's erfinv differ by a few ulps, more in the far tails
+        assert float(diff.max()) < 1e-11, float(diff.max())
+        assert float(diff[zh.abs() < 3.0].max()) < 1e-13, float(diff[zh.abs() < 3.0].max())
     assert sampling.base_samples_device(0, 2, 8, 1, "cuda:0").shape == (8, 0, 2)
