@@ -121,3 +121,9 @@ struct KernelGradArgs {
   int accumulate;       // 0: overwrite dX, 1: add (outputs after the first)
 };
 int launch_kernel_grad(const KernelGradArgs& a, cudaStream_t st, LaunchCounter* lc);
+
+// ---- mll.cu: exact marginal log likelihood and its hyper-parameter gradient ----------------------
+int launch_mll_grad(const ModelD& md, const PrepD& train, int N, int ldk, const double* alpha, const double* Kinv,
+                    const int* ls_offset, int n_ls_total, double* part, double* out_params, cudaStream_t st, LaunchCounter* lc);
+int launch_mll_scalars(const double* resid, const double* alpha, const double* Lmat, const double* Kinv, int N, int ldk,
+                       double* out5, cudaStream_t st, LaunchCounter* lc);

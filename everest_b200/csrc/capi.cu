@@ -909,6 +909,47 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
   return BO_OK;
 }
 
+extern "C" int bo_mll_forward_backward(bo_state* st, int32_t m, double* mll_out, double* d_noise, double* d_mean_const,
+                                       double* d_lengthscale, int32_t n_lengthscale, double* d_coef, int32_t n_coef,
+                                       void* stream) {
+  if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
+  if (m < 0 || m >= st->M || !mll_out) { bo_set_error("mll: bad output index / null result"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  OutputH& o = st->out[m];
+  const int N = st->N, ldk = st->ldk;
+  // lengthscale slots: ARD dims of the continuous leaves, groups of the Hamming leaves, in leaf order
+  int ls_offset[BO_MAX_LEAVES], n_ls = 0;
+  for (int l = 0; l < o.md.n_leaves; ++l) {
+    if (o.md.leaf[l].kind <= BO_LEAF_HAMMING) { ls_offset[l] = n_ls; n_ls += o.md.leaf[l].nd; }
+    else ls_offset[l] = -1;
+  }
+  if ((d_lengthscale && n_lengthscale != n_ls) || (d_coef && n_coef != o.md.n_terms)) {
+    bo_set_error("mll: expected %d lengthscale slots and %d term coefficients", n_ls, o.md.n_terms);
+    return BO_ERR_INVALID;
+  }
+  RC(ensure_kinv(st, o, s));
+  const int n_params = n_ls + o.md.n_terms;
+  RC(st->wsTmp.ensure(((size_t)N * n_params + n_params + 8) * 8));
+  double* part = st->wsTmp.as<double>();
+  double* outp = part + (size_t)N * n_params;
+  double* out5 = outp + n_params;
+  RC(launch_mll_scalars(o.resid.as<double>(), o.alpha_row.as<double>(), o.L.as<double>(), o.Kinv.as<double>(), N, ldk, out5, s, &st->lc));
+  const bool want_grad = d_lengthscale || d_coef;
+  if (want_grad) RC(launch_mll_grad(o.md, o.train_prepd, N, ldk, o.alpha_row.as<double>(), o.Kinv.as<double>(), ls_offset, n_ls, part, outp, s, &st->lc));
+  std::vector<double> host(n_params + 5);
+  CUDA_CHECK_RET(cudaMemcpyAsync(host.data(), outp, (size_t)(n_params + 5) * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  const double* h5 = host.data() + n_params;
+  *mll_out = -0.5 * h5[0] - h5[1] - 0.5 * (double)N * 1.8378770664093453;  // log(2 pi)
+  if (d_mean_const) *d_mean_const = h5[2];
+  if (d_noise) *d_noise = 0.5 * (h5[3] - h5[4]);
+  if (want_grad) {
+    if (d_lengthscale) for (int k = 0; k < n_ls; ++k) d_lengthscale[k] = host[k];
+    if (d_coef) for (int t = 0; t < o.md.n_terms; ++t) d_coef[t] = host[n_ls + t];
+  }
+  return BO_OK;
+}
+
 extern "C" int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
                                double* out_dev, int32_t* info_dev, void* stream) {
   return acqf_run(st, X_dev, b, q, zq_dev, out_dev, nullptr, info_dev, stream);

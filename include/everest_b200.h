@@ -203,6 +203,15 @@ int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t 
 int bo_pareto_mask(const double* Y_dev, int32_t n, int32_t m, int32_t deduplicate, int32_t* mask_dev, void* stream);
 int bo_hypervolume(const double* Y_dev, int32_t n, int32_t m, const double* ref_point, double* hv_out, void* stream);
 
+/* Exact marginal log likelihood of output m for the CURRENT hyper-parameters of the (factorised) state, and its
+ * gradient: the objective of fit_gpytorch_mll in SingleTaskGPSurrogate._fit (surrogates/single_task_gp.py:39-71) without
+ * the prior terms and the 1/N scaling (both are host-side one-liners).  Derivatives are with respect to the natural
+ * parameters: noise variance, constant mean, every lengthscale (ARD dims of the continuous leaves and groups of the
+ * Hamming leaves, in leaf order) and every term coefficient of the flattened kernel (products of outputscales).  All
+ * outputs are HOST pointers; any gradient pointer may be NULL. */
+int bo_mll_forward_backward(bo_state* st, int32_t m, double* mll_out, double* d_noise, double* d_mean_const,
+                            double* d_lengthscale, int32_t n_lengthscale, double* d_coef, int32_t n_coef, void* stream);
+
 /* Base samples on the device ([UPSTREAM] SobolQMCNormalSampler = torch SobolEngine(scramble=True, seed) + inverse normal
  * CDF, reached from every _get_acqfs and from prune_inferior_points).  bo_sobol_scramble applies the per-dimension
  * unit-lower-triangular GF(2) matrices (ltm_rows_dev [dim, 30]: bit 29-k of row p = L[p][k]) to the direction numbers

@@ -84,7 +84,8 @@ class Mul:
 
 
 def _ls_tensor(ls, n):
-    t = torch.as_tensor(list(ls), dtype=DT)
+    # a tensor is passed through untouched so that autograd can differentiate the marginal likelihood w.r.t. it
+    t = ls.to(DT).reshape(-1) if isinstance(ls, torch.Tensor) else torch.as_tensor(list(ls), dtype=DT)
     if t.numel() == 1:
         t = t.expand(n)
     return t[:n]
@@ -263,6 +264,21 @@ class GPOracle:
             mean[:, m] = mu * o.y_std + o.y_mean
             cov[m] = S * (o.y_std**2)
         return mean, cov
+
+
+def log_marginal_likelihood(X_train, out: "GPOutput"):
+    """[UPSTREAM] gpytorch ExactMarginalLogLikelihood without the prior terms and the 1/N scaling -- the objective
+    SingleTaskGPSurrogate._fit hands to fit_gpytorch_mll (surrogates/single_task_gp.py:69-71).  Hyper-parameters may be
+    tensors that require grad (lengthscales, outputscales, noise, mean constant): autograd gives the reference gradient."""
+    X = torch.as_tensor(X_train, dtype=DT)
+    N = X.shape[0]
+    Xt = (X - out.in_offset) / out.in_scale
+    center = Xt.mean(0)
+    Kmat = eval_kernel(out.kernel, Xt, Xt, center, same=True) + out.noise * torch.eye(N, dtype=DT)
+    r = (out.y - out.y_mean) / out.y_std - out.mean_const
+    L = torch.linalg.cholesky(Kmat)
+    alpha = torch.cholesky_solve(r.unsqueeze(-1), L).squeeze(-1)
+    return -0.5 * (r * alpha).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * N * math.log(2.0 * math.pi)
 
 
 # ----------------------------------------------------------------------------------------
