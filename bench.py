@@ -413,6 +413,24 @@ def run_b200(args):
                "note": "refinement = scipy L-BFGS-B over all restarts, gradient from the analytic adjoint kernels "
                        "(bo_acqf_forward_backward)"}
 
+    if world > 1 and p.get("bounds") is not None:
+        # ask() over the GPUs of the box: raw samples and restarts sharded, one value all-gather + one arg-max exchange
+        from everest_b200 import distributed as D
+
+        barrier()
+        t0 = time.perf_counter()
+        acq2 = Cf.build_acqf(p, st)
+        barrier()
+        t1 = time.perf_counter()
+        cand, val = D.sharded_optimize_acqf(acq2, torch.as_tensor(p["bounds"]), p["q"], p["num_restarts"],
+                                            p["raw_samples"] * world, options={"maxiter": 200}, seed=0)
+        barrier()
+        t2 = time.perf_counter()
+        ask = {"acqf_build_s": t1 - t0, "screen_and_refine_s": t2 - t1, "total_s": t2 - t0, "refine_maxiter": 200,
+               "raw_samples_total": int(p["raw_samples"] * world), "best_refined": float(val),
+               "note": "sharded_optimize_acqf: raw samples and restarts split over the ranks, analytic gradients, "
+                       "one all-gather of the screen values + one (value, rank) arg-max exchange + one broadcast"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -57,3 +57,53 @@ def sharded_argmax(acq: Callable[[torch.Tensor], torch.Tensor], X: torch.Tensor,
     dist.all_gather(pairs, best, group=group)
     top = max(pairs, key=lambda t: (float(t[0]), float(t[1])))
     return float(top[0]), int(-float(top[1]))
+
+
+def sharded_optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
+                          fixed_features=None, options: Optional[dict] = None, seed: int = 0, group=None,
+                          inequality_constraints=None, equality_constraints=None):
+    """optimize_acqf over the GPUs of one box: every rank scores its slice of the raw samples (one
+    all-gather of the values, because initialize_q_batch needs all of them), every rank refines ITS share of the
+    restarts with L-BFGS-B / SLSQP without any per-iteration collective, and the only other exchange is the arg-max over
+    the per-rank best (value, rank) -- "only the per-restart best-acquisition argmax is reduced" -- followed by the
+    broadcast of the winning [q, d] candidate.  All ranks must pass the same `seed`; returns the same (candidate, value)
+    on every rank."""
+    from . import optim
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return optim.optimize_acqf(acq_function, bounds, q, num_restarts, raw_samples, fixed_features=fixed_features,
+                                   options=options, seed=seed, inequality_constraints=inequality_constraints,
+                                   equality_constraints=equality_constraints)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = torch.as_tensor(bounds, dtype=torch.double)
+    dev = acq_function.model.device
+    # identical raw samples on every rank (same seed), scored in slices
+    if inequality_constraints or equality_constraints:
+        X_rnd = optim.sample_q_batches_from_polytope(raw_samples, q, bounds, inequality_constraints, equality_constraints,
+                                                     seed=seed, fixed_features=fixed_features)
+    else:
+        X_rnd = optim.apply_fixed_features(optim.draw_sobol_samples(bounds, raw_samples, q, seed=seed), fixed_features)
+    with torch.no_grad():
+        Y_rnd = sharded_forward(lambda x: acq_function(x.to(dev)), X_rnd, group=group).cpu()
+    gen = torch.Generator().manual_seed(int(seed))          # the same multinomial draw on every rank
+    X_ic, idcs = optim.initialize_q_batch(X_rnd, Y_rnd, n=num_restarts, eta=(options or {}).get("eta", 2.0), generator=gen)
+    Y_ic = Y_rnd[idcs]
+    lo, hi = shard_bounds(num_restarts, rank, world)
+    best_val, best_x = float("-inf"), torch.zeros(q, bounds.shape[-1], dtype=torch.double)
+    if hi > lo:
+        X_ref, Y_ref, _ = optim.gen_candidates_scipy(X_ic[lo:hi], acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
+                                                     options=options, inequality_constraints=inequality_constraints,
+                                                     equality_constraints=equality_constraints)
+        better = Y_ref >= Y_ic[lo:hi]
+        Xb = torch.where(better.view(-1, 1, 1), X_ref, X_ic[lo:hi].cpu())
+        Yb = torch.where(better, Y_ref, Y_ic[lo:hi])
+        i = int(torch.argmax(Yb))
+        best_val, best_x = float(Yb[i]), Xb[i]
+    pair = torch.tensor([best_val, -float(rank)], dtype=torch.double, device=dev)
+    pairs = [torch.empty_like(pair) for _ in range(world)]
+    dist.all_gather(pairs, pair, group=group)
+    top = max(pairs, key=lambda t: (float(t[0]), float(t[1])))
+    winner = int(-float(top[1]))
+    cand = best_x.to(dev).contiguous()
+    dist.broadcast(cand, src=dist.get_global_rank(group, winner) if group is not None else winner, group=group)
+    return cand.cpu(), torch.tensor(float(top[0]), dtype=torch.double)

@@ -236,6 +236,25 @@ got = D.sharded_forward(acq, X)
 assert torch.equal(got, full), "sharded_forward mismatch"
 v, i = D.sharded_argmax(acq, X)
 assert i == int(torch.argmax(full)) and v == float(full.max())
+# sharded ask: screen in slices, each rank refines its share of the restarts, one arg-max exchange + one broadcast
+class _M:
+    device = torch.device("cpu")
+class _Fake:
+    model = _M()
+    def __call__(self, X):
+        return -((X - 0.3) ** 2).sum(dim=(1, 2)) + 0.1 * torch.cos(9.0 * X[:, 0, 0])
+    def forward_backward(self, X):
+        Xr = X.clone().requires_grad_(True)
+        v = self(Xr); v.sum().backward()
+        return v.detach(), Xr.grad
+bounds = torch.tensor([[0.0] * 3, [1.0] * 3], dtype=torch.double)
+cand, val = D.sharded_optimize_acqf(_Fake(), bounds, q=2, num_restarts=4, raw_samples=64, options={"maxiter": 60}, seed=5)
+both = [torch.empty(7, dtype=torch.double) for _ in range(2)]
+dist.all_gather(both, torch.cat([cand.reshape(-1), val.reshape(1)]))
+assert torch.equal(both[0], both[1]), "ranks disagree on the winning candidate"
+from everest_b200 import optim
+X_rnd = optim.draw_sobol_samples(bounds, 64, 2, seed=5)
+assert float(val) >= float(_Fake()(X_rnd).max()) - 1e-12 and abs(float(_Fake()(cand.unsqueeze(0))[0]) - float(val)) < 1e-12
 dist.barrier()
 dist.destroy_process_group()
 print("rank", sys.argv[3], "ok")
