@@ -70,6 +70,13 @@ __device__ __forceinline__ double subset_axis(unsigned sub, const double* __rest
   return w - lo;
 }
 
+// running log-sum-exp as a (max, sum) pair: value = m + log s
+__device__ __forceinline__ void lse_push(double& m, double& s, double v) {
+  if (v > m) { s = s * exp(m - v) + 1.0; m = v; }   // exp(-inf) = 0 on the first push
+  else if (!(isinf(v) && v < 0)) s += exp(v - m);
+}
+__device__ __forceinline__ double lse_value(double m, double s) { return (s > 0.0) ? m + log(s) : -INFINITY; }
+
 struct LhSmem { double *root, *mu, *objs, *lfw, *gob, *glf, *ys, *vals, *red; };
 
 __device__ __forceinline__ LhSmem lh_smem(double* base, int M, int q, int nr, int Mo, int nt, int S, bool grad) {
@@ -115,12 +122,12 @@ __device__ __forceinline__ void lh_load_sample(const McArgs& a, const LhSmem& sm
 
 // log area of the overlap of subset `sub` with the cell
 __device__ __forceinline__ double subset_logarea(const McArgs& a, const LhSmem& sm, unsigned sub, const double* lo,
-                                                 const double* up, int tid, int nt) {
+                                                 const double* up, int tid, int nt, double log_tau_relu) {
   const int Mo = a.od.n_obj;
   double la = 0.0;
   for (int o = 0; o < Mo; ++o) {
     const double len = subset_axis(sub, sm.objs + (size_t)o * nt + tid, Mo * nt, lo[o], up[o], a.tau_max, nullptr);
-    la += log_fatplus_d(len, a.tau_relu);
+    la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
   }
   if (a.od.n_cons)
     for (unsigned rest = sub; rest; rest &= rest - 1) la += sm.lfw[(size_t)(__ffs(rest) - 1) * nt + tid];
@@ -163,6 +170,7 @@ mc_loghvi_kernel(McArgs a) {
   for (int i = tid; i < q * M; i += nt) sm.mu[i] = a.mu[(size_t)batch * q * M + i];
   __syncthreads();
   const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  const double log_tau_relu = log(a.tau_relu);
   double lmax = -INFINITY;
   for (int s = tid; s < S; s += nt) {
     lh_load_sample(a, sm, batch, s, tid, nt);
@@ -176,12 +184,14 @@ mc_loghvi_kernel(McArgs a) {
         lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
         up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
       }
-      double odd = -INFINITY, even = -INFINITY;
+      // running (max, sum) pairs: one exp per subset instead of a full logaddexp
+      double mo = -INFINITY, so = 0.0, me = -INFINITY, se = 0.0;
       for (unsigned sub = 1; sub <= full; ++sub) {
-        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt);
-        if (__popc(sub) & 1) odd = logaddexp_d(odd, la);
-        else even = logaddexp_d(even, la);
+        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt, log_tau_relu);
+        if (__popc(sub) & 1) lse_push(mo, so, la);
+        else lse_push(me, se, la);
       }
+      const double odd = lse_value(mo, so), even = lse_value(me, se);
       const double cellv = (isinf(even) && even < 0) ? odd : odd + log1mexp_d(even - odd);
       if (cellv > R) { ssum = ssum * exp(R - cellv) + 1.0; R = cellv; }
       else if (!(isinf(cellv) && cellv < 0)) ssum += exp(cellv - R);
@@ -230,6 +240,7 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
   __syncthreads();
   const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
   const bool has_cons = a.od.n_cons > 0;
+  const double log_tau_relu = log(a.tau_relu);
   double lmax = -INFINITY;
   for (int s = tid; s < S; s += nt) {
     lh_load_sample(a, sm, batch, s, tid, nt);
@@ -243,12 +254,13 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
         lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
         up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
       }
-      double odd = -INFINITY, even = -INFINITY;
+      double mo = -INFINITY, so = 0.0, me = -INFINITY, se = 0.0;
       for (unsigned sub = 1; sub <= full; ++sub) {
-        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt);
-        if (__popc(sub) & 1) odd = logaddexp_d(odd, la);
-        else even = logaddexp_d(even, la);
+        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt, log_tau_relu);
+        if (__popc(sub) & 1) lse_push(mo, so, la);
+        else lse_push(me, se, la);
       }
+      const double odd = lse_value(mo, so), even = lse_value(me, se);
       const bool no_even = isinf(even) && even < 0;
       const double cellv = no_even ? odd : odd + log1mexp_d(even - odd);
       if (isinf(cellv) && cellv < 0) continue;
@@ -274,7 +286,7 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
         double dlf[LH_MAXO];
         for (int o = 0; o < Mo; ++o) {
           const double len = subset_axis(sub, sm.objs + (size_t)o * nt + tid, Mo * nt, lo[o], up[o], a.tau_max, dlen[o]);
-          la += log_fatplus_d(len, a.tau_relu);
+          la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
           dlf[o] = log_fatplus_grad_d(len, a.tau_relu);
         }
         if (has_cons)

@@ -27,24 +27,41 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
   if (isinf(mx) && mx < 0) return mx;
   return mx + log1p(exp(mn - mx));
 }
-__device__ __forceinline__ double log_fatplus_d(double x, double tau) {
-  double z = x / tau;
-  return log(tau) + logaddexp_d(log_softplus_d(z), log(1e-1) - log1p(z * z));
+// log_fatplus(x, tau) = log(tau) + logaddexp( log_softplus(z), log(0.1) - log1p(z^2) ),  z = x / tau.
+// Far from the kink (|z| large -- the usual case with tau = 1e-6) the same expression needs one or two logarithms:
+//   z > 32  : softplus(z) = z (torch threshold), so the value is log z + log1p(0.1 / (z (1 + z^2)))
+//   z < -750: exp(z - B) underflows, the value is B = log(0.1) - log1p(z^2)
+// Both are algebraic identities of the generic formula (rounding differs at 1e-16).
+__device__ __forceinline__ double log_fatplus_lt(double x, double tau, double log_tau) {
+  const double z = x / tau;
+  if (z > 32.0) {
+    const double r = 0.1 / (z * (1.0 + z * z));
+    return log_tau + log(z) + ((r < 1e-9) ? r : log1p(r));
+  }
+  const double B = -2.302585092994046 - log1p(z * z);
+  if (z < -750.0) return log_tau + B;
+  return log_tau + logaddexp_d(log_softplus_d(z), B);
 }
+__device__ __forceinline__ double log_fatplus_d(double x, double tau) { return log_fatplus_lt(x, tau, log(tau)); }
 // d log_fatplus(x, tau) / dx
 __device__ __forceinline__ double log_fatplus_grad_d(double x, double tau) {
   const double z = x / tau;
-  const double A = log_softplus_d(z), B = log(1e-1) - log1p(z * z);
+  const double dB = -2.0 * z / (1.0 + z * z);
+  if (z > 32.0) {
+    const double r = 0.1 / (z * (1.0 + z * z));     // exp(B - A)
+    return ((1.0 / z) + r * dB) / ((1.0 + r) * tau);
+  }
+  if (z < -750.0) return dB / tau;
+  const double A = log_softplus_d(z), B = -2.302585092994046 - log1p(z * z);
   const double lae = logaddexp_d(A, B);
   double dA;
   if (z > -35.0) {
     const double sp = softplus_d(z);
-    const double sg = (z > 32.0) ? 1.0 : 1.0 / (1.0 + exp(-z));
+    const double sg = 1.0 / (1.0 + exp(-z));
     dA = sg / sp;
   } else {
     dA = 1.0;
   }
-  const double dB = -2.0 * z / (1.0 + z * z);
   return (exp(A - lae) * dA + exp(B - lae) * dB) / tau;
 }
 
