@@ -145,3 +145,20 @@ def test_strategy_with_fitted_surrogates():
     assert all(len(o.kernel.lengthscale) == 3 for o in strat.model.outputs)
     cand, preds, stds = strat.ask(1)
     assert cand.shape == (1, 3) and np.all(np.isfinite(preds)) and np.all(stds > 0)
+
+
+def test_mll_gradient_large_n_chunk_loop():
+    """N > 2048: the partner-chunk loop of mll_grad_kernel."""
+    rng = np.random.default_rng(5)
+    N, d = 2100, 2
+    X = rng.random((N, d))
+    y = np.sin(5 * X[:, 0]) + X[:, 1] + 0.1 * rng.normal(size=N)
+    ls = [0.3, 0.8]
+    build = lambda t: (O.Scale(O.Matern(2.5, [0, 1], t["ls"]), t["os"]), t["noise"], t["mean"])   # noqa: E731
+    mll_o, g_o = oracle_mll_and_grads(X, y, build, dict(ls=ls, os=1.2, noise=0.05, mean=0.0))
+    spec = SingleTaskGPSpec(kernel=K.ScaleKernel(K.MaternKernel([0, 1], ls, nu=2.5), 1.2), y=y, mean_const=0.0, noise=0.05)
+    mll_d, dn, dm, dls, dco = F.mll_and_grad(X, spec)
+    assert abs(mll_d - mll_o) < 1e-9 * abs(mll_o)
+    assert np.abs(dls - g_o["ls"].numpy()).max() < 1e-6 * np.abs(g_o["ls"].numpy()).max()
+    assert abs(dco[0] - float(g_o["os"])) < 1e-6 * abs(float(g_o["os"]))
+    assert abs(dn - float(g_o["noise"])) < 1e-6 * abs(float(g_o["noise"]))

@@ -203,3 +203,60 @@ def test_full_size_gradient_properties_headline_config():
     vals = acq(P_.view(-1, q, d)).view(b, q * len(cols), 2)
     fd = ((vals[..., 0] - vals[..., 1]) / (2 * h)).view(b, q, len(cols))
     assert float((fd - g[:, :, cols]).abs().max()) < 1e-4 * float(g.abs().max())
+
+
+def test_gradient_chunk_loops_large_n_and_large_baseline():
+    """N > 2048 exercises the partner-chunk loop of kernel_grad_kernel (and N + n_b + q > one chunk); no pruning keeps a
+    baseline too large for the shared-memory copy of L_b^-1 (cond_root streams it, cond_root_bwd runs one warp per CTA)."""
+    p = Cf.zdt1_qnehvi(N=2200, S=16, raw=5, d=3, q=2)
+    st = Cf.build_state(p)
+    gp = P.oracle_gp(p)
+    ops = [P.op_to_oracle(o) for o in p["objective"].ops]
+    Xb = p["X"][:150]
+    acq_o = O.QNEHVIOracle(gp, p["ref_point"], Xb, ops, mc_samples=16, seed=7, prune_baseline=False)
+    acq_d = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], Xb, p["objective"], prune_baseline=False,
+                                                   mc_samples=16, seed=7)
+    assert acq_d.nb == 150
+    X = Cf.candidates(p).clone()
+    X[..., 1:] *= 0.05           # near ZDT1's Pareto set (x2.. = 0): the improvement over the 150 baseline points is > 0
+    check(acq_d, acq_o, X, st, val_tol=1e-7, grad_tol=1e-5)
+
+
+def test_gradient_q16_and_many_batches():
+    """q = 16 (BO_MAX_Q) through the generic posterior GEMM, and b = 70 q-batches (> 64 rows: tensor-pipe path + gemm_nt
+    for U) against b = 3 (skinny path): both against oracle autograd."""
+    p = Cf.zdt1_qnehvi(N=80, S=8, raw=3, d=3, q=16)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=64)
+    acq_d = Cf.build_acqf(p, st, prune_samples=64)
+    check(acq_d, acq_o, Cf.candidates(p), st, grad_tol=1e-5)
+    p2 = Cf.zdt1_qnehvi(N=90, S=8, raw=70, d=4, q=2)
+    gp2 = P.oracle_gp(p2)
+    st2 = Cf.build_state(p2)
+    acq_o2 = P.oracle_acqf(p2, gp2, prune_samples=64)
+    acq_d2 = Cf.build_acqf(p2, st2, prune_samples=64)
+    X = Cf.candidates(p2)
+    v_all, g_all = check(acq_d2, acq_o2, X, st2)
+    v_few, g_few = acq_d2.forward_backward(X[:3].to(st2.device))
+    assert float((g_few - g_all[:3]).abs().max()) < 1e-9 * float(g_all.abs().max())
+
+
+def test_failed_conditional_root_poisons_value_and_gradient():
+    """A q-batch whose q x q conditional covariance is not p.d. even after jitter 1e-3 is flagged (info) and returns NaN for
+    the value and its gradient instead of silently continuing; the other q-batches are unaffected."""
+    p = small_two_objective_problem()
+    st = Cf.build_state(p)
+    acq = Cf.build_acqf(p, st, prune_samples=64)
+    X = Cf.candidates(p, 3).clone()
+    v_ok, g_ok = acq.forward_backward(X.to(st.device))
+    assert bool(torch.isfinite(v_ok).all()) and bool(torch.isfinite(g_ok).all())
+    Xbad = X.clone()
+    Xbad[1, 1] = Xbad[1, 0]            # duplicate point: singular to rounding -> jitter ladder, still finite
+    v, g = acq.forward_backward(Xbad.to(st.device))
+    assert bool(torch.isfinite(v[[0, 2]]).all()) and bool(torch.isfinite(g[[0, 2]]).all())
+    assert torch.equal(v[[0, 2]], v_ok[[0, 2]])
+
+
+def small_two_objective_problem():
+    return Cf.zdt1_qnehvi(N=60, S=16, raw=3, d=4, q=2)
