@@ -299,7 +299,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * b * args.steps / float(t_e2e[0])
-    assert np.array_equal(out_h, vals.cpu().numpy()), "host-buffer path disagrees with the device-pointer path"
+    # the host path pipelines chunks of q-batches (copy / compute overlap); chunk size changes the Gram partial-sum
+    # grouping, so the two paths agree to rounding, not bit for bit
+    ref_v = vals.cpu().numpy()
+    assert np.allclose(out_h, ref_v, rtol=1e-10, atol=1e-12 * float(np.abs(ref_v).max())), \
+        "host-buffer path disagrees with the device-pointer path"
 
     # ---- roofline of the dominant kernel (posterior GEMM), timed with CUDA events on its stream ----
     roofline = None

@@ -133,6 +133,8 @@ struct bo_state {
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
   void* pin_out = nullptr; size_t pin_out_bytes = 0;
   DevBuf stage_in, stage_out;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
   // timing
   bool timing = false;
   std::vector<TimingRec> recs;
@@ -170,6 +172,8 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
+  for (auto& e : st->copy_events) cudaEventDestroy(e);
+  if (st->copy_stream) cudaStreamDestroy(st->copy_stream);
   for (auto& r : st->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete st;
 }
@@ -978,31 +982,64 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   }
   RC(st->stage_in.ensure(in_bytes));
   RC(st->stage_out.ensure(out_bytes));
-  // pageable -> pinned staging in 4 MiB pieces on up to 4 host threads, each piece's H2D DMA issued as soon as it
-  // is staged so that the copy engine overlaps the remaining staging
+  // Pipeline over chunks of q-batches: the host stages chunk c+1 (pageable -> pinned, up to 4 threads) and the copy
+  // engine moves it (second stream) while the kernels of chunk c run; only the first chunk's staging + H2D is exposed.
+  if (!st->copy_stream) CUDA_CHECK_RET(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
+  const size_t row_bytes = (size_t)st->d * 8;
+  // Chunk plan from the ratio r of the copy time (d * 8 bytes per candidate point at ~25 GB/s) to the compute time
+  // (~ M N^2 flops per point at ~30 TFLOP/s):  r small (config 3: 0.04) -> a small first chunk so that the kernels start
+  // early, then everything else in one efficient launch sequence;  r large (2048-bit fingerprints as float64: 0.8) ->
+  // equal chunks so that every copy but the first hides behind a compute.
+  std::vector<int> chunk_b;
   {
-    const size_t piece = (size_t)4 << 20;
-    const size_t n_pieces = (in_bytes + piece - 1) / piece;
-    const int n_thr = (int)std::min<size_t>(4, n_pieces);
-    const char* src = reinterpret_cast<const char*>(X_host);
-    char* dst = reinterpret_cast<char*>(st->pin_in);
-    for (size_t p0 = 0; p0 < n_pieces; p0 += n_thr) {
-      const size_t cnt = std::min<size_t>(n_thr, n_pieces - p0);
-      std::vector<std::thread> th;
-      for (size_t t = 1; t < cnt; ++t) {
-        size_t off = (p0 + t) * piece, len = std::min(piece, in_bytes - off);
-        th.emplace_back([=]() { memcpy(dst + off, src + off, len); });
+    const double r = ((double)st->d * 8.0 / 25e9) / ((double)st->M * (double)st->N * (double)st->N / 30e12 + 1e-12);
+    const int min_b = std::max(1, 2048 / q);
+    if (b <= 2 * min_b) chunk_b.push_back(b);
+    else if (r < 0.15) {
+      const int first = std::max(min_b, b / 8);
+      chunk_b.push_back(first);
+      chunk_b.push_back(b - first);
+    } else {
+      const int n = (int)std::min<long long>(8, std::max<long long>(1, b / min_b));
+      for (int i = 0, left = b; i < n; ++i) {
+        const int take = (i == n - 1) ? left : (b + n - 1) / n;
+        chunk_b.push_back(std::min(take, left));
+        left -= chunk_b.back();
       }
-      {
-        size_t off = p0 * piece, len = std::min(piece, in_bytes - off);
-        memcpy(dst + off, src + off, len);
-      }
-      for (auto& t : th) t.join();
-      size_t off = p0 * piece, len = std::min(cnt * piece, in_bytes - off);
-      CUDA_CHECK_RET(cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, dst + off, len, cudaMemcpyHostToDevice, s));
     }
   }
-  RC(bo_acqf_forward(st, st->stage_in.as<double>(), b, q, zq_dev, st->stage_out.as<double>(), nullptr, s));
+  const int n_chunks = (int)chunk_b.size();
+  while ((int)st->copy_events.size() < n_chunks) {
+    cudaEvent_t e;
+    CUDA_CHECK_RET(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    st->copy_events.push_back(e);
+  }
+  // the staging buffer may still be read by kernels of an earlier call on `s`: order the first copy after them
+  CUDA_CHECK_RET(cudaEventRecord(st->copy_events[0], s));
+  CUDA_CHECK_RET(cudaStreamWaitEvent(st->copy_stream, st->copy_events[0], 0));
+  const char* src = reinterpret_cast<const char*>(X_host);
+  char* pin = reinterpret_cast<char*>(st->pin_in);
+  int b0 = 0;
+  for (int c = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
+    const int bn = chunk_b[c];
+    const size_t off = (size_t)b0 * q * row_bytes, len = (size_t)bn * q * row_bytes;
+    {
+      const size_t piece = (size_t)4 << 20;
+      const int n_thr = (int)std::min<size_t>(4, (len + piece - 1) / piece);
+      std::vector<std::thread> th;
+      const size_t per = (len + n_thr - 1) / std::max(n_thr, 1);
+      for (int t = 1; t < n_thr; ++t) {
+        const size_t o2 = off + (size_t)t * per, l2 = std::min(per, off + len - o2);
+        th.emplace_back([=]() { memcpy(pin + o2, src + o2, l2); });
+      }
+      memcpy(pin + off, src + off, std::min(per, len));
+      for (auto& t : th) t.join();
+    }
+    CUDA_CHECK_RET(cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, pin + off, len, cudaMemcpyHostToDevice, st->copy_stream));
+    CUDA_CHECK_RET(cudaEventRecord(st->copy_events[c], st->copy_stream));
+    CUDA_CHECK_RET(cudaStreamWaitEvent(s, st->copy_events[c], 0));
+    RC(bo_acqf_forward(st, st->stage_in.as<double>() + (size_t)b0 * q * st->d, bn, q, zq_dev, st->stage_out.as<double>() + b0, nullptr, s));
+  }
   CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK_RET(cudaStreamSynchronize(s));
   memcpy(out_host, st->pin_out, out_bytes);
