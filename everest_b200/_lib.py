@@ -89,6 +89,7 @@ SYMBOLS = {
     "bo_mll_forward_backward": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32,
                                           c_double_p, C.c_int32, C.c_void_p]),
     "bo_sobol_scramble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "bo_sobol_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bo_sobol_normal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bo_debug_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                C.c_void_p]),

@@ -49,6 +49,36 @@ __global__ void sobol_normal_kernel(const long long* __restrict__ ss, const long
   out[((size_t)s * n_points + i) * M + m] = z;
 }
 
+// uniform points out[s, dim] in [0, 1): SobolEngine.draw(S, dtype=float64) (raw samples of optimize_acqf,
+// [UPSTREAM] draw_sobol_samples)
+__global__ void sobol_uniform_kernel(const long long* __restrict__ ss, const long long* __restrict__ shift, int dim, int S,
+                                     double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)S * dim) return;
+  const int dflat = (int)(idx % dim), s = (int)(idx / dim);
+  unsigned x = (unsigned)shift[dflat];
+  unsigned gray = (unsigned)s ^ ((unsigned)s >> 1);
+  while (gray) {
+    const int b = __ffs(gray) - 1;
+    x ^= (unsigned)ss[(size_t)dflat * SOBOL_MAXBIT + b];
+    gray &= gray - 1;
+  }
+  out[idx] = (s == 0) ? (double)(__uint2float_rn(x) * 9.313225746154785e-10f) : (double)x * 9.313225746154785e-10;
+}
+
+extern "C" int bo_sobol_uniform(const int64_t* sobolstate_dev, const int64_t* shift_dev, int32_t dim, int32_t S,
+                                double* out_dev, void* stream) {
+  if (!sobolstate_dev || !shift_dev || !out_dev || dim < 1 || S < 1 || S > (1 << SOBOL_MAXBIT)) {
+    bo_set_error("sobol_uniform: bad arguments");
+    return BO_ERR_INVALID;
+  }
+  const long long n = (long long)S * dim;
+  sobol_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(sobolstate_dev), reinterpret_cast<const long long*>(shift_dev), dim, S, out_dev);
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 extern "C" int bo_sobol_scramble(int64_t* sobolstate_dev, const int64_t* ltm_rows_dev, int32_t dim, void* stream) {
   if (!sobolstate_dev || !ltm_rows_dev || dim < 1) { bo_set_error("sobol_scramble: bad arguments"); return BO_ERR_INVALID; }
   const long long n = (long long)dim * SOBOL_MAXBIT;

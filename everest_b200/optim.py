@@ -20,9 +20,14 @@ from scipy.optimize import minimize  # imported up front: the first import costs
 from . import sampling
 
 
-def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None) -> torch.Tensor:
-    """[UPSTREAM] botorch.utils.sampling.draw_sobol_samples: [n, q, d] inside bounds [2, d]."""
+def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None, device=None) -> torch.Tensor:
+    """[UPSTREAM] botorch.utils.sampling.draw_sobol_samples: [n, q, d] inside bounds [2, d].  With a CUDA `device` the
+    points are generated there (csrc/sobol.cu, bit-identical to torch's engine for the same seed)."""
     d = bounds.shape[-1]
+    if device is not None and torch.device(device).type == "cuda" and seed is not None:
+        u = sampling.sobol_uniform_device(q * d, n, int(seed), device).view(n, q, d)
+        lo, hi = bounds[0].to(u), bounds[1].to(u)
+        return lo + (hi - lo) * u
     eng = torch.quasirandom.SobolEngine(q * d, scramble=True, seed=seed)
     u = eng.draw(n, dtype=torch.double).view(n, q, d)
     lo, hi = bounds[0].to(torch.double), bounds[1].to(torch.double)
@@ -206,11 +211,15 @@ def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num
                                                seed=seed, n_burnin=options.get("n_burnin", 10000),
                                                n_thinning=options.get("thinning", 32), fixed_features=fixed_features)
     else:
-        X_rnd = apply_fixed_features(draw_sobol_samples(bounds, raw_samples, q, seed=seed), fixed_features)
+        # raw samples are drawn where they are scored: no host Sobol draw, no H2D of raw_samples * q * d doubles
+        dev = acq_function.model.device
+        X_rnd = apply_fixed_features(draw_sobol_samples(bounds, raw_samples, q, seed=seed,
+                                                        device=dev if torch.device(dev).type == "cuda" else None),
+                                     fixed_features)
     with torch.no_grad():
         Y_rnd = acq_function(X_rnd.to(acq_function.model.device))
     X_ic, idcs = initialize_q_batch(X_rnd, Y_rnd, n=num_restarts, eta=options.get("eta", 2.0))
-    return X_ic, Y_rnd.cpu()[idcs], X_rnd, Y_rnd
+    return X_ic.cpu(), Y_rnd.cpu()[idcs], X_rnd, Y_rnd
 
 
 def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function, lower_bounds, upper_bounds,

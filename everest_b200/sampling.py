@@ -63,3 +63,20 @@ def base_samples_device(n_points: int, n_outputs: int, n_samples: int, seed: int
         L.check(lib.bo_sobol_normal(C.c_void_p(ss_d.data_ptr()), C.c_void_p(shift_d.data_ptr()), n_points, n_outputs,
                                     n_samples, C.c_void_p(out.data_ptr()), stream))
     return out
+
+
+def sobol_uniform_device(dim: int, n: int, seed: int, device) -> torch.Tensor:
+    """SobolEngine(dim, scramble=True, seed).draw(n, dtype=float64) on `device`, bit-identical to torch's engine."""
+    from . import _lib as L
+
+    device = torch.device(device)
+    ss, shift, rows = sobol_scramble_inputs(dim, seed)
+    lib = L.load()
+    ss_d, shift_d, rows_d = ss.to(device), shift.to(device), rows.to(device)
+    out = torch.empty(n, dim, dtype=torch.double, device=device)
+    with torch.cuda.device(device):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(lib.bo_sobol_scramble(C.c_void_p(ss_d.data_ptr()), C.c_void_p(rows_d.data_ptr()), dim, stream))
+        L.check(lib.bo_sobol_uniform(C.c_void_p(ss_d.data_ptr()), C.c_void_p(shift_d.data_ptr()), dim, n,
+                                     C.c_void_p(out.data_ptr()), stream))
+    return out

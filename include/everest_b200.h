@@ -220,6 +220,10 @@ int bo_mll_forward_backward(bo_state* st, int32_t m, double* mll_out, double* d_
 int bo_sobol_scramble(int64_t* sobolstate_dev, const int64_t* ltm_rows_dev, int32_t dim, void* stream);
 int bo_sobol_normal(const int64_t* sobolstate_dev, const int64_t* shift_dev, int32_t n_points, int32_t M, int32_t S,
                     double* out_dev, void* stream);
+/* Uniform points out[S, dim] = SobolEngine(dim, scramble=True, seed).draw(S, dtype=float64): the raw samples of
+ * optimize_acqf ([UPSTREAM] draw_sobol_samples, reached from botorch.py:384-405), bit-identical to torch's engine. */
+int bo_sobol_uniform(const int64_t* sobolstate_dev, const int64_t* shift_dev, int32_t dim, int32_t S, double* out_dev,
+                     void* stream);
 
 /* Introspection for tests: copies internal device buffers to the given device pointers. */
 int bo_debug_get(bo_state* st, const char* name, int32_t m, double* out_dev, int64_t capacity, int64_t* n_written,

@@ -97,3 +97,10 @@ def test_device_base_samples_match_the_host_engine():
         assert float(diff.max()) < 1e-9, float(diff.max())
         assert float(diff[zh.abs() < 3.0].max()) < 1e-13, float(diff[zh.abs() < 3.0].max())
     assert sampling.base_samples_device(0, 2, 8, 1, "cuda:0").shape == (8, 0, 2)
+    # uniform raw samples of optimize_acqf: bit-identical to the host engine (including torch's float32 first point)
+    for dim, n, seed in [(1, 5, 0), (120, 257, 7), (960, 64, 123)]:
+        u_h = torch.quasirandom.SobolEngine(dim, scramble=True, seed=seed).draw(n, dtype=DT)
+        u_d = sampling.sobol_uniform_device(dim, n, seed, "cuda:0").cpu()
+        assert torch.equal(u_d, u_h)
+    b_ = torch.tensor([[0.0, -1.0, 2.0], [1.0, 1.0, 5.0]], dtype=DT)
+    assert torch.equal(optim.draw_sobol_samples(b_, 33, 2, seed=4, device="cuda:0").cpu(), optim.draw_sobol_samples(b_, 33, 2, seed=4))
