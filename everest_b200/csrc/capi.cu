@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <map>
 #include <string>
@@ -92,6 +94,8 @@ struct OutputH {
   DevBuf L, Linv, LinvT, LinvExt, alpha_row, dinv, resid, tvec;
   DevBuf Kinv;  // (K + s2 I)^-1, built lazily by the first backward pass
   bool kinv_ready = false;
+  DevBuf ozB, ozScaleB;  // INT8 digit planes of LinvExt + per-row scales (ozaki.cu), rebuilt when LinvExt changes
+  bool oz_ready = false;
   int Rpad = 0;  // rows of LinvExt
   double jitter = 0.0;
   // acquisition state
@@ -124,7 +128,9 @@ struct bo_state {
   bool noisy_scalar = false;   // qNEI / qLogNEI: per-sample incumbent in best_f_s
   DevBuf best_f_s;
   int log_hvi = 0;
+  int ozaki = 0;               // posterior GEMM of large batches on the INT8 tensor cores (ozaki.cu)
   double tau_relu = 1e-6, tau_max = 1e-2;
+  DevBuf wsOzA;  // INT8 digit planes of K(X*,X) (all outputs)
   DevBuf wsDF, wsDRoot, wsDMu, wsEG, wsEW, wsEmu, wsU;  // adjoint workspaces (grad.cu)
   DevBuf wsGramPart, wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
@@ -161,14 +167,14 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (auto& o : st->out) {
     for (void* p : o.owned) cudaFree(p);
     o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
-    DevBuf* bs[] = {&o.Kinv, &o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
+    DevBuf* bs[] = {&o.ozB, &o.ozScaleB, &o.Kinv, &o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
     for (DevBuf* b : bs) b->release();
   }
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s};
+                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
@@ -191,6 +197,7 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
   }
   bo_state* st = new bo_state();
   st->N = cfg->N; st->d = cfg->d; st->M = cfg->M;
+  { const char* e = getenv("EVEREST_OZAKI"); st->ozaki = (e && e[0] == '1') ? 1 : 0; }
   st->ldk = round_up(cfg->N, 16);
   st->Nr = round_up(cfg->N, 128);
   const int N = cfg->N, d = cfg->d;
@@ -319,6 +326,7 @@ static int psd_safe_chol(bo_state* st, const double* src, double* dst, int ld, i
 static int build_linv_ext(bo_state* st, OutputH& o, int nb, cudaStream_t s) {
   const int N = st->N, ldk = st->ldk;
   o.Rpad = round_up(N + 1 + nb, 128);
+  o.oz_ready = false;
   RC(o.LinvExt.ensure((size_t)o.Rpad * ldk * 8, true));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.p, o.Linv.p, (size_t)N * ldk * 8, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.as<double>() + (size_t)N * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
@@ -722,7 +730,9 @@ extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t
 extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) {
   if (!st || !name) { bo_set_error("null argument"); return BO_ERR_INVALID; }
   std::string nm(name);
-  if (nm == "log_hvi") {
+  if (nm == "ozaki") {
+    st->ozaki = value != 0.0;
+  } else if (nm == "log_hvi") {
     if (st->acqf_kind != 1 && st->acqf_kind != 2) { bo_set_error("log_hvi applies to a prepared qNEHVI / qEHVI"); return BO_ERR_STATE; }
     st->log_hvi = value != 0.0;
   } else if (nm == "tau_relu") {
@@ -810,10 +820,43 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
     const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
+    const bool use_ozaki = st->ozaki && !small_rows && (q == 1 || q == 2 || q == 4 || q == 8);
     if (small_rows) {
       RC(st->wsV.ensure(posterior_small_ws_doubles(rows, st->out[0].Rpad, M) * 8));
       rec_begin(st, "posterior_gemm", s);
       RC(launch_posterior_small(pg.data(), M, st->wsV.as<double>(), s, &st->lc));
+      rec_end(st, s);
+    } else if (use_ozaki) {
+      // FP64-accurate GEMM on the INT8 tensor cores: digit planes of K(X*,X) (every call) and of LinvExt (once)
+      const int rows_alloc = round_up(rows, 128);
+      const size_t pa = ozaki_plane_bytes(rows_alloc, ldk);
+      RC(st->wsOzA.ensure(pa * M));
+      RC(st->wsGramPart.ensure(ozaki_partial_ws_doubles(rows, q, M) * 8));
+      std::vector<OzakiArgs> oa(M);
+      rec_begin(st, "ozaki_slice", s);
+      for (int m = 0; m < M; ++m) {
+        OutputH& o = st->out[m];
+        if (!o.oz_ready) {
+          RC(o.ozScaleB.ensure((size_t)o.Rpad * 8));
+          RC(o.ozB.ensure(ozaki_plane_bytes(o.Rpad, ldk)));
+          RC(launch_ozaki_row_scale(o.LinvExt.as<double>(), o.Rpad, st->N, ldk, o.ozScaleB.as<double>(), s, &st->lc));
+          RC(launch_ozaki_slice(o.LinvExt.as<double>(), o.Rpad, st->N, ldk, o.ozScaleB.as<double>(), 0.0,
+                                o.ozB.as<signed char>(), o.Rpad, ldk, s, &st->lc));
+          o.oz_ready = true;
+        }
+        double kmax = 0.0;
+        for (int t = 0; t < o.md.n_terms; ++t) kmax += fabs(o.md.coef[t]);   // every leaf is <= 1
+        const double scaleA = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
+        signed char* Ap = st->wsOzA.as<signed char>() + (size_t)m * pa;
+        RC(launch_ozaki_slice(pg[m].Kx, rows, st->N, ldk, nullptr, scaleA, Ap, rows_alloc, ldk, s, &st->lc));
+        OzakiArgs& a = oa[m];
+        a.Aplanes = Ap; a.rows = rows; a.rows_alloc = rows_alloc; a.ldk = ldk; a.Bplanes = o.ozB.as<signed char>();
+        a.scaleB = o.ozScaleB.as<double>(); a.scaleA = scaleA; a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad; a.q = q;
+        a.Gqq = pg[m].Gqq; a.W = pg[m].W; a.ldw = ldw; a.mu_raw = pg[m].mu_raw;
+      }
+      rec_end(st, s);
+      rec_begin(st, "posterior_gemm", s);
+      RC(launch_ozaki_gemm(oa.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
       rec_end(st, s);
     } else {
       size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);

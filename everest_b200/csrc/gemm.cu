@@ -524,6 +524,14 @@ __global__ void sum_gram_partials_kernel(const double* __restrict__ part, long l
   out[i] = t;
 }
 
+int launch_sum_gram_partials(const double* part, long long stride, int groups, double* out, cudaStream_t s, LaunchCounter* lc) {
+  if (stride <= 0) return BO_OK;
+  sum_gram_partials_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, s>>>(part, stride, groups, stride, out);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -1,0 +1,447 @@
+// FP64-accurate posterior GEMM on the 5th-generation tensor cores (tcgen05.mma.kind::i8, accumulators in TMEM):
+// Ozaki-style error-free splitting of V = K(X*,X) LinvExt^T.
+//
+// Every operand row is scaled by a power of two and written as a 56-bit fixed-point number in SEVEN balanced base-256
+// digits d_p in [-128, 127] (x = s * 2^-55 * sum_p d_p 256^p, |x / s| < 0.498).  A product of two digit planes is an exact
+// INT8 x INT8 -> INT32 GEMM (|d d'| <= 2^14, K <= 2^11 per tile, <= 7 pairs per accumulator: < 2^28); the 28 plane pairs
+// with p + p' >= 6 are accumulated on SEVEN weight levels (p + p' = 6 .. 12), each level in its own TMEM accumulator
+// (7 x 64 columns of the 512), and recombined in FP64 in the epilogue:
+//     V[r][n] = sA * sB[n] * 2^-14 * sum_L acc_L[r][n] * 2^(8 (L - 12)).
+// The dropped pairs (p + p' <= 5) are random-signed and below 2^-51 of sA * sB: ~10x the rounding of a DGEMM, far inside
+// the 1e-9 posterior bar.  Same outputs as posterior_gemm_tma_kernel: Gram V_q V_q^T per q-batch (partial
+// sums per column group), mu_raw and W = V_q V_b^T from the extra columns.
+//
+// Tile: 128 candidate rows x 64 columns per CTA pass (TMEM capacity: 128 lanes x 512 columns of INT32), K in blocks of 64
+// bytes.  One warp issues TMA (two 4-D boxes per K block: all 7 planes of A and of B), one warp issues the 56 MMAs of the
+// block, four warps form the epilogue (tcgen05.ld, FP64 recombination, shuffle Gram).  Operand tiles are K-major in the
+// canonical no-swizzle layout [plane][16-byte K chunk][row][16 B], which is exactly how the planes are stored in HBM, so
+// a TMA box lands in shared memory ready for the UMMA descriptors.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+#define OZ_PLANES 7
+#define OZ_LEVELS 7
+#define OZ_BM 128
+#define OZ_BN 64
+#define OZ_BK 64                      // bytes of K per block = 4 chunks of 16 B = 2 MMAs of K = 32
+#define OZ_CH (OZ_BK / 16)
+#define OZ_ST 2
+#define OZ_A_PLANE (OZ_CH * OZ_BM * 16)      // 8192 B
+#define OZ_B_PLANE (OZ_CH * OZ_BN * 16)      // 4096 B
+#define OZ_A_BYTES (OZ_PLANES * OZ_A_PLANE)  // 57344
+#define OZ_B_BYTES (OZ_PLANES * OZ_B_PLANE)  // 28672
+#define OZ_STAGE_BYTES (OZ_A_BYTES + OZ_B_BYTES)
+#define OZ_THREADS 192                // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+#define OZ_MAXOUT 8
+#define OZ_MAXGROUPS 16
+
+// ------------------------------------------------------------------------------------------------
+// slicing: FP64 rows -> 7 balanced base-256 digit planes, layout [plane][K chunk][row][16 B]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_digits(double x_over_s, signed char* d) {
+  long long I = __double2ll_rn(x_over_s * 36028797018963968.0);  // 2^55, exact scaling; |I| < 0.498 * 2^55
+#pragma unroll
+  for (int p = 0; p < OZ_PLANES - 1; ++p) {
+    const long long dig = ((I + 128) & 0xFF) - 128;
+    d[p] = (signed char)dig;
+    I = (I - dig) >> 8;
+  }
+  d[OZ_PLANES - 1] = (signed char)I;
+}
+
+// per-row power-of-two scale: smallest 2^e with max|row| / 2^e < 0.49
+__global__ void __launch_bounds__(256)
+oz_row_scale_kernel(const double* __restrict__ X, int rows, int cols, int ld, double* __restrict__ scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  double mx = 0.0;
+  for (int k = lane; k < cols; k += 32) mx = fmax(mx, fabs(X[(size_t)warp * ld + k]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    double s = 1.0;
+    if (mx > 0.0) {
+      int e;
+      frexp(mx, &e);              // mx = f * 2^e, f in [0.5, 1)
+      s = ldexp(1.0, e + 2);      // mx / s < 0.25 <= 0.49
+    }
+    scale[warp] = s;
+  }
+}
+
+// X [rows, ld] (cols valid, zero beyond) -> planes; row_scale == nullptr: global scale `gscale`
+__global__ void __launch_bounds__(256)
+oz_slice_kernel(const double* __restrict__ X, int rows, int cols, int ld, const double* __restrict__ row_scale, double gscale,
+                signed char* __restrict__ planes, int rows_alloc, int n_chunks) {
+  // thread = (row, 16-byte chunk): reads 16 doubles, writes 16 B to each plane
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(idx % rows_alloc), c = (int)(idx / rows_alloc);
+  if (c >= n_chunks) return;
+  signed char dig[OZ_PLANES][16];
+  const double inv = (r < rows) ? 1.0 / (row_scale ? row_scale[r] : gscale) : 0.0;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int k = c * 16 + t;
+    const double v = (r < rows && k < cols) ? X[(size_t)r * ld + k] * inv : 0.0;
+    signed char d[OZ_PLANES];
+    split_digits(v, d);
+#pragma unroll
+    for (int p = 0; p < OZ_PLANES; ++p) dig[p][t] = d[p];
+  }
+  const size_t plane_stride = (size_t)n_chunks * rows_alloc * 16;
+#pragma unroll
+  for (int p = 0; p < OZ_PLANES; ++p) {
+    int4 w;
+    memcpy(&w, dig[p], 16);
+    *reinterpret_cast<int4*>(planes + p * plane_stride + ((size_t)c * rows_alloc + r) * 16) = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 GEMM
+// ------------------------------------------------------------------------------------------------
+struct alignas(128) OzItem {
+  CUtensorMap mapA;          // planes of K(X*,X): dims {rows_alloc * 16 B as u64, chunks, 7}
+  CUtensorMap mapB;          // planes of LinvExt
+  const double* scaleB;      // [Rpad] per-row scale of LinvExt
+  double scaleA;             // global scale of K(X*,X)
+  double* gqq_part;          // [groups][b, q, q]
+  double* W;                 // [rows, ldw] or null
+  double* mu_raw;            // [rows]
+};
+struct OzBatch {
+  OzItem item[OZ_MAXOUT];
+  int rows, q, N, n_ext, Rpad, ldw, n_chunks_k;   // n_chunks_k = ldk / 16
+  int n_groups;
+  int gbeg[OZ_MAXGROUPS + 1];                     // column-tile ranges (units of OZ_BN columns)
+  long long gqq_stride;
+};
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void oz_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_NONE canonical layout ((8, m), 2) : ((16 B, SBO), LBO)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzBatch batch) {
+  extern __shared__ unsigned char ozraw[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bars[2 * OZ_ST + 2];   // full[ST], empty[ST], acc_full, acc_empty
+  const OzItem& item = batch.item[blockIdx.y];
+  const uint32_t base = (oz_smem_u32(ozraw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = (int)(blockIdx.x % batch.n_groups), row_tile = (int)(blockIdx.x / batch.n_groups);
+  const int row0 = row_tile * OZ_BM;
+  const int jt_begin = batch.gbeg[grp], jt_end = batch.gbeg[grp + 1];
+  const uint32_t full0 = oz_smem_u32(&bars[0]), empty0 = oz_smem_u32(&bars[OZ_ST]);
+  const uint32_t acc_full = oz_smem_u32(&bars[2 * OZ_ST]), acc_empty = oz_smem_u32(&bars[2 * OZ_ST + 1]);
+  if (tid == 0) {
+    for (int s = 0; s < OZ_ST; ++s) { oz_mbar_init(full0 + 8 * s, 1); oz_mbar_init(empty0 + 8 * s, 1); }
+    oz_mbar_init(acc_full, 1);
+    oz_mbar_init(acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  // K blocks of a column tile: purely triangular tiles (all 64 rows of L^-1 below N) stop at their last row
+  auto k_blocks_of = [&](int jt) {
+    const int n_end = (jt + 1) * OZ_BN;
+    const int kbytes = (n_end <= batch.N) ? n_end : batch.n_chunks_k * 16;
+    return (min(kbytes, batch.n_chunks_k * 16) + OZ_BK - 1) / OZ_BK;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int it = 0;
+      for (int jt = jt_begin; jt < jt_end; ++jt) {
+        const int nkb = k_blocks_of(jt);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % OZ_ST;
+          const uint32_t ph = (uint32_t)((it / OZ_ST) & 1);
+          oz_mbar_wait(empty0 + 8 * s, ph ^ 1u);          // first use of a stage passes immediately
+          const uint32_t fb = full0 + 8 * s;
+          oz_mbar_expect_tx(fb, OZ_STAGE_BYTES);
+          const uint32_t dst = base + (uint32_t)s * OZ_STAGE_BYTES;
+          oz_tma_load_3d(dst, &item.mapA, row0 * 2, kb * OZ_CH, 0, fb);              // inner coordinate in 8-byte units
+          oz_tma_load_3d(dst + OZ_A_BYTES, &item.mapB, jt * OZ_BN * 2, kb * OZ_CH, 0, fb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      uint32_t idesc = 0;
+      idesc |= 2u << 4;                       // D = S32
+      idesc |= 1u << 7;                       // A signed 8 bit
+      idesc |= 1u << 10;                      // B signed 8 bit
+      idesc |= (uint32_t)(OZ_BN >> 3) << 17;
+      idesc |= (uint32_t)(OZ_BM >> 4) << 24;
+      int it = 0, tile = 0;
+      for (int jt = jt_begin; jt < jt_end; ++jt, ++tile) {
+        const int nkb = k_blocks_of(jt);
+        // the epilogue must have drained the accumulators of the previous tile
+        oz_mbar_wait(acc_empty, (uint32_t)((tile & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % OZ_ST;
+          const uint32_t ph = (uint32_t)((it / OZ_ST) & 1);
+          oz_mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t sa = base + (uint32_t)s * OZ_STAGE_BYTES, sb = sa + OZ_A_BYTES;
+          unsigned started = (kb == 0) ? 0u : 0x7Fu;
+#pragma unroll 1
+          for (int pa = OZ_PLANES - 1; pa >= 0; --pa) {
+#pragma unroll 1
+            for (int pb = OZ_PLANES - 1; pb >= 6 - pa; --pb) {
+              const int lvl = pa + pb - 6;
+              const uint32_t tcol = tmem_base + (uint32_t)(lvl * OZ_BN);
+#pragma unroll
+              for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+                const uint64_t da = oz_desc(sa + pa * OZ_A_PLANE + ks * 2 * (OZ_BM * 16), OZ_BM * 16, 128);
+                const uint64_t db = oz_desc(sb + pb * OZ_B_PLANE + ks * 2 * (OZ_BN * 16), OZ_BN * 16, 128);
+                oz_mma_i8(tcol, da, db, idesc, (started >> lvl) & 1u);
+                started |= 1u << lvl;
+              }
+            }
+          }
+          oz_commit(empty0 + 8 * s);          // the stage is free once these MMAs have read it
+        }
+        oz_commit(acc_full);                  // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+    const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;
+    const int row = row0 + r_local;
+    const int q = batch.q;
+    const int lane_base = lane & ~(q - 1);
+    double g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.0;
+    const double sA = item.scaleA * 6.103515625e-05;   // 2^-14
+    int tile = 0;
+    for (int jt = jt_begin; jt < jt_end; ++jt, ++tile) {
+      oz_mbar_wait(acc_full, (uint32_t)(tile & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int n0 = jt * OZ_BN;
+      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        double s[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s[c] = 0.0;
+#pragma unroll
+        for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          const double wl = ldexp(1.0, 8 * (lvl - 6));    // level L = lvl + 6: 2^(8 (L - 12))
+#pragma unroll
+          for (int c = 0; c < 16; ++c) s[c] = fma((double)(int)v[c], wl, s[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int n = n0 + c0 + c;
+          const double val = s[c] * (sA * item.scaleB[n]);
+          if (n < batch.N) {
+            // Gram of the q-batch: this thread owns row i of G, partners are the q lanes of its group
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < q) g[j] = fma(val, __shfl_sync(0xffffffffu, val, lane_base + j), g[j]);
+          } else {
+            const int e = n - batch.N;
+            if (row < batch.rows) {
+              if (e == 0) item.mu_raw[row] = val;
+              else if (item.W && e < batch.n_ext) item.W[(size_t)row * batch.ldw + (e - 1)] = val;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      oz_mbar_arrive(acc_empty);
+    }
+    if (row < batch.rows) {
+      double* dst = item.gqq_part + (size_t)grp * batch.gqq_stride + ((size_t)(row / q) * q + (row % q)) * q;
+      for (int j = 0; j < q; ++j) dst[j] = g[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiledOz)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int oz_make_map(CUtensorMap* map, const signed char* planes, int rows_alloc, int n_chunks, int box_rows) {
+  static PFN_encodeTiledOz fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      bo_set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+      return BO_ERR_CUDA;
+    }
+    fn = reinterpret_cast<PFN_encodeTiledOz>(p);
+  }
+  // The [row][16 B] slab of one (plane, K chunk) is contiguous: describe it as ONE inner dimension of 8-byte elements so
+  // that a box row is a 1-2 KB contiguous request (a 16-byte inner dimension makes the TMA unit issue 16-byte requests and
+  // caps the fill rate at ~13 B/clk per SM).
+  cuuint64_t dims[3] = {(cuuint64_t)rows_alloc * 2, (cuuint64_t)n_chunks, OZ_PLANES};
+  cuuint64_t strides[2] = {(cuuint64_t)rows_alloc * 16, (cuuint64_t)n_chunks * rows_alloc * 16};
+  cuuint32_t box[3] = {(cuuint32_t)box_rows * 2, OZ_CH, OZ_PLANES};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<signed char*>(planes), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { bo_set_error("cuTensorMapEncodeTiled (int8 planes) failed (%d)", (int)r); return BO_ERR_CUDA; }
+  return BO_OK;
+}
+
+size_t ozaki_plane_bytes(int rows_alloc, int ldk) { return (size_t)OZ_PLANES * (ldk / 16) * rows_alloc * 16; }
+
+int launch_ozaki_row_scale(const double* X, int rows, int cols, int ld, double* scale, cudaStream_t s, LaunchCounter* lc) {
+  if (rows <= 0) return BO_OK;
+  oz_row_scale_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(X, rows, cols, ld, scale);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+int launch_ozaki_slice(const double* X, int rows, int cols, int ld, const double* row_scale, double gscale, signed char* planes,
+                       int rows_alloc, int ldk, cudaStream_t s, LaunchCounter* lc) {
+  const int n_chunks = ldk / 16;
+  const long long n = (long long)rows_alloc * n_chunks;
+  if (n <= 0) return BO_OK;
+  oz_slice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, rows, cols, ld, row_scale, gscale, planes, rows_alloc, n_chunks);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_out * OZ_MAXGROUPS * rows * q; }
+
+int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStream_t s, LaunchCounter* lc) {
+  if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
+  const OzakiArgs& a0 = args[0];
+  if (!(a0.q == 1 || a0.q == 2 || a0.q == 4 || a0.q == 8) || a0.rows % a0.q) { bo_set_error("ozaki_gemm: q must be 1, 2, 4 or 8"); return BO_ERR_INVALID; }
+  if (a0.ldk % 16 || a0.Rpad % OZ_BN || !part_ws) { bo_set_error("ozaki_gemm: padding / workspace violated"); return BO_ERR_INVALID; }
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  static bool attr_set = false;
+  const size_t smem = (size_t)OZ_ST * OZ_STAGE_BYTES + 1024;
+  if (!attr_set) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
+  const int n_tiles = a0.Rpad / OZ_BN;
+  // column groups: resident K(X*,X) digit panels (n_sm / G panels of 7 * 128 * ldk bytes) should stay in L2 (~40 MB)
+  int groups;
+  {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("EVEREST_OZAKI_GROUPS"); forced = e ? atoi(e) : -1; }
+    const double panel_mb = (double)OZ_PLANES * OZ_BM * a0.ldk / (1 << 20);
+    groups = (int)((n_sm * panel_mb + 39.0) / 40.0);
+    if (forced >= 1) groups = forced;
+    groups = std::max(1, std::min(groups, std::min(n_tiles, OZ_MAXGROUPS)));
+  }
+  for (int m0 = 0; m0 < n_out; m0 += OZ_MAXOUT) {
+    const int cnt = std::min(OZ_MAXOUT, n_out - m0);
+    OzBatch batch;
+    memset(&batch, 0, sizeof(batch));
+    batch.rows = a0.rows; batch.q = a0.q; batch.N = a0.N; batch.n_ext = a0.n_ext; batch.Rpad = a0.Rpad; batch.ldw = a0.ldw;
+    batch.n_chunks_k = a0.ldk / 16; batch.n_groups = groups; batch.gqq_stride = (long long)a0.rows * a0.q;
+    {
+      std::vector<long long> pre(n_tiles + 1, 0);
+      for (int jt = 0; jt < n_tiles; ++jt) {
+        const int n_end = (jt + 1) * OZ_BN;
+        const int kbytes = (n_end <= a0.N) ? n_end : a0.ldk;
+        pre[jt + 1] = pre[jt] + (std::min(kbytes, a0.ldk) + OZ_BK - 1) / OZ_BK;
+      }
+      batch.gbeg[0] = 0;
+      for (int g = 1; g < groups; ++g) {
+        long long target = pre[n_tiles] * g / groups;
+        int jt = batch.gbeg[g - 1] + 1;
+        while (jt < n_tiles - (groups - g) && pre[jt] < target) ++jt;
+        batch.gbeg[g] = jt;
+      }
+      batch.gbeg[groups] = n_tiles;
+    }
+    for (int i = 0; i < cnt; ++i) {
+      const OzakiArgs& a = args[m0 + i];
+      int rc;
+      if ((rc = oz_make_map(&batch.item[i].mapA, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM)) != BO_OK) return rc;
+      if ((rc = oz_make_map(&batch.item[i].mapB, a.Bplanes, a.Rpad, a.ldk / 16, OZ_BN)) != BO_OK) return rc;
+      batch.item[i].scaleB = a.scaleB; batch.item[i].scaleA = a.scaleA;
+      batch.item[i].gqq_part = part_ws + (size_t)(m0 + i) * groups * batch.gqq_stride;
+      batch.item[i].W = a.W; batch.item[i].mu_raw = a.mu_raw;
+    }
+    dim3 grid(row_tiles * groups, cnt);
+    ozaki_gemm_kernel<<<grid, OZ_THREADS, smem, s>>>(batch);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    for (int i = 0; i < cnt; ++i) {
+      int rc = launch_sum_gram_partials(batch.item[i].gqq_part, batch.gqq_stride, groups, args[m0 + i].Gqq, s, lc);
+      if (rc != BO_OK) return rc;
+    }
+  }
+  return BO_OK;
+}
