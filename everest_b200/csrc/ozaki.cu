@@ -237,19 +237,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
           oz_mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t sa = base + (uint32_t)s * OZ_STAGE_BYTES, sb = sa + OZ_A_BYTES;
-          unsigned started = (kb == 0) ? 0u : 0x7Fu;
-#pragma unroll 1
+          // descriptors differ only in the 14-bit start-address field: one base per operand, compile-time offsets
+          // (the issuing thread must deliver one MMA every ~48 clocks)
+          const uint64_t dA0 = oz_desc(sa, OZ_BM * 16, 128), dB0 = oz_desc(sb, OZ_BN * 16, 128);
+          const uint32_t acc0 = (kb > 0) ? 1u : 0u;
+#pragma unroll
           for (int pa = OZ_PLANES - 1; pa >= 0; --pa) {
-#pragma unroll 1
-            for (int pb = OZ_PLANES - 1; pb >= 6 - pa; --pb) {
+#pragma unroll
+            for (int pb = OZ_PLANES - 1; pb >= 0; --pb) {
+              if (pa + pb < 6) continue;
               const int lvl = pa + pb - 6;
-              const uint32_t tcol = tmem_base + (uint32_t)(lvl * OZ_BN);
+              // with pa descending from 6 the first pair of every level is (6, L - 6)
+              const bool first = (pa == OZ_PLANES - 1);
 #pragma unroll
               for (int ks = 0; ks < OZ_BK / 32; ++ks) {
-                const uint64_t da = oz_desc(sa + pa * OZ_A_PLANE + ks * 2 * (OZ_BM * 16), OZ_BM * 16, 128);
-                const uint64_t db = oz_desc(sb + pb * OZ_B_PLANE + ks * 2 * (OZ_BN * 16), OZ_BN * 16, 128);
-                oz_mma_i8(tcol, da, db, idesc, (started >> lvl) & 1u);
-                started |= 1u << lvl;
+                const uint64_t da = dA0 + (uint64_t)((pa * OZ_A_PLANE + ks * 2 * (OZ_BM * 16)) >> 4);
+                const uint64_t db = dB0 + (uint64_t)((pb * OZ_B_PLANE + ks * 2 * (OZ_BN * 16)) >> 4);
+                oz_mma_i8(tmem_base + (uint32_t)(lvl * OZ_BN), da, db, idesc, (first && ks == 0) ? acc0 : 1u);
               }
             }
           }
@@ -275,21 +279,24 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int n0 = jt * OZ_BN;
       for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-        double s[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) s[c] = 0.0;
+        uint32_t v[OZ_LEVELS][16];
 #pragma unroll
         for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) {
-          uint32_t v[16];
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + c0);
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "=r"(v[lvl][0]), "=r"(v[lvl][1]), "=r"(v[lvl][2]), "=r"(v[lvl][3]), "=r"(v[lvl][4]), "=r"(v[lvl][5]),
+                         "=r"(v[lvl][6]), "=r"(v[lvl][7]), "=r"(v[lvl][8]), "=r"(v[lvl][9]), "=r"(v[lvl][10]), "=r"(v[lvl][11]),
+                         "=r"(v[lvl][12]), "=r"(v[lvl][13]), "=r"(v[lvl][14]), "=r"(v[lvl][15])
                        : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          const double wl = ldexp(1.0, 8 * (lvl - 6));    // level L = lvl + 6: 2^(8 (L - 12))
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        double s[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) s[c] = fma((double)(int)v[c], wl, s[c]);
+        for (int c = 0; c < 16; ++c) {
+          double acc = 0.0;
+#pragma unroll
+          for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) acc = fma((double)(int)v[lvl][c], ldexp(1.0, 8 * (lvl - 6)), acc);
+          s[c] = acc;
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
