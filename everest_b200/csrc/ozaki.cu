@@ -37,7 +37,8 @@
 #define OZ_A_BYTES (OZ_PLANES * OZ_A_PLANE)  // 57344
 #define OZ_B_BYTES (OZ_PLANES * OZ_B_PLANE)  // 28672
 #define OZ_STAGE_BYTES (OZ_A_BYTES + OZ_B_BYTES)
-#define OZ_THREADS 192                // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+#define OZ_THREADS 320                // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+#define OZ_EPI_THREADS 256
 #define OZ_MAXOUT 8
 #define OZ_MAXGROUPS 16
 
@@ -118,6 +119,7 @@ struct OzBatch {
   OzItem item[OZ_MAXOUT];
   int rows, q, N, n_ext, Rpad, ldw, n_chunks_k;   // n_chunks_k = ldk / 16
   int n_groups;
+  int dbg;                                        // EVEREST_OZAKI_DBG bits: 1 = no MMAs, 2 = no epilogue math (timing experiments)
   int gbeg[OZ_MAXGROUPS + 1];                     // column-tile ranges (units of OZ_BN columns)
   long long gqq_stride;
 };
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   extern __shared__ unsigned char ozraw[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bars[2 * OZ_ST + 2];   // full[ST], empty[ST], acc_full, acc_empty
+  __shared__ double sB_s[8][32];                          // per-epilogue-warp column scales of the current tile
   const OzItem& item = batch.item[blockIdx.y];
   const uint32_t base = (oz_smem_u32(ozraw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < OZ_ST; ++s) { oz_mbar_init(full0 + 8 * s, 1); oz_mbar_init(empty0 + 8 * s, 1); }
     oz_mbar_init(acc_full, 1);
-    oz_mbar_init(acc_empty, 128);
+    oz_mbar_init(acc_empty, OZ_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
           // (the issuing thread must deliver one MMA every ~48 clocks)
           const uint64_t dA0 = oz_desc(sa, OZ_BM * 16, 128), dB0 = oz_desc(sb, OZ_BN * 16, 128);
           const uint32_t acc0 = (kb > 0) ? 1u : 0u;
+          if (!(batch.dbg & 1))
 #pragma unroll
           for (int pa = OZ_PLANES - 1; pa >= 0; --pa) {
 #pragma unroll
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-    const int quarter = warp & 3;
+    // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
+    const int quarter = warp & 3, half = (warp - 2) >> 2, ewarp = warp - 2;
     const int r_local = quarter * 32 + lane;
     const int row = row0 + r_local;
     const int q = batch.q;
@@ -275,14 +279,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     const double sA = item.scaleA * 6.103515625e-05;   // 2^-14
     int tile = 0;
     for (int jt = jt_begin; jt < jt_end; ++jt, ++tile) {
+      const int n0 = jt * OZ_BN + half * 32;           // this warp's 32 columns
+      // per-column scales of the tile: one coalesced load per warp, broadcast from shared memory
+      sB_s[ewarp][lane] = item.scaleB[n0 + lane] * sA;
+      __syncwarp();
       oz_mbar_wait(acc_full, (uint32_t)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int n0 = jt * OZ_BN;
-      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+      for (int c0 = 0; c0 < ((batch.dbg & 2) ? 0 : 32); c0 += 16) {
         uint32_t v[OZ_LEVELS][16];
 #pragma unroll
         for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + c0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32 + c0);
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                        : "=r"(v[lvl][0]), "=r"(v[lvl][1]), "=r"(v[lvl][2]), "=r"(v[lvl][3]), "=r"(v[lvl][4]), "=r"(v[lvl][5]),
                          "=r"(v[lvl][6]), "=r"(v[lvl][7]), "=r"(v[lvl][8]), "=r"(v[lvl][9]), "=r"(v[lvl][10]), "=r"(v[lvl][11]),
@@ -290,18 +297,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                        : "r"(taddr));
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        double s[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          double acc = 0.0;
+          // exact integer recombination: levels 3..6 and 0..2 each fit a 53-bit integer, two int -> double conversions
+          long long hi = 0, lo = 0;
 #pragma unroll
-          for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) acc = fma((double)(int)v[lvl][c], ldexp(1.0, 8 * (lvl - 6)), acc);
-          s[c] = acc;
-        }
+          for (int lvl = 3; lvl < OZ_LEVELS; ++lvl) hi += (long long)(int)v[lvl][c] << (8 * (lvl - 3));
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+          for (int lvl = 0; lvl < 3; ++lvl) lo += (long long)(int)v[lvl][c] << (8 * lvl);
+          const double sum = fma((double)lo, 3.552713678800501e-15 /* 2^-48 */, (double)hi * 5.960464477539063e-08 /* 2^-24 */);
           const int n = n0 + c0 + c;
-          const double val = s[c] * (sA * item.scaleB[n]);
+          const double val = sum * sB_s[ewarp][c0 + c];
           if (n < batch.N) {
             // Gram of the q-batch: this thread owns row i of G, partners are the q lanes of its group
 #pragma unroll
@@ -318,9 +324,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       oz_mbar_arrive(acc_empty);
+      __syncwarp();
     }
     if (row < batch.rows) {
-      double* dst = item.gqq_part + (size_t)grp * batch.gqq_stride + ((size_t)(row / q) * q + (row % q)) * q;
+      // partial Gram slot = (column group, column half): summed in a fixed order by sum_gram_partials_kernel
+      double* dst = item.gqq_part + (size_t)(grp * 2 + half) * batch.gqq_stride + ((size_t)(row / q) * q + (row % q)) * q;
       for (int j = 0; j < q; ++j) dst[j] = g[j];
     }
   }
@@ -383,7 +391,7 @@ int launch_ozaki_slice(const double* X, int rows, int cols, int ld, const double
   return BO_OK;
 }
 
-size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_out * OZ_MAXGROUPS * rows * q; }
+size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_out * 2 * OZ_MAXGROUPS * rows * q; }
 
 int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStream_t s, LaunchCounter* lc) {
   if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
@@ -415,6 +423,7 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
     OzBatch batch;
     memset(&batch, 0, sizeof(batch));
     batch.rows = a0.rows; batch.q = a0.q; batch.N = a0.N; batch.n_ext = a0.n_ext; batch.Rpad = a0.Rpad; batch.ldw = a0.ldw;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("EVEREST_OZAKI_DBG"); dbg = e ? atoi(e) : 0; } batch.dbg = dbg; }
     batch.n_chunks_k = a0.ldk / 16; batch.n_groups = groups; batch.gqq_stride = (long long)a0.rows * a0.q;
     {
       std::vector<long long> pre(n_tiles + 1, 0);
@@ -438,7 +447,7 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
       if ((rc = oz_make_map(&batch.item[i].mapA, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM)) != BO_OK) return rc;
       if ((rc = oz_make_map(&batch.item[i].mapB, a.Bplanes, a.Rpad, a.ldk / 16, OZ_BN)) != BO_OK) return rc;
       batch.item[i].scaleB = a.scaleB; batch.item[i].scaleA = a.scaleA;
-      batch.item[i].gqq_part = part_ws + (size_t)(m0 + i) * groups * batch.gqq_stride;
+      batch.item[i].gqq_part = part_ws + (size_t)(m0 + i) * 2 * groups * batch.gqq_stride;
       batch.item[i].W = a.W; batch.item[i].mu_raw = a.mu_raw;
     }
     dim3 grid(row_tiles * groups, cnt);
@@ -446,7 +455,7 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
     if (lc) lc->n++;
     CUDA_CHECK_RET(cudaGetLastError());
     for (int i = 0; i < cnt; ++i) {
-      int rc = launch_sum_gram_partials(batch.item[i].gqq_part, batch.gqq_stride, groups, args[m0 + i].Gqq, s, lc);
+      int rc = launch_sum_gram_partials(batch.item[i].gqq_part, batch.gqq_stride, 2 * groups, args[m0 + i].Gqq, s, lc);
       if (rc != BO_OK) return rc;
     }
   }
