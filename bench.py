@@ -315,7 +315,7 @@ def run_b200(args):
         for _ in range(reps):
             acq(X)
             torch.cuda.synchronize(device)
-            for name in ("prep", "crosscov", "posterior_gemm", "cond_root", "sample_gemm", "mc_acqf"):
+            for name in ("prep", "crosscov", "ozaki_slice", "posterior_gemm", "cond_root", "sample_gemm", "mc_acqf"):
                 t, cnt = st.last_timing(name)
                 per.setdefault(name, []).append((t, cnt))
         st.set_timing(False)
@@ -333,6 +333,8 @@ def run_b200(args):
         # DRAM bytes of one launch from the committed ncu --set full capture (profiles/r01_ncu_summary.txt); only valid
         # for the default headline workload, null otherwise
         traffic = 2.349e9 if (args.workload == "zdt1" and not args.raw_samples) else None  # profiles/r01_s2_ncu_gemm_dram_groups8.csv
+        oz_ms, oz_cnt = st.last_timing("ozaki_slice")
+        roofline_fp64 = None
         roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu, profiles/r01_s2_ncu_gemm_dram_groups8.csv; "
@@ -342,6 +344,25 @@ def run_b200(args):
                                    "for raw DMMA and DFMA issue on this pool",
                     "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": g_ms / g_cnt,
                     "launches_per_step": g_cnt, "step_time_share": kernel_share}
+        if oz_cnt > 0:
+            # the GEMM ran as 28 exact INT8 digit-plane products on tcgen05 (csrc/ozaki.cu): the roofline that bounds it is
+            # the INT8 tensor pipe = 2 x the dense bf16 rate of MEASURED_PEAKS.json (same pipe, half the operand width)
+            import json as _json
+            try:
+                mp = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                i8_peak, src = 2.0 * float(mp["bf16_tflops"]), "2 x bf16_tflops (burst) of MEASURED_PEAKS.json"
+            except Exception:
+                i8_peak, src = 4500.0, "nominal 4.5 POPS dense INT8 (MEASURED_PEAKS.json unavailable)"
+            i8_ops = 28.0 * flops_per_step / (g_ms * 1e-3) / 1e12
+            roofline.update({
+                "kernel": "ozaki_gemm_kernel (tcgen05.mma.kind::i8, TMEM accumulators: 28 exact INT8 digit-plane products "
+                          "= one FP64-accurate GEMM)",
+                "achieved": i8_ops, "peak": i8_peak, "unit": "TFLOP/s", "frac": i8_ops / i8_peak,
+                "peak_source": src + "; tools/i8_mma_probe: 4.6 POPS (N >= 128) / 3.07 POPS (N = 64, this kernel's tile) "
+                                     "single-SM issue rate x 148 at 1.9 GHz",
+                "algorithmic_ops_note": "achieved = 28 digit-plane products x algorithmic FP64 flops / kernel time (INT8 TOP/s)",
+                "fp64_equivalent_tflops": achieved, "fp64_pipe_peak_tflops": peak, "fp64_equivalent_over_fp64_pipe": achieved / peak,
+                "traffic": None})
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------
     cpu = None

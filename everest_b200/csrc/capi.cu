@@ -197,7 +197,7 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
   }
   bo_state* st = new bo_state();
   st->N = cfg->N; st->d = cfg->d; st->M = cfg->M;
-  { const char* e = getenv("EVEREST_OZAKI"); st->ozaki = (e && e[0] == '1') ? 1 : 0; }
+  { const char* e = getenv("EVEREST_OZAKI"); st->ozaki = e ? std::max(0, std::min(2, atoi(e))) : 1; }
   st->ldk = round_up(cfg->N, 16);
   st->Nr = round_up(cfg->N, 128);
   const int N = cfg->N, d = cfg->d;
@@ -731,7 +731,8 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
   if (!st || !name) { bo_set_error("null argument"); return BO_ERR_INVALID; }
   std::string nm(name);
   if (nm == "ozaki") {
-    st->ozaki = value != 0.0;
+    if (value != 0.0 && value != 1.0 && value != 2.0) { bo_set_error("ozaki must be 0 (off), 1 (automatic) or 2 (always)"); return BO_ERR_INVALID; }
+    st->ozaki = (int)value;
   } else if (nm == "log_hvi") {
     if (st->acqf_kind != 1 && st->acqf_kind != 2) { bo_set_error("log_hvi applies to a prepared qNEHVI / qEHVI"); return BO_ERR_STATE; }
     st->log_hvi = value != 0.0;
@@ -820,7 +821,10 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
     const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
-    const bool use_ozaki = st->ozaki && !small_rows && (q == 1 || q == 2 || q == 4 || q == 8);
+    // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
+    // pay off when the GEMM dominates), 2 = always (tests)
+    const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 65536;
+    const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
     if (small_rows) {
       RC(st->wsV.ensure(posterior_small_ws_doubles(rows, st->out[0].Rpad, M) * 8));
       rec_begin(st, "posterior_gemm", s);

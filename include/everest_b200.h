@@ -172,8 +172,9 @@ int bo_scalar_prepare(bo_state* st, int32_t variant, double param, int32_t S, in
 int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S, int32_t combine,
                            const bo_objective_op* obj, int32_t n_obj, int32_t* counts_dev, int32_t* info, void* stream);
 
-/* Named options of the prepared acquisition function: "ozaki" (0 / 1: run the posterior GEMM of large batches as an
- * error-free INT8 digit-plane product on the tcgen05 tensor cores instead of FP64 DMMA; default from EVEREST_OZAKI), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of
+/* Named options of the prepared acquisition function: "ozaki" (run the posterior GEMM as an error-free INT8 digit-plane
+ * product on the tcgen05 tensor cores instead of FP64 DMMA: 0 = never, 1 = automatically for large problems (default, or
+ * EVEREST_OZAKI), 2 = whenever the shape allows), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of
  * qEHVI / qNEHVI -- MoboStrategy's default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2). */
 int bo_acqf_set_option(bo_state* st, const char* name, double value);
 

@@ -504,3 +504,38 @@ def test_errors_are_loud():
                                                  mc_samples=16, seed=0)
     with pytest.raises(ValueError):
         acq(torch.zeros(2, 1, 4, dtype=DT))
+
+
+@pytest.mark.parametrize("N,q,raw,d", [(300, 4, 100, 6), (257, 1, 333, 3), (640, 2, 70, 5), (130, 8, 40, 4), (1000, 4, 300, 8)])
+def test_int8_digit_plane_gemm_matches_fp64_and_oracle(N, q, raw, d):
+    """csrc/ozaki.cu: the posterior GEMM as 28 exact INT8 x INT8 -> INT32 products of 7 balanced base-256 digit planes on
+    tcgen05 (accumulators in TMEM), recombined in FP64.  Forced on (option 2) for shapes with ragged row / column / K tiles
+    and extra columns (mean, baseline rows); compared with the FP64 DMMA kernel (1e-11) and with the oracle (1e-8)."""
+    p = Cf.zdt1_qnehvi(N=N, S=16, raw=raw, d=d, q=q)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    acq_o = P.oracle_acqf(p, gp, prune_samples=64)
+    acq_d = Cf.build_acqf(p, st, prune_samples=64)
+    X = Cf.candidates(p)
+    Xd = X.to(st.device)
+    nr = acq_o.nb + q
+    outs = {}
+    for mode in (0, 2):
+        acq_d.set_option("ozaki", mode)
+        v = acq_d(Xd).cpu()
+        root = st.debug_get("root").view(-1)[: X.shape[0] * st.M * q * nr].cpu().clone()
+        mu = st.debug_get("mu").view(-1)[: X.shape[0] * q * st.M].cpu().clone()
+        outs[mode] = (v, root, mu)
+    v_o, parts = acq_o.forward(X, return_parts=True)
+    scale = float(v_o.abs().max())
+    assert scale > 0
+    assert float((outs[2][0] - v_o).abs().max()) < 1e-8 * scale
+    assert float((outs[2][0] - outs[0][0]).abs().max()) < 1e-11 * scale
+    assert float((outs[2][1] - outs[0][1]).abs().max()) < 1e-10 * float(outs[0][1].abs().max())
+    assert float((outs[2][2] - outs[0][2]).abs().max()) < 1e-11 * float(outs[0][2].abs().max())
+    assert rel_err(outs[2][2].view(X.shape[0], q, st.M), parts["mu"], floor=1e-6) < 1e-9
+    # determinism of the INT8 path
+    acq_d.set_option("ozaki", 2)
+    assert torch.equal(acq_d(Xd).cpu(), outs[2][0])
+    with pytest.raises(ValueError):
+        acq_d.set_option("ozaki", 3)

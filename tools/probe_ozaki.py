@@ -9,7 +9,7 @@ acq = Cf.build_acqf(p, st, prune_samples=256 if size == "small" else 2048)
 X = Cf.candidates(p).to(st.device)
 b, q, M = X.shape[0], p["q"], st.M
 def run(oz):
-    acq.set_option("ozaki", oz)
+    acq.set_option("ozaki", 2 * oz)
     v = acq(X).clone()
     torch.cuda.synchronize()
     nr = acq.nb + q
@@ -22,7 +22,7 @@ print("values   max abs diff", float((v1 - v0).abs().max()), "scale", float(v0.a
 print("roots    max abs diff", float((r1 - r0).abs().max()), "scale", float(r0.abs().max()))
 print("means    max abs diff", float((m1 - m0).abs().max()), "scale", float(m0.abs().max()))
 for oz in (0, 1):
-    acq.set_option("ozaki", oz)
+    acq.set_option("ozaki", 2 * oz)
     for _ in range(2): acq(X)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5): acq(X)
