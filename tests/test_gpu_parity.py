@@ -530,9 +530,11 @@ def test_int8_digit_plane_gemm_matches_fp64_and_oracle(N, q, raw, d):
     scale = float(v_o.abs().max())
     assert scale > 0
     assert float((outs[2][0] - v_o).abs().max()) < 1e-8 * scale
-    assert float((outs[2][0] - outs[0][0]).abs().max()) < 1e-11 * scale
-    assert float((outs[2][1] - outs[0][1]).abs().max()) < 1e-10 * float(outs[0][1].abs().max())
-    assert float((outs[2][2] - outs[0][2]).abs().max()) < 1e-11 * float(outs[0][2].abs().max())
+    # the digit-plane product drops the pairs below 2^-51 of (row scale x column scale): ~10x the rounding of a DGEMM; the
+    # conditional roots (Cholesky of a nearly singular q x q block) amplify that like they amplify DGEMM rounding
+    assert float((outs[2][0] - outs[0][0]).abs().max()) < 1e-10 * scale
+    assert float((outs[2][1] - outs[0][1]).abs().max()) < 1e-8 * float(outs[0][1].abs().max())
+    assert float((outs[2][2] - outs[0][2]).abs().max()) < 1e-10 * float(outs[0][2].abs().max())
     assert rel_err(outs[2][2].view(X.shape[0], q, st.M), parts["mu"], floor=1e-6) < 1e-9
     # determinism of the INT8 path
     acq_d.set_option("ozaki", 2)
