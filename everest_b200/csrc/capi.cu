@@ -805,6 +805,16 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
     const double* Xc = X_dev + (size_t)b0 * q * st->d;
+    const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
+    // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
+    // pay off when the GEMM dominates), 2 = always (tests)
+    const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 65536;
+    const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
+    const int oz_rows_alloc = round_up(rows, 128);
+    const size_t oz_pa = use_ozaki ? ozaki_plane_bytes(oz_rows_alloc, ldk) : 0;
+    std::vector<double> oz_scaleA(M, 1.0);
+    std::vector<char> oz_fused(M, 0);
+    if (use_ozaki) RC(st->wsOzA.ensure(oz_pa * M));
     for (int m = 0; m < M; ++m) {
       OutputH& o = st->out[m];
       double* Kx = st->wsKx.as<double>() + (size_t)m * rows_max * ldk;
@@ -813,18 +823,26 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       RC(launch_prep_points(o.md, Xc, rows, st->d, o.q_prepd, s, &st->lc));
       rec_end(st, s);
       rec_begin(st, "crosscov", s);
-      RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, s, &st->lc));
+      if (use_ozaki) {
+        // the cross-covariance kernel emits the INT8 digit planes directly (and the FP64 matrix only for the adjoint)
+        double kmax = 0.0;
+        for (int t = 0; t < o.md.n_terms; ++t) kmax += fabs(o.md.coef[t]);   // every leaf is <= 1
+        oz_scaleA[m] = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
+        OzPlanesOut po;
+        po.planes = st->wsOzA.as<signed char>() + (size_t)m * oz_pa; po.plane_stride = (long long)(ldk / 16) * oz_rows_alloc * 16;
+        po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = dX_dev ? 1 : 0;
+        bool fz = false;
+        RC(launch_crosscov_ex(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, &po, &fz, s, &st->lc));
+        oz_fused[m] = fz ? 1 : 0;
+      } else {
+        RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, s, &st->lc));
+      }
       rec_end(st, s);
       PostGemmArgs& a = pg[m];
       a.Kx = Kx; a.rows = rows; a.ldk = ldk; a.B = o.LinvExt.as<double>(); a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad;
       a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
-    const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
-    // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
-    // pay off when the GEMM dominates), 2 = always (tests)
-    const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 65536;
-    const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
     if (small_rows) {
       RC(st->wsV.ensure(posterior_small_ws_doubles(rows, st->out[0].Rpad, M) * 8));
       rec_begin(st, "posterior_gemm", s);
@@ -832,9 +850,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       rec_end(st, s);
     } else if (use_ozaki) {
       // FP64-accurate GEMM on the INT8 tensor cores: digit planes of K(X*,X) (every call) and of LinvExt (once)
-      const int rows_alloc = round_up(rows, 128);
-      const size_t pa = ozaki_plane_bytes(rows_alloc, ldk);
-      RC(st->wsOzA.ensure(pa * M));
+      const int rows_alloc = oz_rows_alloc;
+      const size_t pa = oz_pa;
       RC(st->wsGramPart.ensure(ozaki_partial_ws_doubles(rows, q, M) * 8));
       std::vector<OzakiArgs> oa(M);
       rec_begin(st, "ozaki_slice", s);
@@ -848,11 +865,9 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
                                 o.ozB.as<signed char>(), o.Rpad, ldk, s, &st->lc));
           o.oz_ready = true;
         }
-        double kmax = 0.0;
-        for (int t = 0; t < o.md.n_terms; ++t) kmax += fabs(o.md.coef[t]);   // every leaf is <= 1
-        const double scaleA = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
+        const double scaleA = oz_scaleA[m];
         signed char* Ap = st->wsOzA.as<signed char>() + (size_t)m * pa;
-        RC(launch_ozaki_slice(pg[m].Kx, rows, st->N, ldk, nullptr, scaleA, Ap, rows_alloc, ldk, s, &st->lc));
+        if (!oz_fused[m]) RC(launch_ozaki_slice(pg[m].Kx, rows, st->N, ldk, nullptr, scaleA, Ap, rows_alloc, ldk, s, &st->lc));
         OzakiArgs& a = oa[m];
         a.Aplanes = Ap; a.rows = rows; a.rows_alloc = rows_alloc; a.ldk = ldk; a.Bplanes = o.ozB.as<signed char>();
         a.scaleB = o.ozScaleB.as<double>(); a.scaleA = scaleA; a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad; a.q = q;

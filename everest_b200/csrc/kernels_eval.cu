@@ -12,6 +12,8 @@
 // Tanimoto uses AND + POPC over bit-packed words, Hamming compares integer codes.  Distances,
 // lengthscales (pre-divided coordinates), outputscales (term coefficients) and the kernel function
 // are applied in the same pass; HBM traffic is one 8-byte store per element.
+#include <string.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -279,7 +281,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256, 2)
 crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n2a_g, int n_rows,
                      const double* __restrict__ Bt, const double* __restrict__ n2b_g, int n_cols, int dpad,
-                     double coef, double* __restrict__ out, int ld, int same_set) {
+                     double coef, double* __restrict__ out, int ld, int same_set, OzPlanesOut oz) {
   extern __shared__ __align__(16) double cc3sm[];
   double* As = cc3sm;
   double* Bs[2] = {cc3sm + CC_TILE * CC_LDS, cc3sm + 2 * CC_TILE * CC_LDS};
@@ -334,7 +336,10 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
     for (int idx = tid; idx < CC_TILE * (CC_TILE / 2); idx += 256) {
       const int r = idx >> 5, c2 = (idx & 31) * 2;
       const int gr = row0 + r, gc = col0 + c2;
-      if (gr >= n_rows || gc >= ld) continue;
+      if (gr >= n_rows || gc >= ld) {
+        if (oz.planes) *reinterpret_cast<double2*>(Cs + r * CC3_CLD + c2) = make_double2(0.0, 0.0);
+        continue;
+      }
       const double2 d = *reinterpret_cast<const double2*>(Cs + r * CC3_CLD + c2);
       const double na = n2a_s[r];
       double s0 = fmax(na + n2b_s[c2] - 2.0 * d.x, 0.0);
@@ -345,14 +350,48 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
       }
       const double v0 = (gc < n_cols) ? coef * leaf_value_from_stat(KIND, s0) : 0.0;
       const double v1 = (gc + 1 < n_cols) ? coef * leaf_value_from_stat(KIND, s1) : 0.0;
-      if (gc + 1 < ld) *reinterpret_cast<double2*>(out + (size_t)gr * ld + gc) = make_double2(v0, v1);
-      else out[(size_t)gr * ld + gc] = v0;
+      if (!oz.planes || oz.write_fp64) {
+        if (gc + 1 < ld) *reinterpret_cast<double2*>(out + (size_t)gr * ld + gc) = make_double2(v0, v1);
+        else out[(size_t)gr * ld + gc] = v0;
+      }
+      if (oz.planes) *reinterpret_cast<double2*>(Cs + r * CC3_CLD + c2) = make_double2(v0, (gc + 1 < ld) ? v1 : 0.0);
+    }
+    if (oz.planes) {
+      // fused slicing for the INT8 digit-plane GEMM (ozaki.cu): thread = (row, 16-column chunk) of the 64 x 64 tile,
+      // 7 x 16 bytes per thread, consecutive threads -> consecutive rows of one [chunk][row][16 B] slab
+      __syncthreads();
+      const int r = tid & 63, c = tid >> 6;
+      const int gr = row0 + r, chunk = (col0 >> 4) + c;
+      if (gr < oz.rows_alloc && chunk < oz.n_chunks) {
+        signed char dig[OZ_PLANES][16];
+#pragma unroll
+        for (int t2 = 0; t2 < 16; ++t2) {
+          signed char d[OZ_PLANES];
+          oz_split_digits(Cs[r * CC3_CLD + c * 16 + t2] * oz.inv_scale, d);
+#pragma unroll
+          for (int p = 0; p < OZ_PLANES; ++p) dig[p][t2] = d[p];
+        }
+#pragma unroll
+        for (int p = 0; p < OZ_PLANES; ++p) {
+          int4 w;
+          memcpy(&w, dig[p], 16);
+          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride + ((size_t)chunk * oz.rows_alloc + gr) * 16) = w;
+        }
+      }
     }
   }
 }
 
 int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_are_train, int n_cols, double* out,
                     int ld, bool same_set, cudaStream_t s, LaunchCounter* lc) {
+  return launch_crosscov_ex(md, rows, colsOrTrain, cols_are_train, n_cols, out, ld, same_set, nullptr, nullptr, s, lc);
+}
+
+int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_are_train, int n_cols, double* out,
+                       int ld, bool same_set, const OzPlanesOut* ozp, bool* fused, cudaStream_t s, LaunchCounter* lc) {
+  if (fused) *fused = false;
+  OzPlanesOut oz;
+  memset(&oz, 0, sizeof(oz));
   if (rows.n <= 0 || n_cols <= 0) return BO_OK;
   if (ld % 2 != 0) { bo_set_error("crosscov: ld must be even"); return BO_ERR_INVALID; }
   ColSides cs;
@@ -375,6 +414,11 @@ int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_a
     const LeafD& L = md.leaf[l];
     const int n_ct = (ld + CC_TILE - 1) / CC_TILE;
     dim3 gridf((n_ct + CC3_CT - 1) / CC3_CT, (rows.n + CC_TILE - 1) / CC_TILE);
+    if (ozp && ozp->planes) {
+      oz = *ozp;
+      gridf.y = (oz.rows_alloc + CC_TILE - 1) / CC_TILE;   // the padding rows of the planes are written (zeros) too
+      if (fused) *fused = true;
+    }
     const double* Aq = rows.Xs[l];
     const double* n2a = rows.n2[l];
     const size_t smf = ((size_t)3 * CC_TILE * CC_LDS + (size_t)CC_TILE * CC3_CLD + 2 * CC_TILE) * sizeof(double);
@@ -388,16 +432,16 @@ int launch_crosscov(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool cols_a
     }
     switch (L.kind) {
       case BO_LEAF_RBF:
-        crosscov_fast_kernel<BO_LEAF_RBF><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        crosscov_fast_kernel<BO_LEAF_RBF><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
         break;
       case BO_LEAF_MATERN12:
-        crosscov_fast_kernel<BO_LEAF_MATERN12><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        crosscov_fast_kernel<BO_LEAF_MATERN12><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
         break;
       case BO_LEAF_MATERN32:
-        crosscov_fast_kernel<BO_LEAF_MATERN32><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        crosscov_fast_kernel<BO_LEAF_MATERN32><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
         break;
       default:
-        crosscov_fast_kernel<BO_LEAF_MATERN52><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0);
+        crosscov_fast_kernel<BO_LEAF_MATERN52><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
         break;
     }
     if (lc) lc->n++;

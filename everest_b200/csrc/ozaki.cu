@@ -25,7 +25,6 @@
 
 #include "common.cuh"
 
-#define OZ_PLANES 7
 #define OZ_LEVELS 7
 #define OZ_BM 128
 #define OZ_BN 64
@@ -45,17 +44,6 @@
 // ------------------------------------------------------------------------------------------------
 // slicing: FP64 rows -> 7 balanced base-256 digit planes, layout [plane][K chunk][row][16 B]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_digits(double x_over_s, signed char* d) {
-  long long I = __double2ll_rn(x_over_s * 36028797018963968.0);  // 2^55, exact scaling; |I| < 0.498 * 2^55
-#pragma unroll
-  for (int p = 0; p < OZ_PLANES - 1; ++p) {
-    const long long dig = ((I + 128) & 0xFF) - 128;
-    d[p] = (signed char)dig;
-    I = (I - dig) >> 8;
-  }
-  d[OZ_PLANES - 1] = (signed char)I;
-}
-
 // per-row power-of-two scale: smallest 2^e with max|row| / 2^e < 0.49
 __global__ void __launch_bounds__(256)
 oz_row_scale_kernel(const double* __restrict__ X, int rows, int cols, int ld, double* __restrict__ scale) {
@@ -90,7 +78,7 @@ oz_slice_kernel(const double* __restrict__ X, int rows, int cols, int ld, const 
     const int k = c * 16 + t;
     const double v = (r < rows && k < cols) ? X[(size_t)r * ld + k] * inv : 0.0;
     signed char d[OZ_PLANES];
-    split_digits(v, d);
+    oz_split_digits(v, d);
 #pragma unroll
     for (int p = 0; p < OZ_PLANES; ++p) dig[p][t] = d[p];
   }

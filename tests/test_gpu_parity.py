@@ -386,10 +386,11 @@ def test_full_size_properties_headline_config():
     assert bool(torch.isfinite(v).all()) and float(v.min()) >= 0.0 and float(v.max()) > 0.0
     assert int(acq.last_info.sum()) == 0
     # reproducible bit for bit for a fixed batch shape; independent of the batch it is evaluated in up to the
-    # summation order of the Gram partials (the column-block grouping of the GEMM depends on the batch size)
+    # summation order of the Gram partials (the column-block grouping of the GEMM depends on the batch size) and to the
+    # GEMM variant the batch size selects (INT8 digit planes for the large batch, FP64 DMMA for the slice: ~1e-12)
     assert torch.equal(acq(X.to(st.device)), v)
     v2 = acq(X[300:700].to(st.device))
-    assert float((v2 - v[300:700]).abs().max()) <= 1e-12 * float(v.abs().max())
+    assert float((v2 - v[300:700]).abs().max()) <= 1e-10 * float(v.abs().max())
     # a q-batch whose points are all dominated by the baseline front in every MC sample scores exactly 0
     Xbad = torch.ones(1, p["q"], p["d"], dtype=DT)
     assert float(acq(Xbad.to(st.device))[0]) < 1e-3
