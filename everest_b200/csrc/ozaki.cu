@@ -273,29 +273,39 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       __syncwarp();
       oz_mbar_wait(acc_full, (uint32_t)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (int c0 = 0; c0 < ((batch.dbg & 2) ? 0 : 32); c0 += 16) {
-        uint32_t v[OZ_LEVELS][16];
+      // Drain all seven accumulators into two exact 64-bit integers per column (Horner in base 256: levels 6..3 and 2..0),
+      // hand TMEM back to the MMA warp, and only then do the FP64 work -- it overlaps the next tile's MMAs.
+      long long hi[32], lo[32];
 #pragma unroll
-        for (int lvl = 0; lvl < OZ_LEVELS; ++lvl) {
+      for (int lvl = OZ_LEVELS - 1; lvl >= 0; --lvl) {
+        uint32_t v[32];
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32 + c0);
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                       : "=r"(v[lvl][0]), "=r"(v[lvl][1]), "=r"(v[lvl][2]), "=r"(v[lvl][3]), "=r"(v[lvl][4]), "=r"(v[lvl][5]),
-                         "=r"(v[lvl][6]), "=r"(v[lvl][7]), "=r"(v[lvl][8]), "=r"(v[lvl][9]), "=r"(v[lvl][10]), "=r"(v[lvl][11]),
-                         "=r"(v[lvl][12]), "=r"(v[lvl][13]), "=r"(v[lvl][14]), "=r"(v[lvl][15])
+                       : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                         "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                         "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
                        : "r"(taddr));
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          // exact integer recombination: levels 3..6 and 0..2 each fit a 53-bit integer, two int -> double conversions
-          long long hi = 0, lo = 0;
+        for (int c = 0; c < 32; ++c) {
+          if (lvl == OZ_LEVELS - 1) hi[c] = (long long)(int)v[c];
+          else if (lvl >= 3) hi[c] = hi[c] * 256 + (long long)(int)v[c];
+          else if (lvl == 2) lo[c] = (long long)(int)v[c];
+          else lo[c] = lo[c] * 256 + (long long)(int)v[c];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      oz_mbar_arrive(acc_empty);
+      if (!(batch.dbg & 2)) {
 #pragma unroll
-          for (int lvl = 3; lvl < OZ_LEVELS; ++lvl) hi += (long long)(int)v[lvl][c] << (8 * (lvl - 3));
-#pragma unroll
-          for (int lvl = 0; lvl < 3; ++lvl) lo += (long long)(int)v[lvl][c] << (8 * lvl);
-          const double sum = fma((double)lo, 3.552713678800501e-15 /* 2^-48 */, (double)hi * 5.960464477539063e-08 /* 2^-24 */);
-          const int n = n0 + c0 + c;
-          const double val = sum * sB_s[ewarp][c0 + c];
+        for (int c = 0; c < 32; ++c) {
+          // sum_lvl acc_lvl 2^(8 (lvl - 6)) = hi 2^-24 + lo 2^-48, both integers exact in FP64 (< 2^53)
+          const double sum = fma((double)lo[c], 3.552713678800501e-15 /* 2^-48 */, (double)hi[c] * 5.960464477539063e-08 /* 2^-24 */);
+          const int n = n0 + c;
+          const double val = sum * sB_s[ewarp][c];
           if (n < batch.N) {
             // Gram of the q-batch: this thread owns row i of G, partners are the q lanes of its group
 #pragma unroll
@@ -310,9 +320,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      oz_mbar_arrive(acc_empty);
       __syncwarp();
+
     }
     if (row < batch.rows) {
       // partial Gram slot = (column group, column half): summed in a fixed order by sum_gram_partials_kernel
