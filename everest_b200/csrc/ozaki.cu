@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = (int)(blockIdx.x % batch.n_groups), row_tile = (int)(blockIdx.x / batch.n_groups);
   const int row0 = row_tile * OZ_BM;
-  const int jt_begin = batch.gbeg[grp], jt_end = batch.gbeg[grp + 1];
+  // Column tiles are dealt to the groups in snake order (round r: tile r G + g, or r G + G - 1 - g on odd rounds): every
+  // CTA gets a mix of short (early, triangular) and long tiles of similar total work, so that the FP64 epilogue of one tile
+  // hides behind the MMAs of the next instead of piling up on a run of one-K-block tiles.
+  const int n_tiles = batch.Rpad / OZ_BN, G = batch.n_groups;
+  auto tile_at = [&](int i) { const int j = i * G + ((i & 1) ? (G - 1 - grp) : grp); return (j < n_tiles) ? j : -1; };
   const uint32_t full0 = oz_smem_u32(&bars[0]), empty0 = oz_smem_u32(&bars[OZ_ST]);
   const uint32_t acc_full = oz_smem_u32(&bars[2 * OZ_ST]), acc_empty = oz_smem_u32(&bars[2 * OZ_ST + 1]);
   if (tid == 0) {
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      for (int jt = jt_begin; jt < jt_end; ++jt) {
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
         const int nkb = k_blocks_of(jt);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % OZ_ST;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
       idesc |= (uint32_t)(OZ_BN >> 3) << 17;
       idesc |= (uint32_t)(OZ_BM >> 4) << 24;
       int it = 0, tile = 0;
-      for (int jt = jt_begin; jt < jt_end; ++jt, ++tile) {
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti, ++tile) {
         const int nkb = k_blocks_of(jt);
         // the epilogue must have drained the accumulators of the previous tile
         oz_mbar_wait(acc_empty, (uint32_t)((tile & 1) ^ 1));
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     for (int j = 0; j < 8; ++j) g[j] = 0.0;
     const double sA = item.scaleA * 6.103515625e-05;   // 2^-14
     int tile = 0;
-    for (int jt = jt_begin; jt < jt_end; ++jt, ++tile) {
+    for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti, ++tile) {
       const int n0 = jt * OZ_BN + half * 32;           // this warp's 32 columns
       // per-column scales of the tile: one coalesced load per warp, broadcast from shared memory
       sB_s[ewarp][lane] = item.scaleB[n0 + lane] * sA;
