@@ -117,6 +117,113 @@ __global__ void __launch_bounds__(128) probe_kernel(const int8_t* __restrict__ A
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(N < 32 ? 32 : N));
 }
 
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_c), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+
+// (3) A operand staged in TMEM: tcgen05.cp.128x256b (128 rows x 32 bytes) per K = 32 step, then A-from-TMEM MMAs.
+// `reuse` MMAs are issued per copied A tile (the digit-plane GEMM reuses one A plane for up to 7 B planes).
+template <int N, int KTOT>
+__global__ void __launch_bounds__(128) probe_ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B,
+                                                       int32_t* __restrict__ out, int iters, int reuse, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t mbar;
+  constexpr int CH = KTOT / 16;
+  uint8_t* As = smem;
+  uint8_t* Bs = smem + CH * 128 * 16;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int idx = tid; idx < 128 * KTOT; idx += 128) {
+    const int r = idx / KTOT, k = idx % KTOT;
+    As[(k / 16) * (128 * 16) + r * 16 + (k % 16)] = (uint8_t)A[idx];
+  }
+  for (int idx = tid; idx < N * KTOT; idx += 128) {
+    const int r = idx / KTOT, k = idx % KTOT;
+    Bs[(k / 16) * (N * 16) + r * 16 + (k % 16)] = (uint8_t)B[idx];
+  }
+  if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_a = tmem_base + 448;     // 8 columns (32 bytes per lane) per K = 32 step
+  const uint32_t idesc = make_idesc_s8(128, N);
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int ks = 0; ks < KTOT / 32; ++ks) {
+        const uint64_t da = make_desc(smem_u32(As + (2 * ks) * (128 * 16)), 128 * 16, 128);
+        const uint64_t db = make_desc(smem_u32(Bs + (2 * ks) * (N * 16)), N * 16, 128);
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_a), "l"(da));
+        for (int rpt = 0; rpt < reuse; ++rpt) mma_i8_ts(tmem_base, tmem_a, db, idesc, (it > 0 || ks > 0 || rpt > 0) ? 1u : 0u);
+      }
+    }
+    umma_commit(smem_u32(&mbar));
+  }
+  mbar_wait(smem_u32(&mbar), 0);
+  if (tid == 0) { t1 = clock64(); if (cycles) *cycles = t1 - t0; }
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    for (int j = 0; j < 16; ++j) out[(size_t)tid * N + c0 + j] = (int32_t)v[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+}
+
+template <int N, int KTOT>
+static void run_ts(int iters, int reuse, bool check) {
+  std::vector<int8_t> hA(128 * KTOT), hB(N * KTOT);
+  srand(2);
+  for (auto& v : hA) v = (int8_t)(rand() % 255 - 127);
+  for (auto& v : hB) v = (int8_t)(rand() % 255 - 127);
+  int8_t *dA, *dB; int32_t* dO; long long* dC;
+  CK(cudaMalloc(&dA, hA.size())); CK(cudaMalloc(&dB, hB.size())); CK(cudaMalloc(&dO, 128 * N * 4)); CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
+  size_t smem = (size_t)(128 + N) * KTOT + 1024;
+  CK(cudaFuncSetAttribute(probe_ts_kernel<N, KTOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_ts_kernel<N, KTOT><<<1, 128, smem>>>(dA, dB, dO, iters, reuse, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hO(128 * N);
+  long long cyc = 0;
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  if (check) {
+    long long bad = 0;
+    for (int i = 0; i < 128; ++i)
+      for (int j = 0; j < N; ++j) {
+        long long ref = 0;
+        for (int k = 0; k < KTOT; ++k) ref += (long long)hA[i * KTOT + k] * hB[j * KTOT + k];
+        ref *= (long long)iters * reuse;
+        if ((long long)hO[i * N + j] != ref) { if (bad < 5) printf("  TS mismatch (%d,%d): got %d want %lld\n", i, j, hO[i * N + j], ref); ++bad; }
+      }
+    printf("TS  N=%d K=%d iters=%d reuse=%d: %lld mismatches of %d\n", N, KTOT, iters, reuse, bad, 128 * N);
+  } else {
+    const double mmas = (double)iters * (KTOT / 32) * reuse;
+    printf("TS  N=%3d reuse=%d: %lld cycles for %.0f MMAs -> %.1f clk/MMA\n", N, reuse, cyc, mmas, cyc / mmas);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
+}
+
 template <int N, int KTOT>
 static void run(int iters, bool check) {
   std::vector<int8_t> hA(128 * KTOT), hB(N * KTOT);
@@ -161,5 +268,11 @@ int main() {
   run<64, 128>(2000, false);
   run<128, 128>(2000, false);
   run<256, 128>(2000, false);
+  run_ts<64, 64>(1, 1, true);
+  run_ts<64, 64>(2, 3, true);
+  run_ts<64, 128>(500, 1, false);
+  run_ts<64, 128>(500, 4, false);
+  run_ts<64, 128>(500, 7, false);
+  run_ts<128, 128>(500, 4, false);
   return 0;
 }
