@@ -299,10 +299,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * b * args.steps / float(t_e2e[0])
-    # the host path pipelines chunks of q-batches (copy / compute overlap); chunk size changes the Gram partial-sum
-    # grouping, so the two paths agree to rounding, not bit for bit
+    # the host path pipelines chunks of q-batches (copy / compute overlap); the chunk size changes the Gram partial-sum
+    # grouping and may select the other GEMM variant (FP64 DMMA below the size threshold, INT8 digit planes above), so the
+    # two paths agree to rounding (amplified by the inclusion-exclusion sums for q = 8), not bit for bit
     ref_v = vals.cpu().numpy()
-    assert np.allclose(out_h, ref_v, rtol=1e-10, atol=1e-12 * float(np.abs(ref_v).max())), \
+    assert np.allclose(out_h, ref_v, rtol=1e-8, atol=1e-10 * float(np.abs(ref_v).max())), \
         "host-buffer path disagrees with the device-pointer path"
 
     # ---- roofline of the dominant kernel (posterior GEMM), timed with CUDA events on its stream ----

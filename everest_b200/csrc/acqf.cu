@@ -769,31 +769,37 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
   double up[MO];
 #pragma unroll
   for (int o = 0; o < MO; ++o) up[o] = up_p[o * stride];
-  double cell = 0.0;
-  for (int size = 1; size <= q; ++size) {
-    double asum = 0.0;
-    bool any = false;
-    for (unsigned sub = active; sub; sub = (sub - 1) & active) {
-      if (__popc(sub) != size) continue;
-      any = true;
-      double vol = 1.0;
+  // one pass over the subsets of the active set; the per-size sums keep the order of the reference (sizes 1..q with
+  // alternating sign, subsets of one size in the same descending enumeration order as a size-by-size loop)
+  double asum[QMAX + 1];
 #pragma unroll
-      for (int o = 0; o < MO; ++o) {
-        double mn = up[o];
+  for (int i = 0; i <= QMAX; ++i) asum[i] = 0.0;
+  unsigned seen = 0;
+  for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+    const int size = __popc(sub);
+    seen |= 1u << size;
+    double vol = 1.0;
 #pragma unroll
-        for (int j = 0; j < QMAX; ++j)
-          if ((sub >> j) & 1u) mn = fmin(mn, obj[j][o]);
-        vol *= fmax(mn - lo[o], 0.0);
-      }
-      if (has_cons) {
+    for (int o = 0; o < MO; ++o) {
+      double mn = up[o];
 #pragma unroll
-        for (int j = 0; j < QMAX; ++j)
-          if ((sub >> j) & 1u) vol *= fwt[j];
-      }
-      asum += vol;
+      for (int j = 0; j < QMAX; ++j)
+        if ((sub >> j) & 1u) mn = fmin(mn, obj[j][o]);
+      vol *= fmax(mn - lo[o], 0.0);
     }
-    if (any) cell += (size & 1) ? asum : -asum;
+    if (has_cons) {
+#pragma unroll
+      for (int j = 0; j < QMAX; ++j)
+        if ((sub >> j) & 1u) vol *= fwt[j];
+    }
+#pragma unroll
+    for (int i = 1; i <= QMAX; ++i)
+      if (i == size) asum[i] += vol;
   }
+  double cell = 0.0;
+#pragma unroll
+  for (int size = 1; size <= QMAX; ++size)
+    if ((seen >> size) & 1u) cell += (size & 1) ? asum[size] : -asum[size];
   return cell;
 }
 
