@@ -336,6 +336,10 @@ def run_b200(args):
         traffic = 2.349e9 if (args.workload == "zdt1" and not args.raw_samples) else None  # profiles/r01_s2_ncu_gemm_dram_groups8.csv
         oz_ms, oz_cnt = st.last_timing("ozaki_slice")
         roofline_fp64 = None
+        chk = st.debug_get("ozaki_check", capacity=16).cpu().tolist()
+        int8_check = {"state": {0: "not run (problem below the INT8 threshold)", 1: "accepted", -1: "rejected -> FP64 DMMA kernel"}[int(chk[0])],
+                      "max_rel_err_posterior_variance": chk[1], "max_rel_err_posterior_mean": chk[2], "accept_below": 1e-10,
+                      "note": "first large call after every prepare: both kernels on a 256-row probe"}
         roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu, profiles/r01_s2_ncu_gemm_dram_groups8.csv; "
@@ -344,7 +348,7 @@ def run_b200(args):
                                    "MEASURED_PEAKS.json holds no fp64 figure; tools/fp64_peak measured 37.0 TFLOP/s "
                                    "for raw DMMA and DFMA issue on this pool",
                     "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": g_ms / g_cnt,
-                    "launches_per_step": g_cnt, "step_time_share": kernel_share}
+                    "launches_per_step": g_cnt, "step_time_share": kernel_share, "int8_self_check": int8_check}
         if oz_cnt > 0:
             # the GEMM ran as 28 exact INT8 digit-plane products on tcgen05 (csrc/ozaki.cu): the roofline that bounds it is
             # the INT8 tensor pipe = 2 x the dense bf16 rate of MEASURED_PEAKS.json (same pipe, half the operand width)

@@ -129,6 +129,9 @@ struct bo_state {
   DevBuf best_f_s;
   int log_hvi = 0;
   int ozaki = 0;               // posterior GEMM of large batches on the INT8 tensor cores (ozaki.cu)
+  int oz_calib = 0;            // automatic mode: 0 = not checked yet for this prepared state, 1 = accepted, -1 = rejected
+  double oz_err_var = 0.0, oz_err_mu = 0.0;   // what the self-check measured
+  DevBuf wsOzRef;
   double tau_relu = 1e-6, tau_max = 1e-2;
   DevBuf wsOzA;  // INT8 digit planes of K(X*,X) (all outputs)
   DevBuf wsDF, wsDRoot, wsDMu, wsEG, wsEW, wsEmu, wsU;  // adjoint workspaces (grad.cu)
@@ -174,7 +177,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA};
+                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA, &st->wsOzRef};
   for (DevBuf* b : bs) b->release();
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
@@ -327,6 +330,7 @@ static int build_linv_ext(bo_state* st, OutputH& o, int nb, cudaStream_t s) {
   const int N = st->N, ldk = st->ldk;
   o.Rpad = round_up(N + 1 + nb, 128);
   o.oz_ready = false;
+  st->oz_calib = 0;   // the digit-plane product is re-checked against the FP64 kernel for every new factor
   RC(o.LinvExt.ensure((size_t)o.Rpad * ldk * 8, true));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.p, o.Linv.p, (size_t)N * ldk * 8, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.as<double>() + (size_t)N * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
@@ -808,8 +812,12 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
     // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
     // pay off when the GEMM dominates), 2 = always (tests)
-    const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 65536;
-    const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
+    // N <= 16384: 7 plane pairs x N x 2^14 per S32 accumulator stays below 2^31
+    const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 16384;
+    const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && st->oz_calib >= 0 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
+    // automatic mode: the first large call after a prepare runs BOTH kernels on a probe of rows and keeps the INT8 path
+    // only if the posterior variance agrees with the FP64 kernel to 1e-10 (10x inside the 1e-9 parity bar)
+    const bool oz_check = use_ozaki && st->ozaki == 1 && st->oz_calib == 0;
     const int oz_rows_alloc = round_up(rows, 128);
     const size_t oz_pa = use_ozaki ? ozaki_plane_bytes(oz_rows_alloc, ldk) : 0;
     std::vector<double> oz_scaleA(M, 1.0);
@@ -830,7 +838,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         oz_scaleA[m] = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
         OzPlanesOut po;
         po.planes = st->wsOzA.as<signed char>() + (size_t)m * oz_pa; po.plane_stride = (long long)(ldk / 16) * oz_rows_alloc * 16;
-        po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = dX_dev ? 1 : 0;
+        po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = (dX_dev || oz_check) ? 1 : 0;
         bool fz = false;
         RC(launch_crosscov_ex(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, &po, &fz, s, &st->lc));
         oz_fused[m] = fz ? 1 : 0;
@@ -877,6 +885,43 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       rec_begin(st, "posterior_gemm", s);
       RC(launch_ozaki_gemm(oa.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
       rec_end(st, s);
+      if (oz_check) {
+        const int pr = std::min(rows, (256 / q) * q);
+        const size_t per_out = (size_t)pr * q + pr + (size_t)pr * ldw;
+        RC(st->wsOzRef.ensure(((size_t)M * per_out + 2 * M) * 8));
+        double* ref = st->wsOzRef.as<double>();
+        std::vector<PostGemmArgs> pr_args(M);
+        for (int m = 0; m < M; ++m) {
+          pr_args[m] = pg[m];
+          pr_args[m].rows = pr;
+          pr_args[m].Gqq = ref + (size_t)m * per_out;
+          pr_args[m].mu_raw = pr_args[m].Gqq + (size_t)pr * q;
+          pr_args[m].W = pr_args[m].mu_raw + pr;
+        }
+        {
+          size_t pw = posterior_gemm_partial_ws_doubles(pr, q, M);
+          if (pw) RC(st->wsGramPart.ensure(pw * 8));
+        }
+        RC(launch_posterior_gemm_multi(pr_args.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+        double* errs = ref + (size_t)M * per_out;
+        for (int m = 0; m < M; ++m) {
+          double kmax = 0.0;
+          for (int t = 0; t < st->out[m].md.n_terms; ++t) kmax += st->out[m].md.coef[t];
+          RC(launch_ozaki_compare(pg[m].Gqq, pr_args[m].Gqq, pg[m].mu_raw, pr_args[m].mu_raw, pr, q, kmax, errs + 2 * m, s, &st->lc));
+        }
+        std::vector<double> herr(2 * M);
+        CUDA_CHECK_RET(cudaMemcpyAsync(herr.data(), errs, (size_t)2 * M * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK_RET(cudaStreamSynchronize(s));
+        st->oz_err_var = 0.0; st->oz_err_mu = 0.0;
+        for (int m = 0; m < M; ++m) { st->oz_err_var = std::max(st->oz_err_var, herr[2 * m]); st->oz_err_mu = std::max(st->oz_err_mu, herr[2 * m + 1]); }
+        st->oz_calib = (st->oz_err_var <= 1e-10 && st->oz_err_mu <= 1e-10) ? 1 : -1;
+        if (st->oz_calib < 0) {
+          // rejected: this call is redone with the FP64 kernel (the FP64 K(X*,X) was kept for the check)
+          size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
+          if (pw) RC(st->wsGramPart.ensure(pw * 8));
+          RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+        }
+      }
     } else {
       size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
       if (pw) RC(st->wsGramPart.ensure(pw * 8));
@@ -1056,7 +1101,8 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   {
     const double r = ((double)st->d * 8.0 / 25e9) / ((double)st->M * (double)st->N * (double)st->N / 30e12 + 1e-12);
     const int min_b = std::max(1, 2048 / q);
-    if (b <= 2 * min_b) chunk_b.push_back(b);
+    // inputs below 8 MiB cross PCIe in ~0.3 ms: nothing worth hiding, and whole-batch launches fill the GPU better
+    if (b <= 2 * min_b || in_bytes < ((size_t)8 << 20)) chunk_b.push_back(b);
     else if (r < 0.15) {
       const int first = std::max(min_b, b / 8);
       chunk_b.push_back(first);
@@ -1229,6 +1275,15 @@ extern "C" int bo_debug_get(bo_state* st, const char* name, int32_t m, double* o
   else if (nm == "cell_up") { src = st->cell_up.as<double>(); n = (int64_t)st->cap * st->od.n_obj * (st->cells_shared ? 1 : st->S); }
   else if (nm == "samples_b") { src = st->samples_b.as<double>(); n = (int64_t)st->S * st->nb * st->M; }
   else if (nm == "obj_b") { src = st->obj_b.as<double>(); n = (int64_t)st->S * st->nb * st->od.n_obj; }
+  else if (nm == "ozaki_check") {
+    // [calibration state (0 unchecked, 1 accepted, -1 rejected), max rel. error of the posterior variance, of the mean]
+    if (capacity < 3) { bo_set_error("debug_get: capacity too small"); return BO_ERR_INVALID; }
+    double h[3] = {(double)st->oz_calib, st->oz_err_var, st->oz_err_mu};
+    CUDA_CHECK_RET(cudaMemcpyAsync(out_dev, h, 24, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));
+    if (n_written) *n_written = 3;
+    return BO_OK;
+  }
   else if (nm == "ncells" || nm == "front_idx") {
     // integer buffers are returned through the same byte pipe (caller views them as int32)
     const void* isrc = (nm == "ncells") ? st->ncells.p : st->front_idx.p;

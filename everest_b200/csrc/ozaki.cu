@@ -462,3 +462,37 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
   }
   return BO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// self-check of the digit-plane product: relative error of the (standardised) posterior variance k** - G_ii on a probe
+// of rows, against the FP64 kernel's Gram.  One block; out[0] = max_i |G_oz - G_ref| / (kmax - G_ref), out[1] = max_i
+// |mu_oz - mu_ref| / (1 + |mu_ref|).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+oz_compare_kernel(const double* __restrict__ Goz, const double* __restrict__ Gref, const double* __restrict__ mu_oz,
+                  const double* __restrict__ mu_ref, int rows, int q, double kmax, double* __restrict__ out) {
+  __shared__ double red[2][256];
+  double e0 = 0.0, e1 = 0.0;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    const size_t di = (size_t)r * q + (r % q);
+    const double gr = Gref[di];
+    const double a = fabs(Goz[di] - gr) / fmax(kmax - gr, 1e-300);
+    const double b = fabs(mu_oz[r] - mu_ref[r]) / (1.0 + fabs(mu_ref[r]));
+    e0 = fmax(e0, isfinite(a) ? a : 1e300);
+    e1 = fmax(e1, isfinite(b) ? b : 1e300);
+  }
+  red[0][threadIdx.x] = e0; red[1][threadIdx.x] = e1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 256; ++i) { e0 = fmax(e0, red[0][i]); e1 = fmax(e1, red[1][i]); }
+    out[0] = e0; out[1] = e1;
+  }
+}
+
+int launch_ozaki_compare(const double* Goz, const double* Gref, const double* mu_oz, const double* mu_ref, int rows, int q,
+                         double kmax, double* out2, cudaStream_t s, LaunchCounter* lc) {
+  oz_compare_kernel<<<1, 256, 0, s>>>(Goz, Gref, mu_oz, mu_ref, rows, q, kmax, out2);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
