@@ -154,6 +154,15 @@ __device__ __forceinline__ void oz_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Gram update of one element: this thread owns row i of its q-batch's G, the partners are the Q lanes of its group.  The
+// shuffles must sit in straight-line code: under a condition the compiler cannot prove warp-uniform every __shfl_sync is
+// wrapped in an elect / divergence-barrier sequence with local-memory spills (ncu: ~100 warp instructions per element).
+template <int Q>
+__device__ __forceinline__ void oz_gram_update(double v, int lane_base, double (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < Q; ++j) g[j] = fma(v, __shfl_sync(0xffffffffu, v, lane_base + j), g[j]);
+}
+template <int Q>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ OzBatch batch) {
   extern __shared__ unsigned char ozraw[];
   __shared__ uint32_t tmem_base_s;
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     const int quarter = warp & 3, half = (warp - 2) >> 2, ewarp = warp - 2;
     const int r_local = quarter * 32 + lane;
     const int row = row0 + r_local;
-    const int q = batch.q;
+    constexpr int q = Q;
     const int lane_base = lane & ~(q - 1);
     double g[8];
 #pragma unroll
@@ -310,17 +319,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
           const double sum = fma((double)lo[c], 3.552713678800501e-15 /* 2^-48 */, (double)hi[c] * 5.960464477539063e-08 /* 2^-24 */);
           const int n = n0 + c;
           const double val = sum * sB_s[ewarp][c];
-          if (n < batch.N) {
-            // Gram of the q-batch: this thread owns row i of G, partners are the q lanes of its group
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < q) g[j] = fma(val, __shfl_sync(0xffffffffu, val, lane_base + j), g[j]);
-          } else {
+          // Gram of the q-batch (columns beyond N contribute zero: branch-free, see oz_gram_update)
+          oz_gram_update<Q>((n < batch.N) ? val : 0.0, lane_base, g);
+          if (n >= batch.N && row < batch.rows) {
             const int e = n - batch.N;
-            if (row < batch.rows) {
-              if (e == 0) item.mu_raw[row] = val;
-              else if (item.W && e < batch.n_ext) item.W[(size_t)row * batch.ldw + (e - 1)] = val;
-            }
+            if (e == 0) item.mu_raw[row] = val;
+            else if (item.W && e < batch.n_ext) item.W[(size_t)row * batch.ldw + (e - 1)] = val;
           }
         }
       }
@@ -339,13 +343,280 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-pass variant with 128 x 128 tiles.  An M128 x N64 MMA occupies the tensor pipe for 48 clocks where M128 x N128 needs
+// 64 (tools/i8_mma_probe.cu), so N = 128 is worth 1.5x -- but seven 128-column accumulators do not fit the 512 TMEM
+// columns.  The K loop of a tile therefore runs twice: pass 1 accumulates the four LOW levels (p + p' = 6..9, 22 plane
+// pairs, all planes), the epilogue warps drain them into one exact 64-bit integer per element and park it in an
+// L2-resident scratch slab (128 KB per SM); pass 2 re-streams only planes 4..6 of both operands for the three HIGH levels
+// (6 pairs).  Operand traffic per MAC is the same as the one-pass kernel's (10/7 of the planes for twice the columns).
+// ------------------------------------------------------------------------------------------------
+#define O2_BN 128
+#define O2_BK 32
+#define O2_CH (O2_BK / 16)
+#define O2_ST 3
+#define O2_PLANE (O2_CH * 128 * 16)            // 4096 B: one plane of one operand per K block
+#define O2_OP_BYTES (OZ_PLANES * O2_PLANE)     // 28672
+#define O2_STAGE_BYTES (2 * O2_OP_BYTES)       // 57344
+#define O2_HI_PLANES 3
+#define O2_HI_OP_BYTES (O2_HI_PLANES * O2_PLANE)   // 12288
+#define O2_MAXOUT 4
+#define O2_SCRATCH_SLOTS 160
+
+struct alignas(128) O2Item {
+  CUtensorMap mapA, mapB;      // box {128 rows, 2 chunks, 7 planes}
+  CUtensorMap mapA3, mapB3;    // box {128 rows, 2 chunks, 3 planes} (planes 4..6)
+  const double* scaleB;
+  double scaleA;
+  double* gqq_part;
+  double* W;
+  double* mu_raw;
+};
+struct O2Batch {
+  O2Item item[O2_MAXOUT];
+  int rows, q, N, n_ext, Rpad, ldw, n_chunks_k;
+  int n_groups;
+  int dbg;
+  long long gqq_stride;
+  long long* scratch;          // [O2_SCRATCH_SLOTS][8 warps][64 columns][32 lanes]
+};
+
+template <int Q>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __grid_constant__ O2Batch batch) {
+  extern __shared__ unsigned char ozraw[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bars[2 * O2_ST + 2];
+  __shared__ double sB_s[8][64];
+  const O2Item& item = batch.item[blockIdx.y];
+  const uint32_t base = (oz_smem_u32(ozraw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = (int)(blockIdx.x % batch.n_groups), row_tile = (int)(blockIdx.x / batch.n_groups);
+  const int row0 = row_tile * OZ_BM;
+  const int n_tiles = batch.Rpad / O2_BN, G = batch.n_groups;
+  auto tile_at = [&](int i) { const int j = i * G + ((i & 1) ? (G - 1 - grp) : grp); return (j < n_tiles) ? j : -1; };
+  const uint32_t full0 = oz_smem_u32(&bars[0]), empty0 = oz_smem_u32(&bars[O2_ST]);
+  const uint32_t acc_full = oz_smem_u32(&bars[2 * O2_ST]), acc_empty = oz_smem_u32(&bars[2 * O2_ST + 1]);
+  if (tid == 0) {
+    for (int s = 0; s < O2_ST; ++s) { oz_mbar_init(full0 + 8 * s, 1); oz_mbar_init(empty0 + 8 * s, 1); }
+    oz_mbar_init(acc_full, 1);
+    oz_mbar_init(acc_empty, OZ_EPI_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto k_blocks_of = [&](int jt) {
+    const int n_end = (jt + 1) * O2_BN;
+    const int kmax = batch.n_chunks_k * 16;
+    const int kbytes = (n_end <= batch.N) ? n_end : kmax;
+    return (min(kbytes, kmax) + O2_BK - 1) / O2_BK;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int it = 0;
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+        const int nkb = k_blocks_of(jt);
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % O2_ST;
+            const uint32_t ph = (uint32_t)((it / O2_ST) & 1);
+            oz_mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t fb = full0 + 8 * s;
+            const uint32_t dst = base + (uint32_t)s * O2_STAGE_BYTES;
+            if (pass == 0) {
+              oz_mbar_expect_tx(fb, O2_STAGE_BYTES);
+              oz_tma_load_3d(dst, &item.mapA, row0 * 2, kb * O2_CH, 0, fb);
+              oz_tma_load_3d(dst + O2_OP_BYTES, &item.mapB, jt * O2_BN * 2, kb * O2_CH, 0, fb);
+            } else {
+              oz_mbar_expect_tx(fb, 2 * O2_HI_OP_BYTES);
+              oz_tma_load_3d(dst, &item.mapA3, row0 * 2, kb * O2_CH, OZ_PLANES - O2_HI_PLANES, fb);
+              oz_tma_load_3d(dst + O2_HI_OP_BYTES, &item.mapB3, jt * O2_BN * 2, kb * O2_CH, OZ_PLANES - O2_HI_PLANES, fb);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      uint32_t idesc = 0;
+      idesc |= 2u << 4;                       // D = S32
+      idesc |= 1u << 7;                       // A signed 8 bit
+      idesc |= 1u << 10;                      // B signed 8 bit
+      idesc |= (uint32_t)(O2_BN >> 3) << 17;
+      idesc |= (uint32_t)(OZ_BM >> 4) << 24;
+      int it = 0, ev = 0;
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+        const int nkb = k_blocks_of(jt);
+        for (int pass = 0; pass < 2; ++pass, ++ev) {
+          // pass 1 needs the previous tile's high levels drained, pass 2 this tile's low levels
+          oz_mbar_wait(acc_empty, (uint32_t)((ev & 1) ^ 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % O2_ST;
+            const uint32_t ph = (uint32_t)((it / O2_ST) & 1);
+            oz_mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t sa = base + (uint32_t)s * O2_STAGE_BYTES;
+            const uint32_t acc0 = (kb > 0) ? 1u : 0u;
+            if (pass == 0) {
+              const uint64_t dA0 = oz_desc(sa, 128 * 16, 128), dB0 = oz_desc(sa + O2_OP_BYTES, 128 * 16, 128);
+              if (!(batch.dbg & 1))
+#pragma unroll
+              for (int pa = OZ_PLANES - 1; pa >= 0; --pa) {
+#pragma unroll
+                for (int pb = OZ_PLANES - 1; pb >= 0; --pb) {
+                  if (pa + pb < 6 || pa + pb > 9) continue;
+                  const int lvl = pa + pb - 6;                         // 0..3; first pair of a level: pa == 6
+                  oz_mma_i8(tmem_base + (uint32_t)(lvl * O2_BN), dA0 + (uint64_t)((pa * O2_PLANE) >> 4),
+                            dB0 + (uint64_t)((pb * O2_PLANE) >> 4), idesc, (pa == OZ_PLANES - 1) ? acc0 : 1u);
+                }
+              }
+            } else {
+              const uint64_t dA0 = oz_desc(sa, 128 * 16, 128), dB0 = oz_desc(sa + O2_HI_OP_BYTES, 128 * 16, 128);
+              if (!(batch.dbg & 1))
+#pragma unroll
+              for (int pa = OZ_PLANES - 1; pa >= OZ_PLANES - O2_HI_PLANES; --pa) {
+#pragma unroll
+                for (int pb = OZ_PLANES - 1; pb >= OZ_PLANES - O2_HI_PLANES; --pb) {
+                  if (pa + pb < 10) continue;
+                  const int lvl = pa + pb - 10;                        // 0..2 = levels 4..6
+                  oz_mma_i8(tmem_base + (uint32_t)(lvl * O2_BN), dA0 + (uint64_t)(((pa - 4) * O2_PLANE) >> 4),
+                            dB0 + (uint64_t)(((pb - 4) * O2_PLANE) >> 4), idesc, (pa == OZ_PLANES - 1) ? acc0 : 1u);
+                }
+              }
+            }
+            oz_commit(empty0 + 8 * s);
+          }
+          oz_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, 64-column half = (warp - 2) / 4 ----------------
+    const int quarter = warp & 3, half = (warp - 2) >> 2, ewarp = warp - 2;
+    const int r_local = quarter * 32 + lane;
+    const int row = row0 + r_local;
+    constexpr int q = Q;
+    const int lane_base = lane & ~(q - 1);
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= O2_SCRATCH_SLOTS) __trap();
+    long long* scr = batch.scratch + (((size_t)smid * 8 + ewarp) * 64) * 32 + lane;   // [column][lane]
+    double g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.0;
+    const double sA = item.scaleA * 6.103515625e-05;   // 2^-14
+    const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+    int ev = 0;
+    for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+      const int n0 = jt * O2_BN + half * 64;
+      sB_s[ewarp][lane] = item.scaleB[n0 + lane] * sA;
+      sB_s[ewarp][lane + 32] = item.scaleB[n0 + 32 + lane] * sA;
+      __syncwarp();
+      // ---- low levels (3..0) -> one exact integer per element, parked in the scratch slab ----
+      oz_mbar_wait(acc_full, (uint32_t)(ev & 1)); ++ev;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        long long lo[32];
+#pragma unroll
+        for (int lvl = 3; lvl >= 0; --lvl) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            const uint32_t taddr = tcol0 + (uint32_t)(lvl * O2_BN + h * 32 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                           "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
+                         : "r"(taddr));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c) lo[c] = (lvl == 3) ? (long long)(int)v[c] : lo[c] * 256 + (long long)(int)v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) scr[(size_t)(h * 32 + c) * 32] = lo[c];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      oz_mbar_arrive(acc_empty);
+      // ---- high levels (6..4) ----
+      oz_mbar_wait(acc_full, (uint32_t)(ev & 1)); ++ev;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      long long hi[64];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int lvl = 2; lvl >= 0; --lvl) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            const uint32_t taddr = tcol0 + (uint32_t)(lvl * O2_BN + h * 32 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                           "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
+                         : "r"(taddr));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            hi[h * 32 + c] = (lvl == 2) ? (long long)(int)v[c] : hi[h * 32 + c] * 256 + (long long)(int)v[c];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      oz_mbar_arrive(acc_empty);
+      if (!(batch.dbg & 2)) {
+#pragma unroll
+        for (int c8 = 0; c8 < 64; c8 += 8) {
+          long long lo[8];                     // the parked low levels come back from L2 eight at a time
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lo[k] = scr[(size_t)(c8 + k) * 32];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c8 + k;
+            // sum_L acc_L 2^(8 (L - 6)) = hi 2^-16 + lo 2^-48
+            const double sum = fma((double)lo[k], 3.552713678800501e-15 /* 2^-48 */, (double)hi[c] * 1.52587890625e-05 /* 2^-16 */);
+            const int n = n0 + c;
+            const double val = sum * sB_s[ewarp][c];
+            oz_gram_update<Q>((n < batch.N) ? val : 0.0, lane_base, g);
+            if (n >= batch.N && row < batch.rows) {
+              const int e = n - batch.N;
+              if (e == 0) item.mu_raw[row] = val;
+              else if (item.W && e < batch.n_ext) item.W[(size_t)row * batch.ldw + (e - 1)] = val;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (row < batch.rows) {
+      double* dst = item.gqq_part + (size_t)(grp * 2 + half) * batch.gqq_stride + ((size_t)(row / q) * q + (row % q)) * q;
+      for (int j = 0; j < q; ++j) dst[j] = g[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiledOz)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int oz_make_map(CUtensorMap* map, const signed char* planes, int rows_alloc, int n_chunks, int box_rows) {
+static int oz_make_map(CUtensorMap* map, const signed char* planes, int rows_alloc, int n_chunks, int box_rows,
+                       int box_chunks = OZ_CH, int box_planes = OZ_PLANES) {
   static PFN_encodeTiledOz fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -362,7 +633,7 @@ static int oz_make_map(CUtensorMap* map, const signed char* planes, int rows_all
   // caps the fill rate at ~13 B/clk per SM).
   cuuint64_t dims[3] = {(cuuint64_t)rows_alloc * 2, (cuuint64_t)n_chunks, OZ_PLANES};
   cuuint64_t strides[2] = {(cuuint64_t)rows_alloc * 16, (cuuint64_t)n_chunks * rows_alloc * 16};
-  cuuint32_t box[3] = {(cuuint32_t)box_rows * 2, OZ_CH, OZ_PLANES};
+  cuuint32_t box[3] = {(cuuint32_t)box_rows * 2, (cuuint32_t)box_chunks, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<signed char*>(planes), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -394,6 +665,64 @@ int launch_ozaki_slice(const double* X, int rows, int cols, int ld, const double
 
 size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_out * 2 * OZ_MAXGROUPS * rows * q; }
 
+static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws, int n_sm, cudaStream_t s, LaunchCounter* lc) {
+  const OzakiArgs& a0 = args[0];
+  static bool attr_set = false;
+  const size_t smem = (size_t)O2_ST * O2_STAGE_BYTES + 1024;
+  if (!attr_set) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static long long* scratch = nullptr;   // 20 MB, L2-resident working set of the CTAs in flight; lives as long as the library
+  if (!scratch) CUDA_CHECK_RET(cudaMalloc(&scratch, (size_t)O2_SCRATCH_SLOTS * 8 * 64 * 32 * sizeof(long long)));
+  const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
+  const int n_tiles = a0.Rpad / O2_BN;
+  int groups;
+  {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("EVEREST_OZAKI_GROUPS"); forced = e ? atoi(e) : -1; }
+    const double panel_mb = (double)OZ_PLANES * OZ_BM * a0.ldk / (1 << 20);
+    groups = (int)((n_sm * panel_mb + 39.0) / 40.0);
+    if (forced >= 1) groups = forced;
+    groups = std::max(1, std::min(groups, std::min(n_tiles, OZ_MAXGROUPS)));
+  }
+  for (int m0 = 0; m0 < n_out; m0 += O2_MAXOUT) {
+    const int cnt = std::min(O2_MAXOUT, n_out - m0);
+    O2Batch batch;
+    memset(&batch, 0, sizeof(batch));
+    batch.rows = a0.rows; batch.q = a0.q; batch.N = a0.N; batch.n_ext = a0.n_ext; batch.Rpad = a0.Rpad; batch.ldw = a0.ldw;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("EVEREST_OZAKI_DBG"); dbg = e ? atoi(e) : 0; } batch.dbg = dbg; }
+    batch.n_chunks_k = a0.ldk / 16; batch.n_groups = groups; batch.gqq_stride = (long long)a0.rows * a0.q;
+    batch.scratch = scratch;
+    for (int i = 0; i < cnt; ++i) {
+      const OzakiArgs& a = args[m0 + i];
+      int rc;
+      if ((rc = oz_make_map(&batch.item[i].mapA, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM, O2_CH, OZ_PLANES)) != BO_OK) return rc;
+      if ((rc = oz_make_map(&batch.item[i].mapB, a.Bplanes, a.Rpad, a.ldk / 16, O2_BN, O2_CH, OZ_PLANES)) != BO_OK) return rc;
+      if ((rc = oz_make_map(&batch.item[i].mapA3, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM, O2_CH, O2_HI_PLANES)) != BO_OK) return rc;
+      if ((rc = oz_make_map(&batch.item[i].mapB3, a.Bplanes, a.Rpad, a.ldk / 16, O2_BN, O2_CH, O2_HI_PLANES)) != BO_OK) return rc;
+      batch.item[i].scaleB = a.scaleB; batch.item[i].scaleA = a.scaleA;
+      batch.item[i].gqq_part = part_ws + (size_t)(m0 + i) * 2 * groups * batch.gqq_stride;
+      batch.item[i].W = a.W; batch.item[i].mu_raw = a.mu_raw;
+    }
+    dim3 grid(row_tiles * groups, cnt);
+    if (a0.q == 1) ozaki_gemm2p_kernel<1><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else if (a0.q == 2) ozaki_gemm2p_kernel<2><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else if (a0.q == 4) ozaki_gemm2p_kernel<4><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else ozaki_gemm2p_kernel<8><<<grid, OZ_THREADS, smem, s>>>(batch);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    for (int i = 0; i < cnt; ++i) {
+      int rc = launch_sum_gram_partials(batch.item[i].gqq_part, batch.gqq_stride, 2 * groups, args[m0 + i].Gqq, s, lc);
+      if (rc != BO_OK) return rc;
+    }
+  }
+  return BO_OK;
+}
+
 int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStream_t s, LaunchCounter* lc) {
   if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
   const OzakiArgs& a0 = args[0];
@@ -404,10 +733,16 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
   static bool attr_set = false;
   const size_t smem = (size_t)OZ_ST * OZ_STAGE_BYTES + 1024;
   if (!attr_set) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
+  static int tile_n = 0;
+  if (!tile_n) { const char* e = getenv("EVEREST_OZAKI_TILE"); tile_n = (e && atoi(e) == 128) ? 128 : 64; }
+  if (tile_n == 128 && a0.Rpad % O2_BN == 0) return launch_ozaki_gemm2p(args, n_out, part_ws, n_sm, s, lc);
   const int n_tiles = a0.Rpad / OZ_BN;
   // column groups: resident K(X*,X) digit panels (n_sm / G panels of 7 * 128 * ldk bytes) should stay in L2 (~40 MB)
   int groups;
@@ -452,7 +787,10 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
       batch.item[i].W = a.W; batch.item[i].mu_raw = a.mu_raw;
     }
     dim3 grid(row_tiles * groups, cnt);
-    ozaki_gemm_kernel<<<grid, OZ_THREADS, smem, s>>>(batch);
+    if (a0.q == 1) ozaki_gemm_kernel<1><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else if (a0.q == 2) ozaki_gemm_kernel<2><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else if (a0.q == 4) ozaki_gemm_kernel<4><<<grid, OZ_THREADS, smem, s>>>(batch);
+    else ozaki_gemm_kernel<8><<<grid, OZ_THREADS, smem, s>>>(batch);
     if (lc) lc->n++;
     CUDA_CHECK_RET(cudaGetLastError());
     for (int i = 0; i < cnt; ++i) {
