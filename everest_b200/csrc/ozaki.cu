@@ -107,7 +107,7 @@ struct OzBatch {
   OzItem item[OZ_MAXOUT];
   int rows, q, N, n_ext, Rpad, ldw, n_chunks_k;   // n_chunks_k = ldk / 16
   int n_groups;
-  int dbg;                                        // EVEREST_OZAKI_DBG bits: 1 = no MMAs, 2 = no epilogue math (timing experiments)
+  int dbg;                                        // EVEREST_OZAKI_DBG bits: 1 = no MMAs, 2 = no epilogue math, 4 = no TMA (pair kernel)
   int gbeg[OZ_MAXGROUPS + 1];                     // column-tile ranges (units of OZ_BN columns)
   long long gqq_stride;
 };
@@ -609,6 +609,285 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the two-pass kernel (tcgen05 cta_group::2, M = 256 x N = 128 per MMA).  Shared-memory bandwidth
+// (128 B/clk per SM) is what bounds the single-CTA kernels: an M128 x N128 x K32 MMA reads 4 KB of A and 4 KB of B while
+// TMA writes another 2.6 KB per MMA into the same memory -> 83 clocks instead of the pipe's 64.  In a pair each SM reads
+// its own 128 rows of A and only HALF of the B tile (the other half arrives from the peer SM) and TMA writes 1.9 KB per
+// MMA: 62 clocks' worth, i.e. the tensor pipe becomes the bound.  Both CTAs load (TMA signalling the leader's barriers),
+// the leader issues every MMA, commits are multicast to both CTAs, each CTA drains its own TMEM.
+// ------------------------------------------------------------------------------------------------
+#define O3_ST 4
+#define O3_B_PLANE (O2_CH * 64 * 16)               // 2048 B: half of the B tile
+#define O3_A_BYTES (OZ_PLANES * O2_PLANE)          // 28672
+#define O3_B_BYTES (OZ_PLANES * O3_B_PLANE)        // 14336
+#define O3_STAGE_BYTES (O3_A_BYTES + O3_B_BYTES)   // 43008
+#define O3_HI_A_BYTES (O2_HI_PLANES * O2_PLANE)    // 12288
+#define O3_HI_B_BYTES (O2_HI_PLANES * O3_B_PLANE)  // 6144
+
+__device__ __forceinline__ uint32_t oz_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// own shared memory as destination, the mbarrier lives in the pair's leader CTA
+__device__ __forceinline__ void oz_tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void oz_mma_i8_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+      "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+__device__ __forceinline__ void oz_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
+}
+
+template <int Q>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2c_kernel(const __grid_constant__ O2Batch batch) {
+  extern __shared__ unsigned char ozraw[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t bars[2 * O3_ST + 2];
+  __shared__ double sB_s[8][64];
+  const O2Item& item = batch.item[blockIdx.y];
+  const uint32_t base = (oz_smem_u32(ozraw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int pair = (int)(blockIdx.x >> 1);
+  const int grp = pair % batch.n_groups, row_pair = pair / batch.n_groups;
+  const int row0 = (row_pair * 2 + (int)rank) * OZ_BM;
+  const int n_tiles = batch.Rpad / O2_BN, G = batch.n_groups;
+  auto tile_at = [&](int i) { const int j = i * G + ((i & 1) ? (G - 1 - grp) : grp); return (j < n_tiles) ? j : -1; };
+  const uint32_t full0 = oz_smem_u32(&bars[0]), empty0 = oz_smem_u32(&bars[O3_ST]);
+  const uint32_t acc_full = oz_smem_u32(&bars[2 * O3_ST]), acc_empty = oz_smem_u32(&bars[2 * O3_ST + 1]);
+  if (tid == 0) {
+    for (int s = 0; s < O3_ST; ++s) { oz_mbar_init(full0 + 8 * s, 1); oz_mbar_init(empty0 + 8 * s, 1); }
+    oz_mbar_init(acc_full, 1);
+    oz_mbar_init(acc_empty, 16);            // one arrival per epilogue warp of both CTAs (leader's barrier only)
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto k_blocks_of = [&](int jt) {
+    const int n_end = (jt + 1) * O2_BN;
+    const int kmax = batch.n_chunks_k * 16;
+    const int kbytes = (n_end <= batch.N) ? n_end : kmax;
+    return (min(kbytes, kmax) + O2_BK - 1) / O2_BK;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs; the leader also posts the byte count of the pair) ----------------
+    if (lane == 0 && !(batch.dbg & 4)) {
+      int it = 0;
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+        const int nkb = k_blocks_of(jt);
+        const int brow = (jt * O2_BN + (int)rank * 64) * 2;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % O3_ST;
+            const uint32_t ph = (uint32_t)((it / O3_ST) & 1);
+            oz_mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t fb = oz_mapa(full0 + 8 * s, 0);
+            const uint32_t dst = base + (uint32_t)s * O3_STAGE_BYTES;
+            if (pass == 0) {
+              if (rank == 0) oz_mbar_expect_tx(full0 + 8 * s, 2 * O3_STAGE_BYTES);
+              oz_tma_load_3d_2sm(dst, &item.mapA, row0 * 2, kb * O2_CH, 0, fb);
+              oz_tma_load_3d_2sm(dst + O3_A_BYTES, &item.mapB, brow, kb * O2_CH, 0, fb);
+            } else {
+              if (rank == 0) oz_mbar_expect_tx(full0 + 8 * s, 2 * (O3_HI_A_BYTES + O3_HI_B_BYTES));
+              oz_tma_load_3d_2sm(dst, &item.mapA3, row0 * 2, kb * O2_CH, OZ_PLANES - O2_HI_PLANES, fb);
+              oz_tma_load_3d_2sm(dst + O3_HI_A_BYTES, &item.mapB3, brow, kb * O2_CH, OZ_PLANES - O2_HI_PLANES, fb);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: leader CTA only ----------------
+    if (lane == 0 && rank == 0) {
+      uint32_t idesc = 0;
+      idesc |= 2u << 4;                       // D = S32
+      idesc |= 1u << 7;                       // A signed 8 bit
+      idesc |= 1u << 10;                      // B signed 8 bit
+      idesc |= (uint32_t)(O2_BN >> 3) << 17;
+      idesc |= (uint32_t)(256 >> 4) << 24;    // M = 256 across the pair
+      int it = 0, ev = 0;
+      for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+        const int nkb = k_blocks_of(jt);
+        for (int pass = 0; pass < 2; ++pass, ++ev) {
+          oz_mbar_wait(acc_empty, (uint32_t)((ev & 1) ^ 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % O3_ST;
+            const uint32_t ph = (uint32_t)((it / O3_ST) & 1);
+            if (!(batch.dbg & 4)) oz_mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t sa = base + (uint32_t)s * O3_STAGE_BYTES;
+            const uint32_t acc0 = (kb > 0) ? 1u : 0u;
+            if (pass == 0) {
+              const uint64_t dA0 = oz_desc(sa, 128 * 16, 128), dB0 = oz_desc(sa + O3_A_BYTES, 64 * 16, 128);
+              if (!(batch.dbg & 1))
+#pragma unroll
+              for (int pa = OZ_PLANES - 1; pa >= 0; --pa) {
+#pragma unroll
+                for (int pb = OZ_PLANES - 1; pb >= 0; --pb) {
+                  if (pa + pb < 6 || pa + pb > 9) continue;
+                  const int lvl = pa + pb - 6;
+                  oz_mma_i8_2sm(tmem_base + (uint32_t)(lvl * O2_BN), dA0 + (uint64_t)((pa * O2_PLANE) >> 4),
+                                dB0 + (uint64_t)((pb * O3_B_PLANE) >> 4), idesc, (pa == OZ_PLANES - 1) ? acc0 : 1u);
+                }
+              }
+            } else {
+              const uint64_t dA0 = oz_desc(sa, 128 * 16, 128), dB0 = oz_desc(sa + O3_HI_A_BYTES, 64 * 16, 128);
+              if (!(batch.dbg & 1))
+#pragma unroll
+              for (int pa = OZ_PLANES - 1; pa >= OZ_PLANES - O2_HI_PLANES; --pa) {
+#pragma unroll
+                for (int pb = OZ_PLANES - 1; pb >= OZ_PLANES - O2_HI_PLANES; --pb) {
+                  if (pa + pb < 10) continue;
+                  const int lvl = pa + pb - 10;
+                  oz_mma_i8_2sm(tmem_base + (uint32_t)(lvl * O2_BN), dA0 + (uint64_t)(((pa - 4) * O2_PLANE) >> 4),
+                                dB0 + (uint64_t)(((pb - 4) * O3_B_PLANE) >> 4), idesc, (pa == OZ_PLANES - 1) ? acc0 : 1u);
+                }
+              }
+            }
+            if (!(batch.dbg & 4)) oz_commit_2sm(empty0 + 8 * s);    // frees the stage in both CTAs
+          }
+          oz_commit_2sm(acc_full);            // both CTAs' epilogues
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own TMEM): warps 2..9 ----------------
+    const int quarter = warp & 3, half = (warp - 2) >> 2, ewarp = warp - 2;
+    const int r_local = quarter * 32 + lane;
+    const int row = row0 + r_local;
+    constexpr int q = Q;
+    const int lane_base = lane & ~(q - 1);
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= O2_SCRATCH_SLOTS) __trap();
+    long long* scr = batch.scratch + (((size_t)smid * 8 + ewarp) * 64) * 32 + lane;
+    const uint32_t acc_empty_leader = oz_mapa(acc_empty, 0);
+    double g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.0;
+    const double sA = item.scaleA * 6.103515625e-05;   // 2^-14
+    const uint32_t tcol0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+    int ev = 0;
+    for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
+      const int n0 = jt * O2_BN + half * 64;
+      sB_s[ewarp][lane] = item.scaleB[n0 + lane] * sA;
+      sB_s[ewarp][lane + 32] = item.scaleB[n0 + 32 + lane] * sA;
+      __syncwarp();
+      oz_mbar_wait(acc_full, (uint32_t)(ev & 1)); ++ev;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        long long lo[32];
+#pragma unroll
+        for (int lvl = 3; lvl >= 0; --lvl) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            const uint32_t taddr = tcol0 + (uint32_t)(lvl * O2_BN + h * 32 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                           "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
+                         : "r"(taddr));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c) lo[c] = (lvl == 3) ? (long long)(int)v[c] : lo[c] * 256 + (long long)(int)v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) scr[(size_t)(h * 32 + c) * 32] = lo[c];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive_cluster(acc_empty_leader);
+      oz_mbar_wait(acc_full, (uint32_t)(ev & 1)); ++ev;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      long long hi[64];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int lvl = 2; lvl >= 0; --lvl) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            const uint32_t taddr = tcol0 + (uint32_t)(lvl * O2_BN + h * 32 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                         : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                           "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                           "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
+                         : "r"(taddr));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            hi[h * 32 + c] = (lvl == 2) ? (long long)(int)v[c] : hi[h * 32 + c] * 256 + (long long)(int)v[c];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive_cluster(acc_empty_leader);
+      if (!(batch.dbg & 2)) {
+#pragma unroll
+        for (int c8 = 0; c8 < 64; c8 += 8) {
+          long long lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lo[k] = scr[(size_t)(c8 + k) * 32];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c8 + k;
+            const double sum = fma((double)lo[k], 3.552713678800501e-15 /* 2^-48 */, (double)hi[c] * 1.52587890625e-05 /* 2^-16 */);
+            const int n = n0 + c;
+            const double val = sum * sB_s[ewarp][c];
+            oz_gram_update<Q>((n < batch.N) ? val : 0.0, lane_base, g);
+            if (n >= batch.N && row < batch.rows) {
+              const int e = n - batch.N;
+              if (e == 0) item.mu_raw[row] = val;
+              else if (item.W && e < batch.n_ext) item.W[(size_t)row * batch.ldw + (e - 1)] = val;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (row < batch.rows) {
+      double* dst = item.gqq_part + (size_t)(grp * 2 + half) * batch.gqq_stride + ((size_t)(row / q) * q + (row % q)) * q;
+      for (int j = 0; j < q; ++j) dst[j] = g[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();       // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiledOz)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -665,15 +944,21 @@ int launch_ozaki_slice(const double* X, int rows, int cols, int ld, const double
 
 size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_out * 2 * OZ_MAXGROUPS * rows * q; }
 
-static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws, int n_sm, cudaStream_t s, LaunchCounter* lc) {
+static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws, int n_sm, bool pair, cudaStream_t s, LaunchCounter* lc) {
   const OzakiArgs& a0 = args[0];
   static bool attr_set = false;
-  const size_t smem = (size_t)O2_ST * O2_STAGE_BYTES + 1024;
+  const size_t smem = pair ? (size_t)O3_ST * O3_STAGE_BYTES + 1024 : (size_t)O2_ST * O2_STAGE_BYTES + 1024;
   if (!attr_set) {
+    const size_t smem = (size_t)O2_ST * O2_STAGE_BYTES + 1024;
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2p_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int smem_pair = O3_ST * O3_STAGE_BYTES + 1024;
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
     attr_set = true;
   }
   static long long* scratch = nullptr;   // 20 MB, L2-resident working set of the CTAs in flight; lives as long as the library
@@ -701,14 +986,22 @@ static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws
       const OzakiArgs& a = args[m0 + i];
       int rc;
       if ((rc = oz_make_map(&batch.item[i].mapA, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM, O2_CH, OZ_PLANES)) != BO_OK) return rc;
-      if ((rc = oz_make_map(&batch.item[i].mapB, a.Bplanes, a.Rpad, a.ldk / 16, O2_BN, O2_CH, OZ_PLANES)) != BO_OK) return rc;
+      const int b_rows = pair ? O2_BN / 2 : O2_BN;   // in a CTA pair every CTA loads half of the B tile
+      if ((rc = oz_make_map(&batch.item[i].mapB, a.Bplanes, a.Rpad, a.ldk / 16, b_rows, O2_CH, OZ_PLANES)) != BO_OK) return rc;
       if ((rc = oz_make_map(&batch.item[i].mapA3, a.Aplanes, a.rows_alloc, a.ldk / 16, OZ_BM, O2_CH, O2_HI_PLANES)) != BO_OK) return rc;
-      if ((rc = oz_make_map(&batch.item[i].mapB3, a.Bplanes, a.Rpad, a.ldk / 16, O2_BN, O2_CH, O2_HI_PLANES)) != BO_OK) return rc;
+      if ((rc = oz_make_map(&batch.item[i].mapB3, a.Bplanes, a.Rpad, a.ldk / 16, b_rows, O2_CH, O2_HI_PLANES)) != BO_OK) return rc;
       batch.item[i].scaleB = a.scaleB; batch.item[i].scaleA = a.scaleA;
       batch.item[i].gqq_part = part_ws + (size_t)(m0 + i) * 2 * groups * batch.gqq_stride;
       batch.item[i].W = a.W; batch.item[i].mu_raw = a.mu_raw;
     }
     dim3 grid(row_tiles * groups, cnt);
+    if (pair) {
+      grid.x = 2 * ((row_tiles + 1) / 2) * groups;
+      if (a0.q == 1) ozaki_gemm2c_kernel<1><<<grid, OZ_THREADS, smem, s>>>(batch);
+      else if (a0.q == 2) ozaki_gemm2c_kernel<2><<<grid, OZ_THREADS, smem, s>>>(batch);
+      else if (a0.q == 4) ozaki_gemm2c_kernel<4><<<grid, OZ_THREADS, smem, s>>>(batch);
+      else ozaki_gemm2c_kernel<8><<<grid, OZ_THREADS, smem, s>>>(batch);
+    } else
     if (a0.q == 1) ozaki_gemm2p_kernel<1><<<grid, OZ_THREADS, smem, s>>>(batch);
     else if (a0.q == 2) ozaki_gemm2p_kernel<2><<<grid, OZ_THREADS, smem, s>>>(batch);
     else if (a0.q == 4) ozaki_gemm2p_kernel<4><<<grid, OZ_THREADS, smem, s>>>(batch);
@@ -741,8 +1034,8 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
   }
   const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
   static int tile_n = 0;
-  if (!tile_n) { const char* e = getenv("EVEREST_OZAKI_TILE"); tile_n = (e && atoi(e) == 128) ? 128 : 64; }
-  if (tile_n == 128 && a0.Rpad % O2_BN == 0) return launch_ozaki_gemm2p(args, n_out, part_ws, n_sm, s, lc);
+  if (!tile_n) { const char* e = getenv("EVEREST_OZAKI_TILE"); tile_n = e ? atoi(e) : 128; if (tile_n != 64 && tile_n != 256) tile_n = 128; }
+  if (tile_n >= 128 && a0.Rpad % O2_BN == 0) return launch_ozaki_gemm2p(args, n_out, part_ws, n_sm, tile_n == 256, s, lc);
   const int n_tiles = a0.Rpad / OZ_BN;
   // column groups: resident K(X*,X) digit panels (n_sm / G panels of 7 * 128 * ldk bytes) should stay in L2 (~40 MB)
   int groups;
