@@ -78,7 +78,7 @@ __global__ void zero_upper_kernel(double* __restrict__ A, int ld, int n) {
 int chol_blocked(double* A, int ld, int n, double* work_dinv, int* info_dev, cudaStream_t s, LaunchCounter* lc) {
   // info_dev must be zeroed by the caller; work_dinv holds ceil(n/64) blocks of 64*64 doubles.
   const size_t potrf_smem = (size_t)2 * CB * CB_LD * sizeof(double);
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
   if (!attr_set) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem));
     attr_set = true;

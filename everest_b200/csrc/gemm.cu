@@ -136,7 +136,7 @@ int launch_gemm_nt(int m, int n, int k, double alpha, const double* A, int lda, 
     bo_set_error("gemm_nt: k=%d padded to 16 exceeds lda=%d / ldb=%d", k, lda, ldb);
     return BO_ERR_INVALID;
   }
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
   size_t smem = (size_t)G1_ST * (G1_BM + G1_BN) * GLDS * sizeof(double);
   if (!attr_set) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -579,7 +579,7 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
     if (a.ldk % GK != 0 || a.Rpad % PG_BN != 0 || a.N + a.n_ext > a.Rpad) { bo_set_error("posterior_gemm: padding violated"); return BO_ERR_INVALID; }
   }
   if (use_v2(args[0])) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
     const size_t smem = (size_t)P2_ST * P2_STAGE_BYTES + 2 * P2_ST * 8 + 1024;
     if (!attr_set) {
       CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -663,7 +663,7 @@ int launch_posterior_gemm_multi(const PostGemmArgs* args, int n_out, double* par
     }
     return BO_OK;
   }
-  static bool attr_set1 = false;
+  static PerDeviceOnce attr_once1; bool& attr_set1 = *attr_once1.slot();
   const size_t smem1 = posterior_gemm_smem_bytes();
   if (!attr_set1) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(posterior_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

@@ -422,7 +422,7 @@ int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool col
     const double* Aq = rows.Xs[l];
     const double* n2a = rows.n2[l];
     const size_t smf = ((size_t)3 * CC_TILE * CC_LDS + (size_t)CC_TILE * CC3_CLD + 2 * CC_TILE) * sizeof(double);
-    static bool attr_set = false;
+    static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
     if (!attr_set) {
       CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
       CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_fast_kernel<BO_LEAF_MATERN12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));

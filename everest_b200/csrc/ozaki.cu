@@ -946,7 +946,7 @@ size_t ozaki_partial_ws_doubles(int rows, int q, int n_out) { return (size_t)n_o
 
 static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws, int n_sm, bool pair, cudaStream_t s, LaunchCounter* lc) {
   const OzakiArgs& a0 = args[0];
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
   const size_t smem = pair ? (size_t)O3_ST * O3_STAGE_BYTES + 1024 : (size_t)O2_ST * O2_STAGE_BYTES + 1024;
   if (!attr_set) {
     const size_t smem = (size_t)O2_ST * O2_STAGE_BYTES + 1024;
@@ -961,7 +961,11 @@ static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
     attr_set = true;
   }
-  static long long* scratch = nullptr;   // 20 MB, L2-resident working set of the CTAs in flight; lives as long as the library
+  // 20 MB per device, L2-resident working set of the CTAs in flight; lives as long as the library
+  static long long* scratch_dev[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  long long*& scratch = scratch_dev[dev_id & 63];
   if (!scratch) CUDA_CHECK_RET(cudaMalloc(&scratch, (size_t)O2_SCRATCH_SLOTS * 8 * 64 * 32 * sizeof(long long)));
   const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
   const int n_tiles = a0.Rpad / O2_BN;
@@ -1023,7 +1027,7 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
   if (a0.ldk % 16 || a0.Rpad % OZ_BN || !part_ws) { bo_set_error("ozaki_gemm: padding / workspace violated"); return BO_ERR_INVALID; }
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-  static bool attr_set = false;
+  static PerDeviceOnce attr_once; bool& attr_set = *attr_once.slot();
   const size_t smem = (size_t)OZ_ST * OZ_STAGE_BYTES + 1024;
   if (!attr_set) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
