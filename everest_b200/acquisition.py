@@ -89,6 +89,9 @@ class _DeviceAcquisition:
         b, q, _ = Xd.shape
         out = torch.empty(b, dtype=torch.double, device=self.model.device)
         info = torch.zeros(b, dtype=torch.int32, device=self.model.device)
+        if b == 0:                       # empty t-batch: BoTorch returns an empty tensor
+            self.last_info = info
+            return out.cpu() if on_cpu else out
         zq = self.base_samples_q(q)
         with torch.cuda.device(self.model.device):
             L.check(self.model.lib.bo_acqf_forward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
@@ -119,6 +122,10 @@ class _DeviceAcquisition:
         out = torch.empty(b, dtype=torch.double, device=self.model.device)
         dX = torch.empty_like(Xd)
         info = torch.zeros(b, dtype=torch.int32, device=self.model.device)
+        if b == 0:
+            self.last_info = info
+            dX = dX[:, :q_in].contiguous()
+            return (out.cpu(), dX.cpu()) if on_cpu else (out, dX)
         zq = self.base_samples_q(q)
         with torch.cuda.device(self.model.device):
             L.check(self.model.lib.bo_acqf_forward_backward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq),

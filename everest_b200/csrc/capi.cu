@@ -129,6 +129,7 @@ struct bo_state {
   DevBuf best_f_s;
   int log_hvi = 0;
   int ozaki = 0;               // posterior GEMM of large batches on the INT8 tensor cores (ozaki.cu)
+  int ozaki_tile = 0;          // kernel variant of the INT8 GEMM (0 = default)
   int oz_calib = 0;            // automatic mode: 0 = not checked yet for this prepared state, 1 = accepted, -1 = rejected
   double oz_err_var = 0.0, oz_err_mu = 0.0;   // what the self-check measured
   DevBuf wsOzRef;
@@ -737,6 +738,12 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
   if (nm == "ozaki") {
     if (value != 0.0 && value != 1.0 && value != 2.0) { bo_set_error("ozaki must be 0 (off), 1 (automatic) or 2 (always)"); return BO_ERR_INVALID; }
     st->ozaki = (int)value;
+    st->oz_calib = 0;
+  } else if (nm == "ozaki_tile") {
+    // 0 = default (EVEREST_OZAKI_TILE or 128); 64 = one-pass 128x64 tiles, 128 = two-pass 128x128, 256 = two-pass on CTA pairs
+    if (value != 0.0 && value != 64.0 && value != 128.0 && value != 256.0) { bo_set_error("ozaki_tile must be 0, 64, 128 or 256"); return BO_ERR_INVALID; }
+    st->ozaki_tile = (int)value;
+    st->oz_calib = 0;
   } else if (nm == "log_hvi") {
     if (st->acqf_kind != 1 && st->acqf_kind != 2) { bo_set_error("log_hvi applies to a prepared qNEHVI / qEHVI"); return BO_ERR_STATE; }
     st->log_hvi = value != 0.0;
@@ -777,6 +784,7 @@ static int ensure_kinv(bo_state* st, OutputH& o, cudaStream_t s) {
 static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev, double* out_dev,
                     double* dX_dev, int32_t* info_dev, void* stream) {
   if (!st || !st->factorized || st->acqf_kind == 0) { bo_set_error("forward before prepare"); return BO_ERR_STATE; }
+  if (b == 0 && q >= 1 && q <= BO_MAX_Q) return BO_OK;   // empty t-batch: nothing to score (BoTorch returns an empty tensor)
   if (b < 1 || q < 1 || q > BO_MAX_Q) { bo_set_error("bad b=%d / q=%d (q <= %d)", b, q, BO_MAX_Q); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   if (st->timing) {
@@ -883,7 +891,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       }
       rec_end(st, s);
       rec_begin(st, "posterior_gemm", s);
-      RC(launch_ozaki_gemm(oa.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+      RC(launch_ozaki_gemm(oa.data(), M, st->wsGramPart.as<double>(), st->ozaki_tile, s, &st->lc));
       rec_end(st, s);
       if (oz_check) {
         const int pr = std::min(rows, (256 / q) * q);
@@ -1076,6 +1084,7 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
                                     double* out_host, void* stream) {
   if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
+  if (b == 0) return BO_OK;
   size_t in_bytes = (size_t)b * q * st->d * 8, out_bytes = (size_t)b * 8;
   if (st->pin_in_bytes < in_bytes) {
     if (st->pin_in) cudaFreeHost(st->pin_in);

@@ -1020,7 +1020,7 @@ static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws
   return BO_OK;
 }
 
-int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStream_t s, LaunchCounter* lc) {
+int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, int tile, cudaStream_t s, LaunchCounter* lc) {
   if (n_out <= 0 || args[0].rows <= 0) return BO_OK;
   const OzakiArgs& a0 = args[0];
   if (!(a0.q == 1 || a0.q == 2 || a0.q == 4 || a0.q == 8) || a0.rows % a0.q) { bo_set_error("ozaki_gemm: q must be 1, 2, 4 or 8"); return BO_ERR_INVALID; }
@@ -1037,8 +1037,9 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, cudaStr
     attr_set = true;
   }
   const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
-  static int tile_n = 0;
-  if (!tile_n) { const char* e = getenv("EVEREST_OZAKI_TILE"); tile_n = e ? atoi(e) : 128; if (tile_n != 64 && tile_n != 256) tile_n = 128; }
+  static int tile_env = 0;
+  if (!tile_env) { const char* e = getenv("EVEREST_OZAKI_TILE"); tile_env = e ? atoi(e) : 128; if (tile_env != 64 && tile_env != 256) tile_env = 128; }
+  const int tile_n = tile ? tile : tile_env;
   if (tile_n >= 128 && a0.Rpad % O2_BN == 0) return launch_ozaki_gemm2p(args, n_out, part_ws, n_sm, tile_n == 256, s, lc);
   const int n_tiles = a0.Rpad / OZ_BN;
   // column groups: resident K(X*,X) digit panels (n_sm / G panels of 7 * 128 * ldk bytes) should stay in L2 (~40 MB)

@@ -174,8 +174,11 @@ int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const d
 
 /* Named options of the prepared acquisition function: "ozaki" (run the posterior GEMM as an error-free INT8 digit-plane
  * product on the tcgen05 tensor cores instead of FP64 DMMA: 0 = never, 1 = automatically for large problems (default, or
- * EVEREST_OZAKI), 2 = whenever the shape allows), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of
- * qEHVI / qNEHVI -- MoboStrategy's default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2). */
+ * EVEREST_OZAKI), 2 = whenever the shape allows; in mode 1 the first large call after every prepare checks the INT8
+ * result against the FP64 kernel on a probe and falls back to FP64 unless the posterior variance agrees to 1e-10),
+ * "ozaki_tile" (kernel variant of that product: 0 = default, 64 = one-pass 128x64 tiles, 128 = two-pass 128x128 tiles,
+ * 256 = two-pass on CTA pairs), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of qEHVI / qNEHVI -- MoboStrategy's
+ * default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2).  An empty t-batch (b = 0) is a no-op. */
 int bo_acqf_set_option(bo_state* st, const char* name, double value);
 
 /* AcquisitionFunction.forward(X[b, q, d]) -> [b]  (called from calc_acquisition botorch.py:223,

@@ -540,5 +540,47 @@ def test_int8_digit_plane_gemm_matches_fp64_and_oracle(N, q, raw, d):
     # determinism of the INT8 path
     acq_d.set_option("ozaki", 2)
     assert torch.equal(acq_d(Xd).cpu(), outs[2][0])
+    # the three kernel variants (one-pass 128x64, two-pass 128x128, two-pass on CTA pairs) compute the same exact integer
+    # sums and differ only in how the FP64 Gram partial sums are grouped
+    for tile in (64, 128, 256):
+        acq_d.set_option("ozaki_tile", tile)
+        v_t = acq_d(Xd).cpu()
+        mu_t = st.debug_get("mu").view(-1)[: X.shape[0] * q * st.M].cpu()
+        assert float((v_t - outs[0][0]).abs().max()) < 1e-10 * scale, tile
+        assert float((mu_t - outs[0][2]).abs().max()) < 1e-10 * float(outs[0][2].abs().max()), tile
+        assert torch.equal(acq_d(Xd).cpu(), v_t), tile
+    acq_d.set_option("ozaki_tile", 0)
     with pytest.raises(ValueError):
         acq_d.set_option("ozaki", 3)
+    with pytest.raises(ValueError):
+        acq_d.set_option("ozaki_tile", 32)
+
+
+def test_int8_self_check_and_empty_batch():
+    """Automatic mode: the first large call after a prepare runs the INT8 and the FP64 kernel on a probe of rows and keeps
+    the INT8 path only if the posterior variance agrees to 1e-10; either way the values match the FP64 kernel's.  An
+    empty t-batch returns an empty tensor."""
+    p = Cf.zdt1_qnehvi(N=1000, S=16, raw=1200, d=8, q=4)
+    st = Cf.build_state(p)
+    acq = Cf.build_acqf(p, st, prune_samples=64)
+    Xd = Cf.candidates(p).to(st.device)
+    assert Xd.shape[0] * 4 * 1000 >= 1 << 22
+    acq.set_option("ozaki", 0)
+    v64 = acq(Xd).clone()
+    assert st.debug_get("ozaki_check", capacity=16)[0] == 0        # nothing checked yet
+    acq.set_option("ozaki", 1)
+    v_auto = acq(Xd)
+    state, err_var, err_mu = st.debug_get("ozaki_check", capacity=16).tolist()
+    assert state in (1.0, -1.0)
+    assert (state == 1.0) == (err_var <= 1e-10 and err_mu <= 1e-10)
+    assert float((v_auto - v64).abs().max()) <= 1e-10 * float(v64.abs().max())
+    assert torch.equal(acq(Xd), v_auto) or state == -1.0
+    # a small call stays on the FP64 kernels and does not disturb the decision
+    v_small = acq(Xd[:16])
+    assert float((v_small - v64[:16]).abs().max()) <= 1e-10 * float(v64.abs().max())
+    assert st.debug_get("ozaki_check", capacity=16)[0] == state
+    # empty t-batch
+    empty = acq(Xd[:0])
+    assert empty.shape == (0,)
+    v0, g0 = acq.forward_backward(Xd[:0])
+    assert v0.shape == (0,) and g0.shape == (0, 4, 8)
