@@ -360,14 +360,19 @@ def run_b200(args):
                 i8_peak, src = 4500.0, "nominal 4.5 POPS dense INT8 (MEASURED_PEAKS.json unavailable)"
             i8_ops = 28.0 * flops_per_step / (g_ms * 1e-3) / 1e12
             roofline.update({
-                "kernel": "ozaki_gemm_kernel (tcgen05.mma.kind::i8, TMEM accumulators: 28 exact INT8 digit-plane products "
-                          "= one FP64-accurate GEMM)",
+                "kernel": "ozaki_gemm2p_kernel (tcgen05.mma.kind::i8 M128xN128xK32, TMEM accumulators, two passes over K: "
+                          "28 exact INT8 digit-plane products = one FP64-accurate GEMM)",
                 "achieved": i8_ops, "peak": i8_peak, "unit": "TFLOP/s", "frac": i8_ops / i8_peak,
                 "peak_source": src + "; tools/i8_mma_probe: 4.6 POPS (N >= 128) / 3.07 POPS (N = 64, this kernel's tile) "
                                      "single-SM issue rate x 148 at 1.9 GHz",
                 "algorithmic_ops_note": "achieved = 28 digit-plane products x algorithmic FP64 flops / kernel time (INT8 TOP/s)",
                 "fp64_equivalent_tflops": achieved, "fp64_pipe_peak_tflops": peak, "fp64_equivalent_over_fp64_pipe": achieved / peak,
-                "traffic": None})
+                # one ncu --set full capture of the kernel on this workload (profiles/r01_s3_ncu_summary.txt): 3.50 GB read +
+                # 1.13 GB written per launch; algorithmic 1.9 GB (7 digit planes of K(X*,X) and LinvExt, both outputs) -- the
+                # rest is the second pass over planes 4..6 and the write-back of the 128 KB-per-SM integer scratch slab
+                "traffic": 4.63e9 if (args.workload == "zdt1" and not args.raw_samples) else None,
+                "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full, "
+                                "profiles/r01_s3_ncu_summary.txt); algorithmic 1.9 GB; 0.8 TB/s = 12 % of HBM, not the bound"})
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------
     cpu = None
