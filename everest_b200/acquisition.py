@@ -54,6 +54,17 @@ class _DeviceAcquisition:
         """The handle holds ONE prepared acquisition function: remember which object prepared it last."""
         self.model._active_acqf = self
 
+    def activate(self):
+        """Make this the prepared acquisition function of its DeviceGPState again (the handle holds one at a time):
+        optimize_acqf_list walks a list of acquisition functions built on the same model.  Re-runs the prepare call with
+        the stored arguments (same base samples, same pruned baseline): results are identical to the first preparation."""
+        if getattr(self.model, "_active_acqf", None) is not self:
+            self._reprepare()
+        return self
+
+    def _reprepare(self):
+        raise NotImplementedError
+
     def _check_active(self):
         if getattr(self.model, "_active_acqf", None) is not self:
             raise L.EverestError("another acquisition function has been prepared on this DeviceGPState since this one "
@@ -239,6 +250,9 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
     def _after_prepare(self):
         pass
 
+    def _reprepare(self):
+        self._prepare(self.X_pending, self._zb)
+
     def set_X_pending(self, X_pending=None):
         """[UPSTREAM] qNEHVI.set_X_pending with cache_pending=True: the pending points join the baseline and the
         per-sample box decompositions are rebuilt (no new pruning)."""
@@ -287,15 +301,23 @@ class qExpectedHypervolumeImprovement(_DeviceAcquisition):
         self.set_X_pending(X_pending)
         self.ref_point = [float(v) for v in ref_point]
         self.objective = objective
-        Y = torch.as_tensor(partitioning_Y, dtype=torch.double).reshape(-1, len(self.ref_point)).to(model.device).contiguous()
+        self._Y = torch.as_tensor(partitioning_Y, dtype=torch.double).reshape(-1, len(self.ref_point)).to(model.device).contiguous()
         self._obj_c, self._n_obj = c_array(list(objective.ops), L.ObjectiveOp)
         self._ref_c = (C.c_double * len(self.ref_point))(*self.ref_point)
+        self._reprepare()
+
+    def _reprepare(self):
+        model, Y = self.model, self._Y
         maxc = C.c_int32(0)
         with torch.cuda.device(model.device):
             L.check(model.lib.bo_ehvi_prepare(model.handle, _dev_ptr(Y), Y.shape[0], self.S, self._obj_c, self._n_obj,
                                               self._ref_c, C.byref(maxc), _stream()))
         self.max_cells = int(maxc.value)
         self._claim()
+        self._after_prepare()
+
+    def _after_prepare(self):
+        pass
 
 
 class qLogNoisyExpectedHypervolumeImprovement(qNoisyExpectedHypervolumeImprovement):
@@ -314,10 +336,13 @@ class qLogNoisyExpectedHypervolumeImprovement(qNoisyExpectedHypervolumeImproveme
 
 class qLogExpectedHypervolumeImprovement(qExpectedHypervolumeImprovement):
     def __init__(self, *args, tau_relu: float = 1e-6, tau_max: float = 1e-2, **kwargs):
+        self._taus = (float(tau_relu), float(tau_max))
         super().__init__(*args, **kwargs)
+
+    def _after_prepare(self):
         self.set_option("log_hvi", 1)
-        self.set_option("tau_relu", tau_relu)
-        self.set_option("tau_max", tau_max)
+        self.set_option("tau_relu", self._taus[0])
+        self.set_option("tau_max", self._taus[1])
 
 
 class _ScalarAcquisition(_DeviceAcquisition):
@@ -365,9 +390,14 @@ class _ScalarAcquisition(_DeviceAcquisition):
                 raise ValueError("best_f is required")
             self.best_f = float(best_f)
         self.set_X_pending(X_pending)    # scored jointly with X ([UPSTREAM] @concatenate_pending_points)
+        self._Xbd = Xbd
+        self._reprepare()
+
+    def _reprepare(self):
+        model, Xbd, zb = self.model, self._Xbd, (self._zb if self._NOISY else None)
         info = (C.c_int32 * model.M)()
         with torch.cuda.device(model.device):
-            L.check(model.lib.bo_scalar_prepare(model.handle, self._VARIANT, self.param, self.S, objective.combine_code,
+            L.check(model.lib.bo_scalar_prepare(model.handle, self._VARIANT, self.param, self.S, self.objective.combine_code,
                                                 self._obj_c, self._n_obj, self._con_c, self._n_con,
                                                 0.0 if self._NOISY else self.best_f,
                                                 _dev_ptr(Xbd) if Xbd is not None else None, self.nb,

@@ -391,6 +391,40 @@ def optimize_acqf_mixed(acq_function, bounds: torch.Tensor, q: int, num_restarts
     return cands, best_v
 
 
+def optimize_acqf_list(acq_function_list, bounds: torch.Tensor, num_restarts: int, raw_samples: int,
+                       fixed_features: Optional[Dict[int, float]] = None, fixed_features_list=None,
+                       options: Optional[dict] = None, seed: Optional[int] = None, refine: bool = True, **unsupported):
+    """[UPSTREAM] botorch.optim.optimize_acqf_list as BotorchStrategy._optimize_acqf_continuous calls it when a strategy
+    hands it more than one acquisition function (botorch.py:337-356, e.g. one scalarisation per candidate): the candidates
+    are generated one at a time, acquisition function i sees the candidates of 0..i-1 as pending points, each step is an
+    optimize_acqf(q=1) -- or optimize_acqf_mixed(q=1) when `fixed_features_list` is given.  Returns
+    (candidates [len(list), d], acquisition values [len(list)]).  All functions may share one DeviceGPState: each is
+    re-activated on the handle before its turn."""
+    if not acq_function_list:
+        raise ValueError("acq_function_list must be non-empty.")
+    if fixed_features and fixed_features_list:
+        raise ValueError("Either fixed_features or fixed_features_list can be provided, not both.")
+    chosen, values = [], []
+    for acqf in acq_function_list:
+        acqf.activate()
+        base_pending = _pending_base(acqf)
+        if chosen:
+            acqf.set_X_pending(torch.cat(([base_pending] if base_pending is not None else []) + chosen, dim=0))
+        try:
+            if fixed_features_list:
+                c, v = optimize_acqf_mixed(acqf, bounds, 1, num_restarts, raw_samples, fixed_features_list=fixed_features_list,
+                                           options=options, seed=seed, refine=refine, **unsupported)
+            else:
+                c, v = optimize_acqf(acqf, bounds, 1, num_restarts, raw_samples, fixed_features=fixed_features,
+                                     options=options, seed=seed, refine=refine, **unsupported)
+        finally:
+            if chosen:
+                acqf.set_X_pending(base_pending)
+        chosen.append(c.reshape(1, -1))
+        values.append(torch.as_tensor(v, dtype=torch.double).reshape(()))
+    return torch.cat(chosen, dim=0), torch.stack(values)
+
+
 def calc_acquisition(acq_function, candidates, combined: bool = False):
     """BotorchStrategy.calc_acquisition (botorch.py:196-225) on already transformed candidates [n, d]:
     one value per row, or a single value for the whole set as one q-batch when `combined`."""

@@ -157,8 +157,6 @@ class DeviceBotorchStrategy:
         if self.X is None:
             raise ValueError("No experiments have been provided yet.")
         acqfs = self._get_acqfs(candidate_count)
-        if len(acqfs) > 1:
-            raise NotImplementedError("optimize_acqf_list (one acquisition function per candidate) is not accelerated")
         sp = self.space
         bounds = torch.as_tensor(sp.bounds)
         if sp.is_fully_combinatorial():
@@ -181,7 +179,15 @@ class DeviceBotorchStrategy:
             kw = dict(options=self._get_optimizer_options(), seed=int(torch.randint(0, 1000000, (1,)).item()),
                       inequality_constraints=sp.inequality_constraints or None,
                       equality_constraints=sp.equality_constraints or None)
-            if len(combos) > 1:
+            if len(acqfs) > 1:
+                # botorch.py:337-356: one acquisition function per candidate -> sequential optimize_acqf_list
+                if len(acqfs) != candidate_count:
+                    raise ValueError("one acquisition function per candidate is expected")
+                ff = (combos[0] if len(combos) == 1 else None) or (dict(sp.fixed_features) or None)
+                cand, _ = optim.optimize_acqf_list(acqfs, bounds, self.num_restarts, self.num_raw_samples,
+                                                   fixed_features=None if len(combos) > 1 else ff,
+                                                   fixed_features_list=combos if len(combos) > 1 else None, **kw)
+            elif len(combos) > 1:
                 cand, _ = optim.optimize_acqf_mixed(acqfs[0], bounds, candidate_count, self.num_restarts,
                                                     self.num_raw_samples, fixed_features_list=combos, **kw)
             else:

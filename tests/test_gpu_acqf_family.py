@@ -157,3 +157,38 @@ def test_factory_errors_are_loud():
                                       constraints=[OutputConstraint(0, 1.0, 0.5, 0.1)])
     with pytest.raises(ValueError):
         A.qProbabilityOfImprovement(st, 0.0, obj, tau=0.0)                       # tau must be > 0
+
+
+def test_activate_and_optimize_acqf_list_on_one_state():
+    """Several acquisition functions built on ONE DeviceGPState (the handle holds one prepared function at a time):
+    activate() re-prepares with the stored arguments and reproduces the values bit for bit; optimize_acqf_list
+    (botorch.py:337-356) generates one candidate per function with the earlier candidates pending."""
+    from everest_b200 import _lib as L
+    from everest_b200 import optim
+
+    p = Cf.zdt1_qnehvi(N=40, S=32, raw=16, d=3, q=1)
+    st = Cf.build_state(p)
+    obj = ScalarObjective([MinimizeObjective(1)], "single")
+    a1 = A.get_acquisition_function("qLogNEI", st, obj, p["X"], mc_samples=32, seed=5)
+    X = Cf.candidates(p)[:8].to(st.device)
+    v1 = a1(X).clone()
+    a2 = A.get_acquisition_function("qUCB", st, obj, p["X"], mc_samples=32, seed=6, beta=0.3)
+    v2 = a2(X).clone()
+    with pytest.raises(L.EverestError):
+        a1(X)                                   # a2 owns the handle now
+    assert torch.equal(a1.activate()(X), v1)
+    assert torch.equal(a2.activate()(X), v2)
+    bounds = torch.tensor([[0.0] * 3, [1.0] * 3])
+    cands, vals = optim.optimize_acqf_list([a1, a2], bounds, num_restarts=3, raw_samples=32, options={"maxiter": 30}, seed=2)
+    assert cands.shape == (2, 3) and vals.shape == (2,) and bool(torch.isfinite(vals).all())
+    # the second value is a2 at its candidate with the first candidate pending
+    a2.activate()
+    a2.set_X_pending(cands[:1])
+    assert abs(float(a2(cands[1:2].unsqueeze(0).to(st.device))[0]) - float(vals[1])) <= 1e-9 * max(1.0, abs(float(vals[1])))
+    a2.set_X_pending(None)
+    # NEHVI-family functions re-activate too (pending points live in the baseline)
+    n1 = Cf.build_acqf(p, st, prune_samples=64)
+    Xq = Cf.candidates(p)[:4].to(st.device)
+    w1 = n1(Xq).clone()
+    a1.activate()
+    assert torch.equal(n1.activate()(Xq), w1)

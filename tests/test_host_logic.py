@@ -174,6 +174,61 @@ def test_gen_candidates_scipy_on_a_known_concave_function():
     assert float((cand[:, 2] - cand[:, 3]).abs().max()) <= 1e-8 and abs(float(val) + 2 * 0.08) < 1e-6
 
 
+def test_optimize_acqf_list_sequencing_with_fake_acqfs():
+    """optimize_acqf_list (botorch.py:337-356): one candidate per acquisition function, function i sees the candidates of
+    0..i-1 as pending points, its own pending points are restored afterwards, every function is activated before use."""
+    class _M:
+        device = torch.device("cpu")
+        d = 3
+
+    log = []
+
+    class _Fake:
+        model = _M()
+
+        def __init__(self, name, target, pending=None):
+            self.name, self.target, self.X_pending = name, target, pending
+
+        def activate(self):
+            log.append(("activate", self.name))
+            return self
+
+        def set_X_pending(self, Xp=None):
+            self.X_pending = None if Xp is None else torch.as_tensor(Xp, dtype=DT).reshape(-1, 3)
+            log.append(("pending", self.name, 0 if self.X_pending is None else self.X_pending.shape[0]))
+
+        def _pen(self, X):
+            # repelled from the pending points: the second function must not return the first one's optimum
+            if self.X_pending is None:
+                return torch.zeros(X.shape[0], dtype=DT), torch.zeros_like(X)
+            diff = X[:, :, None, :] - self.X_pending[None, None]
+            w = torch.exp(-50.0 * (diff ** 2).sum(-1))
+            return w.sum(dim=(1, 2)), (-100.0 * diff * w[..., None]).sum(2)
+
+        def __call__(self, X):
+            return -((X - self.target) ** 2).sum(dim=(1, 2)) - self._pen(X)[0]
+
+        def forward_backward(self, X):
+            return self(X), -2.0 * (X - self.target) - self._pen(X)[1]
+
+    a = _Fake("a", 0.25)
+    b = _Fake("b", 0.25, pending=torch.full((1, 3), 0.9, dtype=DT))
+    bounds = torch.tensor([[0.0] * 3, [1.0] * 3])
+    cands, vals = optim.optimize_acqf_list([a, b], bounds, num_restarts=4, raw_samples=64, options={"maxiter": 100}, seed=3)
+    assert cands.shape == (2, 3) and vals.shape == (2,)
+    assert torch.allclose(cands[0], torch.full((3,), 0.25, dtype=DT), atol=1e-5) and abs(float(vals[0])) < 1e-9
+    assert float((cands[1] - cands[0]).norm()) > 0.05           # b was repelled from a's candidate
+    assert b.X_pending.shape == (1, 3) and a.X_pending is None   # own pending points restored
+    assert [e for e in log if e[0] == "activate"] == [("activate", "a"), ("activate", "b")]
+    assert ("pending", "b", 2) in log                            # b scored with its own pending point + a's candidate
+    with pytest.raises(ValueError):
+        optim.optimize_acqf_list([], bounds, 2, 8)
+    # with a fixed_features_list every step is an optimize_acqf_mixed(q=1)
+    c2, v2 = optim.optimize_acqf_list([a], bounds, 3, 32, fixed_features_list=[{0: 0.0}, {0: 0.25}], options={"maxiter": 50},
+                                      seed=1)
+    assert abs(float(c2[0, 0]) - 0.25) < 1e-12 and abs(float(v2[0])) < 1e-8
+
+
 def test_polytope_sampler_and_dense_constraints():
     """sample_q_batches_from_polytope ([UPSTREAM] hit-and-run, reached from botorch.py:384-405 whenever the domain holds
     Linear(In)EqualityConstraints): feasibility, fixed features, inter-point equalities, roughly uniform marginals."""
