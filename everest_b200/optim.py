@@ -108,6 +108,81 @@ def _has_interpoint(constraints) -> bool:
     return any(torch.as_tensor(c[0]).dim() == 2 for c in (constraints or []))
 
 
+NLC_TOL = -1e-6   # [UPSTREAM] botorch.optim.parameter_constraints.NLC_TOL: slack of the feasibility test of a start point
+
+
+def nchoosek_constraints(indices, max_count: Optional[int] = None, min_count: int = 0, ell: float = 1e-3):
+    """NChooseK as nonlinear inequality callables (utils/torch_tools.py:147-207): the number of zeros among the listed
+    columns is counted by a sum of narrow Gaussians exp(-(x / ell)^2 / 2); at most `max_count` non-zero features means
+    zeros >= n - max_count, at least `min_count` means zeros <= n - min_count.  Returns [(callable, True)] (intra-point)."""
+    idx = torch.as_tensor(indices, dtype=torch.long)
+    n = int(idx.numel())
+
+    def zeros(x):
+        return torch.exp(-0.5 * (x[..., idx] / ell) ** 2).sum(dim=-1)
+
+    out = []
+    if max_count is not None and max_count != n:
+        out.append((lambda x, k=n - int(max_count): zeros(x) - k, True))
+    if min_count > 0:
+        out.append((lambda x, k=n - int(min_count): k - zeros(x), True))
+    return out
+
+
+def product_constraint(indices, exponents, rhs: float, sign: int = 1):
+    """ProductInequalityConstraint as a nonlinear inequality callable (utils/torch_tools.py:210-236):
+    feasible iff  -sign * prod_i x_i^e_i + rhs >= 0."""
+    idx = torch.as_tensor(indices, dtype=torch.long)
+    ex = torch.as_tensor(exponents, dtype=torch.double)
+    return (lambda x: -1.0 * sign * (x[..., idx] ** ex).prod(dim=-1) + rhs, True)
+
+
+def nchoosek_generator(bounds, specs, fixed_features: Optional[Dict[int, float]] = None):
+    """Feasible raw samples for NChooseK-constrained spaces in the (n, q, seed) -> [n, q, d] form that
+    get_initial_conditions_generator hands to gen_batch_initial_conditions (utils/torch_tools.py:809-864; the reference
+    asks its RandomStrategy, strategies/random.py:180-353): per point and constraint a uniformly drawn number of active
+    features in [min_count, max_count], the others exactly 0.  specs: [(indices, max_count, min_count)]."""
+    bounds = torch.as_tensor(bounds, dtype=torch.double)
+
+    def generator(n: int, q: int, seed: int) -> torch.Tensor:
+        g = torch.Generator().manual_seed(int(seed))
+        lo, hi = bounds[0], bounds[1]
+        X = lo + (hi - lo) * torch.rand(n, q, bounds.shape[1], dtype=torch.double, generator=g)
+        for indices, max_count, min_count in specs:
+            idx = torch.as_tensor(indices, dtype=torch.long)
+            m = int(idx.numel())
+            kmax = m if max_count is None else int(max_count)
+            k = torch.randint(int(min_count), kmax + 1, (n, q), generator=g)
+            order = torch.rand(n, q, m, generator=g).argsort(dim=-1)          # random ranking of the features
+            active = order < k.unsqueeze(-1)
+            X[..., idx] = torch.where(active, X[..., idx], torch.zeros((), dtype=torch.double))
+        return apply_fixed_features(X, fixed_features)
+
+    return generator
+
+
+def _split_nlc(nonlinear_inequality_constraints):
+    out = []
+    for c in nonlinear_inequality_constraints or []:
+        if isinstance(c, (tuple, list)):
+            out.append((c[0], bool(c[1])))
+        else:
+            out.append((c, True))     # older BoTorch convention: a bare callable is intra-point
+    return out
+
+
+def nonlinear_constraints_satisfied(X: torch.Tensor, nonlinear_inequality_constraints, tol: float = NLC_TOL) -> torch.Tensor:
+    """[r] bool: every intra-point constraint holds at each of the q points and every inter-point one on the q-batch."""
+    X = torch.as_tensor(X, dtype=torch.double)
+    ok = torch.ones(X.shape[0], dtype=torch.bool)
+    for fn, intra in _split_nlc(nonlinear_inequality_constraints):
+        if intra:
+            ok &= (fn(X) >= tol).reshape(X.shape[0], -1).all(dim=1)
+        else:
+            ok &= torch.stack([torch.as_tensor(fn(X[i]) >= tol).reshape(-1).all() for i in range(X.shape[0])])
+    return ok
+
+
 def sample_polytope(A: np.ndarray, b: np.ndarray, C: np.ndarray, c: np.ndarray, lb: np.ndarray, ub: np.ndarray, n: int,
                     seed: Optional[int] = None, n_burnin: int = 10000, n_thinning: int = 32, n_chains: int = 64) -> np.ndarray:
     """Uniform samples from {x : A x <= b, C x = c, lb <= x <= ub} by hit-and-run ([UPSTREAM]
@@ -200,13 +275,21 @@ def sample_q_batches_from_polytope(n: int, q: int, bounds: torch.Tensor, inequal
 
 def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                                  fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
-                                 seed: Optional[int] = None, inequality_constraints=None, equality_constraints=None):
+                                 seed: Optional[int] = None, inequality_constraints=None, equality_constraints=None,
+                                 generator=None):
     """[UPSTREAM] gen_batch_initial_conditions: Sobol raw samples (hit-and-run polytope samples when linear
-    constraints are given), one screened forward over ALL of them on the device, then initialize_q_batch."""
+    constraints are given; `generator(n, q, seed) -> [n, q, d]` when the caller supplies one, as BoFire does for
+    nonlinear constraints, botorch.py:257-265), one screened forward over ALL of them on the device, then
+    initialize_q_batch."""
     options = options or {}
     if seed is None:
         seed = int(torch.randint(0, 1000000, (1,)).item())
-    if inequality_constraints or equality_constraints:
+    if generator is not None:
+        X_rnd = torch.as_tensor(generator(raw_samples, q, seed), dtype=torch.double)
+        if tuple(X_rnd.shape) != (raw_samples, q, bounds.shape[-1]):
+            raise ValueError(f"generator must return [{raw_samples}, {q}, {bounds.shape[-1]}] samples")
+        X_rnd = apply_fixed_features(X_rnd, fixed_features)
+    elif inequality_constraints or equality_constraints:
         X_rnd = sample_q_batches_from_polytope(raw_samples, q, bounds, inequality_constraints, equality_constraints,
                                                seed=seed, n_burnin=options.get("n_burnin", 10000),
                                                n_thinning=options.get("thinning", 32), fixed_features=fixed_features)
@@ -224,9 +307,12 @@ def gen_batch_initial_conditions(acq_function, bounds: torch.Tensor, q: int, num
 
 def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function, lower_bounds, upper_bounds,
                          fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
-                         inequality_constraints=None, equality_constraints=None):
+                         inequality_constraints=None, equality_constraints=None, nonlinear_inequality_constraints=None):
     """[UPSTREAM] botorch.generation.gen_candidates_scipy: joint L-BFGS-B over all restarts for box bounds, SLSQP
-    with the linear constraints replicated per restart when (in)equality constraints are given.
+    with the linear constraints replicated per restart when (in)equality constraints are given.  Nonlinear inequality
+    constraints ([(callable, is_intrapoint)], feasible iff callable(x) >= 0; NChooseK / Product, utils/torch_tools.py:
+    147-252) also go to SLSQP, one restart at a time (BoFire forces batch_limit = 1 for them, botorch.py:117-121), with
+    their Jacobians from torch autograd on the host; every start point must satisfy them.
     Returns (candidates [r, q, d] CPU, acq values [r] CPU).  options: maxiter (default 2000, BoFire's
     `maxiter`), gradient ("analytic" | "fd"), fd_step (relative to the bound width, default 1e-6)."""
     options = options or {}
@@ -235,6 +321,15 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     rel_h = float(options.get("fd_step", 1e-6))
     X0 = torch.as_tensor(initial_conditions, dtype=torch.double).cpu().clone()
     r, q, d = X0.shape
+    nlcs = _split_nlc(nonlinear_inequality_constraints)
+    if nlcs and r > 1:
+        parts = [gen_candidates_scipy(X0[i:i + 1], acquisition_function, lower_bounds, upper_bounds, fixed_features=fixed_features,
+                                      options=options, inequality_constraints=inequality_constraints,
+                                      equality_constraints=equality_constraints,
+                                      nonlinear_inequality_constraints=nonlinear_inequality_constraints) for i in range(r)]
+        return (torch.cat([p_[0] for p_ in parts]), torch.cat([p_[1] for p_ in parts]),
+                {"nit": max(p_[2]["nit"] for p_ in parts), "n_acqf_evals": sum(p_[2]["n_acqf_evals"] for p_ in parts),
+                 "message": "; ".join(sorted({p_[2]["message"] for p_ in parts}))})
     lb = torch.as_tensor(lower_bounds, dtype=torch.double).cpu().expand(d).clone()
     ub = torch.as_tensor(upper_bounds, dtype=torch.double).cpu().expand(d).clone()
     free = [j for j in range(d) if not (fixed_features and j in fixed_features) and float(ub[j]) > float(lb[j])]
@@ -291,8 +386,28 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     x0 = X0[:, :, free_t].reshape(-1).numpy().astype(np.float64)
     bnds = [(float(lb[j]), float(ub[j])) for _ in range(r * q) for j in free]
     fun = f_and_grad_fd if use_fd else f_and_grad_analytic
-    if inequality_constraints or equality_constraints:
+    if inequality_constraints or equality_constraints or nlcs:
         cons = []
+        if nlcs:
+            if not bool(nonlinear_constraints_satisfied(X0, nlcs).all()):
+                raise ValueError("`batch_initial_conditions` must satisfy the non-linear inequality constraints.")
+
+            def nlc_pair(fn, point):
+                # value and Jacobian (w.r.t. the free variables) of one constraint at one point (or on the whole q-batch)
+                def evaluate(x):
+                    xt = torch.from_numpy(np.ascontiguousarray(x)).requires_grad_(True)
+                    X = X0.clone()
+                    X[:, :, free_t] = xt.view(r, q, nf)
+                    v = fn(X[0, point]) if point is not None else fn(X[0])
+                    v = torch.as_tensor(v, dtype=torch.double).reshape(())
+                    (gx,) = torch.autograd.grad(v, xt, allow_unused=True)
+                    return float(v.detach()), (np.zeros(x.shape[0]) if gx is None else gx.numpy())
+                return evaluate
+
+            for fn, intra in nlcs:
+                for point in (range(q) if intra else [None]):
+                    ev = nlc_pair(fn, point)
+                    cons.append({"type": "ineq", "fun": (lambda x, ev=ev: ev(x)[0]), "jac": (lambda x, ev=ev: ev(x)[1])})
         free_cols = np.asarray([j * d + a for j in range(q) for a in free])
         x_fixed = X0[0].reshape(-1).numpy()     # fixed columns hold the same value in every restart
         fixed_cols = np.setdiff1d(np.arange(q * d), free_cols)
@@ -319,18 +434,27 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
                   return_best_only: bool = True, seed: Optional[int] = None, refine: bool = True, **unsupported):
     """Same signature / return convention as botorch.optim.optimize_acqf as BoFire calls it
     (botorch.py:384-405): (candidates [q, d] on CPU, acq_value scalar tensor)."""
-    if unsupported.get("nonlinear_inequality_constraints"):
-        raise NotImplementedError("nonlinear_inequality_constraints (NChooseK / Product) are not handled by the "
-                                  "accelerated optimiser")
+    nlcs = unsupported.get("nonlinear_inequality_constraints") or None
+    generator = unsupported.get("generator")          # ic_gen_kwargs of botorch.py:258-265
+    if nlcs and generator is None:
+        # [UPSTREAM] optimize_acqf: "`batch_initial_conditions` or `ic_generator` must be given if there are non-linear
+        # inequality constraints" -- Sobol samples are not feasible for NChooseK
+        raise RuntimeError("`ic_generator` (ic_gen_kwargs['generator']) must be given if there are non-linear inequality "
+                           "constraints.")
     ineq = unsupported.get("inequality_constraints") or None
     eq = unsupported.get("equality_constraints") or None
     bounds = torch.as_tensor(bounds, dtype=torch.double)
     X_ic, Y_ic, _, _ = gen_batch_initial_conditions(acq_function, bounds, q, num_restarts, raw_samples,
                                                     fixed_features=fixed_features, options=options, seed=seed,
-                                                    inequality_constraints=ineq, equality_constraints=eq)
+                                                    inequality_constraints=ineq, equality_constraints=eq, generator=generator)
     if refine:
         X_ref, Y_ref, _ = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
-                                               options=options, inequality_constraints=ineq, equality_constraints=eq)
+                                               options=options, inequality_constraints=ineq, equality_constraints=eq,
+                                               nonlinear_inequality_constraints=nlcs)
+        if nlcs:
+            # SLSQP may stop slightly outside: keep a refined restart only if it still satisfies the constraints
+            ok_n = nonlinear_constraints_satisfied(X_ref, nlcs)
+            Y_ref = torch.where(ok_n, Y_ref, torch.full_like(Y_ref, -float("inf")))
         if ineq or eq:
             # SLSQP may stop slightly outside the polytope: keep a refined restart only if it is feasible
             Ai, bi = dense_linear_constraints(ineq, q, bounds.shape[-1])

@@ -36,6 +36,10 @@ class InputSpace:
     equality_constraints: list = field(default_factory=list)
     allowed_categories: Dict[int, Sequence[int]] = field(default_factory=dict)
     discrete_values: Dict[int, Sequence[float]] = field(default_factory=dict)  # DiscreteInput columns
+    # get_nonlinear_constraints (utils/torch_tools.py:239-252): [(callable, is_intrapoint)], feasible iff callable(x) >= 0;
+    # with them BoFire passes a generator of feasible raw samples (n, q, seed) -> [n, q, d] (botorch.py:257-265)
+    nonlinear_constraints: list = field(default_factory=list)
+    initial_conditions_generator: Optional[Callable] = None
 
     def __post_init__(self):
         self.bounds = np.asarray(self.bounds, dtype=np.float64)
@@ -179,6 +183,9 @@ class DeviceBotorchStrategy:
             kw = dict(options=self._get_optimizer_options(), seed=int(torch.randint(0, 1000000, (1,)).item()),
                       inequality_constraints=sp.inequality_constraints or None,
                       equality_constraints=sp.equality_constraints or None)
+            if sp.nonlinear_constraints:
+                kw.update(nonlinear_inequality_constraints=list(sp.nonlinear_constraints),
+                          generator=sp.initial_conditions_generator)
             if len(acqfs) > 1:
                 # botorch.py:337-356: one acquisition function per candidate -> sequential optimize_acqf_list
                 if len(acqfs) != candidate_count:

@@ -229,6 +229,71 @@ def test_optimize_acqf_list_sequencing_with_fake_acqfs():
     assert abs(float(c2[0, 0]) - 0.25) < 1e-12 and abs(float(v2[0])) < 1e-8
 
 
+def test_nonlinear_constraints_nchoosek_and_product():
+    """Nonlinear inequality constraints as BoFire builds them (utils/torch_tools.py:147-252) through optimize_acqf:
+    feasible raw samples from the caller's generator (botorch.py:257-265), SLSQP one restart at a time."""
+    class _M:
+        device = torch.device("cpu")
+        d = 4
+
+    class _Fake:
+        model = _M()
+        X_pending = None
+
+        def __init__(self, t):
+            self.t = t
+
+        def __call__(self, X):
+            return -((X - self.t) ** 2).sum(dim=(1, 2))
+
+        def forward_backward(self, X):
+            return self(X), -2.0 * (X - self.t)
+
+    bounds = torch.tensor([[0.0] * 4, [1.0] * 4])
+    # Product: x0 * x1 <= 0.25 -> the point of the hyperbola closest to (0.8, 0.8) is (0.5, 0.5)
+    prod = [optim.product_constraint([0, 1], [1.0, 1.0], rhs=0.25, sign=1)]
+
+    def gen(n, q, seed):
+        g = torch.Generator().manual_seed(seed)
+        X = torch.rand(n, q, 4, dtype=DT, generator=g)
+        X[..., 0] *= 0.5
+        X[..., 1] *= 0.5
+        return X
+
+    cand, val = optim.optimize_acqf(_Fake(0.8), bounds, q=1, num_restarts=3, raw_samples=32, options={"maxiter": 200}, seed=4,
+                                    nonlinear_inequality_constraints=prod, generator=gen)
+    assert bool(optim.nonlinear_constraints_satisfied(cand.unsqueeze(0), prod).all())
+    assert torch.allclose(cand[0], torch.tensor([0.5, 0.5, 0.8, 0.8], dtype=DT), atol=1e-4)
+    assert abs(float(val) + 2 * 0.09) < 1e-6
+    # no generator -> the same error BoTorch raises; infeasible start points are rejected
+    with pytest.raises(RuntimeError):
+        optim.optimize_acqf(_Fake(0.8), bounds, 1, 2, 8, nonlinear_inequality_constraints=prod)
+    with pytest.raises(ValueError):
+        optim.gen_candidates_scipy(torch.full((1, 1, 4), 0.9, dtype=DT), _Fake(0.8), bounds[0], bounds[1],
+                                   nonlinear_inequality_constraints=prod)
+    # NChooseK: at most one of x0..x2 non-zero; the generator zeroes the others exactly
+    nck = optim.nchoosek_constraints([0, 1, 2], max_count=1, min_count=0)
+    assert len(nck) == 1 and nck[0][1] is True
+    gen2 = optim.nchoosek_generator(bounds, [([0, 1, 2], 1, 0)])
+    Xg = gen2(64, 2, 0)
+    assert Xg.shape == (64, 2, 4) and int(((Xg[..., :3] != 0).sum(-1)).max()) <= 1
+    assert bool(optim.nonlinear_constraints_satisfied(Xg, nck).all())
+    assert not bool(optim.nonlinear_constraints_satisfied(torch.full((1, 1, 4), 0.5, dtype=DT), nck).any())
+    cand2, val2 = optim.optimize_acqf(_Fake(0.5), bounds, q=2, num_restarts=3, raw_samples=48, options={"maxiter": 100}, seed=1,
+                                      nonlinear_inequality_constraints=nck, generator=gen2)
+    assert cand2.shape == (2, 4) and bool(optim.nonlinear_constraints_satisfied(cand2.unsqueeze(0), nck).all())
+    assert int(((cand2[:, :3].abs() > 5e-3).sum(-1)).max()) <= 1
+    # (SLSQP on the narrow-Gaussian relaxation rarely improves on a start with exact zeros -- the constraint gradient
+    # vanishes there; an infeasible refinement is discarded, so the result is at least the best screened raw sample)
+    assert abs(float(val2) - float(_Fake(0.5)(cand2.unsqueeze(0))[0])) < 1e-12
+    # min_count and both bounds
+    both = optim.nchoosek_constraints([0, 1, 2], max_count=2, min_count=1)
+    assert len(both) == 2
+    Xb = optim.nchoosek_generator(bounds, [([0, 1, 2], 2, 1)])(32, 1, 3)
+    nz = (Xb[..., :3] != 0).sum(-1)
+    assert int(nz.min()) >= 1 and int(nz.max()) <= 2 and bool(optim.nonlinear_constraints_satisfied(Xb, both).all())
+
+
 def test_polytope_sampler_and_dense_constraints():
     """sample_q_batches_from_polytope ([UPSTREAM] hit-and-run, reached from botorch.py:384-405 whenever the domain holds
     Linear(In)EqualityConstraints): feasibility, fixed features, inter-point equalities, roughly uniform marginals."""
