@@ -348,8 +348,10 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         if (gr == gc) s0 = 0.0;
         if (gr == gc + 1) s1 = 0.0;
       }
-      const double v0 = (gc < n_cols) ? coef * leaf_value_from_stat(KIND, s0) : 0.0;
-      const double v1 = (gc + 1 < n_cols) ? coef * leaf_value_from_stat(KIND, s1) : 0.0;
+      double l0, l1;
+      leaf_value_from_stat2(KIND, s0, s1, l0, l1);
+      const double v0 = (gc < n_cols) ? coef * l0 : 0.0;
+      const double v1 = (gc + 1 < n_cols) ? coef * l1 : 0.0;
       if (!oz.planes || oz.write_fp64) {
         if (gc + 1 < ld) *reinterpret_cast<double2*>(out + (size_t)gr * ld + gc) = make_double2(v0, v1);
         else out[(size_t)gr * ld + gc] = v0;

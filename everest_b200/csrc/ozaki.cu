@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 #define O2_HI_PLANES 3
 #define O2_HI_OP_BYTES (O2_HI_PLANES * O2_PLANE)   // 12288
 #define O2_MAXOUT 4
-#define O2_SCRATCH_SLOTS 160
+#define O2_SCRATCH_SLOTS 256   // >= %nsmid on every part seen so far (148 SMs on B200); the kernel traps beyond
 
 struct alignas(128) O2Item {
   CUtensorMap mapA, mapB;      // box {128 rows, 2 chunks, 7 planes}
@@ -450,11 +450,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __gri
       idesc |= 2u << 4;                       // D = S32
       idesc |= 1u << 7;                       // A signed 8 bit
       idesc |= 1u << 10;                      // B signed 8 bit
-      idesc |= (uint32_t)(O2_BN >> 3) << 17;
       idesc |= (uint32_t)(OZ_BM >> 4) << 24;
+      const uint32_t idesc_base = idesc;
       int it = 0, ev = 0;
       for (int ti = 0, jt; (jt = tile_at(ti)) >= 0; ++ti) {
         const int nkb = k_blocks_of(jt);
+        // the last column tile usually holds only a few real columns (N + 1 + n_b is padded to 128): issue narrower MMAs
+        // there (N is any multiple of 16); the accumulator columns beyond keep stale integers the epilogue never uses
+        const int n_eff = min(O2_BN, ((batch.N + batch.n_ext - jt * O2_BN + 15) >> 4) << 4);
+        idesc = idesc_base | ((uint32_t)(max(n_eff, 16) >> 3) << 17);
         for (int pass = 0; pass < 2; ++pass, ++ev) {
           // pass 1 needs the previous tile's high levels drained, pass 2 this tile's low levels
           oz_mbar_wait(acc_empty, (uint32_t)((ev & 1) ^ 1));
@@ -961,7 +965,7 @@ static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
     attr_set = true;
   }
-  // 20 MB per device, L2-resident working set of the CTAs in flight; lives as long as the library
+  // 32 MB per device (only the slabs of the resident CTAs, 148 x 128 KB, are ever touched: L2-resident); lives as long as the library
   static long long* scratch_dev[64] = {};
   int dev_id = 0;
   cudaGetDevice(&dev_id);
