@@ -103,11 +103,49 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
 #pragma unroll
   for (int e = 0; e < 16; ++e) total[e] = 0.0;
 
-  for (int term = 0; term < md.n_terms; ++term) {
+  // Evaluation order.  Kernel trees of the form  sum of single leaves (+ ONE product of leaves)  -- SingleTaskGP, Additive,
+  // MixedSingleTaskGP / MixedTanimotoGP (mixed_tanimoto_gp.py:165-215: (s1 Kc + s2 Km + s3 Kh) + (s4 Kc s5 Km s6 Kh)) -- are
+  // evaluated LEAF-major: every leaf (2048-bit Tanimoto: 64 POPCs per pair) is computed once and feeds both its own term
+  // and the product.  Anything else keeps the term-major order (a leaf is re-evaluated in every term that contains it).
+  bool leaf_major = true;
+  int multi = -1, n_fac_total = 0;
+  for (int t2 = 0; t2 < md.n_terms; ++t2) {
+    n_fac_total += md.nfac[t2];
+    if (md.nfac[t2] != 1) {
+      if (multi >= 0 || md.nfac[t2] < 1) leaf_major = false;
+      multi = t2;
+    }
+  }
+  if (leaf_major && multi >= 0)
+    for (int f1 = 0; f1 < md.nfac[multi]; ++f1)
+      for (int f2 = f1 + 1; f2 < md.nfac[multi]; ++f2)
+        if (md.fac[multi][f1] == md.fac[multi][f2]) leaf_major = false;
+  const int n_items = leaf_major ? md.n_leaves : n_fac_total;
+  int term = 0, f = 0;
+  while (!leaf_major && term < md.n_terms && md.nfac[term] < 1) {   // (a constant term: no factors)
 #pragma unroll
-    for (int e = 0; e < 16; ++e) prod[e] = md.coef[term];
-    for (int f = 0; f < md.nfac[term]; ++f) {
-      const int l = md.fac[term][f];
+    for (int e = 0; e < 16; ++e) total[e] += md.coef[term];
+    ++term;
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e)
+    prod[e] = leaf_major ? ((multi >= 0) ? md.coef[multi] : 0.0) : ((term < md.n_terms) ? md.coef[term] : 0.0);
+
+  for (int it = 0; it < n_items; ++it) {
+    int l;
+    double c_single = 0.0;
+    bool single = false, in_prod = false;
+    if (leaf_major) {
+      l = it;
+      for (int t2 = 0; t2 < md.n_terms; ++t2)
+        if (md.nfac[t2] == 1 && md.fac[t2][0] == l) { c_single += md.coef[t2]; single = true; }
+      if (multi >= 0)
+        for (int f2 = 0; f2 < md.nfac[multi]; ++f2) in_prod = in_prod || (md.fac[multi][f2] == l);
+      if (!single && !in_prod) continue;
+    } else {
+      l = md.fac[term][f];
+    }
+    {
       const LeafD& L = md.leaf[l];
       double lv[16];
       if (L.kind <= BO_LEAF_MATERN52) {
@@ -181,7 +219,7 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
               double acc = 0.0;
               for (int f = 0; f < L.nd; ++f)
                 acc += (Ac[rl * BO_MAX_GROUPS + f] != Bc[cl * BO_MAX_GROUPS + f]) ? L.wls[f] : 0.0;
-              lv[(i * 4 + j) * 2 + e] = exp(-(acc / (double)L.nd));
+              lv[(i * 4 + j) * 2 + e] = exp_nonpos(-(acc / (double)L.nd));
             }
       } else {  // Tanimoto
         const int WC = 16;  // words per chunk; row stride WC + 1 words keeps AND/POPC loads conflict-light
@@ -230,9 +268,36 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
             }
         }
       }
+      if (leaf_major) {
+        if (single) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) prod[e] *= lv[e];
+          for (int e = 0; e < 16; ++e) total[e] += c_single * lv[e];
+        }
+        if (in_prod) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) prod[e] *= lv[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) prod[e] *= lv[e];
+        if (++f == md.nfac[term]) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) total[e] += prod[e];
+          ++term; f = 0;
+          while (term < md.n_terms && md.nfac[term] < 1) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) total[e] += md.coef[term];
+            ++term;
+          }
+          if (term < md.n_terms) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) prod[e] = md.coef[term];
+          }
+        }
+      }
     }
+  }
+  if (leaf_major && multi >= 0) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) total[e] += prod[e];
   }

@@ -79,6 +79,14 @@ def flatten(kernel: AnyKernel) -> FlatKernel:
         if isinstance(k, (RBFKernel, MaternKernel, HammingDistanceKernel, TanimotoKernel)):
             if isinstance(k, MaternKernel) and k.nu not in _NU_TO_KIND:
                 raise ValueError(f"Matern nu={k.nu} not in (0.5, 1.5, 2.5)")
+            if isinstance(k, TanimotoKernel):
+                # parameter-free: the Tanimoto leaf of the additive part and of the product part of MixedTanimotoGP
+                # (mixed_tanimoto_gp.py:165-215) are the same function -- share the leaf so that the device evaluates the
+                # 2048-bit AND + POPC once per pair (leaf-major evaluation in crosscov_kernel2).  Leaves with
+                # hyper-parameters are never merged: their lengthscale slots belong to the fit.
+                for i, other in enumerate(flat.leaves):
+                    if isinstance(other, TanimotoKernel) and list(other.active_dims) == list(k.active_dims):
+                        return [(1.0, [i])]
             flat.leaves.append(k)
             return [(1.0, [len(flat.leaves) - 1])]
         if isinstance(k, ScaleKernel):

@@ -3,7 +3,7 @@
 # the kernel inside tools/probe_ozaki.py full and captures that one with --set full
 K=$1; OUT=$2
 ncu --metrics launch__grid_size,gpu__time_duration.sum --clock-control none -k regex:$K -c 60 --csv --log-file /tmp/list_$OUT.csv \
-    python tools/probe_ozaki.py full > /dev/null 2>&1
+    ${PROBE:-python tools/probe_ozaki.py full} > /dev/null 2>&1
 IDX=$(python - <<PY
 import csv
 rows=list(csv.reader(open("/tmp/list_$OUT.csv")))
@@ -18,5 +18,5 @@ print(i[-1])
 PY
 )
 echo "largest-grid launch index of $K: $IDX"
-ncu --set full --clock-control none --import-source on -k regex:$K -s $IDX -c 1 -o gpurun_out/$OUT -f python tools/probe_ozaki.py full > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:$K -s $IDX -c 1 -o gpurun_out/$OUT -f ${PROBE:-python tools/probe_ozaki.py full} > /dev/null 2>&1
 ls -la gpurun_out/$OUT.ncu-rep
