@@ -396,32 +396,42 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         *reinterpret_cast<double2*>(Cs + (wr * 16 + i * 8 + g) * CC3_CLD + wc * 32 + j * 8 + 2 * t) =
             make_double2(acc[i][j][0], acc[i][j][1]);
     __syncthreads();
-    // compact, coalesced epilogue: one instance of the kernel function in the instruction stream
+    // compact, coalesced epilogue: one instance of the kernel function in the instruction stream; two row slices (4 kernel
+    // values) per iteration so that four independent exp chains are in flight per thread
 #pragma unroll 1
-    for (int idx = tid; idx < CC_TILE * (CC_TILE / 2); idx += 256) {
-      const int r = idx >> 5, c2 = (idx & 31) * 2;
-      const int gr = row0 + r, gc = col0 + c2;
-      if (gr >= n_rows || gc >= ld) {
-        if (oz.planes) *reinterpret_cast<double2*>(Cs + r * CC3_CLD + c2) = make_double2(0.0, 0.0);
-        continue;
-      }
-      const double2 d = *reinterpret_cast<const double2*>(Cs + r * CC3_CLD + c2);
-      const double na = n2a_s[r];
-      double s0 = fmax(na + n2b_s[c2] - 2.0 * d.x, 0.0);
-      double s1 = fmax(na + n2b_s[c2 + 1] - 2.0 * d.y, 0.0);
+    for (int idx = tid; idx < CC_TILE * (CC_TILE / 2); idx += 512) {
+      const int c2 = (idx & 31) * 2, gc = col0 + c2;
+      const int rA = idx >> 5, rB = rA + 8;
+      const int grA = row0 + rA, grB = row0 + rB;
+      const double2 dA = *reinterpret_cast<const double2*>(Cs + rA * CC3_CLD + c2);
+      const double2 dB = *reinterpret_cast<const double2*>(Cs + rB * CC3_CLD + c2);
+      const double nb0 = n2b_s[c2], nb1 = n2b_s[c2 + 1], naA = n2a_s[rA], naB = n2a_s[rB];
+      double st[4] = {fmax(naA + nb0 - 2.0 * dA.x, 0.0), fmax(naA + nb1 - 2.0 * dA.y, 0.0),
+                      fmax(naB + nb0 - 2.0 * dB.x, 0.0), fmax(naB + nb1 - 2.0 * dB.y, 0.0)};
       if (same_set) {
-        if (gr == gc) s0 = 0.0;
-        if (gr == gc + 1) s1 = 0.0;
+        if (grA == gc) st[0] = 0.0;
+        if (grA == gc + 1) st[1] = 0.0;
+        if (grB == gc) st[2] = 0.0;
+        if (grB == gc + 1) st[3] = 0.0;
       }
-      double l0, l1;
-      leaf_value_from_stat2(KIND, s0, s1, l0, l1);
-      const double v0 = (gc < n_cols) ? coef * l0 : 0.0;
-      const double v1 = (gc + 1 < n_cols) ? coef * l1 : 0.0;
-      if (!oz.planes || oz.write_fp64) {
-        if (gc + 1 < ld) *reinterpret_cast<double2*>(out + (size_t)gr * ld + gc) = make_double2(v0, v1);
-        else out[(size_t)gr * ld + gc] = v0;
+      double lv[4];
+      leaf_value_from_stat_n<4>(KIND, st, lv);
+      const bool c0 = gc < n_cols, c1 = gc + 1 < n_cols, okA = grA < n_rows, okB = grB < n_rows;
+      const double vA0 = (okA && c0) ? coef * lv[0] : 0.0, vA1 = (okA && c1) ? coef * lv[1] : 0.0;
+      const double vB0 = (okB && c0) ? coef * lv[2] : 0.0, vB1 = (okB && c1) ? coef * lv[3] : 0.0;
+      if ((!oz.planes || oz.write_fp64) && gc < ld) {
+        if (gc + 1 < ld) {
+          if (okA) *reinterpret_cast<double2*>(out + (size_t)grA * ld + gc) = make_double2(vA0, vA1);
+          if (okB) *reinterpret_cast<double2*>(out + (size_t)grB * ld + gc) = make_double2(vB0, vB1);
+        } else {
+          if (okA) out[(size_t)grA * ld + gc] = vA0;
+          if (okB) out[(size_t)grB * ld + gc] = vB0;
+        }
       }
-      if (oz.planes) *reinterpret_cast<double2*>(Cs + r * CC3_CLD + c2) = make_double2(v0, (gc + 1 < ld) ? v1 : 0.0);
+      if (oz.planes) {   // values for the slicing pass (zeros outside the matrix)
+        *reinterpret_cast<double2*>(Cs + rA * CC3_CLD + c2) = make_double2(vA0, vA1);
+        *reinterpret_cast<double2*>(Cs + rB * CC3_CLD + c2) = make_double2(vB0, vB1);
+      }
     }
     if (oz.planes) {
       // fused slicing for the INT8 digit-plane GEMM (ozaki.cu): thread = (row, 16-column chunk) of the 64 x 64 tile,
