@@ -817,7 +817,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
     const double* Xc = X_dev + (size_t)b0 * q * st->d;
-    const bool small_rows = rows <= 64 && !getenv("EVEREST_NO_SKINNY");
+    static const bool no_skinny = getenv("EVEREST_NO_SKINNY") != nullptr;   // debugging switch, read once
+    const bool small_rows = rows <= 64 && !no_skinny;
     // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
     // pay off when the GEMM dominates), 2 = always (tests)
     // N <= 16384: 7 plane pairs x N x 2^14 per S32 accumulator stays below 2^31

@@ -107,7 +107,7 @@ struct OzBatch {
   OzItem item[OZ_MAXOUT];
   int rows, q, N, n_ext, Rpad, ldw, n_chunks_k;   // n_chunks_k = ldk / 16
   int n_groups;
-  int dbg;                                        // EVEREST_OZAKI_DBG bits: 1 = no MMAs, 2 = no epilogue math, 4 = no TMA (pair kernel)
+  int dbg;                                        // EVEREST_OZAKI_DBG bits: 1 = no MMAs, 2 = no epilogue math, 4 = no TMA (pair kernel), 16 = evict_last scratch
   int gbeg[OZ_MAXGROUPS + 1];                     // column-tile ranges (units of OZ_BN columns)
   long long gqq_stride;
 };
@@ -380,6 +380,26 @@ struct O2Batch {
   long long* scratch;          // [O2_SCRATCH_SLOTS][8 warps][64 columns][32 lanes]
 };
 
+// Experiment kept behind EVEREST_OZAKI_DBG bit 16: marking the integer scratch slab (128 KB per SM, rewritten for every
+// tile) evict_last keeps it out of HBM (DRAM writes per launch 1.13 GB -> 0.19 GB, ncu) but the pinned lines cost the
+// neighbouring kernels more than the GEMM gains: the 16384-q-batch screen went from 9.51 to 9.63 ms (A/B on one box).
+// Default: plain stores / loads.
+__device__ __forceinline__ uint64_t oz_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void oz_st_keep(long long* p, long long v, uint64_t pol) {
+  if (pol) asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;\n" ::"l"(p), "l"(v), "l"(pol) : "memory");
+  else *p = v;
+}
+__device__ __forceinline__ long long oz_ld_keep(const long long* p, uint64_t pol) {
+  long long v;
+  if (pol) asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;\n" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  else v = *p;
+  return v;
+}
+
 template <int Q>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __grid_constant__ O2Batch batch) {
   extern __shared__ unsigned char ozraw[];
@@ -513,6 +533,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __gri
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     if (smid >= O2_SCRATCH_SLOTS) __trap();
+    const uint64_t scr_policy = (batch.dbg & 16) ? oz_policy_evict_last() : 0ull;
     long long* scr = batch.scratch + (((size_t)smid * 8 + ewarp) * 64) * 32 + lane;   // [column][lane]
     double g[8];
 #pragma unroll
@@ -548,7 +569,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __gri
           for (int c = 0; c < 32; ++c) lo[c] = (lvl == 3) ? (long long)(int)v[c] : lo[c] * 256 + (long long)(int)v[c];
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) scr[(size_t)(h * 32 + c) * 32] = lo[c];
+        for (int c = 0; c < 32; ++c) oz_st_keep(scr + (size_t)(h * 32 + c) * 32, lo[c], scr_policy);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       oz_mbar_arrive(acc_empty);
@@ -583,7 +604,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm2p_kernel(const __gri
         for (int c8 = 0; c8 < 64; c8 += 8) {
           long long lo[8];                     // the parked low levels come back from L2 eight at a time
 #pragma unroll
-          for (int k = 0; k < 8; ++k) lo[k] = scr[(size_t)(c8 + k) * 32];
+          for (int k = 0; k < 8; ++k) lo[k] = oz_ld_keep(scr + (size_t)(c8 + k) * 32, scr_policy);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int c = c8 + k;
@@ -791,6 +812,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     if (smid >= O2_SCRATCH_SLOTS) __trap();
+    const uint64_t scr_policy = (batch.dbg & 16) ? oz_policy_evict_last() : 0ull;
     long long* scr = batch.scratch + (((size_t)smid * 8 + ewarp) * 64) * 32 + lane;
     const uint32_t acc_empty_leader = oz_mapa(acc_empty, 0);
     double g[8];
@@ -826,7 +848,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
           for (int c = 0; c < 32; ++c) lo[c] = (lvl == 3) ? (long long)(int)v[c] : lo[c] * 256 + (long long)(int)v[c];
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) scr[(size_t)(h * 32 + c) * 32] = lo[c];
+        for (int c = 0; c < 32; ++c) oz_st_keep(scr + (size_t)(h * 32 + c) * 32, lo[c], scr_policy);
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
@@ -862,7 +884,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
         for (int c8 = 0; c8 < 64; c8 += 8) {
           long long lo[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) lo[k] = scr[(size_t)(c8 + k) * 32];
+          for (int k = 0; k < 8; ++k) lo[k] = oz_ld_keep(scr + (size_t)(c8 + k) * 32, scr_policy);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int c = c8 + k;
