@@ -263,7 +263,7 @@ int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc)
   a.linv_in_smem = (a.nb > 0 && smem + linv <= 96 * 1024) ? 1 : 0;
   if (a.linv_in_smem) smem += linv;
   if (smem > 200 * 1024) { bo_set_error("cond_root: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -1089,7 +1089,7 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   size_t smem = ((size_t)a.M * a.q * (a.nb + a.q) + a.q * a.M + (size_t)a.q * a.od.n_obj * nt + (size_t)a.q * nt + 32) *
                 sizeof(double);
   if (smem > 220 * 1024) { bo_set_error("mc_hvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

@@ -199,7 +199,7 @@ int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream
     if (want < nt) nt = want;
     smem = (fixed + per * nt + 32) * sizeof(double);
   }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -242,7 +242,7 @@ int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, co
   if (rows <= 0) return BO_OK;
   size_t smem = (size_t)S * sizeof(double);
   if (smem > 200 * 1024) { bo_set_error("grad_reduce: too many MC samples for shared memory (S=%d)", S); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(grad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -353,7 +353,7 @@ int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounte
   int wpc = (4 * per_warp <= 96 * 1024) ? 4 : 1;
   size_t smem = wpc * per_warp;
   if (smem > 200 * 1024) { bo_set_error("cond_root_bwd: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -534,7 +534,7 @@ int launch_kernel_grad(const KernelGradArgs& a, cudaStream_t st, LaunchCounter* 
     if (a.md.leaf[l].kind <= BO_LEAF_MATERN52) dpad_max = std::max(dpad_max, a.md.leaf[l].dpad);
   size_t smem = ((size_t)2 * KG_CHUNK + 512 + dpad_max + a.d) * sizeof(double);
   if (smem > 200 * 1024) { bo_set_error("kernel_grad: input dimension too large for shared memory (d=%d)", a.d); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(kernel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

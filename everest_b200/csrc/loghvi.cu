@@ -218,7 +218,7 @@ int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
   size_t smem = 0;
   const int nt = lh_pick_threads(a, false, &smem);
   if (!nt) { bo_set_error("mc_loghvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -331,7 +331,7 @@ int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStr
   size_t smem = 0;
   const int nt = lh_pick_threads(a, true, &smem);
   if (!nt) { bo_set_error("mc_loghvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

@@ -214,7 +214,7 @@ int launch_mll_grad(const ModelD& md, const PrepD& train, int N, int ldk, const 
     if (md.leaf[l].kind <= BO_LEAF_MATERN52) dpad_max = std::max(dpad_max, md.leaf[l].dpad);
   size_t smem = ((size_t)2 * ML_CHUNK + 768 + dpad_max + a.n_params + 32) * sizeof(double);
   if (smem > 200 * 1024) { bo_set_error("mll_grad: too many hyper-parameters for shared memory"); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

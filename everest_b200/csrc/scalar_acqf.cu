@@ -168,7 +168,7 @@ int launch_mc_scalar(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
   const int nt = 256;
   size_t smem = scalar_smem_bytes(a);
   if (smem > 220 * 1024) { bo_set_error("mc_scalar: shared memory budget exceeded"); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -291,7 +291,7 @@ int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStr
   const int nt = 128;
   size_t smem = scalar_smem_bytes(a);
   if (smem > 220 * 1024) { bo_set_error("mc_scalar_grad: shared memory budget exceeded"); return BO_ERR_INVALID; }
-  static size_t attr = 0;
+  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_scalar_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
