@@ -131,14 +131,16 @@ cond_root_kernel(CondRootArgs a) {
   const int q = a.q, nb = a.nb, nr = nb + q;
   const ModelD& md = a.md;
   // per-warp scratch, then (optionally) the CTA-shared copy of L_b^-1
-  double* Sqb = csm + (size_t)warp_in_cta * (2 * q * nb + 2 * q * q);  // [q][nb]
+  const int blw = max(nb, a.stage_cols);                               // columns of the BLs scratch (bl, or staged rows)
+  const size_t per_warp = (size_t)q * nb + 2 * q * q + (size_t)q * blw;
+  double* Sqb = csm + (size_t)warp_in_cta * per_warp;                   // [q][nb]
   double* Sc = Sqb + q * nb;                                            // [q][q]
   double* Lq = Sc + q * q;                                              // [q][q]
   double* BLs = Lq + q * q;                                             // [q][nb] bl
   const double* Li = a.LbInv;
   int ldli = a.ldlb;
   if (a.linv_in_smem) {
-    double* Ls = csm + (size_t)4 * (2 * q * nb + 2 * q * q);
+    double* Ls = csm + (size_t)4 * per_warp;
     ldli = nb | 1;  // odd stride: lanes (rows e) hit distinct banks
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x)
       Ls[(idx / nb) * ldli + (idx % nb)] = a.LbInv[(size_t)(idx / nb) * a.ldlb + (idx % nb)];
@@ -149,11 +151,47 @@ cond_root_kernel(CondRootArgs a) {
   const double s2 = md.y_std * md.y_std;
   const int row0 = batch * q;
 
-  for (int j = 0; j < q; ++j)
+  const bool one_cont_leaf = md.n_terms == 1 && md.nfac[0] == 1 && md.leaf[md.fac[0][0]].kind <= BO_LEAF_MATERN52 &&
+                             q <= 8 && md.leaf[md.fac[0][0]].dpad <= 64;
+  if (one_cont_leaf) {
+    // SingleTaskGP default (one RBF / Matern leaf): the q candidate rows of this batch sit in shared memory and every
+    // baseline row is read from global memory ONCE for all q kernel values (model_eval_pair re-reads both rows per value).
+    // Same arithmetic in the same order as leaf_eval_pair -> bit-identical results.
+    const int l = md.fac[0][0];
+    const LeafD& L = md.leaf[l];
+    double* aq = BLs;                       // [q][dpad] staging, overwritten by bl afterwards (q * dpad <= q * nb is not
+                                            // guaranteed: the launcher sizes BLs for max(nb, dpad) columns)
+    for (int idx = lane; idx < q * L.dpad; idx += 32) aq[idx] = a.prep_q.Xs[l][(size_t)row0 * L.dpad + idx];
+    __syncwarp();
     for (int e = lane; e < nb; e += 32) {
-      double kqb = model_eval_pair(md, a.prep_q, row0 + j, a.prep_b, e, false);
-      Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
+      const double* bx = a.prep_b.Xs[l] + (size_t)e * L.dpad;
+      double dot[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot[j] = 0.0;
+      for (int k = 0; k < L.nd; ++k) {
+        const double bk = bx[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < q) dot[j] = fma(aq[j * L.dpad + k], bk, dot[j]);
+      }
+      const double n2b = a.prep_b.n2[l][e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < q) {
+          const double stat = fmax(a.prep_q.n2[l][row0 + j] + n2b - 2.0 * dot[j], 0.0);
+          double kqb = 0.0;
+          kqb += md.coef[0] * leaf_value_from_stat(L.kind, stat);
+          Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
+        }
     }
+    __syncwarp();
+  } else {
+    for (int j = 0; j < q; ++j)
+      for (int e = lane; e < nb; e += 32) {
+        double kqb = model_eval_pair(md, a.prep_q, row0 + j, a.prep_b, e, false);
+        Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
+      }
+  }
   for (int p = lane; p < q * q; p += 32) {
     int i = p / q, j = p % q;
     if (j >= i) {
@@ -168,10 +206,26 @@ cond_root_kernel(CondRootArgs a) {
   if (a.linv_in_smem) {
     for (int e = lane; e < nb; e += 32) {
       const double* lrow = Li + (size_t)e * ldli;
-      for (int j = 0; j < q; ++j) {
-        double s = 0.0;
-        for (int l = 0; l <= e; ++l) s = fma(Sqb[j * nb + l], lrow[l], s);
-        BLs[j * nb + e] = s;
+      if (q <= 8) {
+        // one pass over row e of L_b^-1 for all q points (same summation order per point)
+        double acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+        for (int l = 0; l <= e; ++l) {
+          const double lv = lrow[l];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < q) acc[j] = fma(Sqb[j * nb + l], lv, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < q) BLs[j * nb + e] = acc[j];
+      } else {
+        for (int j = 0; j < q; ++j) {
+          double s = 0.0;
+          for (int l = 0; l <= e; ++l) s = fma(Sqb[j * nb + l], lrow[l], s);
+          BLs[j * nb + e] = s;
+        }
       }
     }
   } else {
@@ -257,7 +311,12 @@ cond_root_kernel(CondRootArgs a) {
 int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc) {
   if (a0.b <= 0) return BO_OK;
   CondRootArgs a = a0;
-  size_t per_warp = (size_t)(2 * a.q * a.nb + 2 * a.q * a.q) * sizeof(double);
+  // the staging of the q candidate rows (single continuous leaf) shares the bl scratch: size it for max(nb, dpad) columns
+  a.stage_cols = 0;
+  if (a.md.n_terms == 1 && a.md.nfac[0] == 1 && a.md.leaf[a.md.fac[0][0]].kind <= BO_LEAF_MATERN52)
+    a.stage_cols = a.md.leaf[a.md.fac[0][0]].dpad;
+  const int blw = std::max(a.nb, a.stage_cols);
+  size_t per_warp = ((size_t)a.q * a.nb + 2 * (size_t)a.q * a.q + (size_t)a.q * blw) * sizeof(double);
   size_t smem = 4 * per_warp;
   size_t linv = (size_t)a.nb * (a.nb | 1) * sizeof(double);
   a.linv_in_smem = (a.nb > 0 && smem + linv <= 96 * 1024) ? 1 : 0;

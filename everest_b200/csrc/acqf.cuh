@@ -15,6 +15,7 @@ struct CondRootArgs {
   const double* LbInvT;  // [nb, ldlb] transpose of the inverse (coalesced access when it does not fit in smem)
   int ldlb;
   int linv_in_smem;      // set by the launcher
+  int stage_cols;        // set by the launcher: dpad of the single continuous leaf (0 = generic kernel tree)
   double* root;          // [b, M, q, nb+q]
   double* BL;            // [b*q, ldbl] copy of bl for output m, zero padded (operand of the sample GEMM) or NULL
   int ldbl;
