@@ -864,9 +864,12 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
 
 #define MT_S 64
 #define MT_B 64
-template <int QMAX, int MO>
+// STAGE: the conditional-root rows br[j][0..q) and the means of the CTA's 64 q-batches are staged in shared memory
+// once (they are the same for all 64 samples), so the only global loads left in the batch loop are the Fp
+// values; `prefetch` asks for those of the lane's next batch while the cells of the current one run.
+template <int QMAX, int MO, bool STAGE>
 __global__ void __launch_bounds__(256, (QMAX <= 4) ? 3 : 2)
-mc_hvi_tiled_kernel(McArgs a, int maxc) {
+mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
   extern __shared__ double tsm[];
   const int tid = threadIdx.x, sl = tid & 63, bl = tid >> 6;
   const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S;
@@ -876,7 +879,17 @@ mc_hvi_tiled_kernel(McArgs a, int maxc) {
   double* zq = cup + (size_t)maxc * MO * MT_S;    // [q*M][64]
   double* half = zq + (size_t)q * M * MT_S;       // [8] warp sums
   int* ncs = reinterpret_cast<int*>(half + 8);    // [64]
+  double* rqs = half + 8 + MT_S / 2;              // [64][M*q][q]  (STAGE)
+  double* mus = rqs + (size_t)MT_B * M * q * q;   // [64][q*M]     (STAGE)
   for (int i = tid; i < MT_S; i += 256) ncs[i] = (s0 + i < S) ? a.ncells[s0 + i] : 0;
+  if (STAGE) {
+    const int nbat = min(MT_B, a.b - b0);
+    for (int idx = tid; idx < nbat * M * q * q; idx += 256) {
+      int k = idx % q, row = idx / q;  // row = ((bat*M + m)*q + j)
+      rqs[idx] = a.root[((size_t)b0 * M * q + row) * nr + nb + k];
+    }
+    for (int idx = tid; idx < nbat * q * M; idx += 256) mus[idx] = a.mu[(size_t)b0 * q * M + idx];
+  }
   for (int idx = tid; idx < maxc * MO * MT_S; idx += 256) {
     int ss = idx & 63, co = idx >> 6;
     bool ok = s0 + ss < S;
@@ -897,6 +910,11 @@ mc_hvi_tiled_kernel(McArgs a, int maxc) {
     if (batch >= a.b) break;  // uniform for the two warps of a batch lane
     double acc = 0.0;
     if (s_ok) {
+      if (prefetch && nb > 0 && bat + 4 < MT_B && batch + 4 < a.b) {
+        for (int m = 0; m < M; ++m)
+          for (int j = 0; j < q; ++j)
+            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(a.Fp + (size_t)m * a.fp_stride + ((size_t)(batch + 4) * q + j) * S + s));
+      }
       double obj[QMAX][MO], fwt[QMAX];
 #pragma unroll
       for (int j = 0; j < QMAX; ++j) {
@@ -906,11 +924,15 @@ mc_hvi_tiled_kernel(McArgs a, int maxc) {
         if (j < q) {
           double y[2 * BO_MAX_OBJECTIVES];
           for (int m = 0; m < M; ++m) {
-            const double* rr = a.root + (((size_t)batch * M + m) * q + j) * nr + nb;
+            const double* rr = STAGE ? rqs + ((bat * M + m) * q + j) * q
+                                     : a.root + (((size_t)batch * M + m) * q + j) * nr + nb;
             double sb = (nb > 0) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0;
             double sq = 0.0;
-            for (int k = 0; k < q; ++k) sq = fma(rr[k], zq[(k * M + m) * MT_S + sl], sq);
-            y[m] = (a.mu[((size_t)batch * q + j) * M + m] + sb) + sq;
+#pragma unroll
+            for (int k = 0; k < QMAX; ++k)
+              if (k < q) sq = fma(rr[k], zq[(k * M + m) * MT_S + sl], sq);
+            const double mu_jm = STAGE ? mus[(bat * q + j) * M + m] : a.mu[((size_t)batch * q + j) * M + m];
+            y[m] = (mu_jm + sb) + sq;
           }
 #pragma unroll
           for (int o = 0; o < MO; ++o) obj[j][o] = objective_apply(a.od.op[o], y);
@@ -937,19 +959,33 @@ mc_hvi_tiled_kernel(McArgs a, int maxc) {
   }
 }
 
-typedef void (*McTiledFn)(McArgs, int);
-template <int MO>
+typedef void (*McTiledFn)(McArgs, int, int);
+template <int MO, bool STAGE>
 static McTiledFn pick_tiled_q(int q) {
-  if (q <= 2) return mc_hvi_tiled_kernel<2, MO>;
-  if (q <= 4) return mc_hvi_tiled_kernel<4, MO>;
-  if (q <= 8) return mc_hvi_tiled_kernel<8, MO>;
+  if (q <= 2) return mc_hvi_tiled_kernel<2, MO, STAGE>;
+  if (q <= 4) return mc_hvi_tiled_kernel<4, MO, STAGE>;
+  if (q <= 8) return mc_hvi_tiled_kernel<8, MO, STAGE>;
   return nullptr;
 }
-static McTiledFn pick_tiled(int q, int Mo) {
-  if (Mo == 2) return pick_tiled_q<2>(q);
-  if (Mo == 3) return pick_tiled_q<3>(q);
-  if (Mo == 4) return pick_tiled_q<4>(q);
+template <bool STAGE>
+static McTiledFn pick_tiled_s(int q, int Mo) {
+  if (Mo == 2) return pick_tiled_q<2, STAGE>(q);
+  if (Mo == 3) return pick_tiled_q<3, STAGE>(q);
+  if (Mo == 4) return pick_tiled_q<4, STAGE>(q);
   return nullptr;
+}
+static McTiledFn pick_tiled(int q, int Mo, bool stage = false) {
+  return stage ? pick_tiled_s<true>(q, Mo) : pick_tiled_s<false>(q, Mo);
+}
+// EVEREST_MC_STAGE=0 keeps the root rows / means in global memory (1.09 vs 0.96 ms per config-3 screen),
+// EVEREST_MC_PREFETCH=1 adds the L1 prefetch of the next Fp values (measured 2 % slower, off by default)
+// (experiment switches, read once).
+static int mc_env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+static size_t mc_stage_bytes(const McArgs& a) {
+  return ((size_t)MT_B * a.M * a.q * a.q + (size_t)MT_B * a.q * a.M) * sizeof(double);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1132,12 +1168,16 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   }
   // tiled path: needs per-sample cells, the sample GEMM output (or no baseline) and a cell list that fits
   size_t tiled = 0;
-  McTiledFn fn = pick_tiled(a.q, Mo);
   if (mc_use_tiled(a, max_cells, &tiled)) {
+    static const int want_stage = mc_env_flag("EVEREST_MC_STAGE", 1), prefetch = mc_env_flag("EVEREST_MC_PREFETCH", 0);
+    // staging must leave room for two CTAs per SM
+    const bool stage = want_stage && tiled + mc_stage_bytes(a) <= 100 * 1024;
+    if (stage) tiled += mc_stage_bytes(a);
+    McTiledFn fn = pick_tiled(a.q, Mo, stage);
     if (tiled > 48 * 1024) CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled));
     CUDA_CHECK_RET(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     dim3 grid((a.S + MT_S - 1) / MT_S, (a.b + MT_B - 1) / MT_B);
-    fn<<<grid, 256, tiled, st>>>(a, max_cells);
+    fn<<<grid, 256, tiled, st>>>(a, max_cells, prefetch);
     if (lc) lc->n++;
     mc_reduce_partials_kernel<<<(a.b + 255) / 256, 256, 0, st>>>(a.partial, grid.x, a.b, a.S, a.out, a.info_in, a.M, a.info_out);
     if (lc) lc->n++;
