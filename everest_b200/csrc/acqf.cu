@@ -811,7 +811,8 @@ mc_hvi_kernel(McArgs a) {
 template <int QMAX, int MO>
 __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO], const double (&fwt)[QMAX], int q,
                                                     bool has_cons, const double* __restrict__ lo_p,
-                                                    const double* __restrict__ up_p, int stride) {
+                                                    const double* __restrict__ up_p, int stride,
+                                                    bool single_fast = false) {
   unsigned active = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
   double lo[MO];
 #pragma unroll
@@ -828,6 +829,24 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
   double up[MO];
 #pragma unroll
   for (int o = 0; o < MO; ++o) up[o] = up_p[o * stride];
+  if (single_fast && (active & (active - 1u)) == 0u) {
+    // one overlapping point (the common case): the only subset is the point itself, same operations as the general
+    // loop below would do for it (vol = 1 * side_0 * side_1 ..., then the weight, then 0 + vol)
+    double vol = 1.0, w = fwt[0];
+#pragma unroll
+    for (int j = 1; j < QMAX; ++j)
+      if ((active >> j) & 1u) w = fwt[j];
+#pragma unroll
+    for (int o = 0; o < MO; ++o) {
+      double v = obj[0][o];
+#pragma unroll
+      for (int j = 1; j < QMAX; ++j)
+        if ((active >> j) & 1u) v = obj[j][o];
+      vol *= fmax(fmin(up[o], v) - lo[o], 0.0);
+    }
+    if (has_cons) vol *= w;
+    return 0.0 + (0.0 + vol);
+  }
   // one pass over the subsets of the active set; the per-size sums keep the order of the reference (sizes 1..q with
   // alternating sign, subsets of one size in the same descending enumeration order as a size-by-size loop)
   double asum[QMAX + 1];
@@ -910,7 +929,7 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
     if (batch >= a.b) break;  // uniform for the two warps of a batch lane
     double acc = 0.0;
     if (s_ok) {
-      if (prefetch && nb > 0 && bat + 4 < MT_B && batch + 4 < a.b) {
+      if ((prefetch & 1) && nb > 0 && bat + 4 < MT_B && batch + 4 < a.b) {
         for (int m = 0; m < M; ++m)
           for (int j = 0; j < q; ++j)
             asm volatile("prefetch.global.L1 [%0];\n" ::"l"(a.Fp + (size_t)m * a.fp_stride + ((size_t)(batch + 4) * q + j) * S + s));
@@ -946,8 +965,28 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
           }
         }
       }
-      for (int c = 0; c < nc; ++c)
-        acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MT_S + sl, cup + (c * MO) * MT_S + sl, MT_S);
+      if (prefetch & 2) {  // EVEREST_MC_FAST=0: the session-3 cell loop
+        for (int c = 0; c < nc; ++c)
+          acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MT_S + sl, cup + (c * MO) * MT_S + sl, MT_S);
+      } else {
+        // A point can only overlap a cell whose lower corner lies below the per-objective maxima over the q points:
+        // two compares reject most cells before the per-point test (rejected cells contribute exactly 0).
+        double mx[MO];
+#pragma unroll
+        for (int o = 0; o < MO; ++o) {
+          mx[o] = obj[0][o];
+#pragma unroll
+          for (int j = 1; j < QMAX; ++j) mx[o] = fmax(mx[o], obj[j][o]);
+        }
+        const double* lp = clo + sl;
+        const double* upp = cup + sl;
+        for (int c = 0; c < nc; ++c, lp += MO * MT_S, upp += MO * MT_S) {
+          bool maybe = true;
+#pragma unroll
+          for (int o = 0; o < MO; ++o) maybe = maybe && (mx[o] > lp[o * MT_S]);
+          if (maybe) acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, lp, upp, MT_S, true);
+        }
+      }
     }
     // sum over this CTA's 64 samples: two warps share one batch lane
     double wsum = warp_sum(acc);
@@ -1169,7 +1208,8 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   // tiled path: needs per-sample cells, the sample GEMM output (or no baseline) and a cell list that fits
   size_t tiled = 0;
   if (mc_use_tiled(a, max_cells, &tiled)) {
-    static const int want_stage = mc_env_flag("EVEREST_MC_STAGE", 1), prefetch = mc_env_flag("EVEREST_MC_PREFETCH", 0);
+    static const int want_stage = mc_env_flag("EVEREST_MC_STAGE", 1),
+                     prefetch = (mc_env_flag("EVEREST_MC_PREFETCH", 0) ? 1 : 0) | (mc_env_flag("EVEREST_MC_FAST", 1) ? 0 : 2);
     // staging must leave room for two CTAs per SM
     const bool stage = want_stage && tiled + mc_stage_bytes(a) <= 100 * 1024;
     if (stage) tiled += mc_stage_bytes(a);
