@@ -935,6 +935,17 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
             asm volatile("prefetch.global.L1 [%0];\n" ::"l"(a.Fp + (size_t)m * a.fp_stride + ((size_t)(batch + 4) * q + j) * S + s));
       }
       double obj[QMAX][MO], fwt[QMAX];
+      // up to two model outputs: all Fp values of the batch are requested before the first one is used, so the
+      // thread waits for global memory once per batch and not once per (point, output)
+      const bool pre = (M <= 2) && nb > 0 && !(prefetch & 4);
+      double sbv[QMAX][2];
+      if (pre) {
+#pragma unroll
+        for (int j = 0; j < QMAX; ++j)
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+            sbv[j][m] = (j < q && m < M) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0;
+      }
 #pragma unroll
       for (int j = 0; j < QMAX; ++j) {
         fwt[j] = 1.0;
@@ -942,16 +953,23 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
         for (int o = 0; o < MO; ++o) obj[j][o] = -INFINITY;  // unused slots never overlap a cell
         if (j < q) {
           double y[2 * BO_MAX_OBJECTIVES];
-          for (int m = 0; m < M; ++m) {
+          auto point_output = [&](int m, double sb) {
             const double* rr = STAGE ? rqs + ((bat * M + m) * q + j) * q
                                      : a.root + (((size_t)batch * M + m) * q + j) * nr + nb;
-            double sb = (nb > 0) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0;
             double sq = 0.0;
 #pragma unroll
             for (int k = 0; k < QMAX; ++k)
               if (k < q) sq = fma(rr[k], zq[(k * M + m) * MT_S + sl], sq);
             const double mu_jm = STAGE ? mus[(bat * q + j) * M + m] : a.mu[((size_t)batch * q + j) * M + m];
             y[m] = (mu_jm + sb) + sq;
+          };
+          if (pre) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+              if (m < M) point_output(m, sbv[j][m]);
+          } else {
+            for (int m = 0; m < M; ++m)
+              point_output(m, (nb > 0) ? a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s] : 0.0);
           }
 #pragma unroll
           for (int o = 0; o < MO; ++o) obj[j][o] = objective_apply(a.od.op[o], y);
@@ -1209,7 +1227,8 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   size_t tiled = 0;
   if (mc_use_tiled(a, max_cells, &tiled)) {
     static const int want_stage = mc_env_flag("EVEREST_MC_STAGE", 1),
-                     prefetch = (mc_env_flag("EVEREST_MC_PREFETCH", 0) ? 1 : 0) | (mc_env_flag("EVEREST_MC_FAST", 1) ? 0 : 2);
+                     prefetch = (mc_env_flag("EVEREST_MC_PREFETCH", 0) ? 1 : 0) | (mc_env_flag("EVEREST_MC_FAST", 1) ? 0 : 2) |
+                                (mc_env_flag("EVEREST_MC_FPBATCH", 1) ? 0 : 4);
     // staging must leave room for two CTAs per SM
     const bool stage = want_stage && tiled + mc_stage_bytes(a) <= 100 * 1024;
     if (stage) tiled += mc_stage_bytes(a);
