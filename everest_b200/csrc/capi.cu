@@ -1114,9 +1114,15 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
     // inputs below 8 MiB cross PCIe in ~0.3 ms: nothing worth hiding, and whole-batch launches fill the GPU better
     if (b <= 2 * min_b || in_bytes < ((size_t)8 << 20)) chunk_b.push_back(b);
     else if (r < 0.15) {
-      const int first = std::max(min_b, b / 8);
+      // EVEREST_HOST_FIRST_DIV=n: first chunk = b / n (default 8); EVEREST_HOST_THREE=1: a third, intermediate
+      // chunk of three times the first (experiment switches, read once).  Measured on config 3 (tools/exp_host.sh):
+      // b/8 9.46 ms per screen, b/4 9.62, b/16 9.60, b/16 + 3b/16 + rest 9.78, b/32 three-way 10.27: b/8 stays.
+      static const int first_div = []() { const char* e = getenv("EVEREST_HOST_FIRST_DIV"); int v = e ? atoi(e) : 8; return v >= 2 ? v : 8; }();
+      static const int three = []() { const char* e = getenv("EVEREST_HOST_THREE"); return e ? atoi(e) : 0; }();
+      const int first = std::max(min_b, b / first_div);
       chunk_b.push_back(first);
-      chunk_b.push_back(b - first);
+      if (three && b - first > 4 * first) chunk_b.push_back(3 * first);
+      chunk_b.push_back(b - first - (chunk_b.size() > 1 ? 3 * first : 0));
     } else {
       const int n = (int)std::min<long long>(8, std::max<long long>(1, b / min_b));
       for (int i = 0, left = b; i < n; ++i) {
