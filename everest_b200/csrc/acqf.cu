@@ -1130,6 +1130,8 @@ mc_hvi_chunked_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
         if (has_cons && j < q) fwt[j] = ob[(size_t)(q * MO + j) * S];
       }
       double sum = 0.0;
+      // (the tiled kernel's maxima pre-filter was tried here too: bit-identical but no faster on config 4, where the
+      // q = 8 points of a batch overlap most cells: 15.05 vs 15.3 ms, tools/exp_mc4.sh)
       for (int c = 0; c < cn; ++c)
         sum += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MC2_S + sl, cup + (c * MO) * MC2_S + sl, MC2_S);
       acc[t] += sum;

@@ -4,9 +4,9 @@ import os, sys, torch
 sys.path.insert(0, '.')
 from everest_b200 import configs as Cf
 tag = sys.argv[1]
-p = Cf.zdt1_qnehvi()
+p = Cf.dtlz2_qnehvi() if len(sys.argv) > 2 and sys.argv[2] == "dtlz2" else Cf.zdt1_qnehvi()
 st = Cf.build_state(p)
-acq = Cf.build_acqf(p, st, prune_samples=2048)
+acq = Cf.build_acqf(p, st, prune_samples=2048) if p.get("name", "") != "dtlz2" and not (len(sys.argv) > 2 and sys.argv[2] == "dtlz2") else Cf.build_acqf(p, st)
 X = Cf.candidates(p).to(st.device)
 for _ in range(3): v = acq(X)
 torch.cuda.synchronize()
