@@ -4,9 +4,10 @@ import os, sys, torch
 sys.path.insert(0, '.')
 from everest_b200 import configs as Cf
 tag = sys.argv[1]
-p = Cf.dtlz2_qnehvi() if len(sys.argv) > 2 and sys.argv[2] == "dtlz2" else Cf.zdt1_qnehvi()
+dtlz2 = len(sys.argv) > 2 and sys.argv[2] == "dtlz2"   # config 4 (many-cell kernel) instead of config 3 (tiled kernel)
+p = Cf.dtlz2_qnehvi() if dtlz2 else Cf.zdt1_qnehvi()
 st = Cf.build_state(p)
-acq = Cf.build_acqf(p, st, prune_samples=2048) if p.get("name", "") != "dtlz2" and not (len(sys.argv) > 2 and sys.argv[2] == "dtlz2") else Cf.build_acqf(p, st)
+acq = Cf.build_acqf(p, st) if dtlz2 else Cf.build_acqf(p, st, prune_samples=2048)
 X = Cf.candidates(p).to(st.device)
 for _ in range(3): v = acq(X)
 torch.cuda.synchronize()
