@@ -76,7 +76,9 @@ SYMBOLS = {
                                     C.POINTER(ConstraintOp), C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
                                     c_int_p, C.c_void_p]),
     "bo_prune_counts_scalar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
-                                         C.POINTER(ObjectiveOp), C.c_int32, C.c_void_p, c_int_p, C.c_void_p]),
+                                         C.POINTER(ObjectiveOp), C.c_int32, C.POINTER(ConstraintOp), C.c_int32, C.c_void_p,
+                                         c_int_p, C.c_void_p]),
+    "bo_scalar_baseline_best": (C.c_int, [C.c_void_p, C.c_double, c_int_p, C.c_void_p]),
     "bo_acqf_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "bo_acqf_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

@@ -345,6 +345,40 @@ class qLogExpectedHypervolumeImprovement(qExpectedHypervolumeImprovement):
         self.set_option("tau_max", self._taus[1])
 
 
+def _feasible(constraints, Y: torch.Tensor) -> torch.Tensor:
+    """[UPSTREAM] compute_feasibility_indicator: every output constraint c(y) <= 0."""
+    ok = torch.ones(Y.shape[:-1], dtype=torch.bool, device=Y.device)
+    for c in constraints or []:
+        ok = ok & (c(Y) <= 0)
+    return ok
+
+
+def estimate_objective_lower_bound(model: DeviceGPState, objective, X, generator=None) -> float:
+    """[UPSTREAM] botorch.acquisition.utils._estimate_objective_lower_bound: minus get_infeasible_cost at 32 random convex
+    combinations of X -- objective(mean - 6 sd), minimum over the points, clamped at 0 from above.  BoTorch draws the
+    weights from torch's global generator; so does this unless `generator` is given."""
+    X = torch.as_tensor(X, dtype=torch.double).cpu()
+    w = torch.rand(32, X.shape[-2], dtype=torch.double, generator=generator)
+    w = w / w.sum(dim=0, keepdim=True)
+    mean, var = model.posterior(w @ X)
+    lb = objective((mean - 6.0 * var.clamp_min(0.0).sqrt()).cpu())
+    return float(lb.min().clamp_max(0.0))
+
+
+def best_feasible_objective(model: DeviceGPState, objective, constraints, Y: torch.Tensor, X_baseline, generator=None) -> float:
+    """[UPSTREAM] compute_best_feasible_objective on posterior means Y [n, M] (the incumbent of qEI / qLogEI / qPI as
+    get_acquisition_function builds it): the best objective among the points that satisfy every output constraint; when
+    none does, the pessimistic lower bound above."""
+    Y = Y.cpu()
+    obj = objective(Y)
+    if not constraints:
+        return float(obj.max())
+    ok = _feasible(constraints, Y)
+    if bool(ok.any()):
+        return float(obj[ok].max())
+    return estimate_objective_lower_bound(model, objective, X_baseline, generator=generator)
+
+
 class _ScalarAcquisition(_DeviceAcquisition):
     """Single-objective MC acquisition functions of SoboStrategy (sobo.py:51-90): qLogEI, qEI, qSR, qUCB, qPI with a
     fixed incumbent and -- when `X_baseline` is given -- the noisy variants qLogNEI (SoboStrategy's default) / qNEI, whose
@@ -356,8 +390,9 @@ class _ScalarAcquisition(_DeviceAcquisition):
     def __init__(self, model: DeviceGPState, objective: ScalarObjective, best_f: Optional[float] = None, X_baseline=None,
                  mc_samples: int = 512, seed: Optional[int] = None, constraints: Optional[List[OutputConstraint]] = None,
                  eta=None, X_pending=None, prune_baseline: bool = True, prune_samples: int = 2048, param: float = 0.0,
-                 cache_root: bool = True):
+                 cache_root: bool = True, lb_generator=None):
         super().__init__(model, mc_samples, seed)
+        self._lb_generator = lb_generator
         if not cache_root:
             raise NotImplementedError("cache_root=False (joint re-sampling of the baseline) is not accelerated")
         self.objective = objective
@@ -402,6 +437,17 @@ class _ScalarAcquisition(_DeviceAcquisition):
                                                 0.0 if self._NOISY else self.best_f,
                                                 _dev_ptr(Xbd) if Xbd is not None else None, self.nb,
                                                 _dev_ptr(zb) if zb is not None else None, info, _stream()))
+            if self._NOISY and self._n_con:
+                # [UPSTREAM] compute_best_feasible_objective: infeasible baseline samples are -inf unless some MC sample
+                # has no feasible baseline point at all -- then BoTorch substitutes its pessimistic lower bound
+                cnt = C.c_int32(0)
+                L.check(model.lib.bo_scalar_baseline_best(model.handle, float("-inf"), C.byref(cnt), _stream()))
+                self.n_all_infeasible = int(cnt.value)
+                if cnt.value > 0:
+                    if getattr(self, "_infeasible_value", None) is None:
+                        self._infeasible_value = estimate_objective_lower_bound(model, self.objective, self.X_baseline,
+                                                                                generator=self._lb_generator)
+                    L.check(model.lib.bo_scalar_baseline_best(model.handle, self._infeasible_value, C.byref(cnt), _stream()))
         self._claim()
 
     def _prune(self, Xb, prune_samples, seed_offset=7919):
@@ -414,8 +460,8 @@ class _ScalarAcquisition(_DeviceAcquisition):
         Xd = Xb.to(model.device).contiguous()
         with torch.cuda.device(model.device):
             L.check(model.lib.bo_prune_counts_scalar(model.handle, _dev_ptr(Xd), n, _dev_ptr(z), prune_samples,
-                                                     self.objective.combine_code, self._obj_c, self._n_obj,
-                                                     _dev_ptr(counts), info, _stream()))
+                                                     self.objective.combine_code, self._obj_c, self._n_obj, self._con_c,
+                                                     self._n_con, _dev_ptr(counts), info, _stream()))
         self.prune_counts = counts
         return torch.nonzero(counts > 0).view(-1)
 
@@ -463,10 +509,10 @@ class qNoisyExpectedImprovement(_ScalarAcquisition):
     _NOISY = True
 
     def __init__(self, model, X_baseline, objective, mc_samples=512, seed=None, constraints=None, eta=None, X_pending=None,
-                 prune_baseline=True, prune_samples=2048, cache_root=True):
+                 prune_baseline=True, prune_samples=2048, cache_root=True, lb_generator=None):
         super().__init__(model, objective, X_baseline=X_baseline, mc_samples=mc_samples, seed=seed, constraints=constraints,
                          eta=eta, X_pending=X_pending, prune_baseline=prune_baseline, prune_samples=prune_samples,
-                         cache_root=cache_root)
+                         cache_root=cache_root, lb_generator=lb_generator)
 
 
 class qLogNoisyExpectedImprovement(qNoisyExpectedImprovement):
@@ -481,8 +527,10 @@ def get_acquisition_function(acquisition_function_name: str, model: DeviceGPStat
     mobo.py:72-90): every name the Sobo / Mobo data models can select."""
     name = acquisition_function_name
     if name in ("qEI", "qLogEI", "qPI"):
+        # [UPSTREAM] the non-noisy variants take the best FEASIBLE objective of the posterior mean at the observed points
+        # (compute_best_feasible_objective); `eta` does not enter the hard feasibility test
         mean, _ = model.posterior(X_observed)
-        best_f = float(objective(mean.cpu()).max())
+        best_f = best_feasible_objective(model, objective, constraints, mean, X_observed, generator=kwargs.pop("lb_generator", None))
         if name == "qLogEI":
             return qLogExpectedImprovement(model, best_f, objective, mc_samples=mc_samples, seed=seed,
                                            constraints=constraints, eta=eta, X_pending=X_pending)

@@ -9,8 +9,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libeverest_b200.so")
 SOURCES = ["kernels_eval.cu", "gemm.cu", "chol.cu", "acqf.cu", "grad.cu", "scalar_acqf.cu", "loghvi.cu", "sobol.cu", "mll.cu", "ozaki.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-pthread", "--use_fast_math=false"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-pthread"]
 
 
 def _stale():

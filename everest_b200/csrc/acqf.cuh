@@ -72,8 +72,10 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
 size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
 int launch_mc_scalar(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
 // scalarised objective of baseline samples F[m][s][ldf] + mean: per-sample best value and / or arg-max counts per point
-int launch_baseline_best(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od, double* best_f_s,
-                         int* counts, cudaStream_t st, LaunchCounter* lc);
+// (infeasible samples, c(y) > 0, take `infeasible_value`; n_all_infeasible counts the MC samples without a feasible point)
+int launch_baseline_best(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od,
+                         double infeasible_value, double* best_f_s, int* counts, int* n_all_infeasible, cudaStream_t st,
+                         LaunchCounter* lc);
 int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
 int launch_front_to_mask(const unsigned char* front, int n, int* mask, cudaStream_t st, LaunchCounter* lc);
 int launch_hypervolume_from_cells(const double* obj, const unsigned char* front, int n, int Mo, const double* ref_dev,

@@ -126,6 +126,7 @@ struct bo_state {
   int scalar_variant = 0;      // bo_scalar_acqf
   double vparam = 0.0;         // qUCB beta / qPI tau
   bool noisy_scalar = false;   // qNEI / qLogNEI: per-sample incumbent in best_f_s
+  bool baseline_f_valid = false;   // wsF / mean_b still hold the baseline samples of the prepared noisy scalar acqf
   DevBuf best_f_s;
   int log_hvi = 0;
   int ozaki = 0;               // posterior GEMM of large batches on the INT8 tensor cores (ozaki.cu)
@@ -207,13 +208,17 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
   const int N = cfg->N, d = cfg->d;
   int rc = st->X_train.ensure((size_t)N * d * sizeof(double));
   if (rc) { bo_state_destroy(st); return rc; }
-  cudaMemcpy(st->X_train.p, cfg->X_train, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice);
+  if (!cfg->X_train || !cfg->outputs) { bo_set_error("X_train / outputs is NULL"); bo_state_destroy(st); return BO_ERR_INVALID; }
+  {
+    cudaError_t ce = cudaMemcpy(st->X_train.p, cfg->X_train, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { bo_set_error("create: copy of X_train failed: %s", cudaGetErrorString(ce)); bo_state_destroy(st); return BO_ERR_CUDA; }
+  }
   st->out.resize(cfg->M);
   for (int m = 0; m < cfg->M; ++m) {
     const bo_output_model& om = cfg->outputs[m];
     OutputH& o = st->out[m];
     memset(&o.md, 0, sizeof(ModelD));
-    if (om.n_leaves < 1 || om.n_leaves > BO_MAX_LEAVES || om.n_terms < 1 || om.n_terms > BO_MAX_TERMS) {
+    if (om.n_leaves < 1 || om.n_leaves > BO_MAX_LEAVES || om.n_terms < 1 || om.n_terms > BO_MAX_TERMS || !om.leaves || !om.terms) {
       bo_set_error("output %d: n_leaves=%d n_terms=%d out of range", m, om.n_leaves, om.n_terms);
       bo_state_destroy(st); return BO_ERR_INVALID;
     }
@@ -233,7 +238,10 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
       const bo_kernel_leaf& kl = om.leaves[l];
       LeafD& L = o.md.leaf[l];
       L.kind = kl.kind; L.nd = kl.n_dims;
-      if (kl.n_dims < 1) { bo_set_error("leaf %d: n_dims < 1", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+      if (kl.n_dims < 1 || !kl.dims) { bo_set_error("leaf %d: n_dims < 1 or dims is NULL", l); bo_state_destroy(st); return BO_ERR_INVALID; }
+      if (kl.kind == BO_LEAF_HAMMING && (!kl.cardinality || !kl.lengthscale)) {
+        bo_set_error("leaf %d: a Hamming leaf needs cardinality and lengthscale", l); bo_state_destroy(st); return BO_ERR_INVALID;
+      }
       for (int k = 0; k < kl.n_dims; ++k) {
         int width = (kl.kind == BO_LEAF_HAMMING) ? kl.cardinality[k] : 1;
         if (kl.dims[k] < 0 || kl.dims[k] + width > d) { bo_set_error("leaf %d: column out of range", l); bo_state_destroy(st); return BO_ERR_INVALID; }
@@ -290,10 +298,14 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
       L.bits = o.train_prepd.bits[l]; L.pc = o.train_prepd.pc[l];
     }
     // residual r = (y - y_mean) / y_std - mean_const, zero padded row of length ldk
+    if (!om.y) { bo_set_error("output %d: y is NULL", m); bo_state_destroy(st); return BO_ERR_INVALID; }
     std::vector<double> r(st->ldk, 0.0);
     for (int i = 0; i < N; ++i) r[i] = (om.y[i] - om.y_mean) / om.y_std - om.mean_const;
     rc = o.resid.ensure((size_t)st->ldk * 8); if (rc) { bo_state_destroy(st); return rc; }
-    cudaMemcpy(o.resid.p, r.data(), (size_t)st->ldk * 8, cudaMemcpyHostToDevice);
+    {
+      cudaError_t ce = cudaMemcpy(o.resid.p, r.data(), (size_t)st->ldk * 8, cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) { bo_set_error("create: copy of the residual failed: %s", cudaGetErrorString(ce)); bo_state_destroy(st); return BO_ERR_CUDA; }
+    }
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { bo_set_error("create: %s", cudaGetErrorString(e)); bo_state_destroy(st); return BO_ERR_CUDA; }
@@ -481,6 +493,7 @@ extern "C" int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, con
   cudaStream_t s = (cudaStream_t)stream;
   ObjD od;
   RC(fill_objd(&od, obj, n_obj, cons, n_cons, 0, st->M));
+  st->baseline_f_valid = false;   // wsF is reused below
   const int M = st->M, ldn = round_up(n, 16), ldk = st->ldk;
   RC(st->wsMean.ensure((size_t)n * M * 8));
   RC(st->wsZM.ensure((size_t)M * S * ldn * 8, true));
@@ -566,6 +579,7 @@ static int prepare_baseline(bo_state* st, const double* Xb_dev, int nb, const do
                             cudaStream_t s) {
   const int M = st->M, ldk = st->ldk, ldlb = round_up(std::max(nb, 1), 16);
   st->nb = nb; st->S = S; st->ldlb = ldlb;
+  st->baseline_f_valid = false;
   RC(st->mean_b.ensure((size_t)std::max(nb, 1) * M * 8));
   RC(st->zbT.ensure((size_t)std::max(nb, 1) * M * S * 8));
   RC(st->zbM.ensure((size_t)M * S * ldlb * 8, true));
@@ -674,8 +688,9 @@ extern "C" int bo_scalar_prepare(bo_state* st, int32_t variant, double param, in
   if (n_b > 0) {
     RC(prepare_baseline(st, Xb_dev, n_b, zb_dev, S, info, s));
     RC(st->best_f_s.ensure((size_t)S * 8));
-    RC(launch_baseline_best(st->wsF.as<double>(), st->ldlb, S, n_b, st->M, st->mean_b.as<double>(), st->od,
-                            st->best_f_s.as<double>(), nullptr, s, &st->lc));
+    RC(launch_baseline_best(st->wsF.as<double>(), st->ldlb, S, n_b, st->M, st->mean_b.as<double>(), st->od, -INFINITY,
+                            st->best_f_s.as<double>(), nullptr, nullptr, s, &st->lc));
+    st->baseline_f_valid = true;
     st->noisy_scalar = true;
   } else {
     st->nb = 0; st->S = S; st->ldlb = 16;
@@ -692,19 +707,38 @@ extern "C" int bo_scalar_prepare(bo_state* st, int32_t variant, double param, in
   return BO_OK;
 }
 
+extern "C" int bo_scalar_baseline_best(bo_state* st, double infeasible_value, int32_t* n_all_infeasible, void* stream) {
+  if (!st || st->acqf_kind != 3 || !st->noisy_scalar || !st->baseline_f_valid) {
+    bo_set_error("scalar_baseline_best: call directly after bo_scalar_prepare of a noisy variant (n_b > 0)");
+    return BO_ERR_STATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  RC(st->wsInfo.ensure(64));
+  CUDA_CHECK_RET(cudaMemsetAsync(st->wsInfo.p, 0, sizeof(int), s));
+  RC(launch_baseline_best(st->wsF.as<double>(), st->ldlb, st->S, st->nb, st->M, st->mean_b.as<double>(), st->od, infeasible_value,
+                          st->best_f_s.as<double>(), nullptr, st->wsInfo.as<int>(), s, &st->lc));
+  int cnt = 0;
+  CUDA_CHECK_RET(cudaMemcpyAsync(&cnt, st->wsInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  if (n_all_infeasible) *n_all_infeasible = cnt;
+  return BO_OK;
+}
+
 extern "C" int bo_logei_prepare(bo_state* st, int32_t S, int32_t combine, const bo_objective_op* obj, int32_t n_obj,
                                 double best_f, void* stream) {
   return bo_scalar_prepare(st, BO_ACQF_QLOGEI, 0.0, S, combine, obj, n_obj, nullptr, 0, best_f, nullptr, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S,
-                                      int32_t combine, const bo_objective_op* obj, int32_t n_obj, int32_t* counts_dev,
-                                      int32_t* info, void* stream) {
+                                      int32_t combine, const bo_objective_op* obj, int32_t n_obj,
+                                      const bo_constraint_op* cons, int32_t n_cons, int32_t* counts_dev, int32_t* info,
+                                      void* stream) {
   if (!st || !st->factorized) { bo_set_error("state not factorized"); return BO_ERR_STATE; }
   if (n < 1 || S < 1) { bo_set_error("bad n / S"); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   ObjD od;
-  RC(fill_objd(&od, obj, n_obj, nullptr, 0, combine, st->M));
+  RC(fill_objd(&od, obj, n_obj, cons, n_cons, combine, st->M));
+  st->baseline_f_valid = false;   // wsF is reused below
   const int M = st->M, ldn = round_up(n, 16), ldk = st->ldk;
   RC(st->wsMean.ensure((size_t)n * M * 8));
   RC(st->wsZM.ensure((size_t)M * S * ldn * 8, true));
@@ -725,7 +759,8 @@ extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t
   }
   if (rcode == BO_OK) {
     cudaMemsetAsync(counts_dev, 0, (size_t)n * sizeof(int), s);
-    rcode = launch_baseline_best(st->wsF.as<double>(), ldn, S, n, M, st->wsMean.as<double>(), od, nullptr, counts_dev, s, &st->lc);
+    rcode = launch_baseline_best(st->wsF.as<double>(), ldn, S, n, M, st->wsMean.as<double>(), od, -INFINITY, nullptr, counts_dev,
+                                 nullptr, s, &st->lc);
   }
   cudaStreamSynchronize(s);
   root.release(); cov.release(); pb.release();
@@ -1291,6 +1326,7 @@ extern "C" int bo_debug_get(bo_state* st, const char* name, int32_t m, double* o
   else if (nm == "cell_up") { src = st->cell_up.as<double>(); n = (int64_t)st->cap * st->od.n_obj * (st->cells_shared ? 1 : st->S); }
   else if (nm == "samples_b") { src = st->samples_b.as<double>(); n = (int64_t)st->S * st->nb * st->M; }
   else if (nm == "obj_b") { src = st->obj_b.as<double>(); n = (int64_t)st->S * st->nb * st->od.n_obj; }
+  else if (nm == "best_f_s" && st->noisy_scalar) { src = st->best_f_s.as<double>(); n = st->S; }
   else if (nm == "ozaki_check") {
     // [calibration state (0 unchecked, 1 accepted, -1 rejected), max rel. error of the posterior variance, of the mean]
     if (capacity < 3) { bo_set_error("debug_get: capacity too small"); return BO_ERR_INVALID; }

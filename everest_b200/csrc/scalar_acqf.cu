@@ -303,37 +303,51 @@ int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Baseline samples of the noisy variants: best scalarised objective per MC sample (qNEI / qLogNEI incumbent) and the
-// arg-max counts of prune_inferior_points.  One warp per MC sample, lanes over the baseline points.
+// Baseline samples of the noisy variants: best FEASIBLE scalarised objective per MC sample (qNEI / qLogNEI incumbent,
+// [UPSTREAM] compute_best_feasible_objective: samples that violate an output constraint, c(y) > 0, take `infeasible_value`
+// -- minus infinity unless some MC sample has no feasible baseline point at all, in which case the host hands in BoTorch's
+// pessimistic lower bound) and the arg-max counts of prune_inferior_points (infeasible samples count as -inf there).
+// One warp per MC sample, lanes over the baseline points.  n_all_infeasible counts the MC samples without a feasible point.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 baseline_best_kernel(const double* __restrict__ F, int ldf, int S, int n, int M, const double* __restrict__ mean, ObjD od,
-                     double* __restrict__ best_f_s, int* __restrict__ counts) {
+                     double infeasible_value, double* __restrict__ best_f_s, int* __restrict__ counts,
+                     int* __restrict__ n_all_infeasible) {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= S) return;
   double best = -INFINITY;
   int arg = 0x7fffffff;
+  int any_feasible = 0;
   for (int e = lane; e < n; e += 32) {
     double y[2 * BO_MAX_OBJECTIVES];
     for (int m = 0; m < M; ++m) y[m] = mean[(size_t)e * M + m] + F[((size_t)m * S + s) * ldf + e];
-    const double o = scalar_objective_apply(od, y, M, nullptr);
-    if (o > best) { best = o; arg = e; }
+    double o = scalar_objective_apply(od, y, M, nullptr);
+    bool ok = true;
+    for (int c = 0; c < od.n_cons; ++c) ok = ok && (od.con[c].sign * (y[od.con[c].out_idx] - od.con[c].tp) <= 0.0);
+    if (!ok) o = infeasible_value;
+    any_feasible |= ok ? 1 : 0;
+    // first arg-max like torch.argmax: a sample whose points are all -inf keeps the smallest index
+    if (o > best || (o == best && e < arg)) { best = o; arg = e; }
   }
   for (int off = 16; off > 0; off >>= 1) {
     const double ob = __shfl_xor_sync(0xffffffffu, best, off);
     const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+    any_feasible |= __shfl_xor_sync(0xffffffffu, any_feasible, off);
     if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }  // first arg-max, like torch.argmax
   }
   if (lane == 0) {
     if (best_f_s) best_f_s[s] = best;
     if (counts && arg < n) atomicAdd(counts + arg, 1);
+    if (n_all_infeasible && !any_feasible) atomicAdd(n_all_infeasible, 1);
   }
 }
 
-int launch_baseline_best(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od, double* best_f_s,
-                         int* counts, cudaStream_t st, LaunchCounter* lc) {
+int launch_baseline_best(const double* F, int ldf, int S, int n, int M, const double* mean, const ObjD& od,
+                         double infeasible_value, double* best_f_s, int* counts, int* n_all_infeasible, cudaStream_t st,
+                         LaunchCounter* lc) {
   if (S <= 0 || n <= 0) return BO_OK;
-  baseline_best_kernel<<<(S * 32 + 255) / 256, 256, 0, st>>>(F, ldf, S, n, M, mean, od, best_f_s, counts);
+  baseline_best_kernel<<<(S * 32 + 255) / 256, 256, 0, st>>>(F, ldf, S, n, M, mean, od, infeasible_value, best_f_s, counts,
+                                                             n_all_infeasible);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -23,7 +23,8 @@ def sharded_forward(acq: Callable[[torch.Tensor], torch.Tensor], X: torch.Tensor
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = X.shape[0]
     lo, hi = shard_bounds(n, rank, world)
-    vals = acq(X[lo:hi]) if hi > lo else torch.empty(0, dtype=torch.double, device=X.device)
+    out_device = getattr(getattr(acq, "model", None), "device", None) or X.device
+    vals = acq(X[lo:hi]) if hi > lo else torch.empty(0, dtype=torch.double, device=out_device)
     width = (n + world - 1) // world
     buf = torch.zeros(width, dtype=torch.double, device=vals.device)
     buf[: hi - lo] = vals
@@ -61,7 +62,8 @@ def sharded_argmax(acq: Callable[[torch.Tensor], torch.Tensor], X: torch.Tensor,
 
 def sharded_optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                           fixed_features=None, options: Optional[dict] = None, seed: int = 0, group=None,
-                          inequality_constraints=None, equality_constraints=None):
+                          inequality_constraints=None, equality_constraints=None, nonlinear_inequality_constraints=None,
+                          generator=None):
     """optimize_acqf over the GPUs of one box: every rank scores its slice of the raw samples (one
     all-gather of the values, because initialize_q_batch needs all of them), every rank refines ITS share of the
     restarts with L-BFGS-B / SLSQP without any per-iteration collective, and the only other exchange is the arg-max over
@@ -73,12 +75,17 @@ def sharded_optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restar
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return optim.optimize_acqf(acq_function, bounds, q, num_restarts, raw_samples, fixed_features=fixed_features,
                                    options=options, seed=seed, inequality_constraints=inequality_constraints,
-                                   equality_constraints=equality_constraints)
+                                   equality_constraints=equality_constraints,
+                                   nonlinear_inequality_constraints=nonlinear_inequality_constraints, generator=generator)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     bounds = torch.as_tensor(bounds, dtype=torch.double)
     dev = acq_function.model.device
+    if nonlinear_inequality_constraints and generator is None:
+        raise RuntimeError("`ic_generator` (generator) must be given if there are non-linear inequality constraints.")
     # identical raw samples on every rank (same seed), scored in slices
-    if inequality_constraints or equality_constraints:
+    if generator is not None:
+        X_rnd = optim.apply_fixed_features(torch.as_tensor(generator(raw_samples, q, seed), dtype=torch.double), fixed_features)
+    elif inequality_constraints or equality_constraints:
         X_rnd = optim.sample_q_batches_from_polytope(raw_samples, q, bounds, inequality_constraints, equality_constraints,
                                                      seed=seed, fixed_features=fixed_features)
     else:
@@ -91,12 +98,10 @@ def sharded_optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restar
     lo, hi = shard_bounds(num_restarts, rank, world)
     best_val, best_x = float("-inf"), torch.zeros(q, bounds.shape[-1], dtype=torch.double)
     if hi > lo:
-        X_ref, Y_ref, _ = optim.gen_candidates_scipy(X_ic[lo:hi], acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
-                                                     options=options, inequality_constraints=inequality_constraints,
-                                                     equality_constraints=equality_constraints)
-        better = Y_ref >= Y_ic[lo:hi]
-        Xb = torch.where(better.view(-1, 1, 1), X_ref, X_ic[lo:hi].cpu())
-        Yb = torch.where(better, Y_ref, Y_ic[lo:hi])
+        Xb, Yb = optim.refine_restarts(acq_function, X_ic[lo:hi], Y_ic[lo:hi], bounds, fixed_features=fixed_features,
+                                       options=options, inequality_constraints=inequality_constraints,
+                                       equality_constraints=equality_constraints,
+                                       nonlinear_inequality_constraints=nonlinear_inequality_constraints)
         i = int(torch.argmax(Yb))
         best_val, best_x = float(Yb[i]), Xb[i]
     pair = torch.tensor([best_val, -float(rank)], dtype=torch.double, device=dev)

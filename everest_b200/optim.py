@@ -429,6 +429,51 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     return Xf, vals, {"nit": int(res.nit), "n_acqf_evals": state["n_eval"] + r, "message": str(res.message)}
 
 
+def linear_feasibility(X: torch.Tensor, inequality_constraints, equality_constraints, rel_tol: float = 1e-6) -> np.ndarray:
+    """[r] bool: the q-batches X[r, q, d] satisfy the linear constraints up to a RELATIVE slack -- rel_tol times
+    max(1, |rhs|, ||row||_1 max|x|) per constraint row, so that e.g. a mixture constraint "sums to 100" is not held to
+    1e-8 absolute (SLSQP's own stopping tolerance is ~1e-6 on the scaled problem)."""
+    r, q, d = X.shape
+    flat = X.reshape(r, -1).numpy()
+    ok = np.ones(r, dtype=bool)
+    xmax = max(1.0, float(np.abs(flat).max())) if flat.size else 1.0
+    for cset, is_eq in ((inequality_constraints, False), (equality_constraints, True)):
+        A, b = dense_linear_constraints(cset, q, d)
+        if not A.shape[0]:
+            continue
+        tol = rel_tol * np.maximum(1.0, np.maximum(np.abs(b), np.abs(A).sum(axis=1) * xmax))
+        res = flat @ A.T - b
+        ok &= ((np.abs(res) <= tol) if is_eq else (res >= -tol)).all(axis=1)
+    return ok
+
+
+def refine_restarts(acq_function, X_ic: torch.Tensor, Y_ic: torch.Tensor, bounds: torch.Tensor, fixed_features=None,
+                    options: Optional[dict] = None, inequality_constraints=None, equality_constraints=None,
+                    nonlinear_inequality_constraints=None):
+    """The refine / filter / keep-if-better block shared by optimize_acqf and distributed.sharded_optimize_acqf:
+    gen_candidates_scipy on the restarts, refined restarts that left the feasible set are discarded (SLSQP may stop
+    slightly outside), and a restart never ends worse than its screened start (piecewise-smooth MC estimate)."""
+    import logging
+
+    q = X_ic.shape[1]
+    X_ref, Y_ref, info = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
+                                              options=options, inequality_constraints=inequality_constraints,
+                                              equality_constraints=equality_constraints,
+                                              nonlinear_inequality_constraints=nonlinear_inequality_constraints)
+    if nonlinear_inequality_constraints:
+        ok_n = nonlinear_constraints_satisfied(X_ref, nonlinear_inequality_constraints)
+        Y_ref = torch.where(ok_n, Y_ref, torch.full_like(Y_ref, -float("inf")))
+    if inequality_constraints or equality_constraints:
+        ok = torch.from_numpy(linear_feasibility(X_ref, inequality_constraints, equality_constraints))
+        if not bool(ok.any()):
+            logging.getLogger(__name__).warning("every refined restart violates the linear constraints: keeping the raw starts")
+        Y_ref = torch.where(ok, Y_ref, torch.full_like(Y_ref, -float("inf")))
+    better = Y_ref >= Y_ic
+    X_out = torch.where(better.view(-1, 1, 1), X_ref, X_ic.cpu())
+    Y_out = torch.where(better, Y_ref, Y_ic)
+    return X_out, Y_out
+
+
 def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int, raw_samples: int,
                   fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None,
                   return_best_only: bool = True, seed: Optional[int] = None, refine: bool = True, **unsupported):
@@ -448,28 +493,9 @@ def optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restarts: int,
                                                     fixed_features=fixed_features, options=options, seed=seed,
                                                     inequality_constraints=ineq, equality_constraints=eq, generator=generator)
     if refine:
-        X_ref, Y_ref, _ = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
-                                               options=options, inequality_constraints=ineq, equality_constraints=eq,
-                                               nonlinear_inequality_constraints=nlcs)
-        if nlcs:
-            # SLSQP may stop slightly outside: keep a refined restart only if it still satisfies the constraints
-            ok_n = nonlinear_constraints_satisfied(X_ref, nlcs)
-            Y_ref = torch.where(ok_n, Y_ref, torch.full_like(Y_ref, -float("inf")))
-        if ineq or eq:
-            # SLSQP may stop slightly outside the polytope: keep a refined restart only if it is feasible
-            Ai, bi = dense_linear_constraints(ineq, q, bounds.shape[-1])
-            Ae, be = dense_linear_constraints(eq, q, bounds.shape[-1])
-            flat = X_ref.reshape(X_ref.shape[0], -1).numpy()
-            ok = np.ones(flat.shape[0], dtype=bool)
-            if Ai.shape[0]:
-                ok &= (flat @ Ai.T - bi >= -1e-8).all(axis=1)
-            if Ae.shape[0]:
-                ok &= (np.abs(flat @ Ae.T - be) <= 1e-8).all(axis=1)
-            Y_ref = torch.where(torch.from_numpy(ok), Y_ref, torch.full_like(Y_ref, -float("inf")))
-        # never return something worse than the screened start (piecewise-smooth MC estimate)
-        better = Y_ref >= Y_ic
-        X_ic = torch.where(better.view(-1, 1, 1), X_ref, X_ic.cpu())
-        Y_ic = torch.where(better, Y_ref, Y_ic)
+        X_ic, Y_ic = refine_restarts(acq_function, X_ic, Y_ic, bounds, fixed_features=fixed_features, options=options,
+                                     inequality_constraints=ineq, equality_constraints=eq,
+                                     nonlinear_inequality_constraints=nlcs)
     if return_best_only:
         best = int(torch.argmax(Y_ic))
         return X_ic[best].cpu(), Y_ic[best]

@@ -20,11 +20,23 @@ def draw_sobol_normal_samples(d: int, n: int, seed: int) -> torch.Tensor:
     return torch.erfinv(2 * v - 1) * math.sqrt(2)
 
 
+MAXDIM = torch.quasirandom.SobolEngine.MAXDIM   # 21201
+
+
+def iid_normal_samples(d: int, n: int, seed: int) -> torch.Tensor:
+    """[UPSTREAM] botorch.sampling.get_sampler falls back from SobolQMCNormalSampler to IIDNormalSampler when the joint
+    sample dimension exceeds SobolEngine.MAXDIM (e.g. pruning a baseline of more than 10600 points with two outputs):
+    seeded i.i.d. N(0, 1) draws."""
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.randn(n, d, dtype=torch.double, generator=g)
+
+
 def base_samples(n_points: int, n_outputs: int, n_samples: int, seed: int) -> torch.Tensor:
     """z[S, n_points, M]; flat Sobol dimension = m * n_points + i (non-interleaved MTMVN layout)."""
     if n_points == 0:
         return torch.zeros(n_samples, 0, n_outputs, dtype=torch.double)
-    z = draw_sobol_normal_samples(n_points * n_outputs, n_samples, seed)
+    dim = n_points * n_outputs
+    z = draw_sobol_normal_samples(dim, n_samples, seed) if dim <= MAXDIM else iid_normal_samples(dim, n_samples, seed)
     return z.view(n_samples, n_outputs, n_points).transpose(1, 2).contiguous()
 
 
@@ -53,6 +65,8 @@ def base_samples_device(n_points: int, n_outputs: int, n_samples: int, seed: int
     if n_points == 0:
         return torch.zeros(n_samples, 0, n_outputs, dtype=torch.double, device=device)
     dim = n_points * n_outputs
+    if dim > MAXDIM:      # IIDNormalSampler fallback (see iid_normal_samples); same layout as the Sobol draw
+        return base_samples(n_points, n_outputs, n_samples, seed).to(device)
     ss, shift, rows = sobol_scramble_inputs(dim, seed)
     lib = L.load()
     ss_d, shift_d, rows_d = ss.to(device), shift.to(device), rows.to(device)

@@ -168,9 +168,19 @@ int bo_scalar_prepare(bo_state* st, int32_t variant, double param, int32_t S, in
                       int32_t n_b, const double* zb_dev, int32_t* info, void* stream);
 
 /* prune_inferior_points for the noisy single-objective variants: counts_dev[n] = number of joint posterior samples
- * (base samples z_dev [S, n, M]) in which point i has the best scalarised objective. */
+ * (base samples z_dev [S, n, M]) in which point i has the best scalarised objective; samples that violate an output
+ * constraint (c(y) > 0) count as -inf, as in BoTorch (SoboStrategy hands its sigmoid / target outputs over as
+ * constraints, sobo.py:120-150). */
 int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S, int32_t combine,
-                           const bo_objective_op* obj, int32_t n_obj, int32_t* counts_dev, int32_t* info, void* stream);
+                           const bo_objective_op* obj, int32_t n_obj, const bo_constraint_op* cons, int32_t n_cons,
+                           int32_t* counts_dev, int32_t* info, void* stream);
+
+/* [UPSTREAM] compute_best_feasible_objective for the noisy variants: recomputes the per-sample incumbent of the prepared
+ * qNEI / qLogNEI with `infeasible_value` in place of the objective of baseline samples that violate an output constraint
+ * (bo_scalar_prepare itself uses -inf).  *n_all_infeasible = number of MC samples without any feasible baseline point:
+ * when it is > 0 BoTorch replaces -inf by a pessimistic lower bound of the objective, which the host computes and hands
+ * in through a second call.  Must follow bo_scalar_prepare directly (it reads that call's baseline samples). */
+int bo_scalar_baseline_best(bo_state* st, double infeasible_value, int32_t* n_all_infeasible, void* stream);
 
 /* Named options of the prepared acquisition function: "ozaki" (run the posterior GEMM as an error-free INT8 digit-plane
  * product on the tcgen05 tensor cores instead of FP64 DMMA: 0 = never, 1 = automatically for large problems (default, or

@@ -366,6 +366,41 @@ def smoothed_feasibility(cons, Y):
     return w
 
 
+def feasibility_indicator(cons, Y):
+    """[UPSTREAM] compute_feasibility_indicator: hard feasibility, every c(y) <= 0."""
+    ok = torch.ones(Y.shape[:-1], dtype=torch.bool)
+    for c in constraint_values(cons, Y):
+        ok = ok & (c <= 0)
+    return ok
+
+
+def objective_lower_bound(gp, spec, X, generator=None):
+    """[UPSTREAM] botorch.acquisition.utils._estimate_objective_lower_bound: -get_infeasible_cost at 32 random convex
+    combinations of X -- the objective of (mean - 6 sd), minimum over the points, clamped at 0 from above.  The convex
+    weights come from torch's global generator in BoTorch; `generator` lets both paths share them."""
+    X = torch.as_tensor(X, dtype=DT)
+    w = torch.rand(32, X.shape[-2], dtype=DT, generator=generator)
+    w = w / w.sum(dim=0, keepdim=True)
+    Xc = w @ X
+    mean, cov = gp.posterior(Xc)
+    var = torch.diagonal(cov, dim1=-2, dim2=-1).transpose(0, 1)           # [n, M]
+    lb = scalar_objective(spec, mean - 6.0 * var.clamp_min(0.0).sqrt())
+    return float(lb.min().clamp_max(0.0))
+
+
+def best_feasible_objective(gp, spec, cons, samples, obj, X_baseline, generator=None):
+    """[UPSTREAM] compute_best_feasible_objective: max over the last dim of `obj` with infeasible entries replaced by -inf
+    when every leading index has at least one feasible point, else by the pessimistic lower bound above."""
+    if not cons:
+        return obj.amax(dim=-1)
+    feas = feasibility_indicator(cons, samples)
+    if bool(feas.any(dim=-1).all()):
+        infeasible_value = -float("inf")
+    else:
+        infeasible_value = objective_lower_bound(gp, spec, X_baseline, generator=generator)
+    return torch.where(feas, obj, torch.full_like(obj, infeasible_value)).amax(dim=-1)
+
+
 # ----------------------------------------------------------------------------------------
 # Pareto / partitioning / hypervolume ([UPSTREAM] botorch.utils.multi_objective)
 # ----------------------------------------------------------------------------------------
@@ -938,7 +973,7 @@ class QLogEHVIOracle(QEHVIOracle):
 class QScalarOracle(QNEHVIOracle):
     def __init__(self, gp, kind, objective_spec, X_observed, mc_samples=512, seed=1234, beta=0.2, tau=1e-3,
                  prune_baseline=True, prune_samples=2048, prune_seed=4321, X_pending=None, constraints=None,
-                 best_f=None):
+                 best_f=None, lb_generator=None):
         self.gp, self.kind, self.spec, self.S, self.seed = gp, kind, objective_spec, mc_samples, seed
         self.beta, self.tau, self.cons = beta, tau, constraints
         # [UPSTREAM] @concatenate_pending_points: pending points are scored jointly with X (also for qNEI / qLogNEI)
@@ -958,14 +993,18 @@ class QScalarOracle(QNEHVIOracle):
             self.baseline_L = psd_safe_cholesky(cov)
             fb = mean.unsqueeze(0) + torch.einsum("mij,sjm->sim", self.baseline_L, self.zb)
             self.samples_b = fb
-            self.best_f_s = scalar_objective(self.spec, fb).max(dim=-1).values  # [S]
+            # [UPSTREAM] qNoisyExpectedImprovement.compute_best_f -> compute_best_feasible_objective: [S]
+            self.best_f_s = best_feasible_objective(gp, self.spec, self.cons, fb, scalar_objective(self.spec, fb), self.Xb,
+                                                    generator=lb_generator)
         else:
             self.Xb, self.nb = torch.zeros(0, gp.d, dtype=DT), 0
             self.baseline_L = torch.zeros(gp.M, 0, 0, dtype=DT)
             self.zb = torch.zeros(self.S, 0, gp.M, dtype=DT)
             if best_f is None:
+                # [UPSTREAM] get_acquisition_function (qEI / qLogEI / qPI): best FEASIBLE objective of the posterior mean
                 mean, _ = gp.posterior(Xo)
-                best_f = float(scalar_objective(objective_spec, mean).max())
+                best_f = float(best_feasible_objective(gp, objective_spec, self.cons, mean, scalar_objective(objective_spec, mean),
+                                                       Xo, generator=lb_generator))
             self.best_f = best_f
 
     def prune_so(self, X, num_samples, seed):
@@ -976,6 +1015,8 @@ class QScalarOracle(QNEHVIOracle):
         L = psd_safe_cholesky(cov)
         samples = mean.unsqueeze(0) + torch.einsum("mij,sjm->sim", L, z)
         obj = scalar_objective(self.spec, samples)
+        if self.cons:   # [UPSTREAM] infeasible samples cannot be the best point
+            obj = torch.where(feasibility_indicator(self.cons, samples), obj, torch.full_like(obj, -float("inf")))
         best = obj.argmax(dim=-1)
         return torch.unique(best)
 

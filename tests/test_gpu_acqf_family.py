@@ -144,6 +144,45 @@ def test_sobo_acquisition_functions_with_output_constraint(name):
     compare(acq_d, acq_o, X, st, log_space=name.startswith("qLog"), val_tol=1e-7 if name.startswith("qLog") else 1e-8)
 
 
+@pytest.mark.parametrize("name", ["qLogEI", "qEI", "qLogNEI", "qNEI"])
+@pytest.mark.parametrize("tp", [0.5, -1.0])
+def test_constrained_incumbent_is_the_best_feasible_point(name, tp):
+    """[UPSTREAM] compute_best_feasible_objective / prune_inferior_points with output constraints (SoboStrategy hands its
+    sigmoid / target outputs over as constraints, sobo.py:120-150): the incumbent is the best FEASIBLE point -- on ZDT1 the
+    points with the best objective (smallest y1) have y0 near 1 and violate y0 <= 0.5 -- and infeasible samples cannot
+    survive the pruning.  tp = -1: no baseline point is feasible, BoTorch's pessimistic lower bound (objective of
+    mean - 6 sd at 32 random convex combinations, shared generator) becomes the incumbent."""
+    p = Cf.zdt1_qnehvi(N=60, S=32, raw=8, d=4, q=2)
+    obj = ScalarObjective([MinimizeObjective(1)], "single")
+    cons = [OutputConstraint(0, 1.0, tp, 0.1)]
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    spec = ("single", P.op_to_oracle(obj.ops[0]))
+    noisy = name in ("qLogNEI", "qNEI")
+    acq_o = O.QScalarOracle(gp, name, spec, p["X"], mc_samples=32, seed=3, prune_samples=128, prune_seed=3 + 7919,
+                            constraints=[(0, 1.0, tp, 0.1)], lb_generator=torch.Generator().manual_seed(77))
+    kw = dict(prune_samples=128) if noisy else {}
+    acq_d = A.get_acquisition_function(name, st, obj, p["X"], constraints=cons, mc_samples=32, seed=3,
+                                       lb_generator=torch.Generator().manual_seed(77), **kw)
+    unconstrained = float(obj(st.posterior(p["X"])[0].cpu()).max())
+    if noisy:
+        assert acq_d.prune_idx.cpu().tolist() == acq_o.prune_idx.tolist()
+        bfs = st.debug_get("best_f_s").cpu()
+        assert float((bfs - acq_o.best_f_s).abs().max()) < 1e-9 * max(1.0, float(acq_o.best_f_s.abs().max()))
+        assert (acq_d.n_all_infeasible > 0) == (tp < 0)
+        if tp < 0:   # every sample takes the same pessimistic value (BoTorch: objective(mean - 6 sd), clamped at 0)
+            assert float(bfs.max()) == float(bfs.min()) <= 0.0
+    else:
+        assert abs(acq_d.best_f - acq_o.best_f) < 1e-9 * max(1.0, abs(acq_o.best_f))
+        assert acq_d.best_f < unconstrained - 1e-3 if tp > 0 else acq_d.best_f <= 0.0
+    g = torch.Generator().manual_seed(1)
+    X = torch.rand(6, 2, p["d"], dtype=DT, generator=g)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device)).cpu()
+    scale = max(1.0, float(v_o.abs().max())) if name.startswith("qLog") else max(float(v_o.abs().max()), 1e-300)
+    assert float((v_d - v_o).abs().max()) < 1e-7 * scale
+
+
 def test_factory_errors_are_loud():
     p = Cf.zdt1_qnehvi(N=40, S=16, raw=4, d=4, q=1)
     st = Cf.build_state(p)

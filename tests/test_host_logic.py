@@ -488,3 +488,46 @@ def test_device_sobol_integer_pipeline_matches_torch_engine():
         assert torch.equal(mine, u)
     with pytest.raises(ValueError):
         sampling.sobol_scramble_inputs(0, 1)
+
+
+def test_base_samples_fall_back_to_iid_above_sobol_maxdim():
+    """[UPSTREAM] get_sampler: IIDNormalSampler above SobolEngine.MAXDIM (pruning > 10600 baseline points with two outputs)."""
+    n_points = sampling.MAXDIM // 2 + 5
+    z = sampling.base_samples(n_points, 2, 4, seed=3)
+    assert z.shape == (4, n_points, 2) and bool(torch.isfinite(z).all())
+    assert torch.equal(z, sampling.base_samples(n_points, 2, 4, seed=3))
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05
+    # at and below MAXDIM the Sobol pipeline is untouched
+    assert torch.equal(sampling.base_samples(3, 2, 8, seed=1), O.base_samples_points_by_outputs(3, 2, 8, 1))
+
+
+def test_linear_feasibility_uses_a_relative_tolerance():
+    """Mixture constraint sum x = 100: a residual of 1e-6 (SLSQP's stopping accuracy) is feasible, 1e-2 is not."""
+    eq = [(torch.arange(3), torch.ones(3, dtype=DT), 100.0)]
+    ineq = [(torch.tensor([0]), torch.tensor([1.0], dtype=DT), 10.0)]   # x0 >= 10
+    X = torch.tensor([[[30.0, 30.0, 40.0 + 1e-6]], [[30.0, 30.0, 40.01]], [[9.0, 41.0, 50.0]], [[10.0 - 1e-7, 40.0, 50.0]]], dtype=DT)
+    ok = optim.linear_feasibility(X, ineq, eq)
+    assert ok.tolist() == [True, False, False, True]
+
+
+def test_oracle_best_feasible_objective_and_constrained_pruning():
+    """[UPSTREAM] compute_best_feasible_objective as restated in the oracle: infeasible entries are -inf while every
+    leading index keeps a feasible point, otherwise the pessimistic lower bound replaces them."""
+    p = Cf.zdt1_qnehvi(N=30, S=8, raw=4, d=3, q=1)
+    gp = P.oracle_gp(p)
+    spec = ("single", ("min", 1, 0.0, 1.0))
+    X = torch.as_tensor(p["X"], dtype=DT)
+    mean, _ = gp.posterior(X)
+    obj = O.scalar_objective(spec, mean)
+    cons = [(0, 1.0, 0.5, 0.1)]
+    feas = mean[:, 0] <= 0.5
+    assert bool(feas.any()) and not bool(feas.all())
+    bf = O.best_feasible_objective(gp, spec, cons, mean, obj, X)
+    assert float(bf) == float(obj[feas].max()) < float(obj.max())
+    none = [(0, 1.0, -5.0, 0.1)]
+    g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    lb = O.objective_lower_bound(gp, spec, X, generator=g1)
+    assert lb <= 0.0 and float(O.best_feasible_objective(gp, spec, none, mean, obj, X, generator=g2)) == lb
+    a = O.QScalarOracle(gp, "qLogNEI", spec, X, mc_samples=8, seed=2, prune_samples=64, constraints=cons)
+    # no pruned-in point may be infeasible in every pruning sample: the survivors are feasible somewhere
+    assert len(a.prune_idx) >= 1 and bool(torch.isfinite(a.best_f_s).all())
