@@ -337,9 +337,12 @@ def run_b200(args):
         oz_ms, oz_cnt = st.last_timing("ozaki_slice")
         roofline_fp64 = None
         chk = st.debug_get("ozaki_check", capacity=16).cpu().tolist()
-        int8_check = {"state": {0: "not run (problem below the INT8 threshold)", 1: "accepted", -1: "rejected -> FP64 DMMA kernel"}[int(chk[0])],
-                      "max_rel_err_posterior_variance": chk[1], "max_rel_err_posterior_mean": chk[2], "accept_below": 1e-10,
-                      "note": "first large call after every prepare: both kernels on a 256-row probe"}
+        int8_check = {"state": {0: "not run (problem below the INT8 threshold)", 1: "INT8 path with per-row guard",
+                                -1: "guard flagged most rows -> FP64 DMMA kernel"}[int(chk[0])],
+                      "q_batches_redone_in_fp64_last_step": int(chk[1]), "q_batches_last_step": int(chk[2]),
+                      "q_batches_redone_since_prepare": int(chk[3]), "q_batches_since_prepare": int(chk[4]),
+                      "guard": f"2 sqrt(G_ii) eps + N eps^2 <= {chk[6]:g} (k** - G_ii), eps = {chk[5]:g} x 2^-56 sqrt(N) sA max sB "
+                               "(csrc/ozaki.cu); flagged q-batches are recomputed by the FP64 kernel"}
         roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu, profiles/r01_s2_ncu_gemm_dram_groups8.csv; "

@@ -5,7 +5,10 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,7 +98,10 @@ struct OutputH {
   DevBuf Kinv;  // (K + s2 I)^-1, built lazily by the first backward pass
   bool kinv_ready = false;
   DevBuf ozB, ozScaleB;  // INT8 digit planes of LinvExt + per-row scales (ozaki.cu), rebuilt when LinvExt changes
+  DevBuf ozSb2;          // [max_{n<N} scaleB[n], scaleB[N]]: what the per-row guard of the INT8 path needs
   bool oz_ready = false;
+  PrepBuf g_prep;        // prepared points of the q-batches the guard sends back through the FP64 kernel
+  PrepD g_prepd;
   int Rpad = 0;  // rows of LinvExt
   double jitter = 0.0;
   // acquisition state
@@ -131,11 +137,17 @@ struct bo_state {
   int log_hvi = 0;
   int ozaki = 0;               // posterior GEMM of large batches on the INT8 tensor cores (ozaki.cu)
   int ozaki_tile = 0;          // kernel variant of the INT8 GEMM (0 = default)
-  int oz_calib = 0;            // automatic mode: 0 = not checked yet for this prepared state, 1 = accepted, -1 = rejected
-  double oz_err_var = 0.0, oz_err_mu = 0.0;   // what the self-check measured
-  DevBuf wsOzRef;
+  int oz_calib = 0;            // automatic mode: 0 = no large call yet for this prepared state, 1 = INT8 path in use,
+                               // -1 = the guard flagged most rows of a call: FP64 kernel from then on
+  long long oz_flagged_last = 0, oz_batches_last = 0;   // q-batches the guard redid in FP64 / scored in the last forward
+  long long oz_flagged_total = 0, oz_batches_total = 0; // ... since the last prepare
+  double oz_kappa = 8.0, oz_tol = 1e-10;
+  DevBuf wsOzFlags, wsOzXg, wsOzKxG, wsOzOutG;
+  int* pin_count = nullptr;    // pinned: the guard's counter of flagged q-batches
+  cudaEvent_t oz_event = nullptr;
   double tau_relu = 1e-6, tau_max = 1e-2;
   DevBuf wsOzA;  // INT8 digit planes of K(X*,X) (all outputs)
+  DevBuf wsOzScratch;  // integer slab of the two-pass INT8 GEMM (ozaki.cu), one per handle
   DevBuf wsDF, wsDRoot, wsDMu, wsEG, wsEW, wsEmu, wsU;  // adjoint workspaces (grad.cu)
   DevBuf wsGramPart, wsObjW, zbT, zbM, cell_lo, cell_up, ncells, front_idx, ref_dev, mean_b, obj_b, samples_b, wsBL, wsFp, wsPartial;
   int max_cells = 0;
@@ -171,16 +183,18 @@ extern "C" void bo_state_destroy(bo_state* st) {
   if (!st) return;
   for (auto& o : st->out) {
     for (void* p : o.owned) cudaFree(p);
-    o.train_prep.release(); o.base_prep.release(); o.q_prep.release();
-    DevBuf* bs[] = {&o.ozB, &o.ozScaleB, &o.Kinv, &o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
+    o.train_prep.release(); o.base_prep.release(); o.q_prep.release(); o.g_prep.release();
+    DevBuf* bs[] = {&o.ozB, &o.ozScaleB, &o.ozSb2, &o.Kinv, &o.L, &o.Linv, &o.LinvT, &o.LinvExt, &o.alpha_row, &o.dinv, &o.resid, &o.tvec, &o.Lb, &o.Sbb, &o.LbInv, &o.LbInvT};
     for (DevBuf* b : bs) b->release();
   }
   DevBuf* bs[] = {&st->X_train, &st->wsKx, &st->wsV, &st->wsGqq, &st->wsW, &st->wsMuRaw, &st->wsRoot, &st->wsMu,
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA, &st->wsOzRef};
+                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA, &st->wsOzFlags, &st->wsOzXg, &st->wsOzKxG, &st->wsOzOutG, &st->wsOzScratch};
   for (DevBuf* b : bs) b->release();
+  if (st->pin_count) cudaFreeHost(st->pin_count);
+  if (st->oz_event) cudaEventDestroy(st->oz_event);
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
   for (auto& e : st->copy_events) cudaEventDestroy(e);
@@ -343,7 +357,8 @@ static int build_linv_ext(bo_state* st, OutputH& o, int nb, cudaStream_t s) {
   const int N = st->N, ldk = st->ldk;
   o.Rpad = round_up(N + 1 + nb, 128);
   o.oz_ready = false;
-  st->oz_calib = 0;   // the digit-plane product is re-checked against the FP64 kernel for every new factor
+  st->oz_calib = 0;   // a new factor: the INT8 path gets a fresh chance, its per-row guard decides again
+  st->oz_flagged_total = 0; st->oz_batches_total = 0;
   RC(o.LinvExt.ensure((size_t)o.Rpad * ldk * 8, true));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.p, o.Linv.p, (size_t)N * ldk * 8, cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK_RET(cudaMemcpyAsync(o.LinvExt.as<double>() + (size_t)N * ldk, o.alpha_row.p, (size_t)ldk * 8, cudaMemcpyDeviceToDevice, s));
@@ -779,6 +794,12 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
     if (value != 0.0 && value != 64.0 && value != 128.0 && value != 256.0) { bo_set_error("ozaki_tile must be 0, 64, 128 or 256"); return BO_ERR_INVALID; }
     st->ozaki_tile = (int)value;
     st->oz_calib = 0;
+  } else if (nm == "ozaki_guard_kappa") {
+    if (!(value > 0.0)) { bo_set_error("ozaki_guard_kappa must be > 0"); return BO_ERR_INVALID; }
+    st->oz_kappa = value;
+  } else if (nm == "ozaki_guard_tol") {
+    if (!(value > 0.0)) { bo_set_error("ozaki_guard_tol must be > 0"); return BO_ERR_INVALID; }
+    st->oz_tol = value;
   } else if (nm == "log_hvi") {
     if (st->acqf_kind != 1 && st->acqf_kind != 2) { bo_set_error("log_hvi applies to a prepared qNEHVI / qEHVI"); return BO_ERR_STATE; }
     st->log_hvi = value != 0.0;
@@ -859,9 +880,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     // N <= 16384: 7 plane pairs x N x 2^14 per S32 accumulator stays below 2^31
     const bool oz_shape = !small_rows && (q == 1 || q == 2 || q == 4 || q == 8) && st->N <= 16384;
     const bool use_ozaki = oz_shape && (st->ozaki == 2 || (st->ozaki == 1 && st->oz_calib >= 0 && (long long)rows * st->N >= (1ll << 22) && st->N >= 512));
-    // automatic mode: the first large call after a prepare runs BOTH kernels on a probe of rows and keeps the INT8 path
-    // only if the posterior variance agrees with the FP64 kernel to 1e-10 (10x inside the 1e-9 parity bar)
-    const bool oz_check = use_ozaki && st->ozaki == 1 && st->oz_calib == 0;
+    // automatic mode: every INT8 call is followed by the per-row guard (ozaki.cu); flagged q-batches are redone in FP64
+    const bool oz_guard = use_ozaki && st->ozaki == 1;
     const int oz_rows_alloc = round_up(rows, 128);
     const size_t oz_pa = use_ozaki ? ozaki_plane_bytes(oz_rows_alloc, ldk) : 0;
     std::vector<double> oz_scaleA(M, 1.0);
@@ -882,7 +902,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         oz_scaleA[m] = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
         OzPlanesOut po;
         po.planes = st->wsOzA.as<signed char>() + (size_t)m * oz_pa; po.plane_stride = (long long)(ldk / 16) * oz_rows_alloc * 16;
-        po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = (dX_dev || oz_check) ? 1 : 0;
+        po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = dX_dev ? 1 : 0;
         bool fz = false;
         RC(launch_crosscov_ex(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, &po, &fz, s, &st->lc));
         oz_fused[m] = fz ? 1 : 0;
@@ -895,6 +915,43 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
       a.ldw = ldw; a.mu_raw = st->wsMuRaw.as<double>() + (size_t)m * rows_max;
     }
+    int *oz_flags = nullptr, *oz_list = nullptr, *oz_count = nullptr;
+    int oz_cap = 0;
+    // FP64 chain over `n` q-batches of the guard's list (count_dev != NULL: fixed capacity, real count on the device):
+    // gather the q-batches, prepare them, K(X*,X) in FP64, FP64 posterior GEMM, scatter Gram / W / mean rows back
+    auto redo_flagged = [&](int n, const int* count_dev) -> int {
+      const int rg = n * q;
+      const size_t per_out = (size_t)rg * q + (size_t)rg * ldw + rg;
+      RC(st->wsOzXg.ensure((size_t)rg * st->d * 8));
+      RC(st->wsOzKxG.ensure((size_t)rg * ldk * 8 * M));
+      RC(st->wsOzOutG.ensure(per_out * 8 * M));
+      RC(launch_ozaki_gather_x(Xc, oz_list, count_dev, n, q * st->d, st->wsOzXg.as<double>(), s, &st->lc));
+      std::vector<PostGemmArgs> gg(M);
+      for (int m = 0; m < M; ++m) {
+        OutputH& o = st->out[m];
+        double* KxG = st->wsOzKxG.as<double>() + (size_t)m * rg * ldk;
+        RC(o.g_prep.ensure(o.md, rg, &o.g_prepd));
+        RC(launch_prep_points(o.md, st->wsOzXg.as<double>(), rg, st->d, o.g_prepd, s, &st->lc));
+        RC(launch_crosscov(o.md, o.g_prepd, o.train_prepd, true, st->N, KxG, ldk, false, s, &st->lc));
+        gg[m] = pg[m];
+        gg[m].Kx = KxG; gg[m].rows = rg;
+        gg[m].Gqq = st->wsOzOutG.as<double>() + (size_t)m * per_out;
+        gg[m].W = gg[m].Gqq + (size_t)rg * q;
+        gg[m].mu_raw = gg[m].W + (size_t)rg * ldw;
+      }
+      if (rg <= 64) {
+        RC(st->wsV.ensure(posterior_small_ws_doubles(rg, st->out[0].Rpad, M) * 8));
+        RC(launch_posterior_small(gg.data(), M, st->wsV.as<double>(), s, &st->lc));
+      } else {
+        size_t pw = posterior_gemm_partial_ws_doubles(rg, q, M);
+        if (pw) RC(st->wsGramPart.ensure(pw * 8));
+        RC(launch_posterior_gemm_multi(gg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+      }
+      for (int m = 0; m < M; ++m)
+        RC(launch_ozaki_scatter(oz_list, count_dev, n, q, nb, ldw, gg[m].Gqq, gg[m].W, gg[m].mu_raw, pg[m].Gqq, pg[m].W, pg[m].mu_raw,
+                                s, &st->lc));
+      return BO_OK;
+    };
     if (small_rows) {
       RC(st->wsV.ensure(posterior_small_ws_doubles(rows, st->out[0].Rpad, M) * 8));
       rec_begin(st, "posterior_gemm", s);
@@ -905,6 +962,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       const int rows_alloc = oz_rows_alloc;
       const size_t pa = oz_pa;
       RC(st->wsGramPart.ensure(ozaki_partial_ws_doubles(rows, q, M) * 8));
+      RC(st->wsOzScratch.ensure(ozaki_scratch_bytes()));
       std::vector<OzakiArgs> oa(M);
       rec_begin(st, "ozaki_slice", s);
       for (int m = 0; m < M; ++m) {
@@ -915,6 +973,8 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
           RC(launch_ozaki_row_scale(o.LinvExt.as<double>(), o.Rpad, st->N, ldk, o.ozScaleB.as<double>(), s, &st->lc));
           RC(launch_ozaki_slice(o.LinvExt.as<double>(), o.Rpad, st->N, ldk, o.ozScaleB.as<double>(), 0.0,
                                 o.ozB.as<signed char>(), o.Rpad, ldk, s, &st->lc));
+          RC(o.ozSb2.ensure(16));
+          RC(launch_ozaki_scale_max(o.ozScaleB.as<double>(), st->N, o.ozSb2.as<double>(), s, &st->lc));
           o.oz_ready = true;
         }
         const double scaleA = oz_scaleA[m];
@@ -924,47 +984,40 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         a.Aplanes = Ap; a.rows = rows; a.rows_alloc = rows_alloc; a.ldk = ldk; a.Bplanes = o.ozB.as<signed char>();
         a.scaleB = o.ozScaleB.as<double>(); a.scaleA = scaleA; a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad; a.q = q;
         a.Gqq = pg[m].Gqq; a.W = pg[m].W; a.ldw = ldw; a.mu_raw = pg[m].mu_raw;
+        a.scratch = st->wsOzScratch.as<long long>();
       }
       rec_end(st, s);
       rec_begin(st, "posterior_gemm", s);
       RC(launch_ozaki_gemm(oa.data(), M, st->wsGramPart.as<double>(), st->ozaki_tile, s, &st->lc));
       rec_end(st, s);
-      if (oz_check) {
-        const int pr = std::min(rows, (256 / q) * q);
-        const size_t per_out = (size_t)pr * q + pr + (size_t)pr * ldw;
-        RC(st->wsOzRef.ensure(((size_t)M * per_out + 2 * M) * 8));
-        double* ref = st->wsOzRef.as<double>();
-        std::vector<PostGemmArgs> pr_args(M);
-        for (int m = 0; m < M; ++m) {
-          pr_args[m] = pg[m];
-          pr_args[m].rows = pr;
-          pr_args[m].Gqq = ref + (size_t)m * per_out;
-          pr_args[m].mu_raw = pr_args[m].Gqq + (size_t)pr * q;
-          pr_args[m].W = pr_args[m].mu_raw + pr;
-        }
-        {
-          size_t pw = posterior_gemm_partial_ws_doubles(pr, q, M);
-          if (pw) RC(st->wsGramPart.ensure(pw * 8));
-        }
-        RC(launch_posterior_gemm_multi(pr_args.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
-        double* errs = ref + (size_t)M * per_out;
+      st->oz_flagged_last = 0; st->oz_batches_last = bc;
+      if (oz_guard) {
+        // ---- per-row guard: which q-batches can the digit planes not guarantee to oz_tol?  The host must not stall the
+        // launch queue waiting for the answer, so the FP64 chain is launched NOW with a fixed capacity of oz_cap q-batches
+        // (<= 64 rows: the skinny FP64 kernels) and takes the real count from device memory; the counter is read back after
+        // the rest of the chunk has been queued, and only a call that flags more q-batches than that is redone.
+        rec_begin(st, "ozaki_guard", s);
+        RC(st->wsOzFlags.ensure(((size_t)2 * bc + 4) * sizeof(int)));
+        oz_flags = st->wsOzFlags.as<int>();
+        oz_list = oz_flags + bc;
+        oz_count = oz_list + bc;
+        CUDA_CHECK_RET(cudaMemsetAsync(oz_flags, 0, ((size_t)2 * bc + 4) * sizeof(int), s));
         for (int m = 0; m < M; ++m) {
           double kmax = 0.0;
           for (int t = 0; t < st->out[m].md.n_terms; ++t) kmax += st->out[m].md.coef[t];
-          RC(launch_ozaki_compare(pg[m].Gqq, pr_args[m].Gqq, pg[m].mu_raw, pr_args[m].mu_raw, pr, q, kmax, errs + 2 * m, s, &st->lc));
+          RC(launch_ozaki_guard(pg[m].Gqq, pg[m].mu_raw, rows, q, st->N, kmax, oz_scaleA[m], st->out[m].ozSb2.as<double>(),
+                                st->oz_kappa, st->oz_tol, oz_flags, oz_list, oz_count, s, &st->lc));
         }
-        std::vector<double> herr(2 * M);
-        CUDA_CHECK_RET(cudaMemcpyAsync(herr.data(), errs, (size_t)2 * M * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK_RET(cudaStreamSynchronize(s));
-        st->oz_err_var = 0.0; st->oz_err_mu = 0.0;
-        for (int m = 0; m < M; ++m) { st->oz_err_var = std::max(st->oz_err_var, herr[2 * m]); st->oz_err_mu = std::max(st->oz_err_mu, herr[2 * m + 1]); }
-        st->oz_calib = (st->oz_err_var <= 1e-10 && st->oz_err_mu <= 1e-10) ? 1 : -1;
-        if (st->oz_calib < 0) {
-          // rejected: this call is redone with the FP64 kernel (the FP64 K(X*,X) was kept for the check)
-          size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
-          if (pw) RC(st->wsGramPart.ensure(pw * 8));
-          RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+        oz_cap = std::min(bc, 64 / q);
+        RC(redo_flagged(oz_cap, oz_count));
+        if (!st->pin_count) {
+          CUDA_CHECK_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->pin_count), 64, cudaHostAllocDefault));
+          CUDA_CHECK_RET(cudaEventCreateWithFlags(&st->oz_event, cudaEventDisableTiming));
         }
+        CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_count, oz_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK_RET(cudaEventRecord(st->oz_event, s));
+        rec_end(st, s);
+        if (st->oz_calib == 0) st->oz_calib = 1;
       }
     } else {
       size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
@@ -973,6 +1026,9 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
       rec_end(st, s);
     }
+    // everything after the posterior GEMM of the chunk: conditional roots, baseline part of the samples, MC acquisition
+    // value (or the adjoint chain).  A lambda because the INT8 guard may have to run it a second time (see below).
+    auto run_tail = [&]() -> int {
     for (int m = 0; m < M; ++m) {
       OutputH& o = st->out[m];
       CondRootArgs c;
@@ -1049,7 +1105,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         RC(launch_kernel_grad(kg, s, &st->lc));
         rec_end(st, s);
       }
-      continue;
+      return BO_OK;
     }
     rec_begin(st, "mc_acqf", s);
     if (st->acqf_kind == 3) RC(launch_mc_scalar(ma, s, &st->lc));
@@ -1060,6 +1116,34 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       RC(launch_mc_hvi(ma, st->max_cells, ow ? st->wsObjW.as<double>() : nullptr, s, &st->lc));
     }
     rec_end(st, s);
+    return BO_OK;
+    };
+    RC(run_tail());
+    if (oz_count) {
+      // the guard's counter: by now the rest of the chunk is queued behind the GEMM, so waiting for it costs no GPU time
+      CUDA_CHECK_RET(cudaEventSynchronize(st->oz_event));
+      const int n_flag = *st->pin_count;
+      st->oz_flagged_last = n_flag;
+      st->oz_flagged_total += n_flag; st->oz_batches_total += bc;
+      if (n_flag > oz_cap) {
+        rec_begin(st, "ozaki_redo", s);
+        if ((long long)n_flag * 4 > bc) {
+          // most of the call is out of the INT8 path's reach (candidates next to the training data): redo everything with
+          // the FP64 kernel and stay there until the next prepare
+          st->oz_calib = -1;
+          for (int m = 0; m < M; ++m)
+            RC(launch_crosscov(st->out[m].md, st->out[m].q_prepd, st->out[m].train_prepd, true, st->N, const_cast<double*>(pg[m].Kx),
+                               ldk, false, s, &st->lc));
+          size_t pw = posterior_gemm_partial_ws_doubles(rows, q, M);
+          if (pw) RC(st->wsGramPart.ensure(pw * 8));
+          RC(launch_posterior_gemm_multi(pg.data(), M, st->wsGramPart.as<double>(), s, &st->lc));
+        } else {
+          RC(redo_flagged(n_flag, nullptr));
+        }
+        rec_end(st, s);
+        RC(run_tail());
+      }
+    }
   }
   return BO_OK;
 }
@@ -1123,7 +1207,9 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   if (b == 0) return BO_OK;
   size_t in_bytes = (size_t)b * q * st->d * 8, out_bytes = (size_t)b * 8;
   if (st->pin_in_bytes < in_bytes) {
-    if (st->pin_in) cudaFreeHost(st->pin_in);
+    if (st->pin_count) cudaFreeHost(st->pin_count);
+  if (st->oz_event) cudaEventDestroy(st->oz_event);
+  if (st->pin_in) cudaFreeHost(st->pin_in);
     CUDA_CHECK_RET(cudaHostAlloc(&st->pin_in, in_bytes, cudaHostAllocDefault));
     st->pin_in_bytes = in_bytes;
   }
@@ -1178,30 +1264,82 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   CUDA_CHECK_RET(cudaStreamWaitEvent(st->copy_stream, st->copy_events[0], 0));
   const char* src = reinterpret_cast<const char*>(X_host);
   char* pin = reinterpret_cast<char*>(st->pin_in);
-  int b0 = 0;
-  for (int c = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
-    const int bn = chunk_b[c];
-    const size_t off = (size_t)b0 * q * row_bytes, len = (size_t)bn * q * row_bytes;
-    {
-      const size_t piece = (size_t)4 << 20;
-      const int n_thr = (int)std::min<size_t>(4, (len + piece - 1) / piece);
-      std::vector<std::thread> th;
-      const size_t per = (len + n_thr - 1) / std::max(n_thr, 1);
-      for (int t = 1; t < n_thr; ++t) {
-        const size_t o2 = off + (size_t)t * per, l2 = std::min(per, off + len - o2);
-        th.emplace_back([=]() { memcpy(pin + o2, src + o2, l2); });
-      }
-      memcpy(pin + off, src + off, std::min(per, len));
-      for (auto& t : th) t.join();
-    }
-    CUDA_CHECK_RET(cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, pin + off, len, cudaMemcpyHostToDevice, st->copy_stream));
-    CUDA_CHECK_RET(cudaEventRecord(st->copy_events[c], st->copy_stream));
-    CUDA_CHECK_RET(cudaStreamWaitEvent(s, st->copy_events[c], 0));
-    RC(bo_acqf_forward(st, st->stage_in.as<double>() + (size_t)b0 * q * st->d, bn, q, zq_dev, st->stage_out.as<double>() + b0, nullptr, s));
+  // A staging thread walks the chunks (pageable -> pinned with up to 4 helper threads, then the H2D on the copy stream) and
+  // publishes each chunk with an event; this thread launches the kernels of a chunk as soon as its event exists.  The
+  // launch thread may block inside a chunk (the per-row guard of the INT8 GEMM reads one counter back), the staging thread
+  // keeps the copy engine busy meanwhile.
+  std::vector<size_t> c_off(n_chunks), c_len(n_chunks);
+  std::vector<int> c_b0(n_chunks);
+  for (int c = 0, b0 = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
+    c_b0[c] = b0;
+    c_off[c] = (size_t)b0 * q * row_bytes;
+    c_len[c] = (size_t)chunk_b[c] * q * row_bytes;
   }
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  std::mutex mtx;
+  std::condition_variable cv;
+  int published = 0;                  // chunks whose H2D has been enqueued and whose event is recorded
+  cudaError_t stage_err = cudaSuccess;
+  auto stage_chunk = [&](int c) -> cudaError_t {
+    const size_t off = c_off[c], len = c_len[c];
+    const size_t piece = (size_t)4 << 20;
+    const int n_thr = (int)std::min<size_t>(4, (len + piece - 1) / piece);
+    std::vector<std::thread> th;
+    const size_t per = (len + n_thr - 1) / std::max(n_thr, 1);
+    for (int t = 1; t < n_thr; ++t) {
+      const size_t o2 = off + (size_t)t * per, l2 = std::min(per, off + len - o2);
+      th.emplace_back([=]() { memcpy(pin + o2, src + o2, l2); });
+    }
+    memcpy(pin + off, src + off, std::min(per, len));
+    for (auto& t : th) t.join();
+    cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, pin + off, len, cudaMemcpyHostToDevice, st->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(st->copy_events[c], st->copy_stream);
+    return e;
+  };
+  // the first chunk is staged here (nothing to overlap with yet), the others by the staging thread
+  stage_err = stage_chunk(0);
+  published = 1;
+  std::thread stager;
+  if (n_chunks > 1 && stage_err == cudaSuccess) {
+    stager = std::thread([&]() {
+      cudaSetDevice(dev_id);
+      for (int c = 1; c < n_chunks; ++c) {
+        cudaError_t e = stage_chunk(c);
+        {
+          std::lock_guard<std::mutex> lk(mtx);
+          if (e != cudaSuccess && stage_err == cudaSuccess) stage_err = e;
+          published = c + 1;
+        }
+        cv.notify_all();
+        if (e != cudaSuccess) break;
+      }
+    });
+  }
+  int rc_fwd = BO_OK;
+  static const bool trace = getenv("EVEREST_HOST_TRACE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+  for (int c = 0; c < n_chunks && rc_fwd == BO_OK; ++c) {
+    {
+      std::unique_lock<std::mutex> lk(mtx);
+      cv.wait(lk, [&]() { return published > c || stage_err != cudaSuccess; });
+      if (stage_err != cudaSuccess) break;
+    }
+    if (trace) fprintf(stderr, "[host] chunk %d (%d q-batches) published at %.3f ms\n", c, chunk_b[c], ms_since());
+    cudaError_t e = cudaStreamWaitEvent(s, st->copy_events[c], 0);
+    if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mtx); stage_err = e; break; }
+    rc_fwd = bo_acqf_forward(st, st->stage_in.as<double>() + (size_t)c_b0[c] * q * st->d, chunk_b[c], q, zq_dev,
+                             st->stage_out.as<double>() + c_b0[c], nullptr, s);
+    if (trace) fprintf(stderr, "[host] chunk %d launched, forward returned at %.3f ms\n", c, ms_since());
+  }
+  if (stager.joinable()) stager.join();
+  if (stage_err != cudaSuccess) { bo_set_error("forward_host: staging failed: %s", cudaGetErrorString(stage_err)); return BO_ERR_CUDA; }
+  RC(rc_fwd);
   CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK_RET(cudaStreamSynchronize(s));
   memcpy(out_host, st->pin_out, out_bytes);
+  if (trace) fprintf(stderr, "[host] done at %.3f ms\n", ms_since());
   return BO_OK;
 }
 
@@ -1328,14 +1466,19 @@ extern "C" int bo_debug_get(bo_state* st, const char* name, int32_t m, double* o
   else if (nm == "obj_b") { src = st->obj_b.as<double>(); n = (int64_t)st->S * st->nb * st->od.n_obj; }
   else if (nm == "best_f_s" && st->noisy_scalar) { src = st->best_f_s.as<double>(); n = st->S; }
   else if (nm == "ozaki_check") {
-    // [calibration state (0 unchecked, 1 accepted, -1 rejected), max rel. error of the posterior variance, of the mean]
-    if (capacity < 3) { bo_set_error("debug_get: capacity too small"); return BO_ERR_INVALID; }
-    double h[3] = {(double)st->oz_calib, st->oz_err_var, st->oz_err_mu};
-    CUDA_CHECK_RET(cudaMemcpyAsync(out_dev, h, 24, cudaMemcpyHostToDevice, s));
+    // [state (0 = no INT8 call yet since the last prepare, 1 = INT8 path with per-row guard, -1 = guard sent the state to FP64),
+    //  q-batches redone in FP64 by the guard in the last forward, q-batches of the last forward, the same two since the last
+    //  prepare, kappa, tol]
+    if (capacity < 7) { bo_set_error("debug_get: capacity too small"); return BO_ERR_INVALID; }
+    double h[7] = {(double)st->oz_calib, (double)st->oz_flagged_last, (double)st->oz_batches_last, (double)st->oz_flagged_total,
+                   (double)st->oz_batches_total, st->oz_kappa, st->oz_tol};
+    CUDA_CHECK_RET(cudaMemcpyAsync(out_dev, h, sizeof(h), cudaMemcpyHostToDevice, s));
     CUDA_CHECK_RET(cudaStreamSynchronize(s));
-    if (n_written) *n_written = 3;
+    if (n_written) *n_written = 7;
     return BO_OK;
   }
+  else if (nm == "Gqq") { src = st->wsGqq.as<double>(); n = std::min<int64_t>(capacity, (int64_t)st->wsGqq.bytes / 8); }
+  else if (nm == "mu_raw") { src = st->wsMuRaw.as<double>(); n = std::min<int64_t>(capacity, (int64_t)st->wsMuRaw.bytes / 8); }
   else if (nm == "ncells" || nm == "front_idx") {
     // integer buffers are returned through the same byte pipe (caller views them as int32)
     const void* isrc = (nm == "ncells") ? st->ncells.p : st->front_idx.p;

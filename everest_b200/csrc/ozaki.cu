@@ -947,6 +947,8 @@ static int oz_make_map(CUtensorMap* map, const signed char* planes, int rows_all
   return BO_OK;
 }
 
+size_t ozaki_scratch_bytes() { return (size_t)O2_SCRATCH_SLOTS * 8 * 64 * 32 * sizeof(long long); }
+
 size_t ozaki_plane_bytes(int rows_alloc, int ldk) { return (size_t)OZ_PLANES * (ldk / 16) * rows_alloc * 16; }
 
 int launch_ozaki_row_scale(const double* X, int rows, int cols, int ld, double* scale, cudaStream_t s, LaunchCounter* lc) {
@@ -987,12 +989,11 @@ static int launch_ozaki_gemm2p(const OzakiArgs* args, int n_out, double* part_ws
     CUDA_CHECK_RET(cudaFuncSetAttribute(ozaki_gemm2c_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pair));
     attr_set = true;
   }
-  // 32 MB per device (only the slabs of the resident CTAs, 148 x 128 KB, are ever touched: L2-resident); lives as long as the library
-  static long long* scratch_dev[64] = {};
-  int dev_id = 0;
-  cudaGetDevice(&dev_id);
-  long long*& scratch = scratch_dev[dev_id & 63];
-  if (!scratch) CUDA_CHECK_RET(cudaMalloc(&scratch, (size_t)O2_SCRATCH_SLOTS * 8 * 64 * 32 * sizeof(long long)));
+  // Integer scratch slab of the two-pass kernels, indexed by %smid (each such CTA allocates all 512 TMEM columns, so at most
+  // one is resident per SM; only the 148 x 128 KB of the resident CTAs are ever touched: L2-resident).  It belongs to the
+  // caller's handle (capi.cu), so that launches of different handles / streams never share a slab.
+  long long* scratch = a0.scratch;
+  if (!scratch) { bo_set_error("ozaki_gemm: the two-pass kernels need a scratch slab"); return BO_ERR_INVALID; }
   const int row_tiles = (a0.rows + OZ_BM - 1) / OZ_BM;
   const int n_tiles = a0.Rpad / O2_BN;
   int groups;
@@ -1126,34 +1127,117 @@ int launch_ozaki_gemm(const OzakiArgs* args, int n_out, double* part_ws, int til
 }
 
 // ------------------------------------------------------------------------------------------------
-// self-check of the digit-plane product: relative error of the (standardised) posterior variance k** - G_ii on a probe
-// of rows, against the FP64 kernel's Gram.  One block; out[0] = max_i |G_oz - G_ref| / (kmax - G_ref), out[1] = max_i
-// |mu_oz - mu_ref| / (1 + |mu_ref|).
+// Per-row guard of the digit-plane product (automatic mode).  The fixed-point planes are accurate relative to the ROW
+// SCALES, not to the entries, so the absolute error of one element of V = K(X*,X) LinvExt^T is
+//     dV ~ 2^-56.2 sqrt(K) sA sB[n]      (6 dropped pairs of level p + p' = 5 with digit products of RMS 2^12.4, K terms of
+//                                          random sign, plus the 2^-56 rounding of the operands to the fixed-point grid)
+// whatever the size of V itself.  What the parity bar is stated on is the posterior variance k** - G_ii, G_ii = sum_n V_in^2:
+//     |dG_ii| <~ 2 sqrt(G_ii) eps,   eps = kappa 2^-56 sqrt(N) sA max_n sB[n]   (kappa = 8: eight standard deviations),
+// and the posterior mean (column N, its own row scale).  A q-batch whose rows do not satisfy
+//     2 sqrt(G_ii) eps + N eps^2 <= tol (k** - G_ii)   and   eps_mu <= tol (1 + |mu|)          (tol = 1e-10)
+// -- candidates next to training points, where the variance is many orders below the prior -- is flagged; the host redoes
+// exactly those q-batches with the FP64 DMMA kernel (capi.cu).  Measured error / this estimate: profiles/r02_guard_calibration.txt.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-oz_compare_kernel(const double* __restrict__ Goz, const double* __restrict__ Gref, const double* __restrict__ mu_oz,
-                  const double* __restrict__ mu_ref, int rows, int q, double kmax, double* __restrict__ out) {
-  __shared__ double red[2][256];
-  double e0 = 0.0, e1 = 0.0;
-  for (int r = threadIdx.x; r < rows; r += 256) {
-    const size_t di = (size_t)r * q + (r % q);
-    const double gr = Gref[di];
-    const double a = fabs(Goz[di] - gr) / fmax(kmax - gr, 1e-300);
-    const double b = fabs(mu_oz[r] - mu_ref[r]) / (1.0 + fabs(mu_ref[r]));
-    e0 = fmax(e0, isfinite(a) ? a : 1e300);
-    e1 = fmax(e1, isfinite(b) ? b : 1e300);
-  }
-  red[0][threadIdx.x] = e0; red[1][threadIdx.x] = e1;
+oz_scale_max_kernel(const double* __restrict__ scaleB, int N, double* __restrict__ out2) {
+  // out2[0] = max_{n < N} scaleB[n], out2[1] = scaleB[N] (the mean-cache row)
+  __shared__ double red[256];
+  double mx = 0.0;
+  for (int n = threadIdx.x; n < N; n += 256) mx = fmax(mx, scaleB[n]);
+  red[threadIdx.x] = mx;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < 256; ++i) { e0 = fmax(e0, red[0][i]); e1 = fmax(e1, red[1][i]); }
-    out[0] = e0; out[1] = e1;
+    for (int i = 1; i < 256; ++i) mx = fmax(mx, red[i]);
+    out2[0] = mx;
+    out2[1] = scaleB[N];
   }
 }
 
-int launch_ozaki_compare(const double* Goz, const double* Gref, const double* mu_oz, const double* mu_ref, int rows, int q,
-                         double kmax, double* out2, cudaStream_t s, LaunchCounter* lc) {
-  oz_compare_kernel<<<1, 256, 0, s>>>(Goz, Gref, mu_oz, mu_ref, rows, q, kmax, out2);
+__global__ void __launch_bounds__(256)
+oz_guard_kernel(const double* __restrict__ Gqq, const double* __restrict__ mu_raw, int rows, int q, int N, double kmax,
+                double scaleA, const double* __restrict__ sb2, double kappa, double tol, int* __restrict__ flags,
+                int* __restrict__ list, int* __restrict__ count) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int batch = r / q, j = r - batch * q;
+  const double c0 = kappa * 1.3877787807814457e-17 /* 2^-56 */ * sqrt((double)N) * scaleA;
+  const double eps = c0 * sb2[0], eps_mu = c0 * sb2[1];
+  const double g = Gqq[((size_t)batch * q + j) * q + j];
+  const double var = kmax - g;
+  const double err = 2.0 * sqrt(fmax(g, 0.0)) * eps + (double)N * eps * eps;
+  const bool ok = (err <= tol * var) && (eps_mu <= tol * (1.0 + fabs(mu_raw[r])));   // NaN / non-positive variance -> flagged
+  if (!ok && atomicExch(flags + batch, 1) == 0) list[atomicAdd(count, 1)] = batch;
+}
+
+// q-batches `list[0..n)` of X [b, q, d] -> Xg [n, q, d].  With `count` (device) only the first *count entries of the list
+// are real: the other slots are filled with a valid q-batch (the first flagged one, or q-batch 0) so that the FP64 chain
+// can be launched with a fixed capacity before the host knows the count.
+__global__ void __launch_bounds__(256)
+oz_gather_x_kernel(const double* __restrict__ X, const int* __restrict__ list, const int* __restrict__ count, int n, int qd,
+                   double* __restrict__ Xg) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * qd) return;
+  const int t = (int)(idx / qd), e = (int)(idx - (long long)t * qd);
+  int src = list[t];
+  if (count) { const int c = *count; src = (t < c) ? list[t] : (c > 0 ? list[0] : 0); }
+  Xg[idx] = X[(size_t)src * qd + e];
+}
+
+// redone Gram / W / mean rows of the flagged q-batches back into the full arrays
+__global__ void __launch_bounds__(256)
+oz_scatter_kernel(const int* __restrict__ list, const int* __restrict__ count, int n, int q, int n_w, int ldw,
+                  const double* __restrict__ Gg, const double* __restrict__ Wg, const double* __restrict__ mug,
+                  double* __restrict__ Gqq, double* __restrict__ W, double* __restrict__ mu_raw) {
+  const int per = q * q + q * n_w + q;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * per) return;
+  const int t = (int)(idx / per);
+  if (count && t >= *count) return;
+  int e = (int)(idx - (long long)t * per);
+  const size_t src_b = (size_t)t, dst_b = (size_t)list[t];
+  if (e < q * q) { Gqq[dst_b * q * q + e] = Gg[src_b * q * q + e]; return; }
+  e -= q * q;
+  if (e < q * n_w) {
+    const int j = e / n_w, c = e - j * n_w;
+    W[(dst_b * q + j) * ldw + c] = Wg[(src_b * q + j) * ldw + c];
+    return;
+  }
+  e -= q * n_w;
+  mu_raw[dst_b * q + e] = mug[src_b * q + e];
+}
+
+int launch_ozaki_scale_max(const double* scaleB, int N, double* out2, cudaStream_t s, LaunchCounter* lc) {
+  oz_scale_max_kernel<<<1, 256, 0, s>>>(scaleB, N, out2);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+int launch_ozaki_guard(const double* Gqq, const double* mu_raw, int rows, int q, int N, double kmax, double scaleA,
+                       const double* sb2, double kappa, double tol, int* flags, int* list, int* count, cudaStream_t s,
+                       LaunchCounter* lc) {
+  if (rows <= 0) return BO_OK;
+  oz_guard_kernel<<<(rows + 255) / 256, 256, 0, s>>>(Gqq, mu_raw, rows, q, N, kmax, scaleA, sb2, kappa, tol, flags, list, count);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+int launch_ozaki_gather_x(const double* X, const int* list, const int* count_dev, int n, int qd, double* Xg, cudaStream_t s,
+                          LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  const long long tot = (long long)n * qd;
+  oz_gather_x_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(X, list, count_dev, n, qd, Xg);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+int launch_ozaki_scatter(const int* list, const int* count_dev, int n, int q, int n_w, int ldw, const double* Gg, const double* Wg,
+                         const double* mug, double* Gqq, double* W, double* mu_raw, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  const long long tot = (long long)n * (q * q + q * n_w + q);
+  oz_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(list, count_dev, n, q, n_w, ldw, Gg, Wg, mug, Gqq, W, mu_raw);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

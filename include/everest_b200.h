@@ -184,11 +184,14 @@ int bo_scalar_baseline_best(bo_state* st, double infeasible_value, int32_t* n_al
 
 /* Named options of the prepared acquisition function: "ozaki" (run the posterior GEMM as an error-free INT8 digit-plane
  * product on the tcgen05 tensor cores instead of FP64 DMMA: 0 = never, 1 = automatically for large problems (default, or
- * EVEREST_OZAKI), 2 = whenever the shape allows; in mode 1 the first large call after every prepare checks the INT8
- * result against the FP64 kernel on a probe and falls back to FP64 unless the posterior variance agrees to 1e-10),
- * "ozaki_tile" (kernel variant of that product: 0 = default, 64 = one-pass 128x64 tiles, 128 = two-pass 128x128 tiles,
- * 256 = two-pass on CTA pairs), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of qEHVI / qNEHVI -- MoboStrategy's
- * default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2).  An empty t-batch (b = 0) is a no-op. */
+ * EVEREST_OZAKI), 2 = whenever the shape allows, unguarded (tests); in mode 1 every INT8 call is followed by a per-row guard
+ * -- digit-plane error estimate 2 sqrt(G_ii) eps against tol x the posterior variance of the row -- and the q-batches it
+ * flags are recomputed by the FP64 kernel; a call that flags more than a quarter of its q-batches sends the state to the
+ * FP64 kernel until the next prepare), "ozaki_guard_tol" (default 1e-10), "ozaki_guard_kappa" (standard deviations of the
+ * error estimate, default 8), "ozaki_tile" (kernel variant of that product: 0 = default, 64 = one-pass 128x64 tiles,
+ * 128 = two-pass 128x128 tiles, 256 = two-pass on CTA pairs), "log_hvi" (0 / 1: qLogEHVI / qLogNEHVI value instead of
+ * qEHVI / qNEHVI -- MoboStrategy's default, mobo.py:72-90), "tau_relu" (default 1e-6), "tau_max" (default 1e-2).  An empty
+ * t-batch (b = 0) is a no-op. */
 int bo_acqf_set_option(bo_state* st, const char* name, double value);
 
 /* AcquisitionFunction.forward(X[b, q, d]) -> [b]  (called from calc_acquisition botorch.py:223,

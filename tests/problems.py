@@ -59,3 +59,29 @@ def oracle_acqf(problem, gp, prune_baseline=True, prune_samples=2048, constraint
             spec = (obj.combine, [(op_to_oracle(o), o.w) for o in obj.ops])
         return O.QLogEIOracle(gp, spec, problem["X"], mc_samples=problem["S"], seed=problem["sampler_seed"])
     raise ValueError(problem["acqf"])
+
+
+def device_cells_for_oracle(acq_d, ref_point):
+    """(lower, upper) [S, C, m] of the DEVICE's per-sample box decompositions, padded to rectangular with empty cells at
+    the reference point -- what QNEHVIOracle(cell_bounds=...) takes.  The oracle's own pure-Python Lacour decomposition of
+    512 fronts with thousands of cells takes minutes; the parity tests pin the device cell lists bit for bit against it at
+    small sizes (tests/test_gpu_parity.py::test_box_decomposition_bit_exact), the full-size tests and bench.py's
+    cpu_baseline leg inject them."""
+    lo, up, nc = acq_d.cell_bounds()
+    C = int(nc.max())
+    ref = torch.tensor(ref_point, dtype=DT)
+    lo, up = lo[:, :C].clone(), up[:, :C].clone()
+    pad = torch.arange(C).unsqueeze(0) >= nc.unsqueeze(1)
+    lo[pad] = ref
+    up[pad] = ref
+    return lo, up
+
+
+def oracle_qnehvi_on_device_baseline(problem, gp, acq_d, inject_cells=False):
+    """QNEHVIOracle on the baseline the device pruned to (same points, no second pruning pass), optionally with the
+    device's cell lists."""
+    idx = acq_d.prune_idx.cpu()
+    cells = device_cells_for_oracle(acq_d, problem["ref_point"]) if inject_cells else None
+    return O.QNEHVIOracle(gp, problem["ref_point"], torch.as_tensor(problem["X"])[idx],
+                          [op_to_oracle(o) for o in problem["objective"].ops], mc_samples=problem["S"],
+                          seed=problem["sampler_seed"], prune_baseline=False, cell_bounds=cells)

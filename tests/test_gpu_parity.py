@@ -556,26 +556,26 @@ def test_int8_digit_plane_gemm_matches_fp64_and_oracle(N, q, raw, d):
         acq_d.set_option("ozaki_tile", 32)
 
 
-def test_int8_self_check_and_empty_batch():
-    """Automatic mode: the first large call after a prepare runs the INT8 and the FP64 kernel on a probe of rows and keeps
-    the INT8 path only if the posterior variance agrees to 1e-10; either way the values match the FP64 kernel's.  An
-    empty t-batch returns an empty tensor."""
-    p = Cf.zdt1_qnehvi(N=1000, S=16, raw=1200, d=8, q=4)
+def test_int8_per_row_guard_and_empty_batch():
+    """Automatic mode: every INT8 call is followed by the per-row guard (csrc/ozaki.cu: digit-plane error estimate
+    2 sqrt(G_ii) eps against 1e-10 x the posterior variance of the row); q-batches it flags are redone with the FP64 kernel,
+    the rest keep the INT8 result.  Random candidates in 30 dimensions (posterior variance within two orders of the
+    prior): almost nothing is flagged and the values match the FP64 kernel's.  An empty t-batch returns an empty tensor."""
+    p = Cf.zdt1_qnehvi(N=1000, S=16, raw=1200, d=30, q=4)
     st = Cf.build_state(p)
     acq = Cf.build_acqf(p, st, prune_samples=64)
     Xd = Cf.candidates(p).to(st.device)
     assert Xd.shape[0] * 4 * 1000 >= 1 << 22
     acq.set_option("ozaki", 0)
     v64 = acq(Xd).clone()
-    assert st.debug_get("ozaki_check", capacity=16)[0] == 0        # nothing checked yet
+    assert st.debug_get("ozaki_check", capacity=16)[0] == 0        # no INT8 call yet
     acq.set_option("ozaki", 1)
     v_auto = acq(Xd)
-    state, err_var, err_mu = st.debug_get("ozaki_check", capacity=16).tolist()
-    assert state in (1.0, -1.0)
-    assert (state == 1.0) == (err_var <= 1e-10 and err_mu <= 1e-10)
+    state, flagged, batches, flagged_tot, batches_tot, kappa, tol = st.debug_get("ozaki_check", capacity=16).tolist()
+    assert state == 1.0 and batches == Xd.shape[0] and flagged <= 0.01 * batches and kappa == 8.0 and tol == 1e-10
     assert float((v_auto - v64).abs().max()) <= 1e-10 * float(v64.abs().max())
-    assert torch.equal(acq(Xd), v_auto) or state == -1.0
-    # a small call stays on the FP64 kernels and does not disturb the decision
+    assert torch.equal(acq(Xd), v_auto)
+    # a small call stays on the FP64 kernels and does not disturb the state
     v_small = acq(Xd[:16])
     assert float((v_small - v64[:16]).abs().max()) <= 1e-10 * float(v64.abs().max())
     assert st.debug_get("ozaki_check", capacity=16)[0] == state
@@ -583,4 +583,78 @@ def test_int8_self_check_and_empty_batch():
     empty = acq(Xd[:0])
     assert empty.shape == (0,)
     v0, g0 = acq.forward_backward(Xd[:0])
-    assert v0.shape == (0,) and g0.shape == (0, 4, 8)
+    assert v0.shape == (0,) and g0.shape == (0, 4, 30)
+    # dense data in few dimensions: the posterior variance of every candidate is ~1e-3 of the prior, the digit planes
+    # cannot hold 1e-10 of that (measured 4e-10, profiles/r02_guard_calibration.txt) -> the guard sends the state to FP64
+    p8 = Cf.zdt1_qnehvi(N=1000, S=16, raw=1200, d=8, q=4)
+    st8 = Cf.build_state(p8)
+    acq8 = Cf.build_acqf(p8, st8, prune_samples=64)
+    X8 = Cf.candidates(p8).to(st8.device)
+    acq8.set_option("ozaki", 0)
+    v8 = acq8(X8).clone()
+    acq8.set_option("ozaki", 1)
+    v8a = acq8(X8)
+    assert st8.debug_get("ozaki_check", capacity=16)[0] == -1.0
+    assert float((v8a - v8).abs().max()) <= 1e-12 * float(v8.abs().max())
+    assert torch.equal(acq8(X8), v8a)
+
+
+def test_int8_guard_redoes_candidates_planted_next_to_training_points():
+    """The failure mode of fixed-point digit planes: the absolute error of V is set by the row SCALES, so a candidate
+    1e-6 away from a training point -- posterior variance four orders below the prior -- loses relative accuracy.  Such
+    q-batches are planted AFTER row 256 (where the round-1 probe never looked) and in a later chunk; the guard must flag
+    exactly q-batches that contain them, redo those in FP64, and the posterior variance of every row must then agree with the
+    all-FP64 call to 1e-10 relative (the 1e-9 bar of the north star with a 10x margin)."""
+    p = Cf.zdt1_qnehvi(N=1000, S=16, raw=1200, d=30, q=4)
+    st = Cf.build_state(p)
+    acq = Cf.build_acqf(p, st, prune_samples=64)
+    X = Cf.candidates(p).clone()
+    Xt = torch.as_tensor(p["X"], dtype=DT)
+    planted = [300, 301, 777, 1199]
+    g = torch.Generator().manual_seed(5)
+    for k, bi in enumerate(planted):
+        idx = torch.randint(0, Xt.shape[0], (4,), generator=g)
+        pts = Xt[idx] + 1e-6 * torch.randn(4, p["d"], dtype=DT, generator=g)
+        if k % 2 == 0:
+            X[bi] = pts.clamp(0.0, 1.0)            # the whole q-batch sits on training points
+        else:
+            X[bi, 2] = pts[2].clamp(0.0, 1.0)      # one point of the q-batch only
+    Xd = X.to(st.device)
+    q, b, M = 4, X.shape[0], st.M
+    kmax = 1.0                                      # RBF without outputscale: prior variance 1 in standardised space
+
+    def gram_and_mean():
+        G = st.debug_get("Gqq", capacity=b * q * q * M).view(M, b, q, q).clone()
+        mu = st.debug_get("mu_raw", capacity=b * q * M).view(M, b * q).clone()
+        return G, mu
+
+    acq.set_option("ozaki", 0)
+    v64 = acq(Xd).clone()
+    G64, mu64 = gram_and_mean()
+    var64 = kmax - torch.diagonal(G64, dim1=-2, dim2=-1)               # [M, b, q]
+    assert float(var64[:, planted].min()) < 1e-2 * float(var64.median())   # the planted rows really are low-variance rows
+    acq.set_option("ozaki", 2)                      # forced INT8, no guard: what the guard protects against
+    acq(Xd)
+    G8, _ = gram_and_mean()
+    err8 = ((torch.diagonal(G8, dim1=-2, dim2=-1) - torch.diagonal(G64, dim1=-2, dim2=-1)).abs() / var64)
+    acq.set_option("ozaki", 1)
+    v_auto = acq(Xd)
+    Ga, mua = gram_and_mean()
+    state, flagged, batches, *_ = st.debug_get("ozaki_check", capacity=16).tolist()
+    assert state == 1.0 and batches == b
+    assert len(planted) <= flagged <= len(planted) + 0.01 * b
+    erra = ((torch.diagonal(Ga, dim1=-2, dim2=-1) - torch.diagonal(G64, dim1=-2, dim2=-1)).abs() / var64)
+    assert float(erra.max()) <= 1e-10, (float(erra.max()), float(err8.max()))
+    assert float(((mua - mu64).abs() / (1.0 + mu64.abs())).max()) <= 1e-10
+    # the redone q-batches carry FP64-kernel numbers (a different summation order than the all-FP64 call: the rounding of
+    # G ~ 1, 1e-16 sqrt(N), relative to a variance of 1e-4), the forced INT8 path is far off on exactly those rows
+    assert float(erra[:, planted].max()) <= 1e-10 < float(err8[:, planted].max())
+    ok = torch.isfinite(v64)
+    assert bool(ok[[i for i in range(b) if i not in planted]].all())
+    assert float((v_auto - v64)[ok].abs().max()) <= 1e-9 * float(v64[ok].abs().max())
+    print(f"forced INT8 max rel. variance error {float(err8.max()):.2e} (planted rows {float(err8[:, planted].max()):.2e}), "
+          f"guarded {float(erra.max()):.2e}, flagged q-batches {int(flagged)}")
+    # a call that is mostly next to the data sends the state to the FP64 kernel for good
+    Xnear = (Xt[torch.randint(0, Xt.shape[0], (b * q,), generator=g)] + 1e-6 * torch.randn(b * q, p["d"], dtype=DT, generator=g))
+    acq(Xnear.clamp(0.0, 1.0).view(b, q, -1).to(st.device))
+    assert st.debug_get("ozaki_check", capacity=16)[0] == -1.0
