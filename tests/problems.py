@@ -85,3 +85,28 @@ def oracle_qnehvi_on_device_baseline(problem, gp, acq_d, inject_cells=False):
     return O.QNEHVIOracle(gp, problem["ref_point"], torch.as_tensor(problem["X"])[idx],
                           [op_to_oracle(o) for o in problem["objective"].ops], mc_samples=problem["S"],
                           seed=problem["sampler_seed"], prune_baseline=False, cell_bounds=cells)
+
+
+class OracleAcqfAdapter:
+    """The CPU oracle behind the interface everest_b200.optim drives (forward, forward_backward through torch autograd,
+    model.device): lets the parity tests run the SAME gen_candidates_scipy / optimize_acqf code on the oracle -- what
+    BoTorch does when it back-propagates through its own acquisition function."""
+
+    class _Model:
+        device = torch.device("cpu")
+
+    def __init__(self, acq_o, d):
+        self.acq_o = acq_o
+        self.model = self._Model()
+        self.model.d = d
+        self.X_pending = None
+
+    def __call__(self, X):
+        with torch.no_grad():
+            return self.acq_o.forward(torch.as_tensor(X, dtype=DT).cpu())
+
+    def forward_backward(self, X):
+        Xr = torch.as_tensor(X, dtype=DT).cpu().detach().clone().requires_grad_(True)
+        v = self.acq_o.forward(Xr)
+        (g,) = torch.autograd.grad(v.sum(), Xr)
+        return v.detach(), g
