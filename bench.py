@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Headline benchmark: acquisition evaluations per second on BASELINE.json config 3
-(ZDT1 30-D, 2 objectives, qNEHVI, N=2000, q=4, 512 MC samples, 16384 raw-sample q-batches).
+(ZDT1 30-D, 2 objectives, qNEHVI, N=2000, q=4, 512 MC samples, 16384 raw-sample q-batches), and ask() latency.
 
     python bench.py --gpus 1 --steps K --warmup W          # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W  # CPU float64 port of the reference path (oracle/)
-    torchrun ... bench.py --gpus N ...                     # one rank per GPU, weak scaling over q-batches
+    torchrun ... bench.py --gpus N ...                     # one rank per GPU: weak scaling (16384 q-batches per GPU) is the
+                                                           # headline line, strong scaling (16384 in total) rides along
 
-One "step" = one raw-sample screen: AcquisitionFunction.forward over `raw_samples` q-batches resident in
-HBM (`value`) or handed over as HOST buffers through bo_acqf_forward_host (`e2e`).  1 eval = one q-batch
-scored with all S MC samples.  Prints ONE JSON line (rank 0).
+One "step" = one raw-sample screen: AcquisitionFunction.forward over `raw_samples` q-batches resident in HBM (`value`) or
+handed over as HOST buffers through bo_acqf_forward_host (`e2e`).  1 eval = one q-batch scored with all S MC samples.
+Prints ONE JSON line (rank 0).  Keys the driver keeps are flat scalars inside `config`, `roofline`, `cpu_baseline`, `e2e`;
+the nested objects (`ask_latency`, `setup_s`, `roofline.step_time_share`, ...) repeat the detail for a reader of the line.
 """
 import argparse
 import json
@@ -28,6 +30,7 @@ import torch  # noqa: E402
 
 METRIC = "acqf_evals_per_sec"
 UNIT = "evals/s"
+ASK_MAXITER = 200
 
 
 def parse_args():
@@ -40,6 +43,9 @@ def parse_args():
     ap.add_argument("--raw-samples", type=int, default=None, help="override the q-batches per step (per GPU)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="q-batches per CPU baseline measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ask", action="store_true", help="skip the ask() latency measurement")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which of the two multi-GPU measurements becomes `value` (the other one is reported beside it)")
     return ap.parse_args()
 
 
@@ -60,38 +66,31 @@ def make_problem(args):
     return Cf.mixed_tanimoto_qlogei(**kw)
 
 
-def workload_config(p, n_gpus, extra=None):
-    cfg = {
+def workload_config(p, n_gpus):
+    """The SAME keys and values in both arms (the driver compares them): only what defines the workload."""
+    return {
         "workload": p["name"], "N_train": int(p["X"].shape[0]), "d": int(p["d"]), "outputs": len(p["outputs"]),
         "q": int(p["q"]), "mc_samples": int(p["S"]), "raw_samples_per_gpu": int(p["raw_samples"]),
         "global_q_batches_per_step": int(p["raw_samples"]) * n_gpus, "acqf": p["acqf"],
         "parallelism": f"q-batches sharded over {n_gpus} GPU(s), model state replicated",
         "eval_definition": "1 eval = one q-batch scored with all MC samples",
+        "l2": "per-step working set (digit planes / K(X*,X) of the q-batches, >= 1 GB) >> 126 MB L2; no flush needed",
     }
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 # ----------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the BoTorch op sequence, all host threads)
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_setup(p, baseline_idx=None, cell_bounds=None):
+def cpu_reference_setup(p, acq_d=None):
+    """Oracle acquisition function.  With the device acquisition function at hand its pruned baseline (and, for more
+    than two objectives, its cell lists) are reused: same points, minutes of pure-Python set-up saved."""
     from tests import problems as P
-    from oracle import bo_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
     gp = P.oracle_gp(p)
-    if p["acqf"] == "qnehvi":
-        if baseline_idx is None:
-            acq = P.oracle_acqf(p, gp, prune_baseline=True)
-        else:  # reuse the pruned baseline found by the device path (same points; saves CPU set-up time)
-            acq = O.QNEHVIOracle(gp, p["ref_point"], torch.as_tensor(p["X"])[baseline_idx],
-                                 [P.op_to_oracle(o) for o in p["objective"].ops], mc_samples=p["S"],
-                                 seed=p["sampler_seed"], prune_baseline=False, cell_bounds=cell_bounds)
-    else:
-        acq = P.oracle_acqf(p, gp)
-    return acq
+    if p["acqf"] == "qnehvi" and acq_d is not None and getattr(acq_d, "prune_idx", None) is not None:
+        return P.oracle_qnehvi_on_device_baseline(p, gp, acq_d, inject_cells=len(p["ref_point"]) > 2)
+    return P.oracle_acqf(p, gp)
 
 
 def cpu_time_forward(acq, X, chunk):
@@ -104,6 +103,32 @@ def cpu_time_forward(acq, X, chunk):
             acq.forward(X[i:i + chunk])
     dt = time.perf_counter() - t0
     return X.shape[0] / dt, dt
+
+
+def cpu_ask_latency(p, acq_o, screen_sample=512, maxiter=ASK_MAXITER):
+    """ask() on the CPU port: acqf build is timed by the caller; the raw-sample screen is timed on `screen_sample`
+    q-batches in chunks of 8 (as BoFire drives BoTorch) and extrapolated to raw_samples; the refinement is the SAME
+    gen_candidates_scipy code as the GPU arm, with the gradient from torch autograd through the oracle (what BoTorch does)."""
+    from everest_b200 import configs as Cf
+    from everest_b200 import optim
+    from tests import problems as P
+
+    if p.get("bounds") is None:
+        return None
+    bounds = torch.as_tensor(p["bounds"])
+    X = Cf.candidates(p, max(screen_sample, 8))[:screen_sample]
+    t0 = time.perf_counter()
+    vals = torch.cat([acq_o.forward(X[i:i + 8]) for i in range(0, X.shape[0], 8)])
+    t_sample = time.perf_counter() - t0
+    screen_s = t_sample * p["raw_samples"] / screen_sample
+    X_ic, _ = optim.initialize_q_batch(X, vals, n=p["num_restarts"])
+    adapter = P.OracleAcqfAdapter(acq_o, p["d"])
+    t0 = time.perf_counter()
+    _, Yref, info = optim.gen_candidates_scipy(X_ic, adapter, bounds[0], bounds[1], options={"maxiter": maxiter})
+    refine_s = time.perf_counter() - t0
+    return {"screen_s": screen_s, "screen_s_note": f"{screen_sample} q-batches timed ({t_sample:.2f} s), scaled to {p['raw_samples']}",
+            "refine_s": refine_s, "refine_maxiter": maxiter, "refine_iterations": info["nit"],
+            "refine_acqf_evals": info["n_acqf_evals"], "best_refined": float(Yref.max())}
 
 
 def run_reference(args):
@@ -127,17 +152,27 @@ def run_reference(args):
     total = sum(times)
     value = n * args.steps / total
     cores = torch.get_num_threads()
+    ask = None
+    if not args.no_ask and len(p.get("ref_point", [0, 0])) <= 2:
+        try:
+            ask = cpu_ask_latency(p, acq)
+            if ask is not None:
+                ask["acqf_build_s"] = t_setup
+                ask["total_s"] = t_setup + ask["screen_s"] + ask["refine_s"]
+        except Exception as exc:  # the latency leg must not take the throughput number down with it
+            ask = {"failed": repr(exc)}
     sample = (f"{n} of {p['raw_samples']} q-batches per step, scored in chunks of 8 (BoFire batch_limit=num_restarts, "
               f"botorch.py:108-128) with the per-call recompute of the n_b={getattr(acq, 'nb', 0)} baseline rows; "
               f"set-up {t_setup:.1f} s not timed")
+    e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if ask and "total_s" in ask:
+        e2e.update(ask_total_s=ask["total_s"], ask_build_s=ask["acqf_build_s"], ask_screen_s=ask["screen_s"], ask_refine_s=ask["refine_s"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(p, 1, {"cpu_sample_q_batches": n}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(p, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sample_q_batches": n},
+        "e2e": e2e, "gpu_launches": 0, "ask_latency": ask, "setup_s": {"acqf_build": t_setup},
     }
     emit(line)
 
@@ -174,7 +209,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
@@ -183,6 +218,7 @@ class ClockSampler:
                 try:
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
+                    pw.append(float(f[3]))
                 except ValueError:
                     continue
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -192,33 +228,173 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       sm_mhz_min=min(sm), power_w_max=max(pw) if pw else None)
         return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# peaks measured in this run (MEASURED_PEAKS.json holds HBM and bf16 only)
+# ----------------------------------------------------------------------------------------------------
+def _best_of(fn, reps, device):
+    fn()
+    torch.cuda.synchronize(device)
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def measure_fp64_peak(device):
+    """cuBLAS DGEMM 8192^3 through torch.matmul, best of 5 (CUDA events): the fp64 roofline denominator."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.double, device=device)
+    b = torch.randn(n, n, dtype=torch.double, device=device)
+    ms = _best_of(lambda: torch.matmul(a, b), 5, device)
+    return 2.0 * n**3 / (ms * 1e-3) / 1e12
+
+
+def measure_int8_peak(device):
+    """cuBLASLt INT8 x INT8 -> INT32 GEMM 8192^3 through torch._int_mm: (burst TOP/s best of 10, sustained TOP/s over ~1 s
+    back to back) -- the same protocol MEASURED_PEAKS.json uses for bf16.  None if this torch build has no such kernel."""
+    try:
+        n = 8192
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=device)
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=device)
+        ms = _best_of(lambda: torch._int_mm(a, b), 10, device)
+        burst = 2.0 * n**3 / (ms * 1e-3) / 1e12
+        reps = max(10, int(1000.0 / ms))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch._int_mm(a, b)
+        e1.record()
+        e1.synchronize()
+        sustained = 2.0 * n**3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        return burst, sustained
+    except Exception:
+        return None
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def committed_ncu(kernel_substr, workload):
+    """Per-launch DRAM traffic and tensor-pipe counters of a kernel from the committed ncu summary of THIS round
+    (profiles/r02_ncu_counters.json, written by tools/ncu_counters.py from a `ncu --set full` capture); None when the file
+    holds nothing for this kernel on this workload -- never a constant typed into this script."""
+    try:
+        db = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_counters.json")))
+    except Exception:
+        return None
+    for rec in db.get("kernels", []):
+        if kernel_substr in rec.get("kernel", "") and rec.get("workload") == workload:
+            return rec
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-kernel rooflines: algorithmic work of one step / measured time of the kernel family in that step
+# ----------------------------------------------------------------------------------------------------
+def kernel_rooflines(p, st, acq, b, avg, peaks, fp64_peak, int8_peak, used_int8, workload):
+    """avg: {family: (ms per step summed over its launches, launches per step)}.  Returns {family: roofline dict}."""
+    N, nb, M, q, S = st.N, int(acq.nb), st.M, int(p["q"]), int(p["S"])
+    rows = b * q
+    ldk = ((N + 15) // 16) * 16
+    hbm = float(peaks["hbm_gbs"]) if peaks else 6650.0
+    hbm_src = "hbm_gbs of MEASURED_PEAKS.json (measured)" if peaks else "6650 GB/s (fallback of B200_PROFILING.md)"
+    out = {}
+
+    def entry(family, kernel, ncu_name, bound, work, unit_scale, unit, peak, peak_src, note):
+        ms, cnt = avg.get(family, (0.0, 0))
+        if cnt <= 0 or ms <= 0:
+            return
+        achieved = work / (ms * 1e-3) / unit_scale
+        rec = committed_ncu(ncu_name, workload)
+        out[family] = {"bound": bound, "kernel": kernel, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                       "traffic": rec.get("dram_bytes_per_launch") if rec else None,
+                       "traffic_source": (rec.get("source") if rec else "no ncu --set full capture of this kernel on this workload "
+                                          "committed this round (profiles/r02_ncu_counters.json): null, not a typed-in constant"),
+                       "peak_source": peak_src, "algorithmic_work_per_launch": work / cnt, "launch_ms": ms / cnt,
+                       "launches_per_step": cnt, "algorithmic_work_note": note}
+        if rec:
+            for k in ("tensor_pipe_active_pct", "imma_pipe_active_pct", "fp64_pipe_active_pct", "issue_active_pct", "dram_throughput_pct"):
+                if rec.get(k) is not None:
+                    out[family]["ncu_" + k] = rec[k]
+
+    # ---- posterior GEMM: V = K(X*,X) LinvExt^T never stored, Gram / W / mean reduced on the fly ----
+    flops = M * rows * (float(N) * N + 2.0 * N * (nb + 1))   # triangular-solve equivalent N^2 per point and output + extras
+    if used_int8:
+        i8_peak = 2.0 * float(peaks["bf16_tflops"]) if peaks else 4500.0
+        src = ("2 x bf16_tflops (burst) of MEASURED_PEAKS.json: INT8 runs on the same tensor pipe at half the operand width"
+               if peaks else "nominal 4.5 POPS dense INT8 (MEASURED_PEAKS.json unavailable)")
+        entry("posterior_gemm", "ozaki_gemm2p_kernel (tcgen05.mma.kind::i8 M128xN128xK32, TMEM accumulators, two passes over K: "
+              "28 exact INT8 digit-plane products = one FP64-accurate GEMM)", "ozaki_gemm2p_kernel", "tensor", 28.0 * flops, 1e12,
+              "TFLOP/s", i8_peak, src,
+              "achieved = 28 digit-plane products x algorithmic FP64 flops M b q (N^2 + 2 N (1 + n_b)) / kernel time (INT8 TOP/s)")
+        r = out.get("posterior_gemm")
+        if r:
+            r["fp64_equivalent_tflops"] = r["achieved"] / 28.0
+            r["fp64_pipe_peak_tflops"] = fp64_peak
+            r["fp64_equivalent_over_fp64_pipe"] = r["achieved"] / 28.0 / fp64_peak
+            if int8_peak:
+                r["int8_peak_measured_in_run_burst"] = int8_peak[0]
+                r["int8_peak_measured_in_run_sustained"] = int8_peak[1]
+                r["frac_vs_measured_int8"] = r["achieved"] / int8_peak[0]
+                r["frac_vs_measured_int8_sustained"] = r["achieved"] / int8_peak[1]
+                r["int8_peak_source"] = "torch._int_mm 8192^3 (cuBLASLt IGEMM) in this run: best of 10 / back to back for ~1 s"
+            if peaks and peaks.get("bf16_tflops_sustained"):
+                r["frac_vs_2x_bf16_sustained"] = r["achieved"] / (2.0 * float(peaks["bf16_tflops_sustained"]))
+    else:
+        entry("posterior_gemm", "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)", "posterior_gemm", "tensor", flops,
+              1e12, "TFLOP/s", fp64_peak,
+              "torch.matmul f64 8192^3 (cuBLAS DGEMM) best of 5 in this run; MEASURED_PEAKS.json has no fp64 figure",
+              "achieved = algorithmic FP64 flops M b q (N^2 + 2 N (1 + n_b)) / kernel time")
+    # ---- K(X*,X): writes 7 digit planes (INT8 path) or the FP64 matrix; one exp per element ----
+    bytes_x = M * rows * float(ldk) * (7.0 if used_int8 else 8.0)
+    entry("crosscov", "crosscov_fast_kernel / crosscov_kernel2 (K(X*,X): distances on FP64 DMMA, kernel function, digit slicing)",
+          "crosscov", "hbm", bytes_x, 1e9, "GB/s", hbm, hbm_src,
+          "algorithmic bytes = M b q ldk x (7 digit planes | 8 B FP64) written once; reads (candidates, training rows) are L2-resident")
+    # ---- MC value: samples -> objectives -> inclusion-exclusion over the cells ----
+    if p["acqf"] == "qnehvi":
+        Mo = len(p["ref_point"])
+        try:
+            cbar = float(st.debug_get("ncells", dtype=torch.int32).double().mean())
+        except Exception:
+            cbar = float(getattr(acq, "max_cells", 0))
+        f_hvi = float(b) * S * cbar * (2 ** q - 1) * 3.0 * Mo + 2.0 * float(b) * S * M * q * (nb + q)
+        entry("mc_acqf", "mc_hvi_tiled_kernel / mc_hvi_chunked_kernel (MC samples, objectives, inclusion-exclusion HVI)", "mc_hvi",
+              "tensor", f_hvi, 1e12, "TFLOP/s", fp64_peak,
+              "FP64 ALU (DFMA) rate = the FP64 tensor-pipe rate on this part (tools/fp64_peak: 37.0 TFLOP/s both); denominator = "
+              "cuBLAS DGEMM measured in this run",
+              f"algorithmic flops = b S C (2^q - 1) 3 M_o + 2 b S M q (n_b + q), C = mean cells per sample = {cbar:.1f}; the kernel "
+              "skips cells and subsets that cannot overlap, so its executed flops are lower")
+    else:
+        f_sc = float(b) * S * q * (M * q + 60.0)
+        entry("mc_acqf", "mc_scalar_kernel (MC samples, objective, log-space EI)", "mc_scalar", "tensor", f_sc, 1e12, "TFLOP/s",
+              fp64_peak, "FP64 ALU: cuBLAS DGEMM measured in this run as the FP64 rate", "algorithmic flops = b S q (M q + ~60)")
+    # ---- conditional root and sample GEMM ----
+    entry("cond_root", "cond_root_kernel (sample_cached_cholesky: bl = Sqb Lb^-T, br = chol(Sqq - bl bl^T))", "cond_root", "tensor",
+          float(b) * M * (q * float(nb) * nb + q ** 3 / 3.0 + 2.0 * q * q * nb), 1e12, "TFLOP/s", fp64_peak,
+          "FP64 ALU: cuBLAS DGEMM measured in this run", "algorithmic flops = b M (q n_b^2 + q^3 / 3 + 2 q^2 n_b); latency-bound kernel")
+    if nb > 0:
+        entry("sample_gemm", "gemm_nt_kernel (baseline part of every MC sample, F' = bl z_b^T)", "gemm_nt", "hbm",
+              M * rows * float(S) * 8.0, 1e9, "GB/s", hbm, hbm_src, "algorithmic bytes = M b q S x 8 B written (the operands are small)")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------
-def measure_fp64_peak(device):
-    """cuBLAS DGEMM 8192^3 through torch.matmul, best of 5 (CUDA events): the fp64 roofline denominator
-    (MEASURED_PEAKS.json only holds HBM and bf16 figures)."""
-    n = 8192
-    a = torch.randn(n, n, dtype=torch.double, device=device)
-    b = torch.randn(n, n, dtype=torch.double, device=device)
-    torch.matmul(a, b)
-    torch.cuda.synchronize(device)
-    best = float("inf")
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        torch.matmul(a, b)
-        e1.record()
-        e1.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    del a, b
-    return 2.0 * n**3 / (best * 1e-3) / 1e12
-
-
 def run_b200(args):
     import torch.distributed as dist
 
@@ -241,7 +417,8 @@ def run_b200(args):
         torch.cuda.synchronize(device)
 
     p = make_problem(args)
-    p["cand_seed"] = p["cand_seed"] + rank  # every rank screens its own raw samples (weak scaling)
+    p_global = dict(p)                                   # strong scaling: ONE candidate set, sliced over the ranks
+    p["cand_seed"] = p["cand_seed"] + rank               # weak scaling: every rank screens its own raw samples
     t0 = time.perf_counter()
     st = Cf.build_state(p, device=device)
     torch.cuda.synchronize(device)
@@ -254,37 +431,68 @@ def run_b200(args):
     X = X_host.to(device)
     b, q, d = X.shape
     stream = torch.cuda.current_stream(device)
+    pair_buf = torch.empty(2, dtype=torch.double, device=device)
+    gather_buf = torch.empty(2 * world, dtype=torch.double, device=device) if world > 1 else None
 
-    def step():
+    def exchange(vals, offset):
+        # the only exchange of the path: best (value, global index) per rank, 16 bytes, one all-gather into a preallocated buffer
+        v, i = torch.max(vals, dim=0)
+        pair_buf[0] = v
+        pair_buf[1] = (i + offset).to(torch.double)
+        dist.all_gather_into_tensor(gather_buf, pair_buf)
+
+    def timed(step_fn, steps, warm):
+        for _ in range(warm):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    def weak_step():
         vals = acq(X)
-        if world > 1:  # the only exchange of the path: best (value, global index) per rank, 16 bytes
-            i = torch.argmax(vals)
-            pair = torch.stack([vals[i], (i + rank * b).to(torch.double)])
-            allp = [torch.empty_like(pair) for _ in range(world)]
-            dist.all_gather(allp, pair)
+        if world > 1:
+            exchange(vals, rank * b)
         return vals
 
-    for _ in range(max(args.warmup, 3)):
-        vals = step()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        vals = weak_step()
     barrier()
     launches0 = st.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        vals = step()
-    e1.record(stream)
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.double, device=device)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_weak = timed(weak_step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     launches = st.launch_count() - launches0
-    ms_total = float(ms[0])
-    value = world * b * args.steps / (ms_total * 1e-3)
+    vals = acq(X)
+    value_weak = world * b * args.steps / (ms_weak * 1e-3)
+
+    # ---- strong scaling: BASELINE config 3 is 16384 raw samples IN TOTAL; every rank scores its 1/N slice ----
+    strong = None
+    if world > 1:
+        from everest_b200 import distributed as D
+
+        Xg = Cf.candidates(p_global)
+        lo, hi = D.shard_bounds(Xg.shape[0], rank, world)
+        Xs = Xg[lo:hi].contiguous().to(device)
+
+        def strong_step():
+            v = acq(Xs)
+            exchange(v, lo)
+
+        ms_strong = timed(strong_step, args.steps, warm)
+        strong = {"value": Xg.shape[0] * args.steps / (ms_strong * 1e-3), "unit": UNIT, "ms_per_step": ms_strong / args.steps,
+                  "q_batches_total": int(Xg.shape[0]), "q_batches_per_gpu": int(hi - lo),
+                  "note": "fixed total work: the 16384 raw samples of the config split over the ranks, same 16-byte exchange"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned staging, H2D, launches, D2H) -------
     Xh = X_host.numpy()
@@ -306,96 +514,57 @@ def run_b200(args):
     assert np.allclose(out_h, ref_v, rtol=1e-8, atol=1e-10 * float(np.abs(ref_v).max())), \
         "host-buffer path disagrees with the device-pointer path"
 
-    # ---- roofline of the dominant kernel (posterior GEMM), timed with CUDA events on its stream ----
+    # ---- rooflines: every kernel family timed with CUDA events on its stream inside the step --------
     roofline = None
-    kernel_share = None
     if rank == 0:
         st.set_timing(True)
         per = {}
-        reps = 3
-        for _ in range(reps):
+        fams = ("prep", "crosscov", "ozaki_slice", "posterior_gemm", "ozaki_guard", "ozaki_redo", "cond_root", "sample_gemm", "mc_acqf")
+        for _ in range(3):
             acq(X)
             torch.cuda.synchronize(device)
-            for name in ("prep", "crosscov", "ozaki_slice", "posterior_gemm", "cond_root", "sample_gemm", "mc_acqf"):
+            for name in fams:
                 t, cnt = st.last_timing(name)
                 per.setdefault(name, []).append((t, cnt))
         st.set_timing(False)
         avg = {k: (sum(t for t, _ in v) / len(v), v[0][1]) for k, v in per.items()}
         total_ms = sum(t for t, _ in avg.values())
-        kernel_share = {k: round(t / total_ms, 4) for k, (t, _) in avg.items()}
-        g_ms, g_cnt = avg["posterior_gemm"]  # ms per step summed over its launches, launches per step
-        N, nb, M = st.N, acq.nb, st.M
-        rows = b * q
-        # triangular solve-equivalent N^2 flops per point and output + the 1 + n_b dense extra rows
-        flops_per_step = M * rows * (float(N) * N + 2.0 * N * (nb + 1))
-        flops_per_launch = flops_per_step / g_cnt
-        achieved = flops_per_step / (g_ms * 1e-3) / 1e12
-        peak = measure_fp64_peak(device)
-        # DRAM bytes of one launch from the committed ncu --set full capture (profiles/r01_ncu_summary.txt); only valid
-        # for the default headline workload, null otherwise
-        traffic = 2.349e9 if (args.workload == "zdt1" and not args.raw_samples) else None  # profiles/r01_s2_ncu_gemm_dram_groups8.csv
-        oz_ms, oz_cnt = st.last_timing("ozaki_slice")
-        roofline_fp64 = None
+        share = {k: round(t / total_ms, 4) for k, (t, _) in avg.items() if t > 0}
         chk = st.debug_get("ozaki_check", capacity=16).cpu().tolist()
-        int8_check = {"state": {0: "not run (problem below the INT8 threshold)", 1: "INT8 path with per-row guard",
-                                -1: "guard flagged most rows -> FP64 DMMA kernel"}[int(chk[0])],
-                      "q_batches_redone_in_fp64_last_step": int(chk[1]), "q_batches_last_step": int(chk[2]),
-                      "q_batches_redone_since_prepare": int(chk[3]), "q_batches_since_prepare": int(chk[4]),
-                      "guard": f"2 sqrt(G_ii) eps + N eps^2 <= {chk[6]:g} (k** - G_ii), eps = {chk[5]:g} x 2^-56 sqrt(N) sA max sB "
-                               "(csrc/ozaki.cu); flagged q-batches are recomputed by the FP64 kernel"}
-        roofline = {"bound": "tensor", "kernel": "posterior_gemm_tma_kernel (FP64 DMMA m8n8k4, TMA + mbarrier ring)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu, profiles/r01_s2_ncu_gemm_dram_groups8.csv; "
-                                    "16.2 GB before the L2-sharing column groups, algorithmic 2.2 GB)",
-                    "peak_source": "torch.matmul f64 8192^3 (cuBLAS DGEMM) best of 5 measured in this run; "
-                                   "MEASURED_PEAKS.json holds no fp64 figure; tools/fp64_peak measured 37.0 TFLOP/s "
-                                   "for raw DMMA and DFMA issue on this pool",
-                    "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": g_ms / g_cnt,
-                    "launches_per_step": g_cnt, "step_time_share": kernel_share, "int8_self_check": int8_check}
-        if oz_cnt > 0:
-            # the GEMM ran as 28 exact INT8 digit-plane products on tcgen05 (csrc/ozaki.cu): the roofline that bounds it is
-            # the INT8 tensor pipe = 2 x the dense bf16 rate of MEASURED_PEAKS.json (same pipe, half the operand width)
-            import json as _json
-            try:
-                mp = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-                i8_peak, src = 2.0 * float(mp["bf16_tflops"]), "2 x bf16_tflops (burst) of MEASURED_PEAKS.json"
-            except Exception:
-                i8_peak, src = 4500.0, "nominal 4.5 POPS dense INT8 (MEASURED_PEAKS.json unavailable)"
-            i8_ops = 28.0 * flops_per_step / (g_ms * 1e-3) / 1e12
-            roofline.update({
-                "kernel": "ozaki_gemm2p_kernel (tcgen05.mma.kind::i8 M128xN128xK32, TMEM accumulators, two passes over K: "
-                          "28 exact INT8 digit-plane products = one FP64-accurate GEMM)",
-                "achieved": i8_ops, "peak": i8_peak, "unit": "TFLOP/s", "frac": i8_ops / i8_peak,
-                "peak_source": src + "; tools/i8_mma_probe: 4.6 POPS (N >= 128) / 3.07 POPS (N = 64, this kernel's tile) "
-                                     "single-SM issue rate x 148 at 1.9 GHz",
-                "algorithmic_ops_note": "achieved = 28 digit-plane products x algorithmic FP64 flops / kernel time (INT8 TOP/s)",
-                "fp64_equivalent_tflops": achieved, "fp64_pipe_peak_tflops": peak, "fp64_equivalent_over_fp64_pipe": achieved / peak,
-                # one ncu --set full capture of the kernel on this workload (profiles/r01_s3_ncu_summary.txt): 3.50 GB read +
-                # 1.13 GB written per launch; algorithmic 1.9 GB (7 digit planes of K(X*,X) and LinvExt, both outputs) -- the
-                # rest is the second pass over planes 4..6 and the write-back of the 128 KB-per-SM integer scratch slab
-                "traffic": 4.63e9 if (args.workload == "zdt1" and not args.raw_samples) else None,
-                "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum (ncu --set full, "
-                                "profiles/r01_s3_ncu_summary.txt); algorithmic 1.9 GB; 0.8 TB/s = 12 % of HBM, not the bound"})
+        used_int8 = avg.get("ozaki_slice", (0, 0))[1] > 0 and int(chk[0]) == 1
+        fp64_peak = measure_fp64_peak(device)
+        int8_peak = measure_int8_peak(device) if used_int8 else None
+        peaks = measured_peaks()
+        rl = kernel_rooflines(p, st, acq, b, avg, peaks, fp64_peak, int8_peak, used_int8, p["name"])
+        dominant = max((k for k in share if k in rl), key=lambda k: share[k], default=None)
+        if dominant:
+            roofline = dict(rl[dominant])
+            roofline["dominant_kernel_family"] = dominant
+            roofline["dominant_share_of_step"] = share[dominant]
+            for k, v in share.items():
+                roofline["share_" + k] = v                  # flat copies: the driver keeps scalars
+            roofline["step_time_share"] = share
+            roofline["other_kernels"] = {k: {kk: vv for kk, vv in v.items() if kk in ("bound", "achieved", "peak", "unit", "frac", "launch_ms")}
+                                         for k, v in rl.items() if k != dominant}
+            roofline["int8_guard"] = {
+                "state": {0: "not run (problem below the INT8 threshold)", 1: "INT8 path with per-row guard",
+                          -1: "guard flagged most rows -> FP64 DMMA kernel"}[int(chk[0])],
+                "q_batches_redone_in_fp64_last_step": int(chk[1]), "q_batches_last_step": int(chk[2]),
+                "q_batches_redone_since_prepare": int(chk[3]), "q_batches_since_prepare": int(chk[4]),
+                "rule": f"2 sqrt(G_ii) eps + N eps^2 <= {chk[6]:g} (k** - G_ii), eps = {chk[5]:g} x 2^-56 sqrt(N) sA max sB "
+                        "(csrc/ozaki.cu); flagged q-batches are recomputed by the FP64 kernel"}
+            roofline["int8_q_batches_redone_in_fp64_per_step"] = int(chk[1])
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------
     cpu = None
+    acq_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            idx = acq.prune_idx.cpu() if getattr(acq, "prune_idx", None) is not None else None
-            cells = None
-            if p["acqf"] == "qnehvi" and len(p["ref_point"]) > 2:
-                # the oracle's pure-Python Lacour decomposition of 512 fronts takes minutes: time its forward pass
-                # on the device's cell list (padded with empty cells), which the parity tests pin at small sizes
-                lo, up, nc = acq.cell_bounds()
-                C = int(nc.max())
-                ref = torch.tensor(p["ref_point"], dtype=torch.double)
-                lo, up = lo[:, :C].clone(), up[:, :C].clone()
-                pad = torch.arange(C).unsqueeze(0) >= nc.unsqueeze(1)
-                lo[pad] = ref
-                up[pad] = ref
-                cells = (lo, up)
-            acq_cpu = cpu_reference_setup(p, baseline_idx=idx, cell_bounds=cells)
-            n = args.cpu_sample or ((2048 if cells is None else 16) if p["acqf"] == "qnehvi" else 4096)  # ~10 s of CPU work
+            t0 = time.perf_counter()
+            acq_cpu = cpu_reference_setup(p, acq_d=acq)
+            t_cpu_setup = time.perf_counter() - t0
+            many = p["acqf"] == "qnehvi" and len(p["ref_point"]) > 2
+            n = args.cpu_sample or ((16 if many else 2048) if p["acqf"] == "qnehvi" else 4096)  # ~10 s of CPU work
             Xc = X_host[:n]
             cpu_time_forward(acq_cpu, Xc[:8], 8)
             v8, dt8 = cpu_time_forward(acq_cpu, Xc, 8)
@@ -405,13 +574,13 @@ def run_b200(args):
             cpu = {"value": max(v8, vall), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{n} of {b} q-batches; as BoFire calls it (chunks of 8): {v8:.1f} evals/s in {dt8:.1f} s; "
                              f"best case (one call over the sample): {vall:.1f} evals/s in {dtall:.1f} s; value = the faster",
-                   "max_rel_err_gpu_vs_cpu_on_sample": err}
+                   "sample_q_batches": n, "max_rel_err_gpu_vs_cpu_on_sample": err, "setup_s": t_cpu_setup}
         except Exception as exc:  # the baseline must never take the headline number down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
 
-    # ---- ask() latency: acqf construction + screen + L-BFGS-B refinement of the restarts (rank 0, N=1) ----
+    # ---- ask() latency: acqf construction + screen + refinement of the restarts -----------------------
     ask = None
-    if rank == 0 and world == 1 and p.get("bounds") is not None:
+    if rank == 0 and world == 1 and p.get("bounds") is not None and not args.no_ask:
         from everest_b200 import optim
 
         torch.cuda.synchronize(device)
@@ -420,18 +589,11 @@ def run_b200(args):
         acq2 = Cf.build_acqf(p, st)
         torch.cuda.synchronize(device)
         t1 = time.perf_counter()
-        if os.environ.get("EVEREST_BENCH_PROFILE"):
-            import cProfile, pstats
-            pr = cProfile.Profile(); pr.enable()
-            acq2 = Cf.build_acqf(p, st); torch.cuda.synchronize(device)
-            pr.disable()
-            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(16)
         bnds = torch.as_tensor(p["bounds"])
         Xic, Yic, _, _ = optim.gen_batch_initial_conditions(acq2, bnds, p["q"], p["num_restarts"], p["raw_samples"], seed=0)
         torch.cuda.synchronize(device)
         t2 = time.perf_counter()
-        maxit = 200
-        _, Yref, info = optim.gen_candidates_scipy(Xic, acq2, bnds[0], bnds[1], options={"maxiter": maxit})
+        _, Yref, info = optim.gen_candidates_scipy(Xic, acq2, bnds[0], bnds[1], options={"maxiter": ASK_MAXITER})
         torch.cuda.synchronize(device)
         t3 = time.perf_counter()
         # one forward+backward of the restarts alone (device time of the adjoint path, CUDA events)
@@ -443,43 +605,69 @@ def run_b200(args):
             acq2.forward_backward(Xr)
         ev1.record()
         torch.cuda.synchronize(device)
-        ask = {"acqf_build_s": t1 - t0, "screen_s": t2 - t1, "refine_s": t3 - t2, "refine_maxiter": maxit,
+        ask = {"acqf_build_s": t1 - t0, "screen_s": t2 - t1, "refine_s": t3 - t2, "refine_maxiter": ASK_MAXITER,
                "refine_iterations": info["nit"], "refine_acqf_evals": info["n_acqf_evals"],
+               "refine_optimizer": info.get("optimizer", "scipy L-BFGS-B, analytic device gradient"),
                "forward_backward_ms": ev0.elapsed_time(ev1) / 10.0,
                "best_screened": float(Yic.max()), "best_refined": float(torch.maximum(Yref, Yic).max()),
-               "total_s": t3 - t0,
-               "note": "refinement = scipy L-BFGS-B over all restarts, gradient from the analytic adjoint kernels "
-                       "(bo_acqf_forward_backward)"}
+               "total_s": t3 - t0}
+        if acq_cpu is not None and len(p.get("ref_point", [0, 0])) <= 2:
+            try:
+                torch.set_num_threads(os.cpu_count() or 1)
+                cpu_ask = cpu_ask_latency(p, acq_cpu)
+                cpu_ask["acqf_build_s"] = cpu["setup_s"] if cpu else None
+                cpu_ask["total_s"] = (cpu_ask["acqf_build_s"] or 0.0) + cpu_ask["screen_s"] + cpu_ask["refine_s"]
+                ask["cpu_port"] = cpu_ask
+                ask["speedup_vs_cpu_port"] = cpu_ask["total_s"] / ask["total_s"]
+            except Exception as exc:
+                ask["cpu_port"] = {"failed": repr(exc)}
 
-    if world > 1 and p.get("bounds") is not None:
-        # ask() over the GPUs of the box: raw samples and restarts sharded, one value all-gather + one arg-max exchange
+    if world > 1 and p.get("bounds") is not None and not args.no_ask:
+        # ask() over the GPUs of the box, STRONG scaling: the config's raw samples and restarts sharded over the ranks
         from everest_b200 import distributed as D
 
         barrier()
         t0 = time.perf_counter()
-        acq2 = Cf.build_acqf(p, st)
+        acq2 = Cf.build_acqf(p_global, st)
         barrier()
         t1 = time.perf_counter()
         cand, val = D.sharded_optimize_acqf(acq2, torch.as_tensor(p["bounds"]), p["q"], p["num_restarts"],
-                                            p["raw_samples"] * world, options={"maxiter": 200}, seed=0)
+                                            p["raw_samples"], options={"maxiter": ASK_MAXITER}, seed=0)
         barrier()
         t2 = time.perf_counter()
-        ask = {"acqf_build_s": t1 - t0, "screen_and_refine_s": t2 - t1, "total_s": t2 - t0, "refine_maxiter": 200,
-               "raw_samples_total": int(p["raw_samples"] * world), "best_refined": float(val),
-               "note": "sharded_optimize_acqf: raw samples and restarts split over the ranks, analytic gradients, "
+        ask = {"acqf_build_s": t1 - t0, "screen_and_refine_s": t2 - t1, "total_s": t2 - t0, "refine_maxiter": ASK_MAXITER,
+               "raw_samples_total": int(p["raw_samples"]), "best_refined": float(val),
+               "note": "sharded_optimize_acqf, strong scaling: the config's raw samples and restarts split over the ranks, "
                        "one all-gather of the screen values + one (value, rank) arg-max exchange + one broadcast"}
 
     if rank == 0:
+        use_strong = args.scaling == "strong" and strong is not None
+        value = strong["value"] if use_strong else value_weak
+        ms_step = strong["ms_per_step"] if use_strong else ms_weak / args.steps
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b * q * d * 8), "d2h_bytes_per_step": int(b * 8)}
+        if ask:
+            e2e["ask_total_s"] = ask["total_s"]
+            e2e["ask_build_s"] = ask["acqf_build_s"]
+            for k_src, k_dst in (("screen_s", "ask_screen_s"), ("refine_s", "ask_refine_s"), ("screen_and_refine_s", "ask_screen_and_refine_s")):
+                if k_src in ask:
+                    e2e[k_dst] = ask[k_src]
+            if isinstance(ask.get("cpu_port"), dict) and "total_s" in ask["cpu_port"]:
+                e2e["ask_total_s_cpu_port"] = ask["cpu_port"]["total_s"]
+        if strong:
+            e2e["strong_scaling_value"] = strong["value"]
+            e2e["strong_scaling_ms_per_step"] = strong["ms_per_step"]
+            e2e["weak_scaling_value"] = value_weak
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": workload_config(p, world, {
-                "n_baseline_after_pruning": int(acq.nb), "max_cells_per_sample": int(getattr(acq, "max_cells", 0)),
-                "l2": "per-step working set (K(X*,X) 1.05 GB per output + factors) >> 126 MB L2; no flush needed",
-                "qbatch_x_mc_samples_per_sec": value * p["S"], "setup_s": {"factorize": t_factor, "acqf_prepare": t_prepare}, "ask_latency": ask}),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b * q * d * 8), "d2h_bytes_per_step": int(b * 8)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if use_strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(p, world),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "weak_scaling": {"value": value_weak, "ms_per_step": ms_weak / args.steps, "q_batches_per_gpu": int(b)},
+            "strong_scaling": strong,
+            "setup_s": {"factorize": t_factor, "acqf_prepare": t_prepare},
+            "ask_latency": ask,
+            "details": {"n_baseline_after_pruning": int(acq.nb), "max_cells_per_sample": int(getattr(acq, "max_cells", 0)),
+                        "qbatch_x_mc_samples_per_sec": value * p["S"]},
         }
         emit(line)
     if world > 1:

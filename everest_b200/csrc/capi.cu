@@ -1207,9 +1207,8 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   if (b == 0) return BO_OK;
   size_t in_bytes = (size_t)b * q * st->d * 8, out_bytes = (size_t)b * 8;
   if (st->pin_in_bytes < in_bytes) {
-    if (st->pin_count) cudaFreeHost(st->pin_count);
-  if (st->oz_event) cudaEventDestroy(st->oz_event);
-  if (st->pin_in) cudaFreeHost(st->pin_in);
+    if (st->pin_in) cudaFreeHost(st->pin_in);
+    st->pin_in = nullptr; st->pin_in_bytes = 0;
     CUDA_CHECK_RET(cudaHostAlloc(&st->pin_in, in_bytes, cudaHostAllocDefault));
     st->pin_in_bytes = in_bytes;
   }
