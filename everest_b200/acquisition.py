@@ -146,6 +146,36 @@ class _DeviceAcquisition:
             dX = dX[:, :q_in].contiguous()   # the pending points are constants
         return (out.cpu(), dX.cpu()) if on_cpu else (out, dX)
 
+    def optimize(self, X0, lower_bounds, upper_bounds, maxiter: int = 2000, history: int = 10, pgtol: float = 1e-5,
+                 ftol: float = 2.220446049250313e-09):
+        """On-device multi-start refinement through bo_acqf_optimize (csrc/lbfgs.cu): every restart X0[i] [q, d] runs its
+        own box-constrained L-BFGS with the analytic gradient, no host round trip per iteration.  The defaults are scipy's
+        L-BFGS-B defaults (m = 10, pgtol = 1e-5, ftol = factr * eps = 2.2e-9), which is what BoTorch's gen_candidates_scipy
+        runs with.  Returns (X [r, q, d], values [r], stats dict) on the device."""
+        X = torch.as_tensor(X0, dtype=torch.double)
+        if X.dim() == 2:
+            X = X.unsqueeze(0)
+        if X.dim() != 3 or X.shape[-1] != self.model.d:
+            raise ValueError(f"X0 must be [r, q, {self.model.d}]")
+        self._check_active()
+        d = self.model.d
+        q_free = X.shape[1]
+        Xd = self._with_pending(X.detach().to(self.model.device)).contiguous().clone()
+        r, q_tot, _ = Xd.shape
+        lb = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(lower_bounds).cpu(), dtype=np.float64), (d,)))
+        ub = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(upper_bounds).cpu(), dtype=np.float64), (d,)))
+        out = torch.empty(r, dtype=torch.double, device=self.model.device)
+        stats = (C.c_int32 * 4)()
+        zq = self.base_samples_q(q_tot)
+        with torch.cuda.device(self.model.device):
+            L.check(self.model.lib.bo_acqf_optimize(self.model.handle, _dev_ptr(Xd), r, q_tot, q_free,
+                                                    lb.ctypes.data_as(L.c_double_p), ub.ctypes.data_as(L.c_double_p), _dev_ptr(zq),
+                                                    int(maxiter), int(history), float(pgtol), float(ftol), _dev_ptr(out), stats,
+                                                    _stream()))
+        info = {"n_acqf_evals": int(stats[0]) * r, "n_steps": int(stats[0]), "nit": int(stats[1]), "n_converged": int(stats[2]),
+                "n_budget": int(stats[3])}
+        return Xd[:, :q_free].contiguous(), out, info
+
     def forward_host(self, X: np.ndarray) -> np.ndarray:
         """Same call with HOST buffers through bo_acqf_forward_host (pinned staging + H2D + D2H inside)."""
         X = np.ascontiguousarray(X, dtype=np.float64)

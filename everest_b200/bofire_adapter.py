@@ -6,8 +6,10 @@
   Runs wherever ``bofire.data_models`` imports (it does in the build image; tests/test_host_logic.py).
 * ``objectives_from_outputs``: ``Outputs`` -> op tables, mirrors ``_callables_and_weights`` /
   ``get_multiobjective_objective`` / ``get_output_constraints`` (utils/torch_tools.py:340-381, 598-727).
-* ``state_from_botorch_model``: fitted ModelListGP / SingleTaskGP -> DeviceGPState.  Needs botorch + gpytorch,
-  which are NOT installable in the build image, so this one function is untested here.
+* ``specs_from_botorch_model`` / ``state_from_botorch_model``: fitted ModelListGP / SingleTaskGP / MixedSingleTaskGP ->
+  specs -> DeviceGPState.  botorch / gpytorch are NOT installable in the build image: the attribute walk is tested on CPU with
+  duck-typed stand-ins (tests/test_host_logic.py) and against the real classes in tests/test_botorch_parity.py where BoTorch is
+  installed.
 """
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -127,18 +129,41 @@ def objectives_from_outputs(outputs, experiments=None):
 # ------------------------------------------------------------------------------------------------
 # fitted BoTorch model -> device state   (needs botorch / gpytorch; untested in the build image)
 # ------------------------------------------------------------------------------------------------
-def _kernel_from_gpytorch(k, d, col_map):  # pragma: no cover
+def _kernel_from_gpytorch(k, d, col_map):
+    """gpytorch / BoTorch / BoFire kernel module -> spec tree.  `col_map[j]` is what dimension j of the space the kernel sees
+    is in the BoFire-transformed layout: a column index, or ("cat", start, cardinality) for an integer-coded categorical that
+    an upstream OneHotToNumeric produced from a one-hot block."""
     name = type(k).__name__
     dims = [col_map[int(i)] for i in (k.active_dims.tolist() if k.active_dims is not None else range(d))]
+
+    def ls():
+        return k.lengthscale.detach().cpu().double().view(-1).tolist()
+
+    def columns():
+        if any(isinstance(c, tuple) for c in dims):
+            raise NotImplementedError(f"{name} over integer-coded categorical dimensions is outside the accelerated path")
+        return dims
+
     if name == "RBFKernel":
-        return K.RBFKernel(dims, k.lengthscale.detach().cpu().double().view(-1).tolist())
+        return K.RBFKernel(columns(), ls())
     if name == "MaternKernel":
-        return K.MaternKernel(dims, k.lengthscale.detach().cpu().double().view(-1).tolist(), nu=float(k.nu))
+        return K.MaternKernel(columns(), ls(), nu=float(k.nu))
     if name == "TanimotoKernel":
-        return K.TanimotoKernel(dims)
+        return K.TanimotoKernel(columns())
     if name == "HammingKernelWithOneHots":
-        cf = {dims[s]: c for s, c in k.trx.categorical_features.items()}
-        return K.HammingDistanceKernel(cf, k.lengthscale.detach().cpu().double().view(-1).tolist())
+        cols = columns()
+        cf = {cols[s]: c for s, c in k.trx.categorical_features.items()}
+        return K.HammingDistanceKernel(cf, ls())
+    if name == "CategoricalKernel":
+        # [UPSTREAM] botorch CategoricalKernel on integer codes: exp(-mean_f(delta_f / l_f)) -- the one-hot Hamming kernel
+        # (equality pinned by tests/bofire/kernels/test_categorical.py), one ARD lengthscale per categorical FEATURE
+        if not all(isinstance(c, tuple) for c in dims):
+            raise NotImplementedError("CategoricalKernel over columns that no OneHotToNumeric produced")
+        vals = ls()
+        if len(vals) == 1:
+            vals = vals * len(dims)
+        order = sorted(range(len(dims)), key=lambda i: dims[i][1])
+        return K.HammingDistanceKernel({dims[i][1]: dims[i][2] for i in order}, [vals[i] for i in order])
     if name == "ScaleKernel":
         return K.ScaleKernel(_kernel_from_gpytorch(k.base_kernel, d, col_map), float(k.outputscale.detach().cpu()))
     if name == "AdditiveKernel":
@@ -148,44 +173,83 @@ def _kernel_from_gpytorch(k, d, col_map):  # pragma: no cover
     raise NotImplementedError(f"gpytorch kernel {name} is outside the accelerated path")
 
 
-def state_from_botorch_model(model, device=None):  # pragma: no cover
-    from .model import DeviceGPState, SingleTaskGPSpec
+def specs_from_botorch_model(model, X_train=None):
+    """Fitted ModelListGP / SingleTaskGP / MixedSingleTaskGP as `BotorchSurrogates.compatibilize` returns it
+    (surrogates/botorch_surrogates.py:79-128) -> (X_train in the BoFire-transformed layout, [SingleTaskGPSpec]).
+    Input transforms understood: FilterFeatures (compatibilize), Normalize / InputStandardize (get_scaler,
+    surrogates/utils.py:103-164), OneHotToNumeric (mixed_single_task_gp.py:82-88: the literal MixedSingleTaskGPSurrogate;
+    its CategoricalKernel becomes the one-hot Hamming leaf on the original one-hot block).  `X_train` [N, d]: the transformed
+    experiments BoFire fitted on (`inputs.transform(experiments, specs)`); needed when a FilterFeatures hides columns from a
+    sub-model, otherwise recovered from the model.  Pure host code that only reads attributes: exercised on CPU with
+    duck-typed stand-ins (tests/test_host_logic.py) and against real BoTorch where installed (tests/test_botorch_parity.py)."""
+    from .model import SingleTaskGPSpec
 
     models = list(model.models) if hasattr(model, "models") else [model]
-    X_full, specs = None, []
+    X_full = None if X_train is None else np.ascontiguousarray(np.asarray(
+        X_train.detach().cpu().numpy() if hasattr(X_train, "detach") else X_train, dtype=np.float64))
+    specs = []
     for sub in models:
         tf = getattr(sub, "input_transform", None)
         chain = list(tf.values()) if tf is not None and hasattr(tf, "values") else ([tf] if tf is not None else [])
+        names = [type(t).__name__ for t in chain]
+        for tn in names:
+            if tn not in ("FilterFeatures", "Normalize", "InputStandardize", "OneHotToNumeric"):
+                raise NotImplementedError(f"input transform {tn} is outside the accelerated path")
         X_raw = sub.train_inputs[0].detach().cpu().double()
-        col_map = list(range(X_raw.shape[-1]))
-        off, scl = None, None
-        for t in chain:
-            tn = type(t).__name__
+        X_raw = X_raw.reshape(-1, X_raw.shape[-1])
+        o2n = next((t for t in chain if type(t).__name__ == "OneHotToNumeric"), None)
+        if X_full is None:
+            if "FilterFeatures" in names:
+                raise ValueError("a sub-model sees a subset of the columns (FilterFeatures): pass X_train, the transformed "
+                                 "experiments of the whole domain")
+            if sub.training:     # train_inputs are as passed to the constructor: unscaled, but already integer-coded
+                X_un = o2n.untransform(X_raw) if o2n is not None else X_raw
+            else:                # eval mode: BoTorch keeps the transformed inputs on the model
+                X_un = tf.untransform(X_raw) if tf is not None else X_raw
+            X_full = np.ascontiguousarray(X_un.detach().cpu().double().numpy())
+        d = X_full.shape[1]
+        # what dimension j of the CURRENT space is in the original layout: a column, or ("cat", start column, cardinality)
+        col_map = list(range(d))
+        in_off, in_scl = np.zeros(d), np.ones(d)
+        for t, tn in zip(chain, names):
             if tn == "FilterFeatures":
                 col_map = [col_map[int(i)] for i in t.feature_indices.tolist()]
-            elif tn == "Normalize":
-                idx = t.indices.tolist() if getattr(t, "indices", None) is not None else list(range(len(col_map)))
-                off = {col_map[i]: float(t.offset.view(-1)[j if t.offset.numel() > 1 else 0]) for j, i in enumerate(idx)}
-                scl = {col_map[i]: float(t.coefficient.view(-1)[j if t.coefficient.numel() > 1 else 0]) for j, i in enumerate(idx)}
-            elif tn in ("OneHotToNumeric",):
-                raise NotImplementedError("OneHotToNumeric + CategoricalKernel: rebuild with HammingKernelWithOneHots")
-            else:
-                raise NotImplementedError(f"input transform {tn} is outside the accelerated path")
-        # BoTorch stores the TRANSFORMED inputs on the model in eval mode; the untransformed ones are what BoFire passes
-        X_un = tf.untransform(X_raw) if (tf is not None and hasattr(tf, "untransform") and not sub.training) else X_raw
-        if X_full is None:
-            X_full = X_un.numpy()
-        d = X_full.shape[1]
-        octf = sub.outcome_transform
-        y_mean, y_std = float(octf.means.view(-1)[0]), float(octf.stdvs.view(-1)[0])
-        y = sub.train_targets.detach().cpu().double().view(-1).numpy() * y_std + y_mean
-        in_off, in_scl = np.zeros(d), np.ones(d)
-        if off:
-            for c, v in off.items():
-                in_off[c] = v
-            for c, v in scl.items():
-                in_scl[c] = v
-        specs.append(SingleTaskGPSpec(kernel=_kernel_from_gpytorch(sub.covar_module, d, col_map), y=y, in_offset=in_off,
+            elif tn in ("Normalize", "InputStandardize"):
+                idx = [int(i) for i in t.indices.tolist()] if getattr(t, "indices", None) is not None else list(range(len(col_map)))
+                offs = (t.offset if tn == "Normalize" else t.means).detach().cpu().double().reshape(-1)
+                cofs = (t.coefficient if tn == "Normalize" else t.stds).detach().cpu().double().reshape(-1)
+
+                def pick(v, j, i):   # statistics are kept over all columns of the space, over `indices` only, or as a scalar
+                    return float(v[i] if v.numel() == len(col_map) else (v[j] if v.numel() == len(idx) else v[0]))
+
+                for j, i in enumerate(idx):
+                    c = col_map[i]
+                    if isinstance(c, tuple):
+                        raise NotImplementedError("a scaler on integer-coded categorical dimensions is outside the accelerated path")
+                    in_off[c], in_scl[c] = pick(offs, j, i), pick(cofs, j, i)
+            else:   # OneHotToNumeric: numeric columns first, one integer code per one-hot block after them
+                cats = {int(s): int(c) for s, c in t.categorical_features.items()}
+                in_group = {s + k for s, c in cats.items() for k in range(c)}
+                for s in cats:
+                    if isinstance(col_map[s], tuple) or col_map[s:s + cats[s]] != list(range(col_map[s], col_map[s] + cats[s])):
+                        raise NotImplementedError("one-hot blocks must be contiguous columns")
+                col_map = [col_map[i] for i in range(len(col_map)) if i not in in_group] + \
+                          [("cat", col_map[s], c) for s, c in sorted(cats.items())]
+        octf = getattr(sub, "outcome_transform", None)
+        if octf is not None:
+            y_mean, y_std = float(octf.means.reshape(-1)[0]), float(octf.stdvs.reshape(-1)[0])
+        else:
+            y_mean, y_std = 0.0, 1.0
+        y = sub.train_targets.detach().cpu().double().reshape(-1).numpy() * y_std + y_mean
+        specs.append(SingleTaskGPSpec(kernel=_kernel_from_gpytorch(sub.covar_module, len(col_map), col_map), y=y, in_offset=in_off,
                                       in_scale=in_scl, mean_const=float(sub.mean_module.constant.detach().cpu()),
-                                      noise=float(sub.likelihood.noise.detach().cpu().view(-1)[0]), y_mean=y_mean, y_std=y_std))
+                                      noise=float(sub.likelihood.noise.detach().cpu().reshape(-1)[0]), y_mean=y_mean, y_std=y_std))
+    return X_full, specs
+
+
+def state_from_botorch_model(model, device=None, X_train=None):
+    """specs_from_botorch_model + factorisation on the device."""
+    from .model import DeviceGPState
+
+    X_full, specs = specs_from_botorch_model(model, X_train=X_train)
     return DeviceGPState(X_full, specs, device=device).factorize()

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libeverest_b200.so")
-SOURCES = ["kernels_eval.cu", "gemm.cu", "chol.cu", "acqf.cu", "grad.cu", "scalar_acqf.cu", "loghvi.cu", "sobol.cu", "mll.cu", "ozaki.cu", "capi.cu"]
+SOURCES = ["kernels_eval.cu", "gemm.cu", "chol.cu", "acqf.cu", "grad.cu", "scalar_acqf.cu", "loghvi.cu", "sobol.cu", "mll.cu", "ozaki.cu", "lbfgs.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread"]
 

@@ -15,6 +15,7 @@
 
 #include "acqf.cuh"
 #include "common.cuh"
+#include "lbfgs.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -58,6 +59,23 @@ struct DevBuf {
 };
 
 #define RC(expr) do { int _rc = (expr); if (_rc != BO_OK) return _rc; } while (0)
+
+// EVEREST_SETUP_TRACE=1: wall-clock checkpoints (stream-synchronised) of the set-up entry points on stderr
+struct SetupTrace {
+  const char* name; cudaStream_t s; bool on;
+  std::chrono::steady_clock::time_point t0;
+  SetupTrace(const char* n, cudaStream_t st) : name(n), s(st) {
+    static const bool enabled = getenv("EVEREST_SETUP_TRACE") != nullptr;
+    on = enabled;
+    if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[setup] %s: %s at %.3f ms\n", name, what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 struct PrepBuf {
   DevBuf Xs[BO_MAX_LEAVES], n2[BO_MAX_LEAVES], codes[BO_MAX_LEAVES], bits[BO_MAX_LEAVES], pc[BO_MAX_LEAVES];
@@ -145,6 +163,11 @@ struct bo_state {
   DevBuf wsOzFlags, wsOzXg, wsOzKxG, wsOzOutG;
   int* pin_count = nullptr;    // pinned: the guard's counter of flagged q-batches
   cudaEvent_t oz_event = nullptr;
+  DevBuf wsLbfgs, wsLbBounds, wsLbGrad;   // on-device multi-start refinement (lbfgs.cu)
+  DevBuf wsJointRoot, wsJointCov, wsJointDinv;   // joint posterior root / covariance of the pruning passes
+  PrepBuf jointPrep;
+  int* pin_lb = nullptr;                  // pinned: progress counters of bo_acqf_optimize
+  std::vector<cudaEvent_t> lb_events;
   double tau_relu = 1e-6, tau_max = 1e-2;
   DevBuf wsOzA;  // INT8 digit planes of K(X*,X) (all outputs)
   DevBuf wsOzScratch;  // integer slab of the two-pass INT8 GEMM (ozaki.cu), one per handle
@@ -195,6 +218,10 @@ extern "C" void bo_state_destroy(bo_state* st) {
   for (DevBuf* b : bs) b->release();
   if (st->pin_count) cudaFreeHost(st->pin_count);
   if (st->oz_event) cudaEventDestroy(st->oz_event);
+  st->wsLbfgs.release(); st->wsLbBounds.release(); st->wsLbGrad.release();
+  st->wsJointRoot.release(); st->wsJointCov.release(); st->wsJointDinv.release(); st->jointPrep.release();
+  if (st->pin_lb) cudaFreeHost(st->pin_lb);
+  for (auto& e : st->lb_events) cudaEventDestroy(e);
   if (st->pin_in) cudaFreeHost(st->pin_in);
   if (st->pin_out) cudaFreeHost(st->pin_out);
   for (auto& e : st->copy_events) cudaEventDestroy(e);
@@ -494,11 +521,8 @@ static int joint_root(bo_state* st, int m, const double* X_dev, int n, int ldn, 
   RC(launch_crosscov(o.md, *pd, *pd, false, n, C, ldn, true, s, &st->lc));
   RC(launch_gemm_nt(n, n, st->N, -1.0, Vdst, ldk, Vdst, ldk, 1.0, C, ldn, false, s, &st->lc));
   RC(launch_scale_matrix(C, ldn, n, n, o.md.y_std * o.md.y_std, s, &st->lc));
-  DevBuf dinv_local;
-  DevBuf& dinv = dinv_keep ? *dinv_keep : dinv_local;
-  int rc = psd_safe_chol(st, C, rootbuf.as<double>(), ldn, n, dinv, info, jit, s);
-  dinv_local.release();
-  return rc;
+  DevBuf& dinv = dinv_keep ? *dinv_keep : st->wsJointDinv;
+  return psd_safe_chol(st, C, rootbuf.as<double>(), ldn, n, dinv, info, jit, s);
 }
 
 extern "C" int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, const double* z_dev, int32_t S,
@@ -510,22 +534,27 @@ extern "C" int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, con
   RC(fill_objd(&od, obj, n_obj, cons, n_cons, 0, st->M));
   st->baseline_f_valid = false;   // wsF is reused below
   const int M = st->M, ldn = round_up(n, 16), ldk = st->ldk;
+  SetupTrace tr("prune_counts", s);
   RC(st->wsMean.ensure((size_t)n * M * 8));
   RC(st->wsZM.ensure((size_t)M * S * ldn * 8, true));
   RC(st->wsF.ensure((size_t)M * S * ldn * 8));
   RC(st->wsV.ensure((size_t)n * ldk * 8, true));
+  tr.mark("workspaces");
   RC(launch_transpose_base_samples(z_dev, S, n, M, nullptr, st->wsZM.as<double>(), ldn, s, &st->lc));
-  DevBuf root, cov;
-  PrepBuf pb; PrepD pd;
+  // persistent temporaries of the handle: allocating and freeing 2 x N^2 doubles per call cost up to 0.5 s of cudaFree
+  DevBuf& root = st->wsJointRoot; DevBuf& cov = st->wsJointCov;
+  PrepBuf& pb = st->jointPrep; PrepD pd;
   int rcode = BO_OK;
   for (int m = 0; m < M && rcode == BO_OK; ++m) {
     int inf = 0; double jit = 0;
     rcode = joint_root(st, m, X_dev, n, ldn, pb, &pd, st->wsMean.as<double>(), root, cov, st->wsV.as<double>(), &inf, &jit, s);
+    tr.mark("joint_root");
     if (info) info[m] = inf;
     if (rcode == BO_OK && inf != 0) { bo_set_error("posterior covariance at the baseline not p.d. (output %d)", m); rcode = BO_ERR_NOT_PSD; }
     if (rcode == BO_OK)
       rcode = launch_gemm_nt(S, n, n, 1.0, st->wsZM.as<double>() + (size_t)m * S * ldn, ldn, root.as<double>(), ldn, 0.0,
                              st->wsF.as<double>() + (size_t)m * S * ldn, ldn, false, s, &st->lc);
+    tr.mark("sample gemm");
   }
   if (rcode == BO_OK) rcode = st->wsObj.ensure((size_t)S * n * n_obj * 8);
   if (rcode == BO_OK) rcode = st->wsFeas.ensure((size_t)S * n);
@@ -541,7 +570,7 @@ extern "C" int bo_prune_counts(bo_state* st, const double* X_dev, int32_t n, con
                          nullptr, counts_dev, s, &st->lc);
   }
   cudaStreamSynchronize(s);
-  root.release(); cov.release(); pb.release();
+  tr.mark("objective + front");
   return rcode;
 }
 
@@ -647,7 +676,9 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
   st->cells_shared = 0;
   RC(st->ref_dev.ensure(BO_MAX_OBJECTIVES * 8));
   CUDA_CHECK_RET(cudaMemcpyAsync(st->ref_dev.p, ref_point, n_obj * 8, cudaMemcpyHostToDevice, s));
+  SetupTrace tr("nehvi_prepare", s);
   RC(prepare_baseline(st, Xb_dev, nb, zb_dev, S, info, s));
+  tr.mark("prepare_baseline");
   const int ldlb = st->ldlb;
   RC(st->obj_b.ensure((size_t)S * std::max(nb, 1) * n_obj * 8));
   RC(st->samples_b.ensure((size_t)S * std::max(nb, 1) * M * 8));
@@ -655,6 +686,7 @@ extern "C" int bo_nehvi_prepare(bo_state* st, const double* Xb_dev, int32_t n_b,
   RC(launch_baseline_objective(st->wsF.as<double>(), ldlb, S, nb, M, st->mean_b.as<double>(), st->od, st->obj_b.as<double>(),
                                st->wsFeas.as<unsigned char>(), st->samples_b.as<double>(), s, &st->lc));
   RC(build_cells(st, st->obj_b.as<double>(), st->wsFeas.as<unsigned char>(), nb, S, n_obj, &st->max_cells, s));
+  tr.mark("cells");
   if (max_cells) *max_cells = st->max_cells;
   st->acqf_kind = 1;
   return BO_OK;
@@ -760,8 +792,9 @@ extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t
   RC(st->wsF.ensure((size_t)M * S * ldn * 8));
   RC(st->wsV.ensure((size_t)n * ldk * 8, true));
   RC(launch_transpose_base_samples(z_dev, S, n, M, nullptr, st->wsZM.as<double>(), ldn, s, &st->lc));
-  DevBuf root, cov;
-  PrepBuf pb; PrepD pd;
+  // persistent temporaries of the handle: allocating and freeing 2 x N^2 doubles per call cost up to 0.5 s of cudaFree
+  DevBuf& root = st->wsJointRoot; DevBuf& cov = st->wsJointCov;
+  PrepBuf& pb = st->jointPrep; PrepD pd;
   int rcode = BO_OK;
   for (int m = 0; m < M && rcode == BO_OK; ++m) {
     int inf = 0; double jit = 0;
@@ -778,7 +811,6 @@ extern "C" int bo_prune_counts_scalar(bo_state* st, const double* X_dev, int32_t
                                  nullptr, s, &st->lc);
   }
   cudaStreamSynchronize(s);
-  root.release(); cov.release(); pb.release();
   return rcode;
 }
 
@@ -1198,6 +1230,78 @@ extern "C" int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32
                                         double* out_dev, double* dX_dev, int32_t* info_dev, void* stream) {
   if (!dX_dev) { bo_set_error("forward_backward: dX_dev is NULL"); return BO_ERR_INVALID; }
   return acqf_run(st, X_dev, b, q, zq_dev, out_dev, dX_dev, info_dev, stream);
+}
+
+extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int32_t q_free, const double* lb,
+                                const double* ub, const double* zq_dev, int32_t maxiter, int32_t history, double pgtol,
+                                double ftol, double* out_dev, int32_t* stats, void* stream) {
+  if (!st || !X_dev || !lb || !ub || !out_dev) { bo_set_error("optimize: null argument"); return BO_ERR_INVALID; }
+  if (r < 1 || q_free < 1 || q_free > q_tot || q_tot > BO_MAX_Q) { bo_set_error("optimize: bad r=%d / q_free=%d / q_tot=%d", r, q_free, q_tot); return BO_ERR_INVALID; }
+  if (maxiter < 1 || history < 1 || history > LB_MAX_HIST) { bo_set_error("optimize: maxiter >= 1, 1 <= history <= %d", LB_MAX_HIST); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = st->d, n = q_free * d;
+  for (int j = 0; j < d; ++j)
+    if (!(lb[j] <= ub[j])) { bo_set_error("optimize: lb[%d] > ub[%d]", j, j); return BO_ERR_INVALID; }
+  RC(st->wsLbfgs.ensure(lbfgs_ws_bytes(r, n, history)));
+  RC(st->wsLbBounds.ensure((size_t)2 * d * 8));
+  RC(st->wsLbGrad.ensure((size_t)r * q_tot * d * 8));
+  if (!st->pin_lb) CUDA_CHECK_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->pin_lb), 64 * sizeof(int), cudaHostAllocDefault));
+  while (st->lb_events.size() < 2) {
+    cudaEvent_t e;
+    CUDA_CHECK_RET(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    st->lb_events.push_back(e);
+  }
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->wsLbBounds.p, lb, (size_t)d * 8, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK_RET(cudaMemcpyAsync(st->wsLbBounds.as<double>() + d, ub, (size_t)d * 8, cudaMemcpyHostToDevice, s));
+  LbArgs a;
+  a.q_tot = q_tot; a.q_free = q_free; a.d = d; a.hist = history; a.maxiter = maxiter; a.pgtol = pgtol; a.ftol = ftol;
+  a.lb = st->wsLbBounds.as<double>(); a.ub = a.lb + d;
+  a.X = X_dev; a.dX = st->wsLbGrad.as<double>(); a.vals = out_dev;
+  lbfgs_carve(a, st->wsLbfgs.p, r, n, history);
+  CUDA_CHECK_RET(cudaMemcpyAsync(a.n_running, &r, sizeof(int), cudaMemcpyHostToDevice, s));   // pageable 4-byte copy: staged at once
+  // every evaluation: the forward + adjoint chain of the r q-batches, then one state-machine step of every restart
+  RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream));
+  RC(launch_lbfgs_step(a, r, true, s, &st->lc));
+  // L-BFGS-B allows ~1.25 evaluations per iteration on average (scipy: maxfun = 15000 for maxiter = 15000); the budget here
+  // is 2 per iteration plus the 20 trials a failing line search may take
+  const long long max_evals = 2ll * maxiter + 20;
+  const int check_every = 8;
+  long long n_eval = 1;
+  int slot = 0, pending[2] = {0, 0};
+  bool done = false;
+  while (!done && n_eval < max_evals) {
+    for (int k = 0; k < check_every && n_eval < max_evals; ++k, ++n_eval) {
+      RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream));
+      RC(launch_lbfgs_step(a, r, false, s, &st->lc));
+    }
+    // progress counter of THIS batch goes to the host asynchronously; the one of the PREVIOUS batch is inspected now, so the
+    // launch queue never runs dry while the host waits
+    CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_lb + slot, a.n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK_RET(cudaEventRecord(st->lb_events[slot], s));
+    pending[slot] = 1;
+    const int prev = slot ^ 1;
+    if (pending[prev]) {
+      CUDA_CHECK_RET(cudaEventSynchronize(st->lb_events[prev]));
+      pending[prev] = 0;
+      if (st->pin_lb[prev] <= 0) done = true;
+    }
+    slot ^= 1;
+  }
+  RC(launch_lbfgs_finish(a, r, s, &st->lc));
+  // values at the returned points (a restart that stopped on a rejected trial returns its last accepted point)
+  RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, nullptr, nullptr, stream));
+  if (stats) {
+    std::vector<LbScalars> sc(r);
+    CUDA_CHECK_RET(cudaMemcpyAsync(sc.data(), a.sc, (size_t)r * sizeof(LbScalars), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));
+    stats[0] = (int)n_eval + 1; stats[1] = 0; stats[2] = 0; stats[3] = 0;
+    for (int i = 0; i < r; ++i) {
+      stats[1] = std::max(stats[1], sc[i].n_iter);
+      if (sc[i].status == 1 || sc[i].status == 2) stats[2]++;
+      if (sc[i].status == 4 || sc[i].status == 6) stats[3]++;
+    }
+  }
+  return BO_OK;
 }
 
 extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,

@@ -57,6 +57,11 @@ class GammaPrior:
         return (self.concentration - 1.0) / x - self.rate
 
     def start(self):
+        # [UPSTREAM] BoTorch initialises a Gamma-distributed hyper-parameter at the prior MODE where it exists (e.g. the
+        # GammaPrior(1.1, 0.05) noise level of MixedSingleTaskGP starts at 2.0, not at its mean of 22, from where the
+        # marginal likelihood is flat and the fit ends in the all-noise solution)
+        if self.concentration > 1.0:
+            return (self.concentration - 1.0) / self.rate
         return self.concentration / self.rate
 
 

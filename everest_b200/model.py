@@ -200,9 +200,9 @@ class DeviceGPState:
         return ms.value, cnt
 
     @classmethod
-    def from_botorch(cls, model, device=None):  # pragma: no cover - needs botorch, absent from this image
-        """Rebuild the device state from a fitted BoTorch ModelListGP / SingleTaskGP (state_dict + train data),
-        the hand-over point of BotorchSurrogates.compatibilize.  See INTEGRATION.md."""
+    def from_botorch(cls, model, device=None, X_train=None):
+        """Rebuild the device state from a fitted BoTorch ModelListGP / SingleTaskGP / MixedSingleTaskGP (hyper-parameters,
+        transforms, train data), the hand-over point of BotorchSurrogates.compatibilize.  See INTEGRATION.md."""
         from .bofire_adapter import state_from_botorch_model
 
-        return state_from_botorch_model(model, device=device)
+        return state_from_botorch_model(model, device=device, X_train=X_train)

@@ -429,6 +429,30 @@ def gen_candidates_scipy(initial_conditions: torch.Tensor, acquisition_function,
     return Xf, vals, {"nit": int(res.nit), "n_acqf_evals": state["n_eval"] + r, "message": str(res.message)}
 
 
+def gen_candidates_device(initial_conditions: torch.Tensor, acquisition_function, lower_bounds, upper_bounds,
+                          fixed_features: Optional[Dict[int, float]] = None, options: Optional[dict] = None):
+    """The box-constrained case of gen_candidates_scipy without the host in the loop: the restarts are
+    refined by bo_acqf_optimize (csrc/lbfgs.cu) -- one projected L-BFGS per restart on the device, scipy's L-BFGS-B
+    defaults for memory and stopping rules.  BoTorch hands scipy the SUM over the restarts as one problem; the sum is
+    separable, so the restarts are optimised independently here (own curvature memory, own step length, own stopping
+    test) and reach the local maxima the joint run converges to.  Fixed features are columns with lb == ub.
+    Returns (candidates [r, q, d] CPU, acq values [r] CPU, info) like gen_candidates_scipy."""
+    options = options or {}
+    X0 = torch.as_tensor(initial_conditions, dtype=torch.double).cpu().clone()
+    d = X0.shape[-1]
+    lb = torch.as_tensor(lower_bounds, dtype=torch.double).cpu().expand(d).clone()
+    ub = torch.as_tensor(upper_bounds, dtype=torch.double).cpu().expand(d).clone()
+    X0 = apply_fixed_features(X0, fixed_features)
+    for j, v in (fixed_features or {}).items():
+        lb[j] = ub[j] = float(v)
+    X0 = torch.minimum(torch.maximum(X0, lb), ub)
+    X, vals, info = acquisition_function.optimize(X0, lb, ub, maxiter=int(options.get("maxiter", 2000)),
+                                                  history=int(options.get("history", 10)), pgtol=float(options.get("pgtol", 1e-5)),
+                                                  ftol=float(options.get("ftol", 2.220446049250313e-09)))
+    info = dict(info, message="device L-BFGS", optimizer="on-device batched projected L-BFGS (bo_acqf_optimize)")
+    return X.cpu(), vals.cpu(), info
+
+
 def linear_feasibility(X: torch.Tensor, inequality_constraints, equality_constraints, rel_tol: float = 1e-6) -> np.ndarray:
     """[r] bool: the q-batches X[r, q, d] satisfy the linear constraints up to a RELATIVE slack -- rel_tol times
     max(1, |rhs|, ||row||_1 max|x|) per constraint row, so that e.g. a mixture constraint "sums to 100" is not held to
@@ -456,10 +480,18 @@ def refine_restarts(acq_function, X_ic: torch.Tensor, Y_ic: torch.Tensor, bounds
     import logging
 
     q = X_ic.shape[1]
-    X_ref, Y_ref, info = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
-                                              options=options, inequality_constraints=inequality_constraints,
-                                              equality_constraints=equality_constraints,
-                                              nonlinear_inequality_constraints=nonlinear_inequality_constraints)
+    constrained = bool(inequality_constraints or equality_constraints or nonlinear_inequality_constraints)
+    which = (options or {}).get("optimizer", "device")
+    if which not in ("device", "scipy"):
+        raise ValueError("options['optimizer'] must be 'device' or 'scipy'")
+    if not constrained and which == "device" and hasattr(acq_function, "optimize") and (options or {}).get("gradient", "analytic") == "analytic":
+        X_ref, Y_ref, info = gen_candidates_device(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
+                                                   options=options)
+    else:
+        X_ref, Y_ref, info = gen_candidates_scipy(X_ic, acq_function, bounds[0], bounds[1], fixed_features=fixed_features,
+                                                  options=options, inequality_constraints=inequality_constraints,
+                                                  equality_constraints=equality_constraints,
+                                                  nonlinear_inequality_constraints=nonlinear_inequality_constraints)
     if nonlinear_inequality_constraints:
         ok_n = nonlinear_constraints_satisfied(X_ref, nonlinear_inequality_constraints)
         Y_ref = torch.where(ok_n, Y_ref, torch.full_like(Y_ref, -float("inf")))

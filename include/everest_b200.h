@@ -209,6 +209,22 @@ int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
 int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
                              double* out_dev, double* dX_dev, int32_t* info_dev, void* stream);
 
+/* On-device multi-start refinement: replaces the host loop of [UPSTREAM] botorch.generation.gen_candidates_scipy that
+ * BotorchStrategy._optimize_acqf_continuous drives through optimize_acqf (botorch.py:384-405) for the box-constrained case
+ * (bounds + fixed features; linear / nonlinear constraints stay on the host SLSQP path).  X_dev [r, q_tot, d] holds the r
+ * restarts on entry and the refined restarts on return; the leading q_free points of every q-batch are optimised, the
+ * trailing q_tot - q_free rows (pending points of the concatenating acquisition functions) are constants.  lb / ub [d] are
+ * HOST arrays (lb[j] == ub[j] fixes column j).  Each restart runs its own projected L-BFGS (`history` curvature pairs,
+ * Armijo line search on the projected arc) on f = -acquisition value with the analytic gradient of
+ * bo_acqf_forward_backward; stopping rules are L-BFGS-B's (projected-gradient inf-norm <= pgtol, relative decrease
+ * <= ftol, maxiter iterations).  out_dev [r] receives the acquisition values at the returned points.  stats (may be
+ * NULL, HOST, 4 ints): evaluations of the acquisition function launched, max iterations over the restarts, restarts
+ * converged by pgtol / ftol, restarts stopped by maxiter or the evaluation budget.  Nothing crosses PCIe inside the loop
+ * but one 4-byte progress counter every few evaluations. */
+int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int32_t q_free, const double* lb,
+                     const double* ub, const double* zq_dev, int32_t maxiter, int32_t history, double pgtol, double ftol,
+                     double* out_dev, int32_t* stats, void* stream);
+
 /* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values. */
 int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
                          double* out_host, void* stream);

@@ -531,3 +531,115 @@ def test_oracle_best_feasible_objective_and_constrained_pruning():
     a = O.QScalarOracle(gp, "qLogNEI", spec, X, mc_samples=8, seed=2, prune_samples=64, constraints=cons)
     # no pruned-in point may be infeasible in every pruning sample: the survivors are feasible somewhere
     assert len(a.prune_idx) >= 1 and bool(torch.isfinite(a.best_f_s).all())
+
+
+def test_specs_from_botorch_model_literal_mixed_single_task_gp_with_stand_ins():
+    """The attribute walk of bofire_adapter.specs_from_botorch_model on duck-typed stand-ins of the objects BoFire's literal
+    MixedSingleTaskGPSurrogate builds (mixed_single_task_gp.py:46-112): Chained(Normalize on the ordinal columns,
+    OneHotToNumeric) + Scale(K_c + Scale(CategoricalKernel)) + Scale(K_c * CategoricalKernel) on [ordinal..., integer codes].
+    The mapped spec must evaluate, on the ONE-HOT layout, to the same Gram matrix as the stand-in tree on the coded layout."""
+    from everest_b200.bofire_adapter import specs_from_botorch_model
+
+    def T(v):
+        return torch.as_tensor(v, dtype=torch.double)
+
+    class _K:
+        active_dims = None
+
+    def mk(name, **kw):
+        return type(name, (_K,), {})().__class__, kw
+
+    def kern(name, **kw):
+        obj = type(name, (_K,), {})()
+        for k, v in kw.items():
+            setattr(obj, k, v)
+        return obj
+
+    g = torch.Generator().manual_seed(0)
+    N, n_ord = 9, 2
+    cats = {2: 3, 5: 2}                       # one-hot blocks of the BoFire layout [a, b | c0 c1 c2 | e0 e1]
+    codes = torch.stack([torch.randint(0, 3, (N,), generator=g), torch.randint(0, 2, (N,), generator=g)], dim=1)
+    Xo = torch.rand(N, n_ord, dtype=torch.double, generator=g) * T([4.0, 2.0]) + T([-1.0, 3.0])
+    onehot = torch.cat([torch.nn.functional.one_hot(codes[:, 0], 3), torch.nn.functional.one_hot(codes[:, 1], 2)], dim=1).double()
+    X_bofire = torch.cat([Xo, onehot], dim=1)                         # [N, 7]
+    X_coded = torch.cat([Xo, codes.double()], dim=1)                 # what MixedSingleTaskGP is constructed with
+
+    class Normalize:
+        indices = torch.tensor([0, 1])
+        offset = T([[-1.0, 3.0]])
+        coefficient = T([[4.0, 2.0]])
+
+    class OneHotToNumeric:
+        dim = 7
+        categorical_features = cats
+
+        def untransform(self, X):
+            return torch.cat([X[:, :n_ord], torch.nn.functional.one_hot(X[:, n_ord].long(), 3).double(),
+                              torch.nn.functional.one_hot(X[:, n_ord + 1].long(), 2).double()], dim=1)
+
+    class Chain(dict):
+        pass
+
+    ls_c1, ls_c2, ls_h1, ls_h2 = T([[0.7, 1.3]]), T([[0.4, 0.9]]), T([[0.8, 2.0]]), T([[1.5, 0.6]])
+    cont1 = kern("MaternKernel", active_dims=torch.tensor([0, 1]), lengthscale=ls_c1, nu=2.5)
+    cont2 = kern("MaternKernel", active_dims=torch.tensor([0, 1]), lengthscale=ls_c2, nu=2.5)
+    cat1 = kern("CategoricalKernel", active_dims=torch.tensor([2, 3]), lengthscale=ls_h1)
+    cat2 = kern("CategoricalKernel", active_dims=torch.tensor([2, 3]), lengthscale=ls_h2)
+    tree = kern("AdditiveKernel", kernels=[
+        kern("ScaleKernel", outputscale=T(1.7), base_kernel=kern("AdditiveKernel", kernels=[cont1, kern("ScaleKernel", outputscale=T(0.6), base_kernel=cat1)])),
+        kern("ScaleKernel", outputscale=T(0.9), base_kernel=kern("ProductKernel", kernels=[cont2, cat2]))])
+
+    class Const:
+        constant = T(0.25)
+
+    class Lik:
+        noise = T([3e-3])
+
+    class Std:
+        means, stdvs = T([[2.0]]), T([[1.5]])
+
+    class Model:
+        training = True
+        input_transform = Chain(tf1=Normalize(), tf2=OneHotToNumeric())
+        train_inputs = (X_coded,)
+        train_targets = T(np.linspace(-1, 1, N))
+        covar_module = tree
+        mean_module = Const()
+        likelihood = Lik()
+        outcome_transform = Std()
+
+    X_full, (spec,) = specs_from_botorch_model(Model())
+    assert np.array_equal(X_full, X_bofire.numpy())
+    assert spec.in_offset.tolist() == [-1.0, 3.0, 0, 0, 0, 0, 0] and spec.in_scale.tolist() == [4.0, 2.0, 1, 1, 1, 1, 1]
+    assert spec.noise == 3e-3 and spec.mean_const == 0.25 and (spec.y_mean, spec.y_std) == (2.0, 1.5)
+    assert np.allclose(spec.y, np.linspace(-1, 1, N) * 1.5 + 2.0)
+    flat = K.flatten(spec.kernel)
+    assert [type(lf).__name__ for lf in flat.leaves] == ["MaternKernel", "HammingDistanceKernel", "MaternKernel", "HammingDistanceKernel"]
+    assert flat.leaves[1].categorical_features == {2: 3, 5: 2} and list(flat.leaves[1].lengthscale) == [0.8, 2.0]
+    # Gram matrix: oracle evaluation of the mapped spec on the normalised one-hot layout vs the coded formula by hand
+    Xn = (X_bofire - T(spec.in_offset)) / T(spec.in_scale)
+    G = O.eval_kernel(P.kernel_to_oracle(spec.kernel), Xn, Xn, Xn.mean(dim=0), same=True)
+
+    def matern(ls):
+        z = Xn[:, :2] / ls
+        r = torch.cdist(z, z)
+        return (1 + 5 ** 0.5 * r + 5.0 / 3.0 * r ** 2) * torch.exp(-(5 ** 0.5) * r)
+
+    def catk(ls):
+        delta = (codes.unsqueeze(1) != codes.unsqueeze(0)).double()
+        return torch.exp(-(delta / ls).mean(-1))
+
+    G_ref = 1.7 * (matern(ls_c1) + 0.6 * catk(ls_h1)) + 0.9 * (matern(ls_c2) * catk(ls_h2))
+    assert torch.allclose(G, G_ref, rtol=1e-10, atol=1e-12)
+    # FilterFeatures without the full training matrix cannot be handed over silently
+    class FilterFeatures:
+        feature_indices = torch.tensor([0, 1])
+
+    class Sub(Model):
+        input_transform = Chain(tcompatibilize=FilterFeatures(), tf2=Normalize())
+        covar_module = cont1
+
+    with pytest.raises(ValueError):
+        specs_from_botorch_model(Sub())
+    Xf, (s2,) = specs_from_botorch_model(Sub(), X_train=X_bofire)
+    assert list(s2.kernel.active_dims) == [0, 1] and s2.in_scale.tolist()[:2] == [4.0, 2.0] and Xf.shape == (N, 7)
