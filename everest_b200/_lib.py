@@ -88,6 +88,10 @@ SYMBOLS = {
                                    C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "bo_acqf_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "bo_pack_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    "bo_pack_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "bo_acqf_forward_host_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "bo_pareto_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bo_hypervolume": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_void_p]),
     "bo_mll_forward_backward": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32,

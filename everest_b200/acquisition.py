@@ -197,6 +197,48 @@ class _DeviceAcquisition:
         return out
 
 
+    # -- packed wire format (fingerprint columns as bits) ---------------------------------------------------------
+    def pack_layout(self):
+        """(dense_cols, bit_cols): which columns of a candidate row travel as float64 and which as bits (bo_pack_layout)."""
+        nd, nb = C.c_int32(0), C.c_int32(0)
+        lib, h = self.model.lib, self.model.handle
+        L.check(lib.bo_pack_layout(h, C.byref(nd), C.byref(nb), None, None))
+        dc = np.zeros(max(nd.value, 1), dtype=np.int32)
+        bc = np.zeros(max(nb.value, 1), dtype=np.int32)
+        L.check(lib.bo_pack_layout(h, C.byref(nd), C.byref(nb), dc.ctypes.data_as(C.c_void_p), bc.ctypes.data_as(C.c_void_p)))
+        return dc[: nd.value], bc[: nb.value]
+
+    def pack_rows(self, X: np.ndarray):
+        """X [..., d] float64 -> (dense [rows, n_dense] float64, bits [rows, ceil(n_bits / 64)] uint64) with the host packer of
+        the library (bo_pack_rows_host); raises ValueError when a fingerprint column holds anything but 0 / 1."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.model.d)
+        dc, bc = self.pack_layout()
+        dense = np.empty((X.shape[0], len(dc)), dtype=np.float64)
+        bits = np.empty((X.shape[0], (len(bc) + 63) // 64), dtype=np.uint64)
+        L.check(self.model.lib.bo_pack_rows_host(self.model.handle, X.ctypes.data_as(C.c_void_p), X.shape[0],
+                                                 dense.ctypes.data_as(C.c_void_p), bits.ctypes.data_as(C.c_void_p)))
+        return dense, bits
+
+    def forward_host_packed(self, dense: np.ndarray, bits: np.ndarray, q: int = 1) -> np.ndarray:
+        """forward over candidates kept in the packed wire format (bo_acqf_forward_host_packed): rows = b * q."""
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        rows = dense.shape[0] if dense.size else bits.shape[0]
+        if rows % q or (bits.size and bits.shape[0] != rows):
+            raise ValueError("dense / bits must hold b * q rows each")
+        if self._PENDING_CONCAT and self.X_pending is not None and self.X_pending.shape[0] > 0:
+            raise NotImplementedError("pending points with the packed wire format: pack them into the rows of every q-batch")
+        self._check_active()
+        b = rows // q
+        out = np.empty(b, dtype=np.float64)
+        zq = self.base_samples_q(q)
+        with torch.cuda.device(self.model.device):
+            L.check(self.model.lib.bo_acqf_forward_host_packed(self.model.handle, dense.ctypes.data_as(C.c_void_p),
+                                                               bits.ctypes.data_as(C.c_void_p), b, q, _dev_ptr(zq),
+                                                               out.ctypes.data_as(C.c_void_p), _stream()))
+        return out
+
+
 class _AcqfAutograd(torch.autograd.Function):
     """torch.autograd bridge: forward = bo_acqf_forward_backward, backward = chain rule with the stored dX."""
 

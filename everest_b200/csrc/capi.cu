@@ -129,6 +129,8 @@ struct OutputH {
   // per-forward query prep
   PrepBuf q_prep;
   PrepD q_prepd;
+  // host copies of every leaf's columns (Hamming: start column + cardinality of each group): wire-format layout
+  std::vector<int> leaf_cols[BO_MAX_LEAVES], leaf_card[BO_MAX_LEAVES];
 };
 
 struct TimingRec { std::string name; cudaEvent_t a, b; };
@@ -177,6 +179,10 @@ struct bo_state {
   int cells_shared = 0;
   // host staging for the HOST-buffer entry point
   void* pin_in = nullptr; size_t pin_in_bytes = 0;
+  // packed wire format of the host entry points: fingerprint columns as bits
+  bool pack_ready = false, pack_src_ready = false;
+  std::vector<int> pack_bit_cols, pack_dense_cols;
+  DevBuf stage_pk, pack_src;
   void* pin_out = nullptr; size_t pin_out_bytes = 0;
   DevBuf stage_in, stage_out;
   cudaStream_t copy_stream = nullptr;
@@ -214,7 +220,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
                   &st->wsZqT, &st->wsTmp, &st->wsInfo, &st->wsCov, &st->wsMean, &st->wsF, &st->wsZM, &st->wsObj,
                   &st->wsFeas, &st->wsFront, &st->wsCounts, &st->wsJit, &st->wsPart, &st->zbT, &st->cell_lo,
                   &st->cell_up, &st->ncells, &st->front_idx, &st->wsGramPart, &st->wsObjW, &st->zbM, &st->wsBL, &st->wsFp, &st->wsPartial, &st->ref_dev, &st->mean_b, &st->obj_b, &st->samples_b,
-                  &st->stage_in, &st->stage_out, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA, &st->wsOzFlags, &st->wsOzXg, &st->wsOzKxG, &st->wsOzOutG, &st->wsOzScratch};
+                  &st->stage_in, &st->stage_out, &st->stage_pk, &st->pack_src, &st->wsDF, &st->wsDRoot, &st->wsDMu, &st->wsEG, &st->wsEW, &st->wsEmu, &st->wsU, &st->best_f_s, &st->wsOzA, &st->wsOzFlags, &st->wsOzXg, &st->wsOzKxG, &st->wsOzOutG, &st->wsOzScratch};
   for (DevBuf* b : bs) b->release();
   if (st->pin_count) cudaFreeHost(st->pin_count);
   if (st->oz_event) cudaEventDestroy(st->oz_event);
@@ -288,6 +294,8 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
         if (kl.dims[k] < 0 || kl.dims[k] + width > d) { bo_set_error("leaf %d: column out of range", l); bo_state_destroy(st); return BO_ERR_INVALID; }
       }
       std::vector<int> col(kl.dims, kl.dims + kl.n_dims);
+      o.leaf_cols[l] = col;
+      if (kl.kind == BO_LEAF_HAMMING) o.leaf_card[l].assign(kl.cardinality, kl.cardinality + kl.n_dims);
       void* p;
       rc = upload(&p, col.data(), col.size() * sizeof(int), o.owned); if (rc) { bo_state_destroy(st); return rc; }
       L.col = (const int*)p;
@@ -1304,17 +1312,120 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
   return BO_OK;
 }
 
-extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
-                                    double* out_host, void* stream) {
+// ---- HOST-buffer entry points -----------------------------------------------------------------------------------
+// Columns read ONLY by Tanimoto leaves hold 0/1 fingerprints (create() checks the training rows): they cross PCIe as bits.
+// A candidate row of BASELINE config 5 is 2060 float64 columns = 16.5 KB; packed it is 12 doubles + 32 words = 352 bytes.
+enum HostMode { HOST_DENSE = 0, HOST_PACK = 1, HOST_PREPACKED = 2 };
+
+static void pack_layout_init(bo_state* st) {
+  if (st->pack_ready) return;
+  const int d = st->d;
+  std::vector<char> tani(d, 0), other(d, 0);
+  for (int m = 0; m < st->M; ++m) {
+    const OutputH& o = st->out[m];
+    for (int l = 0; l < o.md.n_leaves; ++l) {
+      const std::vector<int>& cols = o.leaf_cols[l];
+      const int kind = o.md.leaf[l].kind;
+      for (size_t k = 0; k < cols.size(); ++k) {
+        if (kind == BO_LEAF_TANIMOTO) tani[cols[k]] = 1;
+        else if (kind == BO_LEAF_HAMMING) { for (int j = 0; j < o.leaf_card[l][k]; ++j) other[cols[k] + j] = 1; }
+        else other[cols[k]] = 1;
+      }
+    }
+  }
+  st->pack_bit_cols.clear(); st->pack_dense_cols.clear();
+  for (int c = 0; c < d; ++c) {
+    if (tani[c] && !other[c]) st->pack_bit_cols.push_back(c);
+    else st->pack_dense_cols.push_back(c);
+  }
+  st->pack_ready = true;
+}
+
+extern "C" int bo_pack_layout(bo_state* st, int32_t* n_dense, int32_t* n_bits, int32_t* dense_cols, int32_t* bit_cols) {
+  if (!st || !n_dense || !n_bits) { bo_set_error("pack_layout: null argument"); return BO_ERR_INVALID; }
+  pack_layout_init(st);
+  *n_dense = (int32_t)st->pack_dense_cols.size();
+  *n_bits = (int32_t)st->pack_bit_cols.size();
+  if (dense_cols) std::copy(st->pack_dense_cols.begin(), st->pack_dense_cols.end(), dense_cols);
+  if (bit_cols) std::copy(st->pack_bit_cols.begin(), st->pack_bit_cols.end(), bit_cols);
+  return BO_OK;
+}
+
+// rows [r0, r1) of X [*, d] -> dense [*, n_dense] doubles and bits [*, W] words (bit k of a row = column bit_cols[k]);
+// returns false if a fingerprint column holds something other than 0 / 1
+static bool pack_rows(const bo_state* st, const double* X, size_t r0, size_t r1, double* dense, unsigned long long* bits) {
+  const int d = st->d, nd = (int)st->pack_dense_cols.size(), nbits = (int)st->pack_bit_cols.size(), W = (nbits + 63) / 64;
+  const int* dc = st->pack_dense_cols.data();
+  const int* bc = st->pack_bit_cols.data();
+  const bool contiguous = nbits > 0 && bc[nbits - 1] - bc[0] == nbits - 1;
+  bool ok = true;
+  for (size_t r = r0; r < r1; ++r) {
+    const double* x = X + r * d;
+    double* dr = dense + r * nd;
+    for (int k = 0; k < nd; ++k) dr[k] = x[dc[k]];
+    unsigned long long* br = bits + r * W;
+    if (contiguous) {
+      const double* xb = x + bc[0];
+      for (int w = 0; w < W; ++w) {
+        const int n = std::min(64, nbits - w * 64);
+        unsigned long long word = 0;
+        for (int t = 0; t < n; ++t) {
+          const double v = xb[w * 64 + t];
+          word |= (unsigned long long)(v != 0.0) << t;
+          ok &= (v == 0.0) | (v == 1.0);
+        }
+        br[w] = word;
+      }
+    } else {
+      for (int w = 0; w < W; ++w) {
+        const int n = std::min(64, nbits - w * 64);
+        unsigned long long word = 0;
+        for (int t = 0; t < n; ++t) {
+          const double v = x[bc[w * 64 + t]];
+          word |= (unsigned long long)(v != 0.0) << t;
+          ok &= (v == 0.0) | (v == 1.0);
+        }
+        br[w] = word;
+      }
+    }
+  }
+  return ok;
+}
+
+extern "C" int bo_pack_rows_host(bo_state* st, const double* X_host, int64_t rows, double* dense_out, uint64_t* bits_out) {
+  if (!st || !X_host || !dense_out || !bits_out) { bo_set_error("pack_rows_host: null argument"); return BO_ERR_INVALID; }
+  pack_layout_init(st);
+  const int n_thr = (int)std::min<int64_t>(8, std::max<int64_t>(1, rows / 256));
+  std::vector<std::thread> th;
+  std::vector<char> okv(n_thr, 1);
+  const size_t per = ((size_t)rows + n_thr - 1) / n_thr;
+  for (int t = 0; t < n_thr; ++t) {
+    const size_t r0 = std::min((size_t)rows, t * per), r1 = std::min((size_t)rows, r0 + per);
+    th.emplace_back([=, &okv]() { okv[t] = pack_rows(st, X_host, r0, r1, dense_out, reinterpret_cast<unsigned long long*>(bits_out)) ? 1 : 0; });
+  }
+  for (auto& t : th) t.join();
+  for (char c : okv) if (!c) { bo_set_error("fingerprint (Tanimoto) columns must hold 0 / 1"); return BO_ERR_INVALID; }
+  return BO_OK;
+}
+
+static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, const double* dense_host, const uint64_t* bits_host,
+                             int32_t b, int32_t q, const double* zq_dev, double* out_host, void* stream) {
   if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   if (b == 0) return BO_OK;
-  size_t in_bytes = (size_t)b * q * st->d * 8, out_bytes = (size_t)b * 8;
-  if (st->pin_in_bytes < in_bytes) {
+  const bool packed = mode != HOST_DENSE;
+  if (packed) pack_layout_init(st);
+  const int nd = packed ? (int)st->pack_dense_cols.size() : 0, nbits = packed ? (int)st->pack_bit_cols.size() : 0;
+  const int W = (nbits + 63) / 64;
+  const size_t n_rows = (size_t)b * q;
+  const size_t in_bytes = n_rows * st->d * 8, out_bytes = (size_t)b * 8;
+  const size_t row_wire = packed ? ((size_t)nd + W) * 8 : (size_t)st->d * 8;     // bytes per candidate point on the wire
+  const size_t wire_bytes = n_rows * row_wire;
+  if (st->pin_in_bytes < wire_bytes) {
     if (st->pin_in) cudaFreeHost(st->pin_in);
     st->pin_in = nullptr; st->pin_in_bytes = 0;
-    CUDA_CHECK_RET(cudaHostAlloc(&st->pin_in, in_bytes, cudaHostAllocDefault));
-    st->pin_in_bytes = in_bytes;
+    CUDA_CHECK_RET(cudaHostAlloc(&st->pin_in, wire_bytes, cudaHostAllocDefault));
+    st->pin_in_bytes = wire_bytes;
   }
   if (st->pin_out_bytes < out_bytes) {
     if (st->pin_out) cudaFreeHost(st->pin_out);
@@ -1323,20 +1434,32 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   }
   RC(st->stage_in.ensure(in_bytes));
   RC(st->stage_out.ensure(out_bytes));
+  if (packed) {
+    RC(st->stage_pk.ensure(wire_bytes));
+    if (!st->pack_src_ready) {
+      std::vector<int> src(st->d, 0);
+      for (int k = 0; k < nd; ++k) src[st->pack_dense_cols[k]] = k;
+      for (int k = 0; k < nbits; ++k) src[st->pack_bit_cols[k]] = -(k + 1);
+      RC(st->pack_src.ensure((size_t)st->d * sizeof(int)));
+      CUDA_CHECK_RET(cudaMemcpy(st->pack_src.p, src.data(), (size_t)st->d * sizeof(int), cudaMemcpyHostToDevice));
+      st->pack_src_ready = true;
+    }
+  }
   // Pipeline over chunks of q-batches: the host stages chunk c+1 (pageable -> pinned, up to 4 threads) and the copy
   // engine moves it (second stream) while the kernels of chunk c run; only the first chunk's staging + H2D is exposed.
   if (!st->copy_stream) CUDA_CHECK_RET(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-  const size_t row_bytes = (size_t)st->d * 8;
-  // Chunk plan from the ratio r of the copy time (d * 8 bytes per candidate point at ~25 GB/s) to the compute time
+  // Chunk plan from the ratio r of the copy time (bytes per candidate point at ~25 GB/s) to the compute time
   // (~ M N^2 flops per point at ~30 TFLOP/s):  r small (config 3: 0.04) -> a small first chunk so that the kernels start
-  // early, then everything else in one efficient launch sequence;  r large (2048-bit fingerprints as float64: 0.8) ->
-  // equal chunks so that every copy but the first hides behind a compute.
+  // early, then everything else in one efficient launch sequence;  r large (2048-bit fingerprints as float64: 0.8; the host
+  // pass over the float64 rows costs about as much when they are packed here) -> equal chunks so that every copy but the
+  // first hides behind a compute.
   std::vector<int> chunk_b;
   {
-    const double r = ((double)st->d * 8.0 / 25e9) / ((double)st->M * (double)st->N * (double)st->N / 30e12 + 1e-12);
+    const double host_bytes = (mode == HOST_PREPACKED) ? (double)row_wire : (double)st->d * 8.0;
+    const double r = (host_bytes / 25e9) / ((double)st->M * (double)st->N * (double)st->N / 30e12 + 1e-12);
     const int min_b = std::max(1, 2048 / q);
     // inputs below 8 MiB cross PCIe in ~0.3 ms: nothing worth hiding, and whole-batch launches fill the GPU better
-    if (b <= 2 * min_b || in_bytes < ((size_t)8 << 20)) chunk_b.push_back(b);
+    if (b <= 2 * min_b || (double)n_rows * host_bytes < (double)((size_t)8 << 20)) chunk_b.push_back(b);
     else if (r < 0.15) {
       // EVEREST_HOST_FIRST_DIV=n: first chunk = b / n (default 8); EVEREST_HOST_THREE=1: a third, intermediate
       // chunk of three times the first (experiment switches, read once).  Measured on config 3 (tools/exp_host.sh):
@@ -1365,18 +1488,21 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   // the staging buffer may still be read by kernels of an earlier call on `s`: order the first copy after them
   CUDA_CHECK_RET(cudaEventRecord(st->copy_events[0], s));
   CUDA_CHECK_RET(cudaStreamWaitEvent(st->copy_stream, st->copy_events[0], 0));
-  const char* src = reinterpret_cast<const char*>(X_host);
   char* pin = reinterpret_cast<char*>(st->pin_in);
+  // wire layout of the packed modes: [dense of all rows][bits of all rows], on the host and in stage_pk alike
+  double* pin_dense = reinterpret_cast<double*>(pin);
+  unsigned long long* pin_bits = reinterpret_cast<unsigned long long*>(pin + n_rows * (size_t)nd * 8);
+  char* dev_pk = reinterpret_cast<char*>(st->stage_pk.p);
   // A staging thread walks the chunks (pageable -> pinned with up to 4 helper threads, then the H2D on the copy stream) and
   // publishes each chunk with an event; this thread launches the kernels of a chunk as soon as its event exists.  The
   // launch thread may block inside a chunk (the per-row guard of the INT8 GEMM reads one counter back), the staging thread
   // keeps the copy engine busy meanwhile.
-  std::vector<size_t> c_off(n_chunks), c_len(n_chunks);
+  std::vector<size_t> c_row0(n_chunks), c_rows(n_chunks);
   std::vector<int> c_b0(n_chunks);
   for (int c = 0, b0 = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
     c_b0[c] = b0;
-    c_off[c] = (size_t)b0 * q * row_bytes;
-    c_len[c] = (size_t)chunk_b[c] * q * row_bytes;
+    c_row0[c] = (size_t)b0 * q;
+    c_rows[c] = (size_t)chunk_b[c] * q;
   }
   int dev_id = 0;
   cudaGetDevice(&dev_id);
@@ -1384,19 +1510,40 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   std::condition_variable cv;
   int published = 0;                  // chunks whose H2D has been enqueued and whose event is recorded
   cudaError_t stage_err = cudaSuccess;
+  bool pack_ok = true;
   auto stage_chunk = [&](int c) -> cudaError_t {
-    const size_t off = c_off[c], len = c_len[c];
+    const size_t r0 = c_row0[c], nr = c_rows[c];
+    const size_t host_bytes = nr * (mode == HOST_PREPACKED ? row_wire : (size_t)st->d * 8);
     const size_t piece = (size_t)4 << 20;
-    const int n_thr = (int)std::min<size_t>(4, (len + piece - 1) / piece);
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, (host_bytes + piece - 1) / piece));
+    const size_t per = (nr + n_thr - 1) / n_thr;
     std::vector<std::thread> th;
-    const size_t per = (len + n_thr - 1) / std::max(n_thr, 1);
-    for (int t = 1; t < n_thr; ++t) {
-      const size_t o2 = off + (size_t)t * per, l2 = std::min(per, off + len - o2);
-      th.emplace_back([=]() { memcpy(pin + o2, src + o2, l2); });
-    }
-    memcpy(pin + off, src + off, std::min(per, len));
+    std::vector<char> okv(n_thr, 1);
+    auto work = [&](int t) {
+      const size_t a = std::min(r0 + nr, r0 + (size_t)t * per), e = std::min(r0 + nr, a + per);
+      if (e <= a) return;
+      if (mode == HOST_DENSE) memcpy(pin + a * row_wire, reinterpret_cast<const char*>(X_host) + a * row_wire, (e - a) * row_wire);
+      else if (mode == HOST_PACK) okv[t] = pack_rows(st, X_host, a, e, pin_dense, pin_bits) ? 1 : 0;
+      else {
+        memcpy(pin_dense + a * nd, dense_host + a * nd, (e - a) * (size_t)nd * 8);
+        memcpy(pin_bits + a * W, bits_host + a * W, (e - a) * (size_t)W * 8);
+      }
+    };
+    for (int t = 1; t < n_thr; ++t) th.emplace_back(work, t);
+    work(0);
     for (auto& t : th) t.join();
-    cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + off, pin + off, len, cudaMemcpyHostToDevice, st->copy_stream);
+    for (char ok : okv) if (!ok) pack_ok = false;
+    cudaError_t e;
+    if (!packed) {
+      e = cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + r0 * row_wire, pin + r0 * row_wire, nr * row_wire,
+                          cudaMemcpyHostToDevice, st->copy_stream);
+    } else {
+      e = cudaSuccess;
+      if (nd) e = cudaMemcpyAsync(dev_pk + r0 * (size_t)nd * 8, pin_dense + r0 * nd, nr * (size_t)nd * 8, cudaMemcpyHostToDevice, st->copy_stream);
+      if (e == cudaSuccess && W)
+        e = cudaMemcpyAsync(dev_pk + n_rows * (size_t)nd * 8 + r0 * (size_t)W * 8, pin_bits + r0 * W, nr * (size_t)W * 8,
+                            cudaMemcpyHostToDevice, st->copy_stream);
+    }
     if (e == cudaSuccess) e = cudaEventRecord(st->copy_events[c], st->copy_stream);
     return e;
   };
@@ -1432,8 +1579,13 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
     if (trace) fprintf(stderr, "[host] chunk %d (%d q-batches) published at %.3f ms\n", c, chunk_b[c], ms_since());
     cudaError_t e = cudaStreamWaitEvent(s, st->copy_events[c], 0);
     if (e != cudaSuccess) { std::lock_guard<std::mutex> lk(mtx); stage_err = e; break; }
-    rc_fwd = bo_acqf_forward(st, st->stage_in.as<double>() + (size_t)c_b0[c] * q * st->d, chunk_b[c], q, zq_dev,
-                             st->stage_out.as<double>() + c_b0[c], nullptr, s);
+    double* Xc = st->stage_in.as<double>() + c_row0[c] * st->d;
+    if (packed)
+      rc_fwd = launch_unpack_rows(reinterpret_cast<const double*>(dev_pk) + c_row0[c] * nd,
+                                  reinterpret_cast<const u64*>(dev_pk + n_rows * (size_t)nd * 8) + c_row0[c] * W, nd, W,
+                                  st->pack_src.as<int>(), (int)c_rows[c], st->d, Xc, s, &st->lc);
+    if (rc_fwd == BO_OK)
+      rc_fwd = bo_acqf_forward(st, Xc, chunk_b[c], q, zq_dev, st->stage_out.as<double>() + c_b0[c], nullptr, s);
     if (trace) fprintf(stderr, "[host] chunk %d launched, forward returned at %.3f ms\n", c, ms_since());
   }
   if (stager.joinable()) stager.join();
@@ -1441,9 +1593,31 @@ extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t 
   RC(rc_fwd);
   CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  if (!pack_ok) { bo_set_error("fingerprint (Tanimoto) columns must hold 0 / 1"); return BO_ERR_INVALID; }
   memcpy(out_host, st->pin_out, out_bytes);
   if (trace) fprintf(stderr, "[host] done at %.3f ms\n", ms_since());
   return BO_OK;
+}
+
+extern "C" int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
+                                    double* out_host, void* stream) {
+  if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
+  if (!X_host || !out_host) { bo_set_error("forward_host: null buffer"); return BO_ERR_INVALID; }
+  // wide fingerprint blocks go over PCIe as bits (EVEREST_HOST_PACK=0 keeps the float64 wire format)
+  static const int pack_env = []() { const char* e = getenv("EVEREST_HOST_PACK"); return e ? atoi(e) : 1; }();
+  pack_layout_init(st);
+  const bool pack = pack_env != 0 && st->pack_bit_cols.size() >= 256;
+  return forward_host_impl(st, pack ? HOST_PACK : HOST_DENSE, X_host, nullptr, nullptr, b, q, zq_dev, out_host, stream);
+}
+
+extern "C" int bo_acqf_forward_host_packed(bo_state* st, const double* dense_host, const uint64_t* bits_host, int32_t b, int32_t q,
+                                           const double* zq_dev, double* out_host, void* stream) {
+  if (!st) { bo_set_error("null state"); return BO_ERR_INVALID; }
+  pack_layout_init(st);
+  if ((!dense_host && !st->pack_dense_cols.empty()) || (!bits_host && !st->pack_bit_cols.empty()) || !out_host) {
+    bo_set_error("forward_host_packed: null buffer"); return BO_ERR_INVALID;
+  }
+  return forward_host_impl(st, HOST_PREPACKED, nullptr, dense_host, bits_host, b, q, zq_dev, out_host, stream);
 }
 
 // ---- stand-alone multi-objective utilities (no GP state) ---------------------------------------------

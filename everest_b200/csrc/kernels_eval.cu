@@ -78,6 +78,34 @@ int launch_prep_points(const ModelD& md, const double* X, int n, int d, PrepD pr
   return BO_OK;
 }
 
+// Packed wire format of the host entry points (capi.cu forward_host_impl) -> dense rows: column c of row r comes from
+// dense[r, src[c]] (src[c] >= 0) or from bit -(src[c] + 1) of the row's fingerprint words.
+__global__ void unpack_rows_kernel(const double* __restrict__ dense, const u64* __restrict__ bits, int nd, int W,
+                                   const int* __restrict__ src, int rows, int d, double* __restrict__ X) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * d) return;
+  const size_t r = i / d;
+  const int c = (int)(i - r * d);
+  const int sidx = src[c];
+  double v;
+  if (sidx >= 0) v = dense[r * nd + sidx];
+  else {
+    const int k = -(sidx + 1);
+    v = (double)((bits[r * W + (k >> 6)] >> (k & 63)) & 1ull);
+  }
+  X[i] = v;
+}
+
+int launch_unpack_rows(const double* dense, const u64* bits, int nd, int W, const int* src, int rows, int d, double* X,
+                       cudaStream_t s, LaunchCounter* lc) {
+  if (rows <= 0) return BO_OK;
+  const size_t n = (size_t)rows * d;
+  unpack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dense, bits, nd, W, src, rows, d, X);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // crosscov
 // ------------------------------------------------------------------------------------------------

@@ -225,9 +225,24 @@ int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int3
                      const double* ub, const double* zq_dev, int32_t maxiter, int32_t history, double pgtol, double ftol,
                      double* out_dev, int32_t* stats, void* stream);
 
-/* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values. */
+/* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values.  Columns read only by Tanimoto
+ * leaves (0/1 fingerprints: molfeatures.py:31-48 hands them to BoTorch as float64) cross PCIe as BITS: the staging threads
+ * pack them while they copy (a config-5 candidate shrinks from 16.5 KB to 352 bytes on the wire) and a kernel restores the
+ * float64 row on the device; a fingerprint column holding anything but 0 / 1 is refused (BO_ERR_INVALID). */
 int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
                          double* out_host, void* stream);
+
+/* The packed wire format for callers that keep their candidate set packed (the discrete choice set of
+ * optimize_acqf_discrete, botorch.py:425-467, is scored again after every tell):
+ *   bo_pack_layout     which columns travel as doubles (dense_cols [n_dense]) and which as bits (bit k of a row = column
+ *                      bit_cols[k]; 64 bits per uint64 word, bit k in word k / 64 at position k % 64); arrays may be NULL to
+ *                      query the sizes
+ *   bo_pack_rows_host  X_host [rows, d] float64 -> dense_out [rows, n_dense], bits_out [rows, ceil(n_bits / 64)]
+ *   bo_acqf_forward_host_packed   forward(X[b, q, d]) from the packed buffers ([b * q] rows), values to out_host [b] */
+int bo_pack_layout(bo_state* st, int32_t* n_dense, int32_t* n_bits, int32_t* dense_cols, int32_t* bit_cols);
+int bo_pack_rows_host(bo_state* st, const double* X_host, int64_t rows, double* dense_out, uint64_t* bits_out);
+int bo_acqf_forward_host_packed(bo_state* st, const double* dense_host, const uint64_t* bits_host, int32_t b, int32_t q,
+                                const double* zq_dev, double* out_host, void* stream);
 
 /* Stand-alone multi-objective utilities (maximisation frame), the result metrics of the path:
  * botorch is_non_dominated as used by get_pareto_front (utils/multiobjective.py:58-84) and Hypervolume.compute as

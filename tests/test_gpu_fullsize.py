@@ -136,3 +136,38 @@ def test_config5_mixed_tanimoto_hamming_full_size():
     assert float(((var_d.cpu() - var_o).abs() / var_o).max()) < 1e-9
     # arg-max of the discrete branch (optimize_acqf_discrete, botorch.py:461) agrees on the shared sample
     assert int(torch.argmax(v_d[:1024])) == int(torch.argmax(v_o))
+
+
+def test_packed_wire_format_of_the_host_entry_point():
+    """Config-5 layout (2 continuous | 2048 fingerprint bits | 4 + 6 one-hot): the host entry point ships the fingerprint
+    block as bits (bo_acqf_forward_host packs while staging; bo_pack_layout / bo_pack_rows_host / bo_acqf_forward_host_packed
+    for callers that keep the choice set packed).  The device restores exactly the same 0 / 1 doubles, so the values agree with
+    the device-pointer call on the float64 rows to the rounding that the chunking of the host pipeline introduces (the
+    Gram partial sums are grouped per chunk); a non-binary fingerprint is refused."""
+    import numpy as np
+
+    p = Cf.mixed_tanimoto_qlogei(N=300, S=64, n_choices=6000)
+    st = Cf.build_state(p)
+    acq = Cf.build_acqf(p, st)
+    X = Cf.candidates(p)                              # [6000, 1, 2060]: 99 MB of float64, > 8 MiB: the chunked pipeline
+    v_dev = acq(X.to(st.device)).cpu().numpy()
+    dc, bc = acq.pack_layout()
+    assert bc.tolist() == list(range(2, 2050)) and dc.tolist() == [0, 1] + list(range(2050, 2060))
+    v_host = acq.forward_host(X.numpy())             # packs inside
+    tol = dict(rtol=1e-9, atol=1e-11 * float(np.abs(v_dev).max()))
+    assert np.allclose(v_host, v_dev, **tol)
+    dense, bits = acq.pack_rows(X.numpy())
+    assert dense.shape == (6000, 12) and bits.shape == (6000, 32) and bits.dtype == np.uint64
+    # the library's packer against numpy's: bit k of a row = column bit_cols[k], little-endian inside each 64-bit word
+    ref_bits = np.packbits(X.numpy().reshape(6000, -1)[:, bc].astype(np.uint8), axis=1, bitorder="little").view(np.uint64)
+    assert np.array_equal(bits, ref_bits)
+    v_packed = acq.forward_host_packed(dense, bits, q=1)
+    assert np.allclose(v_packed, v_dev, **tol)
+    v_small = acq.forward_host_packed(dense[:7], bits[:7], q=1)      # single chunk
+    assert np.allclose(v_small, v_dev[:7], **tol)
+    bad = X.numpy().copy()
+    bad[5, 0, 100] = 0.5
+    with pytest.raises(ValueError):
+        acq.forward_host(bad)
+    with pytest.raises(ValueError):
+        acq.pack_rows(bad)

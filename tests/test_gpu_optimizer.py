@@ -1,0 +1,90 @@
+"""On-device multi-start refinement (bo_acqf_optimize, csrc/lbfgs.cu) against the host-driven scipy L-BFGS-B
+that [UPSTREAM] gen_candidates_scipy runs (both take value and gradient from the same adjoint kernels): same local maxima
+from identical initial conditions, bounds and fixed features honoured, pending points held constant, never worse than the
+start."""
+import numpy as np
+import pytest
+import torch
+
+from everest_b200 import acquisition as A
+from everest_b200 import configs as Cf
+from everest_b200 import optim
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(p, n_restarts=8, raw=512):
+    st = Cf.build_state(p)
+    acq = Cf.build_acqf(p, st)
+    bnds = torch.as_tensor(p["bounds"])
+    Xic, Yic, _, _ = optim.gen_batch_initial_conditions(acq, bnds, p["q"], n_restarts, raw, seed=0)
+    return st, acq, bnds, Xic, Yic
+
+
+def test_device_lbfgs_matches_scipy_lbfgsb_candidates_himmelblau():
+    """Config-2 shapes (qLogEI, Matern-5/2): both optimisers converge (scipy: 'RELATIVE REDUCTION OF F', device: pgtol / ftol)
+    to the same local maxima: acquisition values to 1e-8, candidates to 1e-4 of the 12-wide box (scipy's own stopping
+    tolerance pgtol = 1e-5 bounds what two different quasi-Newton paths can agree to)."""
+    p = Cf.himmelblau_qlogei(N=200, S=128, raw=512)
+    st, acq, bnds, Xic, Yic = _setup(p)
+    Xd, Yd, info_d = optim.gen_candidates_device(Xic, acq, bnds[0], bnds[1], options={"maxiter": 200})
+    Xs, Ys, info_s = optim.gen_candidates_scipy(Xic, acq, bnds[0], bnds[1], options={"maxiter": 200})
+    assert info_d["n_converged"] == Xic.shape[0] and "CONVERGENCE" in info_s["message"]
+    assert torch.all(Yd >= Yic - 1e-12)
+    assert torch.allclose(Yd, Ys, rtol=1e-7, atol=1e-8)
+    assert float((Xd - Xs).abs().max()) < 1e-4 * 12.0
+    # tightened tolerances: scipy started from the device optimum does not move
+    Xt, Yt, _ = optim.gen_candidates_device(Xic, acq, bnds[0], bnds[1], options={"maxiter": 500, "pgtol": 1e-9, "ftol": 1e-15})
+    Xp, Yp, info_p = optim.gen_candidates_scipy(Xt, acq, bnds[0], bnds[1], options={"maxiter": 50})
+    assert float((Xt - Xp).abs().max()) < 1e-6 and torch.allclose(Yt, Yp, rtol=1e-9, atol=1e-10)
+
+
+def test_device_lbfgs_bounds_fixed_features_and_monotone_qnehvi():
+    p = Cf.zdt1_qnehvi(N=64, S=64, raw=256, d=6, q=2)
+    st, acq, bnds, Xic, Yic = _setup(p, n_restarts=6, raw=256)
+    ff = {1: 0.25, 4: 0.75}
+    X0 = optim.apply_fixed_features(Xic, ff)
+    with torch.no_grad():
+        Y0 = acq(X0.to(st.device)).cpu()
+    Xd, Yd, info = optim.gen_candidates_device(X0, acq, bnds[0], bnds[1], fixed_features=ff, options={"maxiter": 60})
+    assert Xd.shape == X0.shape and info["nit"] >= 1
+    assert torch.all(Xd >= bnds[0] - 1e-15) and torch.all(Xd <= bnds[1] + 1e-15)
+    assert torch.all(Xd[..., 1] == 0.25) and torch.all(Xd[..., 4] == 0.75)
+    assert torch.all(Yd >= Y0 - 1e-12) and float(Yd.max()) > float(Y0.max())
+    with torch.no_grad():
+        assert torch.allclose(acq(Xd.to(st.device)).cpu(), Yd, rtol=1e-12, atol=1e-14)     # the values belong to the returned points
+    # the default refinement of optimize_acqf is the device optimiser; the scipy path stays selectable and agrees in value
+    torch.manual_seed(0)
+    c_dev, v_dev = optim.optimize_acqf(acq, bnds, p["q"], 4, 128, options={"maxiter": 60}, seed=3)
+    c_sci, v_sci = optim.optimize_acqf(acq, bnds, p["q"], 4, 128, options={"maxiter": 60, "optimizer": "scipy"}, seed=3)
+    assert c_dev.shape == (2, 6) and float(v_dev) > 0
+    assert abs(float(v_dev) - float(v_sci)) <= 0.25 * max(float(v_dev), float(v_sci))   # same starts, nearby local maxima
+
+
+def test_device_lbfgs_keeps_pending_points_constant():
+    """Concatenating acquisition functions (qLogEI with X_pending): the trailing pending rows of every q-batch are constants
+    of the optimisation; same optimum as the scipy path, which sees them through forward_backward."""
+    p = Cf.himmelblau_qlogei(N=120, S=64, raw=256)
+    st = Cf.build_state(p)
+    pend = torch.tensor([[1.0, 2.0], [-3.0, 0.5]], dtype=torch.double)
+    mean, _ = st.posterior(torch.as_tensor(p["X"]))
+    best_f = float(p["objective"](mean.cpu()).max())
+    acq = A.qLogExpectedImprovement(st, best_f, p["objective"], mc_samples=64, seed=5, X_pending=pend)
+    bnds = torch.as_tensor(p["bounds"])
+    Xic, Yic, _, _ = optim.gen_batch_initial_conditions(acq, bnds, 1, 5, 256, seed=1)
+    Xd, Yd, info = optim.gen_candidates_device(Xic, acq, bnds[0], bnds[1], options={"maxiter": 100})
+    Xs, Ys, _ = optim.gen_candidates_scipy(Xic, acq, bnds[0], bnds[1], options={"maxiter": 100})
+    assert Xd.shape == (5, 1, 2)
+    assert torch.allclose(Yd, Ys, rtol=1e-6, atol=1e-7) and float((Xd - Xs).abs().max()) < 2e-3
+    assert torch.equal(acq.X_pending.cpu(), pend)
+
+
+def test_device_lbfgs_argument_validation():
+    p = Cf.himmelblau_qlogei(N=40, S=32, raw=64)
+    st, acq, bnds, Xic, Yic = _setup(p, n_restarts=2, raw=64)
+    with pytest.raises(ValueError):
+        acq.optimize(Xic, bnds[0], bnds[1], history=64)                    # history > 16
+    with pytest.raises(ValueError):
+        acq.optimize(Xic, bnds[1], bnds[0])                                # lb > ub
+    with pytest.raises(ValueError):
+        acq.optimize(torch.zeros(2, 1, 5, dtype=torch.double), bnds[0], bnds[1])   # wrong input dimension
