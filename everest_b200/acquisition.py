@@ -263,8 +263,9 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
                  alpha: float = 0.0, cache_root: bool = True, X_pending=None, mc_samples: int = 512,
                  seed: Optional[int] = None, prune_samples: int = 2048, base_samples_baseline=None):
         super().__init__(model, mc_samples, seed)
-        if alpha != 0.0:
-            raise NotImplementedError("approximate partitioning (alpha > 0) is not part of the accelerated path")
+        if not (0.0 <= float(alpha) <= 0.5):
+            raise ValueError("alpha must be in [0, 0.5]")      # data_models/strategies/predictives/qnehvi.py:19
+        self.alpha = float(alpha)
         if not cache_root:
             raise NotImplementedError("cache_root=False (joint re-sampling of the baseline) is not accelerated")
         self.ref_point = [float(v) for v in ref_point]
@@ -312,6 +313,9 @@ class qNoisyExpectedHypervolumeImprovement(_DeviceAcquisition):
         info = (C.c_int32 * model.M)()
         maxc = C.c_int32(0)
         with torch.cuda.device(model.device):
+            # BoFire's `alpha`: approximate binary partitioning for more than two objectives ([UPSTREAM]
+            # NondominatedPartitioning(alpha)); two objectives are always decomposed exactly, as in BoTorch
+            L.check(model.lib.bo_acqf_set_option(model.handle, b"partition_alpha", float(getattr(self, "alpha", 0.0))))
             L.check(model.lib.bo_nehvi_prepare(model.handle, _dev_ptr(Xbd), self.nb, _dev_ptr(zb), self.S, self._obj_c,
                                                self._n_obj, self._con_c, self._n_con, self._ref_c, info, C.byref(maxc),
                                                _stream()))
@@ -368,8 +372,11 @@ class qExpectedHypervolumeImprovement(_DeviceAcquisition):
     (maximisation frame, already multiplied by the ref-point mask) BoFire hands to NondominatedPartitioning."""
 
     def __init__(self, model: DeviceGPState, ref_point, partitioning_Y, objective: MultiObjective, mc_samples: int = 512,
-                 seed: Optional[int] = None, X_pending=None):
+                 seed: Optional[int] = None, X_pending=None, alpha: float = 0.0):
         super().__init__(model, mc_samples, seed)
+        if not (0.0 <= float(alpha) <= 0.5):
+            raise ValueError("alpha must be in [0, 0.5]")
+        self.alpha = float(alpha)      # [UPSTREAM] NondominatedPartitioning(ref_point, Y, alpha) of get_acquisition_function
         self.set_X_pending(X_pending)
         self.ref_point = [float(v) for v in ref_point]
         self.objective = objective
@@ -382,6 +389,7 @@ class qExpectedHypervolumeImprovement(_DeviceAcquisition):
         model, Y = self.model, self._Y
         maxc = C.c_int32(0)
         with torch.cuda.device(model.device):
+            L.check(model.lib.bo_acqf_set_option(model.handle, b"partition_alpha", float(getattr(self, "alpha", 0.0))))
             L.check(model.lib.bo_ehvi_prepare(model.handle, _dev_ptr(Y), Y.shape[0], self.S, self._obj_c, self._n_obj,
                                               self._ref_c, C.byref(maxc), _stream()))
         self.max_cells = int(maxc.value)
@@ -628,12 +636,10 @@ def get_acquisition_function(acquisition_function_name: str, model: DeviceGPStat
     if name in ("qEHVI", "qLogEHVI"):
         if ref_point is None or Y is None:
             raise ValueError("`ref_point` and `Y` must be specified")
-        if alpha != 0.0:
-            raise NotImplementedError("approximate partitioning (alpha > 0) is not part of the accelerated path")
         if constraints:
             raise NotImplementedError("output constraints with qEHVI / qLogEHVI are not accelerated; use qNEHVI / qLogNEHVI")
         # [UPSTREAM] the partitioning is built from the objective values of the observations
         Yobj = objective(torch.as_tensor(Y, dtype=torch.double))
         cls = qExpectedHypervolumeImprovement if name == "qEHVI" else qLogExpectedHypervolumeImprovement
-        return cls(model, ref_point, Yobj, objective, mc_samples=mc_samples, seed=seed, X_pending=X_pending)
+        return cls(model, ref_point, Yobj, objective, mc_samples=mc_samples, seed=seed, X_pending=X_pending, alpha=alpha)
     raise NotImplementedError(f"Unknown / non-accelerated acquisition function {acquisition_function_name}")

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libeverest_b200.so")
-SOURCES = ["kernels_eval.cu", "gemm.cu", "chol.cu", "acqf.cu", "grad.cu", "scalar_acqf.cu", "loghvi.cu", "sobol.cu", "mll.cu", "ozaki.cu", "lbfgs.cu", "capi.cu"]
+SOURCES = ["kernels_eval.cu", "gemm.cu", "chol.cu", "acqf.cu", "grad.cu", "scalar_acqf.cu", "loghvi.cu", "sobol.cu", "mll.cu", "ozaki.cu", "lbfgs.cu", "host_pack.cpp", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread"]
 
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -8,6 +8,8 @@
 // (sample_cached_cholesky, _compute_qehvi, FastNondominatedPartitioning, log_fatplus/fatmax), restated
 // in oracle/bo_oracle.py.  Objective / constraint formulas: utils/torch_tools.py:258-337,384-450.
 #include "common.cuh"
+#include <algorithm>
+
 #include "acqf.cuh"
 #include "mc_math.cuh"
 
@@ -644,6 +646,155 @@ int launch_partition_nd(const double* obj, const unsigned char* front, int n, in
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc) {
   partition_nd_kernel<<<S, 256, 0, st>>>(obj, front, n, S, Mo, cap, ref_dev, work, lo, up, ncells, overflow);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
+// Approximate / exact box decomposition by BINARY PARTITIONING: [UPSTREAM] botorch NondominatedPartitioning._partition_space
+// (Couckuyt et al. 2012), what qNEHVI builds per MC sample when BoFire passes alpha > 0 and there are more than two
+// objectives (data_models/strategies/predictives/qnehvi.py:19, strategies/predictives/qnehvi.py:50).  Cells are pairs of
+// index vectors into the per-objective sorted (augmented) front; a cell that lies entirely in the non-dominated region is
+// kept, a cell that straddles the front is halved along its longest index edge -- unless its share of the volume between
+// the ideal and the anti-ideal point is <= alpha, in which case it is DROPPED (the approximation), and cells inside the
+// dominated region are dropped.  One warp per MC sample: lane 0 owns the explicit LIFO stack, the 32 lanes share the
+// any / all tests against the front points; cells are emitted in the order the reference's list-based loop appends them.
+// Work buffer per sample: negY [n][Mo] doubles, aug [n + 2][Mo] ints, stack [PB_STACK][2][Mo] ints.
+#define PB_STACK 256
+__global__ void __launch_bounds__(32)
+partition_binary_kernel(const double* __restrict__ obj, const unsigned char* __restrict__ front, int n, int S, int Mo, int cap,
+                        const double* __restrict__ ref, double alpha, double* __restrict__ work, size_t work_stride,
+                        double* __restrict__ lo, double* __restrict__ up, int* __restrict__ ncells, int* __restrict__ overflow) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  char* base = reinterpret_cast<char*>(work) + (size_t)s * work_stride;
+  double* negY = reinterpret_cast<double*>(base);                       // [p][Mo]
+  int* aug = reinterpret_cast<int*>(negY + (size_t)n * Mo);            // [p + 2][Mo]: row of the augmented front per rank
+  int* stack = aug + (size_t)(n + 2) * Mo;                              // [PB_STACK][2][Mo]
+  const double pinf = __longlong_as_double(0x7ff0000000000000LL);
+  // front points of this sample in row order (minimisation frame)
+  int p = 0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    const bool f = e < n && front[(size_t)s * n + e];
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (f) {
+      const int dst = p + __popc(m & ((1u << lane) - 1));
+      for (int j = 0; j < Mo; ++j) negY[(size_t)dst * Mo + j] = -obj[((size_t)s * n + e) * Mo + j];
+    }
+    p += __popc(m);
+  }
+  __syncwarp();
+  if (p == 0) {   // empty front: one cell over the whole non-dominated space
+    if (lane == 0) {
+      for (int j = 0; j < Mo; ++j) { lo[((size_t)0 * Mo + j) * S + s] = ref[j]; up[((size_t)0 * Mo + j) * S + s] = pinf; }
+      ncells[s] = 1;
+    }
+    return;
+  }
+  // argsort of every objective (stable rank): aug[1 + rank][j] = row + 1; aug[0] = 0 (ideal), aug[p + 1] = p + 1 (anti-ideal)
+  for (int idx = lane; idx < p * Mo; idx += 32) {
+    const int i = idx / Mo, j = idx - i * Mo;
+    const double v = negY[(size_t)i * Mo + j];
+    int rank = 0;
+    for (int k = 0; k < p; ++k) {
+      const double w = negY[(size_t)k * Mo + j];
+      rank += (w < v) || (w == v && k < i);
+    }
+    aug[(size_t)(1 + rank) * Mo + j] = i + 1;
+  }
+  for (int j = lane; j < Mo; j += 32) { aug[j] = 0; aug[(size_t)(p + 1) * Mo + j] = p + 1; }
+  __syncwarp();
+  double ideal[BO_MAX_OBJECTIVES], anti[BO_MAX_OBJECTIVES];
+  double total = 1.0;
+  for (int j = 0; j < Mo; ++j) {
+    ideal[j] = negY[(size_t)(aug[(size_t)1 * Mo + j] - 1) * Mo + j] - 1.0;
+    anti[j] = negY[(size_t)(aug[(size_t)p * Mo + j] - 1) * Mo + j] + 1.0;
+    total *= (anti[j] - ideal[j]);
+  }
+  int top = 0, count = 0;
+  bool over = false;
+  if (lane == 0) {
+    for (int j = 0; j < Mo; ++j) { stack[j] = 0; stack[Mo + j] = p + 1; }
+  }
+  top = 1;
+  __syncwarp();
+  while (top > 0) {
+    --top;
+    int c0[BO_MAX_OBJECTIVES], c1[BO_MAX_OBJECTIVES], r0[BO_MAX_OBJECTIVES], r1[BO_MAX_OBJECTIVES];
+    double v0[BO_MAX_OBJECTIVES], v1[BO_MAX_OBJECTIVES];
+    for (int j = 0; j < Mo; ++j) {
+      c0[j] = stack[(size_t)top * 2 * Mo + j];
+      c1[j] = stack[(size_t)top * 2 * Mo + Mo + j];
+      r0[j] = aug[(size_t)c0[j] * Mo + j];
+      r1[j] = aug[(size_t)c1[j] * Mo + j];
+      v0[j] = (r0[j] == 0) ? ideal[j] : ((r0[j] == p + 1) ? anti[j] : negY[(size_t)(r0[j] - 1) * Mo + j]);
+      v1[j] = (r1[j] == 0) ? ideal[j] : ((r1[j] == p + 1) ? anti[j] : negY[(size_t)(r1[j] - 1) * Mo + j]);
+    }
+    __syncwarp();
+    // upper corner better than or equal to every front point in at least one objective: entirely non-dominated
+    bool all_u = true, all_l = true;
+    for (int k = lane; k < p; k += 32) {
+      bool any_u = false, any_l = false;
+      for (int j = 0; j < Mo; ++j) {
+        const double y = negY[(size_t)k * Mo + j];
+        any_u = any_u || (v1[j] <= y);
+        any_l = any_l || (v0[j] <= y);
+      }
+      all_u = all_u && any_u;
+      all_l = all_l && any_l;
+    }
+    all_u = __all_sync(0xffffffffu, all_u);
+    all_l = __all_sync(0xffffffffu, all_l);
+    if (all_u) {
+      if (count < cap) {
+        for (int j = lane; j < Mo; j += 32) {
+          // minimisation bounds [aug'(r0), aug'(r1)] with aug' = (-inf, front, -ref); maximisation = negated and swapped
+          lo[((size_t)count * Mo + j) * S + s] = (r1[j] == p + 1) ? ref[j] : -negY[(size_t)(r1[j] - 1) * Mo + j];
+          up[((size_t)count * Mo + j) * S + s] = (r0[j] == 0) ? pinf : -negY[(size_t)(r0[j] - 1) * Mo + j];
+        }
+      } else over = true;
+      ++count;
+    } else if (all_l) {
+      int length = 0, longest = 0;
+      double vol = 1.0;
+      for (int j = 0; j < Mo; ++j) {
+        const int dj = c1[j] - c0[j];
+        if (dj > length) { length = dj; longest = j; }      // first maximum, like torch.max
+        vol *= (v1[j] - v0[j]);
+      }
+      if (length > 1 && (vol / total) > alpha) {
+        // Python's round(length / 2.0): half to even
+        int n1 = length / 2;
+        if (length & 1) n1 += ((n1 & 1) ? 1 : 0);
+        const int n2 = length - n1;
+        if (top + 2 > PB_STACK) { over = true; break; }
+        if (lane == 0) {
+          int* a = stack + (size_t)top * 2 * Mo;        // cell 1: upper bound lowered by n1 (pushed first, popped second)
+          int* b = stack + (size_t)(top + 1) * 2 * Mo;  // cell 2: lower bound raised by n2
+          for (int j = 0; j < Mo; ++j) {
+            a[j] = c0[j]; a[Mo + j] = c1[j] - (j == longest ? n1 : 0);
+            b[j] = c0[j] + (j == longest ? n2 : 0); b[Mo + j] = c1[j];
+          }
+        }
+        top += 2;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) {
+    if (over) { atomicExch(overflow, 1); ncells[s] = 0; }
+    else ncells[s] = count;
+  }
+}
+size_t partition_binary_work_stride(int n, int Mo) {
+  size_t b = (size_t)std::max(n, 1) * Mo * sizeof(double) + ((size_t)(n + 2) * Mo + (size_t)PB_STACK * 2 * Mo) * sizeof(int);
+  return (b + 15) / 16 * 16;
+}
+int launch_partition_binary(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap, const double* ref_dev,
+                            double alpha, double* work, double* lo, double* up, int* ncells, int* overflow, cudaStream_t st,
+                            LaunchCounter* lc) {
+  partition_binary_kernel<<<S, 32, 0, st>>>(obj, front, n, S, Mo, cap, ref_dev, alpha, work, partition_binary_work_stride(n, Mo),
+                                             lo, up, ncells, overflow);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -68,6 +68,10 @@ int launch_partition2d(const double* obj, const unsigned char* front, int n, int
 int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc);
+size_t partition_binary_work_stride(int n, int Mo);
+int launch_partition_binary(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap, const double* ref_dev,
+                            double alpha, double* work, double* lo, double* up, int* ncells, int* overflow, cudaStream_t st,
+                            LaunchCounter* lc);
 int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc);
 size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
 int launch_mc_scalar(const McArgs& a, cudaStream_t st, LaunchCounter* lc);

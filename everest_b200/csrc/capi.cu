@@ -15,6 +15,7 @@
 
 #include "acqf.cuh"
 #include "common.cuh"
+#include "host_pack.h"
 #include "lbfgs.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -162,6 +163,7 @@ struct bo_state {
   long long oz_flagged_last = 0, oz_batches_last = 0;   // q-batches the guard redid in FP64 / scored in the last forward
   long long oz_flagged_total = 0, oz_batches_total = 0; // ... since the last prepare
   double oz_kappa = 8.0, oz_tol = 1e-10;
+  double part_alpha = 0.0;     // approximate box decomposition threshold of the next prepare (0 = exact)
   DevBuf wsOzFlags, wsOzXg, wsOzKxG, wsOzOutG;
   int* pin_count = nullptr;    // pinned: the guard's counter of flagged q-batches
   cudaEvent_t oz_event = nullptr;
@@ -602,11 +604,19 @@ static int build_cells(bo_state* st, const double* obj, const unsigned char* fea
       st->cap = cap;
       RC(st->cell_lo.ensure((size_t)cap * Mo * S * 8));
       RC(st->cell_up.ensure((size_t)cap * Mo * S * 8));
-      RC(st->wsPart.ensure((size_t)S * 2 * cap * (Mo + Mo * Mo) * 8));
       RC(st->wsInfo.ensure(64));
       CUDA_CHECK_RET(cudaMemsetAsync(st->wsInfo.p, 0, sizeof(int), s));
-      RC(launch_partition_nd(obj, st->wsFront.as<unsigned char>(), n, S, Mo, cap, st->ref_dev.as<double>(), st->wsPart.as<double>(),
-                             st->cell_lo.as<double>(), st->cell_up.as<double>(), st->ncells.as<int>(), st->wsInfo.as<int>(), s, &st->lc));
+      if (st->part_alpha > 0.0) {
+        // approximate partitioning (BoFire's `alpha`): binary partitioning, cells below the volume threshold are dropped
+        RC(st->wsPart.ensure((size_t)S * partition_binary_work_stride(n, Mo)));
+        RC(launch_partition_binary(obj, st->wsFront.as<unsigned char>(), n, S, Mo, cap, st->ref_dev.as<double>(), st->part_alpha,
+                                   st->wsPart.as<double>(), st->cell_lo.as<double>(), st->cell_up.as<double>(), st->ncells.as<int>(),
+                                   st->wsInfo.as<int>(), s, &st->lc));
+      } else {
+        RC(st->wsPart.ensure((size_t)S * 2 * cap * (Mo + Mo * Mo) * 8));
+        RC(launch_partition_nd(obj, st->wsFront.as<unsigned char>(), n, S, Mo, cap, st->ref_dev.as<double>(), st->wsPart.as<double>(),
+                               st->cell_lo.as<double>(), st->cell_up.as<double>(), st->ncells.as<int>(), st->wsInfo.as<int>(), s, &st->lc));
+      }
       int overflow = 0;
       CUDA_CHECK_RET(cudaMemcpyAsync(&overflow, st->wsInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_CHECK_RET(cudaStreamSynchronize(s));
@@ -846,6 +856,12 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
   } else if (nm == "tau_relu") {
     if (!(value > 0.0)) { bo_set_error("tau_relu must be > 0"); return BO_ERR_INVALID; }
     st->tau_relu = value;
+  } else if (nm == "partition_alpha") {
+    // BoFire's `alpha` (data_models/strategies/predictives/qnehvi.py:19): read by the NEXT prepare call.  0 = exact
+    // decomposition (local upper bounds); > 0 = approximate binary partitioning for more than two objectives (two objectives
+    // are always decomposed exactly, as in BoTorch); -1 = exact binary partitioning (BoTorch's NondominatedPartitioning cells)
+    if (!(value >= 0.0 && value <= 0.5) && value != -1.0) { bo_set_error("partition_alpha must be in [0, 0.5] (or -1)"); return BO_ERR_INVALID; }
+    st->part_alpha = (value == -1.0) ? 1e-300 : value;
   } else if (nm == "tau_max") {
     if (!(value > 0.0)) { bo_set_error("tau_max must be > 0"); return BO_ERR_INVALID; }
     st->tau_max = value;
@@ -1351,45 +1367,9 @@ extern "C" int bo_pack_layout(bo_state* st, int32_t* n_dense, int32_t* n_bits, i
   return BO_OK;
 }
 
-// rows [r0, r1) of X [*, d] -> dense [*, n_dense] doubles and bits [*, W] words (bit k of a row = column bit_cols[k]);
-// returns false if a fingerprint column holds something other than 0 / 1
 static bool pack_rows(const bo_state* st, const double* X, size_t r0, size_t r1, double* dense, unsigned long long* bits) {
-  const int d = st->d, nd = (int)st->pack_dense_cols.size(), nbits = (int)st->pack_bit_cols.size(), W = (nbits + 63) / 64;
-  const int* dc = st->pack_dense_cols.data();
-  const int* bc = st->pack_bit_cols.data();
-  const bool contiguous = nbits > 0 && bc[nbits - 1] - bc[0] == nbits - 1;
-  bool ok = true;
-  for (size_t r = r0; r < r1; ++r) {
-    const double* x = X + r * d;
-    double* dr = dense + r * nd;
-    for (int k = 0; k < nd; ++k) dr[k] = x[dc[k]];
-    unsigned long long* br = bits + r * W;
-    if (contiguous) {
-      const double* xb = x + bc[0];
-      for (int w = 0; w < W; ++w) {
-        const int n = std::min(64, nbits - w * 64);
-        unsigned long long word = 0;
-        for (int t = 0; t < n; ++t) {
-          const double v = xb[w * 64 + t];
-          word |= (unsigned long long)(v != 0.0) << t;
-          ok &= (v == 0.0) | (v == 1.0);
-        }
-        br[w] = word;
-      }
-    } else {
-      for (int w = 0; w < W; ++w) {
-        const int n = std::min(64, nbits - w * 64);
-        unsigned long long word = 0;
-        for (int t = 0; t < n; ++t) {
-          const double v = x[bc[w * 64 + t]];
-          word |= (unsigned long long)(v != 0.0) << t;
-          ok &= (v == 0.0) | (v == 1.0);
-        }
-        br[w] = word;
-      }
-    }
-  }
-  return ok;
+  return everest_pack_rows(X, r0, r1, st->d, st->pack_dense_cols.data(), (int)st->pack_dense_cols.size(), st->pack_bit_cols.data(),
+                           (int)st->pack_bit_cols.size(), dense, bits);
 }
 
 extern "C" int bo_pack_rows_host(bo_state* st, const double* X_host, int64_t rows, double* dense_out, uint64_t* bits_out) {
@@ -1515,7 +1495,7 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
     const size_t r0 = c_row0[c], nr = c_rows[c];
     const size_t host_bytes = nr * (mode == HOST_PREPACKED ? row_wire : (size_t)st->d * 8);
     const size_t piece = (size_t)4 << 20;
-    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(4, (host_bytes + piece - 1) / piece));
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(mode == HOST_PACK ? 8 : 4, (host_bytes + piece - 1) / piece));
     const size_t per = (nr + n_thr - 1) / n_thr;
     std::vector<std::thread> th;
     std::vector<char> okv(n_thr, 1);

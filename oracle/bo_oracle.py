@@ -516,6 +516,62 @@ def partition_nd(pareto_Y, ref):
     return -up_min, -lo_min
 
 
+def partition_binary(pareto_Y, ref, alpha=0.0):
+    """[UPSTREAM] botorch NondominatedPartitioning._partition_space + get_hypercell_bounds (binary partitioning of Couckuyt
+    et al. 2012), what BoTorch's qNEHVI builds per MC sample for alpha > 0 and m > 2 (BoFire passes `alpha`:
+    data_models/strategies/predictives/qnehvi.py:19, strategies/predictives/qnehvi.py:50).  Restated from the published
+    algorithm as BoTorch implements it, UNPINNED like the rest of the BoTorch arithmetic:
+      * minimisation frame; per objective the front is sorted, index 0 = ideal point (min - 1; -inf in the final bounds), index
+        p + 1 = anti-ideal point (max + 1; the reference point in the final bounds);
+      * LIFO stack of cells [lower idx, upper idx] per objective, start = [0, p + 1]^m;
+      * upper corner <= every front point in some objective -> accept; else lower corner <= ... -> if an index edge is longer
+        than 1 and volume / total > alpha: halve the longest index edge (first maximum; `round(length / 2)` half-to-even off the
+        upper bound, the rest onto the lower bound of the second child), otherwise DROP; else (dominated) drop.
+    pareto_Y [p, m] maximisation.  Returns (lower [C, m], upper [C, m]) in the maximisation frame, acceptance order."""
+    m = ref.shape[-1]
+    inf = float("inf")
+    p = pareto_Y.shape[0]
+    if p == 0:
+        return ref.view(1, m).clone(), torch.full((1, m), inf, dtype=DT)
+    neg = -pareto_Y
+    outcome = torch.arange(m)
+    aug_idcs = torch.cat([torch.zeros(1, m, dtype=torch.long), torch.argsort(neg, dim=0, stable=True) + 1,
+                          torch.full((1, m), p + 1, dtype=torch.long)], dim=0)
+    ideal = neg.min(dim=0, keepdim=True).values - 1
+    anti = neg.max(dim=0, keepdim=True).values + 1
+    aug_Y = torch.cat([ideal, neg, anti], dim=0)
+    total_volume = (anti - ideal).prod()
+    cell = torch.zeros(2, m, dtype=torch.long)
+    cell[1] = p + 1
+    stack = [cell]
+    hyper = []
+    while stack:
+        cell = stack.pop()
+        idcs = aug_idcs[cell, outcome]                 # [2, m] rows of the augmented front
+        vals = aug_Y[idcs, outcome]                    # [2, m]
+        if bool((vals[1] <= neg).any(dim=1).all()):
+            hyper.append(idcs)
+        elif bool((vals[0] <= neg).any(dim=1).all()):
+            idx_dist = cell[1] - cell[0]
+            volume = float((vals[1] - vals[0]).prod())
+            if bool((idx_dist > 1).any()) and (volume / float(total_volume)) > alpha:
+                length, longest = torch.max(idx_dist, dim=0)
+                length, longest = int(length), int(longest)
+                n1 = int(round(length / 2.0))
+                n2 = length - n1
+                for bound, delta in ((1, -n1), (0, n2)):
+                    child = cell.clone()
+                    child[bound, longest] += delta
+                    stack.append(child)
+    if not hyper:
+        return torch.zeros(0, m, dtype=DT), torch.zeros(0, m, dtype=DT)
+    H = torch.stack(hyper)                              # [C, 2, m]
+    aug2 = torch.cat([torch.full((1, m), -inf, dtype=DT), neg, (-ref).view(1, m)], dim=0)
+    lo_min = aug2[H[:, 0], outcome]
+    up_min = aug2[H[:, 1], outcome]
+    return -up_min, -lo_min
+
+
 def hypervolume(pareto_Y, ref):
     """Exact dominated hypervolume (maximisation) by slicing on the last objective."""
     Y = pareto_Y[(pareto_Y > ref).all(dim=-1)]
@@ -562,12 +618,14 @@ def hvi_inclusion_exclusion(obj, lower, upper, feas=None):
 
 class QNEHVIOracle:
     """qNoisyExpectedHypervolumeImprovement(model, ref_point, X_baseline, prune_baseline,
-    objective, constraints, eta, alpha=0, cache_root=True, X_pending) -- alpha=0 only."""
+    objective, constraints, eta, alpha, cache_root=True, X_pending); alpha > 0 switches the per-sample box decomposition of
+    more than two objectives to the approximate binary partitioning (`partition_binary`)."""
 
     def __init__(self, gp: GPOracle, ref_point, X_baseline, objective_ops, constraints=None,
                  mc_samples=512, seed=1234, prune_baseline=True, prune_samples=2048,
-                 prune_seed=4321, X_pending=None, base_samples_baseline=None, cell_bounds=None):
+                 prune_seed=4321, X_pending=None, base_samples_baseline=None, cell_bounds=None, alpha=0.0):
         self.gp = gp
+        self.alpha = float(alpha)
         self.ref = torch.as_tensor(ref_point, dtype=DT)
         self.ops = objective_ops
         self.cons = constraints
@@ -640,7 +698,7 @@ class QNEHVIOracle:
                 lo, up, order = partition_2d(P, self.ref)
                 fronts.append(idx[order])
             else:
-                lo, up = partition_nd(P, self.ref)
+                lo, up = partition_binary(P, self.ref, self.alpha) if self.alpha > 0 else partition_nd(P, self.ref)
                 fronts.append(idx)
             lows.append(lo)
             ups.append(up)

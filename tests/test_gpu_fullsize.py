@@ -159,7 +159,8 @@ def test_packed_wire_format_of_the_host_entry_point():
     dense, bits = acq.pack_rows(X.numpy())
     assert dense.shape == (6000, 12) and bits.shape == (6000, 32) and bits.dtype == np.uint64
     # the library's packer against numpy's: bit k of a row = column bit_cols[k], little-endian inside each 64-bit word
-    ref_bits = np.packbits(X.numpy().reshape(6000, -1)[:, bc].astype(np.uint8), axis=1, bitorder="little").view(np.uint64)
+    ref_bits = np.ascontiguousarray(np.packbits(X.numpy().reshape(6000, -1)[:, bc].astype(np.uint8), axis=1,
+                                                bitorder="little")).view(np.uint64)
     assert np.array_equal(bits, ref_bits)
     v_packed = acq.forward_host_packed(dense, bits, q=1)
     assert np.allclose(v_packed, v_dev, **tol)

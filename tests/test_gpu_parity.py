@@ -498,9 +498,12 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         DeviceGPState(X, [SingleTaskGPSpec(kernel=K.TanimotoKernel([0, 1, 2]), y=np.zeros(10))])  # not 0/1 bits
     st = DeviceGPState(X, [SingleTaskGPSpec(kernel=K.RBFKernel([0, 1, 2], [0.5]), y=X[:, 0])] * 2).factorize()
+    with pytest.raises(ValueError):      # BoFire's data model bounds alpha to [0, 0.5]
+        A.qNoisyExpectedHypervolumeImprovement(st, [0, 0], X, MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]),
+                                               alpha=0.7)
     with pytest.raises(NotImplementedError):
         A.qNoisyExpectedHypervolumeImprovement(st, [0, 0], X, MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]),
-                                               alpha=0.1)
+                                               cache_root=False)
     acq = A.qNoisyExpectedHypervolumeImprovement(st, [0, 0], X, MultiObjective([MaximizeObjective(0), MaximizeObjective(1)]),
                                                  mc_samples=16, seed=0)
     with pytest.raises(ValueError):
@@ -658,3 +661,58 @@ def test_int8_guard_redoes_candidates_planted_next_to_training_points():
     Xnear = (Xt[torch.randint(0, Xt.shape[0], (b * q,), generator=g)] + 1e-6 * torch.randn(b * q, p["d"], dtype=DT, generator=g))
     acq(Xnear.clamp(0.0, 1.0).view(b, q, -1).to(st.device))
     assert st.debug_get("ozaki_check", capacity=16)[0] == -1.0
+
+
+@pytest.mark.parametrize("kind,alpha", [("dtlz2", 0.01), ("dtlz2", 0.1), ("zdt1", 0.05)])
+def test_qnehvi_approximate_partitioning_alpha(kind, alpha):
+    """BoFire's `alpha` (data_models/strategies/predictives/qnehvi.py:19 -> qnehvi.py:50): approximate binary partitioning
+    ([UPSTREAM] NondominatedPartitioning(alpha)) of every MC sample's front for more than two objectives; exact decomposition
+    for two.  Device cell lists must equal the oracle restatement's bit for bit (same traversal order), values to 1e-8."""
+    p = small_problem(kind)
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    from everest_b200 import acquisition as A
+
+    ops = [P.op_to_oracle(o) for o in p["objective"].ops]
+    acq_o = O.QNEHVIOracle(gp, p["ref_point"], p["X"], ops, mc_samples=p["S"], seed=p["sampler_seed"], prune_baseline=True,
+                           prune_samples=256, prune_seed=p["sampler_seed"] + 7919, alpha=alpha)
+    acq_d = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], torch.as_tensor(p["X"]), p["objective"], prune_baseline=True,
+                                                   alpha=alpha, mc_samples=p["S"], seed=p["sampler_seed"], prune_samples=256)
+    lo, up, nc = acq_d.cell_bounds()
+    assert nc.tolist() == acq_o.n_cells.tolist()
+    for s in range(p["S"]):
+        c = int(nc[s])
+        assert torch.equal(lo[s, :c], acq_o.cell_lower[s, :c]) and torch.equal(up[s, :c], acq_o.cell_upper[s, :c]), s
+    X = Cf.candidates(p, 16)
+    v_o = acq_o.forward(X)
+    v_d = acq_d(X.to(st.device)).cpu()
+    assert float((v_d - v_o).abs().max()) < 1e-8 * max(float(v_o.abs().max()), 1e-12)
+    # dropping cells can only lose hypervolume improvement: the approximate value never exceeds the exact one
+    acq_e = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], torch.as_tensor(p["X"]), p["objective"], prune_baseline=True,
+                                                   alpha=0.0, mc_samples=p["S"], seed=p["sampler_seed"], prune_samples=256)
+    v_e = acq_e(X.to(st.device)).cpu()
+    assert bool((v_d <= v_e + 1e-12 * float(v_e.abs().max())).all())
+    if len(p["ref_point"]) == 2:
+        assert torch.equal(v_d, v_e)
+
+
+def test_exact_binary_partitioning_equals_local_upper_bound_decomposition():
+    """Two different published algorithms (Couckuyt 2012 binary partitioning with threshold 0, Lacour 2017 local upper
+    bounds) must tile the same non-dominated region: identical qNEHVI values up to the summation order over the cells."""
+    from everest_b200 import acquisition as A
+
+    p = small_problem("dtlz2")
+    st = Cf.build_state(p)
+    X = Cf.candidates(p, 16).to(st.device)
+    acq_l = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], torch.as_tensor(p["X"]), p["objective"], prune_baseline=True,
+                                                   mc_samples=p["S"], seed=p["sampler_seed"], prune_samples=256)
+    v_l = acq_l(X).cpu()
+    n_l = acq_l.cell_bounds()[2]
+    acq_b = A.qNoisyExpectedHypervolumeImprovement(st, p["ref_point"], torch.as_tensor(p["X"]), p["objective"], prune_baseline=True,
+                                                   mc_samples=p["S"], seed=p["sampler_seed"], prune_samples=256)
+    acq_b.alpha = -1.0          # the C ABI's spelling of "binary partitioning, nothing dropped"
+    acq_b._reprepare()
+    v_b = acq_b(X).cpu()
+    n_b = acq_b.cell_bounds()[2]
+    assert int(n_b.sum()) != int(n_l.sum())                       # different cell lists ...
+    assert float((v_b - v_l).abs().max()) < 1e-12 * float(v_l.abs().max())   # ... same region
