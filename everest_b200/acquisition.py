@@ -38,6 +38,10 @@ class _DeviceAcquisition:
     # [UPSTREAM] botorch's @concatenate_pending_points: acquisition functions without a cached baseline score the joint
     # batch cat(X, X_pending); the NEHVI family overrides set_X_pending and folds the points into its baseline instead
     _PENDING_CONCAT = True
+    joint_fallback = True      # BoTorch's joint re-sampling when the cached-root update fails (forward only)
+    _force_fallback = False    # tests: re-score every q-batch through the fallback
+    last_resampled = 0
+    nb = 0
 
     def set_X_pending(self, X_pending=None):
         if X_pending is None:
@@ -108,6 +112,15 @@ class _DeviceAcquisition:
             L.check(self.model.lib.bo_acqf_forward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
                                                    _dev_ptr(info), _stream()))
         self.last_info = info
+        if self.joint_fallback and (self.nb > 0 or self._force_fallback):
+            # [UPSTREAM] sample_cached_cholesky: q-batches whose q x q conditional root exhausted the jitter ladder are
+            # re-scored from the joint posterior over (X_baseline, X) -- bo_acqf_resample_flagged reads `info` back (one
+            # synchronisation; skip it with `acq.joint_fallback = False` when launches must stay asynchronous)
+            n = C.c_int32(0)
+            with torch.cuda.device(self.model.device):
+                L.check(self.model.lib.bo_acqf_resample_flagged(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
+                                                                _dev_ptr(info), C.byref(n), _stream()))
+            self.last_resampled = int(n.value)
         return out.cpu() if on_cpu else out
 
     def __call__(self, X):

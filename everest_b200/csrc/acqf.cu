@@ -800,6 +800,27 @@ int launch_partition_binary(const double* obj, const unsigned char* front, int n
   return BO_OK;
 }
 
+// Joint re-sampling fallback (capi.cu bo_acqf_resample_flagged): rows n_b .. n_b + q - 1 of the lower Cholesky root of the
+// JOINT posterior covariance over (baseline, q-batch) are exactly [bl | br] of sample_cached_cholesky -> conditional-root
+// slot `slot` of output m ([b, M, q, n_b + q]); the q-batch's posterior means go to mu [b * q, M].
+__global__ void joint_rows_to_root_kernel(const double* __restrict__ rootj, int ldn, const double* __restrict__ meanj, int nb,
+                                          int q, int M, int m, int slot, double* __restrict__ root, double* __restrict__ mu) {
+  const int nr = nb + q;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < q * nr; idx += gridDim.x * blockDim.x) {
+    const int j = idx / nr, k = idx - j * nr;
+    root[(((size_t)slot * M + m) * q + j) * nr + k] = (k <= nb + j) ? rootj[(size_t)(nb + j) * ldn + k] : 0.0;
+  }
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < q; j += gridDim.x * blockDim.x)
+    mu[((size_t)slot * q + j) * M + m] = meanj[(size_t)(nb + j) * M + m];
+}
+int launch_joint_rows_to_root(const double* rootj, int ldn, const double* meanj, int nb, int q, int M, int m, int slot,
+                              double* root, double* mu, cudaStream_t st, LaunchCounter* lc) {
+  joint_rows_to_root_kernel<<<1, 256, 0, st>>>(rootj, ldn, meanj, nb, q, M, m, slot, root, mu);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 // mask[e] = front flag as int32; ideal[o] = max over the front (or ref if the front is empty)
 __global__ void front_to_mask_kernel(const unsigned char* __restrict__ front, int n, int* __restrict__ mask) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

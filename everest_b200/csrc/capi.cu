@@ -168,6 +168,8 @@ struct bo_state {
   int* pin_count = nullptr;    // pinned: the guard's counter of flagged q-batches
   cudaEvent_t oz_event = nullptr;
   DevBuf wsLbfgs, wsLbBounds, wsLbGrad;   // on-device multi-start refinement (lbfgs.cu)
+  DevBuf Xb_raw, wsXfull, wsMeanJ;        // joint re-sampling fallback: baseline points, (baseline, q-batch), joint mean
+  int force_fallback = 0;                 // test switch: treat every q-batch as flagged
   DevBuf wsJointRoot, wsJointCov, wsJointDinv;   // joint posterior root / covariance of the pruning passes
   PrepBuf jointPrep;
   int* pin_lb = nullptr;                  // pinned: progress counters of bo_acqf_optimize
@@ -227,6 +229,7 @@ extern "C" void bo_state_destroy(bo_state* st) {
   if (st->pin_count) cudaFreeHost(st->pin_count);
   if (st->oz_event) cudaEventDestroy(st->oz_event);
   st->wsLbfgs.release(); st->wsLbBounds.release(); st->wsLbGrad.release();
+  st->Xb_raw.release(); st->wsXfull.release(); st->wsMeanJ.release();
   st->wsJointRoot.release(); st->wsJointCov.release(); st->wsJointDinv.release(); st->jointPrep.release();
   if (st->pin_lb) cudaFreeHost(st->pin_lb);
   for (auto& e : st->lb_events) cudaEventDestroy(e);
@@ -642,6 +645,9 @@ static int prepare_baseline(bo_state* st, const double* Xb_dev, int nb, const do
   const int M = st->M, ldk = st->ldk, ldlb = round_up(std::max(nb, 1), 16);
   st->nb = nb; st->S = S; st->ldlb = ldlb;
   st->baseline_f_valid = false;
+  // raw baseline points: the joint re-sampling fallback scores (baseline, q-batch) together
+  RC(st->Xb_raw.ensure((size_t)std::max(nb, 1) * st->d * 8));
+  if (nb > 0) CUDA_CHECK_RET(cudaMemcpyAsync(st->Xb_raw.p, Xb_dev, (size_t)nb * st->d * 8, cudaMemcpyDeviceToDevice, s));
   RC(st->mean_b.ensure((size_t)std::max(nb, 1) * M * 8));
   RC(st->zbT.ensure((size_t)std::max(nb, 1) * M * S * 8));
   RC(st->zbM.ensure((size_t)M * S * ldlb * 8, true));
@@ -856,6 +862,8 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
   } else if (nm == "tau_relu") {
     if (!(value > 0.0)) { bo_set_error("tau_relu must be > 0"); return BO_ERR_INVALID; }
     st->tau_relu = value;
+  } else if (nm == "force_joint_fallback") {
+    st->force_fallback = value != 0.0;   // tests: bo_acqf_resample_flagged re-scores every q-batch
   } else if (nm == "partition_alpha") {
     // BoFire's `alpha` (data_models/strategies/predictives/qnehvi.py:19): read by the NEXT prepare call.  0 = exact
     // decomposition (local upper bounds); > 0 = approximate binary partitioning for more than two objectives (two objectives
@@ -1254,6 +1262,85 @@ extern "C" int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32
                                         double* out_dev, double* dX_dev, int32_t* info_dev, void* stream) {
   if (!dX_dev) { bo_set_error("forward_backward: dX_dev is NULL"); return BO_ERR_INVALID; }
   return acqf_run(st, X_dev, b, q, zq_dev, out_dev, dX_dev, info_dev, stream);
+}
+
+// [UPSTREAM] sample_cached_cholesky's fallback: when the q x q conditional root of a q-batch cannot be
+// factorised even with jitter 1e-3 (info = 1 from bo_acqf_forward, value NaN), BoTorch catches the NotPSDError / NanError, warns
+// and samples the JOINT posterior over (X_baseline, X) instead -- psd_safe_cholesky of the full (n_b + q) x (n_b + q)
+// covariance with its own jitter ladder on the whole diagonal.  This entry point does that for the flagged q-batches of the
+// last forward call: it reads info_dev back (one synchronisation; the flagged set is expected to be empty), and for every
+// flagged q-batch factorises the joint covariance per output, takes the last q rows of the root as [bl | br], and re-scores
+// the q-batch with the same base samples and the cached cells.  info stays 1 for a re-scored q-batch (the BoTorch warning),
+// becomes 2 when the joint factorisation fails as well (BoTorch: NotPSDError propagates; the value stays NaN).
+// n_resampled (HOST, may be NULL) receives the number of re-scored q-batches.
+extern "C" int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                                        double* out_dev, int32_t* info_dev, int32_t* n_resampled, void* stream) {
+  if (!st || !st->factorized || st->acqf_kind == 0) { bo_set_error("resample_flagged before prepare"); return BO_ERR_STATE; }
+  if (!X_dev || !out_dev || !info_dev || !zq_dev) { bo_set_error("resample_flagged: null argument"); return BO_ERR_INVALID; }
+  if (n_resampled) *n_resampled = 0;
+  if (b < 1) return BO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = st->nb, M = st->M, d = st->d, S = st->S;
+  if (nb == 0 && !st->force_fallback) return BO_OK;   // no cached root: the ladder already WAS the joint factorisation
+  std::vector<int> info((size_t)b);
+  CUDA_CHECK_RET(cudaMemcpyAsync(info.data(), info_dev, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  std::vector<int> flagged;
+  for (int i = 0; i < b; ++i) if (info[i] != 0 || st->force_fallback) flagged.push_back(i);
+  if (flagged.empty()) return BO_OK;
+  const int n = nb + q, ldn = round_up(n, 16), nr = nb + q;
+  RC(st->wsXfull.ensure((size_t)n * d * 8));
+  RC(st->wsMeanJ.ensure((size_t)n * M * 8));
+  RC(st->wsV.ensure((size_t)n * st->ldk * 8, true));
+  RC(st->wsZqT.ensure((size_t)q * M * S * 8));
+  RC(launch_transpose_base_samples(zq_dev, S, q, M, st->wsZqT.as<double>(), nullptr, 0, s, &st->lc));
+  RC(st->wsRoot.ensure((size_t)M * q * nr * 8));
+  RC(st->wsMu.ensure((size_t)q * M * 8));
+  RC(st->wsJit.ensure((size_t)M * sizeof(int)));
+  RC(st->wsPartial.ensure((size_t)((S + 31) / 32) * 8));
+  if (nb > 0) CUDA_CHECK_RET(cudaMemcpyAsync(st->wsXfull.p, st->Xb_raw.p, (size_t)nb * d * 8, cudaMemcpyDeviceToDevice, s));
+  int done = 0;
+  for (int i : flagged) {
+    CUDA_CHECK_RET(cudaMemcpyAsync(st->wsXfull.as<double>() + (size_t)nb * d, X_dev + (size_t)i * q * d, (size_t)q * d * 8,
+                                   cudaMemcpyDeviceToDevice, s));
+    bool ok = true;
+    for (int m = 0; m < M && ok; ++m) {
+      PrepD pd;
+      int inf = 0; double jit = 0.0;
+      RC(joint_root(st, m, st->wsXfull.as<double>(), n, ldn, st->jointPrep, &pd, st->wsMeanJ.as<double>(), st->wsJointRoot, st->wsJointCov,
+                    st->wsV.as<double>(), &inf, &jit, s));
+      if (inf != 0) { ok = false; break; }
+      RC(launch_joint_rows_to_root(st->wsJointRoot.as<double>(), ldn, st->wsMeanJ.as<double>(), nb, q, M, m, 0,
+                                   st->wsRoot.as<double>(), st->wsMu.as<double>(), s, &st->lc));
+    }
+    int new_info = 1;
+    if (!ok) new_info = 2;
+    else {
+      CUDA_CHECK_RET(cudaMemsetAsync(st->wsJit.p, 0, (size_t)M * sizeof(int), s));
+      McArgs ma;
+      ma.b = 1; ma.q = q; ma.nb = nb; ma.M = M; ma.S = S; ma.od = st->od; ma.root = st->wsRoot.as<double>();
+      ma.mu = st->wsMu.as<double>(); ma.zbT = st->zbT.as<double>(); ma.zqT = st->wsZqT.as<double>();
+      ma.cell_lo = st->cell_lo.as<double>(); ma.cell_up = st->cell_up.as<double>(); ma.ncells = st->ncells.as<int>();
+      ma.cells_shared = st->cells_shared; ma.best_f = st->best_f; ma.out = out_dev + i;
+      ma.variant = st->acqf_kind == 3 ? st->scalar_variant : st->log_hvi; ma.vparam = st->vparam;
+      ma.best_f_s = st->noisy_scalar ? st->best_f_s.as<double>() : nullptr; ma.tau_relu = st->tau_relu; ma.tau_max = st->tau_max;
+      ma.info_in = st->wsJit.as<int>(); ma.info_out = nullptr;
+      ma.Fp = nullptr; ma.fp_stride = 0;
+      ma.partial = st->wsPartial.as<double>();
+      if (st->acqf_kind == 3) RC(launch_mc_scalar(ma, s, &st->lc));
+      else if (st->log_hvi) RC(launch_mc_loghvi(ma, s, &st->lc));
+      else {
+        size_t ow = mc_hvi_obj_ws_bytes(ma, st->max_cells);
+        if (ow) RC(st->wsObjW.ensure(ow));
+        RC(launch_mc_hvi(ma, st->max_cells, ow ? st->wsObjW.as<double>() : nullptr, s, &st->lc));
+      }
+      ++done;
+    }
+    CUDA_CHECK_RET(cudaMemcpyAsync(info_dev + i, &new_info, sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));    // new_info lives on this stack frame
+  }
+  if (n_resampled) *n_resampled = done;
+  return BO_OK;
 }
 
 extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int32_t q_free, const double* lb,

@@ -209,6 +209,15 @@ int bo_acqf_forward(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
 int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
                              double* out_dev, double* dX_dev, int32_t* info_dev, void* stream);
 
+/* [UPSTREAM] sample_cached_cholesky's fallback: BoTorch catches the NotPSDError / NanError of the q x q conditional root and
+ * samples the joint posterior over (X_baseline, X) instead.  Call after bo_acqf_forward with the same arguments: q-batches
+ * whose info is non-zero are re-scored from the Cholesky root of the joint (n_b + q) x (n_b + q) covariance (own jitter
+ * ladder on the whole diagonal), same base samples, same cached cells.  info_dev[i] stays 1 for a re-scored q-batch (BoTorch
+ * warns there) and becomes 2 when the joint factorisation fails too (BoTorch: NotPSDError; the value stays NaN).  One
+ * synchronisation (info is read back); n_resampled (HOST, may be NULL) = number of re-scored q-batches. */
+int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev, double* out_dev,
+                             int32_t* info_dev, int32_t* n_resampled, void* stream);
+
 /* On-device multi-start refinement: replaces the host loop of [UPSTREAM] botorch.generation.gen_candidates_scipy that
  * BotorchStrategy._optimize_acqf_continuous drives through optimize_acqf (botorch.py:384-405) for the box-constrained case
  * (bounds + fixed features; linear / nonlinear constraints stay on the host SLSQP path).  X_dev [r, q_tot, d] holds the r

@@ -752,6 +752,36 @@ class QNEHVIOracle:
         br, jit = psd_safe_cholesky(Sqq - bl @ bl.transpose(-1, -2), return_jitter=True)
         return bl, br, jit
 
+    def joint_root_rows(self, X):
+        """[UPSTREAM] the fallback of sample_cached_cholesky (`except (NanError, NotPSDError)` in _get_f_X_samples): the joint
+        posterior over (X_baseline, X) is factorised as a whole -- psd_safe_cholesky of the (n_b + q) x (n_b + q) covariance,
+        jitter on the whole diagonal -- and the samples of the q new points are the last q rows of  mu + L z  with the SAME
+        base samples z = [z_b; z_q].  Returns (mu [b, q, M], bl [M, b, q, n_b], br [M, b, q, q]) = those rows, so that
+        f_q = mu + bl z_b + br z_q as in the cached path (identical to it whenever no jitter is needed)."""
+        b, q, d = X.shape
+        gp, nb = self.gp, self.nb
+        mu = torch.empty(b, q, gp.M, dtype=DT)
+        bl = torch.empty(gp.M, b, q, nb, dtype=DT)
+        br = torch.empty(gp.M, b, q, q, dtype=DT)
+        for i in range(b):
+            mean, cov = gp.posterior(torch.cat([self.Xb, X[i]], dim=0))
+            Lfull = psd_safe_cholesky(cov)                        # [M, nb + q, nb + q]
+            mu[i] = mean[nb:]
+            bl[:, i] = Lfull[:, nb:, :nb]
+            br[:, i] = Lfull[:, nb:, nb:]
+        return mu, bl, br
+
+    def forward_joint(self, X, zq=None):
+        """forward() with every q-batch scored through the joint re-sampling fallback."""
+        X = torch.as_tensor(X, dtype=DT)
+        if zq is None:
+            zq = self.base_samples_q(X.shape[1])
+        mu, bl, br = self.joint_root_rows(X)
+        f = mu.unsqueeze(0) + torch.einsum("mbqk,skm->sbqm", bl, self.zb) + torch.einsum("mbqk,skm->sbqm", br, zq)
+        obj = multi_objective(self.ops, f)
+        feas = smoothed_feasibility(self.cons, f) if self.cons else None
+        return hvi_inclusion_exclusion(obj, self.cell_lower, self.cell_upper, feas)
+
     def sample_q(self, X, zq=None):
         """f_q samples [S, b, q, M] consistent with the cached baseline samples."""
         b, q, _ = X.shape
