@@ -361,9 +361,29 @@ def kernel_rooflines(p, st, acq, b, avg, peaks, fp64_peak, int8_peak, used_int8,
               "achieved = algorithmic FP64 flops M b q (N^2 + 2 N (1 + n_b)) / kernel time")
     # ---- K(X*,X): writes 7 digit planes (INT8 path) or the FP64 matrix; one exp per element ----
     bytes_x = M * rows * float(ldk) * (7.0 if used_int8 else 8.0)
-    entry("crosscov", "crosscov_fast_kernel / crosscov_kernel2 (K(X*,X): distances on FP64 DMMA, kernel function, digit slicing)",
-          "crosscov", "hbm", bytes_x, 1e9, "GB/s", hbm, hbm_src,
-          "algorithmic bytes = M b q ldk x (7 digit planes | 8 B FP64) written once; reads (candidates, training rows) are L2-resident")
+    from everest_b200 import kernels as Kn
+
+    tani_words = 0
+    for o in p["outputs"]:
+        for lf in Kn.flatten(o["kernel"]).leaves:          # parameter-free Tanimoto leaves are shared: counted once
+            if isinstance(lf, Kn.TanimotoKernel):
+                tani_words += (len(lf.active_dims) + 63) // 64
+    if tani_words:
+        # fingerprint inner products <x, x'> = popc(x & x'): 2 x 32-bit POPC per 64-bit word and pair
+        popc = 2.0 * rows * float(N) * tani_words
+        clk = 1.965e9
+        entry("crosscov", "crosscov_kernel2 (kernel trees: Tanimoto by AND + POPC over bit-packed fingerprints, Hamming on codes, "
+              "continuous leaves on FP64 DMMA, kernel functions, sum of products)", "crosscov_kernel2", "alu", popc, 1e9, "GPOPC/s",
+              148 * 16 * clk / 1e9, "derived, not measured: 16 POPC lanes per SM and clock (POPC issues at 1/8 of the warp rate, ncu "
+              "profiles/r01_s3_ncu_summary.txt) x 148 SMs x 1.965 GHz", "algorithmic 32-bit POPCs = 2 b q N W (W = 64-bit words per fingerprint)")
+        if "crosscov" in out:
+            ms, cnt = avg["crosscov"]
+            out["crosscov"]["hbm_write_gbs"] = bytes_x / (ms * 1e-3) / 1e9
+            out["crosscov"]["hbm_write_frac"] = out["crosscov"]["hbm_write_gbs"] / hbm
+    else:
+        entry("crosscov", "crosscov_fast_kernel (K(X*,X): distances on FP64 DMMA, kernel function, digit slicing)",
+              "crosscov_fast", "hbm", bytes_x, 1e9, "GB/s", hbm, hbm_src,
+              "algorithmic bytes = M b q ldk x (7 digit planes | 8 B FP64) written once; reads (candidates, training rows) are L2-resident")
     # ---- MC value: samples -> objectives -> inclusion-exclusion over the cells ----
     if p["acqf"] == "qnehvi":
         Mo = len(p["ref_point"])
@@ -376,8 +396,10 @@ def kernel_rooflines(p, st, acq, b, avg, peaks, fp64_peak, int8_peak, used_int8,
               "tensor", f_hvi, 1e12, "TFLOP/s", fp64_peak,
               "FP64 ALU (DFMA) rate = the FP64 tensor-pipe rate on this part (tools/fp64_peak: 37.0 TFLOP/s both); denominator = "
               "cuBLAS DGEMM measured in this run",
-              f"algorithmic flops = b S C (2^q - 1) 3 M_o + 2 b S M q (n_b + q), C = mean cells per sample = {cbar:.1f}; the kernel "
-              "skips cells and subsets that cannot overlap, so its executed flops are lower")
+              f"algorithmic flops = b S C (2^q - 1) 3 M_o + 2 b S M q (n_b + q) (SURVEY.md 8d), C = mean cells per sample = {cbar:.1f}; "
+              "the kernel skips cells and subsets that cannot overlap (their contribution is exactly 0), so it EXECUTES far fewer "
+              "flops than this count: a fraction above 1 is work avoided, not pipe throughput -- ncu_fp64_pipe_active_pct (committed "
+              "ncu capture) is how busy the FP64 pipe really is")
     else:
         f_sc = float(b) * S * q * (M * q + 60.0)
         entry("mc_acqf", "mc_scalar_kernel (MC samples, objective, log-space EI)", "mc_scalar", "tensor", f_sc, 1e12, "TFLOP/s",

@@ -1527,7 +1527,15 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
     const int min_b = std::max(1, 2048 / q);
     // inputs below 8 MiB cross PCIe in ~0.3 ms: nothing worth hiding, and whole-batch launches fill the GPU better
     if (b <= 2 * min_b || (double)n_rows * host_bytes < (double)((size_t)8 << 20)) chunk_b.push_back(b);
-    else if (r < 0.15) {
+    else if (mode == HOST_PACK) {
+      // the packer reads the float64 rows at ~70 GB/s with 8 threads (270 MB of config 5 in 4 ms, measured), a third of the
+      // compute time, and small chunks cost GPU efficiency (2048 q-batches: 2.0 ms instead of 1.3): two chunks, the first a
+      // quarter, so that the rest is packed by the time the first has been scored (8 equal chunks: 16.7 ms per config-5
+      // screen; this plan: tools/probe_host_mixed.py)
+      const int first = std::max(min_b, b / 4);
+      chunk_b.push_back(first);
+      chunk_b.push_back(b - first);
+    } else if (r < 0.15) {
       // EVEREST_HOST_FIRST_DIV=n: first chunk = b / n (default 8); EVEREST_HOST_THREE=1: a third, intermediate
       // chunk of three times the first (experiment switches, read once).  Measured on config 3 (tools/exp_host.sh):
       // b/8 9.46 ms per screen, b/4 9.62, b/16 9.60, b/16 + 3b/16 + rest 9.78, b/32 three-way 10.27: b/8 stays.

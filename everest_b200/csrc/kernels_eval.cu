@@ -389,6 +389,8 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
   const int n_ct_total = (ld + CC_TILE - 1) / CC_TILE;
   const int n_ct = min(CC3_CT, n_ct_total - ct0);
 
+  __shared__ double2 exptab[32];
+  exp_tab_load(exptab);                 // visible after the first __syncthreads() of the column-tile loop
   cc3_load_tile<CC_TILE>(As, Aq, dpad, row0, n_rows, tid);
   cc3_load_tile<CC_TILE>(Bs[0], Bt, dpad, ct0 * CC_TILE, n_cols, tid);
   cp_async_commit();
@@ -443,7 +445,7 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         if (grB == gc + 1) st[3] = 0.0;
       }
       double lv[4];
-      leaf_value_from_stat_n<4>(KIND, st, lv);
+      leaf_value_from_stat_tab_n<4>(KIND, st, lv, exptab);
       const bool c0 = gc < n_cols, c1 = gc + 1 < n_cols, okA = grA < n_rows, okB = grB < n_rows;
       const double vA0 = (okA && c0) ? coef * lv[0] : 0.0, vA1 = (okA && c1) ? coef * lv[1] : 0.0;
       const double vB0 = (okB && c0) ? coef * lv[2] : 0.0, vB1 = (okB && c1) ? coef * lv[3] : 0.0;
