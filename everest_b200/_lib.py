@@ -86,6 +86,7 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "bo_acqf_resample_flagged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(C.c_int32), C.c_void_p]),
+    "bo_acqf_last_resampled": (C.c_int32, [C.c_void_p]),
     "bo_acqf_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_void_p,
                                    C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "bo_acqf_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -38,7 +38,6 @@ class _DeviceAcquisition:
     # [UPSTREAM] botorch's @concatenate_pending_points: acquisition functions without a cached baseline score the joint
     # batch cat(X, X_pending); the NEHVI family overrides set_X_pending and folds the points into its baseline instead
     _PENDING_CONCAT = True
-    joint_fallback = True      # BoTorch's joint re-sampling when the cached-root update fails (forward only)
     _force_fallback = False    # tests: re-score every q-batch through the fallback
     last_resampled = 0
     nb = 0
@@ -112,10 +111,12 @@ class _DeviceAcquisition:
             L.check(self.model.lib.bo_acqf_forward(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
                                                    _dev_ptr(info), _stream()))
         self.last_info = info
-        if self.joint_fallback and (self.nb > 0 or self._force_fallback):
-            # [UPSTREAM] sample_cached_cholesky: q-batches whose q x q conditional root exhausted the jitter ladder are
-            # re-scored from the joint posterior over (X_baseline, X) -- bo_acqf_resample_flagged reads `info` back (one
-            # synchronisation; skip it with `acq.joint_fallback = False` when launches must stay asynchronous)
+        # [UPSTREAM] sample_cached_cholesky: q-batches whose q x q conditional root exhausted the jitter ladder are re-scored
+        # from the joint posterior over (X_baseline, X).  bo_acqf_forward does it by itself (option "joint_fallback"): the
+        # counter of exhausted ladders is read while the MC kernels still run.  The explicit call below is the test hook that
+        # pushes EVERY q-batch through the fallback.
+        self.last_resampled = int(self.model.lib.bo_acqf_last_resampled(self.model.handle))
+        if self._force_fallback:
             n = C.c_int32(0)
             with torch.cuda.device(self.model.device):
                 L.check(self.model.lib.bo_acqf_resample_flagged(self.model.handle, _dev_ptr(Xd), b, q, _dev_ptr(zq), _dev_ptr(out),
@@ -173,18 +174,27 @@ class _DeviceAcquisition:
         self._check_active()
         d = self.model.d
         q_free = X.shape[1]
-        Xd = self._with_pending(X.detach().to(self.model.device)).contiguous().clone()
-        r, q_tot, _ = Xd.shape
         lb = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(lower_bounds).cpu(), dtype=np.float64), (d,)))
         ub = np.ascontiguousarray(np.broadcast_to(np.asarray(torch.as_tensor(upper_bounds).cpu(), dtype=np.float64), (d,)))
-        out = torch.empty(r, dtype=torch.double, device=self.model.device)
         stats = (C.c_int32 * 4)()
-        zq = self.base_samples_q(q_tot)
-        with torch.cuda.device(self.model.device):
+        # the loop replays a CUDA graph of one evaluation; the legacy default stream cannot be captured, so the call runs
+        # on a side stream ordered after the caller's stream (the C call returns synchronised: it reads its statistics back)
+        dev = self.model.device
+        cur = torch.cuda.current_stream(dev)
+        side = getattr(self.model, "_side_stream", None)
+        if side is None:
+            side = self.model._side_stream = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.device(dev), torch.cuda.stream(side):
+            Xd = self._with_pending(X.detach().to(dev)).contiguous().clone()
+            r, q_tot, _ = Xd.shape
+            out = torch.empty(r, dtype=torch.double, device=dev)
+            zq = self.base_samples_q(q_tot)
             L.check(self.model.lib.bo_acqf_optimize(self.model.handle, _dev_ptr(Xd), r, q_tot, q_free,
                                                     lb.ctypes.data_as(L.c_double_p), ub.ctypes.data_as(L.c_double_p), _dev_ptr(zq),
                                                     int(maxiter), int(history), float(pgtol), float(ftol), _dev_ptr(out), stats,
-                                                    _stream()))
+                                                    C.c_void_p(side.cuda_stream)))
+        cur.wait_stream(side)
         info = {"n_acqf_evals": int(stats[0]) * r, "n_steps": int(stats[0]), "nit": int(stats[1]), "n_converged": int(stats[2]),
                 "n_budget": int(stats[3])}
         return Xd[:, :q_free].contiguous(), out, info

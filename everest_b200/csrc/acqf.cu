@@ -800,6 +800,20 @@ int launch_partition_binary(const double* obj, const unsigned char* front, int n
   return BO_OK;
 }
 
+__global__ void count_nonzero_kernel(const int* __restrict__ v, int n, int* __restrict__ count) {
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += v[i] != 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+int launch_count_nonzero(const int* v, int n, int* count, cudaStream_t st, LaunchCounter* lc) {
+  if (n <= 0) return BO_OK;
+  count_nonzero_kernel<<<std::min((n + 255) / 256, 148), 256, 0, st>>>(v, n, count);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 // Joint re-sampling fallback (capi.cu bo_acqf_resample_flagged): rows n_b .. n_b + q - 1 of the lower Cholesky root of the
 // JOINT posterior covariance over (baseline, q-batch) are exactly [bl | br] of sample_cached_cholesky -> conditional-root
 // slot `slot` of output m ([b, M, q, n_b + q]); the q-batch's posterior means go to mu [b * q, M].

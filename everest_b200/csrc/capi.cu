@@ -170,10 +170,17 @@ struct bo_state {
   DevBuf wsLbfgs, wsLbBounds, wsLbGrad;   // on-device multi-start refinement (lbfgs.cu)
   DevBuf Xb_raw, wsXfull, wsMeanJ;        // joint re-sampling fallback: baseline points, (baseline, q-batch), joint mean
   int force_fallback = 0;                 // test switch: treat every q-batch as flagged
+  int auto_fallback = 1;                  // forward: re-score flagged q-batches from the joint posterior (BoTorch's fallback)
+  int fb_resampled_last = 0;              // q-batches the last forward call re-scored
+  DevBuf wsInfoOut, wsFbCount;
+  int* pin_fb = nullptr;
+  cudaEvent_t fb_event = nullptr;
   DevBuf wsJointRoot, wsJointCov, wsJointDinv;   // joint posterior root / covariance of the pruning passes
   PrepBuf jointPrep;
   int* pin_lb = nullptr;                  // pinned: progress counters of bo_acqf_optimize
   std::vector<cudaEvent_t> lb_events;
+  int lb_launches_per_step = 0;
+  bool lb_graph_used = false;
   double tau_relu = 1e-6, tau_max = 1e-2;
   DevBuf wsOzA;  // INT8 digit planes of K(X*,X) (all outputs)
   DevBuf wsOzScratch;  // integer slab of the two-pass INT8 GEMM (ozaki.cu), one per handle
@@ -229,7 +236,9 @@ extern "C" void bo_state_destroy(bo_state* st) {
   if (st->pin_count) cudaFreeHost(st->pin_count);
   if (st->oz_event) cudaEventDestroy(st->oz_event);
   st->wsLbfgs.release(); st->wsLbBounds.release(); st->wsLbGrad.release();
-  st->Xb_raw.release(); st->wsXfull.release(); st->wsMeanJ.release();
+  st->Xb_raw.release(); st->wsXfull.release(); st->wsMeanJ.release(); st->wsInfoOut.release(); st->wsFbCount.release();
+  if (st->pin_fb) cudaFreeHost(st->pin_fb);
+  if (st->fb_event) cudaEventDestroy(st->fb_event);
   st->wsJointRoot.release(); st->wsJointCov.release(); st->wsJointDinv.release(); st->jointPrep.release();
   if (st->pin_lb) cudaFreeHost(st->pin_lb);
   for (auto& e : st->lb_events) cudaEventDestroy(e);
@@ -862,6 +871,8 @@ extern "C" int bo_acqf_set_option(bo_state* st, const char* name, double value) 
   } else if (nm == "tau_relu") {
     if (!(value > 0.0)) { bo_set_error("tau_relu must be > 0"); return BO_ERR_INVALID; }
     st->tau_relu = value;
+  } else if (nm == "joint_fallback") {
+    st->auto_fallback = value != 0.0;    // 0: flagged q-batches keep their NaN (info = 1), nothing is re-scored
   } else if (nm == "force_joint_fallback") {
     st->force_fallback = value != 0.0;   // tests: bo_acqf_resample_flagged re-scores every q-batch
   } else if (nm == "partition_alpha") {
@@ -900,6 +911,9 @@ static int ensure_kinv(bo_state* st, OutputH& o, cudaStream_t s) {
   return BO_OK;
 }
 
+extern "C" int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev,
+                                        double* out_dev, int32_t* info_dev, int32_t* n_resampled, void* stream);
+
 // forward(X[b, q, d]) -> out[b]; when dX_dev is given also d out[i] / d X[i] (each value depends on its own q-batch only)
 static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev, double* out_dev,
                     double* dX_dev, int32_t* info_dev, void* stream) {
@@ -913,6 +927,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
   }
   const int M = st->M, ldk = st->ldk, nb = st->nb, S = st->S, nr = nb + q;
   const int ldw = std::max(nb, 1);
+  if (!dX_dev) st->fb_resampled_last = 0;
   // chunk the q-batches so that the K(X*,X) workspace (all outputs) stays below ~4 GiB
   long long max_rows = std::max<long long>(((long long)4 << 30) / ((long long)ldk * 8 * M), (long long)q);
   int bchunk = (int)std::min<long long>(b, std::max<long long>(1, max_rows / q));
@@ -937,6 +952,17 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
     const double* Xc = X_dev + (size_t)b0 * q * st->d;
+    // [UPSTREAM] sample_cached_cholesky's fallback applies to the forward pass of acquisition functions with a cached root
+    const bool fb_active = st->auto_fallback && !dX_dev && nb > 0;
+    int* info_chunk = info_dev ? info_dev + b0 : nullptr;
+    if (fb_active) {
+      if (!info_chunk) { RC(st->wsInfoOut.ensure((size_t)bchunk * sizeof(int))); info_chunk = st->wsInfoOut.as<int>(); }
+      RC(st->wsFbCount.ensure(64));
+      if (!st->pin_fb) {
+        CUDA_CHECK_RET(cudaHostAlloc(reinterpret_cast<void**>(&st->pin_fb), 64, cudaHostAllocDefault));
+        CUDA_CHECK_RET(cudaEventCreateWithFlags(&st->fb_event, cudaEventDisableTiming));
+      }
+    }
     static const bool no_skinny = getenv("EVEREST_NO_SKINNY") != nullptr;   // debugging switch, read once
     const bool small_rows = rows <= 64 && !no_skinny;
     // INT8 digit-plane GEMM: 0 = off, 1 = automatic (large problems: the slicing pass and the 448-column TMEM tiles only
@@ -1112,6 +1138,14 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         rec_end(st, s);
       }
     }
+    if (fb_active) {
+      // joint re-sampling fallback: how many (q-batch, output) conditional roots exhausted the jitter ladder?  The counter
+      // travels to the host while the MC kernels below still run, so reading it costs no GPU time
+      CUDA_CHECK_RET(cudaMemsetAsync(st->wsFbCount.p, 0, sizeof(int), s));
+      RC(launch_count_nonzero(st->wsJit.as<int>(), bc * M, st->wsFbCount.as<int>(), s, &st->lc));
+      CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_fb, st->wsFbCount.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK_RET(cudaEventRecord(st->fb_event, s));
+    }
     McArgs ma;
     ma.b = bc; ma.q = q; ma.nb = nb; ma.M = M; ma.S = S; ma.od = st->od; ma.root = st->wsRoot.as<double>();
     ma.mu = st->wsMu.as<double>(); ma.zbT = st->zbT.as<double>(); ma.zqT = st->wsZqT.as<double>();
@@ -1119,7 +1153,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     ma.cells_shared = st->cells_shared; ma.best_f = st->best_f; ma.out = out_dev + b0;
     ma.variant = st->acqf_kind == 3 ? st->scalar_variant : st->log_hvi; ma.vparam = st->vparam;
     ma.best_f_s = st->noisy_scalar ? st->best_f_s.as<double>() : nullptr; ma.tau_relu = st->tau_relu; ma.tau_max = st->tau_max;
-    ma.info_in = st->wsJit.as<int>(); ma.info_out = info_dev ? info_dev + b0 : nullptr;
+    ma.info_in = st->wsJit.as<int>(); ma.info_out = info_chunk;
     ma.Fp = sample_gemm ? st->wsFp.as<double>() : nullptr; ma.fp_stride = rows_max * (size_t)S;
     ma.partial = st->wsPartial.as<double>();
     if (dX_dev) {
@@ -1206,6 +1240,16 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         }
         rec_end(st, s);
         RC(run_tail());
+      }
+    }
+    if (fb_active) {
+      CUDA_CHECK_RET(cudaEventSynchronize(st->fb_event));
+      if (*st->pin_fb > 0) {
+        int n_re = 0;
+        RC(bo_acqf_resample_flagged(st, Xc, bc, q, zq_dev, out_dev + b0, info_chunk, &n_re, stream));
+        st->fb_resampled_last += n_re;
+        // the fallback used the per-call workspaces: the base samples of the next chunk are transposed again
+        RC(launch_transpose_base_samples(zq_dev, S, q, M, st->wsZqT.as<double>(), nullptr, 0, s, &st->lc));
       }
     }
   }
@@ -1343,6 +1387,8 @@ extern "C" int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32
   return BO_OK;
 }
 
+extern "C" int32_t bo_acqf_last_resampled(bo_state* st) { return st ? st->fb_resampled_last : 0; }
+
 extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int32_t q_free, const double* lb,
                                 const double* ub, const double* zq_dev, int32_t maxiter, int32_t history, double pgtol,
                                 double ftol, double* out_dev, int32_t* stats, void* stream) {
@@ -1380,10 +1426,37 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
   long long n_eval = 1;
   int slot = 0, pending[2] = {0, 0};
   bool done = false;
+  // One evaluation + state-machine step = ~20 small launches whose GPU time (0.6 ms on config 3) is about what the host
+  // needs to enqueue them: captured ONCE into a CUDA graph and replayed, so that a busy host cannot stall the loop (every
+  // workspace was sized by the first evaluation above; nothing inside allocates, synchronises or copies from pageable
+  // memory any more).  EVEREST_LBFGS_GRAPH=0, or a capture that fails, falls back to plain launches.
+  static const bool want_graph = []() { const char* e = getenv("EVEREST_LBFGS_GRAPH"); return !e || atoi(e) != 0; }();
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  if (want_graph && s != nullptr) {          // the legacy default stream cannot be captured
+    const long long lc0 = st->lc.n;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc1 = acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream);
+      if (rc1 == BO_OK) rc1 = launch_lbfgs_step(a, r, false, s, nullptr);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc1 != BO_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr; gexec = nullptr;
+        cudaGetLastError();                  // clear the sticky-free error of the failed capture
+      }
+    } else cudaGetLastError();
+    st->lb_launches_per_step = (int)(st->lc.n - lc0) + 1;
+    st->lc.n = lc0;                          // captured launches are counted when the graph is replayed
+  }
   while (!done && n_eval < max_evals) {
     for (int k = 0; k < check_every && n_eval < max_evals; ++k, ++n_eval) {
-      RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream));
-      RC(launch_lbfgs_step(a, r, false, s, &st->lc));
+      if (gexec) {
+        CUDA_CHECK_RET(cudaGraphLaunch(gexec, s));
+        st->lc.n += st->lb_launches_per_step;
+      } else {
+        RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream));
+        RC(launch_lbfgs_step(a, r, false, s, &st->lc));
+      }
     }
     // progress counter of THIS batch goes to the host asynchronously; the one of the PREVIOUS batch is inspected now, so the
     // launch queue never runs dry while the host waits
@@ -1398,6 +1471,8 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
     }
     slot ^= 1;
   }
+  st->lb_graph_used = gexec != nullptr;
+  if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
   RC(launch_lbfgs_finish(a, r, s, &st->lc));
   // values at the returned points (a restart that stopped on a rejected trial returns its last accepted point)
   RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, nullptr, nullptr, stream));

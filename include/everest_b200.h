@@ -217,6 +217,10 @@ int bo_acqf_forward_backward(bo_state* st, const double* X_dev, int32_t b, int32
  * synchronisation (info is read back); n_resampled (HOST, may be NULL) = number of re-scored q-batches. */
 int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32_t b, int32_t q, const double* zq_dev, double* out_dev,
                              int32_t* info_dev, int32_t* n_resampled, void* stream);
+/* bo_acqf_forward runs this fallback by itself (option "joint_fallback", default 1): a 4-byte counter of exhausted jitter
+ * ladders leaves the device behind the conditional-root kernels and is read while the MC kernels still run, so an
+ * unflagged call pays nothing; q-batches re-scored by the last forward call: */
+int32_t bo_acqf_last_resampled(bo_state* st);
 
 /* On-device multi-start refinement: replaces the host loop of [UPSTREAM] botorch.generation.gen_candidates_scipy that
  * BotorchStrategy._optimize_acqf_continuous drives through optimize_acqf (botorch.py:384-405) for the box-constrained case
