@@ -597,36 +597,14 @@ def run_b200(args):
                         "(csrc/ozaki.cu); flagged q-batches are recomputed by the FP64 kernel"}
             roofline["int8_q_batches_redone_in_fp64_per_step"] = int(chk[1])
 
-    # ---- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------
-    cpu = None
-    acq_cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            t0 = time.perf_counter()
-            acq_cpu = cpu_reference_setup(p, acq_d=acq)
-            t_cpu_setup = time.perf_counter() - t0
-            many = p["acqf"] == "qnehvi" and len(p["ref_point"]) > 2
-            n = args.cpu_sample or ((16 if many else 2048) if p["acqf"] == "qnehvi" else 4096)  # ~10 s of CPU work
-            Xc = X_host[:n]
-            cpu_time_forward(acq_cpu, Xc[:8], 8)
-            v8, dt8 = cpu_time_forward(acq_cpu, Xc, 8)
-            vall, dtall = cpu_time_forward(acq_cpu, Xc, n)
-            ref_vals = acq_cpu.forward(Xc)
-            err = float((vals[:n].cpu() - ref_vals).abs().max() / ref_vals.abs().max())
-            cpu = {"value": max(v8, vall), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{n} of {b} q-batches; as BoFire calls it (chunks of 8): {v8:.1f} evals/s in {dt8:.1f} s; "
-                             f"best case (one call over the sample): {vall:.1f} evals/s in {dtall:.1f} s; value = the faster",
-                   "sample_q_batches": n, "max_rel_err_gpu_vs_cpu_on_sample": err, "setup_s": t_cpu_setup}
-        except Exception as exc:  # the baseline must never take the headline number down with it
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
-
     # ---- ask() latency: acqf construction + screen + refinement of the restarts -----------------------
     ask = None
     if rank == 0 and world == 1 and p.get("bounds") is not None and not args.no_ask:
         from everest_b200 import optim
 
+        # measured BEFORE the CPU baseline: its thread pools keep the host cores busy for a while, and the refinement loop
+        # (20 small launches per step) is sensitive to that
         torch.cuda.synchronize(device)
-        torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))  # the CPU baseline above may have raised it
         t0 = time.perf_counter()
         acq2 = Cf.build_acqf(p, st)
         torch.cuda.synchronize(device)
@@ -660,16 +638,40 @@ def run_b200(args):
                "forward_backward_ms": ev0.elapsed_time(ev1) / 10.0,
                "best_screened": float(Yic.max()), "best_refined": float(torch.maximum(Yref, Yic).max()),
                "total_s": t3 - t0}
-        if acq_cpu is not None and len(p.get("ref_point", [0, 0])) <= 2:
-            try:
-                torch.set_num_threads(os.cpu_count() or 1)
-                cpu_ask = cpu_ask_latency(p, acq_cpu)
-                cpu_ask["acqf_build_s"] = cpu["setup_s"] if cpu else None
-                cpu_ask["total_s"] = (cpu_ask["acqf_build_s"] or 0.0) + cpu_ask["screen_s"] + cpu_ask["refine_s"]
-                ask["cpu_port"] = cpu_ask
-                ask["speedup_vs_cpu_port"] = cpu_ask["total_s"] / ask["total_s"]
-            except Exception as exc:
-                ask["cpu_port"] = {"failed": repr(exc)}
+
+    # ---- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------
+    cpu = None
+    acq_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            t0 = time.perf_counter()
+            acq_cpu = cpu_reference_setup(p, acq_d=acq)
+            t_cpu_setup = time.perf_counter() - t0
+            many = p["acqf"] == "qnehvi" and len(p["ref_point"]) > 2
+            n = args.cpu_sample or ((16 if many else 2048) if p["acqf"] == "qnehvi" else 4096)  # ~10 s of CPU work
+            Xc = X_host[:n]
+            cpu_time_forward(acq_cpu, Xc[:8], 8)
+            v8, dt8 = cpu_time_forward(acq_cpu, Xc, 8)
+            vall, dtall = cpu_time_forward(acq_cpu, Xc, n)
+            ref_vals = acq_cpu.forward(Xc)
+            err = float((vals[:n].cpu() - ref_vals).abs().max() / ref_vals.abs().max())
+            cpu = {"value": max(v8, vall), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{n} of {b} q-batches; as BoFire calls it (chunks of 8): {v8:.1f} evals/s in {dt8:.1f} s; "
+                             f"best case (one call over the sample): {vall:.1f} evals/s in {dtall:.1f} s; value = the faster",
+                   "sample_q_batches": n, "max_rel_err_gpu_vs_cpu_on_sample": err, "setup_s": t_cpu_setup}
+        except Exception as exc:  # the baseline must never take the headline number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
+
+    if ask is not None and acq_cpu is not None and len(p.get("ref_point", [0, 0])) <= 2:
+        try:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cpu_ask = cpu_ask_latency(p, acq_cpu)
+            cpu_ask["acqf_build_s"] = cpu["setup_s"] if cpu else None
+            cpu_ask["total_s"] = (cpu_ask["acqf_build_s"] or 0.0) + cpu_ask["screen_s"] + cpu_ask["refine_s"]
+            ask["cpu_port"] = cpu_ask
+            ask["speedup_vs_cpu_port"] = cpu_ask["total_s"] / ask["total_s"]
+        except Exception as exc:
+            ask["cpu_port"] = {"failed": repr(exc)}
 
     if world > 1 and p.get("bounds") is not None and not args.no_ask:
         # ask() over the GPUs of the box, STRONG scaling: the config's raw samples and restarts sharded over the ranks

@@ -95,7 +95,9 @@ struct PrepBuf {
         RC(codes[l].ensure(nn * L.nd * sizeof(int)));
         out->codes[l] = codes[l].as<int>();
       } else {
-        RC(bits[l].ensure(nn * L.dpad * sizeof(u64)));
+        // packed words, followed by the same fingerprints as one 0 / 1 byte per column (rows padded to 256 bytes): the
+        // operands of the u8 tensor-core inner products in crosscov_kernel2
+        RC(bits[l].ensure(nn * L.dpad * sizeof(u64) + nn * (size_t)tanimoto_row_bytes(L.dpad)));
         RC(pc[l].ensure(nn * sizeof(int)));
         out->bits[l] = bits[l].as<u64>();
         out->pc[l] = pc[l].as<int>();
@@ -1426,11 +1428,12 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
   long long n_eval = 1;
   int slot = 0, pending[2] = {0, 0};
   bool done = false;
-  // One evaluation + state-machine step = ~20 small launches whose GPU time (0.6 ms on config 3) is about what the host
-  // needs to enqueue them: captured ONCE into a CUDA graph and replayed, so that a busy host cannot stall the loop (every
-  // workspace was sized by the first evaluation above; nothing inside allocates, synchronises or copies from pageable
-  // memory any more).  EVEREST_LBFGS_GRAPH=0, or a capture that fails, falls back to plain launches.
-  static const bool want_graph = []() { const char* e = getenv("EVEREST_LBFGS_GRAPH"); return !e || atoi(e) != 0; }();
+  // One evaluation + state-machine step = ~20 small launches (0.66 ms of GPU time on config 3; the host enqueues them in
+  // about half of that).  EVEREST_LBFGS_GRAPH=1 captures the step ONCE into a CUDA graph and replays it, which shields the
+  // loop from a busy host (every workspace was sized by the first evaluation above; nothing inside allocates, synchronises
+  // or copies from pageable memory any more).  Measured on an idle host: 0.160 s per 242 steps either way, but the first
+  // instantiation in a process costs ~1 s -- more than an ask() -- so plain launches are the default.
+  static const bool want_graph = []() { const char* e = getenv("EVEREST_LBFGS_GRAPH"); return e && atoi(e) != 0; }();
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   if (want_graph && s != nullptr) {          // the legacy default stream cannot be captured

@@ -51,8 +51,10 @@ __global__ void prep_points_kernel(ModelD md, const double* __restrict__ X, int 
         }
         prep.codes[l][(size_t)warp * L.nd + f] = best;
       }
-    } else {  // Tanimoto: pack 64 columns per word with two ballots
+    } else {  // Tanimoto: pack 64 columns per word with two ballots; the same bits as 0 / 1 bytes behind the words
       int total = 0;
+      const int rb = tanimoto_row_bytes(L.dpad);
+      unsigned char* by = const_cast<unsigned char*>(tanimoto_bytes(prep.bits[l], n, L.dpad)) + (size_t)warp * rb;
       for (int w = 0; w < L.dpad; ++w) {
         int k0 = w * 64 + lane, k1 = k0 + 32;
         bool b0 = (k0 < L.nd) && (x[L.col[k0]] != 0.0);
@@ -62,7 +64,10 @@ __global__ void prep_points_kernel(ModelD md, const double* __restrict__ X, int 
         u64 word = ((u64)hi << 32) | (u64)lo;
         total += __popcll(word);
         if (lane == 0) prep.bits[l][(size_t)warp * L.dpad + w] = word;
+        by[k0] = b0 ? 1 : 0;
+        by[k1] = b1 ? 1 : 0;
       }
+      for (int k = L.dpad * 64 + lane; k < rb; k += 32) by[k] = 0;
       if (lane == 0) prep.pc[l][warp] = total;
     }
   }
@@ -250,37 +255,54 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
               lv[(i * 4 + j) * 2 + e] = exp_nonpos(-(acc / (double)L.nd));
             }
       } else {  // Tanimoto
-        const int WC = 16;  // words per chunk; row stride WC + 1 words keeps AND/POPC loads conflict-light
-        u64* Ab = reinterpret_cast<u64*>(smem);
-        u64* Bb = Ab + CC_TILE * (WC + 1);
+        // <x, x'> over 0 / 1 fingerprints = an exact integer GEMM: u8 x u8 -> s32 tensor-core MMAs (m16n8k32) on the byte
+        // copies of the fingerprints instead of AND + POPC over the packed words (POPC issues at 1/8 rate: the POPC loop was
+        // 41 % of this kernel's instructions and held it at 0.22 of even the POPC-pipe bound).  Chunks of 256 columns per
+        // row; row stride 272 bytes keeps the ldmatrix rows (16 bytes each) on distinct banks.
+        const int TB_CH = 256, TB_LD = 272;
+        unsigned char* Ab = reinterpret_cast<unsigned char*>(smem);
+        unsigned char* Bb = Ab + CC_TILE * TB_LD;
+        const int rb = tanimoto_row_bytes(L.dpad);
+        const unsigned char* Ag = tanimoto_bytes(rows.bits[l], n_rows, L.dpad);
+        const unsigned char* Bg = tanimoto_bytes(cols.s[l].bits, n_cols, L.dpad);
         int dot[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) dot[e] = 0;
-        for (int w0 = 0; w0 < L.dpad; w0 += WC) {
-          const int wn = min(WC, L.dpad - w0);
+        // ldmatrix lane addressing (8 x 8 matrices of 16-bit = 8 rows x 16 bytes): matrix m = lane >> 3, row = lane & 7
+        const int lm = lane >> 3, lr = lane & 7;
+        const unsigned a_off = (unsigned)((wr * 16 + (lm & 1) * 8 + lr) * TB_LD + (lm >> 1) * 16);   // (rows 0-7 | 8-15) x (k 0-15 | 16-31)
+        const unsigned b_off = (unsigned)((wc * 32 + (lm >> 1) * 8 + lr) * TB_LD + (lm & 1) * 16);  // (n 0-7: k lo, k hi | n 8-15: k lo, k hi)
+        const unsigned As_u = (unsigned)__cvta_generic_to_shared(Ab), Bs_u = (unsigned)__cvta_generic_to_shared(Bb);
+        for (int k0 = 0; k0 < rb; k0 += TB_CH) {
           __syncthreads();
-          for (int idx = tid; idx < CC_TILE * WC; idx += 256) {
-            int r = idx / WC, w = idx % WC;
-            u64 va = 0, vb = 0;
-            if (w < wn) {
-              if (row0 + r < n_rows) va = rows.bits[l][(size_t)(row0 + r) * L.dpad + w0 + w];
-              if (col0 + r < n_cols) vb = cols.s[l].bits[(size_t)(col0 + r) * L.dpad + w0 + w];
-            }
-            Ab[r * (WC + 1) + w] = va;
-            Bb[r * (WC + 1) + w] = vb;
+          for (int idx = tid; idx < CC_TILE * (TB_CH / 16); idx += 256) {
+            const int r = idx / (TB_CH / 16), c = idx % (TB_CH / 16);
+            int4 va = make_int4(0, 0, 0, 0), vb = make_int4(0, 0, 0, 0);
+            if (row0 + r < n_rows) va = *reinterpret_cast<const int4*>(Ag + (size_t)(row0 + r) * rb + k0 + c * 16);
+            if (col0 + r < n_cols) vb = *reinterpret_cast<const int4*>(Bg + (size_t)(col0 + r) * rb + k0 + c * 16);
+            *reinterpret_cast<int4*>(Ab + r * TB_LD + c * 16) = va;
+            *reinterpret_cast<int4*>(Bb + r * TB_LD + c * 16) = vb;
           }
           __syncthreads();
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+          for (int ks = 0; ks < TB_CH; ks += 32) {
+            unsigned a0, a1, a2, a3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(As_u + a_off + ks));
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
-                int s = 0;
-                for (int w = 0; w < wn; ++w) s += __popcll(Ab[rl * (WC + 1) + w] & Bb[cl * (WC + 1) + w]);
-                dot[(i * 4 + j) * 2 + e] += s;
-              }
+            for (int jp = 0; jp < 2; ++jp) {      // two n8 groups per ldmatrix.x4
+              unsigned b0, b1, b2, b3;
+              asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                           : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(Bs_u + b_off + jp * 16 * TB_LD + ks));
+              // accumulators of an m16n8 tile: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1) = lv index (i*4+j)*2+e
+              int* d0 = dot + (0 * 4 + jp * 2) * 2;
+              int* d1 = dot + (1 * 4 + jp * 2) * 2;
+              asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                           : "+r"(d0[0]), "+r"(d0[1]), "+r"(d1[0]), "+r"(d1[1]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+              asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                           : "+r"(d0[2]), "+r"(d0[3]), "+r"(d1[2]), "+r"(d1[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b2), "r"(b3));
+            }
+          }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
