@@ -60,6 +60,7 @@ SYMBOLS = {
     "bo_state_create": (C.c_int, [C.POINTER(StateConfig), C.POINTER(C.c_void_p)]),
     "bo_state_destroy": (None, [C.c_void_p]),
     "bo_state_factorize": (C.c_int, [C.c_void_p, c_int_p, c_double_p, C.c_void_p]),
+    "bo_state_set_hyperparameters": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "bo_posterior_marginal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bo_posterior_joint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bo_prune_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(ObjectiveOp),

@@ -134,6 +134,7 @@ struct OutputH {
   PrepD q_prepd;
   // host copies of every leaf's columns (Hamming: start column + cardinality of each group): wire-format layout
   std::vector<int> leaf_cols[BO_MAX_LEAVES], leaf_card[BO_MAX_LEAVES];
+  std::vector<double> y_host;   // raw targets: the residual is rebuilt when the constant mean changes (bo_state_set_hyperparameters)
 };
 
 struct TimingRec { std::string name; cudaEvent_t a, b; };
@@ -364,6 +365,7 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
     }
     // residual r = (y - y_mean) / y_std - mean_const, zero padded row of length ldk
     if (!om.y) { bo_set_error("output %d: y is NULL", m); bo_state_destroy(st); return BO_ERR_INVALID; }
+    o.y_host.assign(om.y, om.y + N);
     std::vector<double> r(st->ldk, 0.0);
     for (int i = 0; i < N; ++i) r[i] = (om.y[i] - om.y_mean) / om.y_std - om.mean_const;
     rc = o.resid.ensure((size_t)st->ldk * 8); if (rc) { bo_state_destroy(st); return rc; }
@@ -375,6 +377,59 @@ extern "C" int bo_state_create(const bo_state_config* cfg, bo_state** out_state)
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { bo_set_error("create: %s", cudaGetErrorString(e)); bo_state_destroy(st); return BO_ERR_CUDA; }
   *out_state = st;
+  return BO_OK;
+}
+
+// New hyper-parameter VALUES for output m of an existing state (same kernel tree, same columns, same transforms and
+// targets): what a step of the marginal-likelihood optimiser changes.  Only the small parameter arrays are rewritten and the
+// training side is prepared again; every large buffer of the handle is reused by the following bo_state_factorize -- a fit of
+// N = 2000 points spent most of its time creating and destroying states (~50 ms per evaluation for a 15 ms factorisation).
+extern "C" int bo_state_set_hyperparameters(bo_state* st, int32_t m, const bo_output_model* om, void* stream) {
+  if (!st || !om) { bo_set_error("set_hyperparameters: null argument"); return BO_ERR_INVALID; }
+  if (m < 0 || m >= st->M) { bo_set_error("set_hyperparameters: bad output index"); return BO_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  OutputH& o = st->out[m];
+  if (om->n_leaves != o.md.n_leaves || om->n_terms != o.md.n_terms || !om->leaves || !om->terms) {
+    bo_set_error("set_hyperparameters: the kernel tree must keep its shape (%d leaves, %d terms)", o.md.n_leaves, o.md.n_terms);
+    return BO_ERR_INVALID;
+  }
+  if (!(om->noise >= 0.0)) { bo_set_error("set_hyperparameters: noise must be >= 0"); return BO_ERR_INVALID; }
+  for (int t = 0; t < om->n_terms; ++t) {
+    const bo_kernel_term& kt = om->terms[t];
+    if (kt.n_factors != o.md.nfac[t]) { bo_set_error("set_hyperparameters: term %d changed its factors", t); return BO_ERR_INVALID; }
+    for (int f = 0; f < kt.n_factors; ++f)
+      if (kt.factors[f] != o.md.fac[t][f]) { bo_set_error("set_hyperparameters: term %d changed its factors", t); return BO_ERR_INVALID; }
+  }
+  for (int l = 0; l < om->n_leaves; ++l) {
+    const bo_kernel_leaf& kl = om->leaves[l];
+    const LeafD& L = o.md.leaf[l];
+    if (kl.kind != L.kind || kl.n_dims != L.nd) { bo_set_error("set_hyperparameters: leaf %d changed kind / dims", l); return BO_ERR_INVALID; }
+    if (kl.kind == BO_LEAF_TANIMOTO) continue;
+    if (!kl.lengthscale || (kl.n_ls != 1 && kl.n_ls < kl.n_dims)) { bo_set_error("set_hyperparameters: leaf %d: bad lengthscale spec", l); return BO_ERR_INVALID; }
+    std::vector<double> v(kl.n_dims);
+    for (int k = 0; k < kl.n_dims; ++k) {
+      const double ls = kl.lengthscale[kl.n_ls == 1 ? 0 : k];
+      if (!(ls > 0.0)) { bo_set_error("set_hyperparameters: leaf %d: non-positive lengthscale", l); return BO_ERR_INVALID; }
+      v[k] = (kl.kind == BO_LEAF_HAMMING) ? 1.0 / ls : ls;
+    }
+    double* dst = const_cast<double*>(kl.kind == BO_LEAF_HAMMING ? L.wls : L.ls);
+    CUDA_CHECK_RET(cudaMemcpyAsync(dst, v.data(), v.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));      // v lives on this stack frame
+  }
+  for (int t = 0; t < om->n_terms; ++t) o.md.coef[t] = om->terms[t].coef;
+  const bool mean_changed = om->mean_const != o.md.mean_const;
+  o.md.noise = om->noise; o.md.mean_const = om->mean_const;
+  RC(launch_prep_points(o.md, st->X_train.as<double>(), st->N, st->d, o.train_prepd, s, &st->lc));
+  if (mean_changed) {
+    std::vector<double> r(st->ldk, 0.0);
+    for (int i = 0; i < st->N; ++i) r[i] = (o.y_host[i] - o.md.y_mean) / o.md.y_std - o.md.mean_const;
+    CUDA_CHECK_RET(cudaMemcpyAsync(o.resid.p, r.data(), (size_t)st->ldk * 8, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK_RET(cudaStreamSynchronize(s));
+  }
+  st->factorized = false;
+  st->acqf_kind = 0;
+  o.kinv_ready = false;
+  o.oz_ready = false;
   return BO_OK;
 }
 

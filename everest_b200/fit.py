@@ -197,14 +197,17 @@ class FitResult:
     message: str
 
 
-def mll_and_grad(X, spec: SingleTaskGPSpec, device=None):
+def mll_and_grad(X, spec: SingleTaskGPSpec, device=None, state: Optional[DeviceGPState] = None):
     """(mll, d/d noise, d/d mean_const, d/d lengthscale slots, d/d term coefficients) from the device for the
-    hyper-parameters in `spec`.  Raises NotPSDError when the training Gram matrix cannot be factorised."""
+    hyper-parameters in `spec`.  Raises NotPSDError when the training Gram matrix cannot be factorised.
+    `state`: a DeviceGPState on the same (X, y, kernel tree) whose hyper-parameters are overwritten in place
+    (set_hyperparameters) instead of building and destroying a state per evaluation."""
     import ctypes as C
 
     from . import _lib as L
 
-    st = DeviceGPState(X, [spec], device=device)
+    own = state is None
+    st = DeviceGPState(X, [spec], device=device) if own else state.set_hyperparameters(0, spec)
     try:
         st.factorize()
         lay = _Layout(spec.kernel)
@@ -217,7 +220,8 @@ def mll_and_grad(X, spec: SingleTaskGPSpec, device=None):
                                                    n_terms, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return mll.value, dn.value, dm.value, np.array(dls[: lay.n_ls]), np.array(dco[:n_terms])
     finally:
-        st.close()
+        if own:
+            st.close()
 
 
 def fit_gp(X, y, kernel, in_offset=None, in_scale=None, noise_prior=None, lengthscale_priors=None, outputscale_priors=None,
@@ -265,7 +269,7 @@ def fit_gp(X, y, kernel, in_offset=None, in_scale=None, noise_prior=None, length
         else:
             raw0.append(0.0)
     raw0 = np.asarray(raw0, dtype=np.float64)
-    state = {"n_eval": 0, "last_mll": float("nan")}
+    state = {"n_eval": 0, "last_mll": float("nan"), "st": None}
 
     def unpack(raw):
         ls_values, scale_values, pos = {}, [], 0
@@ -294,7 +298,10 @@ def fit_gp(X, y, kernel, in_offset=None, in_scale=None, noise_prior=None, length
         state["n_eval"] += 1
         ls_values, scale_values, noise, mean = unpack(raw)
         try:
-            mll, d_noise, d_mean, d_ls, d_coef = mll_and_grad(X, make_spec(raw), device=device)
+            spec_k = make_spec(raw)
+            if state["st"] is None:     # one device state for the whole fit: later evaluations only rewrite its hyper-parameters
+                state["st"] = DeviceGPState(X, [spec_k], device=device)
+            mll, d_noise, d_mean, d_ls, d_coef = mll_and_grad(X, spec_k, device=device, state=state["st"])
         except NotPSDError:
             return 1e10, np.zeros(n_raw)
         if not math.isfinite(mll):
@@ -337,7 +344,11 @@ def fit_gp(X, y, kernel, in_offset=None, in_scale=None, noise_prior=None, length
             pos += cnt
         return -total / N, -grad / N
 
-    res = minimize(loss_and_grad, raw0, jac=True, method="L-BFGS-B", options=dict(options or {"maxiter": 200}))
+    try:
+        res = minimize(loss_and_grad, raw0, jac=True, method="L-BFGS-B", options=dict(options or {"maxiter": 200}))
+    finally:
+        if state["st"] is not None:
+            state["st"].close()
     best = res.x if math.isfinite(res.fun) and res.fun < 1e9 else raw0
     spec = make_spec(best)
     return FitResult(spec=spec, loss=float(res.fun), mll=float(state["last_mll"]), n_iterations=int(res.nit),

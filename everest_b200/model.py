@@ -86,27 +86,7 @@ class DeviceGPState:
         keep = []
         outs = (L.OutputModel * self.M)()
         for m, spec in enumerate(outputs):
-            flat = K.flatten(spec.kernel)
-            leaves = (L.KernelLeaf * len(flat.leaves))(*[K.leaf_to_c(lf, keep) for lf in flat.leaves])
-            terms = (L.KernelTerm * len(flat.terms))()
-            for t, (coef, facs) in enumerate(flat.terms):
-                terms[t].coef = float(coef)
-                terms[t].n_factors = len(facs)
-                for i, f in enumerate(facs):
-                    terms[t].factors[i] = int(f)
-            y = np.ascontiguousarray(np.asarray(spec.y, dtype=np.float64))
-            if y.shape != (self.N,):
-                raise ValueError(f"output {m}: y must have shape [{self.N}]")
-            ym, ys = (spec.y_mean, spec.y_std) if spec.y_mean is not None and spec.y_std is not None else standardize_stats(y)
-            off = np.ascontiguousarray(np.zeros(self.d) if spec.in_offset is None else np.asarray(spec.in_offset, dtype=np.float64))
-            scl = np.ascontiguousarray(np.ones(self.d) if spec.in_scale is None else np.asarray(spec.in_scale, dtype=np.float64))
-            keep += [leaves, terms, y, off, scl]
-            o = outs[m]
-            o.n_leaves, o.leaves, o.n_terms, o.terms = len(flat.leaves), leaves, len(flat.terms), terms
-            o.in_offset = off.ctypes.data_as(L.c_double_p)
-            o.in_scale = scl.ctypes.data_as(L.c_double_p)
-            o.mean_const, o.noise, o.y_mean, o.y_std = float(spec.mean_const), float(spec.noise), float(ym), float(ys)
-            o.y = y.ctypes.data_as(L.c_double_p)
+            self._fill_output(outs[m], m, spec, keep)
         cfg = L.StateConfig(self.N, self.d, self.M, X.ctypes.data_as(L.c_double_p), outs)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -114,6 +94,44 @@ class DeviceGPState:
         self._h = h
         self.jitter = None
         self.factorized = False
+
+    def _fill_output(self, o, m, spec, keep):
+        """SingleTaskGPSpec -> bo_output_model; `keep` collects the arrays the struct points into."""
+        flat = K.flatten(spec.kernel)
+        leaves = (L.KernelLeaf * len(flat.leaves))(*[K.leaf_to_c(lf, keep) for lf in flat.leaves])
+        terms = (L.KernelTerm * len(flat.terms))()
+        for t, (coef, facs) in enumerate(flat.terms):
+            terms[t].coef = float(coef)
+            terms[t].n_factors = len(facs)
+            for i, f in enumerate(facs):
+                terms[t].factors[i] = int(f)
+        y = np.ascontiguousarray(np.asarray(spec.y, dtype=np.float64))
+        if y.shape != (self.N,):
+            raise ValueError(f"output {m}: y must have shape [{self.N}]")
+        ym, ys = (spec.y_mean, spec.y_std) if spec.y_mean is not None and spec.y_std is not None else standardize_stats(y)
+        off = np.ascontiguousarray(np.zeros(self.d) if spec.in_offset is None else np.asarray(spec.in_offset, dtype=np.float64))
+        scl = np.ascontiguousarray(np.ones(self.d) if spec.in_scale is None else np.asarray(spec.in_scale, dtype=np.float64))
+        keep += [leaves, terms, y, off, scl]
+        o.n_leaves, o.leaves, o.n_terms, o.terms = len(flat.leaves), leaves, len(flat.terms), terms
+        o.in_offset = off.ctypes.data_as(L.c_double_p)
+        o.in_scale = scl.ctypes.data_as(L.c_double_p)
+        o.mean_const, o.noise, o.y_mean, o.y_std = float(spec.mean_const), float(spec.noise), float(ym), float(ys)
+        o.y = y.ctypes.data_as(L.c_double_p)
+
+    def set_hyperparameters(self, m: int, spec: SingleTaskGPSpec):
+        """New hyper-parameter VALUES for output m (same kernel tree / columns / transforms / targets) without rebuilding the
+        state: bo_state_set_hyperparameters.  `factorize()` must follow.  This is what one step of the marginal-likelihood
+        optimiser changes (fit.py); every large device buffer of the handle is reused."""
+        keep = []
+        o = L.OutputModel()
+        self._fill_output(o, m, spec, keep)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.bo_state_set_hyperparameters(self.handle, int(m), C.byref(o), _stream()))
+        self.outputs = list(self.outputs)
+        self.outputs[m] = spec
+        self.factorized = False
+        self._active_acqf = None
+        return self
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):

@@ -109,6 +109,11 @@ const char* bo_last_error(void);
  * ModelListGP (botorch_surrogates.py:79-128) + the GPyTorch prediction-strategy caches.  Copies
  * everything; the config may be freed after the call. */
 int bo_state_create(const bo_state_config* cfg, bo_state** out);
+
+/* New hyper-parameter VALUES (lengthscales, term coefficients = products of the outputscales, noise, constant mean) for
+ * output m of an existing state; kernel tree, columns, transforms and targets stay.  What one step of fit_gpytorch_mll
+ * changes (surrogates/single_task_gp.py:70-71): the large buffers of the handle are reused, bo_state_factorize must follow. */
+int bo_state_set_hyperparameters(bo_state* st, int32_t m, const bo_output_model* om, void* stream);
 void bo_state_destroy(bo_state* st);
 
 /* Training Gram K + sigma^2 I, psd-safe Cholesky (jitter 1e-8 .. 1e-3), mean cache alpha and the

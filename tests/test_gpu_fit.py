@@ -162,3 +162,39 @@ def test_mll_gradient_large_n_chunk_loop():
     assert np.abs(dls - g_o["ls"].numpy()).max() < 1e-6 * np.abs(g_o["ls"].numpy()).max()
     assert abs(dco[0] - float(g_o["os"])) < 1e-6 * abs(float(g_o["os"]))
     assert abs(dn - float(g_o["noise"])) < 1e-6 * abs(float(g_o["noise"]))
+
+
+def test_in_place_hyperparameter_update_equals_a_fresh_state():
+    """bo_state_set_hyperparameters: one handle serves every evaluation of a fit.  After rewriting lengthscales, outputscale,
+    noise and constant mean in place, the marginal likelihood, its gradient and the posterior must be IDENTICAL to those of
+    a state created from scratch with the same values (same kernels, same buffers: bit for bit); a changed tree is refused."""
+    from everest_b200.model import DeviceGPState
+
+    X, y = synth(N=120, d=4, seed=3)
+    d = X.shape[1]
+
+    def spec(ls, os_, noise, mean, hls):
+        kern = K.AdditiveKernel([K.ScaleKernel(K.MaternKernel([0, 1, 2], ls, nu=2.5), os_), K.RBFKernel([3], [hls])])
+        return SingleTaskGPSpec(kernel=kern, y=y, mean_const=mean, noise=noise)
+
+    a = spec([0.7, 1.1, 0.9], 1.3, 0.02, 0.1, 0.8)
+    b = spec([0.4, 2.0, 1.5], 0.6, 0.005, -0.3, 1.7)
+    st = DeviceGPState(X, [a]).factorize()
+    Xq = np.random.default_rng(1).random((17, d))
+    mean_a, var_a = st.posterior(Xq)
+    in_place = F.mll_and_grad(X, b, state=st)
+    mean_b, var_b = st.posterior(Xq)
+    fresh_state = DeviceGPState(X, [b]).factorize()
+    fresh = F.mll_and_grad(X, b)
+    mean_f, var_f = fresh_state.posterior(Xq)
+    assert in_place[0] == fresh[0] and in_place[1] == fresh[1] and in_place[2] == fresh[2]
+    assert np.array_equal(in_place[3], fresh[3]) and np.array_equal(in_place[4], fresh[4])
+    assert torch.equal(mean_b, mean_f) and torch.equal(var_b, var_f)
+    assert not torch.equal(mean_a, mean_b)
+    # and back again: nothing of the previous values lingers
+    back = F.mll_and_grad(X, a, state=st)
+    ref = F.mll_and_grad(X, a)
+    assert back[0] == ref[0] and np.array_equal(back[3], ref[3])
+    with pytest.raises(ValueError):
+        st.set_hyperparameters(0, SingleTaskGPSpec(kernel=K.RBFKernel([0, 1, 2, 3], [1.0] * 4), y=y))
+    st.close(); fresh_state.close()
