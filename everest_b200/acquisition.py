@@ -9,6 +9,7 @@ forward(X[b, q, d]) -> [b] is the L1 boundary of SURVEY.md 8b (called from calc_
 botorch.py:223, optimize_acqf's raw-sample screen and optimize_acqf_discrete botorch.py:461).
 """
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -180,11 +181,18 @@ class _DeviceAcquisition:
         # the loop replays a CUDA graph of one evaluation; the legacy default stream cannot be captured, so the call runs
         # on a side stream ordered after the caller's stream (the C call returns synchronised: it reads its statistics back)
         dev = self.model.device
+        # EVEREST_LBFGS_GRAPH=1 replays a CUDA graph of one evaluation; the legacy default stream cannot be captured, so the
+        # call then runs on a side stream ordered after the caller's (creating the first non-default torch stream of a
+        # process costs up to 0.5 s on this platform -- measured in bench.py -- which is why plain launches on the caller's
+        # stream are the default)
+        use_side = os.environ.get("EVEREST_LBFGS_GRAPH", "0") not in ("", "0")
         cur = torch.cuda.current_stream(dev)
-        side = getattr(self.model, "_side_stream", None)
-        if side is None:
-            side = self.model._side_stream = torch.cuda.Stream(device=dev)
-        side.wait_stream(cur)
+        side = cur
+        if use_side:
+            side = getattr(self.model, "_side_stream", None)
+            if side is None:
+                side = self.model._side_stream = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
         with torch.cuda.device(dev), torch.cuda.stream(side):
             Xd = self._with_pending(X.detach().to(dev)).contiguous().clone()
             r, q_tot, _ = Xd.shape
@@ -194,7 +202,8 @@ class _DeviceAcquisition:
                                                     lb.ctypes.data_as(L.c_double_p), ub.ctypes.data_as(L.c_double_p), _dev_ptr(zq),
                                                     int(maxiter), int(history), float(pgtol), float(ftol), _dev_ptr(out), stats,
                                                     C.c_void_p(side.cuda_stream)))
-        cur.wait_stream(side)
+        if use_side:
+            cur.wait_stream(side)
         info = {"n_acqf_evals": int(stats[0]) * r, "n_steps": int(stats[0]), "nit": int(stats[1]), "n_converged": int(stats[2]),
                 "n_budget": int(stats[3])}
         return Xd[:, :q_free].contiguous(), out, info

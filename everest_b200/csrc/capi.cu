@@ -1456,6 +1456,7 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
   const int d = st->d, n = q_free * d;
   for (int j = 0; j < d; ++j)
     if (!(lb[j] <= ub[j])) { bo_set_error("optimize: lb[%d] > ub[%d]", j, j); return BO_ERR_INVALID; }
+  SetupTrace tr("acqf_optimize", s);
   RC(st->wsLbfgs.ensure(lbfgs_ws_bytes(r, n, history)));
   RC(st->wsLbBounds.ensure((size_t)2 * d * 8));
   RC(st->wsLbGrad.ensure((size_t)r * q_tot * d * 8));
@@ -1473,9 +1474,11 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
   a.X = X_dev; a.dX = st->wsLbGrad.as<double>(); a.vals = out_dev;
   lbfgs_carve(a, st->wsLbfgs.p, r, n, history);
   CUDA_CHECK_RET(cudaMemcpyAsync(a.n_running, &r, sizeof(int), cudaMemcpyHostToDevice, s));   // pageable 4-byte copy: staged at once
+  tr.mark("workspaces");
   // every evaluation: the forward + adjoint chain of the r q-batches, then one state-machine step of every restart
   RC(acqf_run(st, X_dev, r, q_tot, zq_dev, out_dev, st->wsLbGrad.as<double>(), nullptr, stream));
   RC(launch_lbfgs_step(a, r, true, s, &st->lc));
+  tr.mark("first evaluation");
   // L-BFGS-B allows ~1.25 evaluations per iteration on average (scipy: maxfun = 15000 for maxiter = 15000); the budget here
   // is 2 per iteration plus the 20 trials a failing line search may take
   const long long max_evals = 2ll * maxiter + 20;
@@ -1529,6 +1532,7 @@ extern "C" int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t 
     }
     slot ^= 1;
   }
+  tr.mark("loop");
   st->lb_graph_used = gexec != nullptr;
   if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
   RC(launch_lbfgs_finish(a, r, s, &st->lc));
