@@ -994,7 +994,35 @@ mc_hvi_kernel(McArgs a) {
 // Contribution of one cell to the inclusion-exclusion sum for one MC sample.  A point overlaps the cell iff
 // obj > lower in every objective (cells are non-empty, so upper > lower); the overlap test is compare-only
 // and most cells are rejected after the first objective.  Only overlapping points enter the subset sums.
-template <int QMAX, int MO>
+template <int QMAX, int MO, int J, int SIZE>
+struct SubsetWalk {
+  static __device__ __forceinline__ void go(const double (&obj)[QMAX][MO], const double (&fwt)[QMAX], unsigned active,
+                                            const double (&mn)[MO], double w, const double (&lo)[MO], double (&asum)[QMAX + 1],
+                                            bool has_cons) {
+    SubsetWalk<QMAX, MO, J + 1, SIZE>::go(obj, fwt, active, mn, w, lo, asum, has_cons);          // subsets without point J
+    if ((active >> J) & 1u) {                                                                      // subsets with point J
+      double m2[MO];
+#pragma unroll
+      for (int o = 0; o < MO; ++o) m2[o] = fmin(mn[o], obj[J][o]);
+      SubsetWalk<QMAX, MO, J + 1, SIZE + 1>::go(obj, fwt, active, m2, has_cons ? w * fwt[J] : w, lo, asum, has_cons);
+    }
+  }
+};
+template <int QMAX, int MO, int SIZE>
+struct SubsetWalk<QMAX, MO, QMAX, SIZE> {
+  static __device__ __forceinline__ void go(const double (&)[QMAX][MO], const double (&)[QMAX], unsigned, const double (&mn)[MO],
+                                            double w, const double (&lo)[MO], double (&asum)[QMAX + 1], bool has_cons) {
+    if (SIZE > 0) {
+      double vol = 1.0;
+#pragma unroll
+      for (int o = 0; o < MO; ++o) vol *= fmax(mn[o] - lo[o], 0.0);
+      if (has_cons) vol *= w;
+      asum[SIZE] += vol;
+    }
+  }
+};
+
+template <int QMAX, int MO, bool TREE = true>
 __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO], const double (&fwt)[QMAX], int q,
                                                     bool has_cons, const double* __restrict__ lo_p,
                                                     const double* __restrict__ up_p, int stride,
@@ -1033,37 +1061,48 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
     if (has_cons) vol *= w;
     return 0.0 + (0.0 + vol);
   }
-  // one pass over the subsets of the active set; the per-size sums keep the order of the reference (sizes 1..q with
-  // alternating sign, subsets of one size in the same descending enumeration order as a size-by-size loop)
+  // The subsets of the active set are walked as a binary decision tree over the points (include / exclude point J), fully
+  // unrolled at compile time: the running minimum per objective is extended by ONE fmin per objective when a point joins
+  // (nested subsets share their prefix), the subset size is a template parameter (static index into the per-size sums),
+  // and a point that does not overlap the cell prunes its whole "include" subtree.  Per subset: MO fmin + MO (sub, fmax) +
+  // MO mul + 1 add, no loop or index arithmetic -- the enumeration loop it replaces spent ~100 instructions per subset
+  // (QMAX * MO predicated fmin, popc, QMAX predicated per-size adds), which made the q = 8 many-objective kernel issue-bound
+  // at 17 % FP64 utilisation (ncu, profiles/r02_ncu_counters.json).  Sizes are summed per size first and combined with
+  // alternating signs afterwards, like the reference's size-by-size loop.
   double asum[QMAX + 1];
 #pragma unroll
   for (int i = 0; i <= QMAX; ++i) asum[i] = 0.0;
-  unsigned seen = 0;
-  for (unsigned sub = active; sub; sub = (sub - 1) & active) {
-    const int size = __popc(sub);
-    seen |= 1u << size;
-    double vol = 1.0;
+  if (TREE) {
+    SubsetWalk<QMAX, MO, 0, 0>::go(obj, fwt, active, up, 1.0, lo, asum, has_cons);
+  } else {
+    // enumeration loop, kept for q = 8: the 256-leaf tree was measured on config 4 (q = 8, 4 objectives, thousands of cells
+    // per sample) and changed nothing (18.89 vs 18.94 ms per screen) -- that kernel spends its ~107 instructions per
+    // (sample, q-batch, cell) on the overlap test and the cell stream, not on the subset sums -- while costing 3 minutes of
+    // compile time; for q <= 4 (16 leaves) the tree took config 3's MC kernel from 0.85 to 0.78 ms per screen
+    for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+      const int size = __popc(sub);
+      double vol = 1.0;
 #pragma unroll
-    for (int o = 0; o < MO; ++o) {
-      double mn = up[o];
+      for (int o = 0; o < MO; ++o) {
+        double mn = up[o];
 #pragma unroll
-      for (int j = 0; j < QMAX; ++j)
-        if ((sub >> j) & 1u) mn = fmin(mn, obj[j][o]);
-      vol *= fmax(mn - lo[o], 0.0);
+        for (int j = 0; j < QMAX; ++j)
+          if ((sub >> j) & 1u) mn = fmin(mn, obj[j][o]);
+        vol *= fmax(mn - lo[o], 0.0);
+      }
+      if (has_cons) {
+#pragma unroll
+        for (int j = 0; j < QMAX; ++j)
+          if ((sub >> j) & 1u) vol *= fwt[j];
+      }
+#pragma unroll
+      for (int i = 1; i <= QMAX; ++i)
+        if (i == size) asum[i] += vol;
     }
-    if (has_cons) {
-#pragma unroll
-      for (int j = 0; j < QMAX; ++j)
-        if ((sub >> j) & 1u) vol *= fwt[j];
-    }
-#pragma unroll
-    for (int i = 1; i <= QMAX; ++i)
-      if (i == size) asum[i] += vol;
   }
   double cell = 0.0;
 #pragma unroll
-  for (int size = 1; size <= QMAX; ++size)
-    if ((seen >> size) & 1u) cell += (size & 1) ? asum[size] : -asum[size];
+  for (int size = 1; size <= QMAX; ++size) cell += (size & 1) ? asum[size] : -asum[size];
   return cell;
 }
 
@@ -1171,7 +1210,7 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
       }
       if (prefetch & 2) {  // EVEREST_MC_FAST=0: the session-3 cell loop
         for (int c = 0; c < nc; ++c)
-          acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MT_S + sl, cup + (c * MO) * MT_S + sl, MT_S);
+          acc += cell_contribution<QMAX, MO, (QMAX <= 4)>(obj, fwt, q, has_cons, clo + (c * MO) * MT_S + sl, cup + (c * MO) * MT_S + sl, MT_S);
       } else {
         // A point can only overlap a cell whose lower corner lies below the per-objective maxima over the q points:
         // two compares reject most cells before the per-point test (rejected cells contribute exactly 0).
@@ -1188,7 +1227,7 @@ mc_hvi_tiled_kernel(McArgs a, int maxc, int prefetch) {
           bool maybe = true;
 #pragma unroll
           for (int o = 0; o < MO; ++o) maybe = maybe && (mx[o] > lp[o * MT_S]);
-          if (maybe) acc += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, lp, upp, MT_S, true);
+          if (maybe) acc += cell_contribution<QMAX, MO, (QMAX <= 4)>(obj, fwt, q, has_cons, lp, upp, MT_S, true);
         }
       }
     }
@@ -1319,7 +1358,7 @@ mc_hvi_chunked_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
       // (the tiled kernel's maxima pre-filter was tried here too: bit-identical but no faster on config 4, where the
       // q = 8 points of a batch overlap most cells: 15.05 vs 15.3 ms, tools/exp_mc4.sh)
       for (int c = 0; c < cn; ++c)
-        sum += cell_contribution<QMAX, MO>(obj, fwt, q, has_cons, clo + (c * MO) * MC2_S + sl, cup + (c * MO) * MC2_S + sl, MC2_S);
+        sum += cell_contribution<QMAX, MO, (QMAX <= 4)>(obj, fwt, q, has_cons, clo + (c * MO) * MC2_S + sl, cup + (c * MO) * MC2_S + sl, MC2_S);
       acc[t] += sum;
     }
   }
