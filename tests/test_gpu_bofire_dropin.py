@@ -122,3 +122,98 @@ def test_sobo_predictions_match_oracle_built_from_fitted_specs():
     assert np.allclose(pred["y_sd"].values ** 2, var_o, rtol=1e-8, atol=1e-9 * var_o.max())
     # MinimizeObjective desirability = -(y - 0) / (1 - 0)  (get_objective / Outputs.__call__)
     assert np.allclose(pred["y_des"].values, -pred["y_pred"].values)
+
+
+def test_qehvi_additive_sobo_and_nchoosek_through_the_data_models():
+    """Further strategy data models on the device: QehviStrategy (fixed partitioning of the observed front), AdditiveSoboStrategy
+    (weighted sum objective + sigmoid output constraint), and a domain with an NChooseK constraint (nonlinear constraint
+    callables + RandomStrategy as the generator of feasible raw samples, SLSQP one restart at a time: botorch.py:117-121,
+    250-265)."""
+    import everest_b200.bofire_strategy as strategies
+    from bofire.data_models.constraints.api import NChooseKConstraint
+    from bofire.data_models.domain.domain import Domain
+    from bofire.data_models.features.api import ContinuousInput, ContinuousOutput
+    from bofire.data_models.objectives.api import MaximizeObjective, MaximizeSigmoidObjective, MinimizeObjective
+    from bofire.data_models.strategies.predictives.qehvi import QehviStrategy
+    from bofire.data_models.strategies.predictives.sobo import AdditiveSoboStrategy, SoboStrategy
+    from bofire.data_models.strategies.random import RandomStrategy
+    from everest_b200 import acquisition as A
+
+    # --- qEHVI on two objectives
+    dom = Domain.from_lists(
+        inputs=[ContinuousInput(key=f"x{i}", bounds=[0, 1]) for i in range(3)],
+        outputs=[ContinuousOutput(key="y1", objective=MaximizeObjective()), ContinuousOutput(key="y2", objective=MinimizeObjective())])
+
+    def f(domain, c):
+        X = c[domain.inputs.get_keys()].reset_index(drop=True)
+        out = X.copy()
+        out["y1"] = np.sin(3 * X["x0"]) + X["x1"]
+        out["y2"] = (X["x0"] - 0.4) ** 2 + X["x2"]
+        if "y3" in domain.outputs.get_keys():
+            out["y3"] = 0.5 * X["x1"] + 0.2 * X["x2"]
+        for k in domain.outputs.get_keys():
+            out[f"valid_{k}"] = 1
+        return out
+
+    exp = f(dom, strategies.map(RandomStrategy(domain=dom, seed=0)).ask(12))
+    strat = strategies.map(QehviStrategy(domain=dom, seed=1, num_raw_samples=64, num_restarts=2, maxiter=30, num_sobol_samples=64,
+                                         ref_point={"y1": -0.5, "y2": 2.5}), fit_options={"maxiter": 40})
+    strat.tell(exp)
+    acqf = strat._get_acqfs(1)[0]
+    assert isinstance(acqf, A.qExpectedHypervolumeImprovement) and strat.get_adjusted_refpoint() == [-0.5, -2.5]
+    cand = strat.ask(1)
+    assert len(cand) == 1 and all(0.0 <= float(cand[f"x{i}"].iloc[0]) <= 1.0 for i in range(3))
+
+    # --- additive SOBO with an output constraint, qLogNEI default
+    dom2 = Domain.from_lists(
+        inputs=[ContinuousInput(key=f"x{i}", bounds=[0, 1]) for i in range(3)],
+        outputs=[ContinuousOutput(key="y1", objective=MaximizeObjective(w=1.0)), ContinuousOutput(key="y2", objective=MinimizeObjective(w=0.5)),
+                 ContinuousOutput(key="y3", objective=MaximizeSigmoidObjective(steepness=20.0, tp=0.2))])
+    exp2 = f(dom2, strategies.map(RandomStrategy(domain=dom2, seed=2)).ask(14))
+    s2 = strategies.map(AdditiveSoboStrategy(domain=dom2, seed=3, num_raw_samples=64, num_restarts=2, maxiter=30,
+                                             use_output_constraints=True), fit_options={"maxiter": 40})
+    s2.tell(exp2)
+    obj, cons = s2._get_objective_and_constraints()
+    assert obj.combine == "additive" and [(o.kind, o.idx, o.w) for o in obj.ops] == [("max", 0, 1.0), ("min", 1, 0.5)]
+    assert len(cons) == 1 and cons[0].idx == 2
+    c2 = s2.ask(2)
+    assert len(c2) == 2 and {"y1_pred", "y2_pred", "y3_pred", "y3_des"} <= set(c2.columns)
+
+    # --- NChooseK: at most 2 of the 3 inputs non-zero
+    dom3 = Domain.from_lists(
+        inputs=[ContinuousInput(key=f"x{i}", bounds=[0, 1]) for i in range(3)],
+        outputs=[ContinuousOutput(key="y1", objective=MaximizeObjective())],
+        constraints=[NChooseKConstraint(features=["x0", "x1", "x2"], min_count=1, max_count=2, none_also_valid=False)])
+    exp3 = f(dom3, strategies.map(RandomStrategy(domain=dom3, seed=4)).ask(12))
+    assert ((exp3[["x0", "x1", "x2"]].values > 0).sum(axis=1) <= 2).all()
+    s3 = strategies.map(SoboStrategy(domain=dom3, seed=5, num_raw_samples=32, num_restarts=2, maxiter=20), fit_options={"maxiter": 40})
+    s3.tell(exp3)
+    assert s3._get_optimizer_options()["batch_limit"] == 1
+    c3 = s3.ask(1)
+    x = c3[["x0", "x1", "x2"]].values[0]
+    assert (np.abs(x) > 1e-3).sum() <= 2 and (x >= -1e-9).all() and (x <= 1 + 1e-9).all()
+
+
+def test_fully_combinatorial_space_through_the_data_models():
+    """All inputs categorical / discrete (botorch.py:425-467): the choices are enumerated as DataFrames by BoFire's own
+    `get_categorical_combinations`, the measured ones are dropped, and optimize_acqf_discrete picks unique candidates."""
+    import everest_b200.bofire_strategy as strategies
+    from bofire.data_models.domain.domain import Domain
+    from bofire.data_models.features.api import CategoricalInput, ContinuousOutput, DiscreteInput
+    from bofire.data_models.objectives.api import MaximizeObjective
+    from bofire.data_models.strategies.predictives.sobo import SoboStrategy
+
+    dom = Domain.from_lists(
+        inputs=[CategoricalInput(key="c", categories=["a", "b", "c"]), DiscreteInput(key="n", values=[1.0, 2.0, 4.0, 8.0])],
+        outputs=[ContinuousOutput(key="y", objective=MaximizeObjective())])
+    rows = [("a", 1.0), ("b", 2.0), ("c", 4.0), ("a", 8.0), ("b", 8.0), ("c", 1.0)]
+    exp = pd.DataFrame({"c": [r[0] for r in rows], "n": [r[1] for r in rows]})
+    exp["y"] = [0.1, 0.5, 0.9, 0.4, 0.7, 0.2]
+    exp["valid_y"] = 1
+    strat = strategies.map(SoboStrategy(domain=dom, seed=0), fit_options={"maxiter": 40})
+    strat.tell(exp)
+    cand = strat.ask(3)
+    got = set(zip(cand["c"], cand["n"]))
+    assert len(got) == 3 and not (got & set(rows))                     # unique, none of them measured before
+    assert set(cand["c"]) <= {"a", "b", "c"} and set(cand["n"]) <= {1.0, 2.0, 4.0, 8.0}
+    assert {"y_pred", "y_sd", "y_des"} <= set(cand.columns)
