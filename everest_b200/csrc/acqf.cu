@@ -800,6 +800,17 @@ int launch_partition_binary(const double* obj, const unsigned char* front, int n
   return BO_OK;
 }
 
+__global__ void add_inplace_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+int launch_add_inplace(double* dst, const double* src, size_t n, cudaStream_t st, LaunchCounter* lc) {
+  if (n == 0) return BO_OK;
+  add_inplace_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, st>>>(dst, src, n);
+  if (lc) lc->n++;
+  CUDA_CHECK_RET(cudaGetLastError());
+  return BO_OK;
+}
+
 __global__ void count_nonzero_kernel(const int* __restrict__ v, int n, int* __restrict__ count) {
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += v[i] != 0;

@@ -68,6 +68,7 @@ int launch_partition2d(const double* obj, const unsigned char* front, int n, int
 int launch_partition_nd(const double* obj, const unsigned char* front, int n, int S, int Mo, int cap,
                         const double* ref_dev, double* work, double* lo, double* up, int* ncells, int* overflow,
                         cudaStream_t st, LaunchCounter* lc);
+int launch_add_inplace(double* dst, const double* src, size_t n, cudaStream_t st, LaunchCounter* lc);
 int launch_count_nonzero(const int* v, int n, int* count, cudaStream_t st, LaunchCounter* lc);
 int launch_joint_rows_to_root(const double* rootj, int ldn, const double* meanj, int nb, int q, int M, int m, int slot,
                               double* root, double* mu, cudaStream_t st, LaunchCounter* lc);

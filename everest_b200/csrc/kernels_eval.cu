@@ -14,6 +14,8 @@
 // are applied in the same pass; HBM traffic is one 8-byte store per element.
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -396,7 +398,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256, 2)
 crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n2a_g, int n_rows,
                      const double* __restrict__ Bt, const double* __restrict__ n2b_g, int n_cols, int dpad,
-                     double coef, double* __restrict__ out, int ld, int same_set, OzPlanesOut oz) {
+                     double coef, double* __restrict__ out, int ld, int same_set, OzPlanesOut oz, int ct_per_cta) {
   extern __shared__ __align__(16) double cc3sm[];
   double* As = cc3sm;
   double* Bs[2] = {cc3sm + CC_TILE * CC_LDS, cc3sm + 2 * CC_TILE * CC_LDS};
@@ -407,9 +409,9 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
   const int g = lane >> 2, t = lane & 3;
   const int wr = warp & 3, wc = warp >> 2;
   const int row0 = blockIdx.y * CC_TILE;
-  const int ct0 = blockIdx.x * CC3_CT;
+  const int ct0 = blockIdx.x * ct_per_cta;
   const int n_ct_total = (ld + CC_TILE - 1) / CC_TILE;
-  const int n_ct = min(CC3_CT, n_ct_total - ct0);
+  const int n_ct = min(ct_per_cta, n_ct_total - ct0);
 
   __shared__ double2 exptab[32];
   exp_tab_load(exptab);                 // visible after the first __syncthreads() of the column-tile loop
@@ -417,6 +419,9 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
   cc3_load_tile<CC_TILE>(Bs[0], Bt, dpad, ct0 * CC_TILE, n_cols, tid);
   cp_async_commit();
   if (tid < CC_TILE) n2a_s[tid] = (row0 + tid < n_rows) ? n2a_g[row0 + tid] : 0.0;
+  // not unrolled: the compiler otherwise replicates the body for the 8 column tiles (9248 instructions = 148 KB of code) and
+  // the kernel stalls on instruction fetch (ncu r02: 1.75 `no_instruction` stalls per issue)
+#pragma unroll 1
   for (int ci = 0; ci < n_ct; ++ci) {
     const int col0 = (ct0 + ci) * CC_TILE;
     cp_async_wait<0>();
@@ -542,7 +547,12 @@ int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool col
     const int l = md.fac[0][0];
     const LeafD& L = md.leaf[l];
     const int n_ct = (ld + CC_TILE - 1) / CC_TILE;
-    dim3 gridf((n_ct + CC3_CT - 1) / CC3_CT, (rows.n + CC_TILE - 1) / CC_TILE);
+    // column tiles per CTA: 8 amortise the A tile for the big screens; a refinement step has one or two row tiles, and 8 tiles
+    // in sequence per CTA left 4 CTAs working for 47 us -- one tile per CTA until the grid covers the SMs
+    const int row_tiles = (std::max(rows.n, 1) + CC_TILE - 1) / CC_TILE;
+    int ctp = CC3_CT;
+    while (ctp > 1 && (long long)row_tiles * ((n_ct + ctp - 1) / ctp) < 296) ctp >>= 1;
+    dim3 gridf((n_ct + ctp - 1) / ctp, (rows.n + CC_TILE - 1) / CC_TILE);
     if (ozp && ozp->planes) {
       oz = *ozp;
       gridf.y = (oz.rows_alloc + CC_TILE - 1) / CC_TILE;   // the padding rows of the planes are written (zeros) too
@@ -561,16 +571,16 @@ int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool col
     }
     switch (L.kind) {
       case BO_LEAF_RBF:
-        crosscov_fast_kernel<BO_LEAF_RBF><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
+        crosscov_fast_kernel<BO_LEAF_RBF><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz, ctp);
         break;
       case BO_LEAF_MATERN12:
-        crosscov_fast_kernel<BO_LEAF_MATERN12><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
+        crosscov_fast_kernel<BO_LEAF_MATERN12><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz, ctp);
         break;
       case BO_LEAF_MATERN32:
-        crosscov_fast_kernel<BO_LEAF_MATERN32><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
+        crosscov_fast_kernel<BO_LEAF_MATERN32><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz, ctp);
         break;
       default:
-        crosscov_fast_kernel<BO_LEAF_MATERN52><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz);
+        crosscov_fast_kernel<BO_LEAF_MATERN52><<<gridf, 256, smf, s>>>(Aq, n2a, rows.n, cs.s[l].Xs, cs.s[l].n2, n_cols, L.dpad, md.coef[0], out, ld, same_set ? 1 : 0, oz, ctp);
         break;
     }
     if (lc) lc->n++;
