@@ -1045,7 +1045,12 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     // Refinement steps: the outputs are independent until the MC kernel, and every kernel of a 32-point step is latency
     // bound (a few CTAs): the chains of the odd outputs run on a second stream next to those of the even ones.
     const bool par = small_rows && M > 1 && !st->timing;
-    if (par && !st->side2) {
+    // big screens: the conditional roots and sample GEMMs of the outputs (0.18 + 0.13 ms each on config 3) are medium-sized
+    // kernels that do not fill the GPU either: forked as well (9.00 -> 8.87 ms per config-3 screen, same bits;
+    // EVEREST_TAIL_FORK=0 switches it off)
+    static const bool tail_fork_env = []() { const char* e = getenv("EVEREST_TAIL_FORK"); return !e || atoi(e) != 0; }();
+    const bool par_tail = par || (tail_fork_env && M > 1 && !st->timing && !dX_dev);
+    if ((par || par_tail) && !st->side2) {
       CUDA_CHECK_RET(cudaStreamCreateWithFlags(&st->side2, cudaStreamNonBlocking));
       CUDA_CHECK_RET(cudaEventCreateWithFlags(&st->side2_fork, cudaEventDisableTiming));
       CUDA_CHECK_RET(cudaEventCreateWithFlags(&st->side2_join, cudaEventDisableTiming));
@@ -1227,9 +1232,9 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     // everything after the posterior GEMM of the chunk: conditional roots, baseline part of the samples, MC acquisition
     // value (or the adjoint chain).  A lambda because the INT8 guard may have to run it a second time (see below).
     auto run_tail = [&]() -> int {
-    if (par) RC(fork2());
+    if (par_tail) RC(fork2());
     for (int m = 0; m < M; ++m) {
-      cudaStream_t s = (par && (m & 1)) ? st->side2 : s_main;
+      cudaStream_t s = (par_tail && (m & 1)) ? st->side2 : s_main;
       OutputH& o = st->out[m];
       CondRootArgs c;
       c.md = o.md; c.prep_q = o.q_prepd; c.prep_b = o.base_prepd; c.b = bc; c.q = q; c.nb = nb; c.M = M; c.m = m;
@@ -1248,7 +1253,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         rec_end(st, s);
       }
     }
-    if (par) RC(join2());
+    if (par_tail) RC(join2());
     if (fb_active) {
       // joint re-sampling fallback: how many (q-batch, output) conditional roots exhausted the jitter ladder?  The counter
       // travels to the host while the MC kernels below still run, so reading it costs no GPU time
