@@ -1038,17 +1038,20 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
                                                     bool has_cons, const double* __restrict__ lo_p,
                                                     const double* __restrict__ up_p, int stride,
                                                     bool single_fast = false) {
-  unsigned active = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  // which points overlap the cell: one chained compare per (point, objective) -- DSETP.AND folds the conjunction over the
+  // objectives into the predicate, so a point costs MO compares + one select; the per-objective bit masks this replaces cost
+  // three instructions per (point, objective) and were most of the ~107 instructions per cell visit of the q = 8 kernel
+  // (ncu r02: DSETP / SEL / LOP3 1.06e9 / 1.06e9 / 0.56e9 warp instructions per config-4 screen).  Unused slots hold -inf.
   double lo[MO];
 #pragma unroll
-  for (int o = 0; o < MO; ++o) {
-    if (active) {
-      lo[o] = lo_p[o * stride];
-      unsigned m = 0;
+  for (int o = 0; o < MO; ++o) lo[o] = lo_p[o * stride];
+  unsigned active = 0;
 #pragma unroll
-      for (int j = 0; j < QMAX; ++j) m |= (obj[j][o] > lo[o]) ? (1u << j) : 0u;
-      active &= m;
-    }
+  for (int j = 0; j < QMAX; ++j) {
+    bool in = obj[j][0] > lo[0];
+#pragma unroll
+    for (int o = 1; o < MO; ++o) in = in && (obj[j][o] > lo[o]);
+    active |= in ? (1u << j) : 0u;
   }
   if (!active) return 0.0;
   double up[MO];
@@ -1381,7 +1384,89 @@ mc_hvi_chunked_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
   }
 }
 
+// Round 2: the many-cell kernel with the roles swapped -- a WARP owns one MC sample and its 32 lanes own 32 q-batches.
+// The cells of a sample are then warp-uniform: one shared-memory broadcast per bound instead of 32 different addresses, one
+// trip count per warp instead of 32 cell lists of different length, and every thread keeps the objective values of ITS
+// q-batch in registers for the whole kernel (the kernel above re-read them from global memory for every chunk of 24 cells
+// and kept 8 running sums in local memory).  8 samples per CTA, chunks of 64 cells; ncu on the kernel above (config 4):
+// 21 % of the stall samples at the chunk barriers, LDL / STL 8 %, long-scoreboard waits on the objective loads.
+#define MC3_SW 8      // samples (warps) per CTA
+#define MC3_CH 64     // cells per chunk
+template <int QMAX, int MO>
+__global__ void __launch_bounds__(256, 2)
+mc_hvi_bcast_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
+  __shared__ double clo[MC3_CH * MO * MC3_SW];   // [(c * MO + o)][sample]
+  __shared__ double cup[MC3_CH * MO * MC3_SW];
+  __shared__ double red[MC3_SW][33];
+  __shared__ int ncs[MC3_SW];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int q = a.q, S = a.S;
+  const int s0 = blockIdx.x * MC3_SW, s = s0 + w;
+  const int batch = blockIdx.y * 32 + lane;
+  const bool ok = s < S && batch < a.b;
+  const int slots = q * MO + q;
+  const bool has_cons = a.od.n_cons > 0;
+  if (tid < MC3_SW) ncs[tid] = (s0 + tid < S) ? a.ncells[s0 + tid] : 0;
+  double obj[QMAX][MO], fwt[QMAX];
+  {
+    const double* ob = objw + (size_t)(ok ? batch : 0) * slots * S + (ok ? s : 0);
+#pragma unroll
+    for (int j = 0; j < QMAX; ++j) {
+      fwt[j] = 1.0;
+#pragma unroll
+      for (int o = 0; o < MO; ++o) obj[j][o] = (ok && j < q) ? ob[(size_t)(j * MO + o) * S] : -INFINITY;
+      if (has_cons && ok && j < q) fwt[j] = ob[(size_t)(q * MO + j) * S];
+    }
+  }
+  __syncthreads();
+  int ncmax = 0;
+#pragma unroll
+  for (int k = 0; k < MC3_SW; ++k) ncmax = max(ncmax, ncs[k]);
+  const int nc = ncs[w];
+  double acc = 0.0;
+  for (int c0 = 0; c0 < ncmax; c0 += MC3_CH) {
+    __syncthreads();
+    for (int idx = tid; idx < MC3_CH * MO * MC3_SW; idx += 256) {
+      const int ss = idx % MC3_SW, co = idx / MC3_SW;      // 8 consecutive samples of one (cell, objective): 64 contiguous bytes
+      const int c = c0 + co / MO, sg = s0 + ss;
+      const bool in = (sg < S) && (c < ncs[ss]);
+      // cells past the end of a sample's list can never overlap anything
+      clo[idx] = in ? a.cell_lo[((size_t)c * MO + co % MO) * S + sg] : INFINITY;
+      cup[idx] = in ? a.cell_up[((size_t)c * MO + co % MO) * S + sg] : -INFINITY;
+    }
+    __syncthreads();
+    if (ok) {
+      const int cn = min(MC3_CH, nc - c0);                   // warp-uniform
+      for (int c = 0; c < cn; ++c)
+        acc += cell_contribution<QMAX, MO, (QMAX <= 4)>(obj, fwt, q, has_cons, clo + (c * MO) * MC3_SW + w, cup + (c * MO) * MC3_SW + w, MC3_SW);
+    }
+  }
+  red[w][lane] = ok ? acc : 0.0;
+  __syncthreads();
+  if (w == 0 && batch < a.b) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < MC3_SW; ++k) t += red[k][lane];     // fixed order over the CTA's samples
+    a.partial[(size_t)blockIdx.x * a.b + batch] = t;
+  }
+}
+
 typedef void (*McChunkedFn)(McArgs, const double*, int);
+template <int MO>
+static McChunkedFn pick_bcast_q(int q) {
+  if (q <= 2) return mc_hvi_bcast_kernel<2, MO>;
+  if (q <= 4) return mc_hvi_bcast_kernel<4, MO>;
+  if (q <= 8) return mc_hvi_bcast_kernel<8, MO>;
+  return nullptr;
+}
+static McChunkedFn pick_bcast(int q, int Mo) {
+  if (Mo == 2) return pick_bcast_q<2>(q);
+  if (Mo == 3) return pick_bcast_q<3>(q);
+  if (Mo == 4) return pick_bcast_q<4>(q);
+  return nullptr;
+}
+int mc_hvi_partial_groups(int S) { return (S + MC3_SW - 1) / MC3_SW; }
+
 template <int MO>
 static McChunkedFn pick_chunked_q(int q) {
   if (q <= 2) return mc_hvi_chunked_kernel<2, MO>;
@@ -1424,7 +1509,7 @@ static int mc_forced_path() {
   const char* e = getenv("EVEREST_MC_PATH");
   if (!e) return 0;
   if (e[0] == 't') return 1;
-  if (e[0] == 'c') return 2;
+  if (e[0] == 'c' || e[0] == 'o') return 2;
   if (e[0] == 'g') return 3;
   return 0;
 }
@@ -1452,9 +1537,18 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
   if (obj_ws && mc_use_chunked(a, max_cells)) {
     mc_objectives_kernel<<<a.b, 256, 0, st>>>(a, obj_ws);
     if (lc) lc->n++;
-    McChunkedFn cf = pick_chunked(a.q, Mo);
-    dim3 grid((a.S + MC2_S - 1) / MC2_S, (a.b + MC2_BG * MC2_BPT - 1) / (MC2_BG * MC2_BPT));
-    cf<<<grid, 256, 0, st>>>(a, obj_ws, max_cells);
+    // EVEREST_MC_PATH=old keeps the round-1 kernel (thread = sample, 8 q-batches per thread) for comparison
+    static const bool old_kernel = []() { const char* e = getenv("EVEREST_MC_PATH"); return e && e[0] == 'o'; }();
+    dim3 grid;
+    if (old_kernel) {
+      McChunkedFn cf = pick_chunked(a.q, Mo);
+      grid = dim3((a.S + MC2_S - 1) / MC2_S, (a.b + MC2_BG * MC2_BPT - 1) / (MC2_BG * MC2_BPT));
+      cf<<<grid, 256, 0, st>>>(a, obj_ws, max_cells);
+    } else {
+      McChunkedFn cf = pick_bcast(a.q, Mo);
+      grid = dim3((a.S + MC3_SW - 1) / MC3_SW, (a.b + 31) / 32);
+      cf<<<grid, 256, 0, st>>>(a, obj_ws, max_cells);
+    }
     if (lc) lc->n++;
     mc_reduce_partials_kernel<<<(a.b + 255) / 256, 256, 0, st>>>(a.partial, grid.x, a.b, a.S, a.out, a.info_in, a.M, a.info_out);
     if (lc) lc->n++;

@@ -78,6 +78,7 @@ int launch_partition_binary(const double* obj, const unsigned char* front, int n
                             LaunchCounter* lc);
 int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t st, LaunchCounter* lc);
 size_t mc_hvi_obj_ws_bytes(const McArgs& a, int max_cells);
+int mc_hvi_partial_groups(int S);   // sample groups of the MC/HVI partial sums (rows of McArgs::partial)
 int launch_mc_scalar(const McArgs& a, cudaStream_t st, LaunchCounter* lc);
 // scalarised objective of baseline samples F[m][s][ldf] + mean: per-sample best value and / or arg-max counts per point
 // (infeasible samples, c(y) > 0, take `infeasible_value`; n_all_infeasible counts the MC samples without a feasible point)

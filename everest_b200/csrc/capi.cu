@@ -1012,7 +1012,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
     RC(st->wsBL.ensure(rows_max * ldbl * 8 * M));
     RC(st->wsFp.ensure(rows_max * (size_t)S * 8 * M));
   }
-  RC(st->wsPartial.ensure((size_t)((S + 31) / 32) * bchunk * 8));
+  RC(st->wsPartial.ensure((size_t)mc_hvi_partial_groups(S) * bchunk * 8));
   std::vector<PostGemmArgs> pg(M);
   for (int b0 = 0; b0 < b; b0 += bchunk) {
     const int bc = std::min(bchunk, b - b0), rows = bc * q;
@@ -1479,7 +1479,7 @@ extern "C" int bo_acqf_resample_flagged(bo_state* st, const double* X_dev, int32
   RC(st->wsRoot.ensure((size_t)M * q * nr * 8));
   RC(st->wsMu.ensure((size_t)q * M * 8));
   RC(st->wsJit.ensure((size_t)M * sizeof(int)));
-  RC(st->wsPartial.ensure((size_t)((S + 31) / 32) * 8));
+  RC(st->wsPartial.ensure((size_t)mc_hvi_partial_groups(S) * 8));
   if (nb > 0) CUDA_CHECK_RET(cudaMemcpyAsync(st->wsXfull.p, st->Xb_raw.p, (size_t)nb * d * 8, cudaMemcpyDeviceToDevice, s));
   int done = 0;
   for (int i : flagged) {
