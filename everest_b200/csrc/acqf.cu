@@ -1005,6 +1005,37 @@ mc_hvi_kernel(McArgs a) {
 // Contribution of one cell to the inclusion-exclusion sum for one MC sample.  A point overlaps the cell iff
 // obj > lower in every objective (cells are non-empty, so upper > lower); the overlap test is compare-only
 // and most cells are rejected after the first objective.  Only overlapping points enter the subset sums.
+// One point against one cell's lower bounds: the conjunction over the objectives is carried in the predicate operand of the
+// compares (setp.gt.and), and the point's bit is OR-ed in under that predicate -- MO + 1 instructions per point.  Written in
+// PTX because the compiler turns the C++ form into a compare AND a select per objective (ncu source view, config 4: 32 DSETP
+// + 32 SEL per cell visit).
+template <int MO>
+__device__ __forceinline__ unsigned overlap_bit(const double (&v)[MO], const double (&lo)[MO], unsigned active, unsigned bit) {
+  static_assert(MO >= 2 && MO <= 4, "2 to 4 objectives");
+  if (MO == 2)
+    asm("{ .reg .pred p;\n setp.gt.f64 p, %2, %4;\n setp.gt.and.f64 p, %3, %5, p;\n @p or.b32 %0, %0, %1;\n }"
+        : "+r"(active) : "r"(bit), "d"(v[0]), "d"(v[1]), "d"(lo[0]), "d"(lo[1]));
+  else if (MO == 3)
+    asm("{ .reg .pred p;\n setp.gt.f64 p, %2, %5;\n setp.gt.and.f64 p, %3, %6, p;\n setp.gt.and.f64 p, %4, %7, p;\n"
+        " @p or.b32 %0, %0, %1;\n }"
+        : "+r"(active) : "r"(bit), "d"(v[0]), "d"(v[1]), "d"(v[MO > 2 ? 2 : 0]), "d"(lo[0]), "d"(lo[1]), "d"(lo[MO > 2 ? 2 : 0]));
+  else
+    asm("{ .reg .pred p;\n setp.gt.f64 p, %2, %6;\n setp.gt.and.f64 p, %3, %7, p;\n setp.gt.and.f64 p, %4, %8, p;\n"
+        " setp.gt.and.f64 p, %5, %9, p;\n @p or.b32 %0, %0, %1;\n }"
+        : "+r"(active) : "r"(bit), "d"(v[0]), "d"(v[1]), "d"(v[MO > 2 ? 2 : 0]), "d"(v[MO > 3 ? 3 : 0]), "d"(lo[0]), "d"(lo[1]),
+          "d"(lo[MO > 2 ? 2 : 0]), "d"(lo[MO > 3 ? 3 : 0]));
+  return active;
+}
+__device__ __forceinline__ unsigned overlap_bit_f(const float* v, const float* lo, int mo, unsigned active, unsigned bit) {
+  bool in = v[0] > lo[0];
+  for (int o = 1; o < mo; ++o) in = in && (v[o] > lo[o]);
+  return active | (in ? bit : 0u);
+}
+template <int MO>
+__device__ __forceinline__ unsigned overlap_bit(const float (&v)[MO], const float (&lo)[MO], unsigned active, unsigned bit) {
+  return overlap_bit_f(v, lo, MO, active, bit);
+}
+
 template <int QMAX, int MO, int J, int SIZE>
 struct SubsetWalk {
   static __device__ __forceinline__ void go(const double (&obj)[QMAX][MO], const double (&fwt)[QMAX], unsigned active,
@@ -1047,12 +1078,7 @@ __device__ __forceinline__ double cell_contribution(const double (&obj)[QMAX][MO
   for (int o = 0; o < MO; ++o) lo[o] = lo_p[o * stride];
   unsigned active = 0;
 #pragma unroll
-  for (int j = 0; j < QMAX; ++j) {
-    bool in = obj[j][0] > lo[0];
-#pragma unroll
-    for (int o = 1; o < MO; ++o) in = in && (obj[j][o] > lo[o]);
-    active |= in ? (1u << j) : 0u;
-  }
+  for (int j = 0; j < QMAX; ++j) active = overlap_bit<MO>(obj[j], lo, active, 1u << j);
   if (!active) return 0.0;
   double up[MO];
 #pragma unroll
@@ -1451,7 +1477,176 @@ mc_hvi_bcast_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
   }
 }
 
+// Round 2, second step: the same warp = sample / lane = q-batch layout, but the cells are SCANNED first and the subset sums
+// run from a per-lane work list afterwards.  ncu source view of the kernel above on config 4 (q = 8, 4 objectives, ~1500
+// cells per sample): 10.8 of 32 lanes active on average -- for a given cell only a few of the warp's 32 q-batches overlap
+// it, and the others wait while those walk their subsets, each subset costing QMAX * MO predicated FP64 minima (three
+// instructions each).  Here
+//   scan     every lane tests every cell of the chunk (uniform, compare-only; with FILT on FP32 copies rounded outwards,
+//            which can only add candidates) and notes the overlapping points of cell c in act[c][lane] and bit c of `hit`;
+//   process  each lane walks ITS hit cells and their subsets as one flattened loop (one trip per subset, cell switches
+//            inside the loop), so a lane waits for the longest work list of the warp instead of for the busiest lane of
+//            every single cell; the members of a subset are visited by set bit from a shared-memory copy of the lane's
+//            objective values (dynamic point index without local memory), not by QMAX predicated steps.
+// Cells are accumulated in ascending order per lane as before (deterministic); inside a cell the subset volumes are summed
+// with their signs in enumeration order instead of size by size.
+#define MC4_SW 4      // samples (warps) per CTA
+#define MC4_CH 64     // cells per chunk (one bit each in `hit`)
+template <int QMAX, int MO>
+struct Mc4Layout {
+  static constexpr int CS = 2 * MO + 1;              // lower, upper, pad: odd stride, lanes read different cells
+  static constexpr int CB = MC4_CH * CS;             // doubles
+  static constexpr int OB = QMAX * MO * 32;          // [(j * MO + o)][lane]
+  static constexpr int FW = QMAX * 32;               // [j][lane]
+  static constexpr int AC = MC4_CH * 32 / 8;         // act bytes, in doubles
+  static constexpr int LF = MC4_CH * MO / 2 + 1;     // FP32 lower bounds, in doubles
+  static constexpr int PER_WARP = CB + OB + FW + AC + LF;
+};
+template <bool FILT> struct Mc4Scan { typedef double T; };
+template <> struct Mc4Scan<true> { typedef float T; };
+
+template <int QMAX, int MO, bool FILT>
+__global__ void __launch_bounds__(MC4_SW * 32)
+mc_hvi_queue_kernel(McArgs a, const double* __restrict__ objw, int maxc) {
+  extern __shared__ double qsm[];
+  typedef Mc4Layout<QMAX, MO> L;
+  typedef typename Mc4Scan<FILT>::T T;
+  __shared__ double red[MC4_SW][33];
+  __shared__ int ncs[MC4_SW];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double* cb = qsm + (size_t)w * L::PER_WARP;
+  double* objs = cb + L::CB;
+  double* fwts = objs + L::OB;
+  unsigned char* act = reinterpret_cast<unsigned char*>(fwts + L::FW);
+  const float* lof = reinterpret_cast<const float*>(fwts + L::FW + L::AC);
+  const int q = a.q, S = a.S;
+  const int s0 = blockIdx.x * MC4_SW, s = s0 + w;
+  const int batch = blockIdx.y * 32 + lane;
+  const bool ok = s < S && batch < a.b;
+  const int slots = q * MO + q;
+  const bool has_cons = a.od.n_cons > 0;
+  if (tid < MC4_SW) ncs[tid] = (s0 + tid < S) ? a.ncells[s0 + tid] : 0;
+  T objr[QMAX][MO];
+  {
+    const double* ob = objw + (size_t)(ok ? batch : 0) * slots * S + (ok ? s : 0);
+#pragma unroll
+    for (int j = 0; j < QMAX; ++j) {
+#pragma unroll
+      for (int o = 0; o < MO; ++o) {
+        const double v = (ok && j < q) ? ob[(size_t)(j * MO + o) * S] : -INFINITY;
+        objs[(j * MO + o) * 32 + lane] = v;
+        objr[j][o] = FILT ? (T)__double2float_ru(v) : (T)v;
+      }
+      fwts[j * 32 + lane] = (has_cons && ok && j < q) ? ob[(size_t)(q * MO + j) * S] : 1.0;
+    }
+  }
+  __syncthreads();
+  int ncmax = 0;
+#pragma unroll
+  for (int k = 0; k < MC4_SW; ++k) ncmax = max(ncmax, ncs[k]);
+  const int nc = ncs[w];
+  double acc = 0.0;
+  for (int c0 = 0; c0 < ncmax; c0 += MC4_CH) {
+    __syncthreads();
+    for (int idx = tid; idx < MC4_CH * MO * MC4_SW; idx += MC4_SW * 32) {
+      const int ss = idx % MC4_SW, co = idx / MC4_SW;      // consecutive samples of one (cell, objective): one 32-byte sector
+      const int cc = co / MO, o = co % MO, c = c0 + cc, sg = s0 + ss;
+      const bool in = (sg < S) && (c < ncs[ss]);
+      const double lo = in ? a.cell_lo[((size_t)c * MO + o) * S + sg] : INFINITY;
+      const double up = in ? a.cell_up[((size_t)c * MO + o) * S + sg] : -INFINITY;
+      double* cbs = qsm + (size_t)ss * L::PER_WARP;
+      cbs[cc * L::CS + o] = lo;
+      cbs[cc * L::CS + MO + o] = up;
+      if (FILT) reinterpret_cast<float*>(cbs + L::CB + L::OB + L::FW + L::AC)[cc * MO + o] = __double2float_rd(lo);
+    }
+    __syncthreads();
+    const int cn = min(MC4_CH, nc - c0);                     // warp-uniform, <= 0 past the end of this sample's list
+    // ---- scan
+    unsigned long long hit = 0ull;
+    for (int c = 0; c < cn; ++c) {
+      T lo[MO];
+#pragma unroll
+      for (int o = 0; o < MO; ++o) lo[o] = FILT ? (T)lof[c * MO + o] : (T)cb[c * L::CS + o];
+      unsigned active = 0;
+#pragma unroll
+      for (int j = 0; j < QMAX; ++j) active = overlap_bit<MO>(objr[j], lo, active, 1u << j);
+      act[c * 32 + lane] = (unsigned char)active;
+      hit |= (unsigned long long)(active != 0u) << c;
+    }
+    // ---- process: one trip per (hit cell, subset of its overlapping points)
+    unsigned sub = 0, active = 0;
+    double cell = 0.0, lo[MO], up[MO];
+    for (;;) {
+      if (sub == 0) {
+        acc += cell;
+        cell = 0.0;
+        if (!hit) break;
+        const int c = __ffsll((long long)hit) - 1;
+        hit &= hit - 1ull;
+        const double* l = cb + c * L::CS;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) { lo[o] = l[o]; up[o] = l[MO + o]; }
+        const unsigned cand = act[c * 32 + lane];
+        if (FILT) {                                            // exact re-test of the FP32 candidates
+          active = 0;
+          for (unsigned m = cand; m; m &= m - 1u) {
+            const int j = __ffs((int)m) - 1;
+            bool in = objs[(j * MO) * 32 + lane] > lo[0];
+#pragma unroll
+            for (int o = 1; o < MO; ++o) in = in && (objs[(j * MO + o) * 32 + lane] > lo[o]);
+            active |= in ? (1u << j) : 0u;
+          }
+        } else {
+          active = cand;
+        }
+        sub = active;
+        if (!sub) continue;
+      }
+      // volume of the intersection of the subset's boxes with the cell; every member exceeds `lo` in every objective,
+      // so the sides are positive without a clamp
+      unsigned m = sub;
+      int j = __ffs((int)m) - 1;
+      m &= m - 1u;
+      double mn[MO];
+#pragma unroll
+      for (int o = 0; o < MO; ++o) mn[o] = fmin(up[o], objs[(j * MO + o) * 32 + lane]);
+      for (; m; m &= m - 1u) {
+        j = __ffs((int)m) - 1;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) mn[o] = fmin(mn[o], objs[(j * MO + o) * 32 + lane]);
+      }
+      double vol = mn[0] - lo[0];
+#pragma unroll
+      for (int o = 1; o < MO; ++o) vol *= mn[o] - lo[o];
+      if (has_cons)
+        for (unsigned m2 = sub; m2; m2 &= m2 - 1u) vol *= fwts[(__ffs((int)m2) - 1) * 32 + lane];
+      cell += (__popc(sub) & 1) ? vol : -vol;
+      sub = (sub - 1u) & active;
+    }
+  }
+  red[w][lane] = ok ? acc : 0.0;
+  __syncthreads();
+  if (w == 0 && batch < a.b) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < MC4_SW; ++k) t += red[k][lane];     // fixed order over the CTA's samples
+    a.partial[(size_t)blockIdx.x * a.b + batch] = t;
+  }
+}
+
 typedef void (*McChunkedFn)(McArgs, const double*, int);
+template <int MO>
+static McChunkedFn pick_queue_q(int q, bool filt, size_t* bytes) {
+  if (q <= 4) { *bytes = (size_t)MC4_SW * Mc4Layout<4, MO>::PER_WARP * sizeof(double); return filt ? mc_hvi_queue_kernel<4, MO, true> : mc_hvi_queue_kernel<4, MO, false>; }
+  if (q <= 8) { *bytes = (size_t)MC4_SW * Mc4Layout<8, MO>::PER_WARP * sizeof(double); return filt ? mc_hvi_queue_kernel<8, MO, true> : mc_hvi_queue_kernel<8, MO, false>; }
+  return nullptr;
+}
+static McChunkedFn pick_queue(int q, int Mo, bool filt, size_t* bytes) {
+  if (Mo == 2) return pick_queue_q<2>(q, filt, bytes);
+  if (Mo == 3) return pick_queue_q<3>(q, filt, bytes);
+  if (Mo == 4) return pick_queue_q<4>(q, filt, bytes);
+  return nullptr;
+}
 template <int MO>
 static McChunkedFn pick_bcast_q(int q) {
   if (q <= 2) return mc_hvi_bcast_kernel<2, MO>;
@@ -1465,7 +1660,7 @@ static McChunkedFn pick_bcast(int q, int Mo) {
   if (Mo == 4) return pick_bcast_q<4>(q);
   return nullptr;
 }
-int mc_hvi_partial_groups(int S) { return (S + MC3_SW - 1) / MC3_SW; }
+int mc_hvi_partial_groups(int S) { return (S + MC4_SW - 1) / MC4_SW; }   // the finest grouping of the three kernels
 
 template <int MO>
 static McChunkedFn pick_chunked_q(int q) {
@@ -1539,8 +1734,17 @@ int launch_mc_hvi(const McArgs& a, int max_cells, double* obj_ws, cudaStream_t s
     if (lc) lc->n++;
     // EVEREST_MC_PATH=old keeps the round-1 kernel (thread = sample, 8 q-batches per thread) for comparison
     static const bool old_kernel = []() { const char* e = getenv("EVEREST_MC_PATH"); return e && e[0] == 'o'; }();
+    // EVEREST_MC_QUEUE: 0 = broadcast kernel, 1 = scan / work-list kernel with FP64 scan (default), 2 = with the FP32
+    // pre-filter (measured slower on config 4: 10.2 vs 9.15 ms per screen; the exact re-test costs more than the scan saves)
+    static const int queue_mode = mc_env_flag("EVEREST_MC_QUEUE", 1);
     dim3 grid;
-    if (old_kernel) {
+    size_t qbytes = 0;
+    McChunkedFn qf = (!old_kernel && queue_mode > 0 && a.q > 4) ? pick_queue(a.q, Mo, queue_mode > 1, &qbytes) : nullptr;
+    if (qf) {
+      CUDA_CHECK_RET(cudaFuncSetAttribute(qf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qbytes));
+      grid = dim3((a.S + MC4_SW - 1) / MC4_SW, (a.b + 31) / 32);
+      qf<<<grid, MC4_SW * 32, qbytes, st>>>(a, obj_ws, max_cells);
+    } else if (old_kernel) {
       McChunkedFn cf = pick_chunked(a.q, Mo);
       grid = dim3((a.S + MC2_S - 1) / MC2_S, (a.b + MC2_BG * MC2_BPT - 1) / (MC2_BG * MC2_BPT));
       cf<<<grid, 256, 0, st>>>(a, obj_ws, max_cells);
