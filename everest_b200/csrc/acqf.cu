@@ -121,35 +121,41 @@ int launch_finish_var(const ModelD& md, PrepD prep, const double* g, int n, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// cond_root: one warp per (q-batch, output).  Sqq, Sqb -> bl = Sqb L_b^-T (forward substitution with
-// warp-shuffle dot products), br = psd_safe_chol(Sqq - bl bl^T) with the 1e-8..1e-3 jitter ladder,
-// un-standardised mean.  root[(batch*M + m)][q][nb + q] = [bl | br].
+// cond_root: one warp per (q-batch, output) -- or, for large baselines (launcher: wpb = 4), the four warps of a CTA on one
+// q-batch.  Sqq, Sqb -> bl = Sqb L_b^-T (product with the cached inverse root), br = psd_safe_chol(Sqq - bl bl^T) with the
+// 1e-8..1e-3 jitter ladder, un-standardised mean.  root[(batch*M + m)][q][nb + q] = [bl | br].
+// Every sum is accumulated in the same order whichever way the work is split (lanes own columns e; a pair (i, j) of the
+// Gram update is reduced by one warp), so both layouts give bit-identical roots.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 cond_root_kernel(CondRootArgs a) {
   extern __shared__ double csm[];
   const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int batch = blockIdx.x * 4 + warp_in_cta;
+  const bool wide = a.wpb == 4;                                         // uniform over the grid
+  const int batch = wide ? blockIdx.x : blockIdx.x * 4 + warp_in_cta;
+  const int tl = wide ? (int)threadIdx.x : lane, tn = wide ? 128 : 32;  // thread index / count within the q-batch's team
+  const int wsub = wide ? warp_in_cta : 0, nw = wide ? 4 : 1;           // warp index / count within the team
   const int q = a.q, nb = a.nb, nr = nb + q;
   const ModelD& md = a.md;
-  // per-warp scratch, then (optionally) the CTA-shared copy of L_b^-1
+  // per-team scratch, then (optionally) the CTA-shared copy of L_b^-1
   const int blw = max(nb, a.stage_cols);                               // columns of the BLs scratch (bl, or staged rows)
-  const size_t per_warp = (size_t)q * nb + 2 * q * q + (size_t)q * blw;
-  double* Sqb = csm + (size_t)warp_in_cta * per_warp;                   // [q][nb]
+  const size_t per_team = (size_t)q * nb + 2 * q * q + (size_t)q * blw;
+  double* Sqb = csm + (wide ? 0 : (size_t)warp_in_cta * per_team);      // [q][nb]
   double* Sc = Sqb + q * nb;                                            // [q][q]
   double* Lq = Sc + q * q;                                              // [q][q]
   double* BLs = Lq + q * q;                                             // [q][nb] bl
   const double* Li = a.LbInv;
   int ldli = a.ldlb;
   if (a.linv_in_smem) {
-    double* Ls = csm + (size_t)4 * per_warp;
+    double* Ls = csm + (size_t)(wide ? 1 : 4) * per_team;
     ldli = nb | 1;  // odd stride: lanes (rows e) hit distinct banks
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x)
       Ls[(idx / nb) * ldli + (idx % nb)] = a.LbInv[(size_t)(idx / nb) * a.ldlb + (idx % nb)];
     Li = Ls;
   }
   __syncthreads();
-  if (batch >= a.b) return;
+  if (batch >= a.b) return;   // (wide: the whole CTA leaves together)
+#define TEAM_SYNC() do { if (wide) __syncthreads(); else __syncwarp(); } while (0)
   const double s2 = md.y_std * md.y_std;
   const int row0 = batch * q;
 
@@ -163,9 +169,9 @@ cond_root_kernel(CondRootArgs a) {
     const LeafD& L = md.leaf[l];
     double* aq = BLs;                       // [q][dpad] staging, overwritten by bl afterwards (q * dpad <= q * nb is not
                                             // guaranteed: the launcher sizes BLs for max(nb, dpad) columns)
-    for (int idx = lane; idx < q * L.dpad; idx += 32) aq[idx] = a.prep_q.Xs[l][(size_t)row0 * L.dpad + idx];
-    __syncwarp();
-    for (int e = lane; e < nb; e += 32) {
+    for (int idx = tl; idx < q * L.dpad; idx += tn) aq[idx] = a.prep_q.Xs[l][(size_t)row0 * L.dpad + idx];
+    TEAM_SYNC();
+    for (int e = tl; e < nb; e += tn) {
       const double* bx = a.prep_b.Xs[l] + (size_t)e * L.dpad;
       double dot[8];
 #pragma unroll
@@ -186,15 +192,15 @@ cond_root_kernel(CondRootArgs a) {
           Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
         }
     }
-    __syncwarp();
+    TEAM_SYNC();
   } else {
     for (int j = 0; j < q; ++j)
-      for (int e = lane; e < nb; e += 32) {
+      for (int e = tl; e < nb; e += tn) {
         double kqb = model_eval_pair(md, a.prep_q, row0 + j, a.prep_b, e, false);
         Sqb[j * nb + e] = (kqb - a.W[(size_t)(row0 + j) * a.ldw + e]) * s2;
       }
   }
-  for (int p = lane; p < q * q; p += 32) {
+  for (int p = tl; p < q * q; p += tn) {
     int i = p / q, j = p % q;
     if (j >= i) {
       double kqq = model_eval_pair(md, a.prep_q, row0 + i, a.prep_q, row0 + j, i == j);
@@ -203,10 +209,10 @@ cond_root_kernel(CondRootArgs a) {
       Sc[j * q + i] = v;
     }
   }
-  __syncwarp();
+  TEAM_SYNC();
   // bl = Sqb L_b^-T with the cached inverse root: bl[j][e] = sum_{l<=e} Sqb[j][l] LbInv[e][l]  (lanes over e)
   if (a.linv_in_smem) {
-    for (int e = lane; e < nb; e += 32) {
+    for (int e = tl; e < nb; e += tn) {
       const double* lrow = Li + (size_t)e * ldli;
       if (q <= 8) {
         // one pass over row e of L_b^-1 for all q points (same summation order per point)
@@ -232,21 +238,37 @@ cond_root_kernel(CondRootArgs a) {
     }
   } else {
     // large baselines: stream the TRANSPOSED inverse (rows l, lanes over consecutive e -> coalesced);
-    // entries with l > e are exact zeros of the triangular factor
-    for (int e0 = 0; e0 < nb; e0 += 32) {
+    // entries with l > e are exact zeros of the triangular factor.  Blocks of 32 columns are dealt to the team's warps; a
+    // row of the inverse is read ONCE for up to 8 points of the q-batch (the loads do not depend on the FMA chains, so
+    // the unrolled loop keeps several of them in flight).
+    for (int e0 = wsub * 32; e0 < nb; e0 += 32 * nw) {
       const int e = e0 + lane;
       const int lmax = min(nb, e0 + 32);
-      for (int j = 0; j < q; ++j) {
-        double s = 0.0;
-        if (e < nb)
-          for (int l = 0; l < lmax; ++l) s = fma(Sqb[j * nb + l], a.LbInvT[(size_t)l * a.ldlb + e], s);
-        if (e < nb) BLs[j * nb + e] = s;
+      const int ec = min(e, nb - 1);               // clamp: lanes past the last column compute a value nobody stores
+      for (int j0 = 0; j0 < q; j0 += 8) {
+        double acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+        const double* lp = a.LbInvT + ec;
+        const double* sq = Sqb + (size_t)j0 * nb;
+#pragma unroll 4
+        for (int l = 0; l < lmax; ++l) {
+          const double lv = lp[(size_t)l * a.ldlb];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j0 + j < q) acc[j] = fma(sq[j * nb + l], lv, acc[j]);
+        }
+        if (e < nb) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j0 + j < q) BLs[(j0 + j) * nb + e] = acc[j];
+        }
       }
     }
   }
-  __syncwarp();
-  // Sc -= bl bl^T
-  for (int p = 0; p < q * q; ++p) {
+  TEAM_SYNC();
+  // Sc -= bl bl^T  (one warp per pair)
+  for (int p = wsub; p < q * q; p += nw) {
     int i = p / q, j = p % q;
     if (j < i) continue;
     double s = 0.0;
@@ -257,19 +279,19 @@ cond_root_kernel(CondRootArgs a) {
       if (i != j) Sc[j * q + i] -= s;
     }
   }
-  __syncwarp();
-  // psd_safe_cholesky on q x q (lane 0), jitter ladder 1e-8 * 10^i, i = 0..5, added incrementally
+  TEAM_SYNC();
+  // psd_safe_cholesky on q x q (one thread), jitter ladder 1e-8 * 10^i, i = 0..5, added incrementally
   int fail = 0;
   double jitter_total = 0.0;
-  if (lane == 0) {
+  if (tl == 0) {
     double prev = 0.0;
     for (int attempt = 0; attempt <= 6; ++attempt) {
       if (attempt > 0) {
         const double ladder[6] = {1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0};
-        double nw = 1e-8 * ladder[attempt - 1];
-        for (int i = 0; i < q; ++i) Sc[i * q + i] += (nw - prev);
-        jitter_total += (nw - prev);
-        prev = nw;
+        double nw2 = 1e-8 * ladder[attempt - 1];
+        for (int i = 0; i < q; ++i) Sc[i * q + i] += (nw2 - prev);
+        jitter_total += (nw2 - prev);
+        prev = nw2;
       }
       fail = 0;
       for (int j = 0; j < q && !fail; ++j) {
@@ -294,20 +316,21 @@ cond_root_kernel(CondRootArgs a) {
     if (a.info) a.info[(size_t)batch * a.M + a.m] = fail;
     if (a.jitter) a.jitter[(size_t)batch * a.M + a.m] = jitter_total;
   }
-  __syncwarp();
+  TEAM_SYNC();
   double* root = a.root + ((size_t)batch * a.M + a.m) * q * nr;
-  for (int idx = lane; idx < q * nr; idx += 32) {
+  for (int idx = tl; idx < q * nr; idx += tn) {
     int j = idx / nr, c = idx % nr;
     root[idx] = (c < nb) ? BLs[j * nb + c] : Lq[j * q + (c - nb)];
   }
   if (a.BL) {
-    for (int idx = lane; idx < q * a.ldbl; idx += 32) {
+    for (int idx = tl; idx < q * a.ldbl; idx += tn) {
       int j = idx / a.ldbl, c = idx % a.ldbl;
       a.BL[(size_t)(row0 + j) * a.ldbl + c] = (c < nb) ? BLs[j * nb + c] : 0.0;
     }
   }
-  for (int j = lane; j < q; j += 32)
+  for (int j = tl; j < q; j += tn)
     a.mu[((size_t)(row0 + j)) * a.M + a.m] = (md.mean_const + a.mu_raw[row0 + j]) * md.y_std + md.y_mean;
+#undef TEAM_SYNC
 }
 
 int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc) {
@@ -318,10 +341,13 @@ int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc)
   if (a.md.n_terms == 1 && a.md.nfac[0] == 1 && a.md.leaf[a.md.fac[0][0]].kind <= BO_LEAF_MATERN52)
     a.stage_cols = a.md.leaf[a.md.fac[0][0]].dpad;
   const int blw = std::max(a.nb, a.stage_cols);
-  size_t per_warp = ((size_t)a.q * a.nb + 2 * (size_t)a.q * a.q + (size_t)a.q * blw) * sizeof(double);
-  size_t smem = 4 * per_warp;
+  size_t per_team = ((size_t)a.q * a.nb + 2 * (size_t)a.q * a.q + (size_t)a.q * blw) * sizeof(double);
+  // large baselines: one q-batch per CTA (its four warps share the columns), so that the scratch of four q-batches does
+  // not hold the SM at one resident CTA (n_b = 286, q = 8: 150 KB per CTA before, 37 KB now)
+  a.wpb = (a.nb > 64) ? 4 : 1;
+  size_t smem = (a.wpb == 4 ? 1 : 4) * per_team;
   size_t linv = (size_t)a.nb * (a.nb | 1) * sizeof(double);
-  a.linv_in_smem = (a.nb > 0 && smem + linv <= 96 * 1024) ? 1 : 0;
+  a.linv_in_smem = (a.nb > 0 && a.wpb == 1 && smem + linv <= 96 * 1024) ? 1 : 0;
   if (a.linv_in_smem) smem += linv;
   if (smem > 200 * 1024) { bo_set_error("cond_root: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
@@ -329,7 +355,7 @@ int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc)
     CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  cond_root_kernel<<<(a.b + 3) / 4, 128, smem, st>>>(a);
+  cond_root_kernel<<<a.wpb == 4 ? a.b : (a.b + 3) / 4, 128, smem, st>>>(a);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

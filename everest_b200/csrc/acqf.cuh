@@ -16,6 +16,7 @@ struct CondRootArgs {
   int ldlb;
   int linv_in_smem;      // set by the launcher
   int stage_cols;        // set by the launcher: dpad of the single continuous leaf (0 = generic kernel tree)
+  int wpb;               // set by the launcher: warps per q-batch (1, or 4 = the whole CTA for large baselines)
   double* root;          // [b, M, q, nb+q]
   double* BL;            // [b*q, ldbl] copy of bl for output m, zero padded (operand of the sample GEMM) or NULL
   int ldbl;

@@ -156,6 +156,22 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
       for (int f2 = f1 + 1; f2 < md.nfac[multi]; ++f2)
         if (md.fac[multi][f1] == md.fac[multi][f2]) leaf_major = false;
   const int n_items = leaf_major ? md.n_leaves : n_fac_total;
+  // role of every leaf in the leaf-major order, found once per CTA (it was re-derived by every thread for every leaf):
+  // coefficient of the single-leaf terms that hold it, and whether the product term holds it
+  __shared__ double s_csingle[BO_MAX_LEAVES];
+  __shared__ int s_role[BO_MAX_LEAVES];   // bit 0: has a single-leaf term, bit 1: factor of the product
+  if (leaf_major && tid < md.n_leaves) {
+    double c = 0.0;
+    int role = 0;
+    for (int t2 = 0; t2 < md.n_terms; ++t2)
+      if (md.nfac[t2] == 1 && md.fac[t2][0] == tid) { c += md.coef[t2]; role |= 1; }
+    if (multi >= 0)
+      for (int f2 = 0; f2 < md.nfac[multi]; ++f2)
+        if (md.fac[multi][f2] == tid) role |= 2;
+    s_csingle[tid] = c;
+    s_role[tid] = role;
+  }
+  __syncthreads();
   int term = 0, f = 0;
   while (!leaf_major && term < md.n_terms && md.nfac[term] < 1) {   // (a constant term: no factors)
 #pragma unroll
@@ -172,10 +188,9 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
     bool single = false, in_prod = false;
     if (leaf_major) {
       l = it;
-      for (int t2 = 0; t2 < md.n_terms; ++t2)
-        if (md.nfac[t2] == 1 && md.fac[t2][0] == l) { c_single += md.coef[t2]; single = true; }
-      if (multi >= 0)
-        for (int f2 = 0; f2 < md.nfac[multi]; ++f2) in_prod = in_prod || (md.fac[multi][f2] == l);
+      c_single = s_csingle[l];
+      single = (s_role[l] & 1) != 0;
+      in_prod = (s_role[l] & 2) != 0;
       if (!single && !in_prod) continue;
     } else {
       l = md.fac[term][f];
@@ -194,15 +209,15 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         for (int k0 = 0; k0 < L.dpad; k0 += CC_KC) {
           const int kc = min(CC_KC, L.dpad - k0);
           __syncthreads();
-          for (int idx = tid; idx < CC_TILE * CC_KC; idx += 256) {
-            int r = idx / CC_KC, k = idx % CC_KC;
-            double va = 0.0, vb = 0.0;
-            if (k < kc) {
-              if (row0 + r < n_rows) va = Ag[(size_t)(row0 + r) * L.dpad + k0 + k];
-              if (col0 + r < n_cols) vb = Bg[(size_t)(col0 + r) * L.dpad + k0 + k];
-            }
-            As[r * CC_LDS + k] = va;
-            Bs[r * CC_LDS + k] = vb;
+          // 16-byte pieces of the kc (a multiple of 4) columns the MMA loop reads; nothing beyond kc is touched
+          const int kh = kc >> 1;
+          for (int idx = tid; idx < CC_TILE * kh; idx += 256) {
+            const int r = (kh == CC_KC / 2) ? (idx >> 4) : (idx / kh), k = (idx - r * kh) * 2;
+            double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+            if (row0 + r < n_rows) va = *reinterpret_cast<const double2*>(Ag + (size_t)(row0 + r) * L.dpad + k0 + k);
+            if (col0 + r < n_cols) vb = *reinterpret_cast<const double2*>(Bg + (size_t)(col0 + r) * L.dpad + k0 + k);
+            *reinterpret_cast<double2*>(As + r * CC_LDS + k) = va;
+            *reinterpret_cast<double2*>(Bs + r * CC_LDS + k) = vb;
           }
           __syncthreads();
           for (int kk = 0; kk < kc; kk += 4) {
@@ -243,19 +258,45 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
           Ac[r * BO_MAX_GROUPS + f] = (row0 + r < n_rows) ? rows.codes[l][(size_t)(row0 + r) * L.nd + f] : 0;
           Bc[r * BO_MAX_GROUPS + f] = (col0 + r < n_cols) ? cols.s[l].codes[(size_t)(col0 + r) * L.nd + f] : 0;
         }
+        // A leaf over nd groups takes only 2^nd distinct values (one per mismatch pattern): for nd <= 6 they are tabulated
+        // once per CTA with exactly the per-pair arithmetic (weights added in group order, the matching groups add 0.0), and
+        // a pair costs nd compares and one shared-memory load instead of an FP64 division (slow path whenever all groups
+        // match: 0 / nd) and an exp.
+        double* Ht = reinterpret_cast<double*>(Bc + CC_TILE * BO_MAX_GROUPS);
+        const bool tabulated = L.nd <= 6;
+        if (tabulated && tid < (1 << L.nd)) {
+          double acc = 0.0;
+          for (int f = 0; f < L.nd; ++f) acc += ((tid >> f) & 1) ? L.wls[f] : 0.0;
+          Ht[tid] = exp_nonpos(-(acc / (double)L.nd));
+        }
         __syncthreads();
+        if (tabulated) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
-              double acc = 0.0;
-              for (int f = 0; f < L.nd; ++f)
-                acc += (Ac[rl * BO_MAX_GROUPS + f] != Bc[cl * BO_MAX_GROUPS + f]) ? L.wls[f] : 0.0;
-              lv[(i * 4 + j) * 2 + e] = exp_nonpos(-(acc / (double)L.nd));
-            }
+              for (int e = 0; e < 2; ++e) {
+                int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
+                int mask = 0;
+                for (int f = 0; f < L.nd; ++f)
+                  mask |= (Ac[rl * BO_MAX_GROUPS + f] != Bc[cl * BO_MAX_GROUPS + f]) ? (1 << f) : 0;
+                lv[(i * 4 + j) * 2 + e] = Ht[mask];
+              }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                int rl = wr * 16 + i * 8 + g, cl = wc * 32 + j * 8 + 2 * t + e;
+                double acc = 0.0;
+                for (int f = 0; f < L.nd; ++f)
+                  acc += (Ac[rl * BO_MAX_GROUPS + f] != Bc[cl * BO_MAX_GROUPS + f]) ? L.wls[f] : 0.0;
+                lv[(i * 4 + j) * 2 + e] = exp_nonpos(-(acc / (double)L.nd));
+              }
+        }
       } else {  // Tanimoto
         // <x, x'> over 0 / 1 fingerprints = an exact integer GEMM: u8 x u8 -> s32 tensor-core MMAs (m16n8k32) on the byte
         // copies of the fingerprints instead of AND + POPC over the packed words (POPC issues at 1/8 rate: the POPC loop was

@@ -1,8 +1,10 @@
-"""Timing probe: analytic forward_backward vs batched finite differences on BASELINE config 3 (ZDT1-30D)."""
+"""Timing probe: analytic forward_backward (per-kernel-family breakdown) vs batched finite differences.
+usage: python tools/probe_grad.py [zdt1|dtlz2] [--no-opt]"""
 import sys, time, torch
 sys.path.insert(0, '.')
 from everest_b200 import configs as Cf, optim
-p = Cf.zdt1_qnehvi()
+name = next((a for a in sys.argv[1:] if not a.startswith("-")), "zdt1")
+p = {"zdt1": Cf.zdt1_qnehvi, "dtlz2": Cf.dtlz2_qnehvi}[name]()
 st = Cf.build_state(p); acq = Cf.build_acqf(p, st)
 print("nb", acq.nb, "max_cells", acq.max_cells)
 bnds = torch.as_tensor(p["bounds"])
@@ -25,7 +27,7 @@ for name in ["prep", "crosscov", "posterior_gemm", "cond_root", "sample_gemm", "
     n = st.lib.bo_last_timing(st.handle, name.encode(), C.byref(ms))
     print(f"  {name:16s} {ms.value*1e3:9.1f} us  ({n} launches)")
 st.lib.bo_set_timing(st.handle, 0)
-for mode in ("analytic", "fd"):
+for mode in (() if "--no-opt" in sys.argv else ("analytic", "fd")):
     t0 = time.perf_counter()
     _, Y, info = optim.gen_candidates_scipy(Xic, acq, bnds[0], bnds[1], options={"maxiter": 50, "gradient": mode})
     t1 = time.perf_counter()
