@@ -124,8 +124,9 @@ int launch_finish_var(const ModelD& md, PrepD prep, const double* g, int n, int 
 // cond_root: one warp per (q-batch, output) -- or, for large baselines (launcher: wpb = 4), the four warps of a CTA on one
 // q-batch.  Sqq, Sqb -> bl = Sqb L_b^-T (product with the cached inverse root), br = psd_safe_chol(Sqq - bl bl^T) with the
 // 1e-8..1e-3 jitter ladder, un-standardised mean.  root[(batch*M + m)][q][nb + q] = [bl | br].
-// Every sum is accumulated in the same order whichever way the work is split (lanes own columns e; a pair (i, j) of the
-// Gram update is reduced by one warp), so both layouts give bit-identical roots.
+// The work split does not change the order in which a sum is accumulated (lanes own columns e; a pair (i, j) of the Gram
+// update is reduced by one warp; Cholesky entries are ordered dot products).  Baselines that do not fit shared memory
+// form bl on the FP64 tensor pipe (k-blocks of 4 per DMMA) instead of one FMA chain per entry.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 cond_root_kernel(CondRootArgs a) {
@@ -237,31 +238,42 @@ cond_root_kernel(CondRootArgs a) {
       }
     }
   } else {
-    // large baselines: stream the TRANSPOSED inverse (rows l, lanes over consecutive e -> coalesced);
-    // entries with l > e are exact zeros of the triangular factor.  Blocks of 32 columns are dealt to the team's warps; a
-    // row of the inverse is read ONCE for up to 8 points of the q-batch (the loads do not depend on the FMA chains, so
-    // the unrolled loop keeps several of them in flight).
+    // large baselines: bl = Sqb L_b^-T on the FP64 tensor pipe (DMMA m8n8k4), straight from the TRANSPOSED inverse in
+    // L2: a warp owns blocks of 32 columns e (four n-tiles), A = up to 8 points of the q-batch x 4 rows l from shared
+    // memory, B[k = l][n = e] = LbInvT[l][e].  Entries with l > e are exact zeros of the triangular factor, so a block
+    // stops at its last column.  (The scalar loop this replaces issued 8 LDS + 8 DFMA + 1 LDG per l and was bound by
+    // instruction issue: 0.31 ms per output for 1024 q-batches at n_b = 286.)
+    const int g = lane >> 2, t = lane & 3;
     for (int e0 = wsub * 32; e0 < nb; e0 += 32 * nw) {
-      const int e = e0 + lane;
       const int lmax = min(nb, e0 + 32);
-      const int ec = min(e, nb - 1);               // clamp: lanes past the last column compute a value nobody stores
       for (int j0 = 0; j0 < q; j0 += 8) {
-        double acc[8];
+        double acc[4][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-        const double* lp = a.LbInvT + ec;
-        const double* sq = Sqb + (size_t)j0 * nb;
+        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = 0.0;
+        const bool arow = (j0 + g) < q;
+        const double* sq = Sqb + (size_t)(arow ? j0 + g : 0) * nb;
 #pragma unroll 4
-        for (int l = 0; l < lmax; ++l) {
-          const double lv = lp[(size_t)l * a.ldlb];
+        for (int l = 0; l < lmax; l += 4) {
+          const bool kin = (l + t) < lmax;
+          const double av = (arow && kin) ? sq[l + t] : 0.0;
+          const double* lrow = a.LbInvT + (size_t)(kin ? l + t : 0) * a.ldlb;
+          double bv[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j0 + j < q) acc[j] = fma(sq[j * nb + l], lv, acc[j]);
+          for (int n = 0; n < 4; ++n) {
+            const int e = e0 + n * 8 + g;
+            bv[n] = (kin && e < nb) ? lrow[e] : 0.0;
+          }
+#pragma unroll
+          for (int n = 0; n < 4; ++n) mma_884(acc[n][0], acc[n][1], av, bv[n]);
         }
-        if (e < nb) {
+        if (arow) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j0 + j < q) BLs[(j0 + j) * nb + e] = acc[j];
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int e = e0 + n * 8 + 2 * t + h;
+              if (e < nb) BLs[(size_t)(j0 + g) * nb + e] = acc[n][h];
+            }
         }
       }
     }
@@ -280,41 +292,48 @@ cond_root_kernel(CondRootArgs a) {
     }
   }
   TEAM_SYNC();
-  // psd_safe_cholesky on q x q (one thread), jitter ladder 1e-8 * 10^i, i = 0..5, added incrementally
+  // psd_safe_cholesky on q x q, jitter ladder 1e-8 * 10^i, i = 0..5, added incrementally.  One warp, column by column:
+  // every lane forms the pivot (same value, uniform control flow), the rows below it are spread over the lanes; each
+  // entry is the ordered sum a single thread would form.
   int fail = 0;
   double jitter_total = 0.0;
-  if (tl == 0) {
+  if (wsub == 0) {
     double prev = 0.0;
     for (int attempt = 0; attempt <= 6; ++attempt) {
       if (attempt > 0) {
         const double ladder[6] = {1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0};
         double nw2 = 1e-8 * ladder[attempt - 1];
-        for (int i = 0; i < q; ++i) Sc[i * q + i] += (nw2 - prev);
+        for (int i = lane; i < q; i += 32) Sc[i * q + i] += (nw2 - prev);
         jitter_total += (nw2 - prev);
         prev = nw2;
+        __syncwarp();
       }
       fail = 0;
-      for (int j = 0; j < q && !fail; ++j) {
+      for (int j = 0; j < q; ++j) {
         double d = Sc[j * q + j];
         for (int l = 0; l < j; ++l) d -= Lq[j * q + l] * Lq[j * q + l];
         if (!(d > 0.0)) { fail = 1; break; }
         d = sqrt(d);
-        Lq[j * q + j] = d;
-        for (int i = j + 1; i < q; ++i) {
+        for (int i = j + 1 + lane; i < q; i += 32) {
           double s = Sc[i * q + j];
           for (int l = 0; l < j; ++l) s -= Lq[i * q + l] * Lq[j * q + l];
           Lq[i * q + j] = s / d;
         }
-        for (int i = 0; i < j; ++i) Lq[i * q + j] = 0.0;
+        if (lane == 0) Lq[j * q + j] = d;
+        for (int i = lane; i < j; i += 32) Lq[i * q + j] = 0.0;
+        __syncwarp();
       }
       if (!fail) break;
     }
     if (fail) {
       const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-      for (int p = 0; p < q * q; ++p) Lq[p] = nanv;
+      __syncwarp();
+      for (int p = lane; p < q * q; p += 32) Lq[p] = nanv;
     }
-    if (a.info) a.info[(size_t)batch * a.M + a.m] = fail;
-    if (a.jitter) a.jitter[(size_t)batch * a.M + a.m] = jitter_total;
+    if (lane == 0) {
+      if (a.info) a.info[(size_t)batch * a.M + a.m] = fail;
+      if (a.jitter) a.jitter[(size_t)batch * a.M + a.m] = jitter_total;
+    }
   }
   TEAM_SYNC();
   double* root = a.root + ((size_t)batch * a.M + a.m) * q * nr;

@@ -96,7 +96,7 @@ int launch_hypervolume_from_cells(const double* obj, const unsigned char* front,
 // MC value + d value / d f for every MC sample: dF[m * df_stride + (batch * q + j) * S + s]
 int launch_mc_reduce_partials(const double* partial, int groups, int b, int S, double* out, const int* info_in, int M,
                               int* info_out, cudaStream_t st, LaunchCounter* lc);
-int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+int launch_mc_hvi_grad(const McArgs& a, int max_cells, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 // dF -> d root [b, M, q, nb+q] (= [d bl | d br]) and d mu [b*q, M]

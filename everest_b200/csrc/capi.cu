@@ -1288,7 +1288,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       rec_begin(st, "mc_grad", s);
       if (st->acqf_kind == 3) RC(launch_mc_scalar_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
       else if (st->log_hvi) RC(launch_mc_loghvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
-      else RC(launch_mc_hvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      else RC(launch_mc_hvi_grad(ma, st->max_cells, st->wsDF.as<double>(), dfs, s, &st->lc));
       rec_end(st, s);
       rec_begin(st, "grad_reduce", s);
       RC(launch_grad_reduce(st->wsDF.as<double>(), dfs, st->zbT.as<double>(), st->wsZqT.as<double>(), S, nb, q, M, rows,

@@ -17,24 +17,28 @@
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------------
-// MC value and d value / d f for qNEHVI / qEHVI: one CTA per q-batch, threads over MC samples
+// MC value and d value / d f for qNEHVI / qEHVI: one CTA per (q-batch, slice of the MC samples).  A CTA holds `nst` samples
+// at a time (lanes = consecutive samples: coalesced cell reads) and `CL` "cell lanes" per sample: thread (sl, cl) walks the
+// cells c = cl, cl + CL, ... of its sample and accumulates its own d value / d objective block; the blocks of a sample are
+// added in cell-lane order afterwards (fixed order: deterministic).  Refinement calls have 8 q-batches x 512 samples; with
+// thousands of cells per sample (4 objectives) the cells are the only parallelism left.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
+mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) {
   extern __shared__ double gsm[];
   const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int nst = nt / CL, sl = tid % nst, cl = tid / nst;
   const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
   double* root = gsm;                          // [M][q][nr]
   double* mu = root + (size_t)M * q * nr;      // [q][M]
-  double* objs = mu + q * M;                   // [q*Mo][nt]
-  double* fw = objs + (size_t)q * Mo * nt;     // [q][nt]
-  double* gob = fw + (size_t)q * nt;           // [q*Mo][nt]  d value / d objective
-  double* gfw = gob + (size_t)q * Mo * nt;     // [q][nt]     d value / d feasibility weight
-  double* ys = gfw + (size_t)q * nt;           // [q*M][nt]   model-output samples
-  double* red = ys + (size_t)q * M * nt;       // [32]
+  double* objs = mu + q * M;                   // [q*Mo][nst]
+  double* fw = objs + (size_t)q * Mo * nst;    // [q][nst]
+  double* ys = fw + (size_t)q * nst;           // [q*M][nst]   model-output samples
+  double* gob = ys + (size_t)q * M * nst;      // [q*Mo][nt]  d value / d objective (per thread)
+  double* gfw = gob + (size_t)q * Mo * nt;     // [q][nt]     d value / d feasibility weight (per thread)
+  double* red = gfw + (size_t)q * nt;          // [32]
   for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
   for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
-  __syncthreads();
   const double invS = 1.0 / (double)S;
   const bool has_cons = a.od.n_cons > 0;
 
@@ -42,132 +46,142 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
   // the MC samples are split over gridDim.y CTAs (few q-batches: more CTAs than q-batches); partial sums per split
   const int per_split = (S + gridDim.y - 1) / gridDim.y;
   const int s_begin = blockIdx.y * per_split, s_end = min(S, s_begin + per_split);
-  for (int s = s_begin + tid; s < s_end; s += nt) {
-    for (int j = 0; j < q; ++j) {
-      double y[2 * BO_MAX_OBJECTIVES];
-      for (int m = 0; m < M; ++m) {
-        const double* rr = root + ((size_t)m * q + j) * nr;
-        double sb = 0.0, sq = 0.0;
-        if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
-        else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
-        for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
-        y[m] = (mu[j * M + m] + sb) + sq;
-        ys[((size_t)j * M + m) * nt + tid] = y[m];
+  for (int s0 = s_begin; s0 < s_end; s0 += nst) {
+    const int s = s0 + sl;
+    const bool valid = s < s_end;
+    __syncthreads();   // staging done / the previous pass has been read
+    if (valid)
+      for (int j = cl; j < q; j += CL) {
+        double y[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) {
+          const double* rr = root + ((size_t)m * q + j) * nr;
+          double sb = 0.0, sq = 0.0;
+          if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
+          else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+          for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+          y[m] = (mu[j * M + m] + sb) + sq;
+          ys[((size_t)j * M + m) * nst + sl] = y[m];
+        }
+        for (int o = 0; o < Mo; ++o) objs[((size_t)j * Mo + o) * nst + sl] = objective_apply(a.od.op[o], y);
+        double w = 1.0;
+        for (int c = 0; c < a.od.n_cons; ++c) {
+          double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+          w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+        }
+        fw[(size_t)j * nst + sl] = w;
       }
-      for (int o = 0; o < Mo; ++o) {
-        objs[((size_t)j * Mo + o) * nt + tid] = objective_apply(a.od.op[o], y);
-        gob[((size_t)j * Mo + o) * nt + tid] = 0.0;
-      }
-      double w = 1.0;
-      for (int c = 0; c < a.od.n_cons; ++c) {
-        double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
-        w *= 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
-      }
-      fw[(size_t)j * nt + tid] = w;
-      gfw[(size_t)j * nt + tid] = 0.0;
-    }
-    const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
-    const int sc = a.cells_shared ? 0 : s;
-    const int Sc = a.cells_shared ? 1 : S;
-    double acc = 0.0;
-    for (int c = 0; c < nc; ++c) {
-      double lo[BO_MAX_OBJECTIVES], up[BO_MAX_OBJECTIVES];
-      for (int o = 0; o < Mo; ++o) {
-        lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
-        up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
-      }
-      unsigned active = 0;
-      for (int j = 0; j < q; ++j) {
-        bool pos = true;
+    for (int i = 0; i < q * Mo; ++i) gob[(size_t)i * nt + tid] = 0.0;
+    for (int j = 0; j < q; ++j) gfw[(size_t)j * nt + tid] = 0.0;
+    __syncthreads();
+    if (valid) {
+      const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+      const int sc = a.cells_shared ? 0 : s;
+      const int Sc = a.cells_shared ? 1 : S;
+      double acc = 0.0;
+      for (int c = cl; c < nc; c += CL) {
+        double lo[BO_MAX_OBJECTIVES], up[BO_MAX_OBJECTIVES];
         for (int o = 0; o < Mo; ++o) {
-          double len = fmin(objs[((size_t)j * Mo + o) * nt + tid], up[o]) - lo[o];
-          pos = pos && (len > 0.0);
+          lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+          up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
         }
-        if (pos) active |= (1u << j);
-      }
-      if (!active) continue;
-      double cell = 0.0;
-      for (int size = 1; size <= q; ++size) {
-        double asum = 0.0;
-        bool any = false;
-        const double sgn = (size & 1) ? 1.0 : -1.0;
-        for (unsigned sub = active; sub; sub = (sub - 1) & active) {
-          if (__popc(sub) != size) continue;
-          any = true;
-          double vol = 1.0, wprod = 1.0;
-          double len[BO_MAX_OBJECTIVES];
-          int arg[BO_MAX_OBJECTIVES];
+        unsigned active = 0;
+        for (int j = 0; j < q; ++j) {
+          bool pos = true;
           for (int o = 0; o < Mo; ++o) {
-            double mn = up[o];
-            int aj = -1;
-            for (unsigned rest = sub; rest; rest &= rest - 1) {
-              int j = __ffs(rest) - 1;
-              double v = objs[((size_t)j * Mo + o) * nt + tid];
-              if (v < mn) { mn = v; aj = j; }
-            }
-            len[o] = fmax(mn - lo[o], 0.0);  // > 0: every point of an active subset overlaps the cell
-            arg[o] = aj;
-            vol *= len[o];
+            double len = fmin(objs[((size_t)j * Mo + o) * nst + sl], up[o]) - lo[o];
+            pos = pos && (len > 0.0);
           }
-          if (has_cons)
-            for (unsigned rest = sub; rest; rest &= rest - 1) wprod *= fw[(size_t)(__ffs(rest) - 1) * nt + tid];
-          // adjoint: the side length along o moves with the subset's minimum iff that minimum is below the cell's upper bound
-          for (int o = 0; o < Mo; ++o)
-            if (arg[o] >= 0) {
-              double other = 1.0;
-              for (int o2 = 0; o2 < Mo; ++o2)
-                if (o2 != o) other *= len[o2];
-              gob[((size_t)arg[o] * Mo + o) * nt + tid] += sgn * wprod * other;
-            }
-          if (has_cons) {
-            for (unsigned rest = sub; rest; rest &= rest - 1) {
-              const int j = __ffs(rest) - 1;
-              double others = 1.0;
-              for (unsigned r2 = sub; r2; r2 &= r2 - 1) {
-                const int j2 = __ffs(r2) - 1;
-                if (j2 != j) others *= fw[(size_t)j2 * nt + tid];
+          if (pos) active |= (1u << j);
+        }
+        if (!active) continue;
+        double cell = 0.0;
+        for (int size = 1; size <= q; ++size) {
+          double asum = 0.0;
+          bool any = false;
+          const double sgn = (size & 1) ? 1.0 : -1.0;
+          for (unsigned sub = active; sub; sub = (sub - 1) & active) {
+            if (__popc(sub) != size) continue;
+            any = true;
+            double vol = 1.0, wprod = 1.0;
+            double len[BO_MAX_OBJECTIVES];
+            int arg[BO_MAX_OBJECTIVES];
+            for (int o = 0; o < Mo; ++o) {
+              double mn = up[o];
+              int aj = -1;
+              for (unsigned rest = sub; rest; rest &= rest - 1) {
+                int j = __ffs(rest) - 1;
+                double v = objs[((size_t)j * Mo + o) * nst + sl];
+                if (v < mn) { mn = v; aj = j; }
               }
-              gfw[(size_t)j * nt + tid] += sgn * vol * others;
+              len[o] = fmax(mn - lo[o], 0.0);  // > 0: every point of an active subset overlaps the cell
+              arg[o] = aj;
+              vol *= len[o];
             }
-            vol *= wprod;
+            if (has_cons)
+              for (unsigned rest = sub; rest; rest &= rest - 1) wprod *= fw[(size_t)(__ffs(rest) - 1) * nst + sl];
+            // adjoint: the side length along o moves with the subset's minimum iff that minimum is below the cell's upper bound
+            for (int o = 0; o < Mo; ++o)
+              if (arg[o] >= 0) {
+                double other = 1.0;
+                for (int o2 = 0; o2 < Mo; ++o2)
+                  if (o2 != o) other *= len[o2];
+                gob[((size_t)arg[o] * Mo + o) * nt + tid] += sgn * wprod * other;
+              }
+            if (has_cons) {
+              for (unsigned rest = sub; rest; rest &= rest - 1) {
+                const int j = __ffs(rest) - 1;
+                double others = 1.0;
+                for (unsigned r2 = sub; r2; r2 &= r2 - 1) {
+                  const int j2 = __ffs(r2) - 1;
+                  if (j2 != j) others *= fw[(size_t)j2 * nst + sl];
+                }
+                gfw[(size_t)j * nt + tid] += sgn * vol * others;
+              }
+              vol *= wprod;
+            }
+            asum += vol;
           }
-          asum += vol;
+          if (any) cell += (size & 1) ? asum : -asum;
         }
-        if (any) cell += (size & 1) ? asum : -asum;
+        acc += cell;
       }
-      acc += cell;
+      total += acc;
     }
-    total += acc;
-    // objectives / feasibility -> model outputs
-    for (int j = 0; j < q; ++j) {
-      double y[2 * BO_MAX_OBJECTIVES];
-      for (int m = 0; m < M; ++m) y[m] = ys[((size_t)j * M + m) * nt + tid];
-      double dy[2 * BO_MAX_OBJECTIVES];
-      for (int m = 0; m < M; ++m) dy[m] = 0.0;
-      for (int o = 0; o < Mo; ++o) {
-        const double gv = gob[((size_t)j * Mo + o) * nt + tid];
-        if (gv != 0.0) dy[a.od.op[o].out_idx] += gv * objective_grad(a.od.op[o], y);
-      }
-      if (has_cons) {
-        const double gw = gfw[(size_t)j * nt + tid];
-        if (gw != 0.0) {
-          double sg[BO_MAX_CONSTRAINTS];
-          for (int c = 0; c < a.od.n_cons; ++c) {
-            double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
-            sg[c] = 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
-          }
-          for (int c = 0; c < a.od.n_cons; ++c) {
-            double rest = 1.0;
-            for (int c2 = 0; c2 < a.od.n_cons; ++c2)
-              if (c2 != c) rest *= sg[c2];
-            // d sigmoid(-cv / eta) / dy = -sign / eta * sg (1 - sg)
-            dy[a.od.con[c].out_idx] += gw * rest * sg[c] * (1.0 - sg[c]) * (-a.od.con[c].sign / a.od.con[c].eta);
+    __syncthreads();
+    // objectives / feasibility -> model outputs (point j = cl, cl + CL, ...; the cell lanes' blocks added in lane order)
+    if (valid)
+      for (int j = cl; j < q; j += CL) {
+        double y[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) y[m] = ys[((size_t)j * M + m) * nst + sl];
+        double dy[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) dy[m] = 0.0;
+        for (int o = 0; o < Mo; ++o) {
+          double gv = gob[((size_t)j * Mo + o) * nt + sl];
+          for (int c2 = 1; c2 < CL; ++c2) gv += gob[((size_t)j * Mo + o) * nt + c2 * nst + sl];
+          if (gv != 0.0) dy[a.od.op[o].out_idx] += gv * objective_grad(a.od.op[o], y);
+        }
+        if (has_cons) {
+          double gw = gfw[(size_t)j * nt + sl];
+          for (int c2 = 1; c2 < CL; ++c2) gw += gfw[(size_t)j * nt + c2 * nst + sl];
+          if (gw != 0.0) {
+            double sg[BO_MAX_CONSTRAINTS];
+            for (int c = 0; c < a.od.n_cons; ++c) {
+              double cv = a.od.con[c].sign * (y[a.od.con[c].out_idx] - a.od.con[c].tp);
+              sg[c] = 1.0 / (1.0 + exp(cv / a.od.con[c].eta));
+            }
+            for (int c = 0; c < a.od.n_cons; ++c) {
+              double rest = 1.0;
+              for (int c2 = 0; c2 < a.od.n_cons; ++c2)
+                if (c2 != c) rest *= sg[c2];
+              // d sigmoid(-cv / eta) / dy = -sign / eta * sg (1 - sg)
+              dy[a.od.con[c].out_idx] += gw * rest * sg[c] * (1.0 - sg[c]) * (-a.od.con[c].sign / a.od.con[c].eta);
+            }
           }
         }
+        for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m] * invS;
       }
-      for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m] * invS;
-    }
   }
+  __syncthreads();
   double t = block_sum(total, red);
   if (tid == 0) a.partial[(size_t)blockIdx.y * a.b + batch] = t;   // summed in a fixed order by mc_reduce_partials_kernel
 }
@@ -180,24 +194,29 @@ static int pick_threads(size_t fixed_doubles, size_t per_thread_doubles, size_t*
   return 0;
 }
 
-int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
+int launch_mc_hvi_grad(const McArgs& a, int max_cells, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   const int Mo = a.od.n_obj;
-  size_t smem = 0;
-  const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M;
-  const size_t per = (size_t)2 * a.q * Mo + 2 * a.q + (size_t)a.q * a.M;
-  const int nt_max = pick_threads(fixed, per, &smem);
-  if (!nt_max) { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
   if (!a.partial) { bo_set_error("mc_hvi_grad: partial-sum workspace missing"); return BO_ERR_STATE; }
   // about two waves of CTAs: split the MC samples when there are few q-batches (partial has room for ceil(S / 32) splits)
   int nsplit = (296 + a.b - 1) / a.b;
   nsplit = std::max(1, std::min(nsplit, (a.S + 31) / 32));
-  int nt = nt_max;
-  {
-    const int per_split = (a.S + nsplit - 1) / nsplit;
-    const int want = ((per_split + 31) / 32) * 32;
-    if (want < nt) nt = want;
-    smem = (fixed + per * nt + 32) * sizeof(double);
+  const int per_split = (a.S + nsplit - 1) / nsplit;
+  // shared memory: roots + means, per-sample values (objectives, feasibility weights, model outputs), per-thread adjoints
+  const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M + 32;
+  const size_t per_sample = (size_t)a.q * Mo + a.q + (size_t)a.q * a.M;
+  const size_t per_thread = (size_t)a.q * Mo + a.q;
+  int nst = std::min(256, ((per_split + 31) / 32) * 32);
+  // cell lanes per sample: worth it when a sample has many cells and the samples alone do not fill the CTA
+  int CL = (max_cells >= 64) ? 8 : (max_cells >= 8) ? 4 : 1;
+  CL = std::max(1, std::min(CL, 256 / nst));
+  size_t smem = 0;
+  for (;;) {
+    smem = (fixed + per_sample * nst + per_thread * (size_t)nst * CL) * sizeof(double);
+    if (smem <= 200 * 1024) break;
+    if (CL > 1) CL >>= 1;
+    else if (nst > 32) nst >>= 1;
+    else { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
   }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
@@ -205,7 +224,7 @@ int launch_mc_hvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream
     attr = smem;
   }
   dim3 grid(a.b, nsplit);
-  mc_hvi_grad_kernel<<<grid, nt, smem, st>>>(a, dF, df_stride);
+  mc_hvi_grad_kernel<<<grid, nst * CL, smem, st>>>(a, dF, df_stride, CL);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return launch_mc_reduce_partials(a.partial, nsplit, a.b, a.S, a.out, a.info_in, a.M, a.info_out, st, lc);
@@ -260,13 +279,20 @@ int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, co
 // Cholesky adjoint: Cbar = sym( L^-T Phi(L^T Lbar) L^-1 ), Phi = lower triangle with halved diagonal.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta) {
+cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta, int wide) {
+  // Two layouts (uniform over the grid): one warp per q-batch, `warps_per_cta` q-batches per CTA -- or, `wide`, the four
+  // warps of a CTA on one q-batch with the 32-column blocks of d Sqb dealt over the warps AND over gridDim.y CTAs (every
+  // CTA of a q-batch repeats the small q x q adjoint).  Refinement calls have 8 q-batches: one warp each left the 286 x 286
+  // inverse root of a 4-objective problem to 8 warps of the whole GPU.
   extern __shared__ double bsm[];
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int batch = blockIdx.x * warps_per_cta + wic;
-  if (wic >= warps_per_cta || batch >= a.b) return;
+  const int batch = wide ? blockIdx.x : blockIdx.x * warps_per_cta + wic;
+  if (!wide && (wic >= warps_per_cta || batch >= a.b)) return;
+  const int tl = wide ? (int)threadIdx.x : lane, tn = wide ? 128 : 32;
+  const int wsub = wide ? wic : 0, nw = wide ? 4 : 1;
+#define TEAM_SYNC() do { if (wide) __syncthreads(); else __syncwarp(); } while (0)
   const int q = a.q, nb = a.nb, nr = nb + q;
-  double* T = bsm + (size_t)wic * ((size_t)q * nb + 5 * q * q);  // [q][nb] total adjoint of bl
+  double* T = bsm + (wide ? 0 : (size_t)wic * ((size_t)q * nb + 5 * q * q));  // [q][nb] total adjoint of bl
   double* Lq = T + (size_t)q * nb;                               // [q][q]
   double* Lbar = Lq + q * q;
   double* Pm = Lbar + q * q;
@@ -276,81 +302,117 @@ cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta) {
   const double* droot = a.droot + ((size_t)batch * a.M + a.m) * q * nr;
   const double s2 = a.y_std * a.y_std;
   const int row0 = batch * q;
-  for (int p = lane; p < q * q; p += 32) {
-    int i = p / q, j = p % q;
-    Lq[p] = (j <= i) ? root[i * nr + nb + j] : 0.0;
-    Lbar[p] = (j <= i) ? droot[i * nr + nb + j] : 0.0;
-  }
-  __syncwarp();
-  if (lane == 0) {
+  if (wsub == 0) {
+    // the q x q Cholesky adjoint on one warp, one matrix entry (or one column of L^-1) per lane; every entry is the same
+    // ordered dot product a single thread would form
+    for (int p = lane; p < q * q; p += 32) {
+      int i = p / q, j = p % q;
+      Lq[p] = (j <= i) ? root[i * nr + nb + j] : 0.0;
+      Lbar[p] = (j <= i) ? droot[i * nr + nb + j] : 0.0;
+    }
+    __syncwarp();
     // P = Phi(L^T Lbar)
-    for (int i = 0; i < q; ++i)
-      for (int j = 0; j <= i; ++j) {
-        double s = 0.0;
+    for (int p = lane; p < q * q; p += 32) {
+      const int i = p / q, j = p % q;
+      double s = 0.0;
+      if (j <= i)
         for (int k = i; k < q; ++k) s = fma(Lq[k * q + i], Lbar[k * q + j], s);
-        Pm[i * q + j] = (i == j) ? 0.5 * s : s;
-      }
-    for (int i = 0; i < q; ++i)
-      for (int j = i + 1; j < q; ++j) Pm[i * q + j] = 0.0;
-    // Li = L^-1 (lower)
-    for (int c = 0; c < q; ++c) {
+      Pm[p] = (j > i) ? 0.0 : (i == j) ? 0.5 * s : s;
+    }
+    // Li = L^-1 (lower): forward substitution down column c
+    for (int c = lane; c < q; c += 32)
       for (int i = 0; i < q; ++i) {
         if (i < c) { Li[i * q + c] = 0.0; continue; }
         double s = (i == c) ? 1.0 : 0.0;
         for (int k = c; k < i; ++k) s -= Lq[i * q + k] * Li[k * q + c];
         Li[i * q + c] = s / Lq[i * q + i];
       }
-    }
+    __syncwarp();
     // Cb = Li^T P Li, then symmetrise.  tmp = P Li (lower x lower = lower) into Lbar (no longer needed)
-    for (int i = 0; i < q; ++i)
-      for (int j = 0; j < q; ++j) {
-        double s = 0.0;
-        for (int k = j; k <= i; ++k) s = fma(Pm[i * q + k], Li[k * q + j], s);
-        Lbar[i * q + j] = s;
-      }
-    for (int i = 0; i < q; ++i)
-      for (int j = 0; j < q; ++j) {
-        double s = 0.0;
-        for (int k = i; k < q; ++k) s = fma(Li[k * q + i], Lbar[k * q + j], s);
-        Cb[i * q + j] = s;
-      }
-    for (int i = 0; i < q; ++i)
-      for (int j = 0; j < i; ++j) {
+    for (int p = lane; p < q * q; p += 32) {
+      const int i = p / q, j = p % q;
+      double s = 0.0;
+      for (int k = j; k <= i; ++k) s = fma(Pm[i * q + k], Li[k * q + j], s);
+      Lbar[p] = s;
+    }
+    __syncwarp();
+    for (int p = lane; p < q * q; p += 32) {
+      const int i = p / q, j = p % q;
+      double s = 0.0;
+      for (int k = i; k < q; ++k) s = fma(Li[k * q + i], Lbar[k * q + j], s);
+      Cb[p] = s;
+    }
+    __syncwarp();
+    for (int p = lane; p < q * q; p += 32) {
+      const int i = p / q, j = p % q;
+      if (j < i) {
         double v = 0.5 * (Cb[i * q + j] + Cb[j * q + i]);
         Cb[i * q + j] = v;
         Cb[j * q + i] = v;
       }
+    }
   }
-  __syncwarp();
+  TEAM_SYNC();
   // T = d bl - 2 Cbar bl
-  for (int e = lane; e < nb; e += 32)
+  for (int e = tl; e < nb; e += tn)
     for (int j = 0; j < q; ++j) {
       double s = droot[j * nr + e];
       for (int i = 0; i < q; ++i) s = fma(-2.0 * Cb[j * q + i], root[i * nr + e], s);
       T[(size_t)j * nb + e] = s;
     }
-  __syncwarp();
-  // d Sqb[j][l] = sum_{e >= l} T[j][e] LbInv[e][l];  EW = d value / d W = -s^2 d Sqb   (lanes over l: coalesced rows of LbInv)
-  for (int l0 = 0; l0 < nb; l0 += 32) {
-    const int l = l0 + lane;
-    for (int j = 0; j < q; ++j) {
-      double s = 0.0;
-      if (l < nb)
-        for (int e = l0; e < nb; ++e) {
-          const double v = (e >= l) ? a.LbInv[(size_t)e * a.ldlb + l] : 0.0;
-          s = fma(T[(size_t)j * nb + e], v, s);
+  TEAM_SYNC();
+  // d Sqb[j][l] = sum_{e >= l} T[j][e] LbInv[e][l];  EW = d value / d W = -s^2 d Sqb.  Blocks of 32 columns l on the FP64
+  // tensor pipe (DMMA m8n8k4): A = up to 8 points of the q-batch x 4 rows e of T (shared memory), B[k = e][n = l] =
+  // LbInv[e][l] read straight from L2; the rows above a block's first column contribute nothing and are skipped.
+  {
+    const int g = lane >> 2, t = lane & 3;
+    for (int l0 = (blockIdx.y * nw + wsub) * 32; l0 < nb; l0 += 32 * nw * gridDim.y) {
+      for (int j0 = 0; j0 < q; j0 += 8) {
+        double acc[4][2];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = 0.0;
+        const bool arow = (j0 + g) < q;
+        const double* tq = T + (size_t)(arow ? j0 + g : 0) * nb;
+#pragma unroll 4
+        for (int e0 = l0; e0 < nb; e0 += 4) {
+          const int e = e0 + t;
+          const bool kin = e < nb;
+          const double av = (arow && kin) ? tq[e] : 0.0;
+          const double* lrow = a.LbInv + (size_t)(kin ? e : 0) * a.ldlb;
+          double bv[4];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const int l = l0 + n * 8 + g;
+            bv[n] = (kin && l < nb && e >= l) ? lrow[l] : 0.0;
+          }
+#pragma unroll
+          for (int n = 0; n < 4; ++n) mma_884(acc[n][0], acc[n][1], av, bv[n]);
         }
-      if (l < nb) a.EW[(size_t)(row0 + j) * a.ldw + l] = -s2 * s;
+        if (arow) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int l = l0 + n * 8 + 2 * t + h;
+              if (l < nb) a.EW[(size_t)(row0 + j0 + g) * a.ldw + l] = -s2 * acc[n][h];
+            }
+        }
+      }
     }
   }
-  for (int p = lane; p < q * q; p += 32) a.EG[(size_t)batch * q * q + p] = -2.0 * s2 * Cb[p];
-  for (int j = lane; j < q; j += 32) a.Emu[row0 + j] = a.y_std * a.dmu[(size_t)(row0 + j) * a.M + a.m];
+  if (blockIdx.y == 0) {
+    for (int p = tl; p < q * q; p += tn) a.EG[(size_t)batch * q * q + p] = -2.0 * s2 * Cb[p];
+    for (int j = tl; j < q; j += tn) a.Emu[row0 + j] = a.y_std * a.dmu[(size_t)(row0 + j) * a.M + a.m];
+  }
+#undef TEAM_SYNC
 }
 
 int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   size_t per_warp = ((size_t)a.q * a.nb + 5 * a.q * a.q) * sizeof(double);
-  int wpc = (4 * per_warp <= 96 * 1024) ? 4 : 1;
+  // few q-batches (refinement) or a large baseline: the whole CTA on one q-batch, column blocks split over up to 4 CTAs
+  const int wide = (a.nb > 64 || a.b <= 148) ? 1 : 0;
+  int wpc = wide ? 1 : ((4 * per_warp <= 96 * 1024) ? 4 : 1);
   size_t smem = wpc * per_warp;
   if (smem > 200 * 1024) { bo_set_error("cond_root_bwd: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
@@ -358,7 +420,13 @@ int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounte
     CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  cond_root_bwd_kernel<<<(a.b + wpc - 1) / wpc, 128, smem, st>>>(a, wpc);
+  int ysplit = 1;
+  if (wide) {
+    const int blocks = (a.nb + 31) / 32;
+    ysplit = std::max(1, std::min((blocks + 3) / 4, std::max(1, 296 / a.b)));
+  }
+  dim3 grid(wide ? a.b : (a.b + wpc - 1) / wpc, ysplit);
+  cond_root_bwd_kernel<<<grid, 128, smem, st>>>(a, wpc, wide);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -121,10 +121,12 @@ int launch_unpack_rows(const double* dense, const u64* bits, int nd, int W, cons
 #define CC_LDS 36  // CC_KC + 4 -> (stride mod 16) == 4: conflict-free 64-bit fragment loads
 
 struct ColSides { LeafSide s[BO_MAX_LEAVES]; };
+#define CC2_DSM (2 * 2 * CC_TILE * 272)   // crosscov_kernel2: two buffers of (A | B) x 64 rows x 272 bytes
 
 __global__ void __launch_bounds__(256, 2)
 crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __restrict__ out, int ld, int same_set) {
   __shared__ __align__(16) double smem[2 * CC_TILE * CC_LDS];
+  extern __shared__ __align__(16) unsigned char dsm[];   // Tanimoto chunk ring (launcher: CC2_DSM bytes when the tree has such a leaf)
   double* As = smem;
   double* Bs = smem + CC_TILE * CC_LDS;
 
@@ -302,9 +304,10 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         // copies of the fingerprints instead of AND + POPC over the packed words (POPC issues at 1/8 rate: the POPC loop was
         // 41 % of this kernel's instructions and held it at 0.22 of even the POPC-pipe bound).  Chunks of 256 columns per
         // row; row stride 272 bytes keeps the ldmatrix rows (16 bytes each) on distinct banks.
+        // The chunks arrive by cp.async into two buffers: chunk k + 1 is in flight while the MMAs of chunk k run, one
+        // barrier per chunk (the copy into a buffer is issued after the barrier that ends its previous use).
         const int TB_CH = 256, TB_LD = 272;
-        unsigned char* Ab = reinterpret_cast<unsigned char*>(smem);
-        unsigned char* Bb = Ab + CC_TILE * TB_LD;
+        unsigned char* Tb = reinterpret_cast<unsigned char*>(dsm);           // [2 buffers][A | B][64 rows][TB_LD]
         const int rb = tanimoto_row_bytes(L.dpad);
         const unsigned char* Ag = tanimoto_bytes(rows.bits[l], n_rows, L.dpad);
         const unsigned char* Bg = tanimoto_bytes(cols.s[l].bits, n_cols, L.dpad);
@@ -315,18 +318,29 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         const int lm = lane >> 3, lr = lane & 7;
         const unsigned a_off = (unsigned)((wr * 16 + (lm & 1) * 8 + lr) * TB_LD + (lm >> 1) * 16);   // (rows 0-7 | 8-15) x (k 0-15 | 16-31)
         const unsigned b_off = (unsigned)((wc * 32 + (lm >> 1) * 8 + lr) * TB_LD + (lm & 1) * 16);  // (n 0-7: k lo, k hi | n 8-15: k lo, k hi)
-        const unsigned As_u = (unsigned)__cvta_generic_to_shared(Ab), Bs_u = (unsigned)__cvta_generic_to_shared(Bb);
-        for (int k0 = 0; k0 < rb; k0 += TB_CH) {
-          __syncthreads();
-          for (int idx = tid; idx < CC_TILE * (TB_CH / 16); idx += 256) {
-            const int r = idx / (TB_CH / 16), c = idx % (TB_CH / 16);
-            int4 va = make_int4(0, 0, 0, 0), vb = make_int4(0, 0, 0, 0);
-            if (row0 + r < n_rows) va = *reinterpret_cast<const int4*>(Ag + (size_t)(row0 + r) * rb + k0 + c * 16);
-            if (col0 + r < n_cols) vb = *reinterpret_cast<const int4*>(Bg + (size_t)(col0 + r) * rb + k0 + c * 16);
-            *reinterpret_cast<int4*>(Ab + r * TB_LD + c * 16) = va;
-            *reinterpret_cast<int4*>(Bb + r * TB_LD + c * 16) = vb;
+        const unsigned Tb_u = (unsigned)__cvta_generic_to_shared(Tb);
+        const unsigned buf_bytes = 2 * CC_TILE * TB_LD;
+        // this thread's 16-byte pieces of a chunk: piece idx = tid + 256 * i -> row idx / 16, piece idx % 16 (4 per matrix)
+        auto issue_chunk = [&](int k0, int buf) {
+          unsigned char* Ab = Tb + (size_t)buf * buf_bytes;
+          unsigned char* Bb = Ab + CC_TILE * TB_LD;
+#pragma unroll
+          for (int i = 0; i < CC_TILE * (TB_CH / 16) / 256; ++i) {
+            const int idx = tid + 256 * i, r = idx >> 4, c = idx & 15;
+            const bool pa = row0 + r < n_rows, pb = col0 + r < n_cols;
+            cp_async16(Ab + r * TB_LD + c * 16, Ag + (size_t)(pa ? row0 + r : 0) * rb + k0 + c * 16, pa);
+            cp_async16(Bb + r * TB_LD + c * 16, Bg + (size_t)(pb ? col0 + r : 0) * rb + k0 + c * 16, pb);
           }
-          __syncthreads();
+          cp_async_commit();
+        };
+        __syncthreads();               // the previous leaf is done with the static tiles; dsm is only used here
+        issue_chunk(0, 0);
+        int buf = 0;
+        for (int k0 = 0; k0 < rb; k0 += TB_CH, buf ^= 1) {
+          cp_async_wait<0>();
+          __syncthreads();             // chunk k0 visible to all; everyone has finished the MMAs of the chunk before it
+          if (k0 + TB_CH < rb) issue_chunk(k0 + TB_CH, buf ^ 1);
+          const unsigned As_u = Tb_u + buf * buf_bytes, Bs_u = As_u + CC_TILE * TB_LD;
 #pragma unroll
           for (int ks = 0; ks < TB_CH; ks += 32) {
             unsigned a0, a1, a2, a3;
@@ -629,7 +643,17 @@ int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool col
     return BO_OK;
   }
   dim3 grid((ld + CC_TILE - 1) / CC_TILE, (rows.n + CC_TILE - 1) / CC_TILE);
-  crosscov_kernel2<<<grid, 256, 0, s>>>(md, rows, cs, n_cols, out, ld, same_set ? 1 : 0);
+  size_t dsm = 0;
+  for (int l = 0; l < md.n_leaves; ++l)
+    if (md.leaf[l].kind == BO_LEAF_TANIMOTO) dsm = CC2_DSM;   // Tanimoto leaf: two chunk buffers
+  if (dsm) {
+    static PerDeviceOnce attr2_once; bool& attr2_set = *attr2_once.slot();
+    if (!attr2_set) {
+      CUDA_CHECK_RET(cudaFuncSetAttribute(crosscov_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC2_DSM));
+      attr2_set = true;
+    }
+  }
+  crosscov_kernel2<<<grid, 256, dsm, s>>>(md, rows, cs, n_cols, out, ld, same_set ? 1 : 0);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;
