@@ -70,6 +70,36 @@ __device__ __forceinline__ double subset_axis(unsigned sub, const double* __rest
   return w - lo;
 }
 
+// The two halves of subset_axis for the value-only kernel: the fatmin over the members does not depend on the cell, so the
+// forward kernel forms it ONCE per (MC sample, subset, objective) and re-uses it for every cell (same arithmetic, same bits).
+__device__ __forceinline__ double subset_fatmin(unsigned sub, const double* __restrict__ objs_o, int nt, double tau_max) {
+  double mn = INFINITY;
+  for (unsigned rest = sub; rest; rest &= rest - 1) {
+    const double x = objs_o[(size_t)(__ffs(rest) - 1) * nt];
+    if (x < mn) mn = x;
+  }
+  if ((sub & (sub - 1)) == 0) return mn;
+  double ps = 0.0;
+  for (unsigned rest = sub; rest; rest &= rest - 1) {
+    const double y = (objs_o[(size_t)(__ffs(rest) - 1) * nt] - mn) / tau_max;
+    ps += pareto2_d(y);
+  }
+  return mn - tau_max * log(ps);
+}
+__device__ __forceinline__ double axis_from_fatmin(double v, double lo, double up, double tau_max) {
+  double w;
+  if (isinf(up)) {
+    w = v;
+  } else if (v <= up) {
+    const double y = (up - v) / tau_max, P = pareto2_d(y);
+    w = v - tau_max * log(1.0 + P);
+  } else {
+    const double y = (v - up) / tau_max, P = pareto2_d(y);
+    w = up - tau_max * log(1.0 + P);
+  }
+  return w - lo;
+}
+
 // running log-sum-exp as a (max, sum) pair: value = m + log s
 __device__ __forceinline__ void lse_push(double& m, double& s, double v) {
   if (v > m) { s = s * exp(m - v) + 1.0; m = v; }   // exp(-inf) = 0 on the first push
@@ -77,9 +107,9 @@ __device__ __forceinline__ void lse_push(double& m, double& s, double v) {
 }
 __device__ __forceinline__ double lse_value(double m, double s) { return (s > 0.0) ? m + log(s) : -INFINITY; }
 
-struct LhSmem { double *root, *mu, *objs, *lfw, *gob, *glf, *ys, *vals, *red; };
+struct LhSmem { double *root, *mu, *objs, *lfw, *gob, *glf, *ys, *vc, *vals, *red; };
 
-__device__ __forceinline__ LhSmem lh_smem(double* base, int M, int q, int nr, int Mo, int nt, int S, bool grad) {
+__device__ __forceinline__ LhSmem lh_smem(double* base, int M, int q, int nr, int Mo, int nt, int S, bool grad, int vcn = 0) {
   LhSmem sm;
   sm.root = base;
   sm.mu = sm.root + (size_t)M * q * nr;
@@ -93,6 +123,8 @@ __device__ __forceinline__ LhSmem lh_smem(double* base, int M, int q, int nr, in
   } else {
     sm.gob = sm.glf = sm.ys = nullptr;
   }
+  sm.vc = vcn ? p : nullptr;   // [vcn][nt] cell-independent fatmins of the subsets (value kernel)
+  p += (size_t)vcn * nt;
   sm.vals = p;
   sm.red = sm.vals + S;
   return sm;
@@ -161,11 +193,11 @@ __device__ __forceinline__ void lh_finish(const McArgs& a, const LhSmem& sm, dou
 }
 
 __global__ void __launch_bounds__(256)
-mc_loghvi_kernel(McArgs a) {
+mc_loghvi_kernel(McArgs a, int vcn) {
   extern __shared__ double lsm[];
   const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int q = a.q, nr = a.nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
-  LhSmem sm = lh_smem(lsm, M, q, nr, Mo, nt, S, false);
+  LhSmem sm = lh_smem(lsm, M, q, nr, Mo, nt, S, false, vcn);
   for (int i = tid; i < M * q * nr; i += nt) sm.root[i] = a.root[(size_t)batch * M * q * nr + i];
   for (int i = tid; i < q * M; i += nt) sm.mu[i] = a.mu[(size_t)batch * q * M + i];
   __syncthreads();
@@ -174,6 +206,10 @@ mc_loghvi_kernel(McArgs a) {
   double lmax = -INFINITY;
   for (int s = tid; s < S; s += nt) {
     lh_load_sample(a, sm, batch, s, tid, nt);
+    if (sm.vc)
+      for (unsigned sub = 1; sub <= full; ++sub)
+        for (int o = 0; o < Mo; ++o)
+          sm.vc[((size_t)(sub - 1) * Mo + o) * nt + tid] = subset_fatmin(sub, sm.objs + (size_t)o * nt + tid, Mo * nt, a.tau_max);
     const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
     const int sc = a.cells_shared ? 0 : s;
     const int Sc = a.cells_shared ? 1 : S;
@@ -187,7 +223,18 @@ mc_loghvi_kernel(McArgs a) {
       // running (max, sum) pairs: one exp per subset instead of a full logaddexp
       double mo = -INFINITY, so = 0.0, me = -INFINITY, se = 0.0;
       for (unsigned sub = 1; sub <= full; ++sub) {
-        const double la = subset_logarea(a, sm, sub, lo, up, tid, nt, log_tau_relu);
+        double la;
+        if (sm.vc) {
+          la = 0.0;
+          for (int o = 0; o < Mo; ++o) {
+            const double len = axis_from_fatmin(sm.vc[((size_t)(sub - 1) * Mo + o) * nt + tid], lo[o], up[o], a.tau_max);
+            la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
+          }
+          if (a.od.n_cons)
+            for (unsigned rest = sub; rest; rest &= rest - 1) la += sm.lfw[(size_t)(__ffs(rest) - 1) * nt + tid];
+        } else {
+          la = subset_logarea(a, sm, sub, lo, up, tid, nt, log_tau_relu);
+        }
         if (__popc(sub) & 1) lse_push(mo, so, la);
         else lse_push(me, se, la);
       }
@@ -203,9 +250,9 @@ mc_loghvi_kernel(McArgs a) {
   lh_finish(a, sm, lmax, nullptr, nullptr);
 }
 
-static int lh_pick_threads(const McArgs& a, bool grad, size_t* smem_out) {
+static int lh_pick_threads(const McArgs& a, bool grad, size_t* smem_out, int vcn = 0) {
   const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M + a.S + 40;
-  const size_t per = (size_t)a.q * a.od.n_obj + a.q + (grad ? (size_t)a.q * a.od.n_obj + a.q + (size_t)a.q * a.M : 0);
+  const size_t per = (size_t)a.q * a.od.n_obj + a.q + (grad ? (size_t)a.q * a.od.n_obj + a.q + (size_t)a.q * a.M : 0) + vcn;
   for (int nt = 256; nt >= 32; nt >>= 1) {
     size_t smem = (fixed + per * nt) * sizeof(double);
     if (smem <= 200 * 1024) { *smem_out = smem; return nt; }
@@ -216,14 +263,19 @@ static int lh_pick_threads(const McArgs& a, bool grad, size_t* smem_out) {
 int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   size_t smem = 0;
-  const int nt = lh_pick_threads(a, false, &smem);
+  // cell-independent subset fatmins cached per thread when they are few: (2^q - 1) n_obj <= 64 doubles (q <= 4, or q = 5 with
+  // two objectives); and only while that keeps at least 128 threads per CTA
+  int vcn = (a.q <= 5) ? ((1 << a.q) - 1) * a.od.n_obj : 0;
+  if (vcn > 64) vcn = 0;
+  int nt = lh_pick_threads(a, false, &smem, vcn);
+  if (vcn && nt < 128) { vcn = 0; nt = lh_pick_threads(a, false, &smem, 0); }
   if (!nt) { bo_set_error("mc_loghvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  mc_loghvi_kernel<<<a.b, nt, smem, st>>>(a);
+  mc_loghvi_kernel<<<a.b, nt, smem, st>>>(a, vcn);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

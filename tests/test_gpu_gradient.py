@@ -240,6 +240,16 @@ def test_gradient_q16_and_many_batches():
     v_all, g_all = check(acq_d2, acq_o2, X, st2)
     v_few, g_few = acq_d2.forward_backward(X[:3].to(st2.device))
     assert float((g_few - g_all[:3]).abs().max()) < 1e-9 * float(g_all.abs().max())
+    # b = 160 > 148 q-batches: cond_root_bwd keeps its warp-per-q-batch layout (four q-batches per CTA), fewer use a CTA each
+    p3 = Cf.zdt1_qnehvi(N=90, S=8, raw=160, d=4, q=2)
+    gp3 = P.oracle_gp(p3)
+    st3 = Cf.build_state(p3)
+    acq_o3 = P.oracle_acqf(p3, gp3, prune_samples=64)
+    acq_d3 = Cf.build_acqf(p3, st3, prune_samples=64)
+    X3 = Cf.candidates(p3)
+    v3, g3 = check(acq_d3, acq_o3, X3, st3)
+    v3f, g3f = acq_d3.forward_backward(X3[:5].to(st3.device))
+    assert float((g3f - g3[:5]).abs().max()) < 1e-9 * float(g3.abs().max())
 
 
 def test_failed_conditional_root_poisons_value_and_gradient():
