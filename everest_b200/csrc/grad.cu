@@ -23,12 +23,13 @@
 // added in cell-lane order afterwards (fixed order: deterministic).  Refinement calls have 8 q-batches x 512 samples; with
 // thousands of cells per sample (4 objectives) the cells are the only parallelism left.
 // ------------------------------------------------------------------------------------------------
+template <int MO>   // objectives at compile time (2..4: side lengths, bounds and arg-mins stay in registers), 0 = run time
 __global__ void __launch_bounds__(256)
 mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) {
   extern __shared__ double gsm[];
   const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int nst = nt / CL, sl = tid % nst, cl = tid / nst;
-  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = MO > 0 ? MO : a.od.n_obj;
   double* root = gsm;                          // [M][q][nr]
   double* mu = root + (size_t)M * q * nr;      // [q][M]
   double* objs = mu + q * M;                   // [q*Mo][nst]
@@ -80,6 +81,7 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) 
       double acc = 0.0;
       for (int c = cl; c < nc; c += CL) {
         double lo[BO_MAX_OBJECTIVES], up[BO_MAX_OBJECTIVES];
+#pragma unroll
         for (int o = 0; o < Mo; ++o) {
           lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
           up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
@@ -87,6 +89,7 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) 
         unsigned active = 0;
         for (int j = 0; j < q; ++j) {
           bool pos = true;
+#pragma unroll
           for (int o = 0; o < Mo; ++o) {
             double len = fmin(objs[((size_t)j * Mo + o) * nst + sl], up[o]) - lo[o];
             pos = pos && (len > 0.0);
@@ -105,6 +108,7 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) 
             double vol = 1.0, wprod = 1.0;
             double len[BO_MAX_OBJECTIVES];
             int arg[BO_MAX_OBJECTIVES];
+#pragma unroll
             for (int o = 0; o < Mo; ++o) {
               double mn = up[o];
               int aj = -1;
@@ -120,9 +124,11 @@ mc_hvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, int CL) 
             if (has_cons)
               for (unsigned rest = sub; rest; rest &= rest - 1) wprod *= fw[(size_t)(__ffs(rest) - 1) * nst + sl];
             // adjoint: the side length along o moves with the subset's minimum iff that minimum is below the cell's upper bound
+#pragma unroll
             for (int o = 0; o < Mo; ++o)
               if (arg[o] >= 0) {
                 double other = 1.0;
+#pragma unroll
                 for (int o2 = 0; o2 < Mo; ++o2)
                   if (o2 != o) other *= len[o2];
                 gob[((size_t)arg[o] * Mo + o) * nt + tid] += sgn * wprod * other;
@@ -218,13 +224,16 @@ int launch_mc_hvi_grad(const McArgs& a, int max_cells, double* dF, size_t df_str
     else if (nst > 32) nst >>= 1;
     else { bo_set_error("mc_hvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
   }
-  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
+  void (*kern)(McArgs, double*, size_t, int) = (Mo == 2) ? mc_hvi_grad_kernel<2> : (Mo == 3) ? mc_hvi_grad_kernel<3>
+                                              : (Mo == 4) ? mc_hvi_grad_kernel<4> : mc_hvi_grad_kernel<0>;
+  static PerDeviceMax attr_pd[4];
+  size_t& attr = attr_pd[(Mo >= 2 && Mo <= 4) ? Mo - 1 : 0].slot();
   if (smem > 48 * 1024 && smem > attr) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(mc_hvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   dim3 grid(a.b, nsplit);
-  mc_hvi_grad_kernel<<<grid, nst * CL, smem, st>>>(a, dF, df_stride, CL);
+  kern<<<grid, nst * CL, smem, st>>>(a, dF, df_stride, CL);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return launch_mc_reduce_partials(a.partial, nsplit, a.b, a.S, a.out, a.info_in, a.M, a.info_out, st, lc);

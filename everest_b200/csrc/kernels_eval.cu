@@ -265,14 +265,47 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         // a pair costs nd compares and one shared-memory load instead of an FP64 division (slow path whenever all groups
         // match: 0 / nd) and an exp.
         double* Ht = reinterpret_cast<double*>(Bc + CC_TILE * BO_MAX_GROUPS);
+        int* Apk = reinterpret_cast<int*>(Ht + 64);     // codes of a point as nibbles of one word: the mismatch pattern of a
+        int* Bpk = Apk + CC_TILE;                       // pair is read off the XOR of two registers
         const bool tabulated = L.nd <= 6;
         if (tabulated && tid < (1 << L.nd)) {
           double acc = 0.0;
           for (int f = 0; f < L.nd; ++f) acc += ((tid >> f) & 1) ? L.wls[f] : 0.0;
           Ht[tid] = exp_nonpos(-(acc / (double)L.nd));
         }
-        __syncthreads();
-        if (tabulated) {
+        int wide_code = 0;                              // a code that does not fit a nibble (cardinality > 16)
+        if (tabulated && tid < 2 * CC_TILE) {
+          const int r = tid & (CC_TILE - 1);
+          const bool rowside = tid < CC_TILE;
+          const int gr = rowside ? row0 + r : col0 + r;
+          const bool in = rowside ? (gr < n_rows) : (gr < n_cols);
+          const int* cp = (rowside ? rows.codes[l] : cols.s[l].codes) + (size_t)(in ? gr : 0) * L.nd;
+          int pk = 0;
+          for (int f = 0; f < L.nd; ++f) {
+            const int c = in ? cp[f] : 0;
+            wide_code |= (c > 15);
+            pk |= (c & 15) << (4 * f);
+          }
+          (rowside ? Apk : Bpk)[r] = pk;
+        }
+        const int any_wide = __syncthreads_or(wide_code);   // (also the barrier that publishes the staged codes and tables)
+        const bool packed = tabulated && !any_wide;
+        if (packed) {
+          const int ra[2] = {Apk[wr * 16 + g], Apk[wr * 16 + 8 + g]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cb = Bpk[wc * 32 + j * 8 + 2 * t + e];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int x = ra[i] ^ cb;
+                int mask = 0;
+                for (int f = 0; f < L.nd; ++f) mask |= ((x >> (4 * f)) & 15) ? (1 << f) : 0;
+                lv[(i * 4 + j) * 2 + e] = Ht[mask];
+              }
+            }
+        } else if (tabulated) {
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll

@@ -76,6 +76,42 @@ def test_matern_and_scale_kernels(nu):
     assert float((cd.cpu() - co).abs().max()) < 1e-9 * float(co.abs().max())
 
 
+@pytest.mark.parametrize("cards", [(4, 6), (20, 3), (2, 3, 2, 4, 2, 3, 2)])
+def test_hamming_leaf_variants_of_the_tree_kernel(cards):
+    """The generic cross-covariance kernel evaluates a Hamming leaf three ways: the mismatch pattern read off packed nibble
+    codes (up to 6 groups, cardinalities <= 16), per-group compares into the table of the 2^nd patterns (a cardinality above
+    16), and the direct sum + exp (more than 6 groups).  All three must reproduce the reference's HammingKernelWithOneHots
+    arithmetic (kernels/categorical.py), here inside an additive / multiplicative tree with a Matern leaf."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    N, nq = 140, 37
+    def draw(n):
+        cols = [rng.random((n, 2))] + [np.eye(c)[rng.integers(0, c, n)] for c in cards]
+        return np.concatenate(cols, axis=1)
+    X = draw(N)
+    d = X.shape[1]
+    cats, start = {}, 2
+    for c in cards:
+        cats[start] = c
+        start += c
+    y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.3 * X[:, 2] - 0.2 * X[:, 3] + 0.05 * rng.normal(size=N)
+    ls = [0.5 + 0.3 * i for i in range(len(cards))]
+    kern = K.AdditiveKernel([
+        K.ScaleKernel(K.MaternKernel([0, 1], [0.4, 0.6], nu=2.5), 0.8),
+        K.ScaleKernel(K.HammingDistanceKernel(cats, ls), 0.5),
+        K.MultiplicativeKernel([K.ScaleKernel(K.MaternKernel([0, 1], [0.7, 0.3], nu=2.5), 0.9),
+                                K.ScaleKernel(K.HammingDistanceKernel(cats, ls[::-1]), 1.1)])])
+    p = dict(name="hamming_variants", d=d, X=X, Y=y[:, None], bounds=None, in_offset=np.zeros(d), in_scale=np.ones(d),
+             outputs=[dict(kernel=kern, y=y, noise=1e-2, mean_const=0.0)])
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    Xq = torch.as_tensor(draw(nq))
+    mo, co = gp.posterior(Xq)
+    md, cd = st.posterior_joint(Xq)
+    assert rel_err(md, mo, floor=1e-6) < 1e-9
+    assert float((cd.cpu() - co).abs().max()) < 1e-9 * float(co.abs().max())
+
+
 @pytest.mark.parametrize("m_obj,n", [(2, 40), (3, 25), (4, 18)])
 def test_box_decomposition_bit_exact(m_obj, n):
     """Identical objective values in -> identical cell lists out (no arithmetic, only comparisons)."""
