@@ -128,14 +128,16 @@ int launch_finish_var(const ModelD& md, PrepD prep, const double* g, int n, int 
 // update is reduced by one warp; Cholesky entries are ordered dot products).  Baselines that do not fit shared memory
 // form bl on the FP64 tensor pipe (k-blocks of 4 per DMMA) instead of one FMA chain per entry.
 // ------------------------------------------------------------------------------------------------
+template <bool wide>   // the q-batch's team: the whole CTA (launcher: wpb = 4) or one warp
 __global__ void __launch_bounds__(128)
 cond_root_kernel(CondRootArgs a) {
   extern __shared__ double csm[];
   const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool wide = a.wpb == 4;                                         // uniform over the grid
   const int batch = wide ? blockIdx.x : blockIdx.x * 4 + warp_in_cta;
-  const int tl = wide ? (int)threadIdx.x : lane, tn = wide ? 128 : 32;  // thread index / count within the q-batch's team
-  const int wsub = wide ? warp_in_cta : 0, nw = wide ? 4 : 1;           // warp index / count within the team
+  const int tl = wide ? (int)threadIdx.x : lane;                        // thread index / count within the q-batch's team
+  constexpr int tn = wide ? 128 : 32;
+  const int wsub = wide ? warp_in_cta : 0;                              // warp index / count within the team
+  constexpr int nw = wide ? 4 : 1;
   const int q = a.q, nb = a.nb, nr = nb + q;
   const ModelD& md = a.md;
   // per-team scratch, then (optionally) the CTA-shared copy of L_b^-1
@@ -369,12 +371,14 @@ int launch_cond_root(const CondRootArgs& a0, cudaStream_t st, LaunchCounter* lc)
   a.linv_in_smem = (a.nb > 0 && a.wpb == 1 && smem + linv <= 96 * 1024) ? 1 : 0;
   if (a.linv_in_smem) smem += linv;
   if (smem > 200 * 1024) { bo_set_error("cond_root: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
-  static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
+  static PerDeviceMax attr_pd[2]; size_t& attr = attr_pd[a.wpb == 4].slot();
   if (smem > 48 * 1024 && smem > attr) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.wpb == 4) CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  cond_root_kernel<<<a.wpb == 4 ? a.b : (a.b + 3) / 4, 128, smem, st>>>(a);
+  if (a.wpb == 4) cond_root_kernel<true><<<a.b, 128, smem, st>>>(a);
+  else cond_root_kernel<false><<<(a.b + 3) / 4, 128, smem, st>>>(a);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;

@@ -287,8 +287,9 @@ int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, co
 //   br = chol(C), C = Sqq - bl bl^T, bl = Sqb L_b^-T, Sqq = s^2 (K** - G), Sqb = s^2 (K*b - W), mu = y_std (c + K*X alpha) + y_mean
 // Cholesky adjoint: Cbar = sym( L^-T Phi(L^T Lbar) L^-1 ), Phi = lower triangle with halved diagonal.
 // ------------------------------------------------------------------------------------------------
+template <bool wide>
 __global__ void __launch_bounds__(128)
-cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta, int wide) {
+cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta) {
   // Two layouts (uniform over the grid): one warp per q-batch, `warps_per_cta` q-batches per CTA -- or, `wide`, the four
   // warps of a CTA on one q-batch with the 32-column blocks of d Sqb dealt over the warps AND over gridDim.y CTAs (every
   // CTA of a q-batch repeats the small q x q adjoint).  Refinement calls have 8 q-batches: one warp each left the 286 x 286
@@ -297,8 +298,10 @@ cond_root_bwd_kernel(CondRootBwdArgs a, int warps_per_cta, int wide) {
   const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int batch = wide ? blockIdx.x : blockIdx.x * warps_per_cta + wic;
   if (!wide && (wic >= warps_per_cta || batch >= a.b)) return;
-  const int tl = wide ? (int)threadIdx.x : lane, tn = wide ? 128 : 32;
-  const int wsub = wide ? wic : 0, nw = wide ? 4 : 1;
+  const int tl = wide ? (int)threadIdx.x : lane;
+  constexpr int tn = wide ? 128 : 32;
+  const int wsub = wide ? wic : 0;
+  constexpr int nw = wide ? 4 : 1;
 #define TEAM_SYNC() do { if (wide) __syncthreads(); else __syncwarp(); } while (0)
   const int q = a.q, nb = a.nb, nr = nb + q;
   double* T = bsm + (wide ? 0 : (size_t)wic * ((size_t)q * nb + 5 * q * q));  // [q][nb] total adjoint of bl
@@ -426,7 +429,8 @@ int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounte
   if (smem > 200 * 1024) { bo_set_error("cond_root_bwd: baseline too large for shared memory (n_b=%d)", a.nb); return BO_ERR_INVALID; }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(cond_root_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   int ysplit = 1;
@@ -435,7 +439,8 @@ int launch_cond_root_bwd(const CondRootBwdArgs& a, cudaStream_t st, LaunchCounte
     ysplit = std::max(1, std::min((blocks + 3) / 4, std::max(1, 296 / a.b)));
   }
   dim3 grid(wide ? a.b : (a.b + wpc - 1) / wpc, ysplit);
-  cond_root_bwd_kernel<<<grid, 128, smem, st>>>(a, wpc, wide);
+  if (wide) cond_root_bwd_kernel<true><<<grid, 128, smem, st>>>(a, wpc);
+  else cond_root_bwd_kernel<false><<<grid, 128, smem, st>>>(a, wpc);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
   return BO_OK;
