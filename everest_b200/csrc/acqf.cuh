@@ -98,7 +98,8 @@ int launch_mc_reduce_partials(const double* partial, int groups, int b, int S, d
                               int* info_out, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_hvi_grad(const McArgs& a, int max_cells, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
 int launch_mc_scalar_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
-int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc);
+// vals_ws: [b][S] doubles (per-sample values when the MC samples of a q-batch are split over several CTAs) or NULL
+int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, double* vals_ws, cudaStream_t st, LaunchCounter* lc);
 // dF -> d root [b, M, q, nb+q] (= [d bl | d br]) and d mu [b*q, M]
 int launch_grad_reduce(const double* dF, size_t df_stride, const double* zbT, const double* zqT, int S, int nb, int q,
                        int M, int rows, double* droot, double* dmu, cudaStream_t st, LaunchCounter* lc);

@@ -1287,7 +1287,12 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       if (!u_forked) RC(st->wsU.ensure(rows_max * ldk * 8, false));
       rec_begin(st, "mc_grad", s);
       if (st->acqf_kind == 3) RC(launch_mc_scalar_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
-      else if (st->log_hvi) RC(launch_mc_loghvi_grad(ma, st->wsDF.as<double>(), dfs, s, &st->lc));
+      else if (st->log_hvi) {
+        // the partial-sum workspace doubles as the [b][S] per-sample values of the sample-split log-space adjoint
+        RC(st->wsPartial.ensure((size_t)bchunk * S * 8));
+        ma.partial = st->wsPartial.as<double>();
+        RC(launch_mc_loghvi_grad(ma, st->wsDF.as<double>(), dfs, st->wsPartial.as<double>(), s, &st->lc));
+      }
       else RC(launch_mc_hvi_grad(ma, st->max_cells, st->wsDF.as<double>(), dfs, s, &st->lc));
       rec_end(st, s);
       rec_begin(st, "grad_reduce", s);

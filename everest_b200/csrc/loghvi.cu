@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "mc_math.cuh"
 
+#include <algorithm>
+
 #define LH_MAXO BO_MAX_OBJECTIVES
 
 // side length of the overlap of subset `sub` with the cell along objective o; optionally d len / d obj_j for the members
@@ -281,8 +283,45 @@ int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
   return BO_OK;
 }
 
+// Few q-batches (refinement: 8 restarts): the MC samples of a q-batch are split over gridDim.y CTAs, which leave the
+// per-sample values in `vals_g` [b][S] and the un-normalised d value / d f in dF; loghvi_grad_finish_kernel then forms the
+// log-mean-exp over the samples and applies the samples' softmax weights.
 __global__ void __launch_bounds__(256)
-mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
+loghvi_grad_finish_kernel(McArgs a, const double* __restrict__ vals_g, double* __restrict__ dF, size_t df_stride) {
+  __shared__ double red[40];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, S = a.S, q = a.q, M = a.M;
+  const double* v = vals_g + (size_t)batch * S;
+  double lmax = -INFINITY;
+  for (int s = tid; s < S; s += nt) lmax = fmax(lmax, v[s]);
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lmax;
+  __syncthreads();
+  double bm = -INFINITY;
+  for (int w = 0; w < (nt >> 5); ++w) bm = fmax(bm, red[w]);
+  __syncthreads();
+  double se = 0.0;
+  for (int s = tid; s < S; s += nt) se += exp(v[s] - bm);
+  const double t = block_sum(se, red);
+  if (tid == 0) red[32] = t;
+  __syncthreads();
+  const double tsum = red[32];
+  if (tid == 0) {
+    a.out[batch] = bm + log(tsum) - log((double)S);
+    if (a.info_out) {
+      int f = 0;
+      for (int m = 0; m < M; ++m) f |= a.info_in[(size_t)batch * M + m];
+      a.info_out[batch] = f;
+    }
+  }
+  for (int s = tid; s < S; s += nt) {
+    const double wS = exp(v[s] - bm) / tsum;
+    for (int j = 0; j < q; ++j)
+      for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] *= wS;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, double* __restrict__ vals_g) {
   extern __shared__ double lsm[];
   const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int q = a.q, nr = a.nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
@@ -294,7 +333,9 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
   const bool has_cons = a.od.n_cons > 0;
   const double log_tau_relu = log(a.tau_relu);
   double lmax = -INFINITY;
-  for (int s = tid; s < S; s += nt) {
+  const int per_split = (S + gridDim.y - 1) / gridDim.y;
+  const int s_begin = blockIdx.y * per_split, s_end = min(S, s_begin + per_split);
+  for (int s = s_begin + tid; s < s_end; s += nt) {
     lh_load_sample(a, sm, batch, s, tid, nt);
     const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
     const int sc = a.cells_shared ? 0 : s;
@@ -355,6 +396,7 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
     }
     const double sv = (ssum > 0.0) ? R + log(ssum) : -INFINITY;
     sm.vals[s] = sv;
+    if (vals_g) vals_g[(size_t)batch * S + s] = sv;
     lmax = fmax(lmax, sv);
     // un-normalised d sample value / d f (scaled by the sample's softmax weight after the block reduction)
     const double inv = (ssum > 0.0) ? 1.0 / ssum : 0.0;
@@ -369,6 +411,7 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
       for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m];
     }
   }
+  if (vals_g) return;   // split over the samples: loghvi_grad_finish_kernel completes the q-batch
   double bm, tsum;
   lh_finish(a, sm, lmax, &bm, &tsum);
   for (int s = tid; s < S; s += nt) {
@@ -378,18 +421,38 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride) {
   }
 }
 
-int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, cudaStream_t st, LaunchCounter* lc) {
+int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, double* vals_ws, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   size_t smem = 0;
-  const int nt = lh_pick_threads(a, true, &smem);
+  int nt = lh_pick_threads(a, true, &smem);
   if (!nt) { bo_set_error("mc_loghvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
+  // about two waves of CTAs: split the MC samples when there are few q-batches (needs the [b][S] value workspace)
+  int nsplit = 1;
+  if (vals_ws && a.b < 148) {
+    nsplit = std::max(1, std::min((296 + a.b - 1) / a.b, (a.S + 31) / 32));
+    const int per_split = (a.S + nsplit - 1) / nsplit;
+    const int want = ((per_split + 31) / 32) * 32;
+    if (want < nt) {
+      // the per-thread part of the shared-memory budget shrinks with the CTA
+      const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M + a.S + 40;
+      const size_t per = (size_t)2 * a.q * a.od.n_obj + 2 * a.q + (size_t)a.q * a.M;
+      nt = want;
+      smem = (fixed + per * nt) * sizeof(double);
+    }
+  }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  mc_loghvi_grad_kernel<<<a.b, nt, smem, st>>>(a, dF, df_stride);
+  dim3 grid(a.b, nsplit);
+  mc_loghvi_grad_kernel<<<grid, nt, smem, st>>>(a, dF, df_stride, nsplit > 1 ? vals_ws : nullptr);
   if (lc) lc->n++;
   CUDA_CHECK_RET(cudaGetLastError());
+  if (nsplit > 1) {
+    loghvi_grad_finish_kernel<<<a.b, 256, 0, st>>>(a, vals_ws, dF, df_stride);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+  }
   return BO_OK;
 }
