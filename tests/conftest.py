@@ -25,3 +25,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _pin_global_generators():
+    """torch's default seed is random per process (torch 2.11), and BoTorch-style code paths draw from the GLOBAL generator
+    (initialize_q_batch's multinomial pick of the restarts, default seeds of strategies): pin it per test so that a test's
+    outcome does not depend on the process it runs in or on the tests before it."""
+    import numpy as np
+    import torch
+
+    torch.manual_seed(20250711)
+    np.random.seed(20250711)
+    yield
