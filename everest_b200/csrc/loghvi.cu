@@ -421,25 +421,195 @@ mc_loghvi_grad_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, doubl
   }
 }
 
+// Few q-batches (refinement): besides the split over the MC samples (gridDim.y), the CELLS of a sample are dealt to CL "cell
+// lanes": thread (sl, cl) of a CTA holding nst samples walks the cells c = cl, cl + CL, ... with its own running maximum,
+// sum and adjoint block; the lanes of a sample are merged afterwards in lane order (deterministic) by rescaling to the
+// common maximum.  Leaves the per-sample values in vals_g and the un-normalised d value / d f in dF
+// (loghvi_grad_finish_kernel completes the q-batch).
+__global__ void __launch_bounds__(256)
+mc_loghvi_grad_cl_kernel(McArgs a, double* __restrict__ dF, size_t df_stride, double* __restrict__ vals_g, int CL) {
+  extern __shared__ double lsm[];
+  const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int nst = nt / CL, sl = tid % nst, cl = tid / nst;
+  const int q = a.q, nb = a.nb, nr = nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
+  double* root = lsm;                            // [M][q][nr]
+  double* mu = root + (size_t)M * q * nr;        // [q][M]
+  double* objs = mu + q * M;                     // [q*Mo][nst]
+  double* lfw = objs + (size_t)q * Mo * nst;     // [q][nst]
+  double* ys = lfw + (size_t)q * nst;            // [q*M][nst]
+  double* gob = ys + (size_t)q * M * nst;        // [q*Mo][nt]  per thread
+  double* glf = gob + (size_t)q * Mo * nt;       // [q][nt]     per thread
+  double* Rs = glf + (size_t)q * nt;             // [nt] running maximum of the thread's cells
+  double* Ss = Rs + nt;                          // [nt] running sum
+  for (int i = tid; i < M * q * nr; i += nt) root[i] = a.root[(size_t)batch * M * q * nr + i];
+  for (int i = tid; i < q * M; i += nt) mu[i] = a.mu[(size_t)batch * q * M + i];
+  const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
+  const bool has_cons = a.od.n_cons > 0;
+  const double log_tau_relu = log(a.tau_relu);
+  const int per_split = (S + gridDim.y - 1) / gridDim.y;
+  const int s_begin = blockIdx.y * per_split, s_end = min(S, s_begin + per_split);
+  for (int s0 = s_begin; s0 < s_end; s0 += nst) {
+    const int s = s0 + sl;
+    const bool valid = s < s_end;
+    __syncthreads();
+    if (valid)
+      for (int j = cl; j < q; j += CL) {
+        double y[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) {
+          const double* rr = root + ((size_t)m * q + j) * nr;
+          double sb = 0.0, sq = 0.0;
+          if (a.Fp) sb = a.Fp[(size_t)m * a.fp_stride + ((size_t)batch * q + j) * S + s];
+          else for (int e = 0; e < nb; ++e) sb = fma(rr[e], a.zbT[((size_t)e * M + m) * S + s], sb);
+          for (int k = 0; k < q; ++k) sq = fma(rr[nb + k], a.zqT[((size_t)k * M + m) * S + s], sq);
+          y[m] = (mu[j * M + m] + sb) + sq;
+          ys[((size_t)j * M + m) * nst + sl] = y[m];
+        }
+        for (int o = 0; o < Mo; ++o) objs[((size_t)j * Mo + o) * nst + sl] = objective_apply(a.od.op[o], y);
+        lfw[(size_t)j * nst + sl] = a.od.n_cons ? log_feas_fat(a.od, y, 0.0, nullptr) : 0.0;
+      }
+    for (int i = 0; i < q * Mo; ++i) gob[(size_t)i * nt + tid] = 0.0;
+    for (int j = 0; j < q; ++j) glf[(size_t)j * nt + tid] = 0.0;
+    __syncthreads();
+    double R = -INFINITY, ssum = 0.0;
+    if (valid) {
+      const int nc = a.cells_shared ? a.ncells[0] : a.ncells[s];
+      const int sc = a.cells_shared ? 0 : s;
+      const int Sc = a.cells_shared ? 1 : S;
+      for (int c = cl; c < nc; c += CL) {
+        double lo[LH_MAXO], up[LH_MAXO];
+        for (int o = 0; o < Mo; ++o) {
+          lo[o] = a.cell_lo[((size_t)c * Mo + o) * Sc + sc];
+          up[o] = a.cell_up[((size_t)c * Mo + o) * Sc + sc];
+        }
+        double mo = -INFINITY, so = 0.0, me = -INFINITY, se = 0.0;
+        for (unsigned sub = 1; sub <= full; ++sub) {
+          double la = 0.0;
+          for (int o = 0; o < Mo; ++o) {
+            const double len = subset_axis(sub, objs + (size_t)o * nst + sl, Mo * nst, lo[o], up[o], a.tau_max, nullptr);
+            la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
+          }
+          if (has_cons)
+            for (unsigned rest = sub; rest; rest &= rest - 1) la += lfw[(size_t)(__ffs(rest) - 1) * nst + sl];
+          if (__popc(sub) & 1) lse_push(mo, so, la);
+          else lse_push(me, se, la);
+        }
+        const double odd = lse_value(mo, so), even = lse_value(me, se);
+        const bool no_even = isinf(even) && even < 0;
+        const double cellv = no_even ? odd : odd + log1mexp_d(even - odd);
+        if (isinf(cellv) && cellv < 0) continue;
+        double wc;
+        if (cellv > R) {
+          const double sc_old = exp(R - cellv);  // 0 when R = -inf
+          for (int i = 0; i < q * Mo; ++i) gob[(size_t)i * nt + tid] *= sc_old;
+          if (has_cons) for (int j = 0; j < q; ++j) glf[(size_t)j * nt + tid] *= sc_old;
+          ssum = ssum * sc_old + 1.0;
+          R = cellv;
+          wc = 1.0;
+        } else {
+          wc = exp(cellv - R);
+          ssum += wc;
+        }
+        const double r = no_even ? 0.0 : exp(even - odd);
+        const double a_odd = 1.0 / (1.0 - r), a_even = -r / (1.0 - r);
+        for (unsigned sub = 1; sub <= full; ++sub) {
+          double la = 0.0;
+          double dlen[LH_MAXO][BO_MAX_Q];
+          double dlf[LH_MAXO];
+          for (int o = 0; o < Mo; ++o) {
+            const double len = subset_axis(sub, objs + (size_t)o * nst + sl, Mo * nst, lo[o], up[o], a.tau_max, dlen[o]);
+            la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
+            dlf[o] = log_fatplus_grad_d(len, a.tau_relu);
+          }
+          if (has_cons)
+            for (unsigned rest = sub; rest; rest &= rest - 1) la += lfw[(size_t)(__ffs(rest) - 1) * nst + sl];
+          const bool is_odd = __popc(sub) & 1;
+          const double kappa = wc * (is_odd ? a_odd * exp(la - odd) : a_even * exp(la - even));
+          if (kappa == 0.0) continue;
+          for (unsigned rest = sub; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
+            for (int o = 0; o < Mo; ++o) gob[((size_t)j * Mo + o) * nt + tid] += kappa * dlf[o] * dlen[o][j];
+            if (has_cons) glf[(size_t)j * nt + tid] += kappa;
+          }
+        }
+      }
+    }
+    Rs[tid] = R;
+    Ss[tid] = ssum;
+    __syncthreads();
+    if (valid) {
+      // merge the cell lanes of this sample: common maximum, then sums in lane order
+      double Rm = -INFINITY;
+      for (int k = 0; k < CL; ++k) Rm = fmax(Rm, Rs[k * nst + sl]);
+      double stot = 0.0, wk[8];                  // CL <= 8 (launcher); lanes without a finite cell weigh nothing
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double Rk = (k < CL) ? Rs[k * nst + sl] : -INFINITY;
+        wk[k] = (isinf(Rk) && Rk < 0) ? 0.0 : exp(Rk - Rm);
+        if (k < CL) stot += Ss[k * nst + sl] * wk[k];
+      }
+      if (cl == 0) vals_g[(size_t)batch * S + s] = (stot > 0.0) ? Rm + log(stot) : -INFINITY;
+      const double inv = (stot > 0.0) ? 1.0 / stot : 0.0;
+      for (int j = cl; j < q; j += CL) {
+        double y[2 * BO_MAX_OBJECTIVES], dy[2 * BO_MAX_OBJECTIVES];
+        for (int m = 0; m < M; ++m) { y[m] = ys[((size_t)j * M + m) * nst + sl]; dy[m] = 0.0; }
+        double gl = 0.0;
+        for (int o = 0; o < Mo; ++o) {
+          double gv = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < CL) gv += gob[((size_t)j * Mo + o) * nt + k * nst + sl] * wk[k];
+          gv *= inv;
+          if (gv != 0.0) dy[a.od.op[o].out_idx] += gv * objective_grad(a.od.op[o], y);
+        }
+        if (has_cons) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < CL) gl += glf[(size_t)j * nt + k * nst + sl] * wk[k];
+          log_feas_fat(a.od, y, gl * inv, dy);
+        }
+        for (int m = 0; m < M; ++m) dF[(size_t)m * df_stride + ((size_t)batch * q + j) * S + s] = dy[m];
+      }
+    }
+  }
+}
+
 int launch_mc_loghvi_grad(const McArgs& a, double* dF, size_t df_stride, double* vals_ws, cudaStream_t st, LaunchCounter* lc) {
   if (a.b <= 0) return BO_OK;
   size_t smem = 0;
-  int nt = lh_pick_threads(a, true, &smem);
+  const int nt = lh_pick_threads(a, true, &smem);
   if (!nt) { bo_set_error("mc_loghvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
-  // about two waves of CTAs: split the MC samples when there are few q-batches (needs the [b][S] value workspace)
-  int nsplit = 1;
+  // few q-batches: MC samples split over CTAs and cells over cell lanes (needs the [b][S] value workspace)
   if (vals_ws && a.b < 148) {
-    nsplit = std::max(1, std::min((296 + a.b - 1) / a.b, (a.S + 31) / 32));
+    const int nsplit = std::max(1, std::min((296 + a.b - 1) / a.b, (a.S + 31) / 32));
     const int per_split = (a.S + nsplit - 1) / nsplit;
-    const int want = ((per_split + 31) / 32) * 32;
-    if (want < nt) {
-      // the per-thread part of the shared-memory budget shrinks with the CTA
-      const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M + a.S + 40;
-      const size_t per = (size_t)2 * a.q * a.od.n_obj + 2 * a.q + (size_t)a.q * a.M;
-      nt = want;
-      smem = (fixed + per * nt) * sizeof(double);
+    int nst = std::min(256, ((per_split + 31) / 32) * 32);
+    int CL = std::max(1, std::min(8, 256 / nst));
+    const size_t fixed = (size_t)a.M * a.q * (a.nb + a.q) + (size_t)a.q * a.M;
+    const size_t per_sample = (size_t)a.q * a.od.n_obj + a.q + (size_t)a.q * a.M;
+    const size_t per_thread = (size_t)a.q * a.od.n_obj + a.q + 2;
+    size_t sm2 = 0;
+    for (;;) {
+      sm2 = (fixed + per_sample * nst + per_thread * (size_t)nst * CL) * sizeof(double);
+      if (sm2 <= 200 * 1024) break;
+      if (CL > 1) CL >>= 1;
+      else if (nst > 32) nst >>= 1;
+      else { bo_set_error("mc_loghvi_grad: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
     }
+    static PerDeviceMax attr2_pd; size_t& attr2 = attr2_pd.slot();
+    if (sm2 > 48 * 1024 && sm2 > attr2) {
+      CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_grad_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      attr2 = sm2;
+    }
+    dim3 grid(a.b, nsplit);
+    mc_loghvi_grad_cl_kernel<<<grid, nst * CL, sm2, st>>>(a, dF, df_stride, vals_ws, CL);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    loghvi_grad_finish_kernel<<<a.b, 256, 0, st>>>(a, vals_ws, dF, df_stride);
+    if (lc) lc->n++;
+    CUDA_CHECK_RET(cudaGetLastError());
+    return BO_OK;
   }
+  const int nsplit = 1;
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
   if (smem > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
