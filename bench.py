@@ -181,7 +181,10 @@ def run_reference(args):
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi` polled every 50 ms for the whole life of the process (it needs a few hundred ms to deliver its first line,
+    which a 90 ms timed region does not wait for); `mark_begin` / `mark_end` bracket the timed region and `stop` reports the
+    samples that fall inside it -- or, when the region slipped between two polls, the samples nearest to it (flagged)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -189,17 +192,26 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.path = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
     def stop(self):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -209,27 +221,43 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
+        recs = []
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                    pw.append(float(f[3]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rec = (ts, float(f[2]), float(f[3]), float(f[4]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                rs = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10])
+                      if v.lower().startswith("active")]
+                recs.append(rec + (rs,))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       sm_mhz_min=min(sm), power_w_max=max(pw) if pw else None)
+        if not recs:
+            return out
+        t0 = self.t_begin if self.t_begin is not None else recs[0][0]
+        t1 = self.t_end if self.t_end is not None else recs[-1][0]
+        inside = [r for r in recs if t0 - 0.02 <= r[0] <= t1 + 0.02]
+        nearest = False
+        if not inside:
+            # the region fell between two polls: the two samples closest to it (the GPU is under the same load during the
+            # warm-up steps right before and the end-to-end steps right after)
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(recs, key=lambda r: abs(r[0] - mid))[:2]
+            nearest = True
+        sm = [r[1] for r in inside]
+        out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(r[2] for r in inside),
+                   reasons=sorted({x for r in inside for x in r[4]}), samples=len(inside), sm_mhz_min=min(sm),
+                   power_w_max=max(r[3] for r in inside), timed_region_s=round(t1 - t0, 4),
+                   samples_in_process=len(recs))
+        if nearest:
+            out["nearest_samples_only"] = True
+            out["nearest_sample_offset_s"] = round(min(abs(r[0] - 0.5 * (t0 + t1)) for r in inside), 3)
         return out
 
 
@@ -438,6 +466,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # nvidia-smi needs a few hundred ms to deliver its first line, which a 90 ms timed region does not wait for: the poller runs
+    # from here on (set-up takes seconds) and the timed region is bracketed by mark_begin / mark_end
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     p = make_problem(args)
     p_global = dict(p)                                   # strong scaling: ONE candidate set, sliced over the ranks
     p["cand_seed"] = p["cand_seed"] + rank               # weak scaling: every rank screens its own raw samples
@@ -489,10 +522,9 @@ def run_b200(args):
         vals = weak_step()
     barrier()
     launches0 = st.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ms_weak = timed(weak_step, args.steps, 0)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = st.launch_count() - launches0
     vals = acq(X)
