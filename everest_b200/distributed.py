@@ -89,11 +89,16 @@ def sharded_optimize_acqf(acq_function, bounds: torch.Tensor, q: int, num_restar
         X_rnd = optim.sample_q_batches_from_polytope(raw_samples, q, bounds, inequality_constraints, equality_constraints,
                                                      seed=seed, fixed_features=fixed_features)
     else:
-        X_rnd = optim.apply_fixed_features(optim.draw_sobol_samples(bounds, raw_samples, q, seed=seed), fixed_features)
+        # drawn where they are scored, like optimize_acqf: no host Sobol draw and no H2D of raw_samples * q * d doubles (the
+        # device generator is bit-identical to torch's engine for the same seed, so every rank still holds the same set)
+        X_rnd = optim.apply_fixed_features(optim.draw_sobol_samples(bounds, raw_samples, q, seed=seed,
+                                                                    device=dev if torch.device(dev).type == "cuda" else None),
+                                           fixed_features)
     with torch.no_grad():
         Y_rnd = sharded_forward(lambda x: acq_function(x.to(dev)), X_rnd, group=group).cpu()
     gen = torch.Generator().manual_seed(int(seed))          # the same multinomial draw on every rank
     X_ic, idcs = optim.initialize_q_batch(X_rnd, Y_rnd, n=num_restarts, eta=(options or {}).get("eta", 2.0), generator=gen)
+    X_ic = X_ic.cpu()
     Y_ic = Y_rnd[idcs]
     lo, hi = shard_bounds(num_restarts, rank, world)
     best_val, best_x = float("-inf"), torch.zeros(q, bounds.shape[-1], dtype=torch.double)
