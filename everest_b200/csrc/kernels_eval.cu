@@ -541,6 +541,45 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         *reinterpret_cast<double2*>(Cs + (wr * 16 + i * 8 + g) * CC3_CLD + wc * 32 + j * 8 + 2 * t) =
             make_double2(acc[i][j][0], acc[i][j][1]);
     __syncthreads();
+    if (oz.planes && !oz.write_fp64) {
+      // Screens (digit planes only): kernel function and slicing in ONE pass over the tile -- thread = (row, 16-column chunk)
+      // reads its 16 raw dot products, evaluates the kernel four values at a time (four independent exp chains) and splits
+      // them straight into its 7 x 16 bytes.  The two-pass form below stored the kernel values back to the tile and read them
+      // again behind another barrier (ncu r02: shared-memory pipe 45 % busy, issue 42 %).
+      const int r = tid & 63, c = tid >> 6;
+      const int gr = row0 + r, chunk = (col0 >> 4) + c;
+      const double naR = n2a_s[r];
+      const bool okR = gr < n_rows;
+      signed char dig[OZ_PLANES][16];
+#pragma unroll
+      for (int t4 = 0; t4 < 16; t4 += 4) {
+        double st[4], lv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c * 16 + t4 + u;
+          st[u] = fmax(naR + n2b_s[cc] - 2.0 * Cs[r * CC3_CLD + cc], 0.0);
+          if (same_set && gr == col0 + cc) st[u] = 0.0;
+        }
+        leaf_value_from_stat_tab_n<4>(KIND, st, lv, exptab);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double v = (okR && col0 + c * 16 + t4 + u < n_cols) ? coef * lv[u] : 0.0;
+          signed char d[OZ_PLANES];
+          oz_split_digits(v * oz.inv_scale, d);
+#pragma unroll
+          for (int p = 0; p < OZ_PLANES; ++p) dig[p][t4 + u] = d[p];
+        }
+      }
+      if (gr < oz.rows_alloc && chunk < oz.n_chunks) {
+#pragma unroll
+        for (int p = 0; p < OZ_PLANES; ++p) {
+          int4 w;
+          memcpy(&w, dig[p], 16);
+          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride + ((size_t)chunk * oz.rows_alloc + gr) * 16) = w;
+        }
+      }
+      continue;
+    }
     // compact, coalesced epilogue: one instance of the kernel function in the instruction stream; two row slices (4 kernel
     // values) per iteration so that four independent exp chains are in flight per thread
 #pragma unroll 1

@@ -90,6 +90,32 @@ def test_qlognehvi_with_constraint_and_pending():
     compare(acq_d, acq_o, Cf.candidates(p), st, log_space=True)
 
 
+def test_qlognehvi_gradient_both_adjoint_kernels():
+    """Few q-batches (< 148: refinement) run the sample-split / cell-lane adjoint (mc_loghvi_grad_cl_kernel + finishing kernel),
+    many q-batches the one-CTA-per-q-batch kernel: both against oracle autograd, and against each other on shared q-batches
+    (the lanes' running sums are merged in a different order: agreement to rounding, not bit for bit)."""
+    p = Cf.zdt1_qnehvi(N=80, S=32, raw=160, d=5, q=2)
+    p["outputs"].append(dict(kernel=K.RBFKernel(list(range(5)), [0.7] * 5), y=p["X"][:, 2] + 0.1 * p["X"][:, 3], noise=1e-3,
+                             mean_const=0.1))
+    cons = [OutputConstraint(2, 1.0, 0.6, 0.25)]
+    gp = P.oracle_gp(p)
+    st = Cf.build_state(p)
+    ops = [P.op_to_oracle(o) for o in p["objective"].ops]
+    acq_o = O.QLogNEHVIOracle(gp, p["ref_point"], p["X"], ops, constraints=[(2, 1.0, 0.6, 0.25)], mc_samples=p["S"],
+                              seed=p["sampler_seed"], prune_baseline=True, prune_samples=128, prune_seed=p["sampler_seed"] + 7919)
+    acq_d = A.qLogNoisyExpectedHypervolumeImprovement(st, p["ref_point"], p["X"], p["objective"], constraints=cons,
+                                                      prune_baseline=True, mc_samples=p["S"], seed=p["sampler_seed"],
+                                                      prune_samples=128)
+    X = Cf.candidates(p)
+    assert X.shape[0] == 160
+    compare(acq_d, acq_o, X, st, log_space=True)                    # 160 q-batches: one CTA per q-batch
+    compare(acq_d, acq_o, X[:7], st, log_space=True)                # 7 q-batches: samples split, cells over lanes
+    v_all, g_all = acq_d.forward_backward(X.to(st.device))
+    v_few, g_few = acq_d.forward_backward(X[:7].to(st.device))
+    assert float((v_few - v_all[:7]).abs().max()) <= 1e-11 * max(1.0, float(v_all.abs().max()))
+    assert float((g_few - g_all[:7]).abs().max()) <= 1e-9 * float(g_all.abs().max())
+
+
 def test_qlogehvi_value_and_gradient():
     p = Cf.zdt1_qnehvi(N=80, S=32, raw=8, d=5, q=2)
     gp = P.oracle_gp(p)
