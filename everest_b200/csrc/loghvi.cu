@@ -102,6 +102,58 @@ __device__ __forceinline__ double axis_from_fatmin(double v, double lo, double u
   return w - lo;
 }
 
+// ---- value kernel only: table-driven logarithm and reciprocal temperatures ---------------------------------------------------
+// The value kernel spends its time in FP64 `log` and divisions (two of each per (cell, subset, objective) after the fatmin
+// cache).  Every logarithm here has a positive, finite, normal argument and enters a sum of O(1) terms, so 2e-16 ABSOLUTE
+// accuracy is what matters: x = 2^e m, m in [1, 2); the top 6 mantissa bits pick c_i = 1 + (i + 1/2) / 64; r = m / c_i - 1
+// (|r| < 2^-7, one FMA with the tabulated reciprocal); log x = e ln 2 + log c_i + log1p(r), log1p(r) by its series to r^8
+// (|r|^9 / 9 < 2^-66).  log c_i is tabulated for the ROUNDED reciprocal, so the identity is exact up to the final roundings.
+// The adjoint kernels keep the library functions; their values agree with this kernel's to ~1e-15.
+#define LH_LOGTAB 64
+__device__ __forceinline__ void lh_logtab_fill(double2* tab) {   // call with all threads of the CTA, then __syncthreads()
+  for (int i = threadIdx.x; i < LH_LOGTAB; i += blockDim.x) {
+    const double invc = 1.0 / (1.0 + ((double)i + 0.5) / (double)LH_LOGTAB);
+    tab[i] = make_double2(invc, -log(invc));
+  }
+}
+__device__ __forceinline__ double lh_log(double x, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = tab[(hi >> 14) & (LH_LOGTAB - 1)];
+  const double r = fma(m, t.x, -1.0);
+  double p = fma(r, -0.125, 1.0 / 7.0);
+  p = fma(p, r, -1.0 / 6.0);
+  p = fma(p, r, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  p = fma(p * r, r, r);                       // r - r^2/2 + ... - r^8/8
+  return fma((double)e, 0.6931471805599453, t.y) + p;
+}
+// axis_from_fatmin / log_fatplus_lt with the table logarithm and reciprocal temperatures (same branches, same formulas)
+__device__ __forceinline__ double axis_from_fatmin_fast(double v, double lo, double up, double tau_max, double inv_tau_max,
+                                                        const double2* __restrict__ tab) {
+  double w;
+  if (isinf(up)) {
+    w = v;
+  } else {
+    const double y = fabs(up - v) * inv_tau_max, P = pareto2_d(y);
+    w = fmin(v, up) - tau_max * lh_log(1.0 + P, tab);
+  }
+  return w - lo;
+}
+__device__ __forceinline__ double log_fatplus_fast(double x, double tau, double inv_tau, double log_tau, const double2* __restrict__ tab) {
+  const double z = x * inv_tau;
+  if (z > 32.0) {
+    const double r = 0.1 / (z * (1.0 + z * z));
+    return log_tau + lh_log(z, tab) + ((r < 1e-9) ? r : log1p(r));
+  }
+  const double B = -2.302585092994046 - ((z * z < 1e300) ? lh_log(1.0 + z * z, tab) : log1p(z * z));
+  if (z < -750.0) return log_tau + B;
+  return log_tau + logaddexp_d(log_softplus_d(z), B);
+}
+
 // running log-sum-exp as a (max, sum) pair: value = m + log s
 __device__ __forceinline__ void lse_push(double& m, double& s, double v) {
   if (v > m) { s = s * exp(m - v) + 1.0; m = v; }   // exp(-inf) = 0 on the first push
@@ -200,11 +252,14 @@ mc_loghvi_kernel(McArgs a, int vcn) {
   const int batch = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int q = a.q, nr = a.nb + q, M = a.M, S = a.S, Mo = a.od.n_obj;
   LhSmem sm = lh_smem(lsm, M, q, nr, Mo, nt, S, false, vcn);
+  __shared__ double2 logtab[LH_LOGTAB];
+  lh_logtab_fill(logtab);
   for (int i = tid; i < M * q * nr; i += nt) sm.root[i] = a.root[(size_t)batch * M * q * nr + i];
   for (int i = tid; i < q * M; i += nt) sm.mu[i] = a.mu[(size_t)batch * q * M + i];
   __syncthreads();
   const unsigned full = (q >= 32) ? 0xffffffffu : ((1u << q) - 1u);
   const double log_tau_relu = log(a.tau_relu);
+  const double inv_tau_relu = 1.0 / a.tau_relu, inv_tau_max = 1.0 / a.tau_max;
   double lmax = -INFINITY;
   for (int s = tid; s < S; s += nt) {
     lh_load_sample(a, sm, batch, s, tid, nt);
@@ -229,8 +284,9 @@ mc_loghvi_kernel(McArgs a, int vcn) {
         if (sm.vc) {
           la = 0.0;
           for (int o = 0; o < Mo; ++o) {
-            const double len = axis_from_fatmin(sm.vc[((size_t)(sub - 1) * Mo + o) * nt + tid], lo[o], up[o], a.tau_max);
-            la += log_fatplus_lt(len, a.tau_relu, log_tau_relu);
+            const double len = axis_from_fatmin_fast(sm.vc[((size_t)(sub - 1) * Mo + o) * nt + tid], lo[o], up[o], a.tau_max,
+                                                     inv_tau_max, logtab);
+            la += log_fatplus_fast(len, a.tau_relu, inv_tau_relu, log_tau_relu, logtab);
           }
           if (a.od.n_cons)
             for (unsigned rest = sub; rest; rest &= rest - 1) la += sm.lfw[(size_t)(__ffs(rest) - 1) * nt + tid];
@@ -273,7 +329,8 @@ int launch_mc_loghvi(const McArgs& a, cudaStream_t st, LaunchCounter* lc) {
   if (vcn && nt < 128) { vcn = 0; nt = lh_pick_threads(a, false, &smem, 0); }
   if (!nt) { bo_set_error("mc_loghvi: shared memory budget exceeded (n_b=%d q=%d)", a.nb, a.q); return BO_ERR_INVALID; }
   static PerDeviceMax attr_pd; size_t& attr = attr_pd.slot();
-  if (smem > 48 * 1024 && smem > attr) {
+  // (the kernel also holds 1 KB of static shared memory, the logarithm table: static + dynamic above 48 KB needs the opt-in)
+  if (smem + 2048 > 48 * 1024 && smem > attr) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(mc_loghvi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
