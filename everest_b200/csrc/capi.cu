@@ -11,6 +11,9 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <atomic>
+#include <memory>
+#include <functional>
 #include <vector>
 
 #include "acqf.cuh"
@@ -206,6 +209,11 @@ struct bo_state {
   DevBuf stage_in, stage_out;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
+  // host entry point, piece-wise input (forward_host_impl -> acqf_run): X of the next forward call arrives in row pieces;
+  // piece_wait(i) blocks until piece i's copy has been enqueued and makes the call's stream wait for it.  Only the point
+  // preparation and K(X*,X) of output 0 are launched piece by piece; everything after them sees the whole batch.
+  std::vector<int> piece_row_end;                       // cumulative candidate rows per piece (empty: X is complete)
+  std::function<int(int)> piece_wait;
   // timing
   bool timing = false;
   std::vector<TimingRec> recs;
@@ -1066,12 +1074,65 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
       return BO_OK;
     };
     cudaStream_t const s_main = s;
+    // Piece-wise input (host entry point, forward_host_impl): usable when this call is ONE chunk over all rows and every
+    // output takes the fused single-leaf cross-covariance path into the digit planes.  Pieces outermost, outputs inside: the
+    // K(X*,X) work of ALL outputs (1.5 ms on config 3) is what the 15.7 MB of host rows (1.3 ms over PCIe on this pool)
+    // hide behind; everything after this stage sees the whole batch.  Otherwise all pieces are awaited first.
+    bool pieces_done = false;
+    if (!st->piece_row_end.empty()) {
+      bool ok = use_ozaki && !dX_dev && b0 == 0 && bc == b && st->piece_row_end.back() == rows;
+      for (int m = 0; m < M && ok; ++m) {
+        const ModelD& md = st->out[m].md;
+        ok = md.n_terms == 1 && md.nfac[0] == 1 && md.leaf[md.fac[0][0]].kind <= BO_LEAF_MATERN52 && md.leaf[md.fac[0][0]].dpad <= 32;
+      }
+      if (ok) {
+        for (int m = 0; m < M; ++m) {
+          OutputH& o = st->out[m];
+          RC(o.q_prep.ensure(o.md, rows, &o.q_prepd));
+          double kmax = 0.0;
+          for (int t = 0; t < o.md.n_terms; ++t) kmax += fabs(o.md.coef[t]);   // every leaf is <= 1
+          oz_scaleA[m] = ldexp(1.0, (int)ceil(log2(std::max(kmax, 1e-300) / 0.49)));
+        }
+        rec_begin(st, "crosscov", s);
+        for (int i = 0, r0 = 0; i < (int)st->piece_row_end.size(); ++i) {
+          const int r1 = st->piece_row_end[i];
+          const bool last = i + 1 == (int)st->piece_row_end.size();
+          RC(st->piece_wait(i));
+          for (int m = 0; m < M; ++m) {
+            OutputH& o = st->out[m];
+            const int l = o.md.fac[0][0];
+            const int dpad = o.md.leaf[l].dpad;
+            PrepD view = o.q_prepd;                            // rows [r0, r1) of the prepared candidate points
+            view.n = r1 - r0;
+            view.Xs[l] = o.q_prepd.Xs[l] + (size_t)r0 * dpad;
+            view.n2[l] = o.q_prepd.n2[l] + r0;
+            RC(launch_prep_points(o.md, Xc + (size_t)r0 * st->d, r1 - r0, st->d, view, s, &st->lc));
+            OzPlanesOut po;
+            po.planes = st->wsOzA.as<signed char>() + (size_t)m * oz_pa; po.plane_stride = (long long)(ldk / 16) * oz_rows_alloc * 16;
+            po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = 0;
+            po.row_offset = r0; po.rows_cover = last ? oz_rows_alloc - r0 : r1 - r0;
+            bool fz = false;
+            double* Kxm = st->wsKx.as<double>() + (size_t)m * rows_max * ldk;
+            RC(launch_crosscov_ex(o.md, view, o.train_prepd, true, st->N, Kxm + (size_t)r0 * ldk, ldk, false, &po, &fz, s, &st->lc));
+            if (!fz) { bo_set_error("piece-wise K(X*,X): fused path expected"); return BO_ERR_STATE; }
+          }
+          r0 = r1;
+        }
+        rec_end(st, s);
+        pieces_done = true;
+      } else {
+        for (int i = 0; i < (int)st->piece_row_end.size(); ++i) RC(st->piece_wait(i));
+      }
+    }
     if (par) RC(fork2());
     for (int m = 0; m < M; ++m) {
       cudaStream_t s = (par && (m & 1)) ? st->side2 : s_main;      // shadows the call's stream inside this loop body
       OutputH& o = st->out[m];
       double* Kx = st->wsKx.as<double>() + (size_t)m * rows_max * ldk;
       RC(o.q_prep.ensure(o.md, rows, &o.q_prepd));
+      if (pieces_done) {
+        oz_fused[m] = 1;     // prepared and sliced piece by piece above
+      } else {
       rec_begin(st, "prep", s);
       RC(launch_prep_points(o.md, Xc, rows, st->d, o.q_prepd, s, &st->lc));
       rec_end(st, s);
@@ -1084,6 +1145,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         OzPlanesOut po;
         po.planes = st->wsOzA.as<signed char>() + (size_t)m * oz_pa; po.plane_stride = (long long)(ldk / 16) * oz_rows_alloc * 16;
         po.rows_alloc = oz_rows_alloc; po.n_chunks = ldk / 16; po.inv_scale = 1.0 / oz_scaleA[m]; po.write_fp64 = dX_dev ? 1 : 0;
+        po.row_offset = 0; po.rows_cover = 0;
         bool fz = false;
         RC(launch_crosscov_ex(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, &po, &fz, s, &st->lc));
         oz_fused[m] = fz ? 1 : 0;
@@ -1091,6 +1153,7 @@ static int acqf_run(bo_state* st, const double* X_dev, int32_t b, int32_t q, con
         RC(launch_crosscov(o.md, o.q_prepd, o.train_prepd, true, st->N, Kx, ldk, false, s, &st->lc));
       }
       rec_end(st, s);
+      }
       PostGemmArgs& a = pg[m];
       a.Kx = Kx; a.rows = rows; a.ldk = ldk; a.B = o.LinvExt.as<double>(); a.N = st->N; a.n_ext = nb + 1; a.Rpad = o.Rpad;
       a.q = q; a.Gqq = st->wsGqq.as<double>() + (size_t)m * rows_max * q; a.W = st->wsW.as<double>() + (size_t)m * rows_max * ldw;
@@ -1777,7 +1840,28 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
       }
     }
   }
-  const int n_chunks = (int)chunk_b.size();
+  // Piece mode (float64 rows, every output a single continuous leaf, input above 8 MiB: configs 3 and 4): the kernels run ONCE
+  // over the whole batch -- no small, inefficient first chunk -- and only the point preparation and K(X*,X) of the first
+  // output are launched piece by piece as the copies land (acqf_run, `piecewise`).  Measured on config 3: the two-chunk plan
+  // cost 1.65 + 7.88 ms against 8.73 ms for one launch sequence.  EVEREST_HOST_PIECES=0 restores the chunk plan.
+  static const bool pieces_env = []() { const char* e = getenv("EVEREST_HOST_PIECES"); return !e || atoi(e) != 0; }();
+  bool piece_mode = pieces_env && mode == HOST_DENSE && chunk_b.size() > 1 && st->ozaki == 1 && st->oz_calib >= 0;
+  for (int m = 0; m < st->M && piece_mode; ++m) {
+    const ModelD& md = st->out[m].md;
+    piece_mode = md.n_terms == 1 && md.nfac[0] == 1 && md.leaf[md.fac[0][0]].kind <= BO_LEAF_MATERN52 && md.leaf[md.fac[0][0]].dpad <= 32;
+  }
+  std::vector<size_t> piece_rows;
+  if (piece_mode) {
+    // a first piece of ~1 MiB (the kernels start as soon as it has landed), then ~2 MiB pieces (the K(X*,X) work on the last
+    // piece is what stays exposed); whole 128-row blocks, at most 16 pieces
+    static const int piece_mib = []() { const char* e = getenv("EVEREST_HOST_PIECE_MIB"); int v = e ? atoi(e) : 5; return v >= 1 ? v : 5; }();
+    size_t per = std::max<size_t>(128, (((size_t)piece_mib << 20) / row_wire) / 128 * 128);
+    if ((n_rows + per - 1) / per > 15) per = ((n_rows + 14) / 15 + 127) / 128 * 128;
+    const size_t first = std::min(n_rows, std::max<size_t>(128, (((size_t)1 << 20) / row_wire) / 128 * 128));
+    piece_rows.push_back(first);
+    for (size_t r = first; r < n_rows; r += per) piece_rows.push_back(std::min(per, n_rows - r));
+  }
+  const int n_chunks = piece_mode ? (int)piece_rows.size() : (int)chunk_b.size();
   while ((int)st->copy_events.size() < n_chunks) {
     cudaEvent_t e;
     CUDA_CHECK_RET(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1797,10 +1881,15 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
   // keeps the copy engine busy meanwhile.
   std::vector<size_t> c_row0(n_chunks), c_rows(n_chunks);
   std::vector<int> c_b0(n_chunks);
-  for (int c = 0, b0 = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
-    c_b0[c] = b0;
-    c_row0[c] = (size_t)b0 * q;
-    c_rows[c] = (size_t)chunk_b[c] * q;
+  if (piece_mode) {
+    size_t r = 0;
+    for (int c = 0; c < n_chunks; r += piece_rows[c], ++c) { c_b0[c] = 0; c_row0[c] = r; c_rows[c] = piece_rows[c]; }
+  } else {
+    for (int c = 0, b0 = 0; c < n_chunks; b0 += chunk_b[c], ++c) {
+      c_b0[c] = b0;
+      c_row0[c] = (size_t)b0 * q;
+      c_rows[c] = (size_t)chunk_b[c] * q;
+    }
   }
   int dev_id = 0;
   cudaGetDevice(&dev_id);
@@ -1812,7 +1901,7 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
   auto stage_chunk = [&](int c) -> cudaError_t {
     const size_t r0 = c_row0[c], nr = c_rows[c];
     const size_t host_bytes = nr * (mode == HOST_PREPACKED ? row_wire : (size_t)st->d * 8);
-    const size_t piece = (size_t)4 << 20;
+    const size_t piece = piece_mode ? (size_t)1 << 20 : (size_t)4 << 20;
     const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(mode == HOST_PACK ? 8 : 4, (host_bytes + piece - 1) / piece));
     const size_t per = (nr + n_thr - 1) / n_thr;
     std::vector<std::thread> th;
@@ -1845,11 +1934,53 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
     if (e == cudaSuccess) e = cudaEventRecord(st->copy_events[c], st->copy_stream);
     return e;
   };
+  // Piece mode: a team of staging threads spawned once per call; thread t copies slice t of EVERY piece (pageable -> pinned)
+  // and moves on; whoever completes a piece last enqueues its H2D + event and publishes it.  (Spawning helpers per piece cost
+  // 0.4 ms per 4 MiB piece: the copies then arrived more slowly than K(X*,X) consumed them.)
+  std::vector<std::thread> team;
+  std::vector<char> piece_ready(n_chunks, 0);
+  std::unique_ptr<std::atomic<int>[]> piece_cnt;
+  if (piece_mode) {
+    const int T = 6;
+    piece_cnt.reset(new std::atomic<int>[n_chunks]);
+    for (int c = 0; c < n_chunks; ++c) piece_cnt[c].store(0);
+    for (int t = 0; t < T; ++t)
+      team.emplace_back([&, t]() {
+        cudaSetDevice(dev_id);
+        for (int c = 1; c < n_chunks; ++c) {                 // (piece 0 is staged by the calling thread, below)
+          const size_t r0 = c_row0[c], nr = c_rows[c];
+          const size_t a = r0 + nr * (size_t)t / T, e = r0 + nr * (size_t)(t + 1) / T;
+          if (e > a) memcpy(pin + a * row_wire, reinterpret_cast<const char*>(X_host) + a * row_wire, (e - a) * row_wire);
+          if (piece_cnt[c].fetch_add(1) + 1 == T) {
+            cudaError_t er = cudaMemcpyAsync(reinterpret_cast<char*>(st->stage_in.p) + r0 * row_wire, pin + r0 * row_wire,
+                                             nr * row_wire, cudaMemcpyHostToDevice, st->copy_stream);
+            if (er == cudaSuccess) er = cudaEventRecord(st->copy_events[c], st->copy_stream);
+            {
+              std::lock_guard<std::mutex> lk(mtx);
+              if (er != cudaSuccess && stage_err == cudaSuccess) stage_err = er;
+              piece_ready[c] = 1;
+            }
+            cv.notify_all();
+          }
+        }
+      });
+  }
   // the first chunk is staged here (nothing to overlap with yet), the others by the staging thread
-  stage_err = stage_chunk(0);
-  published = 1;
+  if (!piece_mode) {
+    stage_err = stage_chunk(0);
+    published = 1;
+  } else {
+    // the small first piece: copied and sent by this thread while the team starts on the others
+    const size_t nr = c_rows[0];
+    memcpy(pin, X_host, nr * row_wire);
+    cudaError_t er = cudaMemcpyAsync(st->stage_in.p, pin, nr * row_wire, cudaMemcpyHostToDevice, st->copy_stream);
+    if (er == cudaSuccess) er = cudaEventRecord(st->copy_events[0], st->copy_stream);
+    std::lock_guard<std::mutex> lk(mtx);
+    if (er != cudaSuccess && stage_err == cudaSuccess) stage_err = er;
+    piece_ready[0] = 1;
+  }
   std::thread stager;
-  if (n_chunks > 1 && stage_err == cudaSuccess) {
+  if (!piece_mode && n_chunks > 1 && stage_err == cudaSuccess) {
     stager = std::thread([&]() {
       cudaSetDevice(dev_id);
       for (int c = 1; c < n_chunks; ++c) {
@@ -1868,7 +1999,25 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
   static const bool trace = getenv("EVEREST_HOST_TRACE") != nullptr;
   auto t_start = std::chrono::steady_clock::now();
   auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
-  for (int c = 0; c < n_chunks && rc_fwd == BO_OK; ++c) {
+  if (piece_mode) {
+    st->piece_row_end.clear();
+    for (int c = 0; c < n_chunks; ++c) st->piece_row_end.push_back((int)(c_row0[c] + c_rows[c]));
+    st->piece_wait = [&](int c) -> int {
+      {
+        std::unique_lock<std::mutex> lk(mtx);
+        cv.wait(lk, [&]() { return piece_ready[c] || stage_err != cudaSuccess; });
+        if (stage_err != cudaSuccess) { bo_set_error("forward_host: staging failed: %s", cudaGetErrorString(stage_err)); return BO_ERR_CUDA; }
+      }
+      if (trace) fprintf(stderr, "[host] piece %d published at %.3f ms\n", c, ms_since());
+      CUDA_CHECK_RET(cudaStreamWaitEvent(s, st->copy_events[c], 0));
+      return BO_OK;
+    };
+    rc_fwd = bo_acqf_forward(st, st->stage_in.as<double>(), b, q, zq_dev, st->stage_out.as<double>(), nullptr, s);
+    st->piece_row_end.clear();
+    st->piece_wait = nullptr;
+    if (trace) fprintf(stderr, "[host] piece-wise forward returned at %.3f ms\n", ms_since());
+  }
+  for (int c = 0; c < n_chunks && rc_fwd == BO_OK && !piece_mode; ++c) {
     {
       std::unique_lock<std::mutex> lk(mtx);
       cv.wait(lk, [&]() { return published > c || stage_err != cudaSuccess; });
@@ -1887,6 +2036,7 @@ static int forward_host_impl(bo_state* st, HostMode mode, const double* X_host, 
     if (trace) fprintf(stderr, "[host] chunk %d launched, forward returned at %.3f ms\n", c, ms_since());
   }
   if (stager.joinable()) stager.join();
+  for (auto& t : team) t.join();
   if (stage_err != cudaSuccess) { bo_set_error("forward_host: staging failed: %s", cudaGetErrorString(stage_err)); return BO_ERR_CUDA; }
   RC(rc_fwd);
   CUDA_CHECK_RET(cudaMemcpyAsync(st->pin_out, st->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, s));

@@ -570,12 +570,13 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
           for (int p = 0; p < OZ_PLANES; ++p) dig[p][t4 + u] = d[p];
         }
       }
-      if (gr < oz.rows_alloc && chunk < oz.n_chunks) {
+      if (gr < oz.rows_cover && chunk < oz.n_chunks) {
 #pragma unroll
         for (int p = 0; p < OZ_PLANES; ++p) {
           int4 w;
           memcpy(&w, dig[p], 16);
-          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride + ((size_t)chunk * oz.rows_alloc + gr) * 16) = w;
+          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride +
+                                   ((size_t)chunk * oz.rows_alloc + oz.row_offset + gr) * 16) = w;
         }
       }
       continue;
@@ -623,7 +624,7 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
       __syncthreads();
       const int r = tid & 63, c = tid >> 6;
       const int gr = row0 + r, chunk = (col0 >> 4) + c;
-      if (gr < oz.rows_alloc && chunk < oz.n_chunks) {
+      if (gr < oz.rows_cover && chunk < oz.n_chunks) {
         signed char dig[OZ_PLANES][16];
 #pragma unroll
         for (int t2 = 0; t2 < 16; ++t2) {
@@ -636,7 +637,8 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         for (int p = 0; p < OZ_PLANES; ++p) {
           int4 w;
           memcpy(&w, dig[p], 16);
-          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride + ((size_t)chunk * oz.rows_alloc + gr) * 16) = w;
+          *reinterpret_cast<int4*>(oz.planes + (size_t)p * oz.plane_stride +
+                                   ((size_t)chunk * oz.rows_alloc + oz.row_offset + gr) * 16) = w;
         }
       }
     }
@@ -682,7 +684,8 @@ int launch_crosscov_ex(const ModelD& md, PrepD rows, PrepD colsOrTrain, bool col
     dim3 gridf((n_ct + ctp - 1) / ctp, (rows.n + CC_TILE - 1) / CC_TILE);
     if (ozp && ozp->planes) {
       oz = *ozp;
-      gridf.y = (oz.rows_alloc + CC_TILE - 1) / CC_TILE;   // the padding rows of the planes are written (zeros) too
+      if (oz.rows_cover <= 0) oz.rows_cover = oz.rows_alloc - oz.row_offset;
+      gridf.y = (oz.rows_cover + CC_TILE - 1) / CC_TILE;   // the padding rows of the planes are written (zeros) too
       if (fused) *fused = true;
     }
     const double* Aq = rows.Xs[l];
