@@ -50,6 +50,14 @@ def test_config3_zdt1_30d_qnehvi_full_size():
     assert rel_to_max(v_d, v_o) < 1e-9
     mu_d = st.debug_get("mu", capacity=2048 * 4 * 2).view(2048, 4, 2).cpu()
     assert float(((mu_d - parts["mu"]).abs() / (parts["mu"].abs() + 1e-6)).max()) < 1e-9
+    # the whole 16384-q-batch screen from HOST rows (15.7 MB: the piece mode of bo_acqf_forward_host -- point preparation and
+    # K(X*,X) launched piece by piece as the copies land, everything else once over the batch) against the device-resident
+    # call: the same arithmetic per element, so the same bits
+    X_all = Cf.candidates(p)
+    v_host = torch.as_tensor(acq_d.forward_host(X_all.contiguous().numpy()))
+    v_dev = acq_d(X_all.to(st.device)).cpu()
+    assert torch.equal(v_host, v_dev)
+    assert rel_to_max(v_dev[:2048], v_d) < 1e-12
     # the same q-batches through the FP64 kernel
     acq_d.set_option("ozaki", 0)
     assert rel_to_max(acq_d(X.to(st.device)).cpu(), v_o) < 1e-9
