@@ -1,3 +1,4 @@
+"""Timeline of bo_acqf_forward_host on a config-3 screen (EVEREST_HOST_TRACE) next to the device-resident call and the two chunk sizes."""
 import sys, os, time, torch
 sys.path.insert(0, '.')
 os.environ["EVEREST_HOST_TRACE"] = "1"
