@@ -160,6 +160,8 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
   const int n_items = leaf_major ? md.n_leaves : n_fac_total;
   // role of every leaf in the leaf-major order, found once per CTA (it was re-derived by every thread for every leaf):
   // coefficient of the single-leaf terms that hold it, and whether the product term holds it
+  __shared__ double s_n2[2 * CC_TILE];      // squared norms of the tile's rows | columns (current continuous leaf)
+  __shared__ int s_pc[2 * CC_TILE];         // popcounts of the tile's rows | columns (current Tanimoto leaf)
   __shared__ double s_csingle[BO_MAX_LEAVES];
   __shared__ int s_role[BO_MAX_LEAVES];   // bit 0: has a single-leaf term, bit 1: factor of the product
   if (leaf_major && tid < md.n_leaves) {
@@ -211,6 +213,14 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         for (int k0 = 0; k0 < L.dpad; k0 += CC_KC) {
           const int kc = min(CC_KC, L.dpad - k0);
           __syncthreads();
+          // the norms of the tile's points: one coalesced load per CTA instead of 10 scattered global loads per thread behind
+          // the MMA loop (written behind the barrier above -- the previous leaf may still have been reading its own --
+          // and published by the barrier that ends the staging)
+          if (k0 == 0 && tid < 2 * CC_TILE) {
+            const int r = tid & (CC_TILE - 1);
+            s_n2[tid] = (tid < CC_TILE) ? ((row0 + r < n_rows) ? rows.n2[l][row0 + r] : 0.0)
+                                        : ((col0 + r < n_cols) ? cols.s[l].n2[col0 + r] : 0.0);
+          }
           // 16-byte pieces of the kc (a multiple of 4) columns the MMA loop reads; nothing beyond kc is touched
           const int kh = kc >> 1;
           for (int idx = tid; idx < CC_TILE * kh; idx += 256) {
@@ -234,22 +244,41 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
               for (int j = 0; j < 4; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
           }
         }
-        const double* n2a = rows.n2[l];
-        const double* n2b = cols.s[l].n2;
+        // squared distances first, then ONE switch over the kernel function around the 16 values: with the switch inside the
+        // value loop the executed path hopped over 16 scattered copies of the other four functions (ncu: 0.86 `no_instruction`
+        // stalls per issue in this 13 K-instruction kernel)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           int r = row0 + wr * 16 + i * 8 + g;
-          double na = (r < n_rows) ? n2a[r] : 0.0;
+          double na = s_n2[wr * 16 + i * 8 + g];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               int c = col0 + wc * 32 + j * 8 + 2 * t + e;
-              double nb = (c < n_cols) ? n2b[c] : 0.0;
+              double nb = s_n2[CC_TILE + wc * 32 + j * 8 + 2 * t + e];
               double stat = fmax(na + nb - 2.0 * acc[i][j][e], 0.0);
               if (same_set && r == c) stat = 0.0;
-              lv[(i * 4 + j) * 2 + e] = leaf_value_from_stat(L.kind, stat);
+              lv[(i * 4 + j) * 2 + e] = stat;
             }
+        }
+        switch (L.kind) {
+          case BO_LEAF_RBF:
+#pragma unroll
+            for (int e = 0; e < 16; ++e) lv[e] = leaf_value_from_stat(BO_LEAF_RBF, lv[e]);
+            break;
+          case BO_LEAF_MATERN12:
+#pragma unroll
+            for (int e = 0; e < 16; ++e) lv[e] = leaf_value_from_stat(BO_LEAF_MATERN12, lv[e]);
+            break;
+          case BO_LEAF_MATERN32:
+#pragma unroll
+            for (int e = 0; e < 16; ++e) lv[e] = leaf_value_from_stat(BO_LEAF_MATERN32, lv[e]);
+            break;
+          default:
+#pragma unroll
+            for (int e = 0; e < 16; ++e) lv[e] = leaf_value_from_stat(BO_LEAF_MATERN52, lv[e]);
+            break;
         }
       } else if (L.kind == BO_LEAF_HAMMING) {
         int* Ac = reinterpret_cast<int*>(smem);
@@ -367,6 +396,11 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
           cp_async_commit();
         };
         __syncthreads();               // the previous leaf is done with the static tiles; dsm is only used here
+        if (tid < 2 * CC_TILE) {       // popcounts of the tile's points (published by the first barrier of the chunk loop)
+          const int r = tid & (CC_TILE - 1);
+          s_pc[tid] = (tid < CC_TILE) ? ((row0 + r < n_rows) ? rows.pc[l][row0 + r] : 0)
+                                      : ((col0 + r < n_cols) ? cols.s[l].pc[col0 + r] : 0);
+        }
         issue_chunk(0, 0);
         int buf = 0;
         for (int k0 = 0; k0 < rb; k0 += TB_CH, buf ^= 1) {
@@ -396,14 +430,12 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          int r = row0 + wr * 16 + i * 8 + g;
-          int pa = (r < n_rows) ? rows.pc[l][r] : 0;
+          int pa = s_pc[wr * 16 + i * 8 + g];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              int c = col0 + wc * 32 + j * 8 + 2 * t + e;
-              int pb = (c < n_cols) ? cols.s[l].pc[c] : 0;
+              int pb = s_pc[CC_TILE + wc * 32 + j * 8 + 2 * t + e];
               lv[(i * 4 + j) * 2 + e] = tanimoto_value(dot[(i * 4 + j) * 2 + e], pa, pb);
             }
         }
