@@ -328,9 +328,12 @@ crosscov_kernel2(ModelD md, PrepD rows, ColSides cols, int n_cols, double* __res
               const int cb = Bpk[wc * 32 + j * 8 + 2 * t + e];
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                const int x = ra[i] ^ cb;
-                int mask = 0;
-                for (int f = 0; f < L.nd; ++f) mask |= ((x >> (4 * f)) & 15) ? (1 << f) : 0;
+                // bit f of the mismatch pattern = (nibble f of the XOR is not zero), without a loop over the groups: fold each
+                // nibble onto its lowest bit, gather the bits of two neighbouring nibbles per byte, then the three bytes
+                const unsigned x = (unsigned)(ra[i] ^ cb);
+                const unsigned y = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x111111u;
+                const unsigned y2 = (y | (y >> 3)) & 0x030303u;
+                const int mask = (int)((y2 | (y2 >> 6) | (y2 >> 12)) & 0x3fu);
                 lv[(i * 4 + j) * 2 + e] = Ht[mask];
               }
             }
