@@ -643,3 +643,44 @@ def test_specs_from_botorch_model_literal_mixed_single_task_gp_with_stand_ins():
         specs_from_botorch_model(Sub())
     Xf, (s2,) = specs_from_botorch_model(Sub(), X_train=X_bofire)
     assert list(s2.kernel.active_dims) == [0, 1] and s2.in_scale.tolist()[:2] == [4.0, 2.0] and Xf.shape == (N, 7)
+
+
+def test_bench_clock_sampler_brackets_the_timed_region():
+    """bench.py's nvidia-smi poller: samples inside [mark_begin, mark_end] are reported (median clock, throttle reasons); a
+    region that slipped between two polls falls back to the nearest samples and says so."""
+    import datetime
+    import importlib.util
+    import tempfile
+    import time
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+
+    def sampler(t_begin, t_end, now):
+        cs = bench.ClockSampler(0)
+        fd, path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        with open(path, "w") as f:
+            for k in range(10):
+                ts = datetime.datetime.fromtimestamp(now + k * 0.05).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+                cap = "Active" if k == 3 else "Not Active"
+                f.write(f"{ts}, 0, {1900 + k}, 1965, {300 + k}.5, 0x0000000000000004, Not Active, Not Active, Not Active, {cap}\n")
+        cs.proc, cs.path, cs.t_begin, cs.t_end = Done(), path, t_begin, t_end
+        return cs.stop()
+
+    now = time.time()
+    out = sampler(now + 0.12, now + 0.22, now)           # polls 3 and 4 fall inside
+    assert out["samples"] == 2 and out["sm_mhz"] == 1903.5 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and "nearest_samples_only" not in out
+    out = sampler(now + 0.221, now + 0.224, now)         # a 3 ms region between two polls
+    assert out["samples"] == 2 and out["nearest_samples_only"] is True and out["sm_mhz"] in (1904.0, 1904.5, 1903.5)
+    empty = bench.ClockSampler(0).stop()                 # poller never started
+    assert empty["samples"] == 0 and empty["sm_mhz"] is None
