@@ -508,8 +508,9 @@ template <int ROWS>
 __device__ __forceinline__ void cc3_load_tile(double* dst, const double* __restrict__ src, int dpad, int row0, int n_valid,
                                               int tid) {
   const int chunks = dpad >> 1;  // 16-byte chunks per row
+  const int sh = ((chunks & (chunks - 1)) == 0) ? __ffs(chunks) - 1 : -1;   // power of two (dpad = 4, 8, 16, 32): no division
   for (int c = tid; c < ROWS * chunks; c += 256) {
-    int r = c / chunks, ch = c - r * chunks;
+    int r = (sh >= 0) ? (c >> sh) : (c / chunks), ch = c - r * chunks;
     bool p = (row0 + r) < n_valid;
     cp_async16(dst + r * CC_LDS + ch * 2, src + (size_t)(p ? row0 + r : 0) * dpad + ch * 2, p);
   }
@@ -586,6 +587,8 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
       const double naR = n2a_s[r];
       const bool okR = gr < n_rows;
       signed char dig[OZ_PLANES][16];
+      // interior chunks (all 16 columns inside the matrix, no diagonal to pin): no per-value tests
+      const bool plain = okR && !same_set && col0 + c * 16 + 16 <= n_cols;
 #pragma unroll
       for (int t4 = 0; t4 < 16; t4 += 4) {
         double st[4], lv[4];
@@ -593,12 +596,12 @@ crosscov_fast_kernel(const double* __restrict__ Aq, const double* __restrict__ n
         for (int u = 0; u < 4; ++u) {
           const int cc = c * 16 + t4 + u;
           st[u] = fmax(naR + n2b_s[cc] - 2.0 * Cs[r * CC3_CLD + cc], 0.0);
-          if (same_set && gr == col0 + cc) st[u] = 0.0;
+          if (!plain && same_set && gr == col0 + cc) st[u] = 0.0;
         }
         leaf_value_from_stat_tab_n<4>(KIND, st, lv, exptab);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const double v = (okR && col0 + c * 16 + t4 + u < n_cols) ? coef * lv[u] : 0.0;
+          const double v = (plain || (okR && col0 + c * 16 + t4 + u < n_cols)) ? coef * lv[u] : 0.0;
           signed char d[OZ_PLANES];
           oz_split_digits(v * oz.inv_scale, d);
 #pragma unroll
