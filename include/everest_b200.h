@@ -246,7 +246,10 @@ int bo_acqf_optimize(bo_state* st, double* X_dev, int32_t r, int32_t q_tot, int3
 /* Same call with HOST buffers: pinned staging, H2D of X, the launches, D2H of the values.  Columns read only by Tanimoto
  * leaves (0/1 fingerprints: molfeatures.py:31-48 hands them to BoTorch as float64) cross PCIe as BITS: the staging threads
  * pack them while they copy (a config-5 candidate shrinks from 16.5 KB to 352 bytes on the wire) and a kernel restores the
- * float64 row on the device; a fingerprint column holding anything but 0 / 1 is refused (BO_ERR_INVALID). */
+ * float64 row on the device; a fingerprint column holding anything but 0 / 1 is refused (BO_ERR_INVALID).
+ * Large float64 inputs (> 8 MiB) of single-leaf models are copied in pieces by a team of staging threads while the point
+ * preparation and K(X*,X) kernels already run on the pieces that have landed; every later kernel runs once over the whole
+ * batch.  The values equal those of bo_acqf_forward on the same rows bit for bit.  X_host may be pageable memory. */
 int bo_acqf_forward_host(bo_state* st, const double* X_host, int32_t b, int32_t q, const double* zq_dev,
                          double* out_host, void* stream);
 
